@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- rollout cost+gradient throughput, (seed x waypoint) evals/s.
+
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl ours|reference]
+
+One "step" = one pass of the fused rollout kernel over one batch of synthetic joint configurations
+(= what one optimizer iteration's cost+gradient evaluation does, gradient_opt_core.py:445-480).
+Default workload = BASELINE.json configs[1]: Franka IK, 512 targets x 32 seeds (16,384 evals/step),
+primitive-cuboid world, H = 1.  N > 1: the seed batch is sharded (weak scaling: 16,384 evals per GPU),
+no data-path collective; one NCCL all_gather of per-seed costs after the timed region (not timed:
+it happens once per solve, not per iteration).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events per step on the
+launching stream, L2 flushed between steps, max over ranks); `e2e` = same metric through the public
+API with pinned-host inputs and host read-back inside the timed region; `roofline` = algorithmic bytes
+per eval x evals / kernel time vs the measured HBM peak; `cpu_baseline` = the
+numpy oracle (a port of the reference arithmetic; the reference has no CPU path) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "rollout_cost_grad_evals_per_sec"
+UNIT = "evals/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def make_workload(name: str, seed_offset: int = 0):
+    """Returns dict(robot, cfg, B, H, q [B,H,D] np, goal (pos, quat, idx) or None, cuboid world, voxel spec, bytes_per_eval)."""
+    from curobo_b200.robot_model import load_robot
+    from curobo_b200.rollout import RolloutConfig
+    from curobo_b200.world import make_benchmark_cuboid_world
+    from helpers import random_q
+    from oracle import rollout_oracle as O
+    if name == "franka_ik_512x32_cuboid":
+        rm = load_robot("franka")
+        B, H = 512 * 32, 1
+        q = random_q(rm, B, seed=100 + seed_offset)[:, None, :]
+        _, _, gp, gq = O.fk_forward(rm, random_q(rm, 512, seed=7))
+        goal = (gp[:, :, None, :].copy(), gq[:, :, None, :].copy(), (np.arange(B) // 32).astype(np.int32))
+        D, S, L = rm.num_dof, rm.num_spheres, rm.num_tool_frames
+        bpe = 4 * D + 4 * D + 4 * (S + 1 + 2 * L + D)                      # 356 B, cuboid world: no obstacle bytes
+        return dict(robot=rm, cfg=RolloutConfig.ik(), B=B, H=H, q=q, goal=goal, cuboid=make_benchmark_cuboid_world(),
+                    voxel=None, bytes_per_eval=bpe)
+    if name in ("g1_29_8192_esdf", "g1_43_8192_esdf", "franka_16384_esdf"):
+        rname = {"g1_29_8192_esdf": "g1_29", "g1_43_8192_esdf": "g1_43", "franka_16384_esdf": "franka"}[name]
+        rm = load_robot(rname)
+        B, H = (16384 if rname == "franka" else 8192), 1
+        q = random_q(rm, B, seed=200 + seed_offset, scale=0.6)[:, None, :]
+        D, S, L = rm.num_dof, rm.num_spheres, rm.num_tool_frames
+        bpe = 4 * D + 4 * D + 4 * (S + 1 + 2 * L + D) + 16 * S             # + 8 fp16 corners per sphere
+        cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                            cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0))
+        return dict(robot=rm, cfg=cfg, B=B, H=H, q=q, goal=None, cuboid=None, voxel=dict(n=256, voxel=0.01, boxes=12, seed=0),
+                    bytes_per_eval=bpe)
+    raise ValueError(f"unknown workload {name}")
+
+
+def build_engine(wl, device):
+    import torch
+    from curobo_b200.rollout import RolloutEngine
+    from curobo_b200.scene import CuboidData, VoxelData
+    from curobo_b200.world import make_box_esdf
+    cub = CuboidData.from_world(wl["cuboid"], device) if wl["cuboid"] is not None else None
+    vox = None
+    if wl["voxel"] is not None:
+        v = wl["voxel"]
+        sdf = make_box_esdf(n=v["n"], voxel_size=v["voxel"], num_boxes=v["boxes"], seed=v["seed"], xp=torch)
+        t = lambda a, dt: torch.as_tensor(np.asarray(a, dtype=dt)).to(device)  # noqa: E731
+        vox = VoxelData(t([[[v["n"], v["n"], v["n"], v["voxel"]]]], np.float32), t([[[0, 0, 0, 1, 0, 0, 0, 0]]], np.float32),
+                        torch.ones((1, 1), dtype=torch.uint8, device=device), torch.ones(1, dtype=torch.int32, device=device),
+                        sdf.reshape(1, 1, -1).contiguous().to(device), 1, 1, 100.0)
+    eng = RolloutEngine(wl["robot"], wl["cfg"], device, cub, vox)
+    if wl["goal"] is not None:
+        gp, gq, idx = wl["goal"]
+        eng.update_goal(torch.as_tensor(gp).to(device), torch.as_tensor(gq).to(device), torch.as_tensor(idx).to(device))
+    return eng
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.samples, self.proc, self.thread, self.idx = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload: str):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the numpy oracle on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def _oracle_eval(args):
+    wl_name, lo, hi = args
+    from oracle import rollout_oracle as O
+    wl = make_workload(wl_name)
+    vox = None
+    if wl["voxel"] is not None:
+        from curobo_b200.world import VoxelWorld, make_box_esdf
+        v = wl["voxel"]
+        n = 64                                               # same world, coarser grid: the CPU arm's cost is sphere math
+        sdf = make_box_esdf(n=n, voxel_size=v["voxel"] * v["n"] / n, num_boxes=v["boxes"], seed=v["seed"])
+        vox = VoxelWorld.from_grid(sdf.reshape(n, n, n), v["voxel"] * v["n"] / n)
+    q = wl["q"][lo:hi]
+    kw = {}
+    if wl["goal"] is not None:
+        gp, gq, idx = wl["goal"]
+        kw = dict(goal_pos=gp, goal_quat=gq, idxs_goal=idx[lo:hi])
+    t0 = time.perf_counter()
+    O.rollout_cost_grad(wl["robot"], q, wl["cfg"].to_oracle_cfg(wl["robot"].num_tool_frames), world_cuboid=wl["cuboid"],
+                        world_voxel=vox, **kw)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl_name: str, target_seconds: float = 12.0, procs: int = 1):
+    """evals/s of the oracle port.  procs == 1: single numpy process; procs > 1: one process per host core,
+    each evaluating its own slice of the sample."""
+    wl = make_workload(wl_name)
+    probe = 64
+    t = _oracle_eval((wl_name, 0, probe))
+    t = _oracle_eval((wl_name, 0, probe))                    # warm caches / imports
+    per_eval = t / probe
+    n = int(max(probe, min(wl["B"], target_seconds / per_eval)))
+    if procs <= 1:
+        dt = _oracle_eval((wl_name, 0, n))
+        return n / dt, 1, f"{n} of {wl['B'] * wl['H']} evals of {wl_name}, numpy oracle, 1 process"
+    import multiprocessing as mp
+    n = int(min(wl["B"], n * procs)) // procs * procs
+    chunk = n // procs
+    with mp.get_context("fork").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        pool.map(_oracle_eval, [(wl_name, i * chunk, (i + 1) * chunk) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    return n / dt, procs, f"{n} of {wl['B'] * wl['H']} evals of {wl_name}, numpy oracle, {procs} processes"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    """--impl reference: the reference has no CPU implementation of this path (DeviceCfg defaults to cuda,
+    kernels are CUDA/Warp only), so the CPU arm is the oracle port on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    per_step = max(3.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, c, sample = cpu_baseline(args.workload, target_seconds=per_step / 2, procs=cores)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    wl = make_workload(args.workload)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "robot": wl["robot"].name, "batch": wl["B"], "horizon": wl["H"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="franka_ik_512x32_cuboid")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra-workloads", default="g1_29_8192_esdf,franka_16384_esdf",
+                    help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA GPU: the rollout path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def timed_run(wl_name, steps, warmup, sample_clocks):
+        wl = make_workload(wl_name, seed_offset=rank)
+        eng = build_engine(wl, device)
+        q = torch.as_tensor(wl["q"]).to(device)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)       # 2x the 126 MB L2
+        stream = torch.cuda.current_stream(device)
+        for _ in range(warmup):
+            eng.evaluate_action(q)
+        torch.cuda.synchronize(device)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        if sampler:
+            sampler.start()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)                           # evict L2 between timed steps (outside the event pair)
+            starts[i].record(stream)
+            eng.evaluate_action(q)
+            ends[i].record(stream)
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        return wl, eng, q, float(sum(ms)), ms, clocks
+
+    wl, eng, q, total_ms, ms_list, clocks = timed_run(args.workload, args.steps, args.warmup, rank == 0)
+    evals_per_step = wl["B"] * wl["H"]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * evals_per_step * args.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e: pinned host inputs -> H2D -> kernel -> D2H of cost + grad, all inside the timed region
+    q_host = torch.as_tensor(wl["q"]).pin_memory()
+    q_dev = torch.empty_like(q)
+    cost_host = torch.empty((wl["B"], wl["H"]), dtype=torch.float32).pin_memory()
+    grad_host = torch.empty((wl["B"], wl["H"], wl["robot"].num_dof), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        q_dev.copy_(q_host, non_blocking=True)
+        o = eng.evaluate_action(q_dev)
+        cost_host.copy_(o.cost, non_blocking=True)
+        grad_host.copy_(o.grad_q, non_blocking=True)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        q_dev.copy_(q_host, non_blocking=True)
+        o = eng.evaluate_action(q_dev)
+        cost_host.copy_(o.cost, non_blocking=True)
+        grad_host.copy_(o.grad_q, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(device)
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * evals_per_step * args.steps / (float(te.item()) * 1e-3)
+    h2d = int(q_host.numel() * 4)
+    d2h = int(cost_host.numel() * 4 + grad_host.numel() * 4)
+
+    # ---- the one real exchange of the sharded path: per-seed cost all_gather (once per solve; untimed)
+    if world > 1:
+        from curobo_b200.sharded import gather_seed_costs_and_best
+        gather_seed_costs_and_best(eng.out.cost.sum(dim=1), q.view(wl["B"], -1), wl["B"] * world)
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        kernel_ms = float(np.mean(ms_list))
+        achieved = wl["bytes_per_eval"] * evals_per_step / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "robot": wl["robot"].name, "batch_per_gpu": wl["B"], "horizon": wl["H"],
+                       "evals_per_step_per_gpu": evals_per_step, "sharding": f"seeds x{world} (no data-path collective)",
+                       "cache": "L2 flushed (256 MiB write) between timed steps", "timer": "cuda events per step, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "rollout_fused_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                         "bytes_per_eval": wl["bytes_per_eval"], "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "note": "path is FP32-issue/latency bound by construction (working set is L2-resident); see DESIGN.md"},
+        }
+        if world == 1:
+            others = {}
+            for name in [w for w in args.extra_workloads.split(",") if w]:
+                try:
+                    w2, _, _, tot2, ms2, _ = timed_run(name, max(5, args.steps // 5), 3, False)
+                    k_ms = float(np.mean(ms2))
+                    ach = w2["bytes_per_eval"] * w2["B"] * w2["H"] / (k_ms * 1e-3) / 1e9
+                    others[name] = {"value": w2["B"] * w2["H"] / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms,
+                                    "bytes_per_eval": w2["bytes_per_eval"], "hbm_frac": ach / peak}
+                except Exception as ex:                                           # noqa: BLE001
+                    others[name] = {"error": repr(ex)}
+            line["other_workloads"] = others
+            if not args.no_cpu_baseline:
+                v, cores, sample = cpu_baseline(args.workload, target_seconds=12.0, procs=1)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,24 @@
+"""Pre-launch tensor validation, same contract and error behaviour as
+curobo/_src/curobolib/cuda_ops/tensor_checks.py:20-83 (raise ValueError; never call .contiguous())."""
+from __future__ import annotations
+
+import torch
+
+
+def check_tensors(device: torch.device, dtype: torch.dtype, **tensors: torch.Tensor) -> None:
+    for name, t in tensors.items():
+        if t is None:
+            raise ValueError(f"{name}: expected a tensor, got None")
+        if t.device != device:
+            raise ValueError(f"{name}: expected device {device}, got {t.device}")
+        if device.type != "cuda":
+            raise ValueError(f"{name}: curobo_b200 kernels are CUDA-only (sm_100a); got device {t.device}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous tensor, got strides={t.stride()} for shape={tuple(t.shape)}")
+        if t.dtype != dtype:
+            raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+def stream_ptr(device: torch.device) -> int:
+    """The CURRENT torch stream of `device` (never the default stream; graph-capture safe)."""
+    return torch.cuda.current_stream(device).cuda_stream

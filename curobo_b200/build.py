@@ -1,0 +1,100 @@
+"""Build the native libraries in-tree (nvcc cross-compiles sm_100a without a GPU).
+
+  curobo_b200/lib/libcurobo_b200.so   -- the product: sm_100a kernels + C ABI (include/curobo_b200.h)
+  tests/hostmath/libcb200_hostmath.so -- TEST-ONLY host build of the scalar math (CPU unit tests)
+  oracle/_ref/libcurobo_ref.so        -- TEST-ONLY: the reference's own CUDA kernels, compiled from
+                                         /root/reference where they lie (only when that tree exists)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "curobo_b200", "csrc")
+LIBDIR = os.path.join(ROOT, "curobo_b200", "lib")
+PRODUCT_SO = os.path.join(LIBDIR, "libcurobo_b200.so")
+HOSTMATH_SO = os.path.join(ROOT, "tests", "hostmath", "libcb200_hostmath.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libcurobo_ref.so")
+REFERENCE = os.environ.get("CUROBO_REFERENCE", "/root/reference")
+
+# same numeric flags as the reference's NVRTC/pybind builds
+# (curobo/_src/curobolib/backends/cuda_core_backend/kernel_config.py:52-59)
+NUMERIC = ["--ftz=true", "--fmad=true", "--prec-div=false", "--prec-sqrt=false"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _newer(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    if verbose and (r.stdout or r.stderr):
+        print(r.stdout + r.stderr)
+
+
+def build_product(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "curobo_b200.h")]
+    if not force and _newer(PRODUCT_SO, srcs):
+        return PRODUCT_SO
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared",
+           "-Xptxas", "-v" if verbose else "-O3",
+           os.path.join(CSRC, "cb200_kernels.cu"), "-o", PRODUCT_SO, "-lcudart"]
+    _run(cmd, verbose)
+    return PRODUCT_SO
+
+
+def build_hostmath(force: bool = False, verbose: bool = False) -> str:
+    src = os.path.join(ROOT, "tests", "hostmath", "cb200_hostmath.cu")
+    deps = [src, os.path.join(CSRC, "cb200_math.cuh")]
+    if not force and _newer(HOSTMATH_SO, deps):
+        return HOSTMATH_SO
+    cmd = [_nvcc(), "-std=c++17", "-O2", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared", src, "-o", HOSTMATH_SO,
+           "-lcudart"]
+    _run(cmd, verbose)
+    return HOSTMATH_SO
+
+
+def build_reference_kernels(force: bool = False, verbose: bool = False):
+    """oracle/_ref: the reference's CUDA kernels for FK fwd / FK bwd / self-collision, compiled from the
+    reference tree (headers are included by path; nothing is copied).  Returns None if the tree is absent."""
+    src = os.path.join(ROOT, "oracle", "ref_kernels_launcher.cu")
+    kdir = os.path.join(REFERENCE, "curobo", "_src", "curobolib", "kernels")
+    if not os.path.isdir(kdir) or not os.path.exists(src):
+        return REF_SO if os.path.exists(REF_SO) else None
+    if not force and _newer(REF_SO, [src]):
+        return REF_SO
+    os.makedirs(os.path.dirname(REF_SO), exist_ok=True)
+    cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared",
+           "-I", kdir, "-I", os.path.join(kdir, "common"), "-I", os.path.join(kdir, "third_party"),
+           "-I", os.path.join(kdir, "kinematics"), "-I", os.path.join(kdir, "geometry", "self_collision"),
+           src, "-o", REF_SO, "-lcudart"]
+    _run(cmd, verbose)
+    return REF_SO
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return build_product(force, verbose), build_hostmath(force, verbose), build_reference_kernels(force, verbose)
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,1188 @@
+// cb200_kernels.cu -- sm_100a kernels + the C ABI of include/curobo_b200.h.
+//
+// Kernels (all fp32 SIMT; there is no dense contraction on this path, so no tensor cores):
+//   rollout_fused_kernel        persistent, one warp per (seed x waypoint) eval, robot constants staged
+//                               to shared memory with one cp.async.bulk (TMA) per CTA; FK -> spheres ->
+//                               self/scene/pose/c-space cost -> J^T gradient in ONE launch.
+//   kin_forward_kernel          drop-in for kinematics_forward_spheres_kernel
+//   kin_backward_kernel         drop-in for kinematics_backward_kernel
+//   self_collision_kernel       drop-in for self_collision_max_* kernels (single launch)
+//   scene_collision_kernel      drop-in for the Warp sphere/swept obstacle kernels + speed metric
+//   tool_pose_kernel, cspace_state_kernel, cspace_position_kernel   drop-ins for the Warp cost kernels
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/curobo_b200.h"
+#include "cb200_blob.h"
+#include "cb200_math.cuh"
+#include "cb200_warp.cuh"
+
+using namespace cb200;
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+struct FusedArgs {
+  cb200_rollout_cfg cfg;
+  const float *q, *vel, *acc, *jerk, *dt;
+  const unsigned char *blob;
+  CuboidSet cuboids;
+  VoxelSet voxels;
+  const int32_t *env_query_idx;
+  const float *goal_position, *goal_quat;
+  const int32_t *idxs_goal;
+  const float *pose_axes_t, *pose_axes_nt, *pose_tol_t, *pose_tol_nt;
+  float *cost, *grad_q, *self_cost, *scene_cost, *pose_cost, *cspace_cost;
+  float *grad_vel, *grad_acc, *grad_jerk;
+  float *link_pos, *link_quat, *robot_spheres;
+  int32_t *pose_goalset_idx;
+  int32_t B, H;
+  int32_t blob_smem_bytes, eval_floats;
+};
+
+// c-space cost for one dof; returns cost, writes gradient wrt position into gp (and v/a/j grads to global)
+__device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView &rv, int e, int b, int d, float qd,
+                                            float &gp) {
+  const cb200_rollout_cfg &c = a.cfg;
+  const int D = rv.D;
+  const float *lim = rv.limits;
+  float cost = 0.0f;
+  gp = 0.0f;
+  if (c.cspace_type == 1) {
+    bound_cost(qd, lim[d], lim[D + d], c.cspace_activation[0], c.cspace_weight[0], cost, gp);
+  } else if (c.cspace_type == 2) {
+    const size_t idx = (size_t)e * D + d;
+    const float dt = a.dt ? __ldg(a.dt + b) : 1.0f;
+    float wb[5], wr[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      wb[i] = c.cspace_weight[i];
+      wr[i] = c.cspace_reg[i];
+    }
+    if (c.retime_weights) {
+      wb[1] = dt * wb[1];
+      wb[2] = powf(dt, 2.0f) * wb[2];
+      wb[3] = powf(dt, 3.0f) * wb[3];
+    }
+    if (c.retime_regularization_weights) {
+      wr[0] = dt * wr[0];
+      wr[1] = powf(dt, 2.0f) * wr[1];
+      wr[2] = powf(dt, 3.0f) * wr[2];
+      wr[4] = dt * wr[4];
+    }
+    const float v = a.vel ? __ldg(a.vel + idx) : 0.0f;
+    const float ac = a.acc ? __ldg(a.acc + idx) : 0.0f;
+    const float jk = a.jerk ? __ldg(a.jerk + idx) : 0.0f;
+    float gv = 0.0f, ga = 0.0f, gj = 0.0f;
+    bound_cost(qd, lim[d], lim[D + d], c.cspace_activation[0], wb[0], cost, gp);
+    bound_cost(v, lim[2 * D + d], lim[3 * D + d], c.cspace_activation[1], wb[1], cost, gv);
+    bound_cost(ac, lim[4 * D + d], lim[5 * D + d], c.cspace_activation[2], wb[2], cost, ga);
+    bound_cost(jk, lim[6 * D + d], lim[7 * D + d], c.cspace_activation[3], wb[3], cost, gj);
+    // effort = 0 in this path: bound/regularisation/energy terms on torque vanish
+    l2_reg(v, wr[0], cost, gv);
+    l2_reg(ac, wr[1], cost, ga);
+    l2_reg(jk, wr[2], cost, gj);
+    if (a.grad_vel) a.grad_vel[idx] = gv;
+    if (a.grad_acc) a.grad_acc[idx] = ga;
+    if (a.grad_jerk) a.grad_jerk[idx] = gj;
+  }
+  return cost;
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE fused kernel (discrete scene collision; rows independent)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ unsigned long long mbar;
+  stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
+  const RobotView rv = make_robot_view(smem, a.blob);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float *base = reinterpret_cast<float *>(smem + a.blob_smem_bytes) + (size_t)warp * a.eval_floats;
+  const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L);
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int N = a.B * a.H;
+  const int D = rv.D, S = rv.S, L = rv.L;
+  const bool do_pose = (a.goal_position != nullptr);
+
+  for (int e = blockIdx.x * nwarps + warp; e < N; e += gridDim.x * nwarps) {
+    const int b = e / a.H, h = e - b * a.H;
+    // ---- load q, c-space cost (lane per dof)
+    float cs_cost = 0.0f;
+    for (int d = lane; d < D; d += 32) {
+      const float qd = __ldg(a.q + (size_t)e * D + d);
+      es.qv[d] = qd;
+      float gp;
+      const float c = cspace_dof(a, rv, e, b, d, qd, gp);
+      es.gqv[d] = gp;
+      cs_cost += c;
+      if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
+    }
+    __syncwarp();
+    // ---- FK
+    warp_fk(rv, es, lane);
+    warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr);
+    // ---- tool poses + pose cost (lane per tool frame)
+    float pose_c = 0.0f;
+    for (int t = lane; t < L; t += 32) {
+      const float *T = es.cumul + 12 * rv.tool_map[t];
+      const V3 p = mk3(T[3], T[7], T[11]);
+      const Q4 qt = quat_from_transform(T);
+      if (a.link_pos) {
+        float *o = a.link_pos + ((size_t)e * L + t) * 3;
+        o[0] = p.x;
+        o[1] = p.y;
+        o[2] = p.z;
+      }
+      if (a.link_quat) *reinterpret_cast<float4 *>(a.link_quat + ((size_t)e * L + t) * 4) = make_float4(qt.w, qt.x, qt.y, qt.z);
+      float *pg = es.pose_g + 8 * t;
+      pg[0] = pg[1] = pg[2] = pg[4] = pg[5] = pg[6] = 0.0f;
+      if (do_pose) {
+        const int gi = a.idxs_goal ? __ldg(a.idxs_goal + b) : 0;
+        const bool term = !(h < a.H - 1 && a.H > 1);
+        const float *axes = term ? a.pose_axes_t : a.pose_axes_nt;
+        const float *tol = term ? a.pose_tol_t : a.pose_tol_nt;
+        const size_t go = ((size_t)gi * L + t) * cfg.num_goalset;
+        const PoseOut po = tool_pose_cost(p, qt, a.goal_position + go * 3, a.goal_quat + go * 4, cfg.num_goalset,
+                                          cfg.pose_weight[0], cfg.pose_weight[1], axes ? axes + 6 * t : nullptr,
+                                          tol ? __ldg(tol + 2 * t) : 0.0f, tol ? __ldg(tol + 2 * t + 1) : 0.0f,
+                                          cfg.pose_rotation_method);
+        const V3 om = quat_grad_to_omega(qt, po.gq_w, po.gq_x, po.gq_y, po.gq_z);
+        pg[0] = po.g_pos.x;
+        pg[1] = po.g_pos.y;
+        pg[2] = po.g_pos.z;
+        pg[4] = om.x;
+        pg[5] = om.y;
+        pg[6] = om.z;
+        pose_c += po.pos_cost + po.rot_cost;
+        if (a.pose_cost) {
+          a.pose_cost[((size_t)e * L + t) * 2] = po.pos_cost;
+          a.pose_cost[((size_t)e * L + t) * 2 + 1] = po.rot_cost;
+        }
+        if (a.pose_goalset_idx) a.pose_goalset_idx[(size_t)e * L + t] = po.goal_idx;
+      }
+    }
+    __syncwarp();
+    // ---- self collision (reads padded spheres in gsph)
+    float self_c = 0.0f, fmax_ = 0.0f;
+    int bi = 0, bj = 0;
+    if (cfg.self_weight > 0.0f && rv.P > 0) {
+      fmax_ = warp_self_collision_pairs(es.gsph, rv.pairs, rv.P, lane, bi, bj);
+      self_c = (fmax_ > 0.0f) ? 0.5f * cfg.self_weight * fmax_ : 0.0f;
+    }
+    if (a.self_cost && lane == 0) a.self_cost[e] = self_c;
+    __syncwarp();
+    // ---- scene collision (lane per sphere) -> gsph = gradient
+    float scene_c = 0.0f;
+    const bool do_scene = cfg.scene_weight > 0.0f && (a.cuboids.inv_pose != nullptr || a.voxels.inv_pose != nullptr);
+    const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
+    for (int s = lane; s < S; s += 32) {
+      V3 g = mk3(0, 0, 0);
+      float c = 0.0f;
+      if (do_scene) {
+        const float4 sp = es.sph[s];
+        c = sphere_scene_discrete(mk3(sp.x, sp.y, sp.z), sp.w, cfg.scene_activation, cfg.scene_weight, a.cuboids,
+                                  a.voxels, env, g);
+      }
+      es.gsph[s] = make_float4(g.x, g.y, g.z, 0.0f);
+      scene_c += c;
+      if (a.scene_cost) a.scene_cost[(size_t)e * S + s] = c;
+    }
+    __syncwarp();
+    if (fmax_ > 0.0f && lane == 0) {
+      const float4 pi = es.sph[bi], pj = es.sph[bj];
+      const float w = cfg.self_weight;
+      float4 gi = es.gsph[bi], gj = es.gsph[bj];
+      const float gx = w * (pj.x - pi.x), gy = w * (pj.y - pi.y), gz = w * (pj.z - pi.z);
+      gi.x += gx;
+      gi.y += gy;
+      gi.z += gz;
+      gj.x -= gx;
+      gj.y -= gy;
+      gj.z -= gz;
+      es.gsph[bi] = gi;
+      es.gsph[bj] = gj;
+    }
+    __syncwarp();
+    // ---- backward
+    warp_fk_backward(rv, es, lane, a.grad_q + (size_t)e * D);
+    // ---- total cost for the row
+    const float tot = warp_sum(cs_cost + pose_c + scene_c) + self_c;
+    if (lane == 0) a.cost[e] = tot;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Drop-in FK forward: warp per row, parameters read from global memory (L1-resident, a few KB).
+// ------------------------------------------------------------------------------------------------
+struct KinFwdArgs {
+  float *link_pos, *link_quat, *spheres_out, *cumul_out;
+  const float *q, *fixed, *robot_spheres, *joff;
+  const int8_t *jtype;
+  const int16_t *jmap, *lmap, *tool_map, *sph_link;
+  const int32_t *env_query_idx;
+  int num_envs, N, horizon, D, S, nl, L, write_cumul;
+};
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) kin_forward_kernel(const __grid_constant__ KinFwdArgs a) {
+  extern __shared__ __align__(16) float fsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *cumul = fsm + (size_t)warp * a.nl * 12;
+  for (int e = blockIdx.x * kWarpsPerCta + warp; e < a.N; e += gridDim.x * kWarpsPerCta) {
+    for (int l = lane; l < a.nl; l += 32) {
+      const int jt = a.jtype[l];
+      float th = 0.0f;
+      if (jt >= 0) th = __ldg(a.joff + 2 * l) * __ldg(a.q + (size_t)e * a.D + a.jmap[l]) + __ldg(a.joff + 2 * l + 1);
+      local_link_transform(a.fixed + 12 * l, jt, th, cumul + 12 * l);
+    }
+    __syncwarp();
+    const int k = lane, r = k >> 2, c = k & 3;
+    for (int l = 1; l < a.nl; ++l) {  // parents precede children: index order is a valid schedule
+      float out = 0.0f;
+      if (k < 12) {
+        const float *P = cumul + 12 * a.lmap[l];
+        const float *Lm = cumul + 12 * l;
+        const float4 pr = *reinterpret_cast<const float4 *>(P + 4 * r);
+        out = pr.x * Lm[c] + pr.y * Lm[4 + c] + pr.z * Lm[8 + c] + (c == 3 ? pr.w : 0.0f);
+      }
+      __syncwarp();
+      if (k < 12) cumul[12 * l + k] = out;
+      __syncwarp();
+    }
+    if (a.write_cumul) {
+      float4 *dst = reinterpret_cast<float4 *>(a.cumul_out + (size_t)e * a.nl * 12);
+      const float4 *src = reinterpret_cast<const float4 *>(cumul);
+      for (int i = lane; i < a.nl * 3; i += 32) dst[i] = src[i];
+    }
+    const int cfg = (a.num_envs > 1) ? __ldg(a.env_query_idx + e / a.horizon) : 0;
+    const float4 *ls = reinterpret_cast<const float4 *>(a.robot_spheres) + (size_t)cfg * a.S;
+    float4 *so = reinterpret_cast<float4 *>(a.spheres_out) + (size_t)e * a.S;
+    for (int s = lane; s < a.S; s += 32) {
+      const float *T = cumul + 12 * a.sph_link[s];
+      const float4 p = __ldg(ls + s);
+      float4 w;
+      w.x = T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3];
+      w.y = T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7];
+      w.z = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11];
+      w.w = p.w;
+      so[s] = w;
+    }
+    for (int t = lane; t < a.L; t += 32) {
+      const float *T = cumul + 12 * a.tool_map[t];
+      const Q4 qt = quat_from_transform(T);
+      float *o = a.link_pos + ((size_t)e * a.L + t) * 3;
+      o[0] = T[3];
+      o[1] = T[7];
+      o[2] = T[11];
+      *reinterpret_cast<float4 *>(a.link_quat + ((size_t)e * a.L + t) * 4) = make_float4(qt.w, qt.x, qt.y, qt.z);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Drop-in FK backward: warp per row; cumul re-read from global; link force/torque accumulators.
+// ------------------------------------------------------------------------------------------------
+struct KinBwdArgs {
+  float *grad_out;
+  const float *g_pos, *g_quat, *g_sph, *cumul, *robot_spheres, *joff;
+  const int16_t *lmap, *jmap, *tool_map, *sph_link;
+  const int8_t *jtype;
+  const int32_t *env_query_idx;
+  int num_envs, N, horizon, D, S, nl, L;
+};
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) kin_backward_kernel(const __grid_constant__ KinBwdArgs a) {
+  extern __shared__ __align__(16) float fsm[];
+  // CTA-shared: ancestor masks [nl] (uint64)
+  unsigned long long *anc = reinterpret_cast<unsigned long long *>(fsm);
+  float *wbase = fsm + 2 * a.nl + (size_t)(threadIdx.x >> 5) * (a.nl * 12 + a.nl * 8 + a.nl + a.D);
+  float *cumul = wbase, *ft = wbase + a.nl * 12, *contrib = ft + a.nl * 8, *gq = contrib + a.nl;
+  if (threadIdx.x == 0) {
+    anc[0] = 1ull;
+    for (int l = 1; l < a.nl; ++l) anc[l] = anc[a.lmap[l]] | (1ull << l);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = blockIdx.x * kWarpsPerCta + warp; e < a.N; e += gridDim.x * kWarpsPerCta) {
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(a.cumul + (size_t)e * a.nl * 12);
+      float4 *dst = reinterpret_cast<float4 *>(cumul);
+      for (int i = lane; i < a.nl * 3; i += 32) dst[i] = __ldg(src + i);
+    }
+    for (int i = lane; i < a.nl * 8; i += 32) ft[i] = 0.0f;
+    for (int d = lane; d < a.D; d += 32) gq[d] = 0.0f;
+    __syncwarp();
+    const int cfg = (a.num_envs > 1) ? __ldg(a.env_query_idx + e / a.horizon) : 0;
+    // lane per link gathers its spheres (deterministic order)
+    for (int k = lane; k < a.nl; k += 32) {
+      const float *Tk = cumul + 12 * k;
+      const V3 o = mk3(Tk[3], Tk[7], Tk[11]);
+      V3 F = mk3(0, 0, 0), T = mk3(0, 0, 0);
+      if (a.g_sph != nullptr) {
+        for (int s = 0; s < a.S; ++s) {
+          if (a.sph_link[s] != k) continue;
+          const float4 g4 = __ldg(reinterpret_cast<const float4 *>(a.g_sph) + (size_t)e * a.S + s);
+          if (g4.x == 0.0f && g4.y == 0.0f && g4.z == 0.0f) continue;
+          const float4 p = __ldg(reinterpret_cast<const float4 *>(a.robot_spheres) + (size_t)cfg * a.S + s);
+          const V3 rel = mk3(Tk[0] * p.x + Tk[1] * p.y + Tk[2] * p.z, Tk[4] * p.x + Tk[5] * p.y + Tk[6] * p.z,
+                             Tk[8] * p.x + Tk[9] * p.y + Tk[10] * p.z);  // p_world - o_k
+          const V3 g = mk3(g4.x, g4.y, g4.z);
+          F = F + g;
+          T = T + cross(rel, g);
+        }
+      }
+      if (a.g_pos != nullptr) {
+        for (int t = 0; t < a.L; ++t) {
+          if (a.tool_map[t] != k) continue;
+          const float *gp = a.g_pos + ((size_t)e * a.L + t) * 3;
+          const float4 gqv = __ldg(reinterpret_cast<const float4 *>(a.g_quat) + (size_t)e * a.L + t);
+          const V3 g = mk3(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2));
+          if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && gqv.x == 0.0f && gqv.y == 0.0f && gqv.z == 0.0f && gqv.w == 0.0f)
+            continue;
+          const Q4 qt = quat_from_transform(Tk);
+          F = F + g;
+          T = T + quat_grad_to_omega(qt, gqv.x, gqv.y, gqv.z, gqv.w);
+        }
+      }
+      ft[8 * k + 0] = F.x;
+      ft[8 * k + 1] = F.y;
+      ft[8 * k + 2] = F.z;
+      ft[8 * k + 4] = T.x;
+      ft[8 * k + 5] = T.y;
+      ft[8 * k + 6] = T.z;
+    }
+    __syncwarp();
+    for (int j = lane; j < a.nl; j += 32) {
+      const int jt = a.jtype[j];
+      float res = 0.0f;
+      if (jt >= 0) {
+        const float *Tj = cumul + 12 * j;
+        const V3 oj = mk3(Tj[3], Tj[7], Tj[11]);
+        V3 F = mk3(0, 0, 0), T = mk3(0, 0, 0);
+        for (int k = j; k < a.nl; ++k) {
+          if (!((anc[k] >> j) & 1ull)) continue;
+          const V3 Fk = mk3(ft[8 * k], ft[8 * k + 1], ft[8 * k + 2]);
+          const float *Tk = cumul + 12 * k;
+          F = F + Fk;
+          T = T + mk3(ft[8 * k + 4], ft[8 * k + 5], ft[8 * k + 6]) + cross(mk3(Tk[3], Tk[7], Tk[11]) - oj, Fk);
+        }
+        const int ax = (jt >= JT_XR) ? jt - JT_XR : jt;
+        const V3 av = mk3(Tj[ax], Tj[4 + ax], Tj[8 + ax]);
+        res = __ldg(a.joff + 2 * j) * ((jt >= JT_XR) ? dot(av, T) : dot(av, F));
+      }
+      contrib[j] = res;
+    }
+    __syncwarp();
+    for (int d = lane; d < a.D; d += 32) {
+      float g = 0.0f;
+      for (int j = 0; j < a.nl; ++j)
+        if (a.jmap[j] == d && a.jtype[j] >= 0) g += contrib[j];
+      a.grad_out[(size_t)e * a.D + d] = g;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Drop-in self collision.  TPE threads per eval: 32 (warp) for short pair lists, 256 (CTA) otherwise.
+// ------------------------------------------------------------------------------------------------
+struct SelfArgs {
+  float *out_distance, *out_vec, *pair_distance;
+  uint8_t *sparse_index;
+  const float *spheres, *padding, *weight;
+  const uint32_t *pairs;
+  int N, S, P, store_pair, compute_grad;
+};
+
+template <int TPE>
+__global__ void __launch_bounds__(256) self_collision_kernel(const __grid_constant__ SelfArgs a) {
+  extern __shared__ __align__(16) float fsm[];
+  __shared__ unsigned long long red[8];
+  constexpr int EPB = 256 / TPE;  // evals per block
+  const int sub = threadIdx.x / TPE, t = threadIdx.x % TPE;
+  float4 *psph = reinterpret_cast<float4 *>(fsm) + (size_t)sub * a.S;
+  const float w = __ldg(a.weight);
+  for (int e0 = blockIdx.x * EPB; e0 < a.N; e0 += gridDim.x * EPB) {
+    const int e = e0 + sub;
+    const bool valid = e < a.N;
+    if (valid) {
+      for (int s = t; s < a.S; s += TPE) {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(a.spheres) + (size_t)e * a.S + s);
+        v.w += __ldg(a.padding + s);
+        psph[s] = v;
+        const size_t gi = (size_t)e * a.S + s;
+        if (a.sparse_index[gi] == 1) {  // lazy zeroing of last call's two rows
+          *reinterpret_cast<float4 *>(a.out_vec + gi * 4) = make_float4(0, 0, 0, 0);
+          a.sparse_index[gi] = 0;
+        }
+      }
+    }
+    if (TPE == 32) __syncwarp(); else __syncthreads();
+    unsigned long long key = 0ull;  // (float bits << 32) | ~pair index  -> max = largest f, first pair on ties
+    if (valid) {
+      for (int p = t; p < a.P; p += TPE) {
+        const uint32_t pr = __ldg(a.pairs + p);
+        const float4 x = psph[pr & 0xffffu], y = psph[pr >> 16];
+        const float rs = x.w + y.w;
+        const float dx = x.x - y.x, dy = x.y - y.y, dz = x.z - y.z;
+        float f = rs * rs - (dx * dx + dy * dy + dz * dz);
+        if (!(x.w >= 0.0f && y.w >= 0.0f)) f = 0.0f;
+        if (a.store_pair) a.pair_distance[(size_t)e * a.P + p] = f;
+        if (f > 0.0f) {
+          const unsigned long long kk = ((unsigned long long)__float_as_uint(f) << 32) | (0xffffffffu - (uint32_t)p);
+          key = kk > key ? kk : key;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFull, key, o);
+      key = other > key ? other : key;
+    }
+    if (TPE > 32) {
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = key;
+      __syncthreads();
+      key = red[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) key = red[i] > key ? red[i] : key;
+    }
+    if (valid && t == 0) {
+      if (key == 0ull) {
+        a.out_distance[e] = 0.0f;
+      } else {
+        const float f = __uint_as_float((uint32_t)(key >> 32));
+        const uint32_t p = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
+        const uint32_t pr = __ldg(a.pairs + p);
+        const int i = pr & 0xffffu, j = pr >> 16;
+        a.out_distance[e] = 0.5f * w * f;
+        if (a.compute_grad) {
+          const float4 x = psph[i], y = psph[j];
+          float4 g = make_float4(w * (y.x - x.x), w * (y.y - x.y), w * (y.z - x.z), -w);
+          *reinterpret_cast<float4 *>(a.out_vec + ((size_t)e * a.S + i) * 4) = g;
+          g = make_float4(-g.x, -g.y, -g.z, -w);
+          *reinterpret_cast<float4 *>(a.out_vec + ((size_t)e * a.S + j) * 4) = g;
+          a.sparse_index[(size_t)e * a.S + i] = 1;
+          a.sparse_index[(size_t)e * a.S + j] = 1;
+        }
+      }
+    }
+    if (TPE == 32) __syncwarp(); else __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Drop-in scene collision: thread per (b,h,s); discrete or swept(+speed metric).
+// ------------------------------------------------------------------------------------------------
+struct SceneArgs {
+  float *distance, *gradient;
+  const float *spheres, *weight, *eta, *speed_dt;
+  CuboidSet cuboids;
+  VoxelSet voxels;
+  const int32_t *env_query_idx;
+  int B, H, S, use_multi_env, sweep, speed_metric;
+};
+
+__global__ void __launch_bounds__(128) scene_collision_kernel(const __grid_constant__ SceneArgs a) {
+  const long long total = (long long)a.B * a.H * a.S;
+  const float w = __ldg(a.weight), eta = __ldg(a.eta);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / ((long long)a.H * a.S));
+    const int h = (int)((i - (long long)b * a.H * a.S) / a.S);
+    const int env = a.use_multi_env ? __ldg(a.env_query_idx + b) : 0;
+    const float4 sp = __ldg(reinterpret_cast<const float4 *>(a.spheres) + i);
+    const V3 c = mk3(sp.x, sp.y, sp.z);
+    V3 g = mk3(0, 0, 0);
+    float cost;
+    if (!a.sweep) {
+      cost = sphere_scene_discrete(c, sp.w, eta, w, a.cuboids, a.voxels, env, g);
+    } else {
+      const bool hp = h > 0, hn = h < a.H - 1;
+      V3 pv = c, nx = c;
+      if (hp) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(a.spheres) + i - a.S);
+        pv = mk3(t.x, t.y, t.z);
+      }
+      if (hn) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(a.spheres) + i + a.S);
+        nx = mk3(t.x, t.y, t.z);
+      }
+      cost = sphere_scene_swept(c, sp.w, eta, w, hp, pv, hn, nx, a.cuboids, a.voxels, env, g);
+      if (a.speed_metric && hp && hn) speed_metric(pv, c, nx, __ldg(a.speed_dt), cost, g);
+    }
+    a.distance[i] = cost;
+    *reinterpret_cast<float4 *>(a.gradient + 4 * i) = make_float4(g.x, g.y, g.z, 0.0f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Drop-in tool pose cost: thread per (b,h,l)
+// ------------------------------------------------------------------------------------------------
+struct PoseArgs {
+  float *out_distance, *out_pos_dist, *out_rot_dist, *out_pos_grad, *out_rot_grad;
+  int32_t *out_goalset_idx;
+  const float *cur_pos, *cur_quat, *goal_pos, *goal_quat, *weight, *axes_t, *axes_nt, *tol_t, *tol_nt;
+  const int32_t *idxs_goal;
+  int B, H, L, G, method;
+};
+
+__global__ void __launch_bounds__(128) tool_pose_kernel(const __grid_constant__ PoseArgs a) {
+  const int total = a.B * a.H * a.L;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / (a.H * a.L);
+    const int h = (i - b * a.H * a.L) / a.L;
+    const int l = i - b * a.H * a.L - h * a.L;
+    const bool term = !(h < a.H - 1 && a.H > 1);
+    const float *axes = (term ? a.axes_t : a.axes_nt) + 6 * l;
+    const float *tol = (term ? a.tol_t : a.tol_nt) + 2 * l;
+    const int gi = __ldg(a.idxs_goal + b);
+    const V3 p = mk3(__ldg(a.cur_pos + 3 * i), __ldg(a.cur_pos + 3 * i + 1), __ldg(a.cur_pos + 3 * i + 2));
+    const float4 qw = __ldg(reinterpret_cast<const float4 *>(a.cur_quat) + i);
+    const size_t go = ((size_t)gi * a.L + l) * a.G;
+    const PoseOut po = tool_pose_cost(p, Q4{qw.y, qw.z, qw.w, qw.x}, a.goal_pos + go * 3, a.goal_quat + go * 4, a.G,
+                                      __ldg(a.weight), __ldg(a.weight + 1), axes, __ldg(tol), __ldg(tol + 1), a.method);
+    a.out_distance[2 * i] = po.pos_cost;
+    a.out_distance[2 * i + 1] = po.rot_cost;
+    a.out_goalset_idx[i] = po.goal_idx;
+    a.out_pos_dist[i] = po.pos_err;
+    a.out_rot_dist[i] = po.rot_err;
+    a.out_pos_grad[3 * i] = po.g_pos.x;
+    a.out_pos_grad[3 * i + 1] = po.g_pos.y;
+    a.out_pos_grad[3 * i + 2] = po.g_pos.z;
+    *reinterpret_cast<float4 *>(a.out_rot_grad + 4 * i) = make_float4(po.gq_w, po.gq_x, po.gq_y, po.gq_z);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Drop-in c-space kernels: thread per (b,h,d)
+// ------------------------------------------------------------------------------------------------
+struct CsStateArgs {
+  float *out_cost, *gp, *gv, *ga, *gj, *gtau;
+  const float *pos, *vel, *acc, *jerk, *effort, *dt, *target, *p_b, *v_b, *a_b, *j_b, *e_b, *weight, *act, *reg, *tw,
+      *ntf, *tdw;
+  const int32_t *idxs_target;
+  int write_grad, B, H, D, retime_w, retime_r;
+};
+
+__global__ void __launch_bounds__(128) cspace_state_kernel(const __grid_constant__ CsStateArgs a) {
+  const int total = a.B * a.H * a.D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / (a.H * a.D);
+    const int h = (i - b * a.H * a.D) / a.D;
+    const int d = i - b * a.H * a.D - h * a.D;
+    const int D = a.D;
+    const float dt = __ldg(a.dt + b);
+    float tw = __ldg(a.tw);
+    if (h < a.H - 1) tw *= __ldg(a.ntf);
+    float wb[5], wr[5], act[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      wb[k] = __ldg(a.weight + k);
+      wr[k] = __ldg(a.reg + k);
+      act[k] = __ldg(a.act + k);
+    }
+    if (a.retime_w) {
+      wb[1] = dt * wb[1];
+      wb[2] = powf(dt, 2.0f) * wb[2];
+      wb[3] = powf(dt, 3.0f) * wb[3];
+    }
+    if (a.retime_r) {
+      wr[0] = dt * wr[0];
+      wr[1] = powf(dt, 2.0f) * wr[1];
+      wr[2] = powf(dt, 3.0f) * wr[2];
+      wr[4] = dt * wr[4];
+    }
+    const float p = __ldg(a.pos + i), v = __ldg(a.vel + i), ac = __ldg(a.acc + i), jk = __ldg(a.jerk + i),
+                tau = __ldg(a.effort + i);
+    float cost = 0.0f, gp = 0.0f, gv = 0.0f, ga = 0.0f, gj = 0.0f, gt = 0.0f;
+    bound_cost(p, __ldg(a.p_b + d), __ldg(a.p_b + D + d), act[0], wb[0], cost, gp);
+    bound_cost(v, __ldg(a.v_b + d), __ldg(a.v_b + D + d), act[1], wb[1], cost, gv);
+    bound_cost(ac, __ldg(a.a_b + d), __ldg(a.a_b + D + d), act[2], wb[2], cost, ga);
+    bound_cost(jk, __ldg(a.j_b + d), __ldg(a.j_b + D + d), act[3], wb[3], cost, gj);
+    bound_cost(tau, __ldg(a.e_b + d), __ldg(a.e_b + D + d), act[4], wb[4], cost, gt);
+    if (tw > 0.0f) {
+      tw *= __ldg(a.tdw + d);
+      const float err = p - __ldg(a.target + (size_t)__ldg(a.idxs_target + b) * D + d);
+      cost += tw * err * err;
+      gp += 2.0f * tw * err;
+    }
+    l2_reg(v, wr[0], cost, gv);
+    l2_reg(ac, wr[1], cost, ga);
+    l2_reg(jk, wr[2], cost, gj);
+    l2_reg(tau, wr[3], cost, gt);
+    if (wr[4] > 0.0f) {
+      const float ce = tau * v * dt;
+      cost += wr[4] * ce * ce;
+      gt += 2.0f * wr[4] * ce * v * dt;
+      gv += 2.0f * wr[4] * ce * tau * dt;
+    }
+    a.out_cost[i] = cost;
+    if (a.write_grad) {
+      a.gp[i] = gp;
+      a.gv[i] = gv;
+      a.ga[i] = ga;
+      a.gj[i] = gj;
+      a.gtau[i] = gt;
+    }
+  }
+}
+
+struct CsPosArgs {
+  float *out_cost, *gp, *gtau;
+  const float *pos, *effort, *target, *p_b, *e_b, *weight, *act, *tw, *tdw, *reg, *cur_p, *cur_v, *v_b, *dt;
+  const int32_t *target_idx, *idxs_cur;
+  int write_grad, B, H, D;
+};
+
+__global__ void __launch_bounds__(128) cspace_position_kernel(const __grid_constant__ CsPosArgs a) {
+  const int total = a.B * a.H * a.D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / (a.H * a.D);
+    const int d = i % a.D;
+    const int D = a.D;
+    const float eta_p = __ldg(a.act), eta_t = __ldg(a.act + 1), w = __ldg(a.weight), tau_w = __ldg(a.weight + 1);
+    float pl = __ldg(a.p_b + d), pu = __ldg(a.p_b + D + d);
+    {
+      const float r = pu - pl;
+      pl = pl + eta_p * r;
+      pu = pu - eta_p * r;
+    }
+    const int cur = __ldg(a.idxs_cur + b);
+    const float dt = __ldg(a.dt + cur);
+    float cur_p = 0.0f;
+    if (dt > 0.0f) {
+      cur_p = __ldg(a.cur_p + (size_t)cur * D + d);
+      pl = fmaxf(pl, cur_p + __ldg(a.v_b + d) * dt);
+      pu = fminf(pu, cur_p + __ldg(a.v_b + D + d) * dt);
+    }
+    const float p = __ldg(a.pos + i), tau = __ldg(a.effort + i);
+    float cost = 0.0f, gp = 0.0f, gt = 0.0f;
+    bound_cost(p, pl, pu, 0.0f, w, cost, gp);
+    if (tau_w > 0.0f) bound_cost(tau, __ldg(a.e_b + d), __ldg(a.e_b + D + d), eta_t, tau_w, cost, gt);
+    const float tw = __ldg(a.tw) * __ldg(a.tdw + d);
+    if (tw > 0.0f) {
+      const float err = p - __ldg(a.target + (size_t)__ldg(a.target_idx + b) * D + d);
+      cost += tw * err * err;
+      gp += 2.0f * tw * err;
+    }
+    const float vw = __ldg(a.reg) * dt, aw = __ldg(a.reg + 1) * dt * dt;
+    if (dt > 0.0f && (vw > 0.0f || aw > 0.0f)) {
+      const float vi = (p - cur_p) / dt;
+      if (vw > 0.0f) {
+        cost += 0.5f * vw * vi * vi;
+        gp += vw * vi / dt;
+      }
+      if (aw > 0.0f) {
+        const float ai = (vi - __ldg(a.cur_v + (size_t)cur * D + d)) / dt;
+        cost += 0.5f * aw * ai * ai;
+        gp += aw * ai / (dt * dt);
+      }
+    }
+    a.out_cost[i] = cost;
+    if (a.write_grad) {
+      a.gp[i] = gp;
+      a.gtau[i] = gt;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+thread_local int g_last_err = 0;
+inline int ret(cudaError_t e) {
+  g_last_err = (int)e;
+  return (int)e;
+}
+inline int launch_status() { return ret(cudaGetLastError()); }
+
+struct DevInfo {
+  int sm_count = 0, max_smem = 0;
+  bool ok = false;
+};
+DevInfo &dev_info() {
+  static thread_local DevInfo d;
+  if (!d.ok) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+      cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      d.ok = d.sm_count > 0;
+    }
+  }
+  return d;
+}
+
+template <typename K>
+int persistent_grid(K kernel, int block, size_t smem, long long work_items) {
+  DevInfo &d = dev_info();
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+  if (per_sm < 1) per_sm = 1;
+  long long g = (long long)d.sm_count * per_sm;
+  if (g > work_items) g = work_items;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+inline CuboidSet to_dev(const cb200_cuboid_set *c) {
+  CuboidSet o{};
+  if (c != nullptr && c->inv_pose != nullptr && c->max_n > 0)
+    o = CuboidSet{c->dims, c->inv_pose, c->enable, c->count, c->max_n, c->num_envs};
+  return o;
+}
+inline VoxelSet to_dev(const cb200_voxel_set *v) {
+  VoxelSet o{};
+  if (v != nullptr && v->inv_pose != nullptr && v->max_n > 0)
+    o = VoxelSet{v->params, v->inv_pose, v->enable, v->count, v->features, v->n_voxels_per_layer,
+                 v->max_n,  v->num_envs, v->max_dist};
+  return o;
+}
+
+template <typename T>
+inline void align16(std::vector<unsigned char> &buf) {
+  while (buf.size() % 16) buf.push_back(0);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int cb200_abi_version(void) { return CB200_ABI_VERSION; }
+int cb200_sm_arch(void) { return 100; }
+const char *cb200_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
+
+int cb200_device_info(int device, int *sm_count, int *max_smem_optin) {
+  cudaError_t e = cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return ret(e);
+  return ret(cudaDeviceGetAttribute(max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+}
+
+int cb200_kinematics_forward_spheres(float *link_pos, float *link_quat, float *batch_robot_spheres,
+                                     float *batch_center_of_mass, float *global_cumul_mat, const float *joint_vec,
+                                     const float *fixed_transform, const float *robot_spheres,
+                                     const float *link_masses_com, const int8_t *joint_map_type,
+                                     const int16_t *joint_map, const int16_t *link_map, const int16_t *tool_frame_map,
+                                     const int16_t *link_sphere_map, const float *joint_offset_map,
+                                     const int32_t *env_query_idx, int num_envs, int batch_size, int horizon,
+                                     int n_joints, int num_spheres, int num_links, int n_tool_frames,
+                                     int write_global_cumul, int compute_com, cb200_stream_t stream) {
+  (void)batch_center_of_mass;
+  (void)link_masses_com;
+  if (compute_com != 0 || batch_size < 0 || num_links < 1 || horizon < 1) return ret(cudaErrorInvalidValue);
+  if (batch_size == 0) return ret(cudaSuccess);
+  KinFwdArgs a{link_pos, link_quat, batch_robot_spheres, global_cumul_mat, joint_vec, fixed_transform, robot_spheres,
+               joint_offset_map, joint_map_type, joint_map, link_map, tool_frame_map, link_sphere_map, env_query_idx,
+               num_envs, batch_size, horizon, n_joints, num_spheres, num_links, n_tool_frames, write_global_cumul};
+  const size_t smem = (size_t)kWarpsPerCta * num_links * 12 * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kin_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ret(e);
+  }
+  const int grid = persistent_grid(kin_forward_kernel, kWarpsPerCta * 32, smem, (batch_size + kWarpsPerCta - 1) / kWarpsPerCta);
+  kin_forward_kernel<<<grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(a);
+  return launch_status();
+}
+
+int cb200_kinematics_backward(float *grad_out, const float *grad_nlinks_pos, const float *grad_nlinks_quat,
+                              const float *grad_spheres, const float *grad_center_of_mass,
+                              const float *batch_center_of_mass, const float *grad_jacobian,
+                              const float *global_cumul_mat, const float *robot_spheres, const float *link_masses_com,
+                              const int16_t *link_map, const int16_t *joint_map, const int8_t *joint_map_type,
+                              const int16_t *tool_frame_map, const int16_t *link_sphere_map,
+                              const int16_t *link_chain_data, const int16_t *link_chain_offsets,
+                              const int16_t *joint_links_data, const int16_t *joint_links_offsets,
+                              const uint8_t *joint_affects_endeffector, const float *joint_offset_map,
+                              const int32_t *env_query_idx, int num_envs, int batch_size, int horizon, int n_joints,
+                              int num_spheres, int num_links, int n_tool_frames, int compute_com,
+                              int compute_jacobian_grad, cb200_stream_t stream) {
+  (void)grad_center_of_mass;
+  (void)batch_center_of_mass;
+  (void)grad_jacobian;
+  (void)link_masses_com;
+  (void)link_chain_data;
+  (void)link_chain_offsets;
+  (void)joint_links_data;
+  (void)joint_links_offsets;
+  (void)joint_affects_endeffector;
+  if (compute_com != 0 || compute_jacobian_grad != 0 || num_links < 1 || num_links > kMaxLinks || horizon < 1)
+    return ret(cudaErrorInvalidValue);
+  if (batch_size == 0) return ret(cudaSuccess);
+  KinBwdArgs a{grad_out, grad_nlinks_pos, grad_nlinks_quat, num_spheres > 0 ? grad_spheres : nullptr, global_cumul_mat,
+               robot_spheres, joint_offset_map, link_map, joint_map, tool_frame_map, link_sphere_map, joint_map_type,
+               env_query_idx, num_envs, batch_size, horizon, n_joints, num_spheres, num_links, n_tool_frames};
+  const size_t per_warp = (size_t)num_links * 12 + num_links * 8 + num_links + n_joints;
+  const size_t smem = ((size_t)2 * num_links + kWarpsPerCta * per_warp) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kin_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ret(e);
+  }
+  const int grid = persistent_grid(kin_backward_kernel, kWarpsPerCta * 32, smem, (batch_size + kWarpsPerCta - 1) / kWarpsPerCta);
+  kin_backward_kernel<<<grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(a);
+  return launch_status();
+}
+
+int cb200_self_collision_distance(float *out_distance, float *out_vec, float *pair_distance, uint8_t *sparse_index,
+                                  const float *robot_spheres, const float *sphere_padding, const float *weight,
+                                  const int16_t *pair_locations, float *block_batch_max_value,
+                                  int16_t *block_batch_max_index, int num_blocks_per_batch, int max_threads_per_block,
+                                  int batch_size, int horizon, int nspheres, int num_collision_pairs,
+                                  int store_pair_distance, int compute_grad, cb200_stream_t stream) {
+  (void)block_batch_max_value;
+  (void)block_batch_max_index;
+  (void)num_blocks_per_batch;
+  (void)max_threads_per_block;
+  const int N = batch_size * horizon;
+  if (N == 0) return ret(cudaSuccess);
+  if (N < 0 || nspheres < 1 || nspheres > 65535) return ret(cudaErrorInvalidValue);
+  SelfArgs a{out_distance, out_vec, pair_distance, sparse_index, robot_spheres, sphere_padding, weight,
+             reinterpret_cast<const uint32_t *>(pair_locations), N, nspheres, num_collision_pairs, store_pair_distance,
+             compute_grad};
+  cudaError_t e = cudaSuccess;
+  if (num_collision_pairs <= 4096) {
+    const size_t smem = (size_t)8 * nspheres * 16;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(self_collision_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ret(e);
+    const int grid = persistent_grid(self_collision_kernel<32>, 256, smem, (N + 7) / 8);
+    self_collision_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    const size_t smem = (size_t)nspheres * 16;
+    const int grid = persistent_grid(self_collision_kernel<256>, 256, smem, N);
+    self_collision_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  }
+  return launch_status();
+}
+
+static int scene_launch(float *distance, float *gradient, const float *spheres, const cb200_cuboid_set *cuboids,
+                        const cb200_voxel_set *voxels, const float *weight, const float *eta, const float *speed_dt,
+                        int speed_metric, const int32_t *env_query_idx, int B, int H, int S, int use_multi_env, int sweep,
+                        cb200_stream_t stream) {
+  const long long total = (long long)B * H * S;
+  if (total == 0) return ret(cudaSuccess);
+  if (total < 0 || (speed_metric && speed_dt == nullptr)) return ret(cudaErrorInvalidValue);
+  SceneArgs a{distance, gradient, spheres, weight, eta, speed_dt, to_dev(cuboids), to_dev(voxels), env_query_idx,
+              B, H, S, use_multi_env && env_query_idx != nullptr, sweep, speed_metric};
+  const int grid = persistent_grid(scene_collision_kernel, 128, 0, (total + 127) / 128);
+  scene_collision_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  return launch_status();
+}
+
+int cb200_sphere_obstacle_collision(float *distance, float *gradient, const float *spheres,
+                                    const cb200_cuboid_set *cuboids, const cb200_voxel_set *voxels, const float *weight,
+                                    const float *activation_distance, const int32_t *env_query_idx, int batch_size,
+                                    int horizon, int num_spheres, int use_multi_env, cb200_stream_t stream) {
+  return scene_launch(distance, gradient, spheres, cuboids, voxels, weight, activation_distance, nullptr, 0,
+                      env_query_idx, batch_size, horizon, num_spheres, use_multi_env, 0, stream);
+}
+
+int cb200_swept_sphere_obstacle_collision(float *distance, float *gradient, const float *spheres,
+                                          const cb200_cuboid_set *cuboids, const cb200_voxel_set *voxels,
+                                          const float *weight, const float *activation_distance, const float *speed_dt,
+                                          int enable_speed_metric, const int32_t *env_query_idx, int batch_size,
+                                          int horizon, int num_spheres, int use_multi_env, cb200_stream_t stream) {
+  return scene_launch(distance, gradient, spheres, cuboids, voxels, weight, activation_distance, speed_dt,
+                      enable_speed_metric, env_query_idx, batch_size, horizon, num_spheres, use_multi_env, 1, stream);
+}
+
+int cb200_tool_pose_distance(float *out_distance, float *out_position_distance, float *out_rotation_distance,
+                             float *out_position_gradient, float *out_rotation_gradient, int32_t *out_goalset_idx,
+                             const float *current_position, const float *current_quat, const float *goal_position,
+                             const float *goal_quat, const int32_t *idxs_goal, const float *position_orientation_weight,
+                             const float *terminal_pose_axes_weight_factor,
+                             const float *non_terminal_pose_axes_weight_factor,
+                             const float *terminal_pose_convergence_tolerance,
+                             const float *non_terminal_pose_convergence_tolerance, int batch_size, int horizon,
+                             int num_links, int num_goalset, int rotation_method, cb200_stream_t stream) {
+  const int total = batch_size * horizon * num_links;
+  if (total == 0) return ret(cudaSuccess);
+  if (total < 0 || num_goalset < 1 || rotation_method < 0 || rotation_method > 1) return ret(cudaErrorInvalidValue);
+  PoseArgs a{out_distance, out_position_distance, out_rotation_distance, out_position_gradient, out_rotation_gradient,
+             out_goalset_idx, current_position, current_quat, goal_position, goal_quat, position_orientation_weight,
+             terminal_pose_axes_weight_factor, non_terminal_pose_axes_weight_factor,
+             terminal_pose_convergence_tolerance, non_terminal_pose_convergence_tolerance, idxs_goal, batch_size,
+             horizon, num_links, num_goalset, rotation_method};
+  const int grid = persistent_grid(tool_pose_kernel, 128, 0, (total + 127) / 128);
+  tool_pose_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  return launch_status();
+}
+
+int cb200_cspace_state_cost(float *out_cost, float *out_grad_p, float *out_grad_v, float *out_grad_a, float *out_grad_j,
+                            float *out_grad_tau, const float *pos, const float *vel, const float *acc,
+                            const float *jerk, const float *effort, const float *state_dt,
+                            const float *target_joint_position, const int32_t *idxs_target_joint_position,
+                            const float *p_b, const float *v_b, const float *a_b, const float *j_b,
+                            const float *effort_b, const float *weight, const float *activation_distance,
+                            const float *squared_l2_regularization_weights, const float *cspace_target_weight,
+                            const float *cspace_non_terminal_weight_factor, const float *cspace_target_dof_weight,
+                            int write_grad, int batch_size, int horizon, int dof, int retime_weights,
+                            int retime_regularization_weights, cb200_stream_t stream) {
+  const int total = batch_size * horizon * dof;
+  if (total == 0) return ret(cudaSuccess);
+  if (total < 0) return ret(cudaErrorInvalidValue);
+  CsStateArgs a{out_cost, out_grad_p, out_grad_v, out_grad_a, out_grad_j, out_grad_tau, pos, vel, acc, jerk, effort,
+                state_dt, target_joint_position, p_b, v_b, a_b, j_b, effort_b, weight, activation_distance,
+                squared_l2_regularization_weights, cspace_target_weight, cspace_non_terminal_weight_factor,
+                cspace_target_dof_weight, idxs_target_joint_position, write_grad, batch_size, horizon, dof,
+                retime_weights, retime_regularization_weights};
+  const int grid = persistent_grid(cspace_state_kernel, 128, 0, (total + 127) / 128);
+  cspace_state_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  return launch_status();
+}
+
+int cb200_cspace_position_cost(float *out_cost, float *out_grad_p, float *out_grad_tau, const float *pos,
+                               const float *effort, const float *cspace_target, const int32_t *cspace_target_idx,
+                               const float *p_b, const float *effort_b, const float *weight,
+                               const float *activation_distance, const float *cspace_target_weight,
+                               const float *cspace_target_dof_weight, const float *squared_l2_reg_weight,
+                               const float *current_position, const float *current_velocity,
+                               const int32_t *idxs_current_state, const float *v_b, const float *state_dt,
+                               int write_grad, int batch_size, int horizon, int dof, cb200_stream_t stream) {
+  const int total = batch_size * horizon * dof;
+  if (total == 0) return ret(cudaSuccess);
+  if (total < 0) return ret(cudaErrorInvalidValue);
+  CsPosArgs a{out_cost, out_grad_p, out_grad_tau, pos, effort, cspace_target, p_b, effort_b, weight,
+              activation_distance, cspace_target_weight, cspace_target_dof_weight, squared_l2_reg_weight,
+              current_position, current_velocity, v_b, state_dt, cspace_target_idx, idxs_current_state, write_grad,
+              batch_size, horizon, dof};
+  const int grid = persistent_grid(cspace_position_kernel, 128, 0, (total + 127) / 128);
+  cspace_position_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  return launch_status();
+}
+
+// ---- robot blob -------------------------------------------------------------------------------
+static int64_t blob_layout(const cb200_robot_sizes *sz, const int16_t *link_map, BlobHeader *h, int *n_joint_links) {
+  const int nl = sz->num_links, D = sz->num_dof, S = sz->num_spheres, L = sz->num_tool_frames, P = sz->num_pairs;
+  if (nl < 1 || nl > kMaxLinks || D < 0 || S < 0 || L < 0 || P < 0) return -1;
+  int n_levels = 1;
+  if (link_map != nullptr) {
+    std::vector<int> depth(nl, 0);
+    for (int l = 1; l < nl; ++l) {
+      if (link_map[l] < 0 || link_map[l] >= l) return -2;
+      depth[l] = depth[link_map[l]] + 1;
+      n_levels = std::max(n_levels, depth[l] + 1);
+    }
+  } else {
+    n_levels = nl;  // upper bound for sizing
+  }
+  int64_t off = sizeof(BlobHeader);
+  auto take = [&](int64_t bytes) {
+    int64_t o = off;
+    off = (off + bytes + 15) & ~(int64_t)15;
+    return (int32_t)o;
+  };
+  memset(h, 0, sizeof(*h));
+  h->magic = kBlobMagic;
+  h->nl = nl;
+  h->D = D;
+  h->S = S;
+  h->L = L;
+  h->P = P;
+  h->n_levels = n_levels;
+  h->off_fixed = take((int64_t)nl * 48);
+  h->off_joff = take((int64_t)nl * 8);
+  h->off_link_map = take((int64_t)nl * 2);
+  h->off_joint_map = take((int64_t)nl * 2);
+  h->off_joint_type = take(nl);
+  h->off_tool_map = take((int64_t)L * 2);
+  h->off_spheres = take((int64_t)S * 16);
+  h->off_sph_link = take((int64_t)S * 2);
+  h->off_padding = take((int64_t)S * 4);
+  h->off_link_sph_off = take((int64_t)(nl + 1) * 2);
+  h->off_link_sph_idx = take((int64_t)S * 2);
+  h->off_level_off = take((int64_t)(nl + 1) * 2);  // sized for the worst case (n_levels <= nl)
+  h->off_level_links = take((int64_t)nl * 2);
+  h->off_anc_mask = take((int64_t)nl * 8);
+  h->off_jl_off = take((int64_t)(D + 1) * 2);
+  h->off_jl_idx = take((int64_t)nl * 2);
+  h->off_limits = take((int64_t)10 * D * 4);
+  h->smem_bytes = (int32_t)off;
+  h->off_pairs = take((int64_t)P * 4);
+  h->total_bytes = (int32_t)off;
+  (void)n_joint_links;
+  return off;
+}
+
+int64_t cb200_robot_blob_bytes(const cb200_robot_sizes *sz) {
+  BlobHeader h;
+  return blob_layout(sz, nullptr, &h, nullptr);
+}
+
+int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_sizes *sz, const float *fixed_transforms,
+                              const int16_t *link_map, const int16_t *joint_map, const int8_t *joint_map_type,
+                              const float *joint_offset_map, const int16_t *tool_frame_map, const float *link_spheres,
+                              const int16_t *link_sphere_map, const float *sphere_padding,
+                              const int16_t *collision_pairs, const float *position_limits,
+                              const float *velocity_limits, const float *acceleration_limits, const float *jerk_limits,
+                              const float *effort_limits) {
+  BlobHeader h;
+  const int64_t total = blob_layout(sz, link_map, &h, nullptr);
+  if (total < 0) return total;
+  if (out_bytes < total) return -3;
+  const int nl = h.nl, D = h.D, S = h.S, L = h.L, P = h.P;
+  unsigned char *o = static_cast<unsigned char *>(out);
+  memset(o, 0, (size_t)total);
+  memcpy(o, &h, sizeof(h));
+  memcpy(o + h.off_fixed, fixed_transforms, (size_t)nl * 48);
+  memcpy(o + h.off_joff, joint_offset_map, (size_t)nl * 8);
+  memcpy(o + h.off_link_map, link_map, (size_t)nl * 2);
+  memcpy(o + h.off_joint_map, joint_map, (size_t)nl * 2);
+  memcpy(o + h.off_joint_type, joint_map_type, (size_t)nl);
+  if (L) memcpy(o + h.off_tool_map, tool_frame_map, (size_t)L * 2);
+  for (int l = 0; l < nl; ++l) {
+    const int jt = joint_map_type[l];
+    if (jt < -1 || jt > 5) return -4;
+    if (jt >= 0 && (joint_map[l] < 0 || joint_map[l] >= D)) return -5;
+  }
+  for (int t = 0; t < L; ++t)
+    if (tool_frame_map[t] < 0 || tool_frame_map[t] >= nl) return -6;
+  if (S) {
+    memcpy(o + h.off_spheres, link_spheres, (size_t)S * 16);
+    memcpy(o + h.off_sph_link, link_sphere_map, (size_t)S * 2);
+    memcpy(o + h.off_padding, sphere_padding, (size_t)S * 4);
+  }
+  // CSR link -> spheres
+  int16_t *lso = reinterpret_cast<int16_t *>(o + h.off_link_sph_off);
+  int16_t *lsi = reinterpret_cast<int16_t *>(o + h.off_link_sph_idx);
+  int n = 0;
+  for (int l = 0; l < nl; ++l) {
+    lso[l] = (int16_t)n;
+    for (int s = 0; s < S; ++s) {
+      if (link_sphere_map[s] < 0 || link_sphere_map[s] >= nl) return -7;
+      if (link_sphere_map[s] == l) lsi[n++] = (int16_t)s;
+    }
+  }
+  lso[nl] = (int16_t)n;
+  // depth levels + ancestor masks
+  std::vector<int> depth(nl, 0);
+  unsigned long long *anc = reinterpret_cast<unsigned long long *>(o + h.off_anc_mask);
+  anc[0] = 1ull;
+  for (int l = 1; l < nl; ++l) {
+    depth[l] = depth[link_map[l]] + 1;
+    anc[l] = anc[link_map[l]] | (1ull << l);
+  }
+  int16_t *lvo = reinterpret_cast<int16_t *>(o + h.off_level_off);
+  int16_t *lvl = reinterpret_cast<int16_t *>(o + h.off_level_links);
+  n = 0;
+  for (int lev = 0; lev < h.n_levels; ++lev) {
+    lvo[lev] = (int16_t)n;
+    for (int l = 0; l < nl; ++l)
+      if (depth[l] == lev) lvl[n++] = (int16_t)l;
+  }
+  lvo[h.n_levels] = (int16_t)n;
+  // CSR joint -> links
+  int16_t *jlo = reinterpret_cast<int16_t *>(o + h.off_jl_off);
+  int16_t *jli = reinterpret_cast<int16_t *>(o + h.off_jl_idx);
+  n = 0;
+  for (int d = 0; d < D; ++d) {
+    jlo[d] = (int16_t)n;
+    for (int l = 0; l < nl; ++l)
+      if (joint_map_type[l] >= 0 && joint_map[l] == d) jli[n++] = (int16_t)l;
+  }
+  jlo[D] = (int16_t)n;
+  float *lim = reinterpret_cast<float *>(o + h.off_limits);
+  const float *srcs[5] = {position_limits, velocity_limits, acceleration_limits, jerk_limits, effort_limits};
+  for (int k = 0; k < 5; ++k)
+    for (int i = 0; i < 2 * D; ++i) lim[k * 2 * D + i] = srcs[k] ? srcs[k][i] : (i < D ? -1e30f : 1e30f);
+  for (int p = 0; p < P; ++p) {
+    const int i = collision_pairs[2 * p], j = collision_pairs[2 * p + 1];
+    if (i < 0 || j < 0 || i >= S || j >= S) return -8;
+  }
+  if (P) memcpy(o + h.off_pairs, collision_pairs, (size_t)P * 4);
+  return total;
+}
+
+int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io, cb200_stream_t stream) {
+  if (cfg == nullptr || io == nullptr || io->q == nullptr || io->robot_blob == nullptr || io->cost == nullptr ||
+      io->grad_q == nullptr || io->batch_size < 0 || io->horizon < 1)
+    return ret(cudaErrorInvalidValue);
+  if (cfg->use_sweep != 0) return ret(cudaErrorNotSupported);  // swept rollout: see cb200_rollout_traj (next)
+  if (io->goal_position != nullptr && (io->goal_quat == nullptr || cfg->num_goalset < 1)) return ret(cudaErrorInvalidValue);
+  const long long N = (long long)io->batch_size * io->horizon;
+  if (N == 0) return ret(cudaSuccess);
+  if (io->robot_blob_host == nullptr) return ret(cudaErrorInvalidValue);
+  BlobHeader cached_hdr;
+  memcpy(&cached_hdr, io->robot_blob_host, sizeof(BlobHeader));
+  if (cached_hdr.magic != kBlobMagic || cached_hdr.total_bytes != io->robot_blob_bytes) return ret(cudaErrorInvalidValue);
+  const BlobHeader &h = cached_hdr;
+  FusedArgs a{};
+  a.cfg = *cfg;
+  a.q = io->q;
+  a.vel = io->vel;
+  a.acc = io->acc;
+  a.jerk = io->jerk;
+  a.dt = io->dt;
+  a.blob = static_cast<const unsigned char *>(io->robot_blob);
+  a.cuboids = to_dev(io->cuboids);
+  a.voxels = to_dev(io->voxels);
+  a.env_query_idx = io->env_query_idx;
+  a.goal_position = io->goal_position;
+  a.goal_quat = io->goal_quat;
+  a.idxs_goal = io->idxs_goal;
+  a.pose_axes_t = io->pose_axes_terminal;
+  a.pose_axes_nt = io->pose_axes_non_terminal;
+  a.pose_tol_t = io->pose_tol_terminal;
+  a.pose_tol_nt = io->pose_tol_non_terminal;
+  a.cost = io->cost;
+  a.grad_q = io->grad_q;
+  a.self_cost = io->self_cost;
+  a.scene_cost = io->scene_cost;
+  a.pose_cost = io->pose_cost;
+  a.cspace_cost = io->cspace_cost;
+  a.grad_vel = io->grad_vel;
+  a.grad_acc = io->grad_acc;
+  a.grad_jerk = io->grad_jerk;
+  a.link_pos = io->link_pos;
+  a.link_quat = io->link_quat;
+  a.robot_spheres = io->robot_spheres;
+  a.pose_goalset_idx = io->pose_goalset_idx;
+  a.B = io->batch_size;
+  a.H = io->horizon;
+  a.blob_smem_bytes = h.smem_bytes;
+  a.eval_floats = eval_smem_floats(h.nl, h.D, h.S, h.L);
+  DevInfo &d = dev_info();
+  // warps per CTA: the count that keeps the most warps resident per SM (shared memory is the limiter for
+  // big robots); ties go to the larger CTA so the blob is staged fewer times.  Cached per blob geometry.
+  static thread_local int cached_key = -1, cached_nw = 0, cached_grid_per_sm = 0;
+  const int key = h.smem_bytes * 131 + a.eval_floats;
+  if (key != cached_key) {
+    const size_t max_need = (size_t)h.smem_bytes + (size_t)kWarpsPerCta * a.eval_floats * sizeof(float);
+    const size_t cap = std::min(max_need, (size_t)d.max_smem);
+    cudaError_t e = cudaFuncSetAttribute(rollout_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    if (e != cudaSuccess) return ret(e);
+    int best_nw = 0, best_warps = 0, best_per_sm = 0;
+    for (int nw = kWarpsPerCta; nw >= 1; --nw) {
+      const size_t need = (size_t)h.smem_bytes + (size_t)nw * a.eval_floats * sizeof(float);
+      if (need > (size_t)d.max_smem) continue;
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_fused_kernel, nw * 32, need) != cudaSuccess) continue;
+      if (per_sm * nw > best_warps) {
+        best_warps = per_sm * nw;
+        best_nw = nw;
+        best_per_sm = per_sm;
+      }
+    }
+    if (best_nw == 0) return ret(cudaErrorInvalidConfiguration);
+    cached_key = key;
+    cached_nw = best_nw;
+    cached_grid_per_sm = best_per_sm;
+  }
+  const int nw = cached_nw;
+  const size_t smem = (size_t)h.smem_bytes + (size_t)nw * a.eval_floats * sizeof(float);
+  long long grid_ll = (long long)d.sm_count * cached_grid_per_sm;
+  const long long need_ctas = (N + nw - 1) / nw;
+  if (grid_ll > need_ctas) grid_ll = need_ctas;
+  const int grid = (int)(grid_ll < 1 ? 1 : grid_ll);
+  rollout_fused_kernel<<<grid, nw * 32, smem, (cudaStream_t)stream>>>(a);
+  return launch_status();
+}
+
+}  // extern "C"

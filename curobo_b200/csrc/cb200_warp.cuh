@@ -1,0 +1,290 @@
+// cb200_warp.cuh -- warp-cooperative stages of one rollout evaluation (device only).
+//
+// One warp owns one (seed x waypoint) evaluation.  Its working set lives in a private slice of shared
+// memory (`EvalSmem`): the cumulative link transforms never leave the SM, sphere positions and sphere
+// gradients are produced and consumed in place, and the J^T backward runs on per-link force/torque
+// accumulators instead of walking a joint chain per sphere.
+#pragma once
+#include "cb200_blob.h"
+#include "cb200_math.cuh"
+
+namespace cb200 {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// View of the blob once it sits in shared memory (pointers into smem) + the pair list in global memory.
+struct RobotView {
+  int nl, D, S, L, P, n_levels;
+  const float *fixed;
+  const float *joff;
+  const int16_t *link_map;
+  const int16_t *joint_map;
+  const int8_t *joint_type;
+  const int16_t *tool_map;
+  const float4 *spheres;
+  const int16_t *sph_link;
+  const float *padding;
+  const int16_t *link_sph_off;
+  const int16_t *link_sph_idx;
+  const int16_t *level_off;
+  const int16_t *level_links;
+  const unsigned long long *anc_mask;
+  const int16_t *jl_off;
+  const int16_t *jl_idx;
+  const float *limits;
+  const uint32_t *pairs;  // global memory: one packed (i | j<<16) word per pair
+};
+
+__device__ __forceinline__ RobotView make_robot_view(const unsigned char *smem_blob, const unsigned char *gmem_blob) {
+  const BlobHeader *h = reinterpret_cast<const BlobHeader *>(smem_blob);
+  RobotView v;
+  v.nl = h->nl;
+  v.D = h->D;
+  v.S = h->S;
+  v.L = h->L;
+  v.P = h->P;
+  v.n_levels = h->n_levels;
+  v.fixed = reinterpret_cast<const float *>(smem_blob + h->off_fixed);
+  v.joff = reinterpret_cast<const float *>(smem_blob + h->off_joff);
+  v.link_map = reinterpret_cast<const int16_t *>(smem_blob + h->off_link_map);
+  v.joint_map = reinterpret_cast<const int16_t *>(smem_blob + h->off_joint_map);
+  v.joint_type = reinterpret_cast<const int8_t *>(smem_blob + h->off_joint_type);
+  v.tool_map = reinterpret_cast<const int16_t *>(smem_blob + h->off_tool_map);
+  v.spheres = reinterpret_cast<const float4 *>(smem_blob + h->off_spheres);
+  v.sph_link = reinterpret_cast<const int16_t *>(smem_blob + h->off_sph_link);
+  v.padding = reinterpret_cast<const float *>(smem_blob + h->off_padding);
+  v.link_sph_off = reinterpret_cast<const int16_t *>(smem_blob + h->off_link_sph_off);
+  v.link_sph_idx = reinterpret_cast<const int16_t *>(smem_blob + h->off_link_sph_idx);
+  v.level_off = reinterpret_cast<const int16_t *>(smem_blob + h->off_level_off);
+  v.level_links = reinterpret_cast<const int16_t *>(smem_blob + h->off_level_links);
+  v.anc_mask = reinterpret_cast<const unsigned long long *>(smem_blob + h->off_anc_mask);
+  v.jl_off = reinterpret_cast<const int16_t *>(smem_blob + h->off_jl_off);
+  v.jl_idx = reinterpret_cast<const int16_t *>(smem_blob + h->off_jl_idx);
+  v.limits = reinterpret_cast<const float *>(smem_blob + h->off_limits);
+  v.pairs = reinterpret_cast<const uint32_t *>(gmem_blob + h->off_pairs);
+  return v;
+}
+
+// Per-warp scratch (floats).  Layout computed identically on host (cb200_eval_smem_floats).
+struct EvalSmem {
+  float *cumul;   // [nl*12]
+  float4 *sph;    // [S] world spheres (x,y,z,r)
+  float4 *gsph;   // [S] padded spheres during self-collision, then sphere gradients
+  float *ft;      // [nl*8]  F.xyz,_ ,T.xyz,_   (torque about the link origin)
+  float *contrib; // [nl]
+  float *qv;      // [D]
+  float *gqv;     // [D]  c-space position gradient
+  float *pose_g;  // [L*8]  g_pos.xyz,_, omega.xyz,_
+};
+__host__ __device__ inline int eval_smem_floats(int nl, int D, int S, int L) {
+  int n = nl * 12 + S * 8 + nl * 8 + nl + D + D + L * 8;
+  return (n + 3) & ~3;
+}
+__device__ __forceinline__ EvalSmem carve_eval_smem(float *base, int nl, int D, int S, int L) {
+  EvalSmem e;
+  e.cumul = base;
+  e.sph = reinterpret_cast<float4 *>(base + nl * 12);
+  e.gsph = e.sph + S;
+  e.ft = base + nl * 12 + S * 8;
+  e.contrib = e.ft + nl * 8;
+  e.qv = e.contrib + nl;
+  e.gqv = e.qv + D;
+  e.pose_g = e.gqv + D;
+  return e;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// FK: local transforms (one lane per link) then level-synchronous chain compose
+// (12 lanes per link, two links per step).  cumul[l] = cumul[parent[l]] * local[l].
+// Reference semantics: kinematics_forward_helper.cuh:316-512.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es, int lane) {
+  for (int l = lane; l < rv.nl; l += 32) {
+    int jt = rv.joint_type[l];
+    float th = 0.0f;
+    if (jt >= 0) th = rv.joff[2 * l] * es.qv[rv.joint_map[l]] + rv.joff[2 * l + 1];
+    local_link_transform(rv.fixed + 12 * l, jt, th, es.cumul + 12 * l);
+  }
+  __syncwarp();
+  const int sub = lane >> 4, k = lane & 15;
+  const int r = k >> 2, c = k & 3;
+  for (int lev = 1; lev < rv.n_levels; ++lev) {
+    const int b = rv.level_off[lev], e = rv.level_off[lev + 1];
+    for (int i = b; i < e; i += 2) {
+      const bool act = (k < 12) && (i + sub < e);
+      float out = 0.0f;
+      int l = 0;
+      if (act) {
+        l = rv.level_links[i + sub];
+        const float *P = es.cumul + 12 * rv.link_map[l];
+        const float *Lm = es.cumul + 12 * l;
+        const float4 pr = *reinterpret_cast<const float4 *>(P + 4 * r);
+        out = pr.x * Lm[c] + pr.y * Lm[4 + c] + pr.z * Lm[8 + c] + (c == 3 ? pr.w : 0.0f);
+      }
+      __syncwarp();
+      if (act) es.cumul[12 * l + k] = out;
+      __syncwarp();
+    }
+  }
+}
+
+// Spheres: world position of every robot sphere; also the self-collision (padded radius) copy in gsph.
+// Reference: kinematics_forward_helper.cuh:218-254, kinematics_util.cuh:39-49.
+__device__ __forceinline__ void warp_spheres(const RobotView &rv, const EvalSmem &es, int lane, float4 *out_global) {
+  for (int s = lane; s < rv.S; s += 32) {
+    const float *T = es.cumul + 12 * rv.sph_link[s];
+    const float4 p = rv.spheres[s];
+    const float4 r0 = *reinterpret_cast<const float4 *>(T), r1 = *reinterpret_cast<const float4 *>(T + 4),
+                 r2 = *reinterpret_cast<const float4 *>(T + 8);
+    float4 w;
+    w.x = r0.x * p.x + r0.y * p.y + r0.z * p.z + r0.w;
+    w.y = r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w;
+    w.z = r2.x * p.x + r2.y * p.y + r2.z * p.z + r2.w;
+    w.w = p.w;
+    es.sph[s] = w;
+    if (out_global != nullptr) out_global[s] = w;
+    w.w = p.w + rv.padding[s];
+    es.gsph[s] = w;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Self collision over an explicit pair list: f = (ri+rj)^2 - |pi-pj|^2 (padded radii, both >= 0),
+// arg-max over pairs with f > 0, first pair wins ties.
+// Reference: self_collision_helper.cuh:61-71,227-277; collision_pair.cuh:55-57.
+// Returns f_max (0 if none) and the pair (i,j) to every lane.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_self_collision_pairs(const float4 *psph, const uint32_t *pairs, int P, int lane,
+                                                           int &bi, int &bj) {
+  float best = 0.0f;
+  uint32_t best_p = 0xffffffffu;
+  for (int p = lane; p < P; p += 32) {
+    const uint32_t pr = __ldg(pairs + p);
+    const float4 a = psph[pr & 0xffffu], b = psph[pr >> 16];
+    const float rs = a.w + b.w;
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    float f = rs * rs - (dx * dx + dy * dy + dz * dz);
+    if (!(a.w >= 0.0f && b.w >= 0.0f)) f = 0.0f;
+    if (f > best) {
+      best = f;
+      best_p = (uint32_t)p;
+    }
+  }
+  // positive floats order like their bit patterns
+  const uint32_t fb = __reduce_max_sync(kFull, __float_as_uint(best));
+  const uint32_t cand = (__float_as_uint(best) == fb && best > 0.0f) ? best_p : 0xffffffffu;
+  const uint32_t win = __reduce_min_sync(kFull, cand);
+  bi = bj = 0;
+  if (win == 0xffffffffu) return 0.0f;
+  const uint32_t pr = __ldg(pairs + win);
+  bi = (int)(pr & 0xffffu);
+  bj = (int)(pr >> 16);
+  return __uint_as_float(fb);
+}
+
+// ----------------------------------------------------------------------------------------------
+// J^T backward on link force/torque accumulators.
+//   per link k:    F_k = sum g_s ,  T_k = sum (p_s - o_k) x g_s   (+ tool-frame g_pos / omega)
+//   per joint link j: (F,T)_sub = sum over descendants k of shift_to_o_j(F_k, T_k)
+//   revolute: s * a_j . T_sub      prismatic: s * a_j . F_sub
+// Algebraically the reference's per-sphere chain walk (kinematics_backward_helper.cuh:15-183,
+// kinematics_joint_util.cuh:12-67): g.(a x (p-o_j)) = a.((p-o_j) x g).
+// gq_out[d] = gqv[d] + sum over links driven by joint d.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out) {
+  for (int k = lane; k < rv.nl; k += 32) {
+    const float *Tk = es.cumul + 12 * k;
+    const V3 o = mk3(Tk[3], Tk[7], Tk[11]);
+    V3 F = mk3(0, 0, 0), T = mk3(0, 0, 0);
+    for (int i = rv.link_sph_off[k]; i < rv.link_sph_off[k + 1]; ++i) {
+      const int s = rv.link_sph_idx[i];
+      const float4 g4 = es.gsph[s];
+      const V3 g = mk3(g4.x, g4.y, g4.z);
+      if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f) continue;
+      const float4 p4 = es.sph[s];
+      F = F + g;
+      T = T + cross(mk3(p4.x, p4.y, p4.z) - o, g);
+    }
+    for (int e = 0; e < rv.L; ++e) {
+      if (rv.tool_map[e] != k) continue;
+      F = F + mk3(es.pose_g[8 * e + 0], es.pose_g[8 * e + 1], es.pose_g[8 * e + 2]);
+      T = T + mk3(es.pose_g[8 * e + 4], es.pose_g[8 * e + 5], es.pose_g[8 * e + 6]);
+    }
+    float *ft = es.ft + 8 * k;
+    ft[0] = F.x;
+    ft[1] = F.y;
+    ft[2] = F.z;
+    ft[4] = T.x;
+    ft[5] = T.y;
+    ft[6] = T.z;
+  }
+  __syncwarp();
+  for (int j = lane; j < rv.nl; j += 32) {
+    const int jt = rv.joint_type[j];
+    float res = 0.0f;
+    if (jt >= 0) {
+      const float *Tj = es.cumul + 12 * j;
+      const V3 oj = mk3(Tj[3], Tj[7], Tj[11]);
+      V3 F = mk3(0, 0, 0), T = mk3(0, 0, 0);
+      for (int k = j; k < rv.nl; ++k) {
+        if (!((rv.anc_mask[k] >> j) & 1ull)) continue;
+        const float *ft = es.ft + 8 * k;
+        const V3 Fk = mk3(ft[0], ft[1], ft[2]);
+        const float *Tk = es.cumul + 12 * k;
+        const V3 ok = mk3(Tk[3], Tk[7], Tk[11]);
+        F = F + Fk;
+        T = T + mk3(ft[4], ft[5], ft[6]) + cross(ok - oj, Fk);
+      }
+      const int ax = (jt >= JT_XR) ? jt - JT_XR : jt;
+      const V3 a = mk3(Tj[ax], Tj[4 + ax], Tj[8 + ax]);
+      res = rv.joff[2 * j] * ((jt >= JT_XR) ? dot(a, T) : dot(a, F));
+    }
+    es.contrib[j] = res;
+  }
+  __syncwarp();
+  for (int d = lane; d < rv.D; d += 32) {
+    float g = es.gqv[d];
+    for (int i = rv.jl_off[d]; i < rv.jl_off[d + 1]; ++i) g += es.contrib[rv.jl_idx[i]];
+    gq_out[d] = g;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Bulk async copy (TMA 1-D) of the blob prefix into shared memory, completion on an mbarrier.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_blob_to_smem(unsigned char *dst, const unsigned char *src, uint32_t bytes,
+                                                   unsigned long long *mbar) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+  }
+  // every thread waits for phase 0 of the barrier
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(mbar))
+        : "memory");
+  }
+}
+
+}  // namespace cb200

@@ -1,0 +1,110 @@
+"""ctypes binding of libcurobo_b200.so (the C ABI in include/curobo_b200.h).
+
+There is NO fallback: if the library is missing it is built with nvcc; if that fails, import of any
+op raises.  Nothing here computes anything on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_LIB: Optional[C.CDLL] = None
+
+c_f = C.c_void_p      # device float*
+c_p = C.c_void_p
+
+
+class CuboidSet(C.Structure):
+    _fields_ = [("dims", C.c_void_p), ("inv_pose", C.c_void_p), ("enable", C.c_void_p), ("count", C.c_void_p),
+                ("max_n", C.c_int32), ("num_envs", C.c_int32)]
+
+
+class VoxelSet(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("inv_pose", C.c_void_p), ("enable", C.c_void_p), ("count", C.c_void_p),
+                ("features", C.c_void_p), ("n_voxels_per_layer", C.c_int32), ("max_n", C.c_int32),
+                ("num_envs", C.c_int32), ("max_dist", C.c_float)]
+
+
+class RobotSizes(C.Structure):
+    _fields_ = [("num_links", C.c_int32), ("num_dof", C.c_int32), ("num_spheres", C.c_int32),
+                ("num_tool_frames", C.c_int32), ("num_pairs", C.c_int32)]
+
+
+class RolloutCfg(C.Structure):
+    _fields_ = [("self_weight", C.c_float), ("scene_weight", C.c_float), ("scene_activation", C.c_float),
+                ("use_sweep", C.c_int32), ("use_speed_metric", C.c_int32), ("pose_weight", C.c_float * 2),
+                ("pose_rotation_method", C.c_int32), ("cspace_type", C.c_int32), ("cspace_weight", C.c_float * 5),
+                ("cspace_activation", C.c_float * 5), ("cspace_reg", C.c_float * 5), ("retime_weights", C.c_int32),
+                ("retime_regularization_weights", C.c_int32), ("num_goalset", C.c_int32)]
+
+
+class RolloutIO(C.Structure):
+    _fields_ = [("q", c_p), ("vel", c_p), ("acc", c_p), ("jerk", c_p), ("dt", c_p),
+                ("robot_blob", c_p), ("robot_blob_host", c_p), ("robot_blob_bytes", C.c_int32),
+                ("cuboids", C.POINTER(CuboidSet)), ("voxels", C.POINTER(VoxelSet)), ("env_query_idx", c_p),
+                ("goal_position", c_p), ("goal_quat", c_p), ("idxs_goal", c_p),
+                ("pose_axes_terminal", c_p), ("pose_axes_non_terminal", c_p),
+                ("pose_tol_terminal", c_p), ("pose_tol_non_terminal", c_p),
+                ("cost", c_p), ("grad_q", c_p), ("self_cost", c_p), ("scene_cost", c_p), ("pose_cost", c_p),
+                ("cspace_cost", c_p), ("grad_vel", c_p), ("grad_acc", c_p), ("grad_jerk", c_p),
+                ("link_pos", c_p), ("link_quat", c_p), ("robot_spheres", c_p), ("pose_goalset_idx", c_p),
+                ("batch_size", C.c_int32), ("horizon", C.c_int32)]
+
+
+_I = C.c_int
+_SIGS = {
+    "cb200_abi_version": ([], _I),
+    "cb200_sm_arch": ([], _I),
+    "cb200_error_string": ([_I], C.c_char_p),
+    "cb200_device_info": ([_I, C.POINTER(_I), C.POINTER(_I)], _I),
+    "cb200_kinematics_forward_spheres": ([c_p] * 16 + [_I] * 9 + [c_p], _I),
+    "cb200_kinematics_backward": ([c_p] * 22 + [_I] * 9 + [c_p], _I),
+    "cb200_self_collision_distance": ([c_p] * 10 + [_I] * 8 + [c_p], _I),
+    "cb200_sphere_obstacle_collision": ([c_p] * 3 + [C.POINTER(CuboidSet), C.POINTER(VoxelSet)] + [c_p] * 3 + [_I] * 4 + [c_p], _I),
+    "cb200_swept_sphere_obstacle_collision": ([c_p] * 3 + [C.POINTER(CuboidSet), C.POINTER(VoxelSet)] + [c_p] * 3 + [_I, c_p] + [_I] * 4 + [c_p], _I),
+    "cb200_tool_pose_distance": ([c_p] * 16 + [_I] * 5 + [c_p], _I),
+    "cb200_cspace_state_cost": ([c_p] * 25 + [_I] * 6 + [c_p], _I),
+    "cb200_cspace_position_cost": ([c_p] * 19 + [_I] * 4 + [c_p], _I),
+    "cb200_robot_blob_bytes": ([C.POINTER(RobotSizes)], C.c_int64),
+    "cb200_pack_robot_blob": ([c_p, C.c_int64, C.POINTER(RobotSizes)] + [c_p] * 15, C.c_int64),
+    "cb200_rollout_cost_grad": ([C.POINTER(RolloutCfg), C.POINTER(RolloutIO), c_p], _I),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS.keys())
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libcurobo_b200.so")
+
+
+def load() -> C.CDLL:
+    """Load (building first if absent) the native library and attach argtypes."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        from . import build
+        build.build_product()
+    lib = C.CDLL(path)
+    for name, (args, res) in _SIGS.items():
+        fn = getattr(lib, name)       # AttributeError if the symbol is missing: fail loudly
+        fn.argtypes = args
+        fn.restype = res
+    if lib.cb200_abi_version() != 1:
+        raise RuntimeError("libcurobo_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+class CudaCallError(RuntimeError):
+    pass
+
+
+def check(err: int, what: str) -> None:
+    """Error convention of the reference's launch_helper (cudaGetLastError -> log_and_raise,
+    curobo/_src/curobolib/backends/cuda_core_backend/launch_helper.py:13-19)."""
+    if err != 0:
+        msg = load().cb200_error_string(err)
+        raise CudaCallError(f"{what} failed: cudaError {err} ({msg.decode() if msg else '?'})")

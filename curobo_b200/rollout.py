@@ -1,0 +1,248 @@
+"""Host side of the fused rollout cost+gradient evaluation.
+
+`RolloutEngine.evaluate_action(q)` is what one optimizer iteration calls: it stands where the
+reference has  RobotRollout.evaluate_action -> RobotCostManager.compute_costs -> sum -> backward
+(curobo/_src/rollout/rollout_robot.py:252-263; rollout/cost_manager/cost_manager_robot.py:195-286;
+optim/components/gradient_opt_core.py:445-480) and returns the per-row cost and d(cost)/dq from ONE
+kernel launch.  All buffers are allocated once per (B, H) (reference ownership contract,
+cuda_ops/kinematics.py:27-90) so the call is CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .backends.tensor_checks import check_tensors, stream_ptr
+from .robot_model import RobotModel
+from .scene import CuboidData, VoxelData, c_cuboid_set, c_voxel_set
+
+
+@dataclass
+class RolloutConfig:
+    """Weights/switches of the cost terms (value semantics; a zero weight disables the term)."""
+    self_weight: float = 0.0
+    scene_weight: float = 0.0
+    scene_activation: float = 0.0
+    use_sweep: bool = False
+    use_speed_metric: bool = False
+    pose_weight: Optional[Sequence[float]] = None        # (position, rotation)
+    pose_lie: bool = False
+    cspace_type: Optional[str] = None                    # None | "position" | "state"
+    cspace_weight: Sequence[float] = (0.0,) * 5
+    cspace_activation: Sequence[float] = (0.0,) * 5
+    cspace_reg: Sequence[float] = (0.0,) * 5
+    retime_weights: bool = True
+    retime_reg: bool = True
+
+    # shipped task configs of the reference -------------------------------------------------
+    @classmethod
+    def ik(cls) -> "RolloutConfig":
+        """content/configs/task/ik/lbfgs_ik.yml:4-37."""
+        return cls(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.0, pose_weight=(10000.0, 500.0),
+                   cspace_type="position", cspace_weight=(5000.0, 1000.0, 0, 0, 0),
+                   cspace_activation=(0.01, 0.01, 0, 0, 0))
+
+    @classmethod
+    def trajopt(cls) -> "RolloutConfig":
+        """content/configs/task/trajopt/lbfgs_bspline_trajopt.yml:40-90."""
+        return cls(self_weight=10000.0, scene_weight=100000.0, scene_activation=0.0025, use_sweep=True,
+                   use_speed_metric=True, pose_weight=(1000000.0, 100000.0), cspace_type="state",
+                   cspace_weight=(10000.0, 10000.0, 100.0, 50.0, 100.0), cspace_activation=(0.01,) * 5,
+                   cspace_reg=(1000.0, 10000.0, 5.0, 0.0, 10000.0))
+
+    def to_oracle_cfg(self, num_tool_frames: int) -> dict:
+        d = dict(self_weight=self.self_weight, scene_weight=self.scene_weight, scene_eta=self.scene_activation,
+                 sweep=self.use_sweep, speed_metric=self.use_speed_metric, pose_lie=self.pose_lie,
+                 cspace_type=self.cspace_type, cspace_weight=list(self.cspace_weight),
+                 cspace_activation=list(self.cspace_activation), cspace_reg=list(self.cspace_reg),
+                 retime_weights=self.retime_weights, retime_reg=self.retime_reg)
+        if self.pose_weight is not None:
+            d["pose_weight"] = list(self.pose_weight)
+        return d
+
+
+@dataclass
+class RolloutOutput:
+    cost: torch.Tensor                 # [B,H] sum of all terms per row
+    grad_q: torch.Tensor               # [B,H,D]
+    self_cost: torch.Tensor            # [B,H]
+    scene_cost: torch.Tensor           # [B,H,S]
+    pose_cost: torch.Tensor            # [B,H,2L]
+    cspace_cost: torch.Tensor          # [B,H,D]
+    grad_vel: Optional[torch.Tensor] = None
+    grad_acc: Optional[torch.Tensor] = None
+    grad_jerk: Optional[torch.Tensor] = None
+    link_pos: Optional[torch.Tensor] = None
+    link_quat: Optional[torch.Tensor] = None
+    robot_spheres: Optional[torch.Tensor] = None
+    pose_goalset_idx: Optional[torch.Tensor] = None
+
+
+def pack_robot_blob(rm: RobotModel) -> np.ndarray:
+    """Robot constants -> one byte blob (layout: curobo_b200/csrc/cb200_blob.h), packed by the C helper."""
+    L = _lib.load()
+    sz = _lib.RobotSizes(rm.num_links, rm.num_dof, rm.num_spheres, rm.num_tool_frames, int(rm.collision_pairs.shape[0]))
+    nbytes = L.cb200_robot_blob_bytes(C.byref(sz))
+    if nbytes <= 0:
+        raise ValueError(f"robot does not fit the blob format (code {nbytes}); links <= 64 required")
+    out = np.zeros(nbytes, np.uint8)
+
+    def p(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+    keep = []
+    ls = rm.link_spheres if rm.link_spheres.ndim == 2 else rm.link_spheres[0]
+    n = L.cb200_pack_robot_blob(
+        out.ctypes.data, nbytes, C.byref(sz), p(rm.fixed_transforms, np.float32), p(rm.link_map, np.int16),
+        p(rm.joint_map, np.int16), p(rm.joint_map_type, np.int8), p(rm.joint_offset_map, np.float32),
+        p(rm.tool_frame_map, np.int16), p(ls, np.float32), p(rm.link_sphere_idx_map, np.int16),
+        p(rm.sphere_padding, np.float32), p(rm.collision_pairs, np.int16), p(rm.position_limits, np.float32),
+        p(rm.velocity_limits, np.float32), p(rm.acceleration_limits, np.float32), p(rm.jerk_limits, np.float32),
+        p(rm.effort_limits, np.float32))
+    if n <= 0:
+        raise ValueError(f"cb200_pack_robot_blob rejected the robot model (code {n})")
+    return out[:n]
+
+
+class RolloutEngine:
+    def __init__(self, robot: RobotModel, cfg: RolloutConfig, device="cuda:0",
+                 cuboid: Optional[CuboidData] = None, voxel: Optional[VoxelData] = None,
+                 store_fk_outputs: bool = False):
+        self.robot, self.cfg, self.device = robot, cfg, torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("RolloutEngine is CUDA-only (sm_100a); there is no CPU path")
+        self._lib = _lib.load()
+        self._blob_host = pack_robot_blob(robot)
+        self._blob = torch.from_numpy(self._blob_host.copy()).to(self.device)
+        self.cuboid, self.voxel = cuboid, voxel
+        self._cs = c_cuboid_set(cuboid, self.device)
+        self._vs = c_voxel_set(voxel, self.device)
+        self.store_fk_outputs = store_fk_outputs
+        self._B = self._H = -1
+        self._goal = None
+        self._ccfg = self._make_ccfg(1)
+
+    # -- configuration ------------------------------------------------------------------------
+    def _make_ccfg(self, num_goalset: int) -> _lib.RolloutCfg:
+        c = self.cfg
+        cc = _lib.RolloutCfg()
+        cc.self_weight, cc.scene_weight, cc.scene_activation = c.self_weight, c.scene_weight, c.scene_activation
+        cc.use_sweep, cc.use_speed_metric = int(c.use_sweep), int(c.use_speed_metric)
+        pw = c.pose_weight if c.pose_weight is not None else (0.0, 0.0)
+        cc.pose_weight[0], cc.pose_weight[1] = float(pw[0]), float(pw[1])
+        cc.pose_rotation_method = 1 if c.pose_lie else 0
+        cc.cspace_type = {None: 0, "position": 1, "state": 2}[c.cspace_type]
+        for i in range(5):
+            cc.cspace_weight[i] = float(c.cspace_weight[i]) if i < len(c.cspace_weight) else 0.0
+            cc.cspace_activation[i] = float(c.cspace_activation[i]) if i < len(c.cspace_activation) else 0.0
+            cc.cspace_reg[i] = float(c.cspace_reg[i]) if i < len(c.cspace_reg) else 0.0
+        cc.retime_weights, cc.retime_regularization_weights = int(c.retime_weights), int(c.retime_reg)
+        cc.num_goalset = num_goalset
+        return cc
+
+    def setup_batch_tensors(self, batch: int, horizon: int) -> None:
+        """Allocate every output once per (B, H) -- never inside evaluate_action."""
+        rm, dev = self.robot, self.device
+        z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
+        D, S, Lt = rm.num_dof, rm.num_spheres, rm.num_tool_frames
+        self.out = RolloutOutput(cost=z(batch, horizon), grad_q=z(batch, horizon, D), self_cost=z(batch, horizon),
+                                 scene_cost=z(batch, horizon, S), pose_cost=z(batch, horizon, 2 * Lt),
+                                 cspace_cost=z(batch, horizon, D))
+        if self.cfg.cspace_type == "state":
+            self.out.grad_vel, self.out.grad_acc, self.out.grad_jerk = (z(batch, horizon, D) for _ in range(3))
+        if self.store_fk_outputs:
+            self.out.link_pos, self.out.link_quat = z(batch, horizon, Lt, 3), z(batch, horizon, Lt, 4)
+            self.out.robot_spheres = z(batch, horizon, S, 4)
+            self.out.pose_goalset_idx = z(batch, horizon, Lt, dt=torch.int32)
+        self._B, self._H = batch, horizon
+
+    def update_goal(self, goal_position: torch.Tensor, goal_quat: torch.Tensor, idxs_goal: torch.Tensor,
+                    terminal_axes=None, non_terminal_axes=None, terminal_tol=None, non_terminal_tol=None) -> None:
+        """goal_* [G, L, n_goalset, 3|4] (quat wxyz), idxs_goal [B] int32 (GoalRegistry rows)."""
+        dev = self.device
+        check_tensors(dev, torch.float32, goal_position=goal_position, goal_quat=goal_quat)
+        check_tensors(dev, torch.int32, idxs_goal=idxs_goal)
+        Lt = self.robot.num_tool_frames
+        if goal_position.ndim != 4 or goal_position.shape[1] != Lt or goal_quat.shape[:3] != goal_position.shape[:3]:
+            raise ValueError("goal tensors must be [G, num_tool_frames, n_goalset, 3|4]")
+        extra = {}
+        for name, t, shape in (("terminal_axes", terminal_axes, (Lt, 6)), ("non_terminal_axes", non_terminal_axes, (Lt, 6)),
+                               ("terminal_tol", terminal_tol, (Lt, 2)), ("non_terminal_tol", non_terminal_tol, (Lt, 2))):
+            if t is not None:
+                check_tensors(dev, torch.float32, **{name: t})
+                if tuple(t.shape) != shape:
+                    raise ValueError(f"{name} must have shape {shape}")
+            extra[name] = t
+        self._goal = (goal_position, goal_quat, idxs_goal, extra)
+        self._ccfg = self._make_ccfg(int(goal_position.shape[2]))
+
+    # -- the hot call --------------------------------------------------------------------------
+    def evaluate_action(self, q: torch.Tensor, vel=None, acc=None, jerk=None, dt=None,
+                        env_query_idx: Optional[torch.Tensor] = None) -> RolloutOutput:
+        if q.ndim != 3 or q.shape[2] != self.robot.num_dof:
+            raise ValueError(f"q must be [B, H, {self.robot.num_dof}], got {tuple(q.shape)}")
+        B, H, _ = q.shape
+        if (B, H) != (self._B, self._H):
+            self.setup_batch_tensors(B, H)
+        dev = self.device
+        check_tensors(dev, torch.float32, q=q)
+        o = self.out
+        io = _lib.RolloutIO()
+        io.q = q.data_ptr()
+        for name, t in (("vel", vel), ("acc", acc), ("jerk", jerk), ("dt", dt)):
+            if t is not None:
+                check_tensors(dev, torch.float32, **{name: t})
+                setattr(io, name, t.data_ptr())
+        io.robot_blob, io.robot_blob_host = self._blob.data_ptr(), self._blob_host.ctypes.data
+        io.robot_blob_bytes = int(self._blob_host.shape[0])
+        if self._cs is not None:
+            io.cuboids = C.pointer(self._cs)
+        if self._vs is not None:
+            io.voxels = C.pointer(self._vs)
+        if env_query_idx is not None:
+            check_tensors(dev, torch.int32, env_query_idx=env_query_idx)
+            io.env_query_idx = env_query_idx.data_ptr()
+        if self._goal is not None and self.cfg.pose_weight is not None:
+            gp, gq, ig, extra = self._goal
+            if ig.shape[0] != B:
+                raise ValueError("idxs_goal must have one entry per batch row")
+            io.goal_position, io.goal_quat, io.idxs_goal = gp.data_ptr(), gq.data_ptr(), ig.data_ptr()
+            for cname, key in (("pose_axes_terminal", "terminal_axes"), ("pose_axes_non_terminal", "non_terminal_axes"),
+                               ("pose_tol_terminal", "terminal_tol"), ("pose_tol_non_terminal", "non_terminal_tol")):
+                if extra[key] is not None:
+                    setattr(io, cname, extra[key].data_ptr())
+        io.cost, io.grad_q = o.cost.data_ptr(), o.grad_q.data_ptr()
+        io.self_cost, io.scene_cost = o.self_cost.data_ptr(), o.scene_cost.data_ptr()
+        io.pose_cost, io.cspace_cost = o.pose_cost.data_ptr(), o.cspace_cost.data_ptr()
+        for name in ("grad_vel", "grad_acc", "grad_jerk", "link_pos", "link_quat", "robot_spheres", "pose_goalset_idx"):
+            t = getattr(o, name)
+            if t is not None:
+                setattr(io, name, t.data_ptr())
+        io.batch_size, io.horizon = B, H
+        err = self._lib.cb200_rollout_cost_grad(C.byref(self._ccfg), C.byref(io), stream_ptr(dev))
+        _lib.check(err, "rollout_cost_grad")
+        return o
+
+
+class FusedRolloutFunction(torch.autograd.Function):
+    """cost[B] = sum_h rollout cost; backward returns the gradient computed in the same launch
+    (the reference's own pattern: forward writes the gradient buffer, backward hands it out,
+    cuda_ops/geometry.py:95-104, wp_autograd.py:103-110; upstream gradient is all-ones,
+    gradient_opt_core.py:478)."""
+
+    @staticmethod
+    def forward(ctx, q: torch.Tensor, engine: RolloutEngine):
+        out = engine.evaluate_action(q.detach())
+        ctx.save_for_backward(out.grad_q)
+        return out.cost.sum(dim=1)
+
+    @staticmethod
+    def backward(ctx, grad_cost):
+        (g,) = ctx.saved_tensors
+        return g, None

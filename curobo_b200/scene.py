@@ -1,0 +1,182 @@
+"""Scene-collision operators on device tensors (drop-in at the autograd level).
+
+The reference has no backend switch here (Warp kernels are launched from the autograd Functions,
+curobo/_src/geom/collision/wp_autograd.py:37-247), so the drop-in is the Function pair below with the
+reference's own signatures.  Obstacle holders are duck-typed on the reference's attribute names
+(`CuboidData`: dims/inv_pose/enable/count/max_n/num_envs, geom/data/data_cuboid.py:43-110;
+ `VoxelData`:  params/inv_pose/enable/count/features/max_n/num_envs/max_esdf_distance,
+ geom/data/data_voxel.py:41-92) so a reference `SceneData` can be passed directly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import lib as _lib
+from .backends.tensor_checks import check_tensors, stream_ptr
+from .world import CuboidWorld, VoxelWorld
+
+
+@dataclass
+class CuboidData:
+    dims: torch.Tensor
+    inv_pose: torch.Tensor
+    enable: torch.Tensor
+    count: torch.Tensor
+    max_n: int
+    num_envs: int
+
+    @classmethod
+    def from_world(cls, w: CuboidWorld, device) -> "CuboidData":
+        t = lambda a: torch.as_tensor(a).to(device).contiguous()  # noqa: E731
+        return cls(t(w.dims), t(w.inv_pose), t(w.enable), t(w.count), w.max_n, w.num_envs)
+
+
+@dataclass
+class VoxelData:
+    params: torch.Tensor
+    inv_pose: torch.Tensor
+    enable: torch.Tensor
+    count: torch.Tensor
+    features: torch.Tensor        # fp16 [n_env, max_n, n_vox(,1)]
+    max_n: int
+    num_envs: int
+    max_esdf_distance: float
+
+    @classmethod
+    def from_world(cls, w: VoxelWorld, device) -> "VoxelData":
+        t = lambda a: torch.as_tensor(a).to(device).contiguous()  # noqa: E731
+        return cls(t(w.params), t(w.inv_pose), t(w.enable), t(w.count), t(w.features), w.max_n, w.num_envs,
+                   float(w.max_dist))
+
+
+@dataclass
+class SceneData:
+    cuboid: Optional[CuboidData] = None
+    voxel: Optional[VoxelData] = None
+
+    def get_valid_data(self) -> List[object]:
+        return [d for d in (self.cuboid, self.voxel) if d is not None]
+
+
+@dataclass
+class CollisionBuffer:
+    """distance [B,H,S] + gradient [B,H,S,4] (curobo/_src/geom/collision/buffer_collision.py:24-98)."""
+    distance: torch.Tensor
+    gradient: torch.Tensor
+
+    @classmethod
+    def from_shape(cls, shape, device) -> "CollisionBuffer":
+        b, h, n, _ = shape
+        return cls(torch.zeros((b, h, n), dtype=torch.float32, device=device),
+                   torch.zeros((b, h, n, 4), dtype=torch.float32, device=device))
+
+
+def _split_scene(scene):
+    cub = vox = None
+    for d in scene.get_valid_data():
+        if hasattr(d, "features"):
+            vox = d
+        elif hasattr(d, "dims"):
+            cub = d
+        else:
+            raise ValueError("b200 scene collision supports cuboid and voxel (ESDF) obstacles; mesh is out of scope")
+    return cub, vox
+
+
+def c_cuboid_set(d: Optional[object], dev=None) -> Optional[_lib.CuboidSet]:
+    if d is None:
+        return None
+    if dev is not None:
+        check_tensors(dev, torch.float32, cuboid_dims=d.dims, cuboid_inv_pose=d.inv_pose)
+        check_tensors(dev, torch.uint8, cuboid_enable=d.enable)
+        check_tensors(dev, torch.int32, cuboid_count=d.count)
+    return _lib.CuboidSet(d.dims.data_ptr(), d.inv_pose.data_ptr(), d.enable.data_ptr(), d.count.data_ptr(),
+                          int(d.max_n), int(d.num_envs))
+
+
+def c_voxel_set(d: Optional[object], dev=None) -> Optional[_lib.VoxelSet]:
+    if d is None:
+        return None
+    if dev is not None:
+        check_tensors(dev, torch.float32, voxel_params=d.params, voxel_inv_pose=d.inv_pose)
+        check_tensors(dev, torch.float16, voxel_features=d.features)
+        check_tensors(dev, torch.uint8, voxel_enable=d.enable)
+        check_tensors(dev, torch.int32, voxel_count=d.count)
+    n_vox = int(d.features.shape[2])
+    return _lib.VoxelSet(d.params.data_ptr(), d.inv_pose.data_ptr(), d.enable.data_ptr(), d.count.data_ptr(),
+                         d.features.data_ptr(), n_vox, int(d.max_n), int(d.num_envs), float(d.max_esdf_distance))
+
+
+def _launch(sweep, query_spheres, buffer, scene, weight, activation_distance, speed_dt, enable_speed_metric,
+            env_query_idx, use_multi_env):
+    dev = query_spheres.device
+    b, h, n, _ = query_spheres.shape
+    check_tensors(dev, torch.float32, query_spheres=query_spheres, distance=buffer.distance,
+                  gradient=buffer.gradient, weight=weight, activation_distance=activation_distance)
+    cub, vox = _split_scene(scene)
+    cs, vs = c_cuboid_set(cub, dev), c_voxel_set(vox, dev)
+    cp = C.byref(cs) if cs is not None else None
+    vp = C.byref(vs) if vs is not None else None
+    eq = None
+    if env_query_idx is not None:
+        check_tensors(dev, torch.int32, env_query_idx=env_query_idx)
+        eq = env_query_idx.data_ptr()
+    L = _lib.load()
+    if not sweep:
+        err = L.cb200_sphere_obstacle_collision(
+            buffer.distance.data_ptr(), buffer.gradient.data_ptr(), query_spheres.data_ptr(), cp, vp,
+            weight.data_ptr(), activation_distance.data_ptr(), eq, b, h, n, int(bool(use_multi_env)), stream_ptr(dev))
+    else:
+        if enable_speed_metric:
+            check_tensors(dev, torch.float32, speed_dt=speed_dt)
+        err = L.cb200_swept_sphere_obstacle_collision(
+            buffer.distance.data_ptr(), buffer.gradient.data_ptr(), query_spheres.data_ptr(), cp, vp,
+            weight.data_ptr(), activation_distance.data_ptr(), speed_dt.data_ptr() if speed_dt is not None else None,
+            int(bool(enable_speed_metric)), eq, b, h, n, int(bool(use_multi_env)), stream_ptr(dev))
+    _lib.check(err, "sphere_obstacle_collision")
+
+
+class SphereObstacleCollision(torch.autograd.Function):
+    """Same call signature as curobo/_src/geom/collision/wp_autograd.py:37-121."""
+
+    @staticmethod
+    def forward(ctx, query_spheres, buffer, scene, weight, activation_distance, max_distance, env_query_idx,
+                use_multi_env, return_loss=False):
+        _launch(False, query_spheres.detach(), buffer, scene, weight, activation_distance, None, False,
+                env_query_idx, use_multi_env)
+        ctx.return_loss = return_loss
+        ctx.save_for_backward(buffer.gradient)
+        return buffer.distance
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad_sph = None
+        if ctx.needs_input_grad[0]:
+            (g,) = ctx.saved_tensors
+            grad_sph = g * grad_output.unsqueeze(-1) if ctx.return_loss else g
+        return grad_sph, None, None, None, None, None, None, None, None
+
+
+class SweptSphereObstacleCollision(torch.autograd.Function):
+    """Same call signature as curobo/_src/geom/collision/wp_autograd.py:124-247."""
+
+    @staticmethod
+    def forward(ctx, query_spheres, buffer, scene, weight, activation_distance, max_distance, speed_dt,
+                enable_speed_metric, env_query_idx, use_multi_env, return_loss=False):
+        _launch(True, query_spheres.detach(), buffer, scene, weight, activation_distance, speed_dt,
+                enable_speed_metric, env_query_idx, use_multi_env)
+        ctx.return_loss = return_loss
+        ctx.save_for_backward(buffer.gradient)
+        return buffer.distance
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad_sph = None
+        if ctx.needs_input_grad[0]:
+            (g,) = ctx.saved_tensors
+            grad_sph = g * grad_output.unsqueeze(-1) if ctx.return_loss else g
+        return grad_sph, None, None, None, None, None, None, None, None, None, None

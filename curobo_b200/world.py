@@ -145,3 +145,24 @@ def make_benchmark_cuboid_world(max_n: int = 10) -> CuboidWorld:
         {"dims": [2.2, 2.2, 0.2], "pose": [0.0, 0.0, -0.1, 1, 0, 0, 0]},
         {"dims": [0.1, 0.1, 1.5], "pose": [0.45, 0.0, 0.3, 1, 0, 0, 0]},
     ], max_n=max_n)
+
+
+def make_single_box_esdf(grid_dims=(0.5, 0.5, 0.5), voxel_size=0.02, grid_center=(0.0, 0.0, 0.0),
+                         box_center=(0.0, 0.0, 0.0), box_half=(0.05, 0.05, 0.05), max_dist: float = 100.0) -> VoxelWorld:
+    """The reference's own test ESDF (tests/_src/geom/sdf/test_voxel_collision.py:403-440)."""
+    n = [int(round(d / voxel_size)) for d in grid_dims]
+    ax = [grid_center[a] + (np.arange(n[a], dtype=np.float32) - (n[a] - 1) / 2.0) * voxel_size for a in range(3)]
+    gx, gy, gz = np.meshgrid(*ax, indexing="ij")
+    d = [np.abs(g - box_center[a]) - box_half[a] for a, g in enumerate((gx, gy, gz))]
+    out = np.sqrt(sum(np.maximum(x, 0) ** 2 for x in d))
+    ins = np.minimum(np.maximum(np.maximum(d[0], d[1]), d[2]), 0)
+    return VoxelWorld.from_grid((out + ins).astype(np.float16), voxel_size,
+                                pose=[grid_center[0], grid_center[1], grid_center[2], 1, 0, 0, 0], max_dist=max_dist)
+
+
+def make_empty_esdf(dims=(0.5, 0.5, 0.5), voxel_size=0.02, center=(0.0, 0.0, 0.0), fill_value=1.0,
+                    max_dist: float = 100.0) -> VoxelWorld:
+    """All-free-space grid (tests/_src/geom/sdf/test_voxel_collision.py:381-400)."""
+    n = [int(round(d / voxel_size)) for d in dims]
+    return VoxelWorld.from_grid(np.full(n, fill_value, np.float16), voxel_size,
+                                pose=[center[0], center[1], center[2], 1, 0, 0, 0], max_dist=max_dist)

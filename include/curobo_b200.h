@@ -1,0 +1,268 @@
+/*
+ * curobo_b200.h  --  C ABI of libcurobo_b200.so: the sm_100a rollout cost+gradient hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes raw DEVICE pointers,
+ * plain ints/floats and the CUDA stream to launch on, returns a cudaError_t (0 = success) and
+ * never allocates, synchronises or touches the default stream -- exactly what the reference's
+ * `cuda_core` backend passes to its NVRTC kernels (`tensor.data_ptr()` ints + scalars on
+ * `torch.cuda.current_stream`, curobo/_src/curobolib/backends/cuda_core_backend/kinematics.py:130-176),
+ * so the calls are CUDA-graph capturable like the reference's (util/cuda_graph_util.py:101-175).
+ *
+ * Each function names the reference interface it replaces (file:line, relative to the reference
+ * root).  Argument ORDER follows the reference launcher so a binding is a 1:1 forward
+ * (see INTEGRATION.md for the ctypes stub a curobo maintainer would add).
+ *
+ * All tensors are contiguous, float = IEEE fp32, layouts as in the reference:
+ *   q [B*H, D]; link_pos [B*H, L, 3]; link_quat [B*H, L, 4] (w,x,y,z; w >= 0);
+ *   robot_spheres [B*H, S, 4] (x,y,z,r); cumul_mat [B*H, nl, 3, 4] row-major.
+ */
+#ifndef CUROBO_B200_H
+#define CUROBO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *cb200_stream_t; /* == cudaStream_t */
+
+#define CB200_ABI_VERSION 1
+
+/* Library / build identity.  cb200_abi_version() == CB200_ABI_VERSION; cb200_sm_arch() == 100. */
+int cb200_abi_version(void);
+int cb200_sm_arch(void);
+/* Human-readable string for the last non-zero return code of this thread (cudaGetErrorString). */
+const char *cb200_error_string(int err);
+
+/* -------------------------------------------------------------------------------------------
+ * (a2) FK + robot spheres + tool poses.
+ * Replaces launch_kinematics_forward_spheres
+ *   curobo/_src/curobolib/backends/cuda_core_backend/kinematics.py:90-177
+ *   (kernel kinematics_forward_spheres_kernel, kernels/kinematics/kinematics_forward_kernel.cuh:131-261).
+ * batch_size is B*H (cuda_ops/kinematics.py:115).  env_query_idx [B] selects the sphere set
+ * robot_spheres[num_envs, S, 4] for batch row n via env_query_idx[n / horizon] when num_envs > 1.
+ * batch_center_of_mass / link_masses_com are accepted for signature parity; compute_com must be 0.
+ * global_cumul_mat is written iff write_global_cumul != 0.
+ * ------------------------------------------------------------------------------------------- */
+int cb200_kinematics_forward_spheres(
+    float *link_pos, float *link_quat, float *batch_robot_spheres, float *batch_center_of_mass,
+    float *global_cumul_mat, const float *joint_vec, const float *fixed_transform,
+    const float *robot_spheres, const float *link_masses_com, const int8_t *joint_map_type,
+    const int16_t *joint_map, const int16_t *link_map, const int16_t *tool_frame_map,
+    const int16_t *link_sphere_map, const float *joint_offset_map, const int32_t *env_query_idx,
+    int num_envs, int batch_size, int horizon, int n_joints, int num_spheres, int num_links,
+    int n_tool_frames, int write_global_cumul, int compute_com, cb200_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * (a4) FK backward: grad_out[B*H, D] = sum_spheres J^T g + sum_tool_frames J^T (g_pos, omega(g_quat)).
+ * Replaces launch_kinematics_backward
+ *   curobo/_src/curobolib/backends/cuda_core_backend/kinematics.py:282-379
+ *   (kernel kinematics_backward_kernel, kernels/kinematics/kinematics_backward_kernel.cuh:34-160).
+ * link_chain_*, joint_links_*, joint_affects_endeffector are accepted for signature parity (the tree
+ * is re-derived from link_map).  compute_com and compute_jacobian_grad must be 0.
+ * ------------------------------------------------------------------------------------------- */
+int cb200_kinematics_backward(
+    float *grad_out, const float *grad_nlinks_pos, const float *grad_nlinks_quat,
+    const float *grad_spheres, const float *grad_center_of_mass, const float *batch_center_of_mass,
+    const float *grad_jacobian, const float *global_cumul_mat, const float *robot_spheres,
+    const float *link_masses_com, const int16_t *link_map, const int16_t *joint_map,
+    const int8_t *joint_map_type, const int16_t *tool_frame_map, const int16_t *link_sphere_map,
+    const int16_t *link_chain_data, const int16_t *link_chain_offsets, const int16_t *joint_links_data,
+    const int16_t *joint_links_offsets, const uint8_t *joint_affects_endeffector,
+    const float *joint_offset_map, const int32_t *env_query_idx, int num_envs, int batch_size,
+    int horizon, int n_joints, int num_spheres, int num_links, int n_tool_frames, int compute_com,
+    int compute_jacobian_grad, cb200_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * (a7) Self-collision: worst sphere pair, cost 0.5*w*f_max, gradient on the two spheres of that pair.
+ * Replaces self_collision_distance
+ *   curobo/_src/curobolib/backends/cuda_core_backend/geometry.py:63-227
+ *   (kernels self_collision_max_distance_kernel / max_block / max_reduce,
+ *    kernels/geometry/self_collision/self_collision_kernel.cuh:20-303).
+ * One launch for any pair count (the 2-kernel map-reduce of the reference collapses into one kernel;
+ * block_batch_max_* are accepted and left untouched).  out_vec rows are lazily zeroed through
+ * sparse_index exactly like the reference (self_collision_helper.cuh:151-192).
+ * ------------------------------------------------------------------------------------------- */
+int cb200_self_collision_distance(
+    float *out_distance, float *out_vec, float *pair_distance, uint8_t *sparse_index,
+    const float *robot_spheres, const float *sphere_padding, const float *weight,
+    const int16_t *pair_locations, float *block_batch_max_value, int16_t *block_batch_max_index,
+    int num_blocks_per_batch, int max_threads_per_block, int batch_size, int horizon, int nspheres,
+    int num_collision_pairs, int store_pair_distance, int compute_grad, cb200_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Obstacle sets, passed by value.  Tensor layouts are the reference's CuboidData / VoxelData
+ * (geom/data/data_cuboid.py:43-110, geom/data/data_voxel.py:41-92); a null `inv_pose` = absent.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float *dims;       /* [n_env, max_n, 4] full extents */
+  const float *inv_pose;   /* [n_env, max_n, 8] x,y,z,qw,qx,qy,qz,pad (world -> obstacle) */
+  const uint8_t *enable;   /* [n_env, max_n] */
+  const int32_t *count;    /* [n_env] */
+  int32_t max_n;
+  int32_t num_envs;
+} cb200_cuboid_set;
+
+typedef struct {
+  const float *params;     /* [n_env, max_n, 4] nx,ny,nz,voxel_size */
+  const float *inv_pose;   /* [n_env, max_n, 8] */
+  const uint8_t *enable;   /* [n_env, max_n] */
+  const int32_t *count;    /* [n_env] */
+  const uint16_t *features; /* [n_env, max_n, n_voxels_per_layer] IEEE fp16, C order (z fastest) */
+  int32_t n_voxels_per_layer;
+  int32_t max_n;
+  int32_t num_envs;
+  float max_dist;
+} cb200_voxel_set;
+
+/* -------------------------------------------------------------------------------------------
+ * (a8-a11) sphere vs scene, discrete.  distance [B,H,S], gradient [B,H,S,4] are OVERWRITTEN
+ * (the reference zeroes the buffer and atomically accumulates one launch per obstacle type;
+ * here one thread owns a sphere and loops over every obstacle of every type: same sum, no atomics).
+ * Replaces SphereObstacleCollision.forward  curobo/_src/geom/collision/wp_autograd.py:37-121
+ *   (Warp kernel sphere_obstacle_collision_kernel, geom/collision/wp_collision_kernel.py:70-166).
+ * weight / activation_distance are 1-element device arrays, like the reference.
+ * ------------------------------------------------------------------------------------------- */
+int cb200_sphere_obstacle_collision(
+    float *distance, float *gradient, const float *spheres, const cb200_cuboid_set *cuboids,
+    const cb200_voxel_set *voxels, const float *weight, const float *activation_distance,
+    const int32_t *env_query_idx, int batch_size, int horizon, int num_spheres, int use_multi_env,
+    cb200_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * (a12) swept sphere vs scene + optional speed metric (one launch).
+ * Replaces SweptSphereObstacleCollision.forward  curobo/_src/geom/collision/wp_autograd.py:124-247
+ *   (Warp kernels swept_sphere_obstacle_collision_kernel wp_sweep_collision_kernel.py:83-260 and
+ *    apply_speed_metric wp_speed_metric.py:10-93).  speed_dt is a 1-element device array.
+ * ------------------------------------------------------------------------------------------- */
+int cb200_swept_sphere_obstacle_collision(
+    float *distance, float *gradient, const float *spheres, const cb200_cuboid_set *cuboids,
+    const cb200_voxel_set *voxels, const float *weight, const float *activation_distance,
+    const float *speed_dt, int enable_speed_metric, const int32_t *env_query_idx, int batch_size,
+    int horizon, int num_spheres, int use_multi_env, cb200_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * (a13) goal-set tool-pose cost.  Replaces ToolPoseDistance.forward
+ *   curobo/_src/cost/wp_tool_pose.py:698-855 (Warp kernel goalset_pose_distance_* :457-692).
+ * rotation_method: 0 axis-angle, 1 Lie group.  project_distance_to_goal must be all zero.
+ * ------------------------------------------------------------------------------------------- */
+int cb200_tool_pose_distance(
+    float *out_distance, float *out_position_distance, float *out_rotation_distance,
+    float *out_position_gradient, float *out_rotation_gradient, int32_t *out_goalset_idx,
+    const float *current_position, const float *current_quat, const float *goal_position,
+    const float *goal_quat, const int32_t *idxs_goal, const float *position_orientation_weight,
+    const float *terminal_pose_axes_weight_factor, const float *non_terminal_pose_axes_weight_factor,
+    const float *terminal_pose_convergence_tolerance,
+    const float *non_terminal_pose_convergence_tolerance, int batch_size, int horizon,
+    int num_links, int num_goalset, int rotation_method, cb200_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * (a14) c-space costs.
+ * cb200_cspace_state_cost replaces StateCSpaceFunction.forward's kernel launch
+ *   curobo/_src/cost/wp_cspace_state.py:21-285 (forward_cspace_state_warp).
+ * cb200_cspace_position_cost replaces forward_cspace_position_warp
+ *   curobo/_src/cost/wp_cspace_position.py:232-362.
+ * Limits are [2, D] (lower row, upper row); weight/activation/regularisation arrays as in the
+ * reference (5 / 5 / 5 entries for STATE; 2 / 2 / 2 for POSITION).
+ * ------------------------------------------------------------------------------------------- */
+int cb200_cspace_state_cost(
+    float *out_cost, float *out_grad_p, float *out_grad_v, float *out_grad_a, float *out_grad_j,
+    float *out_grad_tau, const float *pos, const float *vel, const float *acc, const float *jerk,
+    const float *effort, const float *state_dt, const float *target_joint_position,
+    const int32_t *idxs_target_joint_position, const float *p_b, const float *v_b, const float *a_b,
+    const float *j_b, const float *effort_b, const float *weight, const float *activation_distance,
+    const float *squared_l2_regularization_weights, const float *cspace_target_weight,
+    const float *cspace_non_terminal_weight_factor, const float *cspace_target_dof_weight,
+    int write_grad, int batch_size, int horizon, int dof, int retime_weights,
+    int retime_regularization_weights, cb200_stream_t stream);
+
+int cb200_cspace_position_cost(
+    float *out_cost, float *out_grad_p, float *out_grad_tau, const float *pos, const float *effort,
+    const float *cspace_target, const int32_t *cspace_target_idx, const float *p_b,
+    const float *effort_b, const float *weight, const float *activation_distance,
+    const float *cspace_target_weight, const float *cspace_target_dof_weight,
+    const float *squared_l2_reg_weight, const float *current_position, const float *current_velocity,
+    const int32_t *idxs_current_state, const float *v_b, const float *state_dt, int write_grad,
+    int batch_size, int horizon, int dof, cb200_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * (a16/a17) THE FUSED HOT PATH: one launch = FK -> spheres -> {self, scene, tool-pose, c-space}
+ * cost -> J^T gradient, for every (seed x waypoint) row of q [B, H, D].
+ * Replaces the whole of  RobotRollout.evaluate_action + cost.backward()
+ *   curobo/_src/rollout/rollout_robot.py:252-263, rollout/cost_manager/cost_manager_robot.py:195-286,
+ *   optim/components/gradient_opt_core.py:445-480
+ * (15-25 launches + 4 streams in the reference).  Robot constants live in one packed device blob
+ * (cb200_robot_blob_*), staged into shared memory by a single bulk async copy per CTA.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Size in bytes of the packed robot blob for the given sizes (host helper; 16-byte multiple). */
+typedef struct {
+  int32_t num_links, num_dof, num_spheres, num_tool_frames, num_pairs;
+} cb200_robot_sizes;
+
+typedef struct {
+  /* weights / switches (value semantics: 0 weight disables a term) */
+  float self_weight;
+  float scene_weight, scene_activation;
+  int32_t use_sweep, use_speed_metric;
+  float pose_weight[2];
+  int32_t pose_rotation_method;        /* 0 axis-angle, 1 Lie */
+  int32_t cspace_type;                 /* 0 off, 1 POSITION, 2 STATE */
+  float cspace_weight[5], cspace_activation[5], cspace_reg[5];
+  int32_t retime_weights, retime_regularization_weights;
+  int32_t num_goalset;
+} cb200_rollout_cfg;
+
+typedef struct {
+  /* inputs */
+  const float *q;                 /* [B,H,D] */
+  const float *vel, *acc, *jerk;  /* [B,H,D] or null (STATE c-space only) */
+  const float *dt;                /* [B] or null */
+  const void *robot_blob;         /* DEVICE copy of the blob packed by cb200_pack_robot_blob */
+  const void *robot_blob_host;    /* HOST copy of (at least the first 128 bytes of) the same blob */
+  int32_t robot_blob_bytes;
+  const cb200_cuboid_set *cuboids; /* host pointers to structs holding device pointers; may be null */
+  const cb200_voxel_set *voxels;
+  const int32_t *env_query_idx;   /* [B] or null */
+  const float *goal_position;     /* [G, L, n_goalset, 3] or null */
+  const float *goal_quat;         /* [G, L, n_goalset, 4] wxyz */
+  const int32_t *idxs_goal;       /* [B] */
+  const float *pose_axes_terminal, *pose_axes_non_terminal; /* [L,6] or null (=1) */
+  const float *pose_tol_terminal, *pose_tol_non_terminal;   /* [L,2] or null (=0) */
+  /* outputs (any may be null except grad_q and cost) */
+  float *cost;          /* [B,H]  sum of all terms for the row */
+  float *grad_q;        /* [B,H,D] */
+  float *self_cost;     /* [B,H] */
+  float *scene_cost;    /* [B,H,S] */
+  float *pose_cost;     /* [B,H,2L] */
+  float *cspace_cost;   /* [B,H,D] */
+  float *grad_vel, *grad_acc, *grad_jerk; /* [B,H,D] (STATE c-space) */
+  float *link_pos, *link_quat;            /* optional FK outputs [B,H,L,3/4] */
+  float *robot_spheres;                   /* optional [B,H,S,4] */
+  int32_t *pose_goalset_idx;              /* optional [B,H,L] */
+  int32_t batch_size, horizon;
+} cb200_rollout_io;
+
+int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io,
+                            cb200_stream_t stream);
+
+/* Host helper: pack robot constants (HOST pointers) into `out` (host buffer of
+ * cb200_robot_blob_bytes(...) bytes) that the caller then copies to the device once.
+ * Returns bytes written or a negative number on invalid input. */
+int64_t cb200_robot_blob_bytes(const cb200_robot_sizes *sz);
+int64_t cb200_pack_robot_blob(
+    void *out, int64_t out_bytes, const cb200_robot_sizes *sz, const float *fixed_transforms,
+    const int16_t *link_map, const int16_t *joint_map, const int8_t *joint_map_type,
+    const float *joint_offset_map, const int16_t *tool_frame_map, const float *link_spheres,
+    const int16_t *link_sphere_map, const float *sphere_padding, const int16_t *collision_pairs,
+    const float *position_limits, const float *velocity_limits, const float *acceleration_limits,
+    const float *jerk_limits, const float *effort_limits);
+
+/* Device properties the host side sizes persistent grids with (SM count, max dynamic smem). */
+int cb200_device_info(int device, int *sm_count, int *max_smem_optin);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUROBO_B200_H */

@@ -1,0 +1,128 @@
+// oracle/ref_kernels_launcher.cu -- TEST INFRASTRUCTURE, NOT PRODUCT.
+//
+// Thin extern "C" launchers around the REFERENCE's own CUDA kernels, which are #included from the
+// reference tree where they lie (-I /root/reference/curobo/_src/curobolib/kernels; nothing is copied
+// into this repository).  Built by curobo_b200/build.py::build_reference_kernels into
+// oracle/_ref/libcurobo_ref.so (git-ignored; travels to the GPU box with the snapshot).
+//
+// Used ONLY by tests/ (to pin the oracle and to compare our kernels against the reference's on the
+// same inputs) and by bench.py's "reference kernels, unfused" side measurement.
+//
+// Launch math follows the reference launchers:
+//   forward : backends/cuda_core_backend/kinematics.py:90-177 + kinematics_config.py:53-95
+//             (threads_per_batch 32, max_threads 256, smem = bpb*nl*96 B)
+//   backward: kinematics.py:282-379 + kinematics_config.py:97-175 (warp-reduce path)
+//   self    : backends/cuda_core_backend/geometry.py:63-227
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "kinematics/kinematics_forward_kernel.cuh"
+#include "kinematics/kinematics_backward_kernel.cuh"
+#include "geometry/self_collision/self_collision_kernel.cuh"
+
+namespace ck = curobo::kinematics;
+namespace cs = curobo::geometry::self_collision;
+
+extern "C" {
+
+int ref_kinematics_forward_spheres(float *link_pos, float *link_quat, float *batch_robot_spheres, float *batch_com,
+                                   float *global_cumul_mat, const float *q, const float *fixed_transform,
+                                   const float *robot_spheres, const float *link_masses_com, const int8_t *joint_map_type,
+                                   const int16_t *joint_map, const int16_t *link_map, const int16_t *tool_frame_map,
+                                   const int16_t *link_sphere_map, const float *joint_offset_map,
+                                   const int32_t *env_query_idx, int num_envs, int batch_size, int horizon, int n_joints,
+                                   int num_spheres, int num_links, int n_tool_frames, cudaStream_t stream) {
+  const int tpb = 32, max_threads = 256;
+  int bpb = 8;
+  const int smem_per = num_links * 12 * 4 * 2;
+  if (bpb > 48 * 1024 / smem_per) bpb = 48 * 1024 / smem_per;
+  if (bpb * tpb > max_threads) bpb = max_threads / tpb;
+  if (bpb < 1) bpb = 1;
+  if (bpb > batch_size) bpb = batch_size;
+  const int threads = bpb * tpb;
+  const int blocks = (batch_size + bpb - 1) / bpb;
+  const size_t smem = (size_t)bpb * smem_per;
+  ck::kinematics_forward_spheres_kernel<-1, 32, true, false><<<blocks, threads, smem, stream>>>(
+      link_pos, link_quat, batch_robot_spheres, batch_com, global_cumul_mat, q, fixed_transform, robot_spheres,
+      link_masses_com, joint_map_type, joint_map, link_map, tool_frame_map, link_sphere_map, joint_offset_map,
+      env_query_idx, batch_size, horizon, num_spheres, num_envs, num_links, n_joints, n_tool_frames);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"
+
+template <int MAXJ>
+static void launch_bwd(int blocks, int threads, size_t smem, cudaStream_t stream, float *grad_out, const float *g_pos,
+                       const float *g_quat, const float *g_sph, const float *g_com, const float *b_com,
+                       const float *g_jac, const float *cumul, const float *robot_spheres, const float *masses,
+                       const int8_t *jtype, const int16_t *jmap, const int16_t *lmap, const int16_t *tool,
+                       const int16_t *sphl, const int32_t *envq, const int16_t *cd, const int16_t *co, const int16_t *jd,
+                       const int16_t *jo, const bool *jae, const float *joff, int batch, int horizon, int ns, int nl,
+                       int nj, int nt, int nenv, int tpb) {
+  ck::kinematics_backward_kernel<float, float, MAXJ, true, false, false><<<blocks, threads, smem, stream>>>(
+      grad_out, g_pos, g_quat, g_sph, g_com, b_com, g_jac, cumul, robot_spheres, masses, jtype, jmap, lmap, tool, sphl,
+      envq, cd, co, jd, jo, jae, joff, batch, horizon, ns, nl, nj, nt, nenv, tpb);
+}
+
+extern "C" {
+
+int ref_kinematics_backward(float *grad_out, const float *g_pos, const float *g_quat, const float *g_sph,
+                            const float *g_com, const float *b_com, const float *g_jac, const float *cumul,
+                            const float *robot_spheres, const float *masses, const int16_t *lmap, const int16_t *jmap,
+                            const int8_t *jtype, const int16_t *tool, const int16_t *sphl, const int16_t *cd,
+                            const int16_t *co, const int16_t *jd, const int16_t *jo, const uint8_t *jae,
+                            const float *joff, const int32_t *envq, int num_envs, int batch_size, int horizon,
+                            int n_joints, int num_spheres, int num_links, int n_tool_frames, cudaStream_t stream) {
+  const int max_threads = 128, tpb = 32;
+  int bpb = 32;
+  const int smem_per = num_links * 12 * 4;
+  if (bpb > 48 * 1024 / smem_per) bpb = 48 * 1024 / smem_per;
+  if (bpb * tpb > max_threads) bpb = max_threads / tpb;
+  if (bpb < 1) bpb = 1;
+  if (bpb > batch_size) bpb = batch_size;
+  const int threads = bpb * tpb;
+  const int blocks = (batch_size * tpb + threads - 1) / threads;
+  const size_t smem = (size_t)bpb * smem_per;
+  const bool *jb = reinterpret_cast<const bool *>(jae);
+  if (n_joints < 16)
+    launch_bwd<16>(blocks, threads, smem, stream, grad_out, g_pos, g_quat, g_sph, g_com, b_com, g_jac, cumul,
+                   robot_spheres, masses, jtype, jmap, lmap, tool, sphl, envq, cd, co, jd, jo, jb, joff, batch_size,
+                   horizon, num_spheres, num_links, n_joints, n_tool_frames, num_envs, tpb);
+  else if (n_joints < 64)
+    launch_bwd<64>(blocks, threads, smem, stream, grad_out, g_pos, g_quat, g_sph, g_com, b_com, g_jac, cumul,
+                   robot_spheres, masses, jtype, jmap, lmap, tool, sphl, envq, cd, co, jd, jo, jb, joff, batch_size,
+                   horizon, num_spheres, num_links, n_joints, n_tool_frames, num_envs, tpb);
+  else
+    launch_bwd<128>(blocks, threads, smem, stream, grad_out, g_pos, g_quat, g_sph, g_com, b_com, g_jac, cumul,
+                    robot_spheres, masses, jtype, jmap, lmap, tool, sphl, envq, cd, co, jd, jo, jb, joff, batch_size,
+                    horizon, num_spheres, num_links, n_joints, n_tool_frames, num_envs, tpb);
+  return (int)cudaGetLastError();
+}
+
+int ref_self_collision_distance(float *out_distance, float *out_vec, float *pair_distance, uint8_t *sparse_index,
+                                const float *robot_spheres, const float *sphere_padding, const float *weight,
+                                int16_t *pair_locations, float *block_batch_max_value, int16_t *block_batch_max_index,
+                                int num_blocks_per_batch, int max_threads_per_block, int batch_size, int horizon,
+                                int nspheres, int num_collision_pairs, int compute_grad, cudaStream_t stream) {
+  const size_t smem = (size_t)16 * nspheres;
+  if (num_blocks_per_batch == 1) {
+    int threads = max_threads_per_block < num_collision_pairs ? max_threads_per_block : num_collision_pairs;
+    threads = ((threads + 31) / 32) * 32;
+    if (threads > max_threads_per_block) threads = max_threads_per_block;
+    cs::self_collision_max_distance_kernel<false><<<batch_size * horizon, threads, smem, stream>>>(
+        out_distance, out_vec, pair_distance, sparse_index, robot_spheres, sphere_padding, weight, pair_locations,
+        batch_size, horizon, nspheres, num_collision_pairs, compute_grad != 0);
+  } else {
+    cs::self_collision_max_block_kernel<false>
+        <<<batch_size * horizon * num_blocks_per_batch, max_threads_per_block, smem, stream>>>(
+            out_vec, pair_distance, sparse_index, robot_spheres, sphere_padding, pair_locations, block_batch_max_value,
+            block_batch_max_index, num_blocks_per_batch, batch_size, horizon, nspheres, num_collision_pairs);
+    const int t2 = num_blocks_per_batch < 512 ? num_blocks_per_batch : 512;
+    cs::self_collision_max_reduce_kernel<<<batch_size * horizon, t2, 0, stream>>>(
+        out_distance, out_vec, pair_distance, sparse_index, robot_spheres, sphere_padding, weight, pair_locations,
+        block_batch_max_value, block_batch_max_index, num_blocks_per_batch, batch_size, horizon, nspheres,
+        num_collision_pairs, compute_grad != 0);
+  }
+  return (int)cudaGetLastError();
+}
+}

@@ -1,0 +1,23 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box)")
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    np.random.seed(42)
+    try:
+        import torch
+        torch.manual_seed(42)
+    except Exception:
+        pass

@@ -1,0 +1,79 @@
+// TEST-ONLY shared library: exposes the scalar __host__ __device__ building blocks of
+// curobo_b200/csrc/cb200_math.cuh to the CPU test-suite so the arithmetic is checked against oracle/
+// without a GPU.  It is NOT part of the product library (libcurobo_b200.so has no host compute path).
+#include <stdint.h>
+
+#include "../../curobo_b200/csrc/cb200_math.cuh"
+
+using namespace cb200;
+
+extern "C" {
+
+void hm_local_transform(const float *fixed12, int jt, float theta, float *out12) {
+  local_link_transform(fixed12, jt, theta, out12);
+}
+
+void hm_quat_from_transform(const float *t12, float *wxyz) {
+  Q4 q = quat_from_transform(t12);
+  wxyz[0] = q.w;
+  wxyz[1] = q.x;
+  wxyz[2] = q.y;
+  wxyz[3] = q.z;
+}
+
+// spheres [B,H,S,4]; sweep/speed as in the product kernel; single env 0
+void hm_scene(const float *spheres, int B, int H, int S, float weight, float eta, int sweep, int speed, float dt,
+              const float *cub_dims, const float *cub_inv_pose, const uint8_t *cub_enable, const int32_t *cub_count,
+              int cub_max_n, const float *vox_params, const float *vox_inv_pose, const uint8_t *vox_enable,
+              const int32_t *vox_count, const uint16_t *vox_feat, int vox_nvox, int vox_max_n, float vox_max_dist,
+              float *out_cost, float *out_grad) {
+  CuboidSet cs{};
+  VoxelSet vs{};
+  if (cub_inv_pose) cs = CuboidSet{cub_dims, cub_inv_pose, cub_enable, cub_count, cub_max_n, 1};
+  if (vox_inv_pose) vs = VoxelSet{vox_params, vox_inv_pose, vox_enable, vox_count, vox_feat, vox_nvox, vox_max_n, 1, vox_max_dist};
+  for (int b = 0; b < B; ++b)
+    for (int h = 0; h < H; ++h)
+      for (int s = 0; s < S; ++s) {
+        const long long i = ((long long)b * H + h) * S + s;
+        const float *sp = spheres + 4 * i;
+        V3 c = mk3(sp[0], sp[1], sp[2]);
+        V3 g = mk3(0, 0, 0);
+        float cost;
+        if (!sweep) {
+          cost = sphere_scene_discrete(c, sp[3], eta, weight, cs, vs, 0, g);
+        } else {
+          bool hp = h > 0, hn = h < H - 1;
+          V3 pv = c, nx = c;
+          if (hp) pv = mk3(sp[-4 * S], sp[-4 * S + 1], sp[-4 * S + 2]);
+          if (hn) nx = mk3(sp[4 * S], sp[4 * S + 1], sp[4 * S + 2]);
+          cost = sphere_scene_swept(c, sp[3], eta, weight, hp, pv, hn, nx, cs, vs, 0, g);
+          if (speed && hp && hn) speed_metric(pv, c, nx, dt, cost, g);
+        }
+        out_cost[i] = cost;
+        out_grad[4 * i] = g.x;
+        out_grad[4 * i + 1] = g.y;
+        out_grad[4 * i + 2] = g.z;
+        out_grad[4 * i + 3] = 0.f;
+      }
+}
+
+// one tool frame
+void hm_tool_pose(const float *pos3, const float *quat_wxyz, const float *goal_pos, const float *goal_quat, int n_goalset,
+                  float w_pos, float w_rot, const float *axes6, float tol_p, float tol_r, int method, float *out /*12*/,
+                  int *goal_idx) {
+  PoseOut o = tool_pose_cost(mk3(pos3[0], pos3[1], pos3[2]), Q4{quat_wxyz[1], quat_wxyz[2], quat_wxyz[3], quat_wxyz[0]},
+                             goal_pos, goal_quat, n_goalset, w_pos, w_rot, axes6, tol_p, tol_r, method);
+  out[0] = o.pos_cost;
+  out[1] = o.rot_cost;
+  out[2] = o.pos_err;
+  out[3] = o.rot_err;
+  out[4] = o.g_pos.x;
+  out[5] = o.g_pos.y;
+  out[6] = o.g_pos.z;
+  out[7] = o.gq_w;
+  out[8] = o.gq_x;
+  out[9] = o.gq_y;
+  out[10] = o.gq_z;
+  *goal_idx = o.goal_idx;
+}
+}

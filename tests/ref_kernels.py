@@ -1,0 +1,84 @@
+"""ctypes access to oracle/_ref/libcurobo_ref.so = the REFERENCE's own CUDA kernels compiled from
+/root/reference (test infrastructure only; see oracle/ref_kernels_launcher.cu)."""
+import ctypes as C
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "oracle", "_ref", "libcurobo_ref.so")
+
+
+def available() -> bool:
+    return os.path.exists(PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(PATH)
+    return _lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def fk_forward(kp, q, horizon=1, env_query_idx=None):
+    """q [N,D] -> (link_pos, link_quat, spheres, cumul) through kinematics_forward_spheres_kernel."""
+    dev = q.device
+    N = q.shape[0]
+    z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+    pos, quat = z(N, kp.num_pose_links, 3), z(N, kp.num_pose_links, 4)
+    sph, com, cum = z(N, kp.num_spheres, 4), z(N, 4), z(N, kp.num_links, 3, 4)
+    eq = env_query_idx if env_query_idx is not None else torch.zeros(1, dtype=torch.int32, device=dev)
+    err = lib().ref_kinematics_forward_spheres(
+        _p(pos), _p(quat), _p(sph), _p(com), _p(cum), _p(q), _p(kp.fixed_transforms), _p(kp.link_spheres),
+        _p(kp.link_masses_com), _p(kp.joint_map_type), _p(kp.joint_map), _p(kp.link_map), _p(kp.tool_frame_map),
+        _p(kp.link_sphere_idx_map), _p(kp.joint_offset_map), _p(eq), kp.num_envs, N, horizon, kp.num_dof,
+        kp.num_spheres, kp.num_links, kp.num_pose_links, _stream(dev))
+    assert err == 0, err
+    return pos, quat, sph, cum
+
+
+def fk_backward(kp, cumul, g_pos, g_quat, g_sph, horizon=1, env_query_idx=None):
+    dev = cumul.device
+    N = cumul.shape[0]
+    out = torch.zeros((N, kp.num_dof), dtype=torch.float32, device=dev)
+    com = torch.zeros((N, 4), dtype=torch.float32, device=dev)
+    eq = env_query_idx if env_query_idx is not None else torch.zeros(1, dtype=torch.int32, device=dev)
+    err = lib().ref_kinematics_backward(
+        _p(out), _p(g_pos), _p(g_quat), _p(g_sph), _p(com), _p(com), None, _p(cumul), _p(kp.link_spheres),
+        _p(kp.link_masses_com), _p(kp.link_map), _p(kp.joint_map), _p(kp.joint_map_type), _p(kp.tool_frame_map),
+        _p(kp.link_sphere_idx_map), _p(kp.link_chain_data), _p(kp.link_chain_offsets), _p(kp.joint_links_data),
+        _p(kp.joint_links_offsets), _p(kp.joint_affects_endeffector), _p(kp.joint_offset_map), _p(eq), kp.num_envs, N,
+        horizon, kp.num_dof, kp.num_spheres, kp.num_links, kp.num_pose_links, _stream(dev))
+    assert err == 0, err
+    return out
+
+
+def self_collision(rm, spheres, padding, pairs, weight):
+    """spheres [B,H,S,4] -> (distance [B,H], grad [B,H,S,4]) through the reference kernels
+    (single-kernel or map-reduce path chosen like the reference does)."""
+    dev = spheres.device
+    B, H, S, _ = spheres.shape
+    nb = rm.num_blocks_per_batch
+    dist = torch.zeros((B, H), dtype=torch.float32, device=dev)
+    vec = torch.zeros((B, H, S, 4), dtype=torch.float32, device=dev)
+    sparse = torch.zeros((B, H, S), dtype=torch.uint8, device=dev)
+    pd = torch.zeros((1,), dtype=torch.float32, device=dev)
+    bv = torch.zeros((B, H, nb), dtype=torch.float32, device=dev)
+    bi = torch.zeros((B, H, nb, 2), dtype=torch.int16, device=dev)
+    w = torch.tensor([weight], dtype=torch.float32, device=dev)
+    err = lib().ref_self_collision_distance(_p(dist), _p(vec), _p(pd), _p(sparse), _p(spheres), _p(padding), _p(w),
+                                            _p(pairs), _p(bv), _p(bi), nb, rm.max_threads_per_block, B, H, S,
+                                            pairs.shape[0], 1, _stream(dev))
+    assert err == 0, err
+    return dist, vec

@@ -1,0 +1,109 @@
+"""The C-ABI library loads and exports every symbol include/curobo_b200.h declares (no compute calls
+without a GPU), and the host-side robot-blob packer produces the layout the kernels expect."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from curobo_b200 import build, lib as cblib
+from curobo_b200.robot_model import load_robot
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    build.build_product()
+    return cblib.load()
+
+
+def _declared_functions():
+    txt = open(os.path.join(ROOT, "include", "curobo_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported(L):
+    names = _declared_functions()
+    assert len(names) >= 15
+    raw = C.CDLL(cblib.lib_path())
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/curobo_b200.h but not exported"
+    assert set(names) == set(cblib.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
+    assert L.cb200_abi_version() == 1 and L.cb200_sm_arch() == 100
+
+
+def test_library_contains_sm100a_sass_and_tma_bulk_copy():
+    """Native code check without a GPU: sm_100a cubin present, the fused kernel stages its constants
+    with a bulk async copy (UBLKCP in SASS = cp.async.bulk)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", cblib.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "rollout_fused_kernel" in sass
+    assert "UBLKCP" in sass
+
+
+@pytest.mark.parametrize("name", ["franka", "g1_29", "g1_43"])
+def test_robot_blob_layout(L, name):
+    from curobo_b200.rollout import pack_robot_blob
+    rm = load_robot(name)
+    blob = pack_robot_blob(rm)
+    hdr = struct.unpack("<32i", blob[:128].tobytes())
+    magic, total, smem, nl, D, S, Lt, P, n_levels = hdr[:9]
+    offs = dict(zip(["fixed", "joff", "link_map", "joint_map", "joint_type", "tool_map", "spheres", "sph_link",
+                     "padding", "link_sph_off", "link_sph_idx", "level_off", "level_links", "anc_mask", "jl_off",
+                     "jl_idx", "limits", "pairs"], hdr[9:27]))
+    assert magic == 0x30324243 and total == blob.shape[0] and smem % 16 == 0 and smem <= total
+    assert (nl, D, S, Lt, P) == (rm.num_links, rm.num_dof, rm.num_spheres, rm.num_tool_frames, rm.collision_pairs.shape[0])
+    assert all(o % 16 == 0 for o in offs.values())
+    view = lambda k, dt, n: np.frombuffer(blob.tobytes(), dtype=dt, count=n, offset=offs[k])  # noqa: E731
+    np.testing.assert_array_equal(view("fixed", np.float32, nl * 12), rm.fixed_transforms.reshape(-1))
+    np.testing.assert_array_equal(view("link_map", np.int16, nl), rm.link_map)
+    np.testing.assert_array_equal(view("spheres", np.float32, S * 4), rm.link_spheres.reshape(-1))
+    np.testing.assert_array_equal(view("pairs", np.int16, 2 * P), rm.collision_pairs.reshape(-1))
+    # depth levels are a valid schedule: every link appears once, parents in earlier levels
+    lo = view("level_off", np.int16, n_levels + 1)
+    ll = view("level_links", np.int16, nl)
+    assert sorted(ll.tolist()) == list(range(nl)) and lo[0] == 0 and lo[-1] == nl
+    level_of = {}
+    for lev in range(n_levels):
+        for l in ll[lo[lev]:lo[lev + 1]]:
+            level_of[int(l)] = lev
+    assert all(level_of[int(rm.link_map[l])] == level_of[l] - 1 for l in range(1, nl))
+    # ancestor masks agree with the reference's link_chain CSR
+    anc = view("anc_mask", np.uint64, nl)
+    for l in range(nl):
+        chain = rm.link_chain_data[rm.link_chain_offsets[l]:rm.link_chain_offsets[l + 1]]
+        assert int(anc[l]) == sum(1 << int(k) for k in chain)
+    # link -> spheres CSR covers every sphere exactly once
+    lso = view("link_sph_off", np.int16, nl + 1)
+    lsi = view("link_sph_idx", np.int16, S)
+    assert sorted(lsi.tolist()) == list(range(S))
+    for l in range(nl):
+        assert all(rm.link_sphere_idx_map[s] == l for s in lsi[lso[l]:lso[l + 1]])
+    # smem budget: at least 4 warps of per-eval state + the staged blob fit the B200 opt-in limit (227 KB)
+    per_warp = (nl * 12 + S * 8 + nl * 8 + nl + 2 * D + Lt * 8 + 3) // 4 * 4 * 4
+    assert smem + 4 * per_warp <= 227 * 1024, (smem, per_warp)
+
+
+def test_blob_packer_rejects_bad_input(L):
+    rm = load_robot("franka")
+    sz = cblib.RobotSizes(65, 7, 65, 1, 0)             # 65 links > 64
+    assert L.cb200_robot_blob_bytes(C.byref(sz)) < 0
+
+
+def test_cpu_tensors_are_refused():
+    """There is no CPU fallback: handing CPU tensors to an op raises before any launch."""
+    import torch
+    from curobo_b200.backends import geometry
+    t = torch.zeros(4)
+    with pytest.raises(ValueError):
+        geometry.self_collision_distance(t, t, t, t.to(torch.uint8), t, t, t, t.to(torch.int16), t, t.to(torch.int16),
+                                         1, 64, 1, 1, 1, 1, False, True)

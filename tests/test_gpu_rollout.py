@@ -1,0 +1,264 @@
+"""GPU parity of the FUSED rollout cost+gradient kernel (through the C ABI) against the oracle and the
+golden fixtures at small sizes, and through size-independent properties at BASELINE.json's full sizes.
+
+Tolerances as in test_gpu_parity.py: costs rel 1e-4 (+1e-6*max), grad_q rel 1e-3 + 1e-5*|g|_inf."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_q, random_walk_q, small_voxel_world
+from curobo_b200.kinematics import Kinematics, SelfCollisionCost
+from curobo_b200.robot_model import load_robot
+from curobo_b200.rollout import FusedRolloutFunction, RolloutConfig, RolloutEngine
+from curobo_b200.scene import (CollisionBuffer, CuboidData, SceneData, SphereObstacleCollision, VoxelData)
+from curobo_b200.world import VoxelWorld, make_benchmark_cuboid_world, make_box_esdf
+from oracle import rollout_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def T(a, dt=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    return t.to(dt) if dt is not None else t
+
+
+def grad_close(a, b, rtol=1e-3, scale=1e-5):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=scale * max(np.abs(b).max(), 1e-6))
+
+
+def cost_close(a, b, rtol=1e-4):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=1e-6 * max(np.abs(b).max(), 1e-6))
+
+
+def goal_from_q(rm, qg):
+    _, _, p, qt = O.fk_forward(rm, qg)
+    return p[:, :, None, :].copy(), qt[:, :, None, :].copy()
+
+
+def check_against_oracle(rm, cfg, q, cub=None, vox=None, goal=None, idx=None):
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV) if cub is not None else None,
+                        VoxelData.from_world(vox, DEV) if vox is not None else None, store_fk_outputs=True)
+    if goal is not None:
+        eng.update_goal(T(goal[0]), T(goal[1]), T(idx))
+    out = eng.evaluate_action(T(q))
+    torch.cuda.synchronize()
+    want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(rm.num_tool_frames), world_cuboid=cub, world_voxel=vox,
+                               goal_pos=None if goal is None else goal[0], goal_quat=None if goal is None else goal[1],
+                               idxs_goal=idx)
+    np.testing.assert_allclose(out.robot_spheres.cpu().numpy(), want["spheres"], atol=1e-5)
+    np.testing.assert_allclose(out.link_pos.cpu().numpy(), want["link_pos"], atol=1e-5)
+    if "self_cost" in want:
+        cost_close(out.self_cost.cpu().numpy(), want["self_cost"])
+    if "scene_cost" in want:
+        np.testing.assert_allclose(out.scene_cost.cpu().numpy(), want["scene_cost"], rtol=1e-4,
+                                   atol=1e-5 * max(want["scene_cost"].max(), 1e-6))
+    if "pose_cost" in want:
+        np.testing.assert_allclose(out.pose_cost.cpu().numpy(), want["pose_cost"], rtol=2e-4,
+                                   atol=1e-5 * want["pose_cost"].max())
+    if "cspace_cost" in want:
+        cost_close(out.cspace_cost.cpu().numpy(), want["cspace_cost"])
+    np.testing.assert_allclose(out.cost.cpu().numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+    return out, want
+
+
+def test_franka_ik_rollout_vs_oracle_and_golden():
+    rm = load_robot("franka")
+    g = np.load(os.path.join(GOLD, "franka_ik_rollout_b48.npz"))
+    cfg = RolloutConfig.ik()
+    out, want = check_against_oracle(rm, cfg, g["q"], cub=make_benchmark_cuboid_world(),
+                                     goal=(g["goal_pos"], g["goal_quat"]), idx=g["idxs_goal"])
+    np.testing.assert_allclose(out.cost.cpu().numpy(), g["cost_bh"], rtol=2e-4, atol=1e-5 * g["cost_bh"].max())
+    grad_close(out.grad_q.cpu().numpy(), g["grad_q"], rtol=2e-3, scale=2e-5)
+    assert (want["self_cost"] > 0).any() and (want["scene_cost"] > 0).any()
+
+
+def test_franka_ik_rollout_larger_batch():
+    rm = load_robot("franka")
+    q = random_q(rm, 700, seed=41)[:, None, :]
+    gp, gq = goal_from_q(rm, random_q(rm, 16, seed=42))
+    idx = (np.arange(700) % 16).astype(np.int32)
+    check_against_oracle(rm, RolloutConfig.ik(), q, cub=make_benchmark_cuboid_world(), goal=(gp, gq), idx=idx)
+
+
+def test_franka_esdf_horizon_rollout_terminal_weights():
+    """H > 1, discrete ESDF + cuboids; non-terminal pose axes weights zero like the trajopt config."""
+    rm = load_robot("franka")
+    q = random_walk_q(rm, 10, 6, seed=43)
+    cfg = RolloutConfig(self_weight=10000.0, scene_weight=100000.0, scene_activation=0.0025,
+                        pose_weight=(1000000.0, 100000.0), cspace_type="position", cspace_weight=(5000.0, 0, 0, 0, 0),
+                        cspace_activation=(0.01, 0, 0, 0, 0))
+    gp, gq = goal_from_q(rm, random_q(rm, 10, seed=44))
+    idx = np.arange(10, dtype=np.int32)
+    rmv = small_voxel_world()
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(make_benchmark_cuboid_world(), DEV), VoxelData.from_world(rmv, DEV))
+    nt = torch.zeros((1, 6), dtype=torch.float32, device=DEV)
+    eng.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=nt)
+    out = eng.evaluate_action(T(q))
+    ocfg = cfg.to_oracle_cfg(1)
+    ocfg["pose_non_terminal_axes"] = np.zeros((1, 6), np.float32)
+    want = O.rollout_cost_grad(rm, q, ocfg, world_cuboid=make_benchmark_cuboid_world(), world_voxel=rmv, goal_pos=gp,
+                               goal_quat=gq, idxs_goal=idx)
+    np.testing.assert_allclose(out.cost.cpu().numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+    assert float(out.pose_cost[:, :-1].abs().sum()) == 0.0 and float(out.pose_cost[:, -1].abs().sum()) > 0
+
+
+@pytest.mark.parametrize("robot,n", [("g1_29", 6), ("g1_29", 40), ("g1_43", 12)])
+def test_humanoid_esdf_rollout_vs_oracle(robot, n):
+    rm = load_robot(robot)
+    cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                        cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0))
+    if robot == "g1_29" and n == 6:
+        g = np.load(os.path.join(GOLD, "g1_29_esdf_rollout_b6.npz"))
+        q = g["q"]
+    else:
+        q = random_q(rm, n, seed=45, scale=0.6)[:, None, :]
+    gp, gq = goal_from_q(rm, random_q(rm, 3, seed=46, scale=0.5))
+    idx = (np.arange(q.shape[0]) % 3).astype(np.int32)
+    cfg_pose = RolloutConfig(**{**cfg.__dict__, "pose_weight": (2000.0, 100.0)})
+    check_against_oracle(rm, cfg_pose, q, vox=small_voxel_world(), goal=(gp, gq), idx=idx)
+    if robot == "g1_29" and n == 6:
+        out, _ = check_against_oracle(rm, cfg, q, vox=small_voxel_world())
+        grad_close(out.grad_q.cpu().numpy(), g["grad_q"], rtol=2e-3, scale=2e-5)
+
+
+def test_state_cspace_rollout_vs_oracle():
+    rm = load_robot("franka")
+    B, H = 6, 9
+    q = random_walk_q(rm, B, H, seed=47)
+    rng = np.random.default_rng(1)
+    v, a, j = [rng.normal(0, s, size=(B, H, 7)).astype(np.float32) for s in (2.0, 12.0, 400.0)]
+    dt = rng.uniform(0.02, 0.1, size=B).astype(np.float32)
+    cfg = RolloutConfig(self_weight=10000.0, cspace_type="state", cspace_weight=(10000.0, 10000.0, 100.0, 50.0, 100.0),
+                        cspace_activation=(0.01,) * 5, cspace_reg=(1000.0, 10000.0, 5.0, 0.0, 0.0))
+    eng = RolloutEngine(rm, cfg, DEV)
+    out = eng.evaluate_action(T(q), vel=T(v), acc=T(a), jerk=T(j), dt=T(dt))
+    want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(1), vel=v, acc=a, jerk=j, dt=dt)
+    cost_close(out.cspace_cost.cpu().numpy(), want["cspace_cost"], rtol=2e-4)
+    grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+    for got, wantg in zip((out.grad_vel, out.grad_acc, out.grad_jerk), want["cspace_grads"][1:4]):
+        grad_close(got.cpu().numpy(), wantg)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE.json configs 2 and 5)
+# ------------------------------------------------------------------------------------------------
+def _ik_engine(rm, B, seed=50):
+    gp, gq = goal_from_q(rm, random_q(rm, 512, seed=seed))
+    eng = RolloutEngine(rm, RolloutConfig.ik(), DEV, CuboidData.from_world(make_benchmark_cuboid_world(), DEV))
+    eng.update_goal(T(gp), T(gq), T((np.arange(B) // 32 % 512).astype(np.int32)))
+    return eng
+
+
+def test_full_size_ik_properties():
+    """config 2: 512 targets x 32 seeds.  (i) bitwise run-to-run determinism, (ii) fused == composition of
+    the per-op kernels + autograd, (iii) row permutation equivariance, (iv) CUDA-graph replay identical."""
+    rm = load_robot("franka")
+    B = 512 * 32
+    q = T(random_q(rm, B, seed=51)[:, None, :])
+    eng = _ik_engine(rm, B)
+    o = eng.evaluate_action(q)
+    c1, g1 = o.cost.clone(), o.grad_q.clone()
+    o = eng.evaluate_action(q)
+    assert torch.equal(c1, o.cost) and torch.equal(g1, o.grad_q)
+    assert torch.isfinite(c1).all() and torch.isfinite(g1).all()
+    # (ii) unfused composition with our per-op kernels (FK -> self + scene -> autograd backward)
+    kin = Kinematics(rm, DEV)
+    selfc = SelfCollisionCost(rm, eng.cfg.self_weight, DEV)
+    scene = SceneData(CuboidData.from_world(make_benchmark_cuboid_world(), DEV), None)
+    buf = CollisionBuffer.from_shape((B, 1, rm.num_spheres, 4), DEV)
+    qg = q.clone().requires_grad_(True)
+    st = kin.compute_kinematics(qg)
+    d_self = selfc.forward(st.robot_spheres)
+    d_scene = SphereObstacleCollision.apply(st.robot_spheres, buf, scene, T(np.array([eng.cfg.scene_weight], np.float32)),
+                                            T(np.array([0.0], np.float32)), None, torch.zeros(B, dtype=torch.int32, device=DEV),
+                                            False, False)
+    (d_self.sum() + d_scene.sum()).backward()
+    eng2 = RolloutEngine(rm, RolloutConfig(self_weight=eng.cfg.self_weight, scene_weight=eng.cfg.scene_weight), DEV,
+                         CuboidData.from_world(make_benchmark_cuboid_world(), DEV))
+    o2 = eng2.evaluate_action(q)
+    torch.testing.assert_close(o2.self_cost.view(-1), d_self.view(-1), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(o2.scene_cost, d_scene, rtol=1e-5, atol=1e-4)
+    scale = float(qg.grad.abs().max())
+    torch.testing.assert_close(o2.grad_q, qg.grad, rtol=2e-3, atol=2e-5 * scale)
+    # (iii) permutation equivariance
+    perm = torch.randperm(B, device=DEV)
+    idx_perm = eng._goal[2][perm].contiguous()
+    eng.update_goal(eng._goal[0], eng._goal[1], idx_perm)
+    o3 = eng.evaluate_action(q[perm].contiguous())
+    assert torch.equal(o3.cost, c1[perm]) and torch.equal(o3.grad_q, g1[perm])
+    # (iv) graph capture + replay
+    eng = _ik_engine(rm, B)
+    eng.evaluate_action(q)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        eng.evaluate_action(q)
+    eng.out.cost.zero_()
+    eng.out.grad_q.zero_()
+    gr.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(eng.out.cost, c1) and torch.equal(eng.out.grad_q, g1)
+
+
+def test_full_size_humanoid_esdf_properties():
+    """config 5 (per-GPU share 1024 seeds of 8192) on the 256^3 fp16 ESDF: determinism, zero weights -> zero
+    cost/grad, gradient is a descent direction (cost decreases along -grad for a small step)."""
+    rm = load_robot("g1_29")
+    sdf = make_box_esdf(n=256, voxel_size=0.01, num_boxes=12, seed=0, xp=torch)
+    vox = VoxelData(T(np.array([[[256, 256, 256, 0.01]]], np.float32)), T(np.array([[[0, 0, 0, 1, 0, 0, 0, 0]]], np.float32)),
+                    torch.ones((1, 1), dtype=torch.uint8, device=DEV), torch.ones(1, dtype=torch.int32, device=DEV),
+                    sdf.reshape(1, 1, -1).contiguous(), 1, 1, 100.0)
+    B = 1024
+    q = T(random_q(rm, B, seed=52, scale=0.5)[:, None, :])
+    cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                        cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0))
+    eng = RolloutEngine(rm, cfg, DEV, voxel=vox)
+    o = eng.evaluate_action(q)
+    c1, g1 = o.cost.clone(), o.grad_q.clone()
+    o = eng.evaluate_action(q)
+    assert torch.equal(c1, o.cost) and torch.equal(g1, o.grad_q)
+    assert torch.isfinite(g1).all() and float(c1.sum()) > 0
+    # scene term alone: small step against the gradient does not increase the (piecewise smooth) scene cost
+    eng_s = RolloutEngine(rm, RolloutConfig(scene_weight=5000.0, scene_activation=0.02), DEV, voxel=vox)
+    o = eng_s.evaluate_action(q)
+    cs, gs = o.cost.clone(), o.grad_q.clone()
+    hit = cs.view(-1) > 0
+    assert int(hit.sum()) > 10
+    step = 1e-4 / gs.norm(dim=-1, keepdim=True).clamp(min=1e-9)
+    c_new = eng_s.evaluate_action((q - step * gs).contiguous()).cost
+    frac = float(((c_new.view(-1) <= cs.view(-1) + 1e-3)[hit]).float().mean())
+    assert frac > 0.95, frac
+    # zero weights -> exact zeros
+    eng_z = RolloutEngine(rm, RolloutConfig(), DEV, voxel=vox)
+    o = eng_z.evaluate_action(q)
+    assert float(o.cost.abs().sum()) == 0.0 and float(o.grad_q.abs().sum()) == 0.0
+    # oracle spot check on a sample of rows at full ESDF size
+    sel = np.arange(0, B, 64)
+    vw = VoxelWorld(vox.params.cpu().numpy(), vox.inv_pose.cpu().numpy(), np.ones((1, 1), np.uint8), np.ones(1, np.int32),
+                    sdf.reshape(1, 1, -1).cpu().numpy(), 100.0)
+    want = O.rollout_cost_grad(rm, q.cpu().numpy()[sel], cfg.to_oracle_cfg(14), world_voxel=vw)
+    np.testing.assert_allclose(c1.cpu().numpy()[sel], want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(g1.cpu().numpy()[sel], want["grad_q"], rtol=2e-3, scale=2e-5)
+
+
+def test_autograd_function_and_errors():
+    rm = load_robot("franka")
+    eng = _ik_engine(rm, 64)
+    q = T(random_q(rm, 64, seed=53)[:, None, :]).requires_grad_(True)
+    cost = FusedRolloutFunction.apply(q, eng)
+    cost.sum().backward()
+    assert cost.shape == (64,) and torch.equal(q.grad, eng.out.grad_q)
+    with pytest.raises(ValueError):
+        eng.evaluate_action(torch.zeros((64, 1, 6), device=DEV))
+    with pytest.raises(ValueError):
+        eng.evaluate_action(torch.zeros((64, 1, 7)))                       # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        eng.evaluate_action(torch.zeros((64, 2, 7), device=DEV)[:, ::2])   # non-contiguous
+    with pytest.raises(ValueError):
+        RolloutEngine(rm, RolloutConfig.ik(), "cpu")
