@@ -67,6 +67,21 @@ def make_workload(name: str, seed_offset: int = 0):
                             cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0))
         return dict(robot=rm, cfg=cfg, B=B, H=H, q=q, goal=None, cuboid=None, voxel=dict(n=256, voxel=0.01, boxes=12, seed=0),
                     bytes_per_eval=bpe)
+    if name in ("franka_mpc_1024x30_esdf_swept", "franka_trajopt_32x32_esdf_swept"):
+        from helpers import random_walk_q
+        rm = load_robot("franka")
+        B, H = (1024, 30) if "mpc" in name else (32, 32)
+        q = random_walk_q(rm, B, H, seed=300 + seed_offset)
+        vel = (np.gradient(q, axis=1) / 0.05).astype(np.float32)
+        acc = (np.gradient(vel, axis=1) / 0.05).astype(np.float32)
+        jerk = (np.gradient(acc, axis=1) / 0.05).astype(np.float32)
+        _, _, gp, gq = O.fk_forward(rm, random_q(rm, B, seed=9))
+        goal = (gp[:, :, None, :].copy(), gq[:, :, None, :].copy(), np.arange(B, dtype=np.int32))
+        D, S, L = rm.num_dof, rm.num_spheres, rm.num_tool_frames
+        bpe = 4 * D + 4 * D + 4 * (S + 1 + 2 * L + D) + 16 * S * 7 + 3 * 4 * D * 2   # swept worst case n_s = 7; v/a/j in + grads out
+        return dict(robot=rm, cfg=RolloutConfig.trajopt(), B=B, H=H, q=q, goal=goal, cuboid=None,
+                    voxel=dict(n=256, voxel=0.01, boxes=12, seed=0), bytes_per_eval=bpe,
+                    extra=dict(vel=vel, acc=acc, jerk=jerk, dt=np.full(B, 0.05, np.float32)))
     raise ValueError(f"unknown workload {name}")
 
 
@@ -181,6 +196,8 @@ def _oracle_eval(args):
     if wl["goal"] is not None:
         gp, gq, idx = wl["goal"]
         kw = dict(goal_pos=gp, goal_quat=gq, idxs_goal=idx[lo:hi])
+    for k, v in wl.get("extra", {}).items():
+        kw[k] = v[lo:hi]
     t0 = time.perf_counter()
     O.rollout_cost_grad(wl["robot"], q, wl["cfg"].to_oracle_cfg(wl["robot"].num_tool_frames), world_cuboid=wl["cuboid"],
                         world_voxel=vox, **kw)
@@ -243,7 +260,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="franka_ik_512x32_cuboid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extra-workloads", default="g1_29_8192_esdf,franka_16384_esdf",
+    ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
                     help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -266,10 +283,11 @@ def main():
         wl = make_workload(wl_name, seed_offset=rank)
         eng = build_engine(wl, device)
         q = torch.as_tensor(wl["q"]).to(device)
+        kw = {k: torch.as_tensor(v).to(device) for k, v in wl.get("extra", {}).items()}
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)       # 2x the 126 MB L2
         stream = torch.cuda.current_stream(device)
         for _ in range(warmup):
-            eng.evaluate_action(q)
+            eng.evaluate_action(q, **kw)
         torch.cuda.synchronize(device)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -282,13 +300,14 @@ def main():
         for i in range(steps):
             flush.fill_(i & 0xFF)                           # evict L2 between timed steps (outside the event pair)
             starts[i].record(stream)
-            eng.evaluate_action(q)
+            eng.evaluate_action(q, **kw)
             ends[i].record(stream)
         torch.cuda.synchronize(device)
         if world > 1:
             dist.barrier()
         clocks = sampler.stop() if sampler else None
         ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        wl["kw"] = kw
         return wl, eng, q, float(sum(ms)), ms, clocks
 
     wl, eng, q, total_ms, ms_list, clocks = timed_run(args.workload, args.steps, args.warmup, rank == 0)
@@ -306,7 +325,7 @@ def main():
     grad_host = torch.empty((wl["B"], wl["H"], wl["robot"].num_dof), dtype=torch.float32).pin_memory()
     for _ in range(3):
         q_dev.copy_(q_host, non_blocking=True)
-        o = eng.evaluate_action(q_dev)
+        o = eng.evaluate_action(q_dev, **wl["kw"])
         cost_host.copy_(o.cost, non_blocking=True)
         grad_host.copy_(o.grad_q, non_blocking=True)
     torch.cuda.synchronize(device)
@@ -316,7 +335,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         q_dev.copy_(q_host, non_blocking=True)
-        o = eng.evaluate_action(q_dev)
+        o = eng.evaluate_action(q_dev, **wl["kw"])
         cost_host.copy_(o.cost, non_blocking=True)
         grad_host.copy_(o.grad_q, non_blocking=True)
     e1.record()

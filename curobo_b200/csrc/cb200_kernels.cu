@@ -11,6 +11,7 @@
 //   tool_pose_kernel, cspace_state_kernel, cspace_position_kernel   drop-ins for the Warp cost kernels
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -95,9 +96,144 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
 }
 
 // ------------------------------------------------------------------------------------------------
-// THE fused kernel (discrete scene collision; rows independent)
+// Row phases shared by the two fused kernels.
+//   phase A: q load + c-space cost, FK, spheres (+ padded copy), tool poses + tool-pose cost
+//   phase B: self collision, scene collision (discrete | swept + speed metric), J^T backward, row cost
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerCta * 32) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
+__device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
+                                            int b, int h, float &cs_cost, float &pose_c) {
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int D = rv.D, S = rv.S, L = rv.L;
+  cs_cost = 0.0f;
+  for (int d = lane; d < D; d += 32) {
+    const float qd = __ldg(a.q + (size_t)e * D + d);
+    es.qv[d] = qd;
+    float gp;
+    const float c = cspace_dof(a, rv, e, b, d, qd, gp);
+    es.gqv[d] = gp;
+    cs_cost += c;
+    if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
+  }
+  __syncwarp();
+  warp_fk(rv, es, lane);
+  warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr);
+  pose_c = 0.0f;
+  const bool do_pose = (a.goal_position != nullptr);
+  for (int t = lane; t < L; t += 32) {
+    const float *T = es.cumul + 12 * rv.tool_map[t];
+    const V3 p = mk3(T[3], T[7], T[11]);
+    const Q4 qt = quat_from_transform(T);
+    if (a.link_pos) {
+      float *o = a.link_pos + ((size_t)e * L + t) * 3;
+      o[0] = p.x;
+      o[1] = p.y;
+      o[2] = p.z;
+    }
+    if (a.link_quat) *reinterpret_cast<float4 *>(a.link_quat + ((size_t)e * L + t) * 4) = make_float4(qt.w, qt.x, qt.y, qt.z);
+    float *pg = es.pose_g + 8 * t;
+    pg[0] = pg[1] = pg[2] = pg[4] = pg[5] = pg[6] = 0.0f;
+    if (do_pose) {
+      const int gi = a.idxs_goal ? __ldg(a.idxs_goal + b) : 0;
+      const bool term = !(h < a.H - 1 && a.H > 1);
+      const float *axes = term ? a.pose_axes_t : a.pose_axes_nt;
+      const float *tol = term ? a.pose_tol_t : a.pose_tol_nt;
+      const size_t go = ((size_t)gi * L + t) * cfg.num_goalset;
+      const PoseOut po = tool_pose_cost(p, qt, a.goal_position + go * 3, a.goal_quat + go * 4, cfg.num_goalset,
+                                        cfg.pose_weight[0], cfg.pose_weight[1], axes ? axes + 6 * t : nullptr,
+                                        tol ? __ldg(tol + 2 * t) : 0.0f, tol ? __ldg(tol + 2 * t + 1) : 0.0f,
+                                        cfg.pose_rotation_method);
+      const V3 om = quat_grad_to_omega(qt, po.gq_w, po.gq_x, po.gq_y, po.gq_z);
+      pg[0] = po.g_pos.x;
+      pg[1] = po.g_pos.y;
+      pg[2] = po.g_pos.z;
+      pg[4] = om.x;
+      pg[5] = om.y;
+      pg[6] = om.z;
+      pose_c += po.pos_cost + po.rot_cost;
+      if (a.pose_cost) {
+        a.pose_cost[((size_t)e * L + t) * 2] = po.pos_cost;
+        a.pose_cost[((size_t)e * L + t) * 2 + 1] = po.rot_cost;
+      }
+      if (a.pose_goalset_idx) a.pose_goalset_idx[(size_t)e * L + t] = po.goal_idx;
+    }
+  }
+  __syncwarp();
+}
+
+template <bool SWEEP>
+__device__ __forceinline__ void row_phase_b(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
+                                            int b, float cs_cost, float pose_c, const float4 *prev_sph,
+                                            const float4 *next_sph) {
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int D = rv.D, S = rv.S;
+  // ---- self collision (reads padded spheres in gsph)
+  float self_c = 0.0f, fmax_ = 0.0f;
+  int bi = 0, bj = 0;
+  if (cfg.self_weight > 0.0f && rv.P > 0) {
+    fmax_ = warp_self_collision_pairs(es.gsph, rv.pairs, rv.P, lane, bi, bj);
+    self_c = (fmax_ > 0.0f) ? 0.5f * cfg.self_weight * fmax_ : 0.0f;
+  }
+  if (a.self_cost && lane == 0) a.self_cost[e] = self_c;
+  __syncwarp();
+  // ---- scene collision (lane per sphere) -> gsph = gradient
+  float scene_c = 0.0f;
+  const bool do_scene = cfg.scene_weight > 0.0f && (a.cuboids.inv_pose != nullptr || a.voxels.inv_pose != nullptr);
+  const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
+  const float sdt = (SWEEP && cfg.use_speed_metric && a.dt != nullptr) ? __ldg(a.dt) : 0.0f;
+  for (int s = lane; s < S; s += 32) {
+    V3 g = mk3(0, 0, 0);
+    float c = 0.0f;
+    if (do_scene) {
+      const float4 sp = es.sph[s];
+      const V3 cen = mk3(sp.x, sp.y, sp.z);
+      if (!SWEEP) {
+        c = sphere_scene_discrete(cen, sp.w, cfg.scene_activation, cfg.scene_weight, a.cuboids, a.voxels, env, g);
+      } else {
+        V3 pv = cen, nx = cen;
+        if (prev_sph != nullptr) {
+          const float4 t = prev_sph[s];
+          pv = mk3(t.x, t.y, t.z);
+        }
+        if (next_sph != nullptr) {
+          const float4 t = next_sph[s];
+          nx = mk3(t.x, t.y, t.z);
+        }
+        c = sphere_scene_swept(cen, sp.w, cfg.scene_activation, cfg.scene_weight, prev_sph != nullptr, pv,
+                               next_sph != nullptr, nx, a.cuboids, a.voxels, env, g);
+        if (cfg.use_speed_metric && prev_sph != nullptr && next_sph != nullptr) speed_metric(pv, cen, nx, sdt, c, g);
+      }
+    }
+    es.gsph[s] = make_float4(g.x, g.y, g.z, 0.0f);
+    scene_c += c;
+    if (a.scene_cost) a.scene_cost[(size_t)e * S + s] = c;
+  }
+  __syncwarp();
+  if (fmax_ > 0.0f && lane == 0) {
+    const float4 pi = es.sph[bi], pj = es.sph[bj];
+    const float w = cfg.self_weight;
+    float4 gi = es.gsph[bi], gj = es.gsph[bj];
+    const float gx = w * (pj.x - pi.x), gy = w * (pj.y - pi.y), gz = w * (pj.z - pi.z);
+    gi.x += gx;
+    gi.y += gy;
+    gi.z += gz;
+    gj.x -= gx;
+    gj.y -= gy;
+    gj.z -= gz;
+    es.gsph[bi] = gi;
+    es.gsph[bj] = gj;
+  }
+  __syncwarp();
+  warp_fk_backward(rv, es, lane, a.grad_q + (size_t)e * D);
+  const float tot = warp_sum(cs_cost + pose_c + scene_c) + self_c;
+  if (lane == 0) a.cost[e] = tot;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE fused kernel, discrete scene collision: rows are independent, one warp per row.
+// ------------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
@@ -105,116 +241,74 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) rollout_fused_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float *base = reinterpret_cast<float *>(smem + a.blob_smem_bytes) + (size_t)warp * a.eval_floats;
   const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L);
-  const cb200_rollout_cfg &cfg = a.cfg;
   const int N = a.B * a.H;
-  const int D = rv.D, S = rv.S, L = rv.L;
-  const bool do_pose = (a.goal_position != nullptr);
-
   for (int e = blockIdx.x * nwarps + warp; e < N; e += gridDim.x * nwarps) {
     const int b = e / a.H, h = e - b * a.H;
-    // ---- load q, c-space cost (lane per dof)
-    float cs_cost = 0.0f;
-    for (int d = lane; d < D; d += 32) {
-      const float qd = __ldg(a.q + (size_t)e * D + d);
-      es.qv[d] = qd;
-      float gp;
-      const float c = cspace_dof(a, rv, e, b, d, qd, gp);
-      es.gqv[d] = gp;
-      cs_cost += c;
-      if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
+    float cs_cost, pose_c;
+    row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    row_phase_b<false>(a, rv, es, lane, e, b, cs_cost, pose_c, nullptr, nullptr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE fused kernel, trajectory mode (swept scene collision + speed metric couple row h to h-1, h+1).
+// A CTA walks tiles of `nwarps` consecutive waypoints of one seed: every warp runs phase A for its
+// waypoint (warp 0 / the last warp also compute the halo waypoints' spheres), the CTA synchronises, then
+// every warp runs phase B reading its neighbours' sphere positions from shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ unsigned long long mbar;
+  stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
+  const RobotView rv = make_robot_view(smem, a.blob);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float *all = reinterpret_cast<float *>(smem + a.blob_smem_bytes);
+  const EvalSmem es = carve_eval_smem(all + (size_t)warp * a.eval_floats, rv.nl, rv.D, rv.S, rv.L);
+  float4 *halo_prev = reinterpret_cast<float4 *>(all + (size_t)nwarps * a.eval_floats);
+  float4 *halo_next = halo_prev + rv.S;
+  const int D = rv.D, S = rv.S;
+  const int tiles_per_seed = (a.H + nwarps - 1) / nwarps;
+  const long long n_tiles = (long long)a.B * tiles_per_seed;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = (int)(tile / tiles_per_seed);
+    const int h0 = (int)(tile - (long long)b * tiles_per_seed) * nwarps;
+    const int h = h0 + warp;
+    const bool active = h < a.H;
+    // halo waypoints: spheres only
+    int hh = -1;
+    float4 *hdst = nullptr;
+    if (warp == 0 && h0 > 0) {
+      hh = h0 - 1;
+      hdst = halo_prev;
+    } else if (warp == nwarps - 1 && h0 + nwarps < a.H) {
+      hh = h0 + nwarps;
+      hdst = halo_next;
     }
-    __syncwarp();
-    // ---- FK
-    warp_fk(rv, es, lane);
-    warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr);
-    // ---- tool poses + pose cost (lane per tool frame)
-    float pose_c = 0.0f;
-    for (int t = lane; t < L; t += 32) {
-      const float *T = es.cumul + 12 * rv.tool_map[t];
-      const V3 p = mk3(T[3], T[7], T[11]);
-      const Q4 qt = quat_from_transform(T);
-      if (a.link_pos) {
-        float *o = a.link_pos + ((size_t)e * L + t) * 3;
-        o[0] = p.x;
-        o[1] = p.y;
-        o[2] = p.z;
+    if (hh >= 0) {
+      const size_t eh = (size_t)b * a.H + hh;
+      for (int d = lane; d < D; d += 32) es.qv[d] = __ldg(a.q + eh * D + d);
+      __syncwarp();
+      warp_fk(rv, es, lane);
+      for (int s = lane; s < S; s += 32) {
+        const float *T = es.cumul + 12 * rv.sph_link[s];
+        const float4 p = rv.spheres[s];
+        hdst[s] = make_float4(T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3], T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7],
+                              T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11], p.w);
       }
-      if (a.link_quat) *reinterpret_cast<float4 *>(a.link_quat + ((size_t)e * L + t) * 4) = make_float4(qt.w, qt.x, qt.y, qt.z);
-      float *pg = es.pose_g + 8 * t;
-      pg[0] = pg[1] = pg[2] = pg[4] = pg[5] = pg[6] = 0.0f;
-      if (do_pose) {
-        const int gi = a.idxs_goal ? __ldg(a.idxs_goal + b) : 0;
-        const bool term = !(h < a.H - 1 && a.H > 1);
-        const float *axes = term ? a.pose_axes_t : a.pose_axes_nt;
-        const float *tol = term ? a.pose_tol_t : a.pose_tol_nt;
-        const size_t go = ((size_t)gi * L + t) * cfg.num_goalset;
-        const PoseOut po = tool_pose_cost(p, qt, a.goal_position + go * 3, a.goal_quat + go * 4, cfg.num_goalset,
-                                          cfg.pose_weight[0], cfg.pose_weight[1], axes ? axes + 6 * t : nullptr,
-                                          tol ? __ldg(tol + 2 * t) : 0.0f, tol ? __ldg(tol + 2 * t + 1) : 0.0f,
-                                          cfg.pose_rotation_method);
-        const V3 om = quat_grad_to_omega(qt, po.gq_w, po.gq_x, po.gq_y, po.gq_z);
-        pg[0] = po.g_pos.x;
-        pg[1] = po.g_pos.y;
-        pg[2] = po.g_pos.z;
-        pg[4] = om.x;
-        pg[5] = om.y;
-        pg[6] = om.z;
-        pose_c += po.pos_cost + po.rot_cost;
-        if (a.pose_cost) {
-          a.pose_cost[((size_t)e * L + t) * 2] = po.pos_cost;
-          a.pose_cost[((size_t)e * L + t) * 2 + 1] = po.rot_cost;
-        }
-        if (a.pose_goalset_idx) a.pose_goalset_idx[(size_t)e * L + t] = po.goal_idx;
-      }
+      __syncwarp();
     }
-    __syncwarp();
-    // ---- self collision (reads padded spheres in gsph)
-    float self_c = 0.0f, fmax_ = 0.0f;
-    int bi = 0, bj = 0;
-    if (cfg.self_weight > 0.0f && rv.P > 0) {
-      fmax_ = warp_self_collision_pairs(es.gsph, rv.pairs, rv.P, lane, bi, bj);
-      self_c = (fmax_ > 0.0f) ? 0.5f * cfg.self_weight * fmax_ : 0.0f;
+    const int e = b * a.H + h;
+    float cs_cost = 0.0f, pose_c = 0.0f;
+    if (active) row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    __syncthreads();
+    if (active) {
+      const float4 *prev = nullptr, *next = nullptr;
+      if (h > 0) prev = (warp > 0) ? reinterpret_cast<const float4 *>(all + (size_t)(warp - 1) * a.eval_floats + rv.nl * 12) : halo_prev;
+      if (h < a.H - 1) next = (warp < nwarps - 1) ? reinterpret_cast<const float4 *>(all + (size_t)(warp + 1) * a.eval_floats + rv.nl * 12) : halo_next;
+      row_phase_b<true>(a, rv, es, lane, e, b, cs_cost, pose_c, prev, next);
     }
-    if (a.self_cost && lane == 0) a.self_cost[e] = self_c;
-    __syncwarp();
-    // ---- scene collision (lane per sphere) -> gsph = gradient
-    float scene_c = 0.0f;
-    const bool do_scene = cfg.scene_weight > 0.0f && (a.cuboids.inv_pose != nullptr || a.voxels.inv_pose != nullptr);
-    const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
-    for (int s = lane; s < S; s += 32) {
-      V3 g = mk3(0, 0, 0);
-      float c = 0.0f;
-      if (do_scene) {
-        const float4 sp = es.sph[s];
-        c = sphere_scene_discrete(mk3(sp.x, sp.y, sp.z), sp.w, cfg.scene_activation, cfg.scene_weight, a.cuboids,
-                                  a.voxels, env, g);
-      }
-      es.gsph[s] = make_float4(g.x, g.y, g.z, 0.0f);
-      scene_c += c;
-      if (a.scene_cost) a.scene_cost[(size_t)e * S + s] = c;
-    }
-    __syncwarp();
-    if (fmax_ > 0.0f && lane == 0) {
-      const float4 pi = es.sph[bi], pj = es.sph[bj];
-      const float w = cfg.self_weight;
-      float4 gi = es.gsph[bi], gj = es.gsph[bj];
-      const float gx = w * (pj.x - pi.x), gy = w * (pj.y - pi.y), gz = w * (pj.z - pi.z);
-      gi.x += gx;
-      gi.y += gy;
-      gi.z += gz;
-      gj.x -= gx;
-      gj.y -= gy;
-      gj.z -= gz;
-      es.gsph[bi] = gi;
-      es.gsph[bj] = gj;
-    }
-    __syncwarp();
-    // ---- backward
-    warp_fk_backward(rv, es, lane, a.grad_q + (size_t)e * D);
-    // ---- total cost for the row
-    const float tot = warp_sum(cs_cost + pose_c + scene_c) + self_c;
-    if (lane == 0) a.cost[e] = tot;
-    __syncwarp();
+    __syncthreads();
   }
 }
 
@@ -302,7 +396,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) kin_backward_kernel(const _
   extern __shared__ __align__(16) float fsm[];
   // CTA-shared: ancestor masks [nl] (uint64)
   unsigned long long *anc = reinterpret_cast<unsigned long long *>(fsm);
-  float *wbase = fsm + 2 * a.nl + (size_t)(threadIdx.x >> 5) * (a.nl * 12 + a.nl * 8 + a.nl + a.D);
+  const int anc_floats = (2 * a.nl + 3) & ~3, per_warp = (a.nl * 12 + a.nl * 8 + a.nl + a.D + 3) & ~3;  // keep float4 alignment
+  float *wbase = fsm + anc_floats + (size_t)(threadIdx.x >> 5) * per_warp;
   float *cumul = wbase, *ft = wbase + a.nl * 12, *contrib = ft + a.nl * 8, *gq = contrib + a.nl;
   if (threadIdx.x == 0) {
     anc[0] = 1ull;
@@ -698,6 +793,7 @@ __global__ void __launch_bounds__(128) cspace_position_kernel(const __grid_const
 thread_local int g_last_err = 0;
 inline int ret(cudaError_t e) {
   g_last_err = (int)e;
+  if (e != cudaSuccess) (void)cudaGetLastError();  // do not leave a stale error for the caller's next CUDA call
   return (int)e;
 }
 inline int launch_status() { return ret(cudaGetLastError()); }
@@ -820,8 +916,8 @@ int cb200_kinematics_backward(float *grad_out, const float *grad_nlinks_pos, con
   KinBwdArgs a{grad_out, grad_nlinks_pos, grad_nlinks_quat, num_spheres > 0 ? grad_spheres : nullptr, global_cumul_mat,
                robot_spheres, joint_offset_map, link_map, joint_map, tool_frame_map, link_sphere_map, joint_map_type,
                env_query_idx, num_envs, batch_size, horizon, n_joints, num_spheres, num_links, n_tool_frames};
-  const size_t per_warp = (size_t)num_links * 12 + num_links * 8 + num_links + n_joints;
-  const size_t smem = ((size_t)2 * num_links + kWarpsPerCta * per_warp) * sizeof(float);
+  const size_t per_warp = ((size_t)num_links * 12 + num_links * 8 + num_links + n_joints + 3) & ~(size_t)3;
+  const size_t smem = ((((size_t)2 * num_links + 3) & ~(size_t)3) + kWarpsPerCta * per_warp) * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kin_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return ret(e);
@@ -1104,7 +1200,6 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   if (cfg == nullptr || io == nullptr || io->q == nullptr || io->robot_blob == nullptr || io->cost == nullptr ||
       io->grad_q == nullptr || io->batch_size < 0 || io->horizon < 1)
     return ret(cudaErrorInvalidValue);
-  if (cfg->use_sweep != 0) return ret(cudaErrorNotSupported);  // swept rollout: see cb200_rollout_traj (next)
   if (io->goal_position != nullptr && (io->goal_quat == nullptr || cfg->num_goalset < 1)) return ret(cudaErrorInvalidValue);
   const long long N = (long long)io->batch_size * io->horizon;
   if (N == 0) return ret(cudaSuccess);
@@ -1149,39 +1244,68 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   a.blob_smem_bytes = h.smem_bytes;
   a.eval_floats = eval_smem_floats(h.nl, h.D, h.S, h.L);
   DevInfo &d = dev_info();
+  const bool traj = cfg->use_sweep != 0;
+  if (traj && cfg->use_speed_metric && io->dt == nullptr) return ret(cudaErrorInvalidValue);
+  // register cap variant (CTAs/SM the compiler must allow at 256 threads): tuning knob, default from measurements
+  static const int minb = []() {
+    const char *e = getenv("CB200_MINB");
+    const int v = e ? atoi(e) : 2;
+    return (v == 3 || v == 4) ? v : 2;
+  }();
+  using KernelT = void (*)(const FusedArgs);
+  static KernelT const table[2][3] = {{rollout_fused_kernel<2>, rollout_fused_kernel<3>, rollout_fused_kernel<4>},
+                                      {rollout_traj_kernel<2>, rollout_traj_kernel<3>, rollout_traj_kernel<4>}};
+  KernelT kern = table[traj ? 1 : 0][minb - 2];
   // warps per CTA: the count that keeps the most warps resident per SM (shared memory is the limiter for
-  // big robots); ties go to the larger CTA so the blob is staged fewer times.  Cached per blob geometry.
-  static thread_local int cached_key = -1, cached_nw = 0, cached_grid_per_sm = 0;
-  const int key = h.smem_bytes * 131 + a.eval_floats;
-  if (key != cached_key) {
-    const size_t max_need = (size_t)h.smem_bytes + (size_t)kWarpsPerCta * a.eval_floats * sizeof(float);
-    const size_t cap = std::min(max_need, (size_t)d.max_smem);
-    cudaError_t e = cudaFuncSetAttribute(rollout_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+  // big robots); ties go to the larger CTA so the blob is staged fewer times.  Cached per (kernel, geometry).
+  struct Plan {
+    long long key = -1;
+    int nw = 0, per_sm = 0;
+  };
+  static thread_local Plan plans[2];
+  Plan &pl = plans[traj ? 1 : 0];
+  const size_t halo_bytes = traj ? (size_t)2 * h.S * sizeof(float4) : 0;
+  const long long key = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ (long long)minb ^
+                        (traj ? ((long long)io->horizon << 40) : 0);
+  if (key != pl.key) {
+    cudaFuncAttributes fa;
+    cudaError_t e0 = cudaFuncGetAttributes(&fa, kern);
+    if (e0 != cudaSuccess) return ret(e0);
+    const size_t limit = (size_t)d.max_smem - fa.sharedSizeBytes;  // opt-in limit covers static + dynamic
+    const size_t max_need = (size_t)h.smem_bytes + halo_bytes + (size_t)kWarpsPerCta * a.eval_floats * sizeof(float);
+    const size_t cap = std::min(max_need, limit);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
     if (e != cudaSuccess) return ret(e);
-    int best_nw = 0, best_warps = 0, best_per_sm = 0;
+    int best_nw = 0, best_per_sm = 0;
+    double best_score = 0.0;
     for (int nw = kWarpsPerCta; nw >= 1; --nw) {
-      const size_t need = (size_t)h.smem_bytes + (size_t)nw * a.eval_floats * sizeof(float);
-      if (need > (size_t)d.max_smem) continue;
+      const size_t need = (size_t)h.smem_bytes + halo_bytes + (size_t)nw * a.eval_floats * sizeof(float);
+      if (need > limit) continue;
       int per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_fused_kernel, nw * 32, need) != cudaSuccess) continue;
-      if (per_sm * nw > best_warps) {
-        best_warps = per_sm * nw;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, need) != cudaSuccess) continue;
+      double score = (double)per_sm * nw;
+      if (traj) {  // rows of the last tile of a trajectory idle, and halo waypoints cost 2 extra FK per tile
+        const int tiles = (io->horizon + nw - 1) / nw;
+        score *= (double)io->horizon / ((double)tiles * nw + 0.3 * 2.0 * (tiles - 1));
+      }
+      if (score > best_score) {
+        best_score = score;
         best_nw = nw;
         best_per_sm = per_sm;
       }
     }
     if (best_nw == 0) return ret(cudaErrorInvalidConfiguration);
-    cached_key = key;
-    cached_nw = best_nw;
-    cached_grid_per_sm = best_per_sm;
+    pl.key = key;
+    pl.nw = best_nw;
+    pl.per_sm = best_per_sm;
   }
-  const int nw = cached_nw;
-  const size_t smem = (size_t)h.smem_bytes + (size_t)nw * a.eval_floats * sizeof(float);
-  long long grid_ll = (long long)d.sm_count * cached_grid_per_sm;
-  const long long need_ctas = (N + nw - 1) / nw;
+  const int nw = pl.nw;
+  const size_t smem = (size_t)h.smem_bytes + halo_bytes + (size_t)nw * a.eval_floats * sizeof(float);
+  long long grid_ll = (long long)d.sm_count * pl.per_sm;
+  const long long need_ctas = traj ? (long long)io->batch_size * ((io->horizon + nw - 1) / nw) : (N + nw - 1) / nw;
   if (grid_ll > need_ctas) grid_ll = need_ctas;
   const int grid = (int)(grid_ll < 1 ? 1 : grid_ll);
-  rollout_fused_kernel<<<grid, nw * 32, smem, (cudaStream_t)stream>>>(a);
+  kern<<<grid, nw * 32, smem, (cudaStream_t)stream>>>(a);
   return launch_status();
 }
 

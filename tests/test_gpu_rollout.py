@@ -262,3 +262,75 @@ def test_autograd_function_and_errors():
         eng.evaluate_action(torch.zeros((64, 2, 7), device=DEV)[:, ::2])   # non-contiguous
     with pytest.raises(ValueError):
         RolloutEngine(rm, RolloutConfig.ik(), "cpu")
+
+
+# ------------------------------------------------------------------------------------------------
+# trajectory mode (swept scene collision + speed metric): rollout_traj_kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H", [(4, 12), (3, 30), (5, 5), (2, 81), (6, 1), (3, 8), (3, 9)])
+@pytest.mark.parametrize("speed", [True, False])
+def test_traj_rollout_vs_oracle(B, H, speed):
+    """configs 3/4 shape: Franka trajectories, 64^3 ESDF + cuboids, swept (3 steps each side) + speed metric,
+    STATE c-space with retimed weights, terminal-only pose cost (lbfgs_bspline_trajopt.yml)."""
+    rm = load_robot("franka")
+    q = random_walk_q(rm, B, H, seed=60 + H)
+    rng = np.random.default_rng(H)
+    dt = np.full(B, 0.05, np.float32)
+    v = np.gradient(q, axis=1).astype(np.float32) / 0.05 if H > 1 else np.zeros_like(q)
+    a_ = rng.normal(0, 5.0, size=q.shape).astype(np.float32)
+    j_ = rng.normal(0, 200.0, size=q.shape).astype(np.float32)
+    cfg = RolloutConfig.trajopt()
+    cfg.use_speed_metric = speed
+    cub, vox = make_benchmark_cuboid_world(), small_voxel_world()
+    gp, gq = goal_from_q(rm, random_q(rm, B, seed=61))
+    idx = np.arange(B, dtype=np.int32)
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    nt = torch.zeros((1, 6), dtype=torch.float32, device=DEV)
+    eng.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=nt)
+    out = eng.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
+    torch.cuda.synchronize()
+    ocfg = cfg.to_oracle_cfg(1)
+    ocfg["pose_non_terminal_axes"] = np.zeros((1, 6), np.float32)
+    want = O.rollout_cost_grad(rm, q, ocfg, world_cuboid=cub, world_voxel=vox, goal_pos=gp, goal_quat=gq, idxs_goal=idx,
+                               vel=v, acc=a_, jerk=j_, dt=dt)
+    np.testing.assert_allclose(out.scene_cost.cpu().numpy(), want["scene_cost"], rtol=2e-4,
+                               atol=1e-5 * max(want["scene_cost"].max(), 1e-6))
+    cost_close(out.self_cost.cpu().numpy(), want["self_cost"])
+    np.testing.assert_allclose(out.cost.cpu().numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+    # determinism
+    c1, g1 = out.cost.clone(), out.grad_q.clone()
+    out = eng.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
+    assert torch.equal(c1, out.cost) and torch.equal(g1, out.grad_q)
+
+
+def test_traj_full_size_mpc_properties():
+    """config 4 shape: 1024 particles x 30 horizon, swept + speed metric on the 256^3 ESDF.
+    fused == FK kernel + swept scene kernel (per-op) on the scene term; stationary trajectories == discrete."""
+    from curobo_b200.scene import SweptSphereObstacleCollision
+    rm = load_robot("franka")
+    B, H = 1024, 30
+    sdf = make_box_esdf(n=256, voxel_size=0.01, num_boxes=12, seed=0, xp=torch)
+    vox = VoxelData(T(np.array([[[256, 256, 256, 0.01]]], np.float32)), T(np.array([[[0, 0, 0, 1, 0, 0, 0, 0]]], np.float32)),
+                    torch.ones((1, 1), dtype=torch.uint8, device=DEV), torch.ones(1, dtype=torch.int32, device=DEV),
+                    sdf.reshape(1, 1, -1).contiguous(), 1, 1, 100.0)
+    q = T(random_walk_q(rm, B, H, seed=70))
+    dt = torch.full((B,), 0.05, dtype=torch.float32, device=DEV)
+    cfg = RolloutConfig(scene_weight=100000.0, scene_activation=0.0025, use_sweep=True, use_speed_metric=True)
+    eng = RolloutEngine(rm, cfg, DEV, voxel=vox)
+    o = eng.evaluate_action(q, dt=dt)
+    kin = Kinematics(rm, DEV)
+    st = kin.compute_kinematics(q)
+    buf = CollisionBuffer.from_shape((B, H, rm.num_spheres, 4), DEV)
+    d = SweptSphereObstacleCollision.apply(st.robot_spheres, buf, SceneData(None, vox), T(np.array([100000.0], np.float32)),
+                                           T(np.array([0.0025], np.float32)), None, dt[:1].contiguous(), True,
+                                           torch.zeros(B, dtype=torch.int32, device=DEV), False, False)
+    assert float(d.sum()) > 0
+    torch.testing.assert_close(o.scene_cost, d, rtol=1e-4, atol=1e-5 * float(d.max()))
+    # stationary trajectories: swept == discrete (reference property test_voxel_collision.py:1014)
+    qs = q[:, :1].expand(B, H, rm.num_dof).contiguous()
+    o_s = eng.evaluate_action(qs, dt=dt)
+    c_sw = o_s.scene_cost.clone()
+    eng_d = RolloutEngine(rm, RolloutConfig(scene_weight=100000.0, scene_activation=0.0025), DEV, voxel=vox)
+    c_d = eng_d.evaluate_action(qs).scene_cost
+    torch.testing.assert_close(c_sw, c_d, rtol=1e-5, atol=1e-6 * float(c_d.max()))
