@@ -60,7 +60,8 @@ def make_workload(name: str, seed_offset: int = 0):
         rname = {"g1_29_8192_esdf": "g1_29", "g1_43_8192_esdf": "g1_43", "franka_16384_esdf": "franka"}[name]
         rm = load_robot(rname)
         B, H = (16384 if rname == "franka" else 8192), 1
-        q = random_q(rm, B, seed=200 + seed_offset, scale=0.6)[:, None, :]
+        from helpers import humanoid_q
+        q = (humanoid_q(rm, B, seed=200 + seed_offset) if rname != "franka" else random_q(rm, B, seed=200 + seed_offset))[:, None, :]
         D, S, L = rm.num_dof, rm.num_spheres, rm.num_tool_frames
         bpe = 4 * D + 4 * D + 4 * (S + 1 + 2 * L + D) + 16 * S             # + 8 fp16 corners per sphere
         cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",

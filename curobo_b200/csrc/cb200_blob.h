@@ -38,8 +38,20 @@ struct BlobHeader {
   int32_t off_jl_idx;       // int16 [n joint links]
   int32_t off_limits;       // float [10*D]    pos lo|hi, vel lo|hi, acc lo|hi, jerk lo|hi, effort lo|hi
   int32_t off_pairs;        // int16 [P*2]     (i<j) -- NOT staged to shared memory
-  int32_t reserved[5];
+  // self-collision broad phase (the pair list is the union of link x link sphere blocks): collision links,
+  // their contiguous sphere ranges, link-frame bounding spheres and the list of checked link pairs.
+  // n_lp == 0 => pair list is not a union of full link blocks: kernels fall back to the explicit pair list.
+  int32_t n_cl, n_lp;
+  int32_t off_cl_link;      // int16 [n_cl]    link index of collision link a
+  int32_t off_cl_start;     // int16 [n_cl+1]  sphere range of collision link a
+  int32_t off_cl_bound;     // float4[n_cl]    bounding sphere (x,y,z,R) in the link frame; R < 0: no enabled sphere
+  int32_t off_lp;           // uint32[n_lp]    (a | b << 16), a < b, indices into the collision-link arrays
+  // FK compose schedule: one word per step = two (link, parent) byte pairs (0xFF = idle slot); links of one
+  // depth level are independent, so a step composes two of them with 12 lanes each.
+  int32_t n_fk_steps;
+  int32_t off_fk_sched;     // uint32[n_fk_steps]  l0 | p0<<8 | l1<<16 | p1<<24
+  int32_t reserved[13];
 };
-static_assert(sizeof(BlobHeader) == 128, "BlobHeader must be 128 bytes");
+static_assert(sizeof(BlobHeader) == 192, "BlobHeader must be 192 bytes");
 
 }  // namespace cb200

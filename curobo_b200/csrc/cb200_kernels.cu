@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "../../include/curobo_b200.h"
@@ -170,7 +171,8 @@ __device__ __forceinline__ void row_phase_b(const FusedArgs &a, const RobotView 
   float self_c = 0.0f, fmax_ = 0.0f;
   int bi = 0, bj = 0;
   if (cfg.self_weight > 0.0f && rv.P > 0) {
-    fmax_ = warp_self_collision_pairs(es.gsph, rv.pairs, rv.P, lane, bi, bj);
+    fmax_ = (rv.n_lp > 0) ? warp_self_collision_tiles(rv, es, lane, bi, bj)
+                          : warp_self_collision_pairs(es.gsph, rv.pairs, rv.P, lane, bi, bj);
     self_c = (fmax_ > 0.0f) ? 0.5f * cfg.self_weight * fmax_ : 0.0f;
   }
   if (a.self_cost && lane == 0) a.self_cost[e] = self_c;
@@ -223,7 +225,7 @@ __device__ __forceinline__ void row_phase_b(const FusedArgs &a, const RobotView 
     es.gsph[bj] = gj;
   }
   __syncwarp();
-  warp_fk_backward(rv, es, lane, a.grad_q + (size_t)e * D);
+  if (!warp_fk_backward_sparse(rv, es, lane, a.grad_q + (size_t)e * D)) warp_fk_backward(rv, es, lane, a.grad_q + (size_t)e * D);
   const float tot = warp_sum(cs_cost + pose_c + scene_c) + self_c;
   if (lane == 0) a.cost[e] = tot;
   __syncwarp();
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
   const RobotView rv = make_robot_view(smem, a.blob);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float *base = reinterpret_cast<float *>(smem + a.blob_smem_bytes) + (size_t)warp * a.eval_floats;
-  const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L);
+  const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
   const int N = a.B * a.H;
   for (int e = blockIdx.x * nwarps + warp; e < N; e += gridDim.x * nwarps) {
     const int b = e / a.H, h = e - b * a.H;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_traj_kernel(c
   const RobotView rv = make_robot_view(smem, a.blob);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float *all = reinterpret_cast<float *>(smem + a.blob_smem_bytes);
-  const EvalSmem es = carve_eval_smem(all + (size_t)warp * a.eval_floats, rv.nl, rv.D, rv.S, rv.L);
+  const EvalSmem es = carve_eval_smem(all + (size_t)warp * a.eval_floats, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
   float4 *halo_prev = reinterpret_cast<float4 *>(all + (size_t)nwarps * a.eval_floats);
   float4 *halo_next = halo_prev + rv.S;
   const int D = rv.D, S = rv.S;
@@ -1055,7 +1057,7 @@ int cb200_cspace_position_cost(float *out_cost, float *out_grad_p, float *out_gr
 }
 
 // ---- robot blob -------------------------------------------------------------------------------
-static int64_t blob_layout(const cb200_robot_sizes *sz, const int16_t *link_map, BlobHeader *h, int *n_joint_links) {
+static int64_t blob_layout(const cb200_robot_sizes *sz, const int16_t *link_map, BlobHeader *h, int n_lp_cap) {
   const int nl = sz->num_links, D = sz->num_dof, S = sz->num_spheres, L = sz->num_tool_frames, P = sz->num_pairs;
   if (nl < 1 || nl > kMaxLinks || D < 0 || S < 0 || L < 0 || P < 0) return -1;
   int n_levels = 1;
@@ -1100,16 +1102,27 @@ static int64_t blob_layout(const cb200_robot_sizes *sz, const int16_t *link_map,
   h->off_jl_off = take((int64_t)(D + 1) * 2);
   h->off_jl_idx = take((int64_t)nl * 2);
   h->off_limits = take((int64_t)10 * D * 4);
+  // broad-phase tables, sized for the worst case (every link a collision link, every link pair checked)
+  const int max_cl = std::min(nl, S);
+  h->off_cl_link = take((int64_t)max_cl * 2);
+  h->off_cl_start = take((int64_t)(max_cl + 1) * 2);
+  h->off_cl_bound = take((int64_t)max_cl * 16);
+  h->off_lp = take((int64_t)n_lp_cap * 4);
+  h->off_fk_sched = take((int64_t)nl * 4);
   h->smem_bytes = (int32_t)off;
   h->off_pairs = take((int64_t)P * 4);
   h->total_bytes = (int32_t)off;
-  (void)n_joint_links;
   return off;
+}
+
+static int lp_cap(const cb200_robot_sizes *sz) {
+  const int m = std::min(sz->num_links, sz->num_spheres);
+  return std::min(m * (m - 1) / 2, std::max(sz->num_pairs, 0));
 }
 
 int64_t cb200_robot_blob_bytes(const cb200_robot_sizes *sz) {
   BlobHeader h;
-  return blob_layout(sz, nullptr, &h, nullptr);
+  return blob_layout(sz, nullptr, &h, lp_cap(sz));
 }
 
 int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_sizes *sz, const float *fixed_transforms,
@@ -1120,7 +1133,7 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
                               const float *velocity_limits, const float *acceleration_limits, const float *jerk_limits,
                               const float *effort_limits) {
   BlobHeader h;
-  const int64_t total = blob_layout(sz, link_map, &h, nullptr);
+  const int64_t total = blob_layout(sz, link_map, &h, lp_cap(sz));
   if (total < 0) return total;
   if (out_bytes < total) return -3;
   const int nl = h.nl, D = h.D, S = h.S, L = h.L, P = h.P;
@@ -1174,6 +1187,22 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
       if (depth[l] == lev) lvl[n++] = (int16_t)l;
   }
   lvo[h.n_levels] = (int16_t)n;
+  {  // FK compose schedule: two independent links (same depth level) per step
+    uint32_t *sched = reinterpret_cast<uint32_t *>(o + h.off_fk_sched);
+    int steps = 0;
+    for (int lev = 1; lev < h.n_levels; ++lev) {
+      for (int i = lvo[lev]; i < lvo[lev + 1]; i += 2) {
+        const uint32_t l0 = (uint32_t)lvl[i], p0 = (uint32_t)link_map[l0];
+        uint32_t w = l0 | (p0 << 8) | 0xffff0000u;
+        if (i + 1 < lvo[lev + 1]) {
+          const uint32_t l1 = (uint32_t)lvl[i + 1], p1 = (uint32_t)link_map[l1];
+          w = l0 | (p0 << 8) | (l1 << 16) | (p1 << 24);
+        }
+        sched[steps++] = w;
+      }
+    }
+    reinterpret_cast<BlobHeader *>(o)->n_fk_steps = steps;
+  }
   // CSR joint -> links
   int16_t *jlo = reinterpret_cast<int16_t *>(o + h.off_jl_off);
   int16_t *jli = reinterpret_cast<int16_t *>(o + h.off_jl_idx);
@@ -1193,6 +1222,82 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
     if (i < 0 || j < 0 || i >= S || j >= S) return -8;
   }
   if (P) memcpy(o + h.off_pairs, collision_pairs, (size_t)P * 4);
+  // ---- self-collision broad phase: collision links = maximal runs of consecutive spheres on one link
+  {
+    std::vector<int> cl_link, cl_start, cl_of_sphere(S, 0);
+    bool ok = S > 0 && P > 0;
+    for (int s0 = 0; s0 < S; ++s0) {
+      if (s0 == 0 || link_sphere_map[s0] != link_sphere_map[s0 - 1]) {
+        for (int l : cl_link) ok = ok && (l != link_sphere_map[s0]);  // a link's spheres must be contiguous
+        cl_link.push_back(link_sphere_map[s0]);
+        cl_start.push_back(s0);
+      }
+      cl_of_sphere[s0] = (int)cl_link.size() - 1;
+    }
+    cl_start.push_back(S);
+    const int n_cl = (int)cl_link.size();
+    std::vector<unsigned char> checked((size_t)n_cl * n_cl, 0);
+    std::vector<uint32_t> lps;
+    long long covered = 0;
+    if (ok) {
+      for (int p = 0; p < P && ok; ++p) {
+        const int i = collision_pairs[2 * p], j = collision_pairs[2 * p + 1];
+        const int a = cl_of_sphere[i], b = cl_of_sphere[j];
+        ok = (i < j) && (a < b);
+        if (ok && !checked[(size_t)a * n_cl + b]) {
+          checked[(size_t)a * n_cl + b] = 1;
+          lps.push_back((uint32_t)a | ((uint32_t)b << 16));
+          covered += (long long)(cl_start[a + 1] - cl_start[a]) * (cl_start[b + 1] - cl_start[b]);
+        }
+      }
+      ok = ok && covered == P && (int)lps.size() <= lp_cap(sz);  // list == union of full link x link blocks
+    }
+    if (ok) {
+      std::sort(lps.begin(), lps.end(), [](uint32_t x, uint32_t y) {
+        return ((x & 0xffffu) != (y & 0xffffu)) ? (x & 0xffffu) < (y & 0xffffu) : (x >> 16) < (y >> 16);
+      });
+      BlobHeader *hh = reinterpret_cast<BlobHeader *>(o);
+      hh->n_cl = n_cl;
+      hh->n_lp = (int32_t)lps.size();
+      int16_t *cll = reinterpret_cast<int16_t *>(o + h.off_cl_link);
+      int16_t *cls = reinterpret_cast<int16_t *>(o + h.off_cl_start);
+      float *clb = reinterpret_cast<float *>(o + h.off_cl_bound);
+      for (int a = 0; a < n_cl; ++a) {
+        cll[a] = (int16_t)cl_link[a];
+        cls[a] = (int16_t)cl_start[a];
+        // bounding sphere of the enabled (padded radius >= 0) spheres: centroid + max(|p - c| + r)
+        double cx = 0, cy = 0, cz = 0;
+        int n = 0;
+        for (int s0 = cl_start[a]; s0 < cl_start[a + 1]; ++s0) {
+          if (link_spheres[4 * s0 + 3] + sphere_padding[s0] < 0.0f) continue;
+          cx += link_spheres[4 * s0];
+          cy += link_spheres[4 * s0 + 1];
+          cz += link_spheres[4 * s0 + 2];
+          ++n;
+        }
+        float R = -1.0f;
+        if (n > 0) {
+          cx /= n;
+          cy /= n;
+          cz /= n;
+          double r = 0;
+          for (int s0 = cl_start[a]; s0 < cl_start[a + 1]; ++s0) {
+            const double rr = (double)link_spheres[4 * s0 + 3] + sphere_padding[s0];
+            if (rr < 0) continue;
+            const double dx = link_spheres[4 * s0] - cx, dy = link_spheres[4 * s0 + 1] - cy, dz = link_spheres[4 * s0 + 2] - cz;
+            r = std::max(r, std::sqrt(dx * dx + dy * dy + dz * dz) + rr);
+          }
+          R = (float)(r * (1.0 + 1e-4) + 1e-5);  // conservative against fp32 rounding of the world transform
+        }
+        clb[4 * a] = (float)cx;
+        clb[4 * a + 1] = (float)cy;
+        clb[4 * a + 2] = (float)cz;
+        clb[4 * a + 3] = R;
+      }
+      cls[n_cl] = (int16_t)S;
+      memcpy(o + h.off_lp, lps.data(), lps.size() * 4);
+    }
+  }
   return total;
 }
 
@@ -1242,7 +1347,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   a.B = io->batch_size;
   a.H = io->horizon;
   a.blob_smem_bytes = h.smem_bytes;
-  a.eval_floats = eval_smem_floats(h.nl, h.D, h.S, h.L);
+  a.eval_floats = eval_smem_floats(h.nl, h.D, h.S, h.L, h.n_cl);
   DevInfo &d = dev_info();
   const bool traj = cfg->use_sweep != 0;
   if (traj && cfg->use_speed_metric && io->dt == nullptr) return ret(cudaErrorInvalidValue);

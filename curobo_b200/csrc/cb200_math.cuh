@@ -225,6 +225,10 @@ CB_HD SdfGrad voxel_sdf_grad(V3 p, const uint16_t *feat, int nx, int ny, int nz,
     bool z0k = z0 >= 0 && z0 < nz, z1k = z0 + 1 >= 0 && z0 + 1 < nz;
     const long long sx = (long long)ny * nz, sy = nz;
     const long long base = (long long)x0 * sx + (long long)y0 * sy + z0;
+    if (!((x0k || x1k) && (y0k || y1k) && (z0k || z1k))) {
+      out.sdf = max_dist;  // all 8 corners outside the grid: weight_sum == 0 -> max_dist (data_voxel.py:1019-1020)
+      return out;
+    }
     if (x0k && x1k && y0k && y1k && z0k && z1k) {
       const uint16_t *b = feat + base;
       float s000 = load_half(b), s001 = load_half(b + 1);

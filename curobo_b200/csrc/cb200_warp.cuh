@@ -33,6 +33,13 @@ struct RobotView {
   const int16_t *jl_idx;
   const float *limits;
   const uint32_t *pairs;  // global memory: one packed (i | j<<16) word per pair
+  int n_cl, n_lp;
+  const int16_t *cl_link;
+  const int16_t *cl_start;
+  const float4 *cl_bound;
+  const uint32_t *lp;
+  int n_fk_steps;
+  const uint32_t *fk_sched;
 };
 
 __device__ __forceinline__ RobotView make_robot_view(const unsigned char *smem_blob, const unsigned char *gmem_blob) {
@@ -62,6 +69,14 @@ __device__ __forceinline__ RobotView make_robot_view(const unsigned char *smem_b
   v.jl_idx = reinterpret_cast<const int16_t *>(smem_blob + h->off_jl_idx);
   v.limits = reinterpret_cast<const float *>(smem_blob + h->off_limits);
   v.pairs = reinterpret_cast<const uint32_t *>(gmem_blob + h->off_pairs);
+  v.n_cl = h->n_cl;
+  v.n_lp = h->n_lp;
+  v.cl_link = reinterpret_cast<const int16_t *>(smem_blob + h->off_cl_link);
+  v.cl_start = reinterpret_cast<const int16_t *>(smem_blob + h->off_cl_start);
+  v.cl_bound = reinterpret_cast<const float4 *>(smem_blob + h->off_cl_bound);
+  v.lp = reinterpret_cast<const uint32_t *>(smem_blob + h->off_lp);
+  v.n_fk_steps = h->n_fk_steps;
+  v.fk_sched = reinterpret_cast<const uint32_t *>(smem_blob + h->off_fk_sched);
   return v;
 }
 
@@ -75,18 +90,21 @@ struct EvalSmem {
   float *qv;      // [D]
   float *gqv;     // [D]  c-space position gradient
   float *pose_g;  // [L*8]  g_pos.xyz,_, omega.xyz,_
+  float4 *bc;     // [n_cl] world-frame bounding spheres of the collision links (self-collision broad phase)
 };
-__host__ __device__ inline int eval_smem_floats(int nl, int D, int S, int L) {
-  int n = nl * 12 + S * 8 + nl * 8 + nl + D + D + L * 8;
+__host__ __device__ inline int eval_smem_floats(int nl, int D, int S, int L, int n_cl) {
+  int n = nl * 12 + S * 8 + nl * 8 + n_cl * 4;   // float4-aligned part
+  n += nl + D + D + L * 8;
   return (n + 3) & ~3;
 }
-__device__ __forceinline__ EvalSmem carve_eval_smem(float *base, int nl, int D, int S, int L) {
+__device__ __forceinline__ EvalSmem carve_eval_smem(float *base, int nl, int D, int S, int L, int n_cl) {
   EvalSmem e;
   e.cumul = base;
   e.sph = reinterpret_cast<float4 *>(base + nl * 12);
   e.gsph = e.sph + S;
   e.ft = base + nl * 12 + S * 8;
-  e.contrib = e.ft + nl * 8;
+  e.bc = reinterpret_cast<float4 *>(e.ft + nl * 8);
+  e.contrib = e.ft + nl * 8 + n_cl * 4;
   e.qv = e.contrib + nl;
   e.gqv = e.qv + D;
   e.pose_g = e.gqv + D;
@@ -105,32 +123,32 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Reference semantics: kinematics_forward_helper.cuh:316-512.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es, int lane) {
+  // local transforms go to a scratch buffer (the not-yet-used sphere-gradient area) when it is large enough,
+  // so a compose step needs one warp barrier instead of two; otherwise they are composed in place.
+  const bool scratch = rv.S * 4 >= rv.nl * 12;
+  float *loc = scratch ? reinterpret_cast<float *>(es.gsph) : es.cumul;
   for (int l = lane; l < rv.nl; l += 32) {
     int jt = rv.joint_type[l];
     float th = 0.0f;
     if (jt >= 0) th = rv.joff[2 * l] * es.qv[rv.joint_map[l]] + rv.joff[2 * l + 1];
-    local_link_transform(rv.fixed + 12 * l, jt, th, es.cumul + 12 * l);
+    local_link_transform(rv.fixed + 12 * l, jt, th, (l == 0 ? es.cumul : loc) + 12 * l);
   }
   __syncwarp();
   const int sub = lane >> 4, k = lane & 15;
   const int r = k >> 2, c = k & 3;
-  for (int lev = 1; lev < rv.n_levels; ++lev) {
-    const int b = rv.level_off[lev], e = rv.level_off[lev + 1];
-    for (int i = b; i < e; i += 2) {
-      const bool act = (k < 12) && (i + sub < e);
-      float out = 0.0f;
-      int l = 0;
-      if (act) {
-        l = rv.level_links[i + sub];
-        const float *P = es.cumul + 12 * rv.link_map[l];
-        const float *Lm = es.cumul + 12 * l;
-        const float4 pr = *reinterpret_cast<const float4 *>(P + 4 * r);
-        out = pr.x * Lm[c] + pr.y * Lm[4 + c] + pr.z * Lm[8 + c] + (c == 3 ? pr.w : 0.0f);
-      }
-      __syncwarp();
-      if (act) es.cumul[12 * l + k] = out;
-      __syncwarp();
+  for (int st = 0; st < rv.n_fk_steps; ++st) {
+    const uint32_t w = rv.fk_sched[st] >> (16 * sub);
+    const int l = w & 0xff, par = (w >> 8) & 0xff;
+    const bool act = (k < 12) && (l != 0xff);
+    float out = 0.0f;
+    if (act) {
+      const float4 pr = *reinterpret_cast<const float4 *>(es.cumul + 12 * par + 4 * r);
+      const float *Lm = loc + 12 * l;
+      out = pr.x * Lm[c] + pr.y * Lm[4 + c] + pr.z * Lm[8 + c] + (c == 3 ? pr.w : 0.0f);
     }
+    if (!scratch) __syncwarp();
+    if (act) es.cumul[12 * l + k] = out;
+    __syncwarp();
   }
 }
 
@@ -186,6 +204,70 @@ __device__ __forceinline__ float warp_self_collision_pairs(const float4 *psph, c
   bi = (int)(pr & 0xffffu);
   bj = (int)(pr >> 16);
   return __uint_as_float(fb);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Self collision with a link-level broad phase.  The reference's pair list is the union of
+// (spheres of link a) x (spheres of link b) over the checked link pairs, and only pairs with
+// f = (ri+rj)^2 - |pi-pj|^2 > 0 can matter (the running max starts at 0, self_collision_helper.cuh:239,264).
+// If the bounding spheres of two links are disjoint no sphere pair of that block has f > 0, so the block is
+// skipped -- the result (f_max and the arg-max pair, ties to the first pair in list order = smallest (i,j))
+// is identical to scanning the whole list.  Lanes test 32 link pairs at a time; surviving blocks are scanned
+// with lanes over the flattened |a| x |b| tile.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, const EvalSmem &es, int lane, int &bi,
+                                                           int &bj) {
+  for (int a = lane; a < rv.n_cl; a += 32) {
+    const float4 c = rv.cl_bound[a];
+    const float *T = es.cumul + 12 * rv.cl_link[a];
+    es.bc[a] = make_float4(T[0] * c.x + T[1] * c.y + T[2] * c.z + T[3], T[4] * c.x + T[5] * c.y + T[6] * c.z + T[7],
+                           T[8] * c.x + T[9] * c.y + T[10] * c.z + T[11], c.w);
+  }
+  __syncwarp();
+  unsigned long long key = 0ull;  // f bits | ~i | ~j : max = largest f, then smallest i, then smallest j
+  for (int base = 0; base < rv.n_lp; base += 32) {
+    uint32_t pr = 0;
+    bool hit = false;
+    if (base + lane < rv.n_lp) {
+      pr = rv.lp[base + lane];
+      const float4 A = es.bc[pr & 0xffffu], B = es.bc[pr >> 16];
+      const float dx = A.x - B.x, dy = A.y - B.y, dz = A.z - B.z, rs = A.w + B.w;
+      hit = (A.w >= 0.0f) && (B.w >= 0.0f) && (dx * dx + dy * dy + dz * dz < rs * rs);
+    }
+    unsigned m = __ballot_sync(kFull, hit);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t q = __shfl_sync(kFull, pr, src);
+      const int a = q & 0xffffu, b = q >> 16;
+      const int sa = rv.cl_start[a], na = rv.cl_start[a + 1] - sa;
+      const int sb = rv.cl_start[b], nb = rv.cl_start[b + 1] - sb;
+      const float inv_nb = 1.0f / (float)nb;
+      for (int t = lane; t < na * nb; t += 32) {
+        const int io = (int)(((float)t + 0.5f) * inv_nb);
+        const int i = sa + io, j = sb + (t - io * nb);
+        const float4 x = es.gsph[i], y = es.gsph[j];
+        const float rs = x.w + y.w;
+        const float dx = x.x - y.x, dy = x.y - y.y, dz = x.z - y.z;
+        const float f = rs * rs - (dx * dx + dy * dy + dz * dz);
+        if (f > 0.0f && x.w >= 0.0f && y.w >= 0.0f) {
+          const unsigned long long k = ((unsigned long long)__float_as_uint(f) << 32) |
+                                       ((unsigned long long)(0xffffu - (unsigned)i) << 16) | (0xffffu - (unsigned)j);
+          key = k > key ? k : key;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(kFull, key, o);
+    key = other > key ? other : key;
+  }
+  bi = bj = 0;
+  if (key == 0ull) return 0.0f;
+  bi = 0xffff - (int)((key >> 16) & 0xffffu);
+  bj = 0xffff - (int)(key & 0xffffu);
+  return __uint_as_float((uint32_t)(key >> 32));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -253,6 +335,94 @@ __device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const Eval
     for (int i = rv.jl_off[d]; i < rv.jl_off[d + 1]; ++i) g += es.contrib[rv.jl_idx[i]];
     gq_out[d] = g;
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Same J^T backward, transposed for SPARSE sphere gradients (the common case: self-collision touches two
+// spheres, scene collision only the colliding ones): lanes own links (up to 64 = 2 per lane); every sphere
+// or tool frame with a non-zero gradient is broadcast to the warp and each lane whose link is an ancestor
+// adds  s * a . ((p - o) x g [+ omega])  (revolute) or  s * a . g  (prismatic)  -- the reference's per-sphere
+// chain walk (kinematics_backward_helper.cuh:15-99) with the chain laid across lanes.
+// Returns false (nothing written) when the gradient is dense; the caller then uses warp_fk_backward.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out) {
+  int nnz = 0;
+  for (int base = 0; base < rv.S; base += 32) {
+    const int s = base + lane;
+    bool nz = false;
+    if (s < rv.S) {
+      const float4 g = es.gsph[s];
+      nz = (g.x != 0.0f) || (g.y != 0.0f) || (g.z != 0.0f);
+    }
+    nnz += __popc(__ballot_sync(kFull, nz));
+  }
+  if (nnz > 2 * rv.nl) return false;
+  // per-lane link constants (slot 0: link lane, slot 1: link lane + 32)
+  V3 ax[2], og[2];
+  float sc[2];
+  int jt[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = lane + 32 * u;
+    jt[u] = -1;
+    sc[u] = 0.0f;
+    ax[u] = og[u] = mk3(0, 0, 0);
+    if (j < rv.nl) {
+      jt[u] = rv.joint_type[j];
+      if (jt[u] >= 0) {
+        const float *Tj = es.cumul + 12 * j;
+        const int a = (jt[u] >= JT_XR) ? jt[u] - JT_XR : jt[u];
+        ax[u] = mk3(Tj[a], Tj[4 + a], Tj[8 + a]);
+        og[u] = mk3(Tj[3], Tj[7], Tj[11]);
+        sc[u] = rv.joff[2 * j];
+      }
+    }
+  }
+  float acc[2] = {0.0f, 0.0f};
+  auto add = [&](unsigned long long mask, V3 p, V3 g, V3 om) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = lane + 32 * u;
+      if (jt[u] >= 0 && ((mask >> j) & 1ull)) {
+        acc[u] += (jt[u] >= JT_XR) ? sc[u] * (dot(ax[u], cross(p - og[u], g)) + dot(ax[u], om)) : sc[u] * dot(ax[u], g);
+      }
+    }
+  };
+  for (int base = 0; base < rv.S; base += 32) {
+    const int s = base + lane;
+    bool nz = false;
+    if (s < rv.S) {
+      const float4 g = es.gsph[s];
+      nz = (g.x != 0.0f) || (g.y != 0.0f) || (g.z != 0.0f);
+    }
+    unsigned m = __ballot_sync(kFull, nz);
+    while (m) {
+      const int ss = base + __ffs(m) - 1;
+      m &= m - 1;
+      const float4 g4 = es.gsph[ss], p4 = es.sph[ss];
+      add(rv.anc_mask[rv.sph_link[ss]], mk3(p4.x, p4.y, p4.z), mk3(g4.x, g4.y, g4.z), mk3(0, 0, 0));
+    }
+  }
+  for (int t = 0; t < rv.L; ++t) {
+    const float *pg = es.pose_g + 8 * t;
+    const V3 g = mk3(pg[0], pg[1], pg[2]), om = mk3(pg[4], pg[5], pg[6]);
+    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && om.x == 0.0f && om.y == 0.0f && om.z == 0.0f) continue;
+    const int k = rv.tool_map[t];
+    const float *Tk = es.cumul + 12 * k;
+    add(rv.anc_mask[k], mk3(Tk[3], Tk[7], Tk[11]), g, om);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = lane + 32 * u;
+    if (j < rv.nl) es.contrib[j] = acc[u];
+  }
+  __syncwarp();
+  for (int d = lane; d < rv.D; d += 32) {
+    float g = es.gqv[d];
+    for (int i = rv.jl_off[d]; i < rv.jl_off[d + 1]; ++i) g += es.contrib[rv.jl_idx[i]];
+    gq_out[d] = g;
+  }
+  return true;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -220,7 +220,7 @@ typedef struct {
   const float *vel, *acc, *jerk;  /* [B,H,D] or null (STATE c-space only) */
   const float *dt;                /* [B] or null */
   const void *robot_blob;         /* DEVICE copy of the blob packed by cb200_pack_robot_blob */
-  const void *robot_blob_host;    /* HOST copy of (at least the first 128 bytes of) the same blob */
+  const void *robot_blob_host;    /* HOST copy of the same blob (its 192-byte header is read on the host) */
   int32_t robot_blob_bytes;
   const cb200_cuboid_set *cuboids; /* host pointers to structs holding device pointers; may be null */
   const cb200_voxel_set *voxels;

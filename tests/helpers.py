@@ -17,6 +17,21 @@ def random_q(rm, n, seed=0, scale=1.0):
     return rng.uniform(mid - half, mid + half, size=(n, rm.num_dof)).astype(np.float32)
 
 
+def humanoid_q(rm, n, seed=0, scale=0.6):
+    """Floating-base humanoid standing inside a 2.56 m world: virtual base joints (base_j_*) near the origin,
+    pelvis ~0.8 m above the ground plane, small base rotations; other joints uniform in `scale` of their range."""
+    q = random_q(rm, n, seed=seed, scale=scale)
+    rng = np.random.default_rng(seed + 1000)
+    for d, name in enumerate(rm.joint_names):
+        if name in ("base_j_x", "base_j_y"):
+            q[:, d] = rng.uniform(-0.3, 0.3, size=n)
+        elif name == "base_j_z":
+            q[:, d] = rng.uniform(0.75, 0.85, size=n)
+        elif name.startswith("base_j_"):
+            q[:, d] = rng.uniform(-0.2, 0.2, size=n)
+    return q.astype(np.float32)
+
+
 def random_walk_q(rm, b, h, seed=0, sigma=0.05):
     rng = np.random.default_rng(seed)
     q0 = random_q(rm, b, seed=seed + 1, scale=0.8)

@@ -55,11 +55,13 @@ def test_robot_blob_layout(L, name):
     from curobo_b200.rollout import pack_robot_blob
     rm = load_robot(name)
     blob = pack_robot_blob(rm)
-    hdr = struct.unpack("<32i", blob[:128].tobytes())
+    hdr = struct.unpack("<48i", blob[:192].tobytes())
     magic, total, smem, nl, D, S, Lt, P, n_levels = hdr[:9]
     offs = dict(zip(["fixed", "joff", "link_map", "joint_map", "joint_type", "tool_map", "spheres", "sph_link",
                      "padding", "link_sph_off", "link_sph_idx", "level_off", "level_links", "anc_mask", "jl_off",
                      "jl_idx", "limits", "pairs"], hdr[9:27]))
+    n_cl, n_lp = hdr[27:29]
+    offs.update(dict(zip(["cl_link", "cl_start", "cl_bound", "lp"], hdr[29:33])))
     assert magic == 0x30324243 and total == blob.shape[0] and smem % 16 == 0 and smem <= total
     assert (nl, D, S, Lt, P) == (rm.num_links, rm.num_dof, rm.num_spheres, rm.num_tool_frames, rm.collision_pairs.shape[0])
     assert all(o % 16 == 0 for o in offs.values())
@@ -89,7 +91,28 @@ def test_robot_blob_layout(L, name):
     for l in range(nl):
         assert all(rm.link_sphere_idx_map[s] == l for s in lsi[lso[l]:lso[l + 1]])
     # smem budget: at least 4 warps of per-eval state + the staged blob fit the B200 opt-in limit (227 KB)
-    per_warp = (nl * 12 + S * 8 + nl * 8 + nl + 2 * D + Lt * 8 + 3) // 4 * 4 * 4
+    per_warp = (nl * 12 + S * 8 + nl * 8 + n_cl * 4 + nl + 2 * D + Lt * 8 + 3) // 4 * 4 * 4
+    # broad-phase tables: collision links partition the spheres; link pairs reproduce the pair list exactly
+    assert n_cl == len(rm.collision_link_names) and n_lp > 0
+    cls = view("cl_start", np.int16, n_cl + 1)
+    cll = view("cl_link", np.int16, n_cl)
+    lp = view("lp", np.uint32, n_lp)
+    assert cls[0] == 0 and cls[-1] == S and all(rm.link_sphere_idx_map[cls[a]] == cll[a] for a in range(n_cl))
+    rebuilt = set()
+    for w in lp:
+        a, b = int(w) & 0xffff, int(w) >> 16
+        rebuilt.update((i, j) for i in range(cls[a], cls[a + 1]) for j in range(cls[b], cls[b + 1]))
+    assert rebuilt == set(map(tuple, rm.collision_pairs.tolist()))
+    bnd = view("cl_bound", np.float32, 4 * n_cl).reshape(n_cl, 4)
+    for a in range(n_cl):
+        ids = np.arange(cls[a], cls[a + 1])
+        r = rm.link_spheres[ids, 3] + rm.sphere_padding[ids]
+        en = r >= 0
+        if en.any():
+            d = np.linalg.norm(rm.link_spheres[ids[en], :3] - bnd[a, :3], axis=1) + r[en]
+            assert (d <= bnd[a, 3]).all()
+        else:
+            assert bnd[a, 3] < 0
     assert smem + 4 * per_warp <= 227 * 1024, (smem, per_warp)
 
 

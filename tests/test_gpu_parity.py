@@ -157,7 +157,7 @@ def test_fk_backward_mimic_and_negative_axis():
     kin = Kinematics(rm, DEV)
     qt = T(q).requires_grad_(True)
     st = kin.compute_kinematics(qt)
-    np.testing.assert_allclose(st.robot_spheres.cpu().numpy().reshape(sph.shape), sph, atol=1e-6)
+    np.testing.assert_allclose(st.robot_spheres.detach().cpu().numpy().reshape(sph.shape), sph, atol=1e-6)
     ((st.robot_spheres.view(sph.shape) * T(gs)).sum() + (st.tool_pose_position.view(pos.shape) * T(gp)).sum()
      + (st.tool_pose_quaternion.view(quat.shape) * T(gq)).sum()).backward()
     grad_close(qt.grad.cpu().numpy(), O.fk_backward(rm, cum, gs, gp, gq))
@@ -174,7 +174,7 @@ def test_self_collision_vs_oracle_and_reference(robot, n):
     cost = SelfCollisionCost(rm, 5000.0, DEV)
     st = T(sph.reshape(n, 1, -1, 4)).requires_grad_(True)
     d = cost.forward(st)
-    got_c = d.cpu().numpy().reshape(n)
+    got_c = d.detach().cpu().numpy().reshape(n)
     np.testing.assert_allclose(got_c, want_c, rtol=1e-4, atol=1e-6 * want_c.max())
     got_g = cost._out_vec.cpu().numpy().reshape(want_g.shape)
     # identical worst pair (no exact ties on random inputs) -> identical sparsity pattern
@@ -196,7 +196,7 @@ def test_self_collision_lazy_zeroing_and_golden():
     rm = load_robot("franka")
     cost = SelfCollisionCost(rm, 5000.0, DEV)
     sph = g["spheres"].reshape(64, 1, -1, 4)
-    d1 = cost.forward(T(sph).requires_grad_(True)).cpu().numpy().reshape(-1)
+    d1 = cost.forward(T(sph).requires_grad_(True)).detach().cpu().numpy().reshape(-1)
     np.testing.assert_allclose(d1, g["self_cost"], rtol=1e-4, atol=1e-3)
     grad_close(cost._out_vec.cpu().numpy().reshape(g["self_grad"].shape), g["self_grad"])
     d2 = cost.forward(T(sph[::-1].copy()).requires_grad_(True))
@@ -334,7 +334,7 @@ def test_cspace_costs_vs_oracle():
     rm = load_robot("franka")
     rng = np.random.default_rng(3)
     B, H, D = 9, 7, 7
-    q = random_walk_q(rm, B, H, seed=3) * 1.05
+    q = rng.uniform(rm.position_limits[0] - 0.15, rm.position_limits[1] + 0.15, size=(B, H, D)).astype(np.float32)
     v, a, j = [rng.normal(0, s, size=(B, H, D)).astype(np.float32) for s in (2.0, 12.0, 400.0)]
     dt = rng.uniform(0.02, 0.2, size=B).astype(np.float32)
     lim = dict(p=rm.position_limits, v=rm.velocity_limits, a=rm.acceleration_limits, j=rm.jerk_limits, tau=rm.effort_limits)

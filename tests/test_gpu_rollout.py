@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import random_q, random_walk_q, small_voxel_world
+from helpers import humanoid_q, random_q, random_walk_q, small_voxel_world
 from curobo_b200.kinematics import Kinematics, SelfCollisionCost
 from curobo_b200.robot_model import load_robot
 from curobo_b200.rollout import FusedRolloutFunction, RolloutConfig, RolloutEngine
@@ -117,8 +117,8 @@ def test_humanoid_esdf_rollout_vs_oracle(robot, n):
         g = np.load(os.path.join(GOLD, "g1_29_esdf_rollout_b6.npz"))
         q = g["q"]
     else:
-        q = random_q(rm, n, seed=45, scale=0.6)[:, None, :]
-    gp, gq = goal_from_q(rm, random_q(rm, 3, seed=46, scale=0.5))
+        q = humanoid_q(rm, n, seed=45)[:, None, :]
+    gp, gq = goal_from_q(rm, humanoid_q(rm, 3, seed=46, scale=0.5))
     idx = (np.arange(q.shape[0]) % 3).astype(np.int32)
     cfg_pose = RolloutConfig(**{**cfg.__dict__, "pose_weight": (2000.0, 100.0)})
     check_against_oracle(rm, cfg_pose, q, vox=small_voxel_world(), goal=(gp, gq), idx=idx)
@@ -215,7 +215,7 @@ def test_full_size_humanoid_esdf_properties():
                     torch.ones((1, 1), dtype=torch.uint8, device=DEV), torch.ones(1, dtype=torch.int32, device=DEV),
                     sdf.reshape(1, 1, -1).contiguous(), 1, 1, 100.0)
     B = 1024
-    q = T(random_q(rm, B, seed=52, scale=0.5)[:, None, :])
+    q = T(humanoid_q(rm, B, seed=52, scale=0.5)[:, None, :])
     cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
                         cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0))
     eng = RolloutEngine(rm, cfg, DEV, voxel=vox)
