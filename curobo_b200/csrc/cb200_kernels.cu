@@ -106,6 +106,7 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
   const cb200_rollout_cfg &cfg = a.cfg;
   const int D = rv.D, S = rv.S, L = rv.L;
   cs_cost = 0.0f;
+  #pragma unroll 1
   for (int d = lane; d < D; d += 32) {
     const float qd = __ldg(a.q + (size_t)e * D + d);
     es.qv[d] = qd;
@@ -120,6 +121,7 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
   warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr);
   pose_c = 0.0f;
   const bool do_pose = (a.goal_position != nullptr);
+  #pragma unroll 1
   for (int t = lane; t < L; t += 32) {
     const float *T = es.cumul + 12 * rv.tool_map[t];
     const V3 p = mk3(T[3], T[7], T[11]);
@@ -140,9 +142,9 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
       const float *tol = term ? a.pose_tol_t : a.pose_tol_nt;
       const size_t go = ((size_t)gi * L + t) * cfg.num_goalset;
       const PoseOut po = tool_pose_cost(p, qt, a.goal_position + go * 3, a.goal_quat + go * 4, cfg.num_goalset,
-                                        cfg.pose_weight[0], cfg.pose_weight[1], axes ? axes + 6 * t : nullptr,
-                                        tol ? __ldg(tol + 2 * t) : 0.0f, tol ? __ldg(tol + 2 * t + 1) : 0.0f,
-                                        cfg.pose_rotation_method);
+                                        cfg.pose_weight[0], cfg.pose_weight[1], axes, t,
+                                        tol != nullptr ? __ldg(tol + 2 * t) : 0.0f,
+                                        tol != nullptr ? __ldg(tol + 2 * t + 1) : 0.0f, cfg.pose_rotation_method);
       const V3 om = quat_grad_to_omega(qt, po.gq_w, po.gq_x, po.gq_y, po.gq_z);
       pg[0] = po.g_pos.x;
       pg[1] = po.g_pos.y;
@@ -161,27 +163,32 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
   __syncwarp();
 }
 
-template <bool SWEEP>
-__device__ __forceinline__ void row_phase_b(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
-                                            int b, float cs_cost, float pose_c, const float4 *prev_sph,
-                                            const float4 *next_sph) {
+// phase B1: self collision + scene collision.  Leaves the scene sphere-gradients in es.gsph and returns the
+// pieces phase B2 needs in registers.
+struct RowB1 {
+  float self_c, fmax, scene_c;
+  int bi, bj;
+};
+
+template <bool SWEEP, int SCENE>
+__device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
+                                              int b, const float4 *prev_sph, const float4 *next_sph) {
   const cb200_rollout_cfg &cfg = a.cfg;
-  const int D = rv.D, S = rv.S;
+  const int S = rv.S;
+  RowB1 r{0.0f, 0.0f, 0.0f, 0, 0};
   // ---- self collision (reads padded spheres in gsph)
-  float self_c = 0.0f, fmax_ = 0.0f;
-  int bi = 0, bj = 0;
   if (cfg.self_weight > 0.0f && rv.P > 0) {
-    fmax_ = (rv.n_lp > 0) ? warp_self_collision_tiles(rv, es, lane, bi, bj)
-                          : warp_self_collision_pairs(es.gsph, rv.pairs, rv.P, lane, bi, bj);
-    self_c = (fmax_ > 0.0f) ? 0.5f * cfg.self_weight * fmax_ : 0.0f;
+    r.fmax = (rv.n_lp > 0) ? warp_self_collision_tiles(rv, es, lane, r.bi, r.bj)
+                           : warp_self_collision_pairs(es.gsph, rv.pairs, rv.P, lane, r.bi, r.bj);
+    r.self_c = (r.fmax > 0.0f) ? 0.5f * cfg.self_weight * r.fmax : 0.0f;
   }
-  if (a.self_cost && lane == 0) a.self_cost[e] = self_c;
+  if (a.self_cost && lane == 0) a.self_cost[e] = r.self_c;
   __syncwarp();
   // ---- scene collision (lane per sphere) -> gsph = gradient
-  float scene_c = 0.0f;
-  const bool do_scene = cfg.scene_weight > 0.0f && (a.cuboids.inv_pose != nullptr || a.voxels.inv_pose != nullptr);
+  const bool do_scene = SCENE != 0 && cfg.scene_weight > 0.0f;
   const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
   const float sdt = (SWEEP && cfg.use_speed_metric && a.dt != nullptr) ? __ldg(a.dt) : 0.0f;
+  #pragma unroll 1
   for (int s = lane; s < S; s += 32) {
     V3 g = mk3(0, 0, 0);
     float c = 0.0f;
@@ -189,7 +196,7 @@ __device__ __forceinline__ void row_phase_b(const FusedArgs &a, const RobotView 
       const float4 sp = es.sph[s];
       const V3 cen = mk3(sp.x, sp.y, sp.z);
       if (!SWEEP) {
-        c = sphere_scene_discrete(cen, sp.w, cfg.scene_activation, cfg.scene_weight, a.cuboids, a.voxels, env, g);
+        c = sphere_scene_discrete<SCENE>(cen, sp.w, cfg.scene_activation, cfg.scene_weight, a.cuboids, a.voxels, env, g);
       } else {
         V3 pv = cen, nx = cen;
         if (prev_sph != nullptr) {
@@ -200,20 +207,27 @@ __device__ __forceinline__ void row_phase_b(const FusedArgs &a, const RobotView 
           const float4 t = next_sph[s];
           nx = mk3(t.x, t.y, t.z);
         }
-        c = sphere_scene_swept(cen, sp.w, cfg.scene_activation, cfg.scene_weight, prev_sph != nullptr, pv,
-                               next_sph != nullptr, nx, a.cuboids, a.voxels, env, g);
+        c = sphere_scene_swept<SCENE>(cen, sp.w, cfg.scene_activation, cfg.scene_weight, prev_sph != nullptr, pv,
+                                      next_sph != nullptr, nx, a.cuboids, a.voxels, env, g);
         if (cfg.use_speed_metric && prev_sph != nullptr && next_sph != nullptr) speed_metric(pv, cen, nx, sdt, c, g);
       }
     }
     es.gsph[s] = make_float4(g.x, g.y, g.z, 0.0f);
-    scene_c += c;
+    r.scene_c += c;
     if (a.scene_cost) a.scene_cost[(size_t)e * S + s] = c;
   }
   __syncwarp();
-  if (fmax_ > 0.0f && lane == 0) {
-    const float4 pi = es.sph[bi], pj = es.sph[bj];
-    const float w = cfg.self_weight;
-    float4 gi = es.gsph[bi], gj = es.gsph[bj];
+  return r;
+}
+
+// phase B2: add the self-collision gradient to the two spheres of the worst pair, J^T backward, row cost.
+__device__ __forceinline__ void row_phase_b2(const FusedArgs &a, const RobotView &rv, const EvalSmem &es,
+                                             const unsigned char *smem_blob, int lane, int e, const RowB1 &r,
+                                             float cs_cost, float pose_c) {
+  if (r.fmax > 0.0f && lane == 0) {
+    const float4 pi = es.sph[r.bi], pj = es.sph[r.bj];
+    const float w = a.cfg.self_weight;
+    float4 gi = es.gsph[r.bi], gj = es.gsph[r.bj];
     const float gx = w * (pj.x - pi.x), gy = w * (pj.y - pi.y), gz = w * (pj.z - pi.z);
     gi.x += gx;
     gi.y += gy;
@@ -221,21 +235,25 @@ __device__ __forceinline__ void row_phase_b(const FusedArgs &a, const RobotView 
     gj.x -= gx;
     gj.y -= gy;
     gj.z -= gz;
-    es.gsph[bi] = gi;
-    es.gsph[bj] = gj;
+    es.gsph[r.bi] = gi;
+    es.gsph[r.bj] = gj;
   }
   __syncwarp();
-  if (!warp_fk_backward_sparse(rv, es, lane, a.grad_q + (size_t)e * D)) warp_fk_backward(rv, es, lane, a.grad_q + (size_t)e * D);
-  const float tot = warp_sum(cs_cost + pose_c + scene_c) + self_c;
+  float *gq = a.grad_q + (size_t)e * rv.D;
+  if (!warp_fk_backward_sparse(rv, es, lane, gq)) warp_fk_backward_cold(smem_blob, a.blob, es.cumul, lane, gq);
+  const float tot = warp_sum(cs_cost + pose_c + r.scene_c) + r.self_c;
   if (lane == 0) a.cost[e] = tot;
   __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
-// THE fused kernel, discrete scene collision: rows are independent, one warp per row.
+// THE fused kernel, discrete scene collision: rows are independent, one warp per row.  The warps of a CTA
+// walk the phases together (__syncthreads between phases): the kernel is ~40 KB of straight-line code per
+// row, and warps drifting through different phases thrash the instruction cache (measured: 19 % of issue
+// stalls were `no_instructions` before this).
 // ------------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
+template <int SCENE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
@@ -244,11 +262,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
   float *base = reinterpret_cast<float *>(smem + a.blob_smem_bytes) + (size_t)warp * a.eval_floats;
   const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
   const int N = a.B * a.H;
-  for (int e = blockIdx.x * nwarps + warp; e < N; e += gridDim.x * nwarps) {
-    const int b = e / a.H, h = e - b * a.H;
-    float cs_cost, pose_c;
-    row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
-    row_phase_b<false>(a, rv, es, lane, e, b, cs_cost, pose_c, nullptr, nullptr);
+  const int stride = gridDim.x * nwarps;
+  const int n_iter = (N + stride - 1) / stride;
+  for (int it = 0; it < n_iter; ++it) {
+    const int e = it * stride + blockIdx.x * nwarps + warp;
+    const bool active = e < N;
+    const int b = active ? e / a.H : 0, h = active ? e - b * a.H : 0;
+    float cs_cost = 0.0f, pose_c = 0.0f;
+    RowB1 r{0.0f, 0.0f, 0.0f, 0, 0};
+    if (active) row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    __syncthreads();
+    if (active) r = row_phase_b1<false, SCENE>(a, rv, es, lane, e, b, nullptr, nullptr);
+    __syncthreads();
+    if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+    __syncthreads();
   }
 }
 
@@ -258,8 +285,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
 // waypoint (warp 0 / the last warp also compute the halo waypoints' spheres), the CTA synchronises, then
 // every warp runs phase B reading its neighbours' sphere positions from shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
+template <int SCENE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
@@ -302,15 +329,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_traj_kernel(c
     }
     const int e = b * a.H + h;
     float cs_cost = 0.0f, pose_c = 0.0f;
+    RowB1 r{0.0f, 0.0f, 0.0f, 0, 0};
     if (active) row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
     __syncthreads();
     if (active) {
       const float4 *prev = nullptr, *next = nullptr;
       if (h > 0) prev = (warp > 0) ? reinterpret_cast<const float4 *>(all + (size_t)(warp - 1) * a.eval_floats + rv.nl * 12) : halo_prev;
       if (h < a.H - 1) next = (warp < nwarps - 1) ? reinterpret_cast<const float4 *>(all + (size_t)(warp + 1) * a.eval_floats + rv.nl * 12) : halo_next;
-      row_phase_b<true>(a, rv, es, lane, e, b, cs_cost, pose_c, prev, next);
+      r = row_phase_b1<true, SCENE>(a, rv, es, lane, e, b, prev, next);
     }
     __syncthreads();
+    if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
   }
 }
 
@@ -636,14 +665,14 @@ __global__ void __launch_bounds__(128) tool_pose_kernel(const __grid_constant__ 
     const int h = (i - b * a.H * a.L) / a.L;
     const int l = i - b * a.H * a.L - h * a.L;
     const bool term = !(h < a.H - 1 && a.H > 1);
-    const float *axes = (term ? a.axes_t : a.axes_nt) + 6 * l;
+    const float *axes = term ? a.axes_t : a.axes_nt;
     const float *tol = (term ? a.tol_t : a.tol_nt) + 2 * l;
     const int gi = __ldg(a.idxs_goal + b);
     const V3 p = mk3(__ldg(a.cur_pos + 3 * i), __ldg(a.cur_pos + 3 * i + 1), __ldg(a.cur_pos + 3 * i + 2));
     const float4 qw = __ldg(reinterpret_cast<const float4 *>(a.cur_quat) + i);
     const size_t go = ((size_t)gi * a.L + l) * a.G;
     const PoseOut po = tool_pose_cost(p, Q4{qw.y, qw.z, qw.w, qw.x}, a.goal_pos + go * 3, a.goal_quat + go * 4, a.G,
-                                      __ldg(a.weight), __ldg(a.weight + 1), axes, __ldg(tol), __ldg(tol + 1), a.method);
+                                      __ldg(a.weight), __ldg(a.weight + 1), axes, l, __ldg(tol), __ldg(tol + 1), a.method);
     a.out_distance[2 * i] = po.pos_cost;
     a.out_distance[2 * i + 1] = po.rot_cost;
     a.out_goalset_idx[i] = po.goal_idx;
@@ -1351,24 +1380,23 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   DevInfo &d = dev_info();
   const bool traj = cfg->use_sweep != 0;
   if (traj && cfg->use_speed_metric && io->dt == nullptr) return ret(cudaErrorInvalidValue);
-  // register cap variant (CTAs/SM the compiler must allow at 256 threads): tuning knob, default from measurements
-  static const int minb = []() {
-    const char *e = getenv("CB200_MINB");
-    const int v = e ? atoi(e) : 2;
-    return (v == 3 || v == 4) ? v : 2;
-  }();
+  // kernels are specialised on the obstacle types present (bit 0 cuboids, bit 1 voxel grids) so that e.g. the
+  // IK kernel carries no ESDF code: the fused kernel's instruction footprint is what limits it.
+  const int scene = (cfg->scene_weight > 0.0f ? ((a.cuboids.inv_pose ? 1 : 0) | (a.voxels.inv_pose ? 2 : 0)) : 0);
   using KernelT = void (*)(const FusedArgs);
-  static KernelT const table[2][3] = {{rollout_fused_kernel<2>, rollout_fused_kernel<3>, rollout_fused_kernel<4>},
-                                      {rollout_traj_kernel<2>, rollout_traj_kernel<3>, rollout_traj_kernel<4>}};
-  KernelT kern = table[traj ? 1 : 0][minb - 2];
+  static KernelT const table[2][4] = {
+      {rollout_fused_kernel<0>, rollout_fused_kernel<1>, rollout_fused_kernel<2>, rollout_fused_kernel<3>},
+      {rollout_traj_kernel<0>, rollout_traj_kernel<1>, rollout_traj_kernel<2>, rollout_traj_kernel<3>}};
+  KernelT kern = table[traj ? 1 : 0][scene];
+  const int minb = scene;  // part of the plan-cache key
   // warps per CTA: the count that keeps the most warps resident per SM (shared memory is the limiter for
   // big robots); ties go to the larger CTA so the blob is staged fewer times.  Cached per (kernel, geometry).
   struct Plan {
     long long key = -1;
     int nw = 0, per_sm = 0;
   };
-  static thread_local Plan plans[2];
-  Plan &pl = plans[traj ? 1 : 0];
+  static thread_local Plan plans[2][4];
+  Plan &pl = plans[traj ? 1 : 0][scene];
   const size_t halo_bytes = traj ? (size_t)2 * h.S * sizeof(float4) : 0;
   const long long key = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ (long long)minb ^
                         (traj ? ((long long)io->horizon << 40) : 0);

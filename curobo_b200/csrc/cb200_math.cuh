@@ -198,6 +198,75 @@ CB_HD float load_half(const uint16_t *p) {
 #endif
 }
 
+// Boundary case of the trilinear sample (some of the 8 corners outside the grid): validity-weighted
+// interpolation (data_voxel.py:919-1069).  Rare (spheres at the rim of the grid) -> kept out of line so the
+// hot path stays small in the instruction cache.
+static __host__ __device__ __noinline__ void voxel_sdf_boundary(const uint16_t *feat, long long base, long long sx, long long sy, bool x0k, bool x1k, bool y0k,
+                        bool y1k, bool z0k, bool z1k, float fx, float fy, float fz, float inv, float max_dist,
+                        float &sdf, float &gx, float &gy, float &gz) {
+  const float fx1 = 1.0f - fx, fy1 = 1.0f - fy, fz1 = 1.0f - fz;
+  float s[8], v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    int cx = (c >> 2) & 1, cy = (c >> 1) & 1, cz = c & 1;
+    bool ok = (cx ? x1k : x0k) && (cy ? y1k : y0k) && (cz ? z1k : z0k);
+    s[c] = max_dist;
+    v[c] = 0.0f;
+    if (ok) {
+      s[c] = load_half(feat + base + cx * sx + cy * sy + cz);
+      v[c] = 1.0f;
+    }
+  }
+  float w[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) w[c] = (((c >> 2) & 1) ? fx : fx1) * (((c >> 1) & 1) ? fy : fy1) * ((c & 1) ? fz : fz1);
+  float ws = 0.0f, vsum = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    vsum += s[c] * w[c] * v[c];
+    ws += w[c] * v[c];
+  }
+  if (ws <= 0.0f) {
+    sdf = max_dist;
+    gx = gy = gz = 0.0f;
+    return;
+  }
+  sdf = vsum / ws;
+  float gs, gw, wt;
+  gs = gw = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {  // x: pairs (c, c+4) weighted by (y,z) bilinear weights
+    wt = (((c >> 1) & 1) ? fy : fy1) * ((c & 1) ? fz : fz1);
+    if (v[c] > 0.0f && v[c + 4] > 0.0f) {
+      gs += (s[c + 4] - s[c]) * wt;
+      gw += wt;
+    }
+  }
+  gx = gw > 0.0f ? gs / gw * inv : 0.0f;
+  gs = gw = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int c = ((k >> 1) << 2) | (k & 1);  // (x, y=0, z)
+    wt = (((c >> 2) & 1) ? fx : fx1) * ((c & 1) ? fz : fz1);
+    if (v[c] > 0.0f && v[c + 2] > 0.0f) {
+      gs += (s[c + 2] - s[c]) * wt;
+      gw += wt;
+    }
+  }
+  gy = gw > 0.0f ? gs / gw * inv : 0.0f;
+  gs = gw = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int c = k << 1;  // (x, y, z=0)
+    wt = (((c >> 2) & 1) ? fx : fx1) * (((c >> 1) & 1) ? fy : fy1);
+    if (v[c] > 0.0f && v[c + 1] > 0.0f) {
+      gs += (s[c + 1] - s[c]) * wt;
+      gw += wt;
+    }
+  }
+  gz = gw > 0.0f ? gs / gw * inv : 0.0f;
+}
+
 // Trilinear ESDF sample + analytic gradient; feat points at the layer start (flat, z fastest).
 CB_HD SdfGrad voxel_sdf_grad(V3 p, const uint16_t *feat, int nx, int ny, int nz, float vs, float max_dist) {
   SdfGrad out;
@@ -241,67 +310,7 @@ CB_HD SdfGrad voxel_sdf_grad(V3 p, const uint16_t *feat, int nx, int ny, int nz,
       gy = ((s010 - s000) * fx1 * fz1 + (s011 - s001) * fx1 * fz + (s110 - s100) * fx * fz1 + (s111 - s101) * fx * fz) * inv;
       gz = ((s001 - s000) * fx1 * fy1 + (s011 - s010) * fx1 * fy + (s101 - s100) * fx * fy1 + (s111 - s110) * fx * fy) * inv;
     } else {
-      float s[8], v[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        int cx = (c >> 2) & 1, cy = (c >> 1) & 1, cz = c & 1;
-        bool ok = (cx ? x1k : x0k) && (cy ? y1k : y0k) && (cz ? z1k : z0k);
-        s[c] = max_dist;
-        v[c] = 0.0f;
-        if (ok) {
-          s[c] = load_half(feat + base + cx * sx + cy * sy + cz);
-          v[c] = 1.0f;
-        }
-      }
-      float w[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) w[c] = (((c >> 2) & 1) ? fx : fx1) * (((c >> 1) & 1) ? fy : fy1) * ((c & 1) ? fz : fz1);
-      float ws = 0.0f, vsum = 0.0f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        vsum += s[c] * w[c] * v[c];
-        ws += w[c] * v[c];
-      }
-      if (ws <= 0.0f) {
-        sdf = max_dist;
-        gx = gy = gz = 0.0f;
-      } else {
-        sdf = vsum / ws;
-        float gs, gw, wt;
-        // x: pairs (c, c+4) weighted by (y,z) bilinear weights
-        gs = gw = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          wt = (((c >> 1) & 1) ? fy : fy1) * ((c & 1) ? fz : fz1);
-          if (v[c] > 0.0f && v[c + 4] > 0.0f) {
-            gs += (s[c + 4] - s[c]) * wt;
-            gw += wt;
-          }
-        }
-        gx = gw > 0.0f ? gs / gw * inv : 0.0f;
-        gs = gw = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          int c = ((k >> 1) << 2) | (k & 1);  // (x, y=0, z)
-          wt = (((c >> 2) & 1) ? fx : fx1) * ((c & 1) ? fz : fz1);
-          if (v[c] > 0.0f && v[c + 2] > 0.0f) {
-            gs += (s[c + 2] - s[c]) * wt;
-            gw += wt;
-          }
-        }
-        gy = gw > 0.0f ? gs / gw * inv : 0.0f;
-        gs = gw = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          int c = k << 1;  // (x, y, z=0)
-          wt = (((c >> 2) & 1) ? fx : fx1) * (((c >> 1) & 1) ? fy : fy1);
-          if (v[c] > 0.0f && v[c + 1] > 0.0f) {
-            gs += (s[c + 1] - s[c]) * wt;
-            gw += wt;
-          }
-        }
-        gz = gw > 0.0f ? gs / gw * inv : 0.0f;
-      }
+      voxel_sdf_boundary(feat, base, sx, sy, x0k, x1k, y0k, y1k, z0k, z1k, fx, fy, fz, inv, max_dist, sdf, gx, gy, gz);
     }
   }
   if (sdf >= max_dist) {
@@ -362,18 +371,23 @@ struct Obstacle {
   int nx, ny, nz;
   float vs, max_dist;
 };
+template <int SCENE>
 CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p) {
+  if (SCENE == 1) return cuboid_sdf_grad(p, o.a, o.b, o.c);
+  if (SCENE == 2) return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist);
   if (o.kind == 0) return cuboid_sdf_grad(p, o.a, o.b, o.c);
   return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist);
 }
 
 // Iterate every enabled obstacle of env `env` (cuboids then voxel grids) and call fn(frame, obstacle).
-template <typename Fn>
+// SCENE is a compile-time mask (bit 0: cuboids, bit 1: voxel grids) so specialised kernels carry no dead code.
+template <int SCENE, typename Fn>
 CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, Fn fn) {
-  if (cs.inv_pose != nullptr) {
+  if ((SCENE & 1) && cs.inv_pose != nullptr) {
     int ce = env < cs.num_envs ? env : 0;
     int n = cs.count[ce];
     if (n > cs.max_n) n = cs.max_n;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       int k = ce * cs.max_n + i;
       if (cs.enable[k] != 1) continue;
@@ -389,10 +403,11 @@ CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, F
       fn(load_obs_frame(cs.inv_pose + 8 * k), o);
     }
   }
-  if (vx.inv_pose != nullptr) {
+  if ((SCENE & 2) && vx.inv_pose != nullptr) {
     int ve = env < vx.num_envs ? env : 0;
     int n = vx.count[ve];
     if (n > vx.max_n) n = vx.max_n;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       int k = ve * vx.max_n + i;
       if (vx.enable[k] != 1) continue;
@@ -412,14 +427,15 @@ CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, F
 
 // Discrete sphere-vs-scene: returns weighted cost, adds weighted world-frame gradient to g.
 // (wp_collision_kernel.py:112-166)
+template <int SCENE = 3>
 CB_HD float sphere_scene_discrete(V3 c, float r, float eta, float w, const CuboidSet &cs, const VoxelSet &vx, int env,
                                   V3 &g) {
   float cost = 0.0f;
   if (r < 0.0f) return 0.0f;
   const float radj = r + eta;
-  for_each_obstacle(cs, vx, env, [&](const ObsFrame &f, const Obstacle &o) {
+  for_each_obstacle<SCENE>(cs, vx, env, [&](const ObsFrame &f, const Obstacle &o) {
     V3 lp = qrot(f.q, c) + f.p;
-    SdfGrad sg = obstacle_sdf(o, lp);
+    SdfGrad sg = obstacle_sdf<SCENE>(o, lp);
     float pen = radj - sg.sdf;
     if (pen > 0.0f) {
       float ac, as;
@@ -434,17 +450,18 @@ CB_HD float sphere_scene_discrete(V3 c, float r, float eta, float w, const Cuboi
 
 // Swept sphere-vs-scene (wp_sweep_collision_kernel.py:137-260).  prev/next are the same sphere at
 // h-1 / h+1 (has_prev / has_next false at the trajectory ends).
+template <int SCENE = 3>
 CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev, V3 prev, bool has_next, V3 next,
                                const CuboidSet &cs, const VoxelSet &vx, int env, V3 &g) {
   float cost = 0.0f;
   if (r < 0.0f) return 0.0f;
   const float radj = r + eta;
-  for_each_obstacle(cs, vx, env, [&](const ObsFrame &f, const Obstacle &o) {
+  for_each_obstacle<SCENE>(cs, vx, env, [&](const ObsFrame &f, const Obstacle &o) {
     V3 lc = qrot(f.q, c) + f.p;
     float csum = 0.0f;
     V3 gsum = mk3(0.f, 0.f, 0.f);
     {
-      SdfGrad sg = obstacle_sdf(o, lc);
+      SdfGrad sg = obstacle_sdf<SCENE>(o, lc);
       float pen = radj - sg.sdf;
       if (pen > 0.0f) {
         float ac, as;
@@ -465,7 +482,7 @@ CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev,
         if (jump >= half) break;
         float t = 1.0f - 0.5f * jump * inv_half;
         V3 pt = t * lc + (1.0f - t) * ln;
-        SdfGrad sg = obstacle_sdf(o, pt);
+        SdfGrad sg = obstacle_sdf<SCENE>(o, pt);
         float pen = radj - sg.sdf;
         if (pen > 0.0f) {
           float ac, as;
@@ -514,10 +531,12 @@ struct PoseOut {
 
 CB_HD PoseOut tool_pose_cost(V3 cp, Q4 cq /*xyzw*/, const float *goal_pos /*[n_goalset,3]*/,
                              const float *goal_quat /*[n_goalset,4] wxyz*/, int n_goalset, float w_pos, float w_rot,
-                             const float *axes6 /*or null*/, float tol_p, float tol_r, int method) {
+                             const float *axes_base /*[L,6] or null*/, int frame, float tol_p, float tol_r,
+                             int method) {
   float ax[6] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-  if (axes6 != nullptr)
-    for (int i = 0; i < 6; ++i) ax[i] = ldgf(axes6 + i);
+  if (axes_base != nullptr) {  // NB: test the BASE pointer; never form (null + offset)
+    for (int i = 0; i < 6; ++i) ax[i] = ldgf(axes_base + 6 * frame + i);
+  }
   tol_p = tol_p * tol_p;
   tol_r = tol_r * tol_r;
   float best = -1.0f;
@@ -527,6 +546,7 @@ CB_HD PoseOut tool_pose_cost(V3 cp, Q4 cq /*xyzw*/, const float *goal_pos /*[n_g
   V3 best_rg = mk3(0, 0, 0);
   o.goal_idx = 0;
   o.rot_err = -1.0f;
+  #pragma unroll 1
   for (int g = 0; g < n_goalset; ++g) {
     V3 gp = mk3(ldgf(goal_pos + 3 * g), ldgf(goal_pos + 3 * g + 1), ldgf(goal_pos + 3 * g + 2));
     Q4 gq = Q4{ldgf(goal_quat + 4 * g + 1), ldgf(goal_quat + 4 * g + 2), ldgf(goal_quat + 4 * g + 3), ldgf(goal_quat + 4 * g)};

@@ -127,6 +127,7 @@ __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es,
   // so a compose step needs one warp barrier instead of two; otherwise they are composed in place.
   const bool scratch = rv.S * 4 >= rv.nl * 12;
   float *loc = scratch ? reinterpret_cast<float *>(es.gsph) : es.cumul;
+  #pragma unroll 1
   for (int l = lane; l < rv.nl; l += 32) {
     int jt = rv.joint_type[l];
     float th = 0.0f;
@@ -136,6 +137,7 @@ __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es,
   __syncwarp();
   const int sub = lane >> 4, k = lane & 15;
   const int r = k >> 2, c = k & 3;
+  #pragma unroll 1
   for (int st = 0; st < rv.n_fk_steps; ++st) {
     const uint32_t w = rv.fk_sched[st] >> (16 * sub);
     const int l = w & 0xff, par = (w >> 8) & 0xff;
@@ -155,6 +157,7 @@ __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es,
 // Spheres: world position of every robot sphere; also the self-collision (padded radius) copy in gsph.
 // Reference: kinematics_forward_helper.cuh:218-254, kinematics_util.cuh:39-49.
 __device__ __forceinline__ void warp_spheres(const RobotView &rv, const EvalSmem &es, int lane, float4 *out_global) {
+  #pragma unroll 1
   for (int s = lane; s < rv.S; s += 32) {
     const float *T = es.cumul + 12 * rv.sph_link[s];
     const float4 p = rv.spheres[s];
@@ -182,6 +185,7 @@ __device__ __forceinline__ float warp_self_collision_pairs(const float4 *psph, c
                                                            int &bi, int &bj) {
   float best = 0.0f;
   uint32_t best_p = 0xffffffffu;
+  #pragma unroll 1
   for (int p = lane; p < P; p += 32) {
     const uint32_t pr = __ldg(pairs + p);
     const float4 a = psph[pr & 0xffffu], b = psph[pr >> 16];
@@ -217,6 +221,7 @@ __device__ __forceinline__ float warp_self_collision_pairs(const float4 *psph, c
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, const EvalSmem &es, int lane, int &bi,
                                                            int &bj) {
+  #pragma unroll 1
   for (int a = lane; a < rv.n_cl; a += 32) {
     const float4 c = rv.cl_bound[a];
     const float *T = es.cumul + 12 * rv.cl_link[a];
@@ -225,6 +230,7 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
   }
   __syncwarp();
   unsigned long long key = 0ull;  // f bits | ~i | ~j : max = largest f, then smallest i, then smallest j
+  #pragma unroll 1
   for (int base = 0; base < rv.n_lp; base += 32) {
     uint32_t pr = 0;
     bool hit = false;
@@ -243,6 +249,7 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
       const int sa = rv.cl_start[a], na = rv.cl_start[a + 1] - sa;
       const int sb = rv.cl_start[b], nb = rv.cl_start[b + 1] - sb;
       const float inv_nb = 1.0f / (float)nb;
+      #pragma unroll 1
       for (int t = lane; t < na * nb; t += 32) {
         const int io = (int)(((float)t + 0.5f) * inv_nb);
         const int i = sa + io, j = sb + (t - io * nb);
@@ -280,10 +287,12 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
 // gq_out[d] = gqv[d] + sum over links driven by joint d.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out) {
+  #pragma unroll 1
   for (int k = lane; k < rv.nl; k += 32) {
     const float *Tk = es.cumul + 12 * k;
     const V3 o = mk3(Tk[3], Tk[7], Tk[11]);
     V3 F = mk3(0, 0, 0), T = mk3(0, 0, 0);
+    #pragma unroll 1
     for (int i = rv.link_sph_off[k]; i < rv.link_sph_off[k + 1]; ++i) {
       const int s = rv.link_sph_idx[i];
       const float4 g4 = es.gsph[s];
@@ -307,6 +316,7 @@ __device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const Eval
     ft[6] = T.z;
   }
   __syncwarp();
+  #pragma unroll 1
   for (int j = lane; j < rv.nl; j += 32) {
     const int jt = rv.joint_type[j];
     float res = 0.0f;
@@ -314,6 +324,7 @@ __device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const Eval
       const float *Tj = es.cumul + 12 * j;
       const V3 oj = mk3(Tj[3], Tj[7], Tj[11]);
       V3 F = mk3(0, 0, 0), T = mk3(0, 0, 0);
+      #pragma unroll 1
       for (int k = j; k < rv.nl; ++k) {
         if (!((rv.anc_mask[k] >> j) & 1ull)) continue;
         const float *ft = es.ft + 8 * k;
@@ -337,6 +348,15 @@ __device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const Eval
   }
 }
 
+// Dense fallback, out of line: rarely taken, and inlining it would only bloat the instruction footprint of the
+// hot path.  Views are rebuilt from raw pointers so that the caller's RobotView/EvalSmem stay in registers.
+static __device__ __noinline__ void warp_fk_backward_cold(const unsigned char *smem_blob, const unsigned char *gmem_blob,
+                                                          float *eval_base, int lane, float *gq_out) {
+  const RobotView rv = make_robot_view(smem_blob, gmem_blob);
+  const EvalSmem es = carve_eval_smem(eval_base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  warp_fk_backward(rv, es, lane, gq_out);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Same J^T backward, transposed for SPARSE sphere gradients (the common case: self-collision touches two
 // spheres, scene collision only the colliding ones): lanes own links (up to 64 = 2 per lane); every sphere
@@ -347,6 +367,7 @@ __device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const Eval
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out) {
   int nnz = 0;
+  #pragma unroll 1
   for (int base = 0; base < rv.S; base += 32) {
     const int s = base + lane;
     bool nz = false;
@@ -388,6 +409,7 @@ __device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, con
       }
     }
   };
+  #pragma unroll 1
   for (int base = 0; base < rv.S; base += 32) {
     const int s = base + lane;
     bool nz = false;
@@ -403,6 +425,7 @@ __device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, con
       add(rv.anc_mask[rv.sph_link[ss]], mk3(p4.x, p4.y, p4.z), mk3(g4.x, g4.y, g4.z), mk3(0, 0, 0));
     }
   }
+  #pragma unroll 1
   for (int t = 0; t < rv.L; ++t) {
     const float *pg = es.pose_g + 8 * t;
     const V3 g = mk3(pg[0], pg[1], pg[2]), om = mk3(pg[4], pg[5], pg[6]);

@@ -6,9 +6,6 @@ nvidia-smi -L > gpurun_out/gpu.txt
 (timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --maxfail=40 -p no:cacheprovider) > gpurun_out/parity.log 2>&1
 (timeout 900 python -m pytest tests/test_gpu_rollout.py -m gpu -q --maxfail=40 -p no:cacheprovider) > gpurun_out/rollout.log 2>&1
 (timeout 400 python bench.py --steps 200 --warmup 10) > gpurun_out/bench.log 2>&1
-for m in 3 4; do
-  (CB200_MINB=$m timeout 300 python bench.py --steps 200 --warmup 10 --no-cpu-baseline) > gpurun_out/bench_minb$m.log 2>&1
-done
 if [ "$1" != "noprof" ]; then
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --extra-workloads "") > gpurun_out/ncu_launches.log 2>&1
@@ -18,4 +15,4 @@ if [ "$1" != "noprof" ]; then
    python bench.py --workload g1_29_8192_esdf --steps 3 --warmup 3 --no-cpu-baseline --extra-workloads "") > gpurun_out/ncu_full_g1.log 2>&1
 fi
 tail -3 gpurun_out/smoke.log; tail -15 gpurun_out/parity.log; tail -15 gpurun_out/rollout.log
-for f in gpurun_out/bench.log gpurun_out/bench_minb3.log gpurun_out/bench_minb4.log; do tail -1 $f | cut -c1-330; done
+tail -1 gpurun_out/bench.log | cut -c1-2500

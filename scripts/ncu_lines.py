@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Attribute executed warp-instructions of one profiled kernel to source lines.
+
+ncu's CLI prints per-SASS-instruction counters (`--page source --csv`) but not the CUDA-C correlation, so the
+SASS stream is aligned (instruction by instruction, same order) with `nvdisasm -g` line info of a cubin built
+from the SAME sources with the SAME flags.
+
+    python scripts/ncu_lines.py <report.ncu-rep> <kernel-substring> <evals-per-launch> [--top N]
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "--ftz=true", "--fmad=true",
+         "--prec-div=false", "--prec-sqrt=false"]
+
+
+def main():
+    rep, kname, evals = sys.argv[1], sys.argv[2], int(sys.argv[3])
+    top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 40
+    srcdir = os.path.join(ROOT, "curobo_b200", "csrc")
+    tmp = tempfile.mkdtemp()
+    cubin, sass = os.path.join(tmp, "k.cubin"), os.path.join(tmp, "k.sass")
+    subprocess.check_call(["nvcc", *FLAGS, "-cubin", "-o", cubin, os.path.join(srcdir, "cb200_kernels.cu")])
+    open(sass, "w").write(subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout)
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    secs, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "hdr": None, "rows": []}
+            secs.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None:
+            cur["rows"].append(r)
+    sec = next(s for s in secs if kname in s["name"])
+    h = sec["hdr"]
+    ii, ti, si = h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("Source")
+    ncu = [(r[si].strip(), int(r[ii]), int(r[ti])) for r in sec["rows"] if len(r) > ii]
+    mangled = re.sub(r"[^A-Za-z0-9_]", "", kname.split("<")[0].split("::")[-1])
+    tmpl = re.search(r"<\(int\)(\d+)>", sec["name"])
+    txt = open(sass).read().split("\n")
+    starts = [i for i, l in enumerate(txt) if l.startswith(".text.") and mangled in l and (tmpl is None or f"ILi{tmpl.group(1)}E" in l)]
+    start = starts[0]
+    end = next(i for i, l in enumerate(txt) if i > start and l.startswith("//---------------------"))
+    dis, cf, cl = [], None, None
+    for l in txt[start:end]:
+        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+        if m:
+            cf, cl = os.path.basename(m.group(1)), int(m.group(2))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+.*?;", l):
+            dis.append((cf, cl))
+    if len(dis) != len(ncu):
+        print(f"WARNING: {len(dis)} disassembled vs {len(ncu)} profiled instructions (sources differ from the profiled build?)")
+    agg, lanes = collections.Counter(), collections.Counter()
+    for k in range(min(len(dis), len(ncu))):
+        agg[dis[k]] += ncu[k][1]
+        lanes[dis[k]] += ncu[k][2]
+    tot = sum(agg.values())
+    src = {f: open(os.path.join(srcdir, f)).read().split("\n") for f in os.listdir(srcdir)}
+    print(f"kernel: {sec['name']}\nwarp-instructions per eval: {tot / evals:.1f}  (total {tot}, {evals} evals)")
+    print(f"{'instr/eval':>10} {'share':>6} {'lanes':>5}  source")
+    for (f, l), c in agg.most_common(top):
+        code = src[f][l - 1].strip()[:100] if f in src and l else ""
+        print(f"{c / evals:10.1f} {100 * c / tot:5.1f}% {lanes[(f, l)] / max(c, 1):5.1f}  {f}:{l}  {code}")
+
+
+if __name__ == "__main__":
+    main()

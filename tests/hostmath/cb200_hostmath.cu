@@ -62,7 +62,7 @@ void hm_tool_pose(const float *pos3, const float *quat_wxyz, const float *goal_p
                   float w_pos, float w_rot, const float *axes6, float tol_p, float tol_r, int method, float *out /*12*/,
                   int *goal_idx) {
   PoseOut o = tool_pose_cost(mk3(pos3[0], pos3[1], pos3[2]), Q4{quat_wxyz[1], quat_wxyz[2], quat_wxyz[3], quat_wxyz[0]},
-                             goal_pos, goal_quat, n_goalset, w_pos, w_rot, axes6, tol_p, tol_r, method);
+                             goal_pos, goal_quat, n_goalset, w_pos, w_rot, axes6, 0, tol_p, tol_r, method);
   out[0] = o.pos_cost;
   out[1] = o.rot_cost;
   out[2] = o.pos_err;
