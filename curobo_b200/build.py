@@ -51,16 +51,18 @@ def _run(cmd, verbose):
         print(r.stdout + r.stderr)
 
 
-def build_product(force: bool = False, verbose: bool = False) -> str:
+def build_product(force: bool = False, verbose: bool = False, minb: int = 0) -> str:
+    """minb > 0 builds a tuning variant libcurobo_b200_mb<minb>.so (register cap = 65536 / (256 * minb))."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "curobo_b200.h")]
-    if not force and _newer(PRODUCT_SO, srcs):
-        return PRODUCT_SO
+    out = PRODUCT_SO if minb <= 0 else PRODUCT_SO.replace(".so", f"_mb{minb}.so")
+    if not force and _newer(out, srcs):
+        return out
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared",
-           "-Xptxas", "-v" if verbose else "-O3",
-           os.path.join(CSRC, "cb200_kernels.cu"), "-o", PRODUCT_SO, "-lcudart"]
+           "-Xptxas", "-v" if verbose else "-O3", *([f"-DCB200_MINB={minb}"] if minb > 0 else []),
+           os.path.join(CSRC, "cb200_kernels.cu"), "-o", out, "-lcudart"]
     _run(cmd, verbose)
-    return PRODUCT_SO
+    return out
 
 
 def build_hostmath(force: bool = False, verbose: bool = False) -> str:

@@ -28,6 +28,9 @@ using namespace cb200;
 namespace {
 
 constexpr int kWarpsPerCta = 8;
+#ifndef CB200_MINB
+#define CB200_MINB 2  // CTAs/SM the register allocator must leave room for at 256 threads (tuning knob)
+#endif
 
 struct FusedArgs {
   cb200_rollout_cfg cfg;
@@ -45,6 +48,7 @@ struct FusedArgs {
   int32_t *pose_goalset_idx;
   int32_t B, H;
   int32_t blob_smem_bytes, eval_floats;
+  int32_t phase_sync;  // 0: warps free-run; 1: one CTA barrier per row (after phase A); 2: barrier after every phase
 };
 
 // c-space cost for one dof; returns cost, writes gradient wrt position into gp (and v/a/j grads to global)
@@ -253,7 +257,7 @@ __device__ __forceinline__ void row_phase_b2(const FusedArgs &a, const RobotView
 // stalls were `no_instructions` before this).
 // ------------------------------------------------------------------------------------------------
 template <int SCENE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
@@ -271,11 +275,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_fused_kernel(con
     float cs_cost = 0.0f, pose_c = 0.0f;
     RowB1 r{0.0f, 0.0f, 0.0f, 0, 0};
     if (active) row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
-    __syncthreads();
+    if (a.phase_sync) __syncthreads();
     if (active) r = row_phase_b1<false, SCENE>(a, rv, es, lane, e, b, nullptr, nullptr);
-    __syncthreads();
+    if (a.phase_sync > 1) __syncthreads();
     if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
-    __syncthreads();
+    if (a.phase_sync > 1) __syncthreads();
   }
 }
 
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_fused_kernel(con
 // every warp runs phase B reading its neighbours' sphere positions from shared memory.
 // ------------------------------------------------------------------------------------------------
 template <int SCENE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
@@ -1377,6 +1381,11 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   a.H = io->horizon;
   a.blob_smem_bytes = h.smem_bytes;
   a.eval_floats = eval_smem_floats(h.nl, h.D, h.S, h.L, h.n_cl);
+  static const int phase_sync_env = []() {
+    const char *e = getenv("CB200_PHASE_SYNC");
+    return e ? atoi(e) : 0;
+  }();
+  a.phase_sync = phase_sync_env;
   DevInfo &d = dev_info();
   const bool traj = cfg->use_sweep != 0;
   if (traj && cfg->use_speed_metric && io->dt == nullptr) return ret(cudaErrorInvalidValue);

@@ -75,7 +75,11 @@ EXPORTED_SYMBOLS = tuple(_SIGS.keys())
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libcurobo_b200.so")
+    """CB200_LIB_VARIANT=mb3|mb4 selects a register-cap tuning build (same sources, same ABI) if it exists."""
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+    v = os.environ.get("CB200_LIB_VARIANT", "")
+    p = os.path.join(d, f"libcurobo_b200_{v}.so") if v else ""
+    return p if p and os.path.exists(p) else os.path.join(d, "libcurobo_b200.so")
 
 
 def load() -> C.CDLL:
