@@ -49,8 +49,10 @@ struct BlobHeader {
   // FK compose schedule: one word per step = two (link, parent) byte pairs (0xFF = idle slot); links of one
   // depth level are independent, so a step composes two of them with 12 lanes each.
   int32_t n_fk_steps;
-  int32_t off_fk_sched;     // uint32[n_fk_steps]  l0 | p0<<8 | l1<<16 | p1<<24
-  int32_t reserved[13];
+  int32_t off_fk_sched;     // uint32[2*n_fk_steps]  per (step, slot): byte offset of the link's 3x4 (lo16, 0xFFFF = idle) | parent's (hi16)
+  int32_t off_cl_bound_scene;  // float4[n_cl]  like cl_bound but over spheres with r >= 0 and unpadded radii (scene broad phase)
+  int32_t off_sph_cl;       // uint8 [S]  collision-link index of each sphere (valid when n_lp > 0)
+  int32_t reserved[11];
 };
 static_assert(sizeof(BlobHeader) == 192, "BlobHeader must be 192 bytes");
 

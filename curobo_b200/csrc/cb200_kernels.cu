@@ -171,7 +171,7 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
 // pieces phase B2 needs in registers.
 struct RowB1 {
   float self_c, fmax, scene_c;
-  int bi, bj;
+  int bi, bj, nnz;
 };
 
 template <bool SWEEP, int SCENE>
@@ -179,7 +179,7 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
                                               int b, const float4 *prev_sph, const float4 *next_sph) {
   const cb200_rollout_cfg &cfg = a.cfg;
   const int S = rv.S;
-  RowB1 r{0.0f, 0.0f, 0.0f, 0, 0};
+  RowB1 r{0.0f, 0.0f, 0.0f, 0, 0, 0};
   // ---- self collision (reads padded spheres in gsph)
   if (cfg.self_weight > 0.0f && rv.P > 0) {
     r.fmax = (rv.n_lp > 0) ? warp_self_collision_tiles(rv, es, lane, r.bi, r.bj)
@@ -192,7 +192,40 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
   const bool do_scene = SCENE != 0 && cfg.scene_weight > 0.0f;
   const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
   const float sdt = (SWEEP && cfg.use_speed_metric && a.dt != nullptr) ? __ldg(a.dt) : 0.0f;
-  #pragma unroll 1
+  // cuboid broad phase (discrete mode): a box SDF is 1-Lipschitz, so sdf(link bound centre) >= R_link + eta
+  // means no sphere of the link has pen = r + eta - sdf > 0 against that cuboid -> skipping it is exact.
+  int ce = 0, ncub = 0;
+  bool cull = false;
+  if ((SCENE & 1) && do_scene) {
+    ce = env < a.cuboids.num_envs ? env : 0;
+    ncub = a.cuboids.count[ce];
+    if (ncub > a.cuboids.max_n) ncub = a.cuboids.max_n;
+    cull = !SWEEP && rv.n_lp > 0 && ncub <= 32;
+    if (cull) {
+#pragma unroll 1
+      for (int ca = lane; ca < rv.n_cl; ca += 32) {
+        const float4 cb = rv.cl_bound_scene[ca];
+        uint32_t mask = 0u;
+        if (cb.w >= 0.0f) {
+          const float *Tk = es.cumul + 12 * rv.cl_link[ca];
+          const V3 cw = mk3(Tk[0] * cb.x + Tk[1] * cb.y + Tk[2] * cb.z + Tk[3], Tk[4] * cb.x + Tk[5] * cb.y + Tk[6] * cb.z + Tk[7],
+                            Tk[8] * cb.x + Tk[9] * cb.y + Tk[10] * cb.z + Tk[11]);
+#pragma unroll 1
+          for (int i = 0; i < ncub; ++i) {
+            const int kk = ce * a.cuboids.max_n + i;
+            if (a.cuboids.enable[kk] != 1) continue;
+            const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
+            const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cw) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                                               ldgf(a.cuboids.dims + 4 * kk + 2));
+            if (sg.sdf < cb.w + cfg.scene_activation) mask |= (1u << i);
+          }
+        }
+        es.cmask[ca] = mask;
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll 1
   for (int s = lane; s < S; s += 32) {
     V3 g = mk3(0, 0, 0);
     float c = 0.0f;
@@ -200,7 +233,33 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
       const float4 sp = es.sph[s];
       const V3 cen = mk3(sp.x, sp.y, sp.z);
       if (!SWEEP) {
-        c = sphere_scene_discrete<SCENE>(cen, sp.w, cfg.scene_activation, cfg.scene_weight, a.cuboids, a.voxels, env, g);
+        if (sp.w >= 0.0f) {
+          if (SCENE & 1) {
+            uint32_t m = cull ? es.cmask[rv.sph_cl[s]] : 0xffffffffu;
+            const float radj = sp.w + cfg.scene_activation;
+#pragma unroll 1
+            for (int i = 0; i < ncub && m != 0u; ++i) {
+              if (cull && !((m >> i) & 1u)) continue;
+              if (cull) m &= ~(1u << i);
+              const int kk = ce * a.cuboids.max_n + i;
+              if (a.cuboids.enable[kk] != 1) continue;
+              const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
+              const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cen) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                                                 ldgf(a.cuboids.dims + 4 * kk + 2));
+              const float pen = radj - sg.sdf;
+              if (pen > 0.0f) {
+                float ac, as;
+                collision_activation(pen, cfg.scene_activation, ac, as);
+                c += cfg.scene_weight * ac;
+                g = g + (cfg.scene_weight * as) * qrot(qconj(f.q), sg.n);
+              }
+            }
+          }
+          if (SCENE & 2) {
+            const CuboidSet none{};
+            c += sphere_scene_discrete<2>(cen, sp.w, cfg.scene_activation, cfg.scene_weight, none, a.voxels, env, g);
+          }
+        }
       } else {
         V3 pv = cen, nx = cen;
         if (prev_sph != nullptr) {
@@ -217,10 +276,12 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
       }
     }
     es.gsph[s] = make_float4(g.x, g.y, g.z, 0.0f);
+    r.nnz += (g.x != 0.0f || g.y != 0.0f || g.z != 0.0f) ? 1 : 0;
     r.scene_c += c;
     if (a.scene_cost) a.scene_cost[(size_t)e * S + s] = c;
   }
   __syncwarp();
+  r.nnz = (int)__reduce_add_sync(kFull, (unsigned)r.nnz) + 2;  // + the two self-collision spheres
   return r;
 }
 
@@ -244,7 +305,7 @@ __device__ __forceinline__ void row_phase_b2(const FusedArgs &a, const RobotView
   }
   __syncwarp();
   float *gq = a.grad_q + (size_t)e * rv.D;
-  if (!warp_fk_backward_sparse(rv, es, lane, gq)) warp_fk_backward_cold(smem_blob, a.blob, es.cumul, lane, gq);
+  if (!warp_fk_backward_sparse(rv, es, lane, gq, r.nnz)) warp_fk_backward_cold(smem_blob, a.blob, es.cumul, lane, gq);
   const float tot = warp_sum(cs_cost + pose_c + r.scene_c) + r.self_c;
   if (lane == 0) a.cost[e] = tot;
   __syncwarp();
@@ -256,30 +317,61 @@ __device__ __forceinline__ void row_phase_b2(const FusedArgs &a, const RobotView
 // row, and warps drifting through different phases thrash the instruction cache (measured: 19 % of issue
 // stalls were `no_instructions` before this).
 // ------------------------------------------------------------------------------------------------
+// Out-of-line phase wrappers: each phase rebuilds its views from the blob header in shared memory, so only a
+// handful of values stay live across phases.  With everything inlined the row body needs ~120 registers
+// (2 CTAs/SM); split this way the register budget is set by the largest phase.
+struct PhaseAOut {
+  float cs_cost, pose_c;
+};
+static __device__ __noinline__ PhaseAOut phase_a_ool(const FusedArgs *a, const unsigned char *smem, float *base, int lane,
+                                                     int e, int b, int h) {
+  const RobotView rv = make_robot_view(smem, a->blob);
+  const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  PhaseAOut o;
+  row_phase_a(*a, rv, es, lane, e, b, h, o.cs_cost, o.pose_c);
+  return o;
+}
+template <int SCENE>
+static __device__ __noinline__ RowB1 phase_b1_ool(const FusedArgs *a, const unsigned char *smem, float *base, int lane, int e,
+                                                  int b) {
+  const RobotView rv = make_robot_view(smem, a->blob);
+  const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  return row_phase_b1<false, SCENE>(*a, rv, es, lane, e, b, nullptr, nullptr);
+}
+static __device__ __noinline__ void phase_b2_ool(const FusedArgs *a, const unsigned char *smem, float *base, int lane, int e,
+                                                 RowB1 r, float cs_cost, float pose_c) {
+  const RobotView rv = make_robot_view(smem, a->blob);
+  const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  row_phase_b2(*a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+}
+
 template <int SCENE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
-  const RobotView rv = make_robot_view(smem, a.blob);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float *base = reinterpret_cast<float *>(smem + a.blob_smem_bytes) + (size_t)warp * a.eval_floats;
-  const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
   const int N = a.B * a.H;
   const int stride = gridDim.x * nwarps;
-  const int n_iter = (N + stride - 1) / stride;
-  for (int it = 0; it < n_iter; ++it) {
-    const int e = it * stride + blockIdx.x * nwarps + warp;
-    const bool active = e < N;
-    const int b = active ? e / a.H : 0, h = active ? e - b * a.H : 0;
+  for (int e = blockIdx.x * nwarps + warp; e < N; e += stride) {
+    int b = e, h = 0;
+    if (a.H != 1) {  // integer division is ~60 instructions: skip it for H == 1 (IK)
+      b = e / a.H;
+      h = e - b * a.H;
+    }
+#ifndef CB200_OOL_PHASES
+    const RobotView rv = make_robot_view(smem, a.blob);
+    const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
     float cs_cost = 0.0f, pose_c = 0.0f;
-    RowB1 r{0.0f, 0.0f, 0.0f, 0, 0};
-    if (active) row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
-    if (a.phase_sync) __syncthreads();
-    if (active) r = row_phase_b1<false, SCENE>(a, rv, es, lane, e, b, nullptr, nullptr);
-    if (a.phase_sync > 1) __syncthreads();
-    if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
-    if (a.phase_sync > 1) __syncthreads();
+    row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    const RowB1 r = row_phase_b1<false, SCENE>(a, rv, es, lane, e, b, nullptr, nullptr);
+    row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+#else
+    const PhaseAOut pa = phase_a_ool(&a, smem, base, lane, e, b, h);
+    const RowB1 r = phase_b1_ool<SCENE>(&a, smem, base, lane, e, b);
+    phase_b2_ool(&a, smem, base, lane, e, r, pa.cs_cost, pa.pose_c);
+#endif
   }
 }
 
@@ -333,7 +425,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
     }
     const int e = b * a.H + h;
     float cs_cost = 0.0f, pose_c = 0.0f;
-    RowB1 r{0.0f, 0.0f, 0.0f, 0, 0};
+    RowB1 r{0.0f, 0.0f, 0.0f, 0, 0, 0};
     if (active) row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
     __syncthreads();
     if (active) {
@@ -344,6 +436,618 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
     }
     __syncthreads();
     if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE fused kernel for small robots (arms): "tile" schedule.
+//
+// The serial, scalar parts of a row -- the FK chain, the tool-pose cost, the c-space cost and the J^T
+// up-sweep -- use 1..24 of 32 lanes when a warp owns a row (profiles/r01_b), and they are ~60 % of the
+// instructions.  Here a CTA owns a tile of T = 8 warps x 8 rows and alternates between two mappings:
+//   phase 1  thread per row  (T threads): q, c-space, FK chain in registers -> cumul[T] in shared memory,
+//                                         tool poses + tool-pose cost
+//   phase 2  warp per row    (8 warps x 8 rows each): spheres, self collision (broad phase + tiles),
+//                                         scene collision, sparse reduction of the sphere gradients to
+//                                         per-link force / torque accumulators
+//   phase 3  thread per row  (T threads): tool-frame gradients, subtree up-sweep of (F, T) in reverse link
+//                                         order, joint gradients, grad_q and row cost
+// Rows in shared memory are laid out row-major with a stride = 4 (mod 32) floats so that 128-bit accesses of
+// consecutive threads (phase 1/3) are bank-conflict free, and a warp reading one row (phase 2) uses float4.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileEpw = 8;  // rows per warp in phase 2
+
+__host__ __device__ inline int tile_stride(int floats) {  // smallest s >= floats with s % 32 == 4
+  int s = ((floats + 27) / 32) * 32 + 4;
+  return s;
+}
+
+struct TileLayout {
+  int T, cstride, fstride;
+  size_t off_scratch, scratch_floats, off_cum, off_ft, off_q, off_gq, off_pose, off_selfc, off_scenec, total_bytes;
+};
+__host__ __device__ inline TileLayout tile_layout(int blob_smem_bytes, int nwarps, int nl, int D, int S, int L, int n_cl) {
+  TileLayout t;
+  t.T = nwarps * kTileEpw;
+  t.cstride = tile_stride(nl * 12);
+  t.fstride = tile_stride(nl * 8);
+  size_t off = (size_t)blob_smem_bytes;
+  t.off_scratch = off;
+  t.scratch_floats = (size_t)(2 * S + n_cl) * 4 + (size_t)((n_cl + 3) & ~3);
+  off += (size_t)nwarps * t.scratch_floats * 4;
+  t.off_cum = off;
+  off += (size_t)t.T * t.cstride * 4;
+  t.off_ft = off;
+  off += (size_t)t.T * t.fstride * 4;
+  t.off_q = off;
+  off += (size_t)D * t.T * 4;
+  t.off_gq = off;
+  off += (size_t)D * t.T * 4;
+  t.off_pose = off;
+  off += (size_t)L * 8 * t.T * 4;
+  t.off_selfc = off;
+  off += (size_t)t.T * 4;
+  t.off_scenec = off;
+  off += (size_t)t.T * 4;
+  t.total_bytes = (off + 15) & ~(size_t)15;
+  return t;
+}
+
+template <int SCENE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_tile_kernel(const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ unsigned long long mbar;
+  stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
+  const RobotView rv = make_robot_view(smem, a.blob);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const TileLayout tl = tile_layout(a.blob_smem_bytes, nwarps, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  const int T = tl.T, D = rv.D, S = rv.S, L = rv.L, nl = rv.nl;
+  float *scratch = reinterpret_cast<float *>(smem + tl.off_scratch) + (size_t)warp * tl.scratch_floats;
+  float *cum = reinterpret_cast<float *>(smem + tl.off_cum);
+  float *ftb = reinterpret_cast<float *>(smem + tl.off_ft);
+  float *qs = reinterpret_cast<float *>(smem + tl.off_q);
+  float *gqs = reinterpret_cast<float *>(smem + tl.off_gq);
+  float *pose_g = reinterpret_cast<float *>(smem + tl.off_pose);
+  float *selfc = reinterpret_cast<float *>(smem + tl.off_selfc);
+  float *scenec = reinterpret_cast<float *>(smem + tl.off_scenec);
+  EvalSmem es;  // phase-2 view: cumul points at the current row, the rest is this warp's scratch
+  es.sph = reinterpret_cast<float4 *>(scratch);
+  es.gsph = es.sph + S;
+  es.bc = es.gsph + S;
+  es.cmask = reinterpret_cast<uint32_t *>(es.bc + rv.n_cl);
+  es.cumul = es.ft = es.contrib = es.qv = es.gqv = es.pose_g = nullptr;
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int N = a.B * a.H;
+  const int n_tiles = (N + T - 1) / T;
+  const int t = threadIdx.x;
+  const bool do_pose = (a.goal_position != nullptr);
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tile_base = tile * T;
+    // ---------------- phase 1: thread per row
+    float cs_cost = 0.0f, pose_c = 0.0f;
+    const int e1 = tile_base + t;
+    const bool act1 = (t < T) && (e1 < N);
+    if (act1) {
+      const int b = e1 / a.H, h = e1 - b * a.H;
+#pragma unroll 1
+      for (int d = 0; d < D; ++d) {
+        const float qd = __ldg(a.q + (size_t)e1 * D + d);
+        qs[d * T + t] = qd;
+        float gp;
+        const float c = cspace_dof(a, rv, e1, b, d, qd, gp);
+        gqs[d * T + t] = gp;
+        cs_cost += c;
+        if (a.cspace_cost) a.cspace_cost[(size_t)e1 * D + d] = c;
+      }
+      float *C = cum + (size_t)t * tl.cstride;
+#pragma unroll 1
+      for (int l = 0; l < nl; ++l) {
+        const int jt = rv.joint_type[l];
+        float th = 0.0f;
+        if (jt >= 0) th = rv.joff[2 * l] * qs[rv.joint_map[l] * T + t] + rv.joff[2 * l + 1];
+        float m[12];
+        local_link_transform(rv.fixed + 12 * l, jt, th, m);
+        float4 o0, o1, o2;
+        if (l == 0) {
+          o0 = make_float4(m[0], m[1], m[2], m[3]);
+          o1 = make_float4(m[4], m[5], m[6], m[7]);
+          o2 = make_float4(m[8], m[9], m[10], m[11]);
+        } else {
+          const float4 *P = reinterpret_cast<const float4 *>(C + 12 * rv.link_map[l]);
+          const float4 p0 = P[0], p1 = P[1], p2 = P[2];
+          o0 = make_float4(p0.x * m[0] + p0.y * m[4] + p0.z * m[8], p0.x * m[1] + p0.y * m[5] + p0.z * m[9],
+                           p0.x * m[2] + p0.y * m[6] + p0.z * m[10], p0.x * m[3] + p0.y * m[7] + p0.z * m[11] + p0.w);
+          o1 = make_float4(p1.x * m[0] + p1.y * m[4] + p1.z * m[8], p1.x * m[1] + p1.y * m[5] + p1.z * m[9],
+                           p1.x * m[2] + p1.y * m[6] + p1.z * m[10], p1.x * m[3] + p1.y * m[7] + p1.z * m[11] + p1.w);
+          o2 = make_float4(p2.x * m[0] + p2.y * m[4] + p2.z * m[8], p2.x * m[1] + p2.y * m[5] + p2.z * m[9],
+                           p2.x * m[2] + p2.y * m[6] + p2.z * m[10], p2.x * m[3] + p2.y * m[7] + p2.z * m[11] + p2.w);
+        }
+        float4 *O = reinterpret_cast<float4 *>(C + 12 * l);
+        O[0] = o0;
+        O[1] = o1;
+        O[2] = o2;
+      }
+#pragma unroll 1
+      for (int tf = 0; tf < L; ++tf) {
+        const float *Tm = C + 12 * rv.tool_map[tf];
+        const V3 p = mk3(Tm[3], Tm[7], Tm[11]);
+        const Q4 qt = quat_from_transform(Tm);
+        if (a.link_pos) {
+          float *o = a.link_pos + ((size_t)e1 * L + tf) * 3;
+          o[0] = p.x;
+          o[1] = p.y;
+          o[2] = p.z;
+        }
+        if (a.link_quat) *reinterpret_cast<float4 *>(a.link_quat + ((size_t)e1 * L + tf) * 4) = make_float4(qt.w, qt.x, qt.y, qt.z);
+        V3 gpos = mk3(0, 0, 0), om = mk3(0, 0, 0);
+        if (do_pose) {
+          const int gi = a.idxs_goal ? __ldg(a.idxs_goal + b) : 0;
+          const bool term = !(h < a.H - 1 && a.H > 1);
+          const float *axes = term ? a.pose_axes_t : a.pose_axes_nt;
+          const float *tol = term ? a.pose_tol_t : a.pose_tol_nt;
+          const size_t go = ((size_t)gi * L + tf) * cfg.num_goalset;
+          const PoseOut po = tool_pose_cost(p, qt, a.goal_position + go * 3, a.goal_quat + go * 4, cfg.num_goalset,
+                                            cfg.pose_weight[0], cfg.pose_weight[1], axes, tf,
+                                            tol != nullptr ? __ldg(tol + 2 * tf) : 0.0f,
+                                            tol != nullptr ? __ldg(tol + 2 * tf + 1) : 0.0f, cfg.pose_rotation_method);
+          om = quat_grad_to_omega(qt, po.gq_w, po.gq_x, po.gq_y, po.gq_z);
+          gpos = po.g_pos;
+          pose_c += po.pos_cost + po.rot_cost;
+          if (a.pose_cost) {
+            a.pose_cost[((size_t)e1 * L + tf) * 2] = po.pos_cost;
+            a.pose_cost[((size_t)e1 * L + tf) * 2 + 1] = po.rot_cost;
+          }
+          if (a.pose_goalset_idx) a.pose_goalset_idx[(size_t)e1 * L + tf] = po.goal_idx;
+        }
+        float *pg = pose_g + (size_t)tf * 8 * T + t;
+        pg[0 * T] = gpos.x;
+        pg[1 * T] = gpos.y;
+        pg[2 * T] = gpos.z;
+        pg[4 * T] = om.x;
+        pg[5 * T] = om.y;
+        pg[6 * T] = om.z;
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 2: warp per row
+#pragma unroll 1
+    for (int i = 0; i < kTileEpw; ++i) {
+      const int ti = warp * kTileEpw + i;
+      const int e = tile_base + ti;
+      if (e >= N) break;  // warp-uniform
+      const int b = e / a.H;
+      es.cumul = cum + (size_t)ti * tl.cstride;
+      float *FT = ftb + (size_t)ti * tl.fstride;
+      warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr);
+      for (int k = lane; k < nl * 2; k += 32) reinterpret_cast<float4 *>(FT)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      const RowB1 r = row_phase_b1<false, SCENE>(a, rv, es, lane, e, b, nullptr, nullptr);
+      if (r.fmax > 0.0f && lane == 0) {
+        const float4 pi = es.sph[r.bi], pj = es.sph[r.bj];
+        const float w = cfg.self_weight;
+        float4 gi = es.gsph[r.bi], gj = es.gsph[r.bj];
+        const float gx = w * (pj.x - pi.x), gy = w * (pj.y - pi.y), gz = w * (pj.z - pi.z);
+        gi.x += gx;
+        gi.y += gy;
+        gi.z += gz;
+        gj.x -= gx;
+        gj.y -= gy;
+        gj.z -= gz;
+        es.gsph[r.bi] = gi;
+        es.gsph[r.bj] = gj;
+      }
+      __syncwarp();
+      // sparse reduction of the sphere gradients to per-link (F, T about the link origin)
+#pragma unroll 1
+      for (int base = 0; base < S; base += 32) {
+        const int s = base + lane;
+        bool nz = false;
+        if (s < S) {
+          const float4 g = es.gsph[s];
+          nz = (g.x != 0.0f) || (g.y != 0.0f) || (g.z != 0.0f);
+        }
+        unsigned m = __ballot_sync(kFull, nz);
+        while (m) {
+          const int ss = base + __ffs(m) - 1;
+          m &= m - 1;
+          const float4 g4 = es.gsph[ss], p4 = es.sph[ss];
+          const int k = rv.sph_link[ss];
+          const float *Tk = es.cumul + 12 * k;
+          const V3 g = mk3(g4.x, g4.y, g4.z);
+          const V3 tq = cross(mk3(p4.x - Tk[3], p4.y - Tk[7], p4.z - Tk[11]), g);
+          if (lane < 6) {
+            const float v = lane == 0 ? g.x : lane == 1 ? g.y : lane == 2 ? g.z : lane == 3 ? tq.x : lane == 4 ? tq.y : tq.z;
+            FT[8 * k + lane + (lane >= 3 ? 1 : 0)] += v;
+          }
+          __syncwarp();
+        }
+      }
+      const float sc = warp_sum(r.scene_c);
+      if (lane == 0) {
+        selfc[ti] = r.self_c;
+        scenec[ti] = sc;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---------------- phase 3: thread per row
+    if (act1) {
+      const float *C = cum + (size_t)t * tl.cstride;
+      float *FT = ftb + (size_t)t * tl.fstride;
+#pragma unroll 1
+      for (int tf = 0; tf < L; ++tf) {
+        const float *pg = pose_g + (size_t)tf * 8 * T + t;
+        float4 *Fk = reinterpret_cast<float4 *>(FT + 8 * rv.tool_map[tf]);
+        float4 f = Fk[0], tq = Fk[1];
+        f.x += pg[0 * T];
+        f.y += pg[1 * T];
+        f.z += pg[2 * T];
+        tq.x += pg[4 * T];
+        tq.y += pg[5 * T];
+        tq.z += pg[6 * T];
+        Fk[0] = f;
+        Fk[1] = tq;
+      }
+#pragma unroll 1
+      for (int l = nl - 1; l >= 1; --l) {
+        const int p = rv.link_map[l];
+        const float4 f = reinterpret_cast<const float4 *>(FT + 8 * l)[0], tq = reinterpret_cast<const float4 *>(FT + 8 * l)[1];
+        const float *Tl = C + 12 * l, *Tp = C + 12 * p;
+        const V3 dxo = mk3(Tl[3] - Tp[3], Tl[7] - Tp[7], Tl[11] - Tp[11]);
+        const V3 cr = cross(dxo, mk3(f.x, f.y, f.z));
+        float4 *Fp = reinterpret_cast<float4 *>(FT + 8 * p);
+        float4 fp = Fp[0], tp = Fp[1];
+        fp.x += f.x;
+        fp.y += f.y;
+        fp.z += f.z;
+        tp.x += tq.x + cr.x;
+        tp.y += tq.y + cr.y;
+        tp.z += tq.z + cr.z;
+        Fp[0] = fp;
+        Fp[1] = tp;
+      }
+#pragma unroll 1
+      for (int l = 0; l < nl; ++l) {
+        const int jt = rv.joint_type[l];
+        if (jt < 0) continue;
+        const float *Tl = C + 12 * l;
+        const int ax = (jt >= JT_XR) ? jt - JT_XR : jt;
+        const V3 av = mk3(Tl[ax], Tl[4 + ax], Tl[8 + ax]);
+        const float4 w = reinterpret_cast<const float4 *>(FT + 8 * l)[(jt >= JT_XR) ? 1 : 0];
+        gqs[rv.joint_map[l] * T + t] += rv.joff[2 * l] * (av.x * w.x + av.y * w.y + av.z * w.z);
+      }
+#pragma unroll 1
+      for (int d = 0; d < D; ++d) a.grad_q[(size_t)e1 * D + d] = gqs[d * T + t];
+      a.cost[e1] = cs_cost + pose_c + scenec[t] + selfc[t];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE fused kernel for small robots, "lane" schedule: ONE THREAD PER ROW for the whole row.
+//
+// Profiles r01_a/b: with a warp per row, 60 % of the instructions run with 1..24 of 32 lanes (FK chain,
+// tool-pose cost, J^T walk) and the warp-level barriers/shuffles chain their latencies.  For an arm
+// (13 links, 65 spheres) a row is small enough for one thread: 32 rows per warp run in lock-step with every
+// lane busy, no barrier, no shuffle, and no intermediate ever leaves the thread except the link transforms
+// (shared memory, private column per thread).  Two exact broad phases keep the per-thread work small:
+//   self collision: link x link bounding spheres (same test as warp_self_collision_tiles);
+//   cuboids       : a box SDF is 1-Lipschitz, so if sdf(link bound centre) >= R_link + eta no sphere of the
+//                   link can have pen = r + eta - sdf > 0 against that cuboid.
+// Gradients go straight to joint space: every colliding sphere / tool frame walks its ancestor links.
+// ------------------------------------------------------------------------------------------------
+struct LaneLayout {
+  int cstride, bstride;  // floats per thread for cumul / link bounds, both = 4 (mod 32)
+  size_t off_cum, off_bc, off_q, off_gq, total_bytes;
+};
+__host__ __device__ inline LaneLayout lane_layout(int blob_smem_bytes, int T, int nl, int D, int n_cl) {
+  LaneLayout t;
+  t.cstride = tile_stride(nl * 12);
+  t.bstride = tile_stride((n_cl > 0 ? n_cl : 1) * 4);
+  size_t off = (size_t)blob_smem_bytes;
+  t.off_cum = off;
+  off += (size_t)T * t.cstride * 4;
+  t.off_bc = off;
+  off += (size_t)T * t.bstride * 4;
+  t.off_q = off;
+  off += (size_t)D * T * 4;
+  t.off_gq = off;
+  off += (size_t)D * T * 4;
+  t.total_bytes = (off + 15) & ~(size_t)15;
+  return t;
+}
+
+__device__ __forceinline__ V3 xf_point(const float *T, float x, float y, float z) {
+  const float4 r0 = *reinterpret_cast<const float4 *>(T), r1 = *reinterpret_cast<const float4 *>(T + 4),
+               r2 = *reinterpret_cast<const float4 *>(T + 8);
+  return mk3(r0.x * x + r0.y * y + r0.z * z + r0.w, r1.x * x + r1.y * y + r1.z * z + r1.w,
+             r2.x * x + r2.y * y + r2.z * z + r2.w);
+}
+
+constexpr int kLaneThreads = 64;
+
+template <int SCENE>
+__global__ void __launch_bounds__(kLaneThreads, 4) rollout_lane_kernel(const __grid_constant__ FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ unsigned long long mbar;
+  stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
+  const RobotView rv = make_robot_view(smem, a.blob);
+  const int t = threadIdx.x, T = blockDim.x;
+  const LaneLayout ll = lane_layout(a.blob_smem_bytes, T, rv.nl, rv.D, rv.n_cl);
+  float *C = reinterpret_cast<float *>(smem + ll.off_cum) + (size_t)t * ll.cstride;
+  float4 *BC = reinterpret_cast<float4 *>(reinterpret_cast<float *>(smem + ll.off_bc) + (size_t)t * ll.bstride);
+  float *qs = reinterpret_cast<float *>(smem + ll.off_q) + t;    // [d * T]
+  float *gqs = reinterpret_cast<float *>(smem + ll.off_gq) + t;  // [d * T]
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int D = rv.D, S = rv.S, L = rv.L, nl = rv.nl;
+  const int N = a.B * a.H;
+  const bool do_pose = (a.goal_position != nullptr);
+  const bool do_scene = SCENE != 0 && cfg.scene_weight > 0.0f;
+
+  // ancestors of link k: add  s * a_j . ((p - o_j) x g + om)  (revolute) / s * a_j . g (prismatic) to joint(j)
+  auto chain_add = [&](int k, V3 p, V3 g, V3 om) {
+    unsigned long long m = rv.anc_mask[k];
+    while (m) {
+      const int j = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      const int jt = rv.joint_type[j];
+      if (jt < 0) continue;
+      const float *Tj = C + 12 * j;
+      const int ax = (jt >= JT_XR) ? jt - JT_XR : jt;
+      const V3 av = mk3(Tj[ax], Tj[4 + ax], Tj[8 + ax]);
+      float v;
+      if (jt >= JT_XR) {
+        v = dot(av, cross(mk3(p.x - Tj[3], p.y - Tj[7], p.z - Tj[11]), g) + om);
+      } else {
+        v = dot(av, g);
+      }
+      gqs[rv.joint_map[j] * T] += rv.joff[2 * j] * v;
+    }
+  };
+
+#pragma unroll 1
+  for (int e = blockIdx.x * T + t; e < N; e += gridDim.x * T) {
+    const int b = e / a.H, h = e - b * a.H;
+    // ---- q, c-space
+    float cs_cost = 0.0f;
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+      const float qd = __ldg(a.q + (size_t)e * D + d);
+      qs[d * T] = qd;
+      float gp;
+      const float c = cspace_dof(a, rv, e, b, d, qd, gp);
+      gqs[d * T] = gp;
+      cs_cost += c;
+      if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
+    }
+    // ---- FK chain
+#pragma unroll 1
+    for (int l = 0; l < nl; ++l) {
+      const int jt = rv.joint_type[l];
+      float th = 0.0f;
+      if (jt >= 0) th = rv.joff[2 * l] * qs[rv.joint_map[l] * T] + rv.joff[2 * l + 1];
+      float m[12];
+      local_link_transform(rv.fixed + 12 * l, jt, th, m);
+      float4 o0, o1, o2;
+      if (l == 0) {
+        o0 = make_float4(m[0], m[1], m[2], m[3]);
+        o1 = make_float4(m[4], m[5], m[6], m[7]);
+        o2 = make_float4(m[8], m[9], m[10], m[11]);
+      } else {
+        const float4 *P = reinterpret_cast<const float4 *>(C + 12 * rv.link_map[l]);
+        const float4 p0 = P[0], p1 = P[1], p2 = P[2];
+        o0 = make_float4(p0.x * m[0] + p0.y * m[4] + p0.z * m[8], p0.x * m[1] + p0.y * m[5] + p0.z * m[9],
+                         p0.x * m[2] + p0.y * m[6] + p0.z * m[10], p0.x * m[3] + p0.y * m[7] + p0.z * m[11] + p0.w);
+        o1 = make_float4(p1.x * m[0] + p1.y * m[4] + p1.z * m[8], p1.x * m[1] + p1.y * m[5] + p1.z * m[9],
+                         p1.x * m[2] + p1.y * m[6] + p1.z * m[10], p1.x * m[3] + p1.y * m[7] + p1.z * m[11] + p1.w);
+        o2 = make_float4(p2.x * m[0] + p2.y * m[4] + p2.z * m[8], p2.x * m[1] + p2.y * m[5] + p2.z * m[9],
+                         p2.x * m[2] + p2.y * m[6] + p2.z * m[10], p2.x * m[3] + p2.y * m[7] + p2.z * m[11] + p2.w);
+      }
+      float4 *O = reinterpret_cast<float4 *>(C + 12 * l);
+      O[0] = o0;
+      O[1] = o1;
+      O[2] = o2;
+    }
+    // ---- tool poses + tool-pose cost (gradient walks the chain immediately)
+    float pose_c = 0.0f;
+#pragma unroll 1
+    for (int tf = 0; tf < L; ++tf) {
+      const int k = rv.tool_map[tf];
+      const float *Tm = C + 12 * k;
+      const V3 p = mk3(Tm[3], Tm[7], Tm[11]);
+      const Q4 qt = quat_from_transform(Tm);
+      if (a.link_pos) {
+        float *o = a.link_pos + ((size_t)e * L + tf) * 3;
+        o[0] = p.x;
+        o[1] = p.y;
+        o[2] = p.z;
+      }
+      if (a.link_quat) *reinterpret_cast<float4 *>(a.link_quat + ((size_t)e * L + tf) * 4) = make_float4(qt.w, qt.x, qt.y, qt.z);
+      if (do_pose) {
+        const int gi = a.idxs_goal ? __ldg(a.idxs_goal + b) : 0;
+        const bool term = !(h < a.H - 1 && a.H > 1);
+        const float *axes = term ? a.pose_axes_t : a.pose_axes_nt;
+        const float *tol = term ? a.pose_tol_t : a.pose_tol_nt;
+        const size_t go = ((size_t)gi * L + tf) * cfg.num_goalset;
+        const PoseOut po = tool_pose_cost(p, qt, a.goal_position + go * 3, a.goal_quat + go * 4, cfg.num_goalset,
+                                          cfg.pose_weight[0], cfg.pose_weight[1], axes, tf,
+                                          tol != nullptr ? __ldg(tol + 2 * tf) : 0.0f,
+                                          tol != nullptr ? __ldg(tol + 2 * tf + 1) : 0.0f, cfg.pose_rotation_method);
+        const V3 om = quat_grad_to_omega(qt, po.gq_w, po.gq_x, po.gq_y, po.gq_z);
+        pose_c += po.pos_cost + po.rot_cost;
+        if (a.pose_cost) {
+          a.pose_cost[((size_t)e * L + tf) * 2] = po.pos_cost;
+          a.pose_cost[((size_t)e * L + tf) * 2 + 1] = po.rot_cost;
+        }
+        if (a.pose_goalset_idx) a.pose_goalset_idx[(size_t)e * L + tf] = po.goal_idx;
+        const bool nzg = po.g_pos.x != 0.0f || po.g_pos.y != 0.0f || po.g_pos.z != 0.0f || om.x != 0.0f || om.y != 0.0f || om.z != 0.0f;
+        if (nzg) chain_add(k, p, po.g_pos, om);
+      }
+    }
+    // ---- self collision
+    float self_c = 0.0f;
+    if (cfg.self_weight > 0.0f && rv.P > 0) {
+      float best = 0.0f;
+      int bi = 0, bj = 0;
+      if (rv.n_lp > 0) {
+#pragma unroll 4
+        for (int ca = 0; ca < rv.n_cl; ++ca) {
+          const float4 c = rv.cl_bound[ca];
+          const V3 w = xf_point(C + 12 * rv.cl_link[ca], c.x, c.y, c.z);
+          BC[ca] = make_float4(w.x, w.y, w.z, c.w);
+        }
+#pragma unroll 4
+        for (int p = 0; p < rv.n_lp; ++p) {
+          const uint32_t pr = rv.lp[p];
+          const int la = pr & 0xffffu, lb = pr >> 16;
+          const float4 A = BC[la], Bq = BC[lb];
+          const float dx = A.x - Bq.x, dy = A.y - Bq.y, dz = A.z - Bq.z, rs = A.w + Bq.w;
+          if (!((A.w >= 0.0f) && (Bq.w >= 0.0f) && (dx * dx + dy * dy + dz * dz < rs * rs))) continue;
+          const float *Ta = C + 12 * rv.cl_link[la], *Tb = C + 12 * rv.cl_link[lb];
+#pragma unroll 2
+          for (int i = rv.cl_start[la]; i < rv.cl_start[la + 1]; ++i) {
+            const float4 si = rv.spheres[i];
+            const float ri = si.w + rv.padding[i];
+            if (!(ri >= 0.0f)) continue;
+            const V3 pi = xf_point(Ta, si.x, si.y, si.z);
+#pragma unroll 4
+            for (int j = rv.cl_start[lb]; j < rv.cl_start[lb + 1]; ++j) {
+              const float4 sj = rv.spheres[j];
+              const float rj = sj.w + rv.padding[j];
+              if (!(rj >= 0.0f)) continue;
+              const V3 pj = xf_point(Tb, sj.x, sj.y, sj.z);
+              const float rr = ri + rj, ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
+              const float f = rr * rr - (ex * ex + ey * ey + ez * ez);
+              // arg-max with ties to the first pair in list order = smallest (i, j)
+              if (f > best || (f == best && f > 0.0f && (i < bi || (i == bi && j < bj)))) {
+                best = f;
+                bi = i;
+                bj = j;
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int p = 0; p < rv.P; ++p) {  // explicit pair list (not a union of link blocks)
+          const uint32_t pr = __ldg(rv.pairs + p);
+          const int i = pr & 0xffffu, j = pr >> 16;
+          const float4 si = rv.spheres[i], sj = rv.spheres[j];
+          const float ri = si.w + rv.padding[i], rj = sj.w + rv.padding[j];
+          if (!(ri >= 0.0f && rj >= 0.0f)) continue;
+          const V3 pi = xf_point(C + 12 * rv.sph_link[i], si.x, si.y, si.z);
+          const V3 pj = xf_point(C + 12 * rv.sph_link[j], sj.x, sj.y, sj.z);
+          const float rr = ri + rj, ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
+          const float f = rr * rr - (ex * ex + ey * ey + ez * ez);
+          if (f > best) {
+            best = f;
+            bi = i;
+            bj = j;
+          }
+        }
+      }
+      if (best > 0.0f) {
+        self_c = 0.5f * cfg.self_weight * best;
+        const float4 si = rv.spheres[bi], sj = rv.spheres[bj];
+        const int ki = rv.sph_link[bi], kj = rv.sph_link[bj];
+        const V3 pi = xf_point(C + 12 * ki, si.x, si.y, si.z), pj = xf_point(C + 12 * kj, sj.x, sj.y, sj.z);
+        const V3 g = cfg.self_weight * (pj - pi);
+        chain_add(ki, pi, g, mk3(0, 0, 0));
+        chain_add(kj, pj, mk3(-g.x, -g.y, -g.z), mk3(0, 0, 0));
+      }
+    }
+    if (a.self_cost) a.self_cost[e] = self_c;
+    // ---- scene collision
+    float scene_c = 0.0f;
+    const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
+    if (do_scene && rv.n_lp > 0) {
+      // link level first: which cuboids can a link's spheres touch at all?
+#pragma unroll 1
+      for (int ca = 0; ca < rv.n_cl; ++ca) {
+        const int k = rv.cl_link[ca];
+        const float *Tk = C + 12 * k;
+        unsigned cmask = 0u;
+        int ce = 0, ncub = 0;
+        if (SCENE & 1) {
+          ce = env < a.cuboids.num_envs ? env : 0;
+          ncub = a.cuboids.count[ce];
+          if (ncub > a.cuboids.max_n) ncub = a.cuboids.max_n;
+          const float4 cb = rv.cl_bound_scene[ca];
+          if (cb.w >= 0.0f) {
+            const V3 cw = xf_point(Tk, cb.x, cb.y, cb.z);
+            if (ncub > 32) {
+              cmask = 0xffffffffu;  // more cuboids than mask bits: no culling
+            } else {
+              for (int i = 0; i < ncub; ++i) {
+                const int kk = ce * a.cuboids.max_n + i;
+                if (a.cuboids.enable[kk] != 1) continue;
+                const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
+                const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cw) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                                                   ldgf(a.cuboids.dims + 4 * kk + 2));
+                if (sg.sdf < cb.w + cfg.scene_activation) cmask |= (1u << i);
+              }
+            }
+          }
+        }
+#pragma unroll 4
+        for (int s = rv.cl_start[ca]; s < rv.cl_start[ca + 1]; ++s) {
+          const float4 sp = rv.spheres[s];
+          float c = 0.0f;
+          V3 g = mk3(0, 0, 0);
+          V3 pw = mk3(0, 0, 0);
+          const bool need_pos = (a.robot_spheres != nullptr) || (sp.w >= 0.0f && (cmask != 0u || (SCENE & 2)));
+          if (need_pos) pw = xf_point(Tk, sp.x, sp.y, sp.z);
+          if (sp.w >= 0.0f) {
+            const float radj = sp.w + cfg.scene_activation;
+            if ((SCENE & 1) && cmask != 0u) {
+              for (int i = 0; i < ncub; ++i) {
+                if (ncub <= 32 && !((cmask >> i) & 1u)) continue;
+                const int kk = ce * a.cuboids.max_n + i;
+                if (a.cuboids.enable[kk] != 1) continue;
+                const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
+                const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, pw) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                                                   ldgf(a.cuboids.dims + 4 * kk + 2));
+                const float pen = radj - sg.sdf;
+                if (pen > 0.0f) {
+                  float ac, as;
+                  collision_activation(pen, cfg.scene_activation, ac, as);
+                  c += cfg.scene_weight * ac;
+                  g = g + (cfg.scene_weight * as) * qrot(qconj(f.q), sg.n);
+                }
+              }
+            }
+            if (SCENE & 2) {
+              CuboidSet none{};
+              c += sphere_scene_discrete<2>(pw, sp.w, cfg.scene_activation, cfg.scene_weight, none, a.voxels, env, g);
+            }
+          }
+          if (a.robot_spheres) reinterpret_cast<float4 *>(a.robot_spheres)[(size_t)e * S + s] = make_float4(pw.x, pw.y, pw.z, sp.w);
+          if (a.scene_cost) a.scene_cost[(size_t)e * S + s] = c;
+          scene_c += c;
+          if (g.x != 0.0f || g.y != 0.0f || g.z != 0.0f) chain_add(k, pw, g, mk3(0, 0, 0));
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < S; ++s) {  // no link table (or no scene): plain loop over spheres
+        const float4 sp = rv.spheres[s];
+        const int k = rv.sph_link[s];
+        const V3 pw = xf_point(C + 12 * k, sp.x, sp.y, sp.z);
+        float c = 0.0f;
+        V3 g = mk3(0, 0, 0);
+        if (do_scene) c = sphere_scene_discrete<SCENE>(pw, sp.w, cfg.scene_activation, cfg.scene_weight, a.cuboids, a.voxels, env, g);
+        if (a.robot_spheres) reinterpret_cast<float4 *>(a.robot_spheres)[(size_t)e * S + s] = make_float4(pw.x, pw.y, pw.z, sp.w);
+        if (a.scene_cost) a.scene_cost[(size_t)e * S + s] = c;
+        scene_c += c;
+        if (g.x != 0.0f || g.y != 0.0f || g.z != 0.0f) chain_add(k, pw, g, mk3(0, 0, 0));
+      }
+    }
+    // ---- outputs
+#pragma unroll 1
+    for (int d = 0; d < D; ++d) a.grad_q[(size_t)e * D + d] = gqs[d * T];
+    a.cost[e] = cs_cost + pose_c + scene_c + self_c;
   }
 }
 
@@ -1141,7 +1845,9 @@ static int64_t blob_layout(const cb200_robot_sizes *sz, const int16_t *link_map,
   h->off_cl_start = take((int64_t)(max_cl + 1) * 2);
   h->off_cl_bound = take((int64_t)max_cl * 16);
   h->off_lp = take((int64_t)n_lp_cap * 4);
-  h->off_fk_sched = take((int64_t)nl * 4);
+  h->off_fk_sched = take((int64_t)nl * 8);
+  h->off_cl_bound_scene = take((int64_t)max_cl * 16);
+  h->off_sph_cl = take((int64_t)S);
   h->smem_bytes = (int32_t)off;
   h->off_pairs = take((int64_t)P * 4);
   h->total_bytes = (int32_t)off;
@@ -1226,12 +1932,13 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
     for (int lev = 1; lev < h.n_levels; ++lev) {
       for (int i = lvo[lev]; i < lvo[lev + 1]; i += 2) {
         const uint32_t l0 = (uint32_t)lvl[i], p0 = (uint32_t)link_map[l0];
-        uint32_t w = l0 | (p0 << 8) | 0xffff0000u;
+        sched[2 * steps] = (l0 * 48u) | ((p0 * 48u) << 16);
+        sched[2 * steps + 1] = 0xffffu;
         if (i + 1 < lvo[lev + 1]) {
           const uint32_t l1 = (uint32_t)lvl[i + 1], p1 = (uint32_t)link_map[l1];
-          w = l0 | (p0 << 8) | (l1 << 16) | (p1 << 24);
+          sched[2 * steps + 1] = (l1 * 48u) | ((p1 * 48u) << 16);
         }
-        sched[steps++] = w;
+        ++steps;
       }
     }
     reinterpret_cast<BlobHeader *>(o)->n_fk_steps = steps;
@@ -1326,9 +2033,39 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
         clb[4 * a + 1] = (float)cy;
         clb[4 * a + 2] = (float)cz;
         clb[4 * a + 3] = R;
+        // scene broad phase: enabled = radius >= 0, unpadded radii
+        float *cls_b = reinterpret_cast<float *>(o + h.off_cl_bound_scene);
+        double sx = 0, sy = 0, sz = 0;
+        int m = 0;
+        for (int s0 = cl_start[a]; s0 < cl_start[a + 1]; ++s0) {
+          if (link_spheres[4 * s0 + 3] < 0.0f) continue;
+          sx += link_spheres[4 * s0];
+          sy += link_spheres[4 * s0 + 1];
+          sz += link_spheres[4 * s0 + 2];
+          ++m;
+        }
+        float Rs = -1.0f;
+        if (m > 0) {
+          sx /= m;
+          sy /= m;
+          sz /= m;
+          double r = 0;
+          for (int s0 = cl_start[a]; s0 < cl_start[a + 1]; ++s0) {
+            const double rr = link_spheres[4 * s0 + 3];
+            if (rr < 0) continue;
+            const double dx = link_spheres[4 * s0] - sx, dy = link_spheres[4 * s0 + 1] - sy, dz = link_spheres[4 * s0 + 2] - sz;
+            r = std::max(r, std::sqrt(dx * dx + dy * dy + dz * dz) + rr);
+          }
+          Rs = (float)(r * (1.0 + 1e-4) + 1e-5);
+        }
+        cls_b[4 * a] = (float)sx;
+        cls_b[4 * a + 1] = (float)sy;
+        cls_b[4 * a + 2] = (float)sz;
+        cls_b[4 * a + 3] = Rs;
       }
       cls[n_cl] = (int16_t)S;
       memcpy(o + h.off_lp, lps.data(), lps.size() * 4);
+      for (int s0 = 0; s0 < S; ++s0) o[h.off_sph_cl + s0] = (unsigned char)cl_of_sphere[s0];
     }
   }
   return total;
@@ -1393,9 +2130,70 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   // IK kernel carries no ESDF code: the fused kernel's instruction footprint is what limits it.
   const int scene = (cfg->scene_weight > 0.0f ? ((a.cuboids.inv_pose ? 1 : 0) | (a.voxels.inv_pose ? 2 : 0)) : 0);
   using KernelT = void (*)(const FusedArgs);
-  static KernelT const table[2][4] = {
+  static KernelT const table[3][4] = {
       {rollout_fused_kernel<0>, rollout_fused_kernel<1>, rollout_fused_kernel<2>, rollout_fused_kernel<3>},
-      {rollout_traj_kernel<0>, rollout_traj_kernel<1>, rollout_traj_kernel<2>, rollout_traj_kernel<3>}};
+      {rollout_traj_kernel<0>, rollout_traj_kernel<1>, rollout_traj_kernel<2>, rollout_traj_kernel<3>},
+      {rollout_tile_kernel<0>, rollout_tile_kernel<1>, rollout_tile_kernel<2>, rollout_tile_kernel<3>}};
+  // small robots (arms) in discrete mode: thread-per-row "lane" schedule
+  static const int lane_env = []() {
+    const char *e = getenv("CB200_LANE");
+    return e ? atoi(e) : 0;  // off by default: measured 2.3x slower than warp-per-row (profiles/r01_c)
+  }();
+  if (!traj && lane_env != 0 && h.nl <= 24 && h.S <= 128) {
+    static KernelT const lane_table[4] = {rollout_lane_kernel<0>, rollout_lane_kernel<1>, rollout_lane_kernel<2>,
+                                          rollout_lane_kernel<3>};
+    const LaneLayout ll = lane_layout(h.smem_bytes, kLaneThreads, h.nl, h.D, h.n_cl);
+    KernelT lk = lane_table[scene];
+    static thread_local size_t lane_cfg[4] = {0, 0, 0, 0};
+    static thread_local int lane_per_sm[4] = {0, 0, 0, 0};
+    if (lane_cfg[scene] != ll.total_bytes) {
+      int per_sm = 0;
+      if (cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll.total_bytes) == cudaSuccess)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk, kLaneThreads, ll.total_bytes);
+      else
+        (void)cudaGetLastError();
+      lane_per_sm[scene] = per_sm;
+      lane_cfg[scene] = ll.total_bytes;
+    }
+    if (lane_per_sm[scene] >= 2) {
+      const long long need = (N + kLaneThreads - 1) / kLaneThreads;
+      long long g = (long long)d.sm_count * lane_per_sm[scene];
+      if (g > need) g = need;
+      lk<<<(int)g, kLaneThreads, ll.total_bytes, (cudaStream_t)stream>>>(a);
+      return launch_status();
+    }
+  }
+  // tile schedule (kept for A/B; off by default: measured slower than the warp-per-row kernel, profiles/r01_c)
+  static const int tile_env = []() {
+    const char *e = getenv("CB200_TILE");
+    return e ? atoi(e) : 0;
+  }();
+  if (!traj && tile_env != 0) {
+    const TileLayout tl = tile_layout(h.smem_bytes, kWarpsPerCta, h.nl, h.D, h.S, h.L, h.n_cl);
+    KernelT tk = table[2][scene];
+    static thread_local size_t tile_cfg[4] = {0, 0, 0, 0};
+    static thread_local int tile_per_sm[4] = {0, 0, 0, 0};
+    cudaFuncAttributes fa;
+    if (tile_cfg[scene] != tl.total_bytes) {
+      if (cudaFuncGetAttributes(&fa, tk) == cudaSuccess && 2 * (tl.total_bytes + fa.sharedSizeBytes + 1024) <= (size_t)d.max_smem + 4096 &&
+          cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total_bytes) == cudaSuccess) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tk, kWarpsPerCta * 32, tl.total_bytes);
+        tile_per_sm[scene] = per_sm;
+      } else {
+        tile_per_sm[scene] = 0;
+        (void)cudaGetLastError();
+      }
+      tile_cfg[scene] = tl.total_bytes;
+    }
+    if (tile_per_sm[scene] >= 2) {
+      const long long n_tiles = (N + tl.T - 1) / tl.T;
+      long long g = (long long)d.sm_count * tile_per_sm[scene];
+      if (g > n_tiles) g = n_tiles;
+      tk<<<(int)g, kWarpsPerCta * 32, tl.total_bytes, (cudaStream_t)stream>>>(a);
+      return launch_status();
+    }
+  }
   KernelT kern = table[traj ? 1 : 0][scene];
   const int minb = scene;  // part of the plan-cache key
   // warps per CTA: the count that keeps the most warps resident per SM (shared memory is the limiter for

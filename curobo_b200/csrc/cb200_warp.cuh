@@ -40,6 +40,8 @@ struct RobotView {
   const uint32_t *lp;
   int n_fk_steps;
   const uint32_t *fk_sched;
+  const float4 *cl_bound_scene;
+  const uint8_t *sph_cl;
 };
 
 __device__ __forceinline__ RobotView make_robot_view(const unsigned char *smem_blob, const unsigned char *gmem_blob) {
@@ -77,6 +79,8 @@ __device__ __forceinline__ RobotView make_robot_view(const unsigned char *smem_b
   v.lp = reinterpret_cast<const uint32_t *>(smem_blob + h->off_lp);
   v.n_fk_steps = h->n_fk_steps;
   v.fk_sched = reinterpret_cast<const uint32_t *>(smem_blob + h->off_fk_sched);
+  v.cl_bound_scene = reinterpret_cast<const float4 *>(smem_blob + h->off_cl_bound_scene);
+  v.sph_cl = reinterpret_cast<const uint8_t *>(smem_blob + h->off_sph_cl);
   return v;
 }
 
@@ -91,10 +95,11 @@ struct EvalSmem {
   float *gqv;     // [D]  c-space position gradient
   float *pose_g;  // [L*8]  g_pos.xyz,_, omega.xyz,_
   float4 *bc;     // [n_cl] world-frame bounding spheres of the collision links (self-collision broad phase)
+  uint32_t *cmask;  // [n_cl] scene broad phase: bit i set <=> cuboid i may touch a sphere of the link
 };
 __host__ __device__ inline int eval_smem_floats(int nl, int D, int S, int L, int n_cl) {
   int n = nl * 12 + S * 8 + nl * 8 + n_cl * 4;   // float4-aligned part
-  n += nl + D + D + L * 8;
+  n += nl + D + D + L * 8 + n_cl;
   return (n + 3) & ~3;
 }
 __device__ __forceinline__ EvalSmem carve_eval_smem(float *base, int nl, int D, int S, int L, int n_cl) {
@@ -108,6 +113,7 @@ __device__ __forceinline__ EvalSmem carve_eval_smem(float *base, int nl, int D, 
   e.qv = e.contrib + nl;
   e.gqv = e.qv + D;
   e.pose_g = e.gqv + D;
+  e.cmask = reinterpret_cast<uint32_t *>(e.pose_g + L * 8);
   return e;
 }
 
@@ -135,21 +141,26 @@ __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es,
     local_link_transform(rv.fixed + 12 * l, jt, th, (l == 0 ? es.cumul : loc) + 12 * l);
   }
   __syncwarp();
+  // compose: 12 lanes per link, two links (same depth level) per step; the schedule holds byte offsets
   const int sub = lane >> 4, k = lane & 15;
-  const int r = k >> 2, c = k & 3;
-  #pragma unroll 1
+  const bool lane_ok = k < 12;
+  const uint32_t row_off = (uint32_t)(k >> 2) * 16u, col_off = (uint32_t)(k & 3) * 4u, k_off = (uint32_t)k * 4u;
+  const float cw = ((k & 3) == 3) ? 1.0f : 0.0f;
+  unsigned char *cumb = reinterpret_cast<unsigned char *>(es.cumul);
+  const unsigned char *locb = reinterpret_cast<const unsigned char *>(loc);
+#pragma unroll 1
   for (int st = 0; st < rv.n_fk_steps; ++st) {
-    const uint32_t w = rv.fk_sched[st] >> (16 * sub);
-    const int l = w & 0xff, par = (w >> 8) & 0xff;
-    const bool act = (k < 12) && (l != 0xff);
+    const uint32_t w = rv.fk_sched[2 * st + sub];
+    const uint32_t l_off = w & 0xffffu, p_off = w >> 16;
+    const bool act = lane_ok && (l_off != 0xffffu);
     float out = 0.0f;
     if (act) {
-      const float4 pr = *reinterpret_cast<const float4 *>(es.cumul + 12 * par + 4 * r);
-      const float *Lm = loc + 12 * l;
-      out = pr.x * Lm[c] + pr.y * Lm[4 + c] + pr.z * Lm[8 + c] + (c == 3 ? pr.w : 0.0f);
+      const float4 pr = *reinterpret_cast<const float4 *>(cumb + p_off + row_off);
+      const float *Lm = reinterpret_cast<const float *>(locb + l_off + col_off);
+      out = pr.x * Lm[0] + pr.y * Lm[4] + pr.z * Lm[8] + cw * pr.w;
     }
     if (!scratch) __syncwarp();
-    if (act) es.cumul[12 * l + k] = out;
+    if (act) *reinterpret_cast<float *>(cumb + l_off + k_off) = out;
     __syncwarp();
   }
 }
@@ -365,19 +376,10 @@ static __device__ __noinline__ void warp_fk_backward_cold(const unsigned char *s
 // chain walk (kinematics_backward_helper.cuh:15-99) with the chain laid across lanes.
 // Returns false (nothing written) when the gradient is dense; the caller then uses warp_fk_backward.
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out) {
-  int nnz = 0;
-  #pragma unroll 1
-  for (int base = 0; base < rv.S; base += 32) {
-    const int s = base + lane;
-    bool nz = false;
-    if (s < rv.S) {
-      const float4 g = es.gsph[s];
-      nz = (g.x != 0.0f) || (g.y != 0.0f) || (g.z != 0.0f);
-    }
-    nnz += __popc(__ballot_sync(kFull, nz));
-  }
-  if (nnz > 2 * rv.nl) return false;
+__device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out,
+                                                        int nnz) {
+  if (nnz > 2 * rv.nl) return false;  // nnz = spheres with a non-zero gradient (counted by the caller)
+  const int nu = rv.nl > 32 ? 2 : 1;
   // per-lane link constants (slot 0: link lane, slot 1: link lane + 32)
   V3 ax[2], og[2];
   float sc[2];
@@ -386,6 +388,7 @@ __device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, con
   for (int u = 0; u < 2; ++u) {
     const int j = lane + 32 * u;
     jt[u] = -1;
+    if (u >= nu) continue;
     sc[u] = 0.0f;
     ax[u] = og[u] = mk3(0, 0, 0);
     if (j < rv.nl) {
@@ -404,7 +407,7 @@ __device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, con
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int j = lane + 32 * u;
-      if (jt[u] >= 0 && ((mask >> j) & 1ull)) {
+      if (u < nu && jt[u] >= 0 && ((mask >> j) & 1ull)) {
         acc[u] += (jt[u] >= JT_XR) ? sc[u] * (dot(ax[u], cross(p - og[u], g)) + dot(ax[u], om)) : sc[u] * dot(ax[u], g);
       }
     }
