@@ -312,14 +312,13 @@ __device__ __forceinline__ void row_phase_b2(const FusedArgs &a, const RobotView
 }
 
 // ------------------------------------------------------------------------------------------------
-// THE fused kernel, discrete scene collision: rows are independent, one warp per row.  The warps of a CTA
-// walk the phases together (__syncthreads between phases): the kernel is ~40 KB of straight-line code per
-// row, and warps drifting through different phases thrash the instruction cache (measured: 19 % of issue
-// stalls were `no_instructions` before this).
+// THE fused kernel, discrete scene collision: rows are independent, one persistent warp per row, phases
+// inlined (measured best; see profiles/r01_b_tuning_sweep.md).
 // ------------------------------------------------------------------------------------------------
-// Out-of-line phase wrappers: each phase rebuilds its views from the blob header in shared memory, so only a
-// handful of values stay live across phases.  With everything inlined the row body needs ~120 registers
-// (2 CTAs/SM); split this way the register budget is set by the largest phase.
+#ifdef CB200_OOL_PHASES
+// Tuning variant (-DCB200_OOL_PHASES): out-of-line phase wrappers.  Each phase rebuilds its views from the blob
+// header in shared memory, so only a handful of values stay live across phases: 76 instead of ~113 registers,
+// but 84 us vs 82.7 us on the Franka IK workload, hence not the default.
 struct PhaseAOut {
   float cs_cost, pose_c;
 };
@@ -344,6 +343,7 @@ static __device__ __noinline__ void phase_b2_ool(const FusedArgs *a, const unsig
   const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
   row_phase_b2(*a, rv, es, smem, lane, e, r, cs_cost, pose_c);
 }
+#endif  // CB200_OOL_PHASES
 
 template <int SCENE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
