@@ -60,14 +60,28 @@ def build_product(force: bool = False, verbose: bool = False, minb: int = 0) -> 
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared",
            "-Xptxas", "-v" if verbose else "-O3", *([f"-DCB200_MINB={minb}"] if minb > 0 else []),
-           os.path.join(CSRC, "cb200_kernels.cu"), "-o", out, "-lcudart"]
-    _run(cmd, verbose)
+           "-o", out, "-lcudart"]
+    # two translation units (rollout kernels; trajectory kernels), compiled concurrently then linked
+    units = ["cb200_kernels.cu", "cb200_trajectory.cu"]
+    objs = [os.path.join(LIBDIR, (u[:-3] + (f"_mb{minb}" if minb > 0 else "") + ".o")) for u in units]
+    flags = [c for c in cmd[1:] if c not in ("-shared", "-o", out, "-lcudart")]
+    procs = [subprocess.Popen([cmd[0], *flags, "-c", os.path.join(CSRC, u), "-o", o], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for u, o in zip(units, objs)]
+    logs = [p.communicate()[0] for p in procs]
+    if verbose:
+        print("\n".join(logs))
+    if any(p.returncode != 0 for p in procs):
+        sys.stderr.write("\n".join(logs))
+        raise RuntimeError("build failed: nvcc -c " + " ".join(units))
+    _run([cmd[0], *ARCH, "-shared", "-Xcompiler", "-fPIC", *objs, "-o", out, "-lcudart"], verbose)
+    for o in objs:
+        os.remove(o)
     return out
 
 
 def build_hostmath(force: bool = False, verbose: bool = False) -> str:
     src = os.path.join(ROOT, "tests", "hostmath", "cb200_hostmath.cu")
-    deps = [src, os.path.join(CSRC, "cb200_math.cuh")]
+    deps = [src, os.path.join(CSRC, "cb200_math.cuh"), os.path.join(CSRC, "cb200_bspline.cuh")]
     if not force and _newer(HOSTMATH_SO, deps):
         return HOSTMATH_SO
     cmd = [_nvcc(), "-std=c++17", "-O2", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared", src, "-o", HOSTMATH_SO,
@@ -89,6 +103,7 @@ def build_reference_kernels(force: bool = False, verbose: bool = False):
     cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared",
            "-I", kdir, "-I", os.path.join(kdir, "common"), "-I", os.path.join(kdir, "third_party"),
            "-I", os.path.join(kdir, "kinematics"), "-I", os.path.join(kdir, "geometry", "self_collision"),
+           "-I", os.path.join(kdir, "trajectory"), "-I", os.path.join(kdir, "trajectory", "bspline"),
            src, "-o", REF_SO, "-lcudart"]
     _run(cmd, verbose)
     return REF_SO

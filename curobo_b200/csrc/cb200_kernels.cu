@@ -70,15 +70,18 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
       wb[i] = c.cspace_weight[i];
       wr[i] = c.cspace_reg[i];
     }
+    // dt^2, dt^3 by multiplication: correctly rounded products are at least as close to the reference's
+    // wp.pow(dt, n) (wp_cspace_state.py) as powf, which costs ~100 instructions per call
+    const float dt2 = dt * dt, dt3 = dt2 * dt;
     if (c.retime_weights) {
       wb[1] = dt * wb[1];
-      wb[2] = powf(dt, 2.0f) * wb[2];
-      wb[3] = powf(dt, 3.0f) * wb[3];
+      wb[2] = dt2 * wb[2];
+      wb[3] = dt3 * wb[3];
     }
     if (c.retime_regularization_weights) {
       wr[0] = dt * wr[0];
-      wr[1] = powf(dt, 2.0f) * wr[1];
-      wr[2] = powf(dt, 3.0f) * wr[2];
+      wr[1] = dt2 * wr[1];
+      wr[2] = dt3 * wr[2];
       wr[4] = dt * wr[4];
     }
     const float v = a.vel ? __ldg(a.vel + idx) : 0.0f;

@@ -66,6 +66,9 @@ _SIGS = {
     "cb200_tool_pose_distance": ([c_p] * 16 + [_I] * 5 + [c_p], _I),
     "cb200_cspace_state_cost": ([c_p] * 25 + [_I] * 6 + [c_p], _I),
     "cb200_cspace_position_cost": ([c_p] * 19 + [_I] * 4 + [c_p], _I),
+    "cb200_bspline_forward": ([c_p] * 18 + [_I] * 5 + [c_p], _I),
+    "cb200_bspline_single_dt": ([c_p] * 20 + [_I] * 5 + [c_p], _I),
+    "cb200_bspline_backward": ([c_p] * 8 + [_I] * 5 + [c_p], _I),
     "cb200_robot_blob_bytes": ([C.POINTER(RobotSizes)], C.c_int64),
     "cb200_pack_robot_blob": ([c_p, C.c_int64, C.POINTER(RobotSizes)] + [c_p] * 15, C.c_int64),
     "cb200_rollout_cost_grad": ([C.POINTER(RolloutCfg), C.POINTER(RolloutIO), c_p], _I),

@@ -247,6 +247,45 @@ typedef struct {
 int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io,
                             cb200_stream_t stream);
 
+/* -------------------------------------------------------------------------------------------
+ * (8f-1) B-spline knot -> state kernels and their adjoint: the step in front of / behind the rollout
+ * on the trajopt / MPC path.  Argument order and meaning are the reference launchers':
+ *   cb200_bspline_forward    <- launch_bspline_interpolation_forward_kernel
+ *       curobo/_src/curobolib/backends/cuda_core_backend/trajectory.py:25-137
+ *       (pybind twin: backends/pybind/trajectory_kernel_launch.cu:263-404)
+ *   cb200_bspline_single_dt  <- launch_bspline_interpolation_single_dt_kernel  trajectory.py:213-330
+ *   cb200_bspline_backward   <- launch_bspline_interpolation_backward_kernel   trajectory.py:140-210
+ * u_position [B, n_knots, D]; start_* / goal_* [n_start|n_goal, D] gathered through start_idx / goal_idx [B];
+ * traj_dt and use_implicit_goal_state are [n_goal] and indexed through goal_idx (dt_idx in the adjoint);
+ * outputs [B, padded_horizon, D] with padded_horizon = (n_knots + degree + 1) * interpolation_steps + 1.
+ * degree in {3,4,5} (MATRIX basis).  The adjoint returns cudaErrorInvalidValue where the reference launcher
+ * throws (horizon < 5, interpolation_steps == 0 or > 32, unsupported degree).
+ * ------------------------------------------------------------------------------------------- */
+int cb200_bspline_forward(
+    float *out_position, float *out_velocity, float *out_acceleration, float *out_jerk, float *out_dt,
+    const float *u_position, const float *start_position, const float *start_velocity,
+    const float *start_acceleration, const float *start_jerk, const float *goal_position,
+    const float *goal_velocity, const float *goal_acceleration, const float *goal_jerk,
+    const int32_t *start_idx, const int32_t *goal_idx, const float *traj_dt,
+    const uint8_t *use_implicit_goal_state, int batch_size, int padded_horizon, int dof, int n_knots,
+    int bspline_degree, cb200_stream_t stream);
+
+int cb200_bspline_single_dt(
+    float *out_position, float *out_velocity, float *out_acceleration, float *out_jerk, float *out_dt,
+    const float *u_position, const float *knot_dt, const float *start_position,
+    const float *start_velocity, const float *start_acceleration, const float *start_jerk,
+    const float *goal_position, const float *goal_velocity, const float *goal_acceleration,
+    const float *goal_jerk, const int32_t *start_idx, const int32_t *goal_idx,
+    const float *interpolation_dt, const uint8_t *use_implicit_goal_state,
+    const int32_t *interpolation_horizon, int batch_size, int max_out_tsteps, int dof, int n_knots,
+    int bspline_degree, cb200_stream_t stream);
+
+int cb200_bspline_backward(
+    float *out_grad_knots, const float *grad_position, const float *grad_velocity,
+    const float *grad_acceleration, const float *grad_jerk, const float *traj_dt,
+    const int32_t *dt_idx, const uint8_t *use_implicit_goal_state, int batch_size, int padded_horizon,
+    int dof, int n_knots, int bspline_degree, cb200_stream_t stream);
+
 /* Host helper: pack robot constants (HOST pointers) into `out` (host buffer of
  * cb200_robot_blob_bytes(...) bytes) that the caller then copies to the device once.
  * Returns bytes written or a negative number on invalid input. */

@@ -126,3 +126,94 @@ int ref_self_collision_distance(float *out_distance, float *out_vec, float *pair
   return (int)cudaGetLastError();
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// B-spline knot -> state kernels.  Launch math follows
+// backends/pybind/trajectory_kernel_launch.cu:263-404 (forward, 128 threads), :406-566 (single dt, 256 threads),
+// :571-683 (backward, 128 threads, batch*dof*threads_for_n_knots); MATRIX basis backend like :259.
+// ------------------------------------------------------------------------------------------------
+#include "trajectory/bspline/bspline_common.cuh"
+#include "trajectory/bspline/bspline_kernel.cuh"
+
+namespace cbs = curobo::trajectory::bspline;
+
+template <int DEG>
+static void ref_bspline_fwd_t(int blocks, int threads, cudaStream_t stream, float *op, float *ov, float *oa, float *oj,
+                              float *odt, const float *u, const float *sp, const float *sv, const float *sa,
+                              const float *sj, const float *gp, const float *gv, const float *ga, const float *gj,
+                              const int32_t *sidx, const int32_t *gidx, const float *traj_dt, const uint8_t *implicit,
+                              int B, int T, int D, int nk) {
+  cbs::interpolate_bspline_kernel<float, DEG, cbs::BasisBackend::MATRIX><<<blocks, threads, 0, stream>>>(
+      op, ov, oa, oj, odt, u, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, traj_dt, implicit, B, T, D, nk);
+}
+
+template <int DEG>
+static void ref_bspline_sdt_t(int blocks, int threads, cudaStream_t stream, float *op, float *ov, float *oa, float *oj,
+                              float *odt, const float *u, const float *knot_dt, const float *sp, const float *sv,
+                              const float *sa, const float *sj, const float *gp, const float *gv, const float *ga,
+                              const float *gj, const int32_t *sidx, const int32_t *gidx, const float *interp_dt,
+                              const uint8_t *implicit, const int32_t *interp_h, int B, int T, int D, int nk) {
+  cbs::interpolate_bspline_single_dt_kernel<float, DEG, cbs::BasisBackend::MATRIX><<<blocks, threads, 0, stream>>>(
+      op, ov, oa, oj, odt, u, knot_dt, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, interp_dt, implicit, interp_h, B, T,
+      D, nk);
+}
+
+template <int DEG>
+static int ref_bspline_bwd_t(cudaStream_t stream, float *out, const float *gp, const float *gv, const float *ga,
+                             const float *gj, const float *traj_dt, const int32_t *dt_idx, const uint8_t *implicit,
+                             int B, int horizon, int D, int nk) {
+  cbs::BSplineBackwardLayout layout = cbs::compute_bspline_backward_layout<DEG>(horizon, D, nk);
+  if (layout.interpolation_steps <= 0 || layout.interpolation_steps > 32) return 1;
+  const int k_size = B * D * layout.threads_for_n_knots;
+  const int threads = k_size > 128 ? 128 : k_size;
+  const int blocks = (k_size + threads - 1) / threads;
+  cbs::bspline_backward_kernel<DEG, float, cbs::BasisBackend::MATRIX><<<blocks, threads, 0, stream>>>(
+      out, gp, gv, ga, gj, traj_dt, dt_idx, implicit, B, horizon, D, nk);
+  return 0;
+}
+
+extern "C" {
+
+int ref_bspline_forward(float *op, float *ov, float *oa, float *oj, float *odt, const float *u, const float *sp,
+                        const float *sv, const float *sa, const float *sj, const float *gp, const float *gv,
+                        const float *ga, const float *gj, const int32_t *sidx, const int32_t *gidx, const float *traj_dt,
+                        const uint8_t *implicit, int B, int padded_horizon, int D, int nk, int degree,
+                        cudaStream_t stream) {
+  const int k_size = B * padded_horizon * D;
+  const int threads = k_size > 128 ? 128 : k_size;
+  const int blocks = (k_size + threads - 1) / threads;
+  if (degree == 3) ref_bspline_fwd_t<3>(blocks, threads, stream, op, ov, oa, oj, odt, u, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, traj_dt, implicit, B, padded_horizon, D, nk);
+  else if (degree == 4) ref_bspline_fwd_t<4>(blocks, threads, stream, op, ov, oa, oj, odt, u, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, traj_dt, implicit, B, padded_horizon, D, nk);
+  else if (degree == 5) ref_bspline_fwd_t<5>(blocks, threads, stream, op, ov, oa, oj, odt, u, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, traj_dt, implicit, B, padded_horizon, D, nk);
+  else return 1;
+  return (int)cudaGetLastError();
+}
+
+int ref_bspline_single_dt(float *op, float *ov, float *oa, float *oj, float *odt, const float *u, const float *knot_dt,
+                          const float *sp, const float *sv, const float *sa, const float *sj, const float *gp,
+                          const float *gv, const float *ga, const float *gj, const int32_t *sidx, const int32_t *gidx,
+                          const float *interp_dt, const uint8_t *implicit, const int32_t *interp_h, int B,
+                          int max_out_tsteps, int D, int nk, int degree, cudaStream_t stream) {
+  const int k_size = B * max_out_tsteps * D;
+  const int threads = k_size > 256 ? 256 : k_size;
+  const int blocks = (k_size + threads - 1) / threads;
+  if (degree == 3) ref_bspline_sdt_t<3>(blocks, threads, stream, op, ov, oa, oj, odt, u, knot_dt, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, interp_dt, implicit, interp_h, B, max_out_tsteps, D, nk);
+  else if (degree == 4) ref_bspline_sdt_t<4>(blocks, threads, stream, op, ov, oa, oj, odt, u, knot_dt, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, interp_dt, implicit, interp_h, B, max_out_tsteps, D, nk);
+  else if (degree == 5) ref_bspline_sdt_t<5>(blocks, threads, stream, op, ov, oa, oj, odt, u, knot_dt, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, interp_dt, implicit, interp_h, B, max_out_tsteps, D, nk);
+  else return 1;
+  return (int)cudaGetLastError();
+}
+
+int ref_bspline_backward(float *out, const float *gp, const float *gv, const float *ga, const float *gj,
+                         const float *traj_dt, const int32_t *dt_idx, const uint8_t *implicit, int B,
+                         int padded_horizon, int D, int nk, int degree, cudaStream_t stream) {
+  const int horizon = padded_horizon - 1;  // trajectory_kernel_launch.cu:592
+  int rc = 1;
+  if (degree == 3) rc = ref_bspline_bwd_t<3>(stream, out, gp, gv, ga, gj, traj_dt, dt_idx, implicit, B, horizon, D, nk);
+  else if (degree == 4) rc = ref_bspline_bwd_t<4>(stream, out, gp, gv, ga, gj, traj_dt, dt_idx, implicit, B, horizon, D, nk);
+  else if (degree == 5) rc = ref_bspline_bwd_t<5>(stream, out, gp, gv, ga, gj, traj_dt, dt_idx, implicit, B, horizon, D, nk);
+  if (rc) return rc;
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -77,3 +77,75 @@ void hm_tool_pose(const float *pos3, const float *quat_wxyz, const float *goal_p
   *goal_idx = o.goal_idx;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// B-spline knot -> state and adjoint, host build of curobo_b200/csrc/cb200_bspline.cuh
+// ------------------------------------------------------------------------------------------------
+#include "../../curobo_b200/csrc/cb200_bspline.cuh"
+
+namespace bs = cb200::bspline;
+
+template <int DEG>
+static void hm_bspline_forward_t(float *op, float *ov, float *oa, float *oj, const float *u, const float *sp, const float *sv,
+                                 const float *sa, const float *sj, const float *gp, const float *gv, const float *ga,
+                                 const float *gj, const int32_t *sidx, const int32_t *gidx, const float *traj_dt,
+                                 const uint8_t *implicit, const int32_t *interp_h, int B, int T, int D, int nk) {
+  for (int b = 0; b < B; ++b) {
+    int padded = T;
+    float dt = interp_h ? traj_dt[0] : traj_dt[gidx[b]];
+    if (interp_h) padded = (interp_h[b] < T - 1 ? interp_h[b] : T - 1) + 1;
+    const int steps = (padded - 1) / (nk + DEG + 1);
+    for (int d = 0; d < D; ++d) {
+      bs::ControlPolygon<DEG> cp = bs::make_polygon<DEG>(u, b, d, D, nk, dt, steps, implicit[gidx[b]] != 0, sp, sv, sa, sj,
+                                                        sidx[b], gp, gv, ga, gj, gidx[b]);
+      for (int h = 0; h < T; ++h) {
+        bs::State4 s = bs::evaluate<DEG>(cp, h, steps);
+        const size_t o = ((size_t)b * T + h) * D + d;
+        op[o] = s.p;
+        ov[o] = s.v;
+        oa[o] = s.a;
+        oj[o] = s.j;
+      }
+    }
+  }
+}
+
+template <int DEG>
+static void hm_bspline_backward_t(float *out, const float *gp, const float *gv, const float *ga, const float *gj,
+                                  const float *traj_dt, const int32_t *dt_idx, const uint8_t *implicit, int B, int T, int D,
+                                  int nk) {
+  const int horizon = T - 1, steps = horizon / (nk + DEG + 1);
+  for (int b = 0; b < B; ++b)
+    for (int k = 0; k < nk; ++k)
+      for (int d = 0; d < D; ++d) {
+        const size_t base = (size_t)b * T * D + d;
+        auto G = [=](int h, int which) -> float {
+          const float *src = which == 0 ? gp : which == 1 ? gv : which == 2 ? ga : gj;
+          return src[base + (size_t)h * D];
+        };
+        out[((size_t)b * nk + k) * D + d] =
+            bs::knot_gradient<DEG>(k, steps, nk, horizon, implicit[dt_idx[b]] != 0, traj_dt[dt_idx[b]], G);
+      }
+}
+
+extern "C" {
+int hm_bspline_forward(float *op, float *ov, float *oa, float *oj, const float *u, const float *sp, const float *sv,
+                       const float *sa, const float *sj, const float *gp, const float *gv, const float *ga, const float *gj,
+                       const int32_t *sidx, const int32_t *gidx, const float *traj_dt, const uint8_t *implicit,
+                       const int32_t *interp_h, int B, int T, int D, int nk, int degree) {
+  if (degree == 3) hm_bspline_forward_t<3>(op, ov, oa, oj, u, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, traj_dt, implicit, interp_h, B, T, D, nk);
+  else if (degree == 4) hm_bspline_forward_t<4>(op, ov, oa, oj, u, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, traj_dt, implicit, interp_h, B, T, D, nk);
+  else if (degree == 5) hm_bspline_forward_t<5>(op, ov, oa, oj, u, sp, sv, sa, sj, gp, gv, ga, gj, sidx, gidx, traj_dt, implicit, interp_h, B, T, D, nk);
+  else return 1;
+  return 0;
+}
+
+int hm_bspline_backward(float *out, const float *gp, const float *gv, const float *ga, const float *gj, const float *traj_dt,
+                        const int32_t *dt_idx, const uint8_t *implicit, int B, int T, int D, int nk, int degree) {
+  if (degree == 3) hm_bspline_backward_t<3>(out, gp, gv, ga, gj, traj_dt, dt_idx, implicit, B, T, D, nk);
+  else if (degree == 4) hm_bspline_backward_t<4>(out, gp, gv, ga, gj, traj_dt, dt_idx, implicit, B, T, D, nk);
+  else if (degree == 5) hm_bspline_backward_t<5>(out, gp, gv, ga, gj, traj_dt, dt_idx, implicit, B, T, D, nk);
+  else return 1;
+  return 0;
+}
+}

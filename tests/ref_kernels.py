@@ -82,3 +82,40 @@ def self_collision(rm, spheres, padding, pairs, weight):
                                             pairs.shape[0], 1, _stream(dev))
     assert err == 0, err
     return dist, vec
+
+
+# ------------------------------------------------------------------------------------------------
+# B-spline kernels of the reference (kernels/trajectory/bspline/bspline_kernel.cuh)
+# ------------------------------------------------------------------------------------------------
+def bspline_forward(knots, start, goal, start_idx, goal_idx, traj_dt, implicit, padded_horizon, degree):
+    dev = knots.device
+    B, nk, D = knots.shape
+    outs = [torch.zeros((B, padded_horizon, D), dtype=torch.float32, device=dev) for _ in range(4)]
+    odt = torch.zeros((B,), dtype=torch.float32, device=dev)
+    err = lib().ref_bspline_forward(*[_p(o) for o in outs], _p(odt), _p(knots), *[_p(x) for x in start],
+                                    *[_p(x) for x in goal], _p(start_idx), _p(goal_idx), _p(traj_dt), _p(implicit), B,
+                                    padded_horizon, D, nk, degree, _stream(dev))
+    assert err == 0, err
+    return outs + [odt]
+
+
+def bspline_single_dt(knots, start, goal, start_idx, goal_idx, interp_dt, implicit, interp_h, max_out_tsteps, degree):
+    dev = knots.device
+    B, nk, D = knots.shape
+    outs = [torch.zeros((B, max_out_tsteps, D), dtype=torch.float32, device=dev) for _ in range(4)]
+    odt = torch.zeros((B,), dtype=torch.float32, device=dev)
+    err = lib().ref_bspline_single_dt(*[_p(o) for o in outs], _p(odt), _p(knots), None, *[_p(x) for x in start],
+                                      *[_p(x) for x in goal], _p(start_idx), _p(goal_idx), _p(interp_dt), _p(implicit),
+                                      _p(interp_h), B, max_out_tsteps, D, nk, degree, _stream(dev))
+    assert err == 0, err
+    return outs + [odt]
+
+
+def bspline_backward(grads, traj_dt, dt_idx, implicit, n_knots, degree):
+    dev = grads[0].device
+    B, T, D = grads[0].shape
+    out = torch.zeros((B, n_knots, D), dtype=torch.float32, device=dev)
+    err = lib().ref_bspline_backward(_p(out), *[_p(g) for g in grads], _p(traj_dt), _p(dt_idx), _p(implicit), B, T, D,
+                                     n_knots, degree, _stream(dev))
+    assert err == 0, err
+    return out
