@@ -20,6 +20,7 @@
 
 #include "../../include/curobo_b200.h"
 #include "cb200_blob.h"
+#include "cb200_bspline.cuh"
 #include "cb200_math.cuh"
 #include "cb200_warp.cuh"
 
@@ -49,11 +50,64 @@ struct FusedArgs {
   int32_t B, H;
   int32_t blob_smem_bytes, eval_floats;
   int32_t phase_sync;  // 0: warps free-run; 1: one CTA barrier per row (after phase A); 2: barrier after every phase
+  // B-spline front end (8f-1): when spl.knots != nullptr the rows are the spline states of the knots and
+  // q / vel / acc / jerk / dt above are not read
+  struct Spline {
+    const float *knots, *sp, *sv, *sa, *sj, *gp, *gv, *ga, *gj, *traj_dt;
+    const int32_t *start_idx, *goal_idx;
+    const uint8_t *implicit;
+    float *out_p, *out_v, *out_a, *out_j;
+    int32_t n_knots, degree, steps;
+  } spl;
 };
 
+// State (q, qd, qdd, qddd) of row (b, h), dof d.  Spline mode evaluates the knots in place (one out-of-line copy
+// for the three degrees); otherwise the caller's [B,H,D] arrays are read.
+__device__ __noinline__ bspline::State4 spline_row_state(const FusedArgs::Spline &s, int b, int h, int d, int D) {
+  const int srow = __ldg(s.start_idx + b), grow = __ldg(s.goal_idx + b);
+  const float dt = __ldg(s.traj_dt + grow);
+  const bool implicit = s.implicit[grow] != 0;
+  bspline::State4 st;
+  if (s.degree == 3) {
+    st = bspline::evaluate<3>(bspline::make_polygon<3>(s.knots, b, d, D, s.n_knots, dt, s.steps, implicit, s.sp, s.sv, s.sa, s.sj, srow, s.gp, s.gv, s.ga, s.gj, grow), h, s.steps);
+  } else if (s.degree == 5) {
+    st = bspline::evaluate<5>(bspline::make_polygon<5>(s.knots, b, d, D, s.n_knots, dt, s.steps, implicit, s.sp, s.sv, s.sa, s.sj, srow, s.gp, s.gv, s.ga, s.gj, grow), h, s.steps);
+  } else {
+    st = bspline::evaluate<4>(bspline::make_polygon<4>(s.knots, b, d, D, s.n_knots, dt, s.steps, implicit, s.sp, s.sv, s.sa, s.sj, srow, s.gp, s.gv, s.ga, s.gj, grow), h, s.steps);
+  }
+  return st;
+}
+
+template <bool SPLINE>
+__device__ __forceinline__ bspline::State4 load_row_state(const FusedArgs &a, int e, int b, int h, int d, int D) {
+  if (SPLINE) {
+    const bspline::State4 st = spline_row_state(a.spl, b, h, d, D);
+    const size_t idx = (size_t)e * D + d;
+    if (a.spl.out_p) a.spl.out_p[idx] = st.p;
+    if (a.spl.out_v) a.spl.out_v[idx] = st.v;
+    if (a.spl.out_a) a.spl.out_a[idx] = st.a;
+    if (a.spl.out_j) a.spl.out_j[idx] = st.j;
+    return st;
+  }
+  const size_t idx = (size_t)e * D + d;
+  bspline::State4 st;
+  st.p = __ldg(a.q + idx);
+  st.v = a.vel ? __ldg(a.vel + idx) : 0.0f;
+  st.a = a.acc ? __ldg(a.acc + idx) : 0.0f;
+  st.j = a.jerk ? __ldg(a.jerk + idx) : 0.0f;
+  return st;
+}
+
+// trajectory dt of seed b (STATE c-space retiming): the spline's own dt in spline mode
+__device__ __forceinline__ float seed_dt(const FusedArgs &a, int b) {
+  if (a.spl.knots != nullptr) return __ldg(a.spl.traj_dt + __ldg(a.spl.goal_idx + b));
+  return a.dt ? __ldg(a.dt + b) : 1.0f;
+}
+
 // c-space cost for one dof; returns cost, writes gradient wrt position into gp (and v/a/j grads to global)
-__device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView &rv, int e, int b, int d, float qd,
-                                            float &gp) {
+__device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView &rv, int e, int b, int d,
+                                            const bspline::State4 &st, float &gp) {
+  const float qd = st.p;
   const cb200_rollout_cfg &c = a.cfg;
   const int D = rv.D;
   const float *lim = rv.limits;
@@ -63,7 +117,7 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
     bound_cost(qd, lim[d], lim[D + d], c.cspace_activation[0], c.cspace_weight[0], cost, gp);
   } else if (c.cspace_type == 2) {
     const size_t idx = (size_t)e * D + d;
-    const float dt = a.dt ? __ldg(a.dt + b) : 1.0f;
+    const float dt = seed_dt(a, b);
     float wb[5], wr[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -84,9 +138,7 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
       wr[2] = dt3 * wr[2];
       wr[4] = dt * wr[4];
     }
-    const float v = a.vel ? __ldg(a.vel + idx) : 0.0f;
-    const float ac = a.acc ? __ldg(a.acc + idx) : 0.0f;
-    const float jk = a.jerk ? __ldg(a.jerk + idx) : 0.0f;
+    const float v = st.v, ac = st.a, jk = st.j;
     float gv = 0.0f, ga = 0.0f, gj = 0.0f;
     bound_cost(qd, lim[d], lim[D + d], c.cspace_activation[0], wb[0], cost, gp);
     bound_cost(v, lim[2 * D + d], lim[3 * D + d], c.cspace_activation[1], wb[1], cost, gv);
@@ -108,6 +160,7 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
 //   phase A: q load + c-space cost, FK, spheres (+ padded copy), tool poses + tool-pose cost
 //   phase B: self collision, scene collision (discrete | swept + speed metric), J^T backward, row cost
 // ------------------------------------------------------------------------------------------------
+template <bool SPLINE>
 __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
                                             int b, int h, float &cs_cost, float &pose_c) {
   const cb200_rollout_cfg &cfg = a.cfg;
@@ -115,10 +168,10 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
   cs_cost = 0.0f;
   #pragma unroll 1
   for (int d = lane; d < D; d += 32) {
-    const float qd = __ldg(a.q + (size_t)e * D + d);
-    es.qv[d] = qd;
+    const bspline::State4 st = load_row_state<SPLINE>(a, e, b, h, d, D);
+    es.qv[d] = st.p;
     float gp;
-    const float c = cspace_dof(a, rv, e, b, d, qd, gp);
+    const float c = cspace_dof(a, rv, e, b, d, st, gp);
     es.gqv[d] = gp;
     cs_cost += c;
     if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
@@ -194,7 +247,9 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
   // ---- scene collision (lane per sphere) -> gsph = gradient
   const bool do_scene = SCENE != 0 && cfg.scene_weight > 0.0f;
   const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
-  const float sdt = (SWEEP && cfg.use_speed_metric && a.dt != nullptr) ? __ldg(a.dt) : 0.0f;
+  const float sdt = (SWEEP && cfg.use_speed_metric && (a.dt != nullptr || a.spl.knots != nullptr))
+                        ? (a.spl.knots != nullptr ? __ldg(a.spl.traj_dt + __ldg(a.spl.goal_idx)) : __ldg(a.dt))
+                        : 0.0f;
   // cuboid broad phase (discrete mode): a box SDF is 1-Lipschitz, so sdf(link bound centre) >= R_link + eta
   // means no sphere of the link has pen = r + eta - sdf > 0 against that cuboid -> skipping it is exact.
   int ce = 0, ncub = 0;
@@ -330,7 +385,7 @@ static __device__ __noinline__ PhaseAOut phase_a_ool(const FusedArgs *a, const u
   const RobotView rv = make_robot_view(smem, a->blob);
   const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
   PhaseAOut o;
-  row_phase_a(*a, rv, es, lane, e, b, h, o.cs_cost, o.pose_c);
+  row_phase_a<false>(*a, rv, es, lane, e, b, h, o.cs_cost, o.pose_c);
   return o;
 }
 template <int SCENE>
@@ -348,7 +403,7 @@ static __device__ __noinline__ void phase_b2_ool(const FusedArgs *a, const unsig
 }
 #endif  // CB200_OOL_PHASES
 
-template <int SCENE>
+template <int SCENE, bool SPLINE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
@@ -367,7 +422,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_fused_k
     const RobotView rv = make_robot_view(smem, a.blob);
     const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
     float cs_cost = 0.0f, pose_c = 0.0f;
-    row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    row_phase_a<SPLINE>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
     const RowB1 r = row_phase_b1<false, SCENE>(a, rv, es, lane, e, b, nullptr, nullptr);
     row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
 #else
@@ -384,7 +439,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_fused_k
 // waypoint (warp 0 / the last warp also compute the halo waypoints' spheres), the CTA synchronises, then
 // every warp runs phase B reading its neighbours' sphere positions from shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int SCENE>
+template <int SCENE, bool SPLINE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
@@ -415,7 +470,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
     }
     if (hh >= 0) {
       const size_t eh = (size_t)b * a.H + hh;
-      for (int d = lane; d < D; d += 32) es.qv[d] = __ldg(a.q + eh * D + d);
+      for (int d = lane; d < D; d += 32)
+        es.qv[d] = SPLINE ? spline_row_state(a.spl, b, hh, d, D).p : __ldg(a.q + eh * D + d);
       __syncwarp();
       warp_fk(rv, es, lane);
       for (int s = lane; s < S; s += 32) {
@@ -429,7 +485,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
     const int e = b * a.H + h;
     float cs_cost = 0.0f, pose_c = 0.0f;
     RowB1 r{0.0f, 0.0f, 0.0f, 0, 0, 0};
-    if (active) row_phase_a(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    if (active) row_phase_a<SPLINE>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
     __syncthreads();
     if (active) {
       const float4 *prev = nullptr, *next = nullptr;
@@ -535,10 +591,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_tile_kernel(cons
       const int b = e1 / a.H, h = e1 - b * a.H;
 #pragma unroll 1
       for (int d = 0; d < D; ++d) {
-        const float qd = __ldg(a.q + (size_t)e1 * D + d);
-        qs[d * T + t] = qd;
+        const bspline::State4 st = load_row_state<false>(a, e1, b, h, d, D);
+        qs[d * T + t] = st.p;
         float gp;
-        const float c = cspace_dof(a, rv, e1, b, d, qd, gp);
+        const float c = cspace_dof(a, rv, e1, b, d, st, gp);
         gqs[d * T + t] = gp;
         cs_cost += c;
         if (a.cspace_cost) a.cspace_cost[(size_t)e1 * D + d] = c;
@@ -817,10 +873,10 @@ __global__ void __launch_bounds__(kLaneThreads, 4) rollout_lane_kernel(const __g
     float cs_cost = 0.0f;
 #pragma unroll 4
     for (int d = 0; d < D; ++d) {
-      const float qd = __ldg(a.q + (size_t)e * D + d);
-      qs[d * T] = qd;
+      const bspline::State4 st = load_row_state<false>(a, e, b, h, d, D);
+      qs[d * T] = st.p;
       float gp;
-      const float c = cspace_dof(a, rv, e, b, d, qd, gp);
+      const float c = cspace_dof(a, rv, e, b, d, st, gp);
       gqs[d * T] = gp;
       cs_cost += c;
       if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
@@ -2075,9 +2131,25 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
 }
 
 int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io, cb200_stream_t stream) {
-  if (cfg == nullptr || io == nullptr || io->q == nullptr || io->robot_blob == nullptr || io->cost == nullptr ||
-      io->grad_q == nullptr || io->batch_size < 0 || io->horizon < 1)
+  if (cfg == nullptr || io == nullptr || io->robot_blob == nullptr || io->cost == nullptr || io->grad_q == nullptr ||
+      io->batch_size < 0 || io->horizon < 1)
     return ret(cudaErrorInvalidValue);
+  const cb200_spline_input *sp = io->spline;
+  if (sp == nullptr && io->q == nullptr) return ret(cudaErrorInvalidValue);
+  int spline_steps = 0;
+  if (sp != nullptr) {
+    if (sp->knots == nullptr || sp->start_position == nullptr || sp->start_velocity == nullptr ||
+        sp->start_acceleration == nullptr || sp->start_jerk == nullptr || sp->start_idx == nullptr ||
+        sp->goal_idx == nullptr || sp->traj_dt == nullptr || sp->use_implicit_goal_state == nullptr ||
+        sp->goal_position == nullptr || sp->goal_velocity == nullptr || sp->goal_acceleration == nullptr ||
+        sp->goal_jerk == nullptr || sp->n_knots < 1 || sp->degree < 3 || sp->degree > 5)
+      return ret(cudaErrorInvalidValue);
+    spline_steps = (io->horizon - 1) / (sp->n_knots + sp->degree + 1);
+    if (sp->grad_knots != nullptr &&
+        (io->grad_vel == nullptr || io->grad_acc == nullptr || io->grad_jerk == nullptr || io->horizon - 1 < 5 ||
+         spline_steps < 1 || spline_steps > 32))
+      return ret(cudaErrorInvalidValue);
+  }
   if (io->goal_position != nullptr && (io->goal_quat == nullptr || cfg->num_goalset < 1)) return ret(cudaErrorInvalidValue);
   const long long N = (long long)io->batch_size * io->horizon;
   if (N == 0) return ret(cudaSuccess);
@@ -2126,23 +2198,40 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     return e ? atoi(e) : 0;
   }();
   a.phase_sync = phase_sync_env;
+  if (sp != nullptr) {
+    a.spl = FusedArgs::Spline{sp->knots, sp->start_position, sp->start_velocity, sp->start_acceleration, sp->start_jerk,
+                              sp->goal_position, sp->goal_velocity, sp->goal_acceleration, sp->goal_jerk, sp->traj_dt,
+                              sp->start_idx, sp->goal_idx, sp->use_implicit_goal_state, sp->out_position,
+                              sp->out_velocity, sp->out_acceleration, sp->out_jerk, sp->n_knots, sp->degree, spline_steps};
+  }
   DevInfo &d = dev_info();
   const bool traj = cfg->use_sweep != 0;
-  if (traj && cfg->use_speed_metric && io->dt == nullptr) return ret(cudaErrorInvalidValue);
+  if (traj && cfg->use_speed_metric && io->dt == nullptr && sp == nullptr) return ret(cudaErrorInvalidValue);
+  // the adjoint of the spline front end runs right behind the rollout kernel on the same stream
+  auto finish = [&]() -> int {
+    const int rc = launch_status();
+    if (rc != 0 || sp == nullptr || sp->grad_knots == nullptr) return rc;
+    return ret((cudaError_t)cb200_bspline_backward(sp->grad_knots, io->grad_q, io->grad_vel, io->grad_acc, io->grad_jerk,
+                                                   sp->traj_dt, sp->goal_idx, sp->use_implicit_goal_state, io->batch_size,
+                                                   io->horizon, h.D, sp->n_knots, sp->degree, stream));
+  };
   // kernels are specialised on the obstacle types present (bit 0 cuboids, bit 1 voxel grids) so that e.g. the
   // IK kernel carries no ESDF code: the fused kernel's instruction footprint is what limits it.
   const int scene = (cfg->scene_weight > 0.0f ? ((a.cuboids.inv_pose ? 1 : 0) | (a.voxels.inv_pose ? 2 : 0)) : 0);
   using KernelT = void (*)(const FusedArgs);
-  static KernelT const table[3][4] = {
-      {rollout_fused_kernel<0>, rollout_fused_kernel<1>, rollout_fused_kernel<2>, rollout_fused_kernel<3>},
-      {rollout_traj_kernel<0>, rollout_traj_kernel<1>, rollout_traj_kernel<2>, rollout_traj_kernel<3>},
-      {rollout_tile_kernel<0>, rollout_tile_kernel<1>, rollout_tile_kernel<2>, rollout_tile_kernel<3>}};
+  static KernelT const table[5][4] = {
+      {rollout_fused_kernel<0, false>, rollout_fused_kernel<1, false>, rollout_fused_kernel<2, false>, rollout_fused_kernel<3, false>},
+      {rollout_traj_kernel<0, false>, rollout_traj_kernel<1, false>, rollout_traj_kernel<2, false>, rollout_traj_kernel<3, false>},
+      {rollout_tile_kernel<0>, rollout_tile_kernel<1>, rollout_tile_kernel<2>, rollout_tile_kernel<3>},
+      // B-spline front end: rows are evaluated from the knots inside the kernel
+      {rollout_fused_kernel<0, true>, rollout_fused_kernel<1, true>, rollout_fused_kernel<2, true>, rollout_fused_kernel<3, true>},
+      {rollout_traj_kernel<0, true>, rollout_traj_kernel<1, true>, rollout_traj_kernel<2, true>, rollout_traj_kernel<3, true>}};
   // small robots (arms) in discrete mode: thread-per-row "lane" schedule
   static const int lane_env = []() {
     const char *e = getenv("CB200_LANE");
     return e ? atoi(e) : 0;  // off by default: measured 2.3x slower than warp-per-row (profiles/r01_c)
   }();
-  if (!traj && lane_env != 0 && h.nl <= 24 && h.S <= 128) {
+  if (!traj && lane_env != 0 && h.nl <= 24 && h.S <= 128 && sp == nullptr) {
     static KernelT const lane_table[4] = {rollout_lane_kernel<0>, rollout_lane_kernel<1>, rollout_lane_kernel<2>,
                                           rollout_lane_kernel<3>};
     const LaneLayout ll = lane_layout(h.smem_bytes, kLaneThreads, h.nl, h.D, h.n_cl);
@@ -2171,7 +2260,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     const char *e = getenv("CB200_TILE");
     return e ? atoi(e) : 0;
   }();
-  if (!traj && tile_env != 0) {
+  if (!traj && tile_env != 0 && sp == nullptr) {
     const TileLayout tl = tile_layout(h.smem_bytes, kWarpsPerCta, h.nl, h.D, h.S, h.L, h.n_cl);
     KernelT tk = table[2][scene];
     static thread_local size_t tile_cfg[4] = {0, 0, 0, 0};
@@ -2197,7 +2286,8 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       return launch_status();
     }
   }
-  KernelT kern = table[traj ? 1 : 0][scene];
+  const int variant = (traj ? 1 : 0) + (sp != nullptr ? 3 : 0);
+  KernelT kern = table[variant][scene];
   const int minb = scene;  // part of the plan-cache key
   // warps per CTA: the count that keeps the most warps resident per SM (shared memory is the limiter for
   // big robots); ties go to the larger CTA so the blob is staged fewer times.  Cached per (kernel, geometry).
@@ -2205,8 +2295,8 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     long long key = -1;
     int nw = 0, per_sm = 0;
   };
-  static thread_local Plan plans[2][4];
-  Plan &pl = plans[traj ? 1 : 0][scene];
+  static thread_local Plan plans[5][4];
+  Plan &pl = plans[variant][scene];
   const size_t halo_bytes = traj ? (size_t)2 * h.S * sizeof(float4) : 0;
   const long long key = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ (long long)minb ^
                         (traj ? ((long long)io->horizon << 40) : 0);
@@ -2249,7 +2339,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   if (grid_ll > need_ctas) grid_ll = need_ctas;
   const int grid = (int)(grid_ll < 1 ? 1 : grid_ll);
   kern<<<grid, nw * 32, smem, (cudaStream_t)stream>>>(a);
-  return launch_status();
+  return finish();
 }
 
 }  // extern "C"

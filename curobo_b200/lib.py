@@ -39,6 +39,14 @@ class RolloutCfg(C.Structure):
                 ("retime_regularization_weights", C.c_int32), ("num_goalset", C.c_int32)]
 
 
+class SplineInput(C.Structure):
+    _fields_ = [("knots", c_p), ("start_position", c_p), ("start_velocity", c_p), ("start_acceleration", c_p),
+                ("start_jerk", c_p), ("goal_position", c_p), ("goal_velocity", c_p), ("goal_acceleration", c_p),
+                ("goal_jerk", c_p), ("start_idx", c_p), ("goal_idx", c_p), ("traj_dt", c_p),
+                ("use_implicit_goal_state", c_p), ("n_knots", C.c_int32), ("degree", C.c_int32), ("grad_knots", c_p),
+                ("out_position", c_p), ("out_velocity", c_p), ("out_acceleration", c_p), ("out_jerk", c_p)]
+
+
 class RolloutIO(C.Structure):
     _fields_ = [("q", c_p), ("vel", c_p), ("acc", c_p), ("jerk", c_p), ("dt", c_p),
                 ("robot_blob", c_p), ("robot_blob_host", c_p), ("robot_blob_bytes", C.c_int32),
@@ -49,7 +57,7 @@ class RolloutIO(C.Structure):
                 ("cost", c_p), ("grad_q", c_p), ("self_cost", c_p), ("scene_cost", c_p), ("pose_cost", c_p),
                 ("cspace_cost", c_p), ("grad_vel", c_p), ("grad_acc", c_p), ("grad_jerk", c_p),
                 ("link_pos", c_p), ("link_quat", c_p), ("robot_spheres", c_p), ("pose_goalset_idx", c_p),
-                ("batch_size", C.c_int32), ("horizon", C.c_int32)]
+                ("batch_size", C.c_int32), ("horizon", C.c_int32), ("spline", C.POINTER(SplineInput))]
 
 
 _I = C.c_int
@@ -99,7 +107,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)       # AttributeError if the symbol is missing: fail loudly
         fn.argtypes = args
         fn.restype = res
-    if lib.cb200_abi_version() != 1:
+    if lib.cb200_abi_version() != 2:
         raise RuntimeError("libcurobo_b200.so ABI version mismatch")
     _LIB = lib
     return lib

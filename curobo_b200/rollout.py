@@ -81,6 +81,7 @@ class RolloutOutput:
     link_quat: Optional[torch.Tensor] = None
     robot_spheres: Optional[torch.Tensor] = None
     pose_goalset_idx: Optional[torch.Tensor] = None
+    grad_knots: Optional[torch.Tensor] = None   # [B,n_knots,D] (evaluate_knots only)
 
 
 def pack_robot_blob(rm: RobotModel) -> np.ndarray:
@@ -192,13 +193,71 @@ class RolloutEngine:
             self.setup_batch_tensors(B, H)
         dev = self.device
         check_tensors(dev, torch.float32, q=q)
-        o = self.out
         io = _lib.RolloutIO()
         io.q = q.data_ptr()
         for name, t in (("vel", vel), ("acc", acc), ("jerk", jerk), ("dt", dt)):
             if t is not None:
                 check_tensors(dev, torch.float32, **{name: t})
                 setattr(io, name, t.data_ptr())
+        return self._launch(io, B, H, env_query_idx)
+
+    def evaluate_knots(self, knots: torch.Tensor, start_state, start_state_idx: torch.Tensor, goal_state,
+                       goal_state_idx: torch.Tensor, use_implicit_goal_state: torch.Tensor, bspline_degree: int = 4,
+                       interpolation_steps: int = 4, env_query_idx: Optional[torch.Tensor] = None,
+                       store_state: bool = False) -> RolloutOutput:
+        """B-spline action space: knots [B,n_knots,D] -> row costs and d cost / d knots in ONE C
+        call.  The spline states are evaluated inside the rollout kernel (they never touch HBM unless
+        `store_state`), and the adjoint kernel runs right behind it on the same stream.  start_state / goal_state
+        carry position, velocity, acceleration, jerk [n, D]; goal_state.dt [n_goal] is the trajectory dt
+        (same contract as curobo_b200.trajectory.StateFromBSplineKnot.forward)."""
+        D = self.robot.num_dof
+        if knots.ndim != 3 or knots.shape[2] != D:
+            raise ValueError(f"knots must be [B, n_knots, {D}], got {tuple(knots.shape)}")
+        if bspline_degree not in (3, 4, 5):
+            raise RuntimeError(f"Unsupported B-spline degree: {bspline_degree}")
+        if self.cfg.cspace_type != "state":
+            raise ValueError("evaluate_knots needs the STATE c-space cost (velocity / acceleration / jerk gradients)")
+        if goal_state.dt is None:
+            raise ValueError("dt is None")
+        B, nk, _ = knots.shape
+        H = (nk + bspline_degree + 1) * interpolation_steps + 1
+        if not 1 <= interpolation_steps <= 32:
+            raise RuntimeError("interpolation_steps must be in [1, 32]")
+        dev = self.device
+        if (B, H) != (self._B, self._H):
+            self.setup_batch_tensors(B, H)
+        o = self.out
+        if o.grad_knots is None or tuple(o.grad_knots.shape) != (B, nk, D):
+            o.grad_knots = torch.zeros((B, nk, D), dtype=torch.float32, device=dev)
+        f32 = dict(knots=knots, traj_dt=goal_state.dt)
+        for pre, st in (("start", start_state), ("goal", goal_state)):
+            for fld in ("position", "velocity", "acceleration", "jerk"):
+                f32[f"{pre}_{fld}"] = getattr(st, fld)
+        check_tensors(dev, torch.float32, **f32)
+        check_tensors(dev, torch.int32, start_state_idx=start_state_idx, goal_state_idx=goal_state_idx)
+        check_tensors(dev, torch.uint8, use_implicit_goal_state=use_implicit_goal_state)
+        if goal_state_idx.shape[0] != B or start_state_idx.shape[0] != B:
+            raise ValueError("start_state_idx / goal_state_idx need one entry per batch row")
+        sp = _lib.SplineInput()
+        sp.knots = knots.data_ptr()
+        for pre, st in (("start", start_state), ("goal", goal_state)):
+            for fld in ("position", "velocity", "acceleration", "jerk"):
+                setattr(sp, f"{pre}_{fld}", getattr(st, fld).data_ptr())
+        sp.start_idx, sp.goal_idx = start_state_idx.data_ptr(), goal_state_idx.data_ptr()
+        sp.traj_dt, sp.use_implicit_goal_state = goal_state.dt.data_ptr(), use_implicit_goal_state.data_ptr()
+        sp.n_knots, sp.degree = nk, bspline_degree
+        sp.grad_knots = o.grad_knots.data_ptr()
+        if store_state:
+            if getattr(self, "_state", None) is None or tuple(self._state[0].shape) != (B, H, D):
+                self._state = tuple(torch.zeros((B, H, D), dtype=torch.float32, device=dev) for _ in range(4))
+            sp.out_position, sp.out_velocity, sp.out_acceleration, sp.out_jerk = (t.data_ptr() for t in self._state)
+        io = _lib.RolloutIO()
+        io.spline = C.pointer(sp)
+        return self._launch(io, B, H, env_query_idx)
+
+    def _launch(self, io, B: int, H: int, env_query_idx) -> RolloutOutput:
+        dev = self.device
+        o = self.out
         io.robot_blob, io.robot_blob_host = self._blob.data_ptr(), self._blob_host.ctypes.data
         io.robot_blob_bytes = int(self._blob_host.shape[0])
         if self._cs is not None:

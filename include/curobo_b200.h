@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st *cb200_stream_t; /* == cudaStream_t */
 
-#define CB200_ABI_VERSION 1
+#define CB200_ABI_VERSION 2
 
 /* Library / build identity.  cb200_abi_version() == CB200_ABI_VERSION; cb200_sm_arch() == 100. */
 int cb200_abi_version(void);
@@ -214,6 +214,23 @@ typedef struct {
   int32_t num_goalset;
 } cb200_rollout_cfg;
 
+/* Optional B-spline front end of the fused rollout: the rows of the rollout are the
+ * spline states of `knots`, evaluated inside the kernel (q, qd, qdd, qddd never touch HBM), and the adjoint runs
+ * right behind it on the same stream, so one C call maps  knots -> cost, grad_knots.
+ * Semantics of every field = cb200_bspline_forward / cb200_bspline_backward below; io->horizon is the padded
+ * horizon (n_knots + degree + 1) * interpolation_steps + 1 and io->q/vel/acc/jerk/dt are ignored. */
+typedef struct {
+  const float *knots;                                          /* [B, n_knots, D] */
+  const float *start_position, *start_velocity, *start_acceleration, *start_jerk; /* [n_start, D] */
+  const float *goal_position, *goal_velocity, *goal_acceleration, *goal_jerk;     /* [n_goal, D] */
+  const int32_t *start_idx, *goal_idx;                         /* [B] */
+  const float *traj_dt;                                        /* [n_goal] */
+  const uint8_t *use_implicit_goal_state;                      /* [n_goal] */
+  int32_t n_knots, degree;
+  float *grad_knots;                                           /* out [B, n_knots, D]; needs io->grad_vel/acc/jerk */
+  float *out_position, *out_velocity, *out_acceleration, *out_jerk; /* optional state dump [B,H,D] */
+} cb200_spline_input;
+
 typedef struct {
   /* inputs */
   const float *q;                 /* [B,H,D] */
@@ -242,6 +259,7 @@ typedef struct {
   float *robot_spheres;                   /* optional [B,H,S,4] */
   int32_t *pose_goalset_idx;              /* optional [B,H,L] */
   int32_t batch_size, horizon;
+  const cb200_spline_input *spline;       /* optional B-spline front end (host pointer); NULL = rows come from q */
 } cb200_rollout_io;
 
 int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io,

@@ -190,3 +190,142 @@ def test_full_size_adjoint_property_and_graph_capture():
     torch.cuda.synchronize()
     assert torch.equal(outs[0], base[0]) and torch.equal(outs[3], base[3])
     assert torch.equal(gout, gk)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused front end: RolloutEngine.evaluate_knots (knots -> cost, grad_knots in one C call)
+# ------------------------------------------------------------------------------------------------
+def _smooth_knots(rm, B, nk, seed):
+    """knots around a joint-space random walk, inside the joint limits"""
+    from helpers import random_walk_q
+    return random_walk_q(rm, B, nk, seed=seed).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["trajopt_swept", "discrete"])
+@pytest.mark.parametrize("degree,steps,implicit", [(4, 4, False), (3, 2, True), (5, 1, False)])
+def test_fused_knots_rollout_vs_oracle_chain(mode, degree, steps, implicit):
+    """evaluate_knots == oracle chain  bspline_forward -> rollout_cost_grad -> bspline_backward  and
+    == our own unfused chain (spline kernel -> evaluate_action -> adjoint kernel) bit for bit."""
+    from helpers import random_q, small_voxel_world
+    from curobo_b200.robot_model import load_robot
+    from curobo_b200.rollout import RolloutConfig, RolloutEngine
+    from curobo_b200.scene import CuboidData, VoxelData
+    from curobo_b200.world import make_benchmark_cuboid_world
+    from oracle import rollout_oracle as O
+
+    rm = load_robot("franka")
+    B, nk, D = 4, 8, rm.num_dof
+    Tn = bo.padded_horizon_for(nk, degree, steps)
+    rng = np.random.default_rng(7)
+    knots = _smooth_knots(rm, B, nk, seed=80 + degree)
+    q0 = knots[:, 0] + rng.normal(0, 0.02, size=(B, D)).astype(np.float32)
+    z = np.zeros((B, D), np.float32)
+    start = (q0, rng.normal(0, 0.1, (B, D)).astype(np.float32), z, z)
+    goal = (knots[:, -1].copy(), z, z, z)
+    sidx = np.arange(B, dtype=np.int32)
+    gidx = np.arange(B, dtype=np.int32)
+    traj_dt = np.full(B, 0.05, np.float32)
+    imp = np.full(B, int(implicit), np.uint8)
+
+    cfg = RolloutConfig.trajopt()
+    if mode == "discrete":
+        cfg.use_sweep = False
+        cfg.use_speed_metric = False
+    cub, vox = make_benchmark_cuboid_world(), small_voxel_world()
+    gq_ = random_q(rm, B, seed=61)
+    _, _, gp, gqt = O.fk_forward(rm, gq_)
+    gp, gqt = gp[:, :, None, :].copy(), gqt[:, :, None, :].copy()
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    nt = torch.zeros((1, 6), dtype=torch.float32, device=DEV)
+    eng.update_goal(T(gp), T(gqt), T(sidx), non_terminal_axes=nt)
+    start_t = JointState(*[T(x) for x in start])
+    goal_t = JointState(*[T(x) for x in goal], dt=T(traj_dt))
+    out = eng.evaluate_knots(T(knots), start_t, T(sidx), goal_t, T(gidx), T(imp), bspline_degree=degree,
+                             interpolation_steps=steps, store_state=True)
+    torch.cuda.synchronize()
+    cost, gk = out.cost.clone(), out.grad_knots.clone()
+    state = [t.clone() for t in eng._state]
+
+    # oracle chain
+    p, v, a, j, odt = bo.bspline_forward(knots, start, goal, sidx, gidx, traj_dt, imp, Tn, degree)
+    for g, w in zip(state, (p, v, a, j)):
+        assert np.allclose(g.cpu().numpy(), w, rtol=2e-5, atol=2e-5 * max(1.0, np.abs(w).max()))
+    ocfg = cfg.to_oracle_cfg(1)
+    ocfg["pose_non_terminal_axes"] = np.zeros((1, 6), np.float32)
+    want = O.rollout_cost_grad(rm, p, ocfg, world_cuboid=cub, world_voxel=vox, goal_pos=gp, goal_quat=gqt, idxs_goal=sidx,
+                               vel=v, acc=a, jerk=j, dt=odt)
+    np.testing.assert_allclose(cost.cpu().numpy(), want["cost_bh"], rtol=5e-4, atol=2e-5 * want["cost_bh"].max())
+    gs = want["cspace_grads"]
+    want_gk = bo.bspline_backward(want["grad_q"], gs[1], gs[2], gs[3], traj_dt, gidx, imp, nk, degree)
+    np.testing.assert_allclose(gk.cpu().numpy(), want_gk, rtol=5e-3, atol=5e-5 * np.abs(want_gk).max())
+
+    # our own unfused chain, same kernels: must agree exactly
+    fn = StateFromBSplineKnot(DEV, D, batch_size=B, n_knots=nk, interpolation_steps=steps, use_implicit_goal_state=implicit,
+                              control_space={3: ControlSpace.BSPLINE_3, 4: ControlSpace.BSPLINE_4, 5: ControlSpace.BSPLINE_5}[degree])
+    seq = fn.forward(start_t, T(knots), JointState.zeros((B, Tn, D), DEV), start_state_idx=T(sidx), goal_state=goal_t,
+                     goal_state_idx=T(gidx), use_implicit_goal_state=T(imp))
+    for g, w in zip(state, (seq.position, seq.velocity, seq.acceleration, seq.jerk)):
+        assert torch.equal(g, w)
+    eng2 = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    eng2.update_goal(T(gp), T(gqt), T(sidx), non_terminal_axes=nt)
+    o2 = eng2.evaluate_action(seq.position, vel=seq.velocity, acc=seq.acceleration, jerk=seq.jerk, dt=T(traj_dt))
+    assert torch.equal(o2.cost, cost)
+    gk2 = torch.zeros_like(gk)
+    trajectory_cu.launch_bspline_interpolation_backward_kernel(gk2, o2.grad_q, o2.grad_vel, o2.grad_acc, o2.grad_jerk,
+                                                               T(traj_dt), T(gidx), T(imp), B, Tn, D, nk, degree)
+    assert torch.equal(gk2, gk)
+
+
+def test_fused_knots_full_size_mpc_and_graph():
+    """MPC scale: 1024 seeds x 16 knots (degree 4, 1 step -> 22 rows) on the 256^3 ESDF, swept + speed metric.
+    Fused == unfused chain bit for bit, and the two-launch call is CUDA-graph capturable."""
+    from curobo_b200.robot_model import load_robot
+    from curobo_b200.rollout import RolloutConfig, RolloutEngine
+    from curobo_b200.scene import VoxelData
+    from curobo_b200.world import make_box_esdf
+
+    rm = load_robot("franka")
+    B, nk, D, degree, steps = 1024, 16, rm.num_dof, 4, 1
+    Tn = bo.padded_horizon_for(nk, degree, steps)
+    sdf = make_box_esdf(n=256, voxel_size=0.01, num_boxes=12, seed=0, xp=torch)
+    vox = VoxelData(T(np.array([[[256, 256, 256, 0.01]]], np.float32)), T(np.array([[[0, 0, 0, 1, 0, 0, 0, 0]]], np.float32)),
+                    torch.ones((1, 1), dtype=torch.uint8, device=DEV), torch.ones(1, dtype=torch.int32, device=DEV),
+                    sdf.reshape(1, 1, -1).contiguous(), 1, 1, 100.0)
+    knots = T(_smooth_knots(rm, B, nk, seed=90))
+    z = torch.zeros((1, D), device=DEV)
+    start = JointState(knots[:1, 0].contiguous(), z, z, z)
+    goal = JointState(knots[:1, -1].contiguous(), z, z, z, dt=torch.full((1,), 0.05, device=DEV))
+    zi = torch.zeros(B, dtype=torch.int32, device=DEV)
+    imp = torch.zeros(1, dtype=torch.uint8, device=DEV)
+    cfg = RolloutConfig.trajopt()
+    eng = RolloutEngine(rm, cfg, DEV, voxel=vox)
+    out = eng.evaluate_knots(knots, start, zi, goal, zi, imp, degree, steps)
+    torch.cuda.synchronize()
+    cost, gk = out.cost.clone(), out.grad_knots.clone()
+    assert torch.isfinite(cost).all() and torch.isfinite(gk).all() and float(gk.abs().max()) > 0
+
+    fn = StateFromBSplineKnot(DEV, D, batch_size=B, n_knots=nk, interpolation_steps=steps, control_space=ControlSpace.BSPLINE_4)
+    seq = fn.forward(start, knots, JointState.zeros((B, Tn, D), DEV), start_state_idx=zi, goal_state=goal, goal_state_idx=zi,
+                     use_implicit_goal_state=imp)
+    eng2 = RolloutEngine(rm, cfg, DEV, voxel=vox)
+    o2 = eng2.evaluate_action(seq.position, vel=seq.velocity, acc=seq.acceleration, jerk=seq.jerk,
+                              dt=torch.full((B,), 0.05, device=DEV))
+    assert torch.equal(o2.cost, cost)
+    gk2 = torch.zeros_like(gk)
+    trajectory_cu.launch_bspline_interpolation_backward_kernel(gk2, o2.grad_q, o2.grad_vel, o2.grad_acc, o2.grad_jerk, goal.dt,
+                                                               zi, imp, B, Tn, D, nk, degree)
+    assert torch.equal(gk2, gk)
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eng.evaluate_knots(knots, start, zi, goal, zi, imp, degree, steps)   # warm the plan cache outside capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            eng.evaluate_knots(knots, start, zi, goal, zi, imp, degree, steps)
+        eng.out.cost.zero_()
+        eng.out.grad_knots.zero_()
+        graph.replay()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    assert torch.equal(eng.out.cost, cost) and torch.equal(eng.out.grad_knots, gk)
