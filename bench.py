@@ -83,6 +83,24 @@ def make_workload(name: str, seed_offset: int = 0):
         return dict(robot=rm, cfg=RolloutConfig.trajopt(), B=B, H=H, q=q, goal=goal, cuboid=None,
                     voxel=dict(n=256, voxel=0.01, boxes=12, seed=0), bytes_per_eval=bpe,
                     extra=dict(vel=vel, acc=acc, jerk=jerk, dt=np.full(B, 0.05, np.float32)))
+    if name == "franka_mpc_knots_1024x30_esdf_swept":
+        # config 4 driven the way the reference's MPC/trajopt drives it: the action is 24 B-spline knots per seed
+        # (degree 4, 1 interpolation step -> 30 rows); one C call = knots -> row costs + d cost / d knots
+        # (spline evaluated inside the rollout kernel, adjoint kernel right behind it)
+        from helpers import random_walk_q
+        rm = load_robot("franka")
+        B, nk, degree, steps = 1024, 24, 4, 1
+        H = (nk + degree + 1) * steps + 1
+        knots = random_walk_q(rm, B, nk, seed=300 + seed_offset)
+        _, _, gp, gq = O.fk_forward(rm, random_q(rm, B, seed=9))
+        goal = (gp[:, :, None, :].copy(), gq[:, :, None, :].copy(), np.arange(B, dtype=np.int32))
+        D, S, L = rm.num_dof, rm.num_spheres, rm.num_tool_frames
+        bpe = 4 * D * nk / H * 2 + 4 * (S + 1 + 2 * L + D) + 16 * S * 7 + 4 * 4 * D * 2   # knots in / grad out, 4 row grads w+r
+        z = np.zeros((B, D), np.float32)
+        return dict(robot=rm, cfg=RolloutConfig.trajopt(), B=B, H=H, q=None, goal=goal, cuboid=None,
+                    voxel=dict(n=256, voxel=0.01, boxes=12, seed=0), bytes_per_eval=bpe,
+                    knots=dict(knots=knots, start=(knots[:, 0].copy(), z, z, z), goal=(knots[:, -1].copy(), z, z, z),
+                               dt=np.full(B, 0.05, np.float32), degree=degree, steps=steps))
     raise ValueError(f"unknown workload {name}")
 
 
@@ -276,7 +294,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="franka_ik_512x32_cuboid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
+    ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,franka_mpc_knots_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
                     help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -298,12 +316,24 @@ def main():
     def timed_run(wl_name, steps, warmup, sample_clocks):
         wl = make_workload(wl_name, seed_offset=rank)
         eng = build_engine(wl, device)
-        q = torch.as_tensor(wl["q"]).to(device)
         kw = {k: torch.as_tensor(v).to(device) for k, v in wl.get("extra", {}).items()}
+        if "knots" in wl:
+            from curobo_b200.trajectory import JointState
+            kn = wl["knots"]
+            td = lambda a: torch.as_tensor(a).to(device)  # noqa: E731
+            q = td(kn["knots"])
+            ks = JointState(*[td(x) for x in kn["start"]])
+            kg = JointState(*[td(x) for x in kn["goal"]], dt=td(kn["dt"]))
+            kidx = torch.arange(wl["B"], dtype=torch.int32, device=device)
+            kimp = torch.zeros(wl["B"], dtype=torch.uint8, device=device)
+            run = lambda: eng.evaluate_knots(q, ks, kidx, kg, kidx, kimp, kn["degree"], kn["steps"])  # noqa: E731
+        else:
+            q = torch.as_tensor(wl["q"]).to(device)
+            run = lambda: eng.evaluate_action(q, **kw)  # noqa: E731
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)       # 2x the 126 MB L2
         stream = torch.cuda.current_stream(device)
         for _ in range(warmup):
-            eng.evaluate_action(q, **kw)
+            run()
         torch.cuda.synchronize(device)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -316,7 +346,7 @@ def main():
         for i in range(steps):
             flush.fill_(i & 0xFF)                           # evict L2 between timed steps (outside the event pair)
             starts[i].record(stream)
-            eng.evaluate_action(q, **kw)
+            run()
             ends[i].record(stream)
         torch.cuda.synchronize(device)
         if world > 1:
@@ -326,6 +356,8 @@ def main():
         wl["kw"] = kw
         return wl, eng, q, float(sum(ms)), ms, clocks
 
+    if "knots" in args.workload:
+        raise SystemExit("the B-spline knots workload is measured under other_workloads (--extra-workloads) only")
     wl, eng, q, total_ms, ms_list, clocks = timed_run(args.workload, args.steps, args.warmup, rank == 0)
     evals_per_step = wl["B"] * wl["H"]
     t = torch.tensor([total_ms], dtype=torch.float64, device=device)
