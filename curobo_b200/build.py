@@ -61,8 +61,8 @@ def build_product(force: bool = False, verbose: bool = False, minb: int = 0) -> 
     cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared",
            "-Xptxas", "-v" if verbose else "-O3", *([f"-DCB200_MINB={minb}"] if minb > 0 else []),
            "-o", out, "-lcudart"]
-    # two translation units (rollout kernels; trajectory kernels), compiled concurrently then linked
-    units = ["cb200_kernels.cu", "cb200_trajectory.cu"]
+    # three translation units (rollout, trajectory and optimizer kernels), compiled concurrently then linked
+    units = ["cb200_kernels.cu", "cb200_trajectory.cu", "cb200_optim.cu"]
     objs = [os.path.join(LIBDIR, (u[:-3] + (f"_mb{minb}" if minb > 0 else "") + ".o")) for u in units]
     flags = [c for c in cmd[1:] if c not in ("-shared", "-o", out, "-lcudart")]
     procs = [subprocess.Popen([cmd[0], *flags, "-c", os.path.join(CSRC, u), "-o", o], stdout=subprocess.PIPE,
@@ -104,6 +104,7 @@ def build_reference_kernels(force: bool = False, verbose: bool = False):
            "-I", kdir, "-I", os.path.join(kdir, "common"), "-I", os.path.join(kdir, "third_party"),
            "-I", os.path.join(kdir, "kinematics"), "-I", os.path.join(kdir, "geometry", "self_collision"),
            "-I", os.path.join(kdir, "trajectory"), "-I", os.path.join(kdir, "trajectory", "bspline"),
+           "-I", os.path.join(kdir, "optimization", "lbfgs"), "-I", os.path.join(kdir, "optimization", "line_search"),
            src, "-o", REF_SO, "-lcudart"]
     _run(cmd, verbose)
     return REF_SO

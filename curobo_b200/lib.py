@@ -77,6 +77,8 @@ _SIGS = {
     "cb200_bspline_forward": ([c_p] * 18 + [_I] * 5 + [c_p], _I),
     "cb200_bspline_single_dt": ([c_p] * 20 + [_I] * 5 + [c_p], _I),
     "cb200_bspline_backward": ([c_p] * 8 + [_I] * 5 + [c_p], _I),
+    "cb200_lbfgs_step": ([c_p] * 8 + [C.c_float] + [_I] * 4 + [c_p] * 3 + [_I, c_p, _I, _I, c_p], _I),
+    "cb200_line_search": ([c_p] * 5 + [_I, C.c_float, C.c_float] + [c_p] * 13 + [C.c_float, C.c_float] + [_I] * 5 + [c_p], _I),
     "cb200_robot_blob_bytes": ([C.POINTER(RobotSizes)], C.c_int64),
     "cb200_pack_robot_blob": ([c_p, C.c_int64, C.POINTER(RobotSizes)] + [c_p] * 15, C.c_int64),
     "cb200_rollout_cost_grad": ([C.POINTER(RolloutCfg), C.POINTER(RolloutIO), c_p], _I),

@@ -304,6 +304,41 @@ int cb200_bspline_backward(
     const int32_t *dt_idx, const uint8_t *use_implicit_goal_state, int batch_size, int padded_horizon,
     int dof, int n_knots, int bspline_degree, cb200_stream_t stream);
 
+/* -------------------------------------------------------------------------------------------
+ * (8f-2) Optimizer-side kernels of the solve loop: the L-BFGS step and the parallel Wolfe line search
+ * that sit either side of the rollout in every optimizer iteration.
+ *   cb200_lbfgs_step   <- launch_lbfgs_step
+ *       curobo/_src/curobolib/backends/cuda_core_backend/optimization.py:136-246
+ *       (kernels/optimization/lbfgs/lbfgs_step_kernel.cuh:39-199)
+ *   cb200_line_search  <- launch_line_search  cuda_core_backend/optimization.py:26-133
+ *       (kernels/optimization/line_search/line_search_kernel.cuh:60-199)
+ * Buffers and meaning as in the reference: rho [m,B], y/s [m,B,V] (rolled in place, newest pair in slot m-1),
+ * q / grad_q / x_0 / grad_0 / step_vec [B,V]; search_* [B,n,(V)], idx outputs [B,n], iterations int16, converged u8.
+ * 1 <= history_m <= 31, v_dim <= 1024, n_linesearch <= 32 (cudaErrorInvalidValue otherwise, where the reference raises).
+ * Extension (all optional, pass NULL/0 to get the reference kernel's behaviour exactly): the step kernel also
+ * prepares the line search the way LineSearchStrategy._prepare_search_points does
+ * (optim/gradient/line_search_strategy.py:136-240): step_scaled = scale_action(step) with per-dimension
+ * action_step_max [action_dim] (and the terminal action frozen when fix_terminal_action), and
+ * x_set[b,j,:] = q[b,:] + search_magnitudes[j] * step_scaled[b,:].
+ * ------------------------------------------------------------------------------------------- */
+int cb200_lbfgs_step(
+    float *step_vec, float *rho_buffer, float *y_buffer, float *s_buffer, const float *q,
+    const float *grad_q, float *x_0, float *grad_0, float epsilon, int batch_size, int history_m,
+    int v_dim, int stable_mode, float *x_set, float *step_scaled, const float *search_magnitudes,
+    int n_linesearch, const float *action_step_max, int action_dim, int fix_terminal_action,
+    cb200_stream_t stream);
+
+int cb200_line_search(
+    float *best_cost, float *best_action, int16_t *best_iteration, int16_t *current_iteration,
+    uint8_t *converged_global, int convergence_iteration, float cost_delta_threshold,
+    float cost_relative_threshold, float *exploration_cost, float *exploration_action,
+    float *exploration_gradient, int32_t *exploration_idx, float *selected_cost,
+    float *selected_action, float *selected_gradient, int32_t *selected_idx, const float *search_cost,
+    const float *search_action, const float *search_gradient, const float *step_direction,
+    const float *search_magnitudes, float armijo_threshold_c_1, float curvature_threshold_c_2,
+    int strong_wolfe, int approx_wolfe, int n_linesearch, int opt_dim, int batchsize,
+    cb200_stream_t stream);
+
 /* Host helper: pack robot constants (HOST pointers) into `out` (host buffer of
  * cb200_robot_blob_bytes(...) bytes) that the caller then copies to the device once.
  * Returns bytes written or a negative number on invalid input. */

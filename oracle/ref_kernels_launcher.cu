@@ -217,3 +217,68 @@ int ref_bspline_backward(float *out, const float *gp, const float *gv, const flo
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer kernels.  Launch math follows
+// backends/cuda_core_backend/optimization_config.py:54-70 (line search: one CTA of opt_dim threads per problem) and
+// :76-127 (L-BFGS: one CTA of v_dim threads per problem; shared-memory variant when it fits 64 KB).
+// ------------------------------------------------------------------------------------------------
+#include "optimization/lbfgs/lbfgs_step_kernel.cuh"
+#include "optimization/line_search/line_search_kernel.cuh"
+
+namespace cop = curobo::optimization;
+
+template <int M>
+static int ref_lbfgs_t(float *step_vec, float *rho, float *y, float *s, float *q, float *x_0, float *grad_0,
+                       const float *grad_q, float epsilon, int B, int V, int stable, int use_shared, cudaStream_t stream) {
+  const size_t basic = (size_t)M * 4, shared = (size_t)(((2 * V) + 2) * M + 32 + 1) * 4;
+  if (use_shared && shared <= 65536) {
+    if (shared > 48000) cudaFuncSetAttribute(cop::kernel_lbfgs_step_shared_memory<float, false, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared);
+    cop::kernel_lbfgs_step_shared_memory<float, false, M><<<B, V, shared, stream>>>(step_vec, rho, y, s, q, x_0, grad_0, grad_q,
+                                                                                  epsilon, B, M, V, stable != 0);
+  } else {
+    cop::kernel_lbfgs_step<float, false, M><<<B, V, basic, stream>>>(step_vec, rho, y, s, q, x_0, grad_0, grad_q, epsilon, B,
+                                                                     M, V, stable != 0);
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" {
+
+int ref_lbfgs_step(float *step_vec, float *rho, float *y, float *s, float *q, float *x_0, float *grad_0,
+                   const float *grad_q, float epsilon, int B, int m, int V, int stable, int use_shared,
+                   cudaStream_t stream) {
+  switch (m) {  // the reference JIT-compiles FIXED_M = history (optimization.py:178-183); the histories the tests use
+    case 3: return ref_lbfgs_t<3>(step_vec, rho, y, s, q, x_0, grad_0, grad_q, epsilon, B, V, stable, use_shared, stream);
+    case 5: return ref_lbfgs_t<5>(step_vec, rho, y, s, q, x_0, grad_0, grad_q, epsilon, B, V, stable, use_shared, stream);
+    case 7: return ref_lbfgs_t<7>(step_vec, rho, y, s, q, x_0, grad_0, grad_q, epsilon, B, V, stable, use_shared, stream);
+    case 15: return ref_lbfgs_t<15>(step_vec, rho, y, s, q, x_0, grad_0, grad_q, epsilon, B, V, stable, use_shared, stream);
+    case 27: return ref_lbfgs_t<27>(step_vec, rho, y, s, q, x_0, grad_0, grad_q, epsilon, B, V, stable, use_shared, stream);
+    case 31: return ref_lbfgs_t<31>(step_vec, rho, y, s, q, x_0, grad_0, grad_q, epsilon, B, V, stable, use_shared, stream);
+    default: return -1;
+  }
+}
+
+int ref_line_search(float *best_cost, float *best_action, int16_t *best_iteration, int16_t *current_iteration,
+                    uint8_t *converged, int convergence_iteration, float cost_delta_threshold,
+                    float cost_relative_threshold, float *exploration_cost, float *exploration_action,
+                    float *exploration_gradient, int32_t *exploration_idx, float *selected_cost, float *selected_action,
+                    float *selected_gradient, int32_t *selected_idx, const float *search_cost, const float *search_action,
+                    const float *search_gradient, const float *step_direction, const float *search_magnitudes, float c_1,
+                    float c_2, int strong_wolfe, int approx_wolfe, int n, int V, int B, cudaStream_t stream) {
+  if (n == 4)
+    cop::line_search::kernel_line_search<float, 4><<<B, V, 0, stream>>>(
+        best_cost, best_action, best_iteration, current_iteration, converged, convergence_iteration, cost_delta_threshold,
+        cost_relative_threshold, exploration_cost, exploration_action, exploration_gradient, exploration_idx, selected_cost,
+        selected_action, selected_gradient, selected_idx, search_cost, search_action, search_gradient, step_direction,
+        search_magnitudes, c_1, c_2, strong_wolfe != 0, approx_wolfe != 0, n, V, B);
+  else
+    cop::line_search::kernel_line_search<float, -1><<<B, V, 0, stream>>>(
+        best_cost, best_action, best_iteration, current_iteration, converged, convergence_iteration, cost_delta_threshold,
+        cost_relative_threshold, exploration_cost, exploration_action, exploration_gradient, exploration_idx, selected_cost,
+        selected_action, selected_gradient, selected_idx, search_cost, search_action, search_gradient, step_direction,
+        search_magnitudes, c_1, c_2, strong_wolfe != 0, approx_wolfe != 0, n, V, B);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

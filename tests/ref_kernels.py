@@ -119,3 +119,30 @@ def bspline_backward(grads, traj_dt, dt_idx, implicit, n_knots, degree):
                                      n_knots, degree, _stream(dev))
     assert err == 0, err
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer kernels of the reference (kernels/optimization/...): in-place on the passed tensors
+# ------------------------------------------------------------------------------------------------
+def lbfgs_step(step_vec, rho, y, s, q, x_0, grad_0, grad_q, epsilon, stable=True, use_shared=True):
+    m, B, V = y.shape[0], y.shape[1], y.shape[2]
+    err = lib().ref_lbfgs_step(_p(step_vec), _p(rho), _p(y), _p(s), _p(q), _p(x_0), _p(grad_0), _p(grad_q),
+                               C.c_float(epsilon), B, m, V, int(stable), int(use_shared), _stream(y.device))
+    assert err == 0, err
+    return step_vec
+
+
+def line_search(st, search_cost, search_action, search_gradient, step_direction, magnitudes, c_1, c_2, strong, approx,
+                convergence_iteration=10, cost_delta_threshold=0.0, cost_relative_threshold=0.0):
+    """st: dict of state tensors (best_cost, best_action, best_iteration, current_iteration, converged, exploration_*,
+    selected_*, *_idx) updated in place."""
+    B, n, V = search_action.shape
+    err = lib().ref_line_search(
+        _p(st["best_cost"]), _p(st["best_action"]), _p(st["best_iteration"]), _p(st["current_iteration"]), _p(st["converged"]),
+        convergence_iteration, C.c_float(cost_delta_threshold), C.c_float(cost_relative_threshold),
+        _p(st["exploration_cost"]), _p(st["exploration_action"]), _p(st["exploration_gradient"]), _p(st["exploration_idx"]),
+        _p(st["selected_cost"]), _p(st["selected_action"]), _p(st["selected_gradient"]), _p(st["selected_idx"]),
+        _p(search_cost), _p(search_action), _p(search_gradient), _p(step_direction), _p(magnitudes), C.c_float(c_1),
+        C.c_float(c_2), int(strong), int(approx), n, V, B, _stream(search_cost.device))
+    assert err == 0, err
+    return st
