@@ -125,6 +125,53 @@ def build_engine(wl, device):
     return eng
 
 
+def ik_solve_bench(device, problems=512, seeds=32, iters=100, repeats=5):
+    """A complete batched IK solve through the public pieces: LBFGSOpt (lbfgs_ik.yml settings:
+    history 7, line-search scales [0, .1, .5, 1], approx Wolfe, 100 iterations) driving RolloutEngine.evaluate_action
+    on problems x seeds x 4 rows of the config-2 cuboid world -- 3 kernel launches per iteration.  Goals are poses of
+    random collision-unchecked configurations; success = best seed within 5 mm and 0.05 rad of the goal."""
+    import torch
+    from curobo_b200.kinematics import Kinematics
+    from curobo_b200.optim import LBFGSOpt, LBFGSOptCfg
+    from helpers import random_q
+    from oracle import rollout_oracle as O
+    wl = make_workload("franka_ik_512x32_cuboid")
+    rm, n = wl["robot"], 4
+    B, D = problems * seeds, rm.num_dof
+    q_goal = random_q(rm, problems, seed=11) * 0.8
+    _, _, gp, gq = O.fk_forward(rm, q_goal)
+    wl = dict(wl, goal=(gp[:, :, None, :].copy(), gq[:, :, None, :].copy(),
+                        np.repeat(np.arange(B) // seeds, n).astype(np.int32)))
+    eng = build_engine(wl, device)
+
+    def cost_grad(x):
+        out = eng.evaluate_action(x.view(B * n, 1, D))
+        return out.cost.view(-1), out.grad_q.view(B * n, D)
+
+    td = lambda a: torch.as_tensor(a).to(device)  # noqa: E731
+    opt = LBFGSOpt(LBFGSOptCfg(num_iters=iters), B, 1, D, td(rm.position_limits[0]), td(rm.position_limits[1]), cost_grad, device)
+    x0 = td(random_q(rm, B, seed=12))
+    opt.optimize(x0)                                                    # warm-up (allocations, plan caches)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        q_sol = opt.optimize(x0)
+    torch.cuda.synchronize(device)
+    dt = (time.perf_counter() - t0) / repeats
+    q_sol = q_sol.view(B, D)
+    st = Kinematics(rm, device).compute_kinematics(q_sol.view(B, 1, D))
+    pos = st.tool_pose_position.reshape(B, -1, 3)[:, 0].detach().cpu().numpy().reshape(problems, seeds, 3)
+    quat = st.tool_pose_quaternion.reshape(B, -1, 4)[:, 0].detach().cpu().numpy().reshape(problems, seeds, 4)
+    perr = np.linalg.norm(pos - gp[:, 0][:, None, :], axis=-1)
+    dotq = np.abs(np.sum(quat * gq[:, 0][:, None, :], axis=-1)).clip(0, 1)
+    rerr = 2.0 * np.arccos(dotq)
+    ok = ((perr < 5e-3) & (rerr < 0.05)).any(axis=1)
+    return {"problems": problems, "seeds": seeds, "iterations": iters, "line_search_candidates": n,
+            "launches_per_iteration": 3, "solve_ms": dt * 1e3, "ik_solves_per_s": problems / dt,
+            "rollout_evals_per_s": B * n * (iters + 1) / dt, "success_rate": float(ok.mean()),
+            "median_position_error_mm": float(np.median(perr.min(axis=1)) * 1e3), "timer": "wall clock incl. Python loop"}
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
@@ -294,6 +341,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="franka_ik_512x32_cuboid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ik-solve", type=int, default=1,
+                    help="1: also time a complete 100-iteration L-BFGS IK solve (512 goals x 32 seeds), reported under 'ik_solve'")
     ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,franka_mpc_knots_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
                     help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
     args = ap.parse_args()
@@ -456,6 +505,11 @@ def main():
                 except Exception as ex:                                           # noqa: BLE001
                     others[name] = {"error": repr(ex)}
             line["other_workloads"] = others
+            if args.ik_solve:
+                try:
+                    line["ik_solve"] = ik_solve_bench(device)
+                except Exception as ex:                                               # noqa: BLE001
+                    line["ik_solve"] = {"error": repr(ex)}
             if not args.no_cpu_baseline:
                 v, cores, sample = cpu_baseline(args.workload, target_seconds=12.0, procs=1)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
