@@ -83,7 +83,7 @@ def make_workload(name: str, seed_offset: int = 0):
         return dict(robot=rm, cfg=RolloutConfig.trajopt(), B=B, H=H, q=q, goal=goal, cuboid=None,
                     voxel=dict(n=256, voxel=0.01, boxes=12, seed=0), bytes_per_eval=bpe,
                     extra=dict(vel=vel, acc=acc, jerk=jerk, dt=np.full(B, 0.05, np.float32)))
-    if name == "franka_mpc_knots_1024x30_esdf_swept":
+    if name in ("franka_mpc_knots_1024x30_esdf_swept", "franka_mpc_knots_inkernel_1024x30_esdf_swept"):
         # config 4 driven the way the reference's MPC/trajopt drives it: the action is 24 B-spline knots per seed
         # (degree 4, 1 interpolation step -> 30 rows); one C call = knots -> row costs + d cost / d knots
         # (spline evaluated inside the rollout kernel, adjoint kernel right behind it)
@@ -100,7 +100,7 @@ def make_workload(name: str, seed_offset: int = 0):
         return dict(robot=rm, cfg=RolloutConfig.trajopt(), B=B, H=H, q=None, goal=goal, cuboid=None,
                     voxel=dict(n=256, voxel=0.01, boxes=12, seed=0), bytes_per_eval=bpe,
                     knots=dict(knots=knots, start=(knots[:, 0].copy(), z, z, z), goal=(knots[:, -1].copy(), z, z, z),
-                               dt=np.full(B, 0.05, np.float32), degree=degree, steps=steps))
+                               dt=np.full(B, 0.05, np.float32), degree=degree, steps=steps, in_kernel="inkernel" in name))
     raise ValueError(f"unknown workload {name}")
 
 
@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ik-solve", type=int, default=1,
                     help="1: also time a complete 100-iteration L-BFGS IK solve (512 goals x 32 seeds), reported under 'ik_solve'")
-    ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,franka_mpc_knots_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
+    ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,franka_mpc_knots_1024x30_esdf_swept,franka_mpc_knots_inkernel_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
                     help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -375,7 +375,8 @@ def main():
             kg = JointState(*[td(x) for x in kn["goal"]], dt=td(kn["dt"]))
             kidx = torch.arange(wl["B"], dtype=torch.int32, device=device)
             kimp = torch.zeros(wl["B"], dtype=torch.uint8, device=device)
-            run = lambda: eng.evaluate_knots(q, ks, kidx, kg, kidx, kimp, kn["degree"], kn["steps"])  # noqa: E731
+            run = lambda: eng.evaluate_knots(q, ks, kidx, kg, kidx, kimp, kn["degree"], kn["steps"],  # noqa: E731
+                                             in_kernel_spline=kn["in_kernel"])
         else:
             q = torch.as_tensor(wl["q"]).to(device)
             run = lambda: eng.evaluate_action(q, **kw)  # noqa: E731

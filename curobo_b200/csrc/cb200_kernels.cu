@@ -403,8 +403,8 @@ static __device__ __noinline__ void phase_b2_ool(const FusedArgs *a, const unsig
 }
 #endif  // CB200_OOL_PHASES
 
-template <int SCENE, bool SPLINE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
+template <int SCENE, bool SPLINE, int MINB = CB200_MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
@@ -2198,7 +2198,23 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     return e ? atoi(e) : 0;
   }();
   a.phase_sync = phase_sync_env;
-  if (sp != nullptr) {
+  const bool expand = sp != nullptr && sp->out_position != nullptr && sp->out_velocity != nullptr &&
+                      sp->out_acceleration != nullptr && sp->out_jerk != nullptr && sp->out_dt != nullptr;
+  if (expand) {
+    // expanded schedule: knots -> state with the stand-alone spline kernel, then the plain rollout kernels read it
+    const int rc = cb200_bspline_forward(sp->out_position, sp->out_velocity, sp->out_acceleration, sp->out_jerk, sp->out_dt,
+                                         sp->knots, sp->start_position, sp->start_velocity, sp->start_acceleration,
+                                         sp->start_jerk, sp->goal_position, sp->goal_velocity, sp->goal_acceleration,
+                                         sp->goal_jerk, sp->start_idx, sp->goal_idx, sp->traj_dt,
+                                         sp->use_implicit_goal_state, io->batch_size, io->horizon, h.D, sp->n_knots,
+                                         sp->degree, stream);
+    if (rc != 0) return ret((cudaError_t)rc);
+    a.q = sp->out_position;
+    a.vel = sp->out_velocity;
+    a.acc = sp->out_acceleration;
+    a.jerk = sp->out_jerk;
+    a.dt = sp->out_dt;
+  } else if (sp != nullptr) {
     a.spl = FusedArgs::Spline{sp->knots, sp->start_position, sp->start_velocity, sp->start_acceleration, sp->start_jerk,
                               sp->goal_position, sp->goal_velocity, sp->goal_acceleration, sp->goal_jerk, sp->traj_dt,
                               sp->start_idx, sp->goal_idx, sp->use_implicit_goal_state, sp->out_position,
@@ -2206,7 +2222,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   }
   DevInfo &d = dev_info();
   const bool traj = cfg->use_sweep != 0;
-  if (traj && cfg->use_speed_metric && io->dt == nullptr && sp == nullptr) return ret(cudaErrorInvalidValue);
+  if (traj && cfg->use_speed_metric && a.dt == nullptr && a.spl.knots == nullptr) return ret(cudaErrorInvalidValue);
   // the adjoint of the spline front end runs right behind the rollout kernel on the same stream
   auto finish = [&]() -> int {
     const int rc = launch_status();
@@ -2226,12 +2242,21 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       // B-spline front end: rows are evaluated from the knots inside the kernel
       {rollout_fused_kernel<0, true>, rollout_fused_kernel<1, true>, rollout_fused_kernel<2, true>, rollout_fused_kernel<3, true>},
       {rollout_traj_kernel<0, true>, rollout_traj_kernel<1, true>, rollout_traj_kernel<2, true>, rollout_traj_kernel<3, true>}};
+  // arms (few links / spheres): the row state is ~3 KB, so residency is register-bound; an 80-register build keeps
+  // 24 instead of 16 warps per SM resident and is ~7 % faster on the IK workload (slower for humanoids, where shared
+  // memory bounds residency anyway).  CB200_ARM_REGCAP=0 disables.
+  static KernelT const arm_table[4] = {rollout_fused_kernel<0, false, 3>, rollout_fused_kernel<1, false, 3>,
+                                       rollout_fused_kernel<2, false, 3>, rollout_fused_kernel<3, false, 3>};
+  static const int arm_regcap = []() {
+    const char *e = getenv("CB200_ARM_REGCAP");
+    return e ? atoi(e) : 1;
+  }();
   // small robots (arms) in discrete mode: thread-per-row "lane" schedule
   static const int lane_env = []() {
     const char *e = getenv("CB200_LANE");
     return e ? atoi(e) : 0;  // off by default: measured 2.3x slower than warp-per-row (profiles/r01_c)
   }();
-  if (!traj && lane_env != 0 && h.nl <= 24 && h.S <= 128 && sp == nullptr) {
+  if (!traj && lane_env != 0 && h.nl <= 24 && h.S <= 128 && a.spl.knots == nullptr) {
     static KernelT const lane_table[4] = {rollout_lane_kernel<0>, rollout_lane_kernel<1>, rollout_lane_kernel<2>,
                                           rollout_lane_kernel<3>};
     const LaneLayout ll = lane_layout(h.smem_bytes, kLaneThreads, h.nl, h.D, h.n_cl);
@@ -2260,7 +2285,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     const char *e = getenv("CB200_TILE");
     return e ? atoi(e) : 0;
   }();
-  if (!traj && tile_env != 0 && sp == nullptr) {
+  if (!traj && tile_env != 0 && a.spl.knots == nullptr) {
     const TileLayout tl = tile_layout(h.smem_bytes, kWarpsPerCta, h.nl, h.D, h.S, h.L, h.n_cl);
     KernelT tk = table[2][scene];
     static thread_local size_t tile_cfg[4] = {0, 0, 0, 0};
@@ -2286,8 +2311,12 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       return launch_status();
     }
   }
-  const int variant = (traj ? 1 : 0) + (sp != nullptr ? 3 : 0);
+  int variant = (traj ? 1 : 0) + (a.spl.knots != nullptr ? 3 : 0);
   KernelT kern = table[variant][scene];
+  if (variant == 0 && arm_regcap != 0 && scene <= 1 && h.nl <= 24 && h.S <= 128) {  // ESDF variants spill at 80: -3 %
+    kern = arm_table[scene];
+    variant = 5;
+  }
   const int minb = scene;  // part of the plan-cache key
   // warps per CTA: the count that keeps the most warps resident per SM (shared memory is the limiter for
   // big robots); ties go to the larger CTA so the blob is staged fewer times.  Cached per (kernel, geometry).
@@ -2295,7 +2324,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     long long key = -1;
     int nw = 0, per_sm = 0;
   };
-  static thread_local Plan plans[5][4];
+  static thread_local Plan plans[6][4];
   Plan &pl = plans[variant][scene];
   const size_t halo_bytes = traj ? (size_t)2 * h.S * sizeof(float4) : 0;
   const long long key = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ (long long)minb ^

@@ -44,7 +44,8 @@ class SplineInput(C.Structure):
                 ("start_jerk", c_p), ("goal_position", c_p), ("goal_velocity", c_p), ("goal_acceleration", c_p),
                 ("goal_jerk", c_p), ("start_idx", c_p), ("goal_idx", c_p), ("traj_dt", c_p),
                 ("use_implicit_goal_state", c_p), ("n_knots", C.c_int32), ("degree", C.c_int32), ("grad_knots", c_p),
-                ("out_position", c_p), ("out_velocity", c_p), ("out_acceleration", c_p), ("out_jerk", c_p)]
+                ("out_position", c_p), ("out_velocity", c_p), ("out_acceleration", c_p), ("out_jerk", c_p),
+                ("out_dt", c_p)]
 
 
 class RolloutIO(C.Structure):

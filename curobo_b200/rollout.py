@@ -204,10 +204,12 @@ class RolloutEngine:
     def evaluate_knots(self, knots: torch.Tensor, start_state, start_state_idx: torch.Tensor, goal_state,
                        goal_state_idx: torch.Tensor, use_implicit_goal_state: torch.Tensor, bspline_degree: int = 4,
                        interpolation_steps: int = 4, env_query_idx: Optional[torch.Tensor] = None,
-                       store_state: bool = False) -> RolloutOutput:
+                       store_state: bool = False, in_kernel_spline: bool = False) -> RolloutOutput:
         """B-spline action space: knots [B,n_knots,D] -> row costs and d cost / d knots in ONE C
-        call.  The spline states are evaluated inside the rollout kernel (they never touch HBM unless
-        `store_state`), and the adjoint kernel runs right behind it on the same stream.  start_state / goal_state
+        call.  Default schedule: spline kernel -> rollout kernel -> adjoint kernel on the same stream (3 launches, the
+        state makes one round trip through L2).  `in_kernel_spline=True`: the rollout kernel evaluates its rows from the
+        knots itself (2 launches; the state never leaves the SM unless `store_state`); identical results, currently
+        ~15 % slower at MPC scale (profiles/r01_d).  start_state / goal_state
         carry position, velocity, acceleration, jerk [n, D]; goal_state.dt [n_goal] is the trajectory dt
         (same contract as curobo_b200.trajectory.StateFromBSplineKnot.forward)."""
         D = self.robot.num_dof
@@ -247,10 +249,13 @@ class RolloutEngine:
         sp.traj_dt, sp.use_implicit_goal_state = goal_state.dt.data_ptr(), use_implicit_goal_state.data_ptr()
         sp.n_knots, sp.degree = nk, bspline_degree
         sp.grad_knots = o.grad_knots.data_ptr()
-        if store_state:
+        if store_state or not in_kernel_spline:
             if getattr(self, "_state", None) is None or tuple(self._state[0].shape) != (B, H, D):
                 self._state = tuple(torch.zeros((B, H, D), dtype=torch.float32, device=dev) for _ in range(4))
+                self._state_dt = torch.zeros((B,), dtype=torch.float32, device=dev)
             sp.out_position, sp.out_velocity, sp.out_acceleration, sp.out_jerk = (t.data_ptr() for t in self._state)
+            if not in_kernel_spline:
+                sp.out_dt = self._state_dt.data_ptr()
         io = _lib.RolloutIO()
         io.spline = C.pointer(sp)
         return self._launch(io, B, H, env_query_idx)

@@ -228,7 +228,13 @@ typedef struct {
   const uint8_t *use_implicit_goal_state;                      /* [n_goal] */
   int32_t n_knots, degree;
   float *grad_knots;                                           /* out [B, n_knots, D]; needs io->grad_vel/acc/jerk */
-  float *out_position, *out_velocity, *out_acceleration, *out_jerk; /* optional state dump [B,H,D] */
+  float *out_position, *out_velocity, *out_acceleration, *out_jerk; /* optional state buffers [B,H,D] */
+  float *out_dt;                                               /* optional [B] */
+  /* Two schedules, same results to float rounding (tests/test_gpu_bspline.py):
+   *   all five out_* given  -> "expanded": spline kernel -> rollout kernel -> adjoint kernel (3 launches; the state
+   *                            makes one 4*B*H*D*4-byte round trip through L2) -- the faster one at every measured size;
+   *   otherwise             -> "in-kernel": the rollout kernel evaluates each row from the knots (2 launches; state
+   *                            never leaves the SM; out_position.. are then optional dumps). */
 } cb200_spline_input;
 
 typedef struct {

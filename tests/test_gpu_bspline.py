@@ -205,7 +205,8 @@ def _smooth_knots(rm, B, nk, seed):
 @pytest.mark.parametrize("degree,steps,implicit", [(4, 4, False), (3, 2, True), (5, 1, False)])
 def test_fused_knots_rollout_vs_oracle_chain(mode, degree, steps, implicit):
     """evaluate_knots == oracle chain  bspline_forward -> rollout_cost_grad -> bspline_backward  and
-    == our own unfused chain (spline kernel -> evaluate_action -> adjoint kernel) bit for bit."""
+    == our own unfused chain (spline kernel -> evaluate_action -> adjoint kernel) to float rounding
+    (bit for bit whenever both run the same instantiation of the row code)."""
     from helpers import random_q, small_voxel_world
     from curobo_b200.robot_model import load_robot
     from curobo_b200.rollout import RolloutConfig, RolloutEngine
@@ -241,10 +242,18 @@ def test_fused_knots_rollout_vs_oracle_chain(mode, degree, steps, implicit):
     start_t = JointState(*[T(x) for x in start])
     goal_t = JointState(*[T(x) for x in goal], dt=T(traj_dt))
     out = eng.evaluate_knots(T(knots), start_t, T(sidx), goal_t, T(gidx), T(imp), bspline_degree=degree,
-                             interpolation_steps=steps, store_state=True)
+                             interpolation_steps=steps, store_state=True, in_kernel_spline=True)
     torch.cuda.synchronize()
     cost, gk = out.cost.clone(), out.grad_knots.clone()
     state = [t.clone() for t in eng._state]
+    # the default (expanded, 3-launch) schedule of the same call gives the same bits
+    out = eng.evaluate_knots(T(knots), start_t, T(sidx), goal_t, T(gidx), T(imp), bspline_degree=degree,
+                             interpolation_steps=steps)
+    torch.cuda.synchronize()
+    # (different template instantiations of the row code: FMA contraction may differ in the last bit)
+    torch.testing.assert_close(out.cost, cost, rtol=1e-5, atol=1e-6 * float(cost.abs().max()))
+    torch.testing.assert_close(out.grad_knots, gk, rtol=1e-4, atol=1e-5 * float(gk.abs().max()))
+    assert all(torch.equal(a, b) for a, b in zip(state, eng._state))
 
     # oracle chain
     p, v, a, j, odt = bo.bspline_forward(knots, start, goal, sidx, gidx, traj_dt, imp, Tn, degree)
@@ -273,16 +282,16 @@ def test_fused_knots_rollout_vs_oracle_chain(mode, degree, steps, implicit):
     eng2 = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
     eng2.update_goal(T(gp), T(gqt), T(sidx), non_terminal_axes=nt)
     o2 = eng2.evaluate_action(seq.position, vel=seq.velocity, acc=seq.acceleration, jerk=seq.jerk, dt=T(traj_dt))
-    assert torch.equal(o2.cost, cost)
+    torch.testing.assert_close(o2.cost, cost, rtol=1e-5, atol=1e-6 * float(cost.abs().max()))
     gk2 = torch.zeros_like(gk)
     trajectory_cu.launch_bspline_interpolation_backward_kernel(gk2, o2.grad_q, o2.grad_vel, o2.grad_acc, o2.grad_jerk,
                                                                T(traj_dt), T(gidx), T(imp), B, Tn, D, nk, degree)
-    assert torch.equal(gk2, gk)
+    torch.testing.assert_close(gk2, gk, rtol=1e-4, atol=1e-5 * float(gk.abs().max()))
 
 
 def test_fused_knots_full_size_mpc_and_graph():
     """MPC scale: 1024 seeds x 16 knots (degree 4, 1 step -> 22 rows) on the 256^3 ESDF, swept + speed metric.
-    Fused == unfused chain bit for bit, and the two-launch call is CUDA-graph capturable."""
+    Fused == unfused chain, and the call is CUDA-graph capturable."""
     from curobo_b200.robot_model import load_robot
     from curobo_b200.rollout import RolloutConfig, RolloutEngine
     from curobo_b200.scene import VoxelData
@@ -303,9 +312,12 @@ def test_fused_knots_full_size_mpc_and_graph():
     imp = torch.zeros(1, dtype=torch.uint8, device=DEV)
     cfg = RolloutConfig.trajopt()
     eng = RolloutEngine(rm, cfg, DEV, voxel=vox)
-    out = eng.evaluate_knots(knots, start, zi, goal, zi, imp, degree, steps)
+    out = eng.evaluate_knots(knots, start, zi, goal, zi, imp, degree, steps, in_kernel_spline=True)
     torch.cuda.synchronize()
     cost, gk = out.cost.clone(), out.grad_knots.clone()
+    out = eng.evaluate_knots(knots, start, zi, goal, zi, imp, degree, steps)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cost, cost) and torch.equal(out.grad_knots, gk)
     assert torch.isfinite(cost).all() and torch.isfinite(gk).all() and float(gk.abs().max()) > 0
 
     fn = StateFromBSplineKnot(DEV, D, batch_size=B, n_knots=nk, interpolation_steps=steps, control_space=ControlSpace.BSPLINE_4)
