@@ -15,6 +15,48 @@ from .. import lib as _lib
 from .tensor_checks import check_tensors, stream_ptr
 
 
+def launch_kinematics_forward(
+    link_pos: torch.Tensor,
+    link_quat: torch.Tensor,
+    batch_center_of_mass: torch.Tensor,
+    global_cumul_mat: torch.Tensor,
+    joint_vec: torch.Tensor,
+    fixed_transform: torch.Tensor,
+    link_masses_com: torch.Tensor,
+    joint_map_type: torch.Tensor,
+    joint_map: torch.Tensor,
+    link_map: torch.Tensor,
+    tool_frame_map: torch.Tensor,
+    joint_offset_map: torch.Tensor,
+    batch_size: int,
+    horizon: int,
+    n_joints: int,
+    compute_com: bool = False,
+) -> None:
+    """FK without sphere output (cuda_core_backend/kinematics.py:21-88): tool poses + cumulative transforms."""
+    if compute_com:
+        raise ValueError("b200 backend: compute_com is outside the hot-path scope (SURVEY.md section 8)")
+    dev = joint_vec.device
+    check_tensors(dev, torch.float32, link_pos=link_pos, link_quat=link_quat, global_cumul_mat=global_cumul_mat,
+                  joint_vec=joint_vec, fixed_transform=fixed_transform, joint_offset_map=joint_offset_map)
+    check_tensors(dev, torch.int8, joint_map_type=joint_map_type)
+    check_tensors(dev, torch.int16, joint_map=joint_map, link_map=link_map, tool_frame_map=tool_frame_map)
+    L = _lib.load()
+    err = L.cb200_kinematics_forward_spheres(
+        link_pos.data_ptr(), link_quat.data_ptr(), None, None, global_cumul_mat.data_ptr(), joint_vec.data_ptr(),
+        fixed_transform.data_ptr(), None, None, joint_map_type.data_ptr(), joint_map.data_ptr(), link_map.data_ptr(),
+        tool_frame_map.data_ptr(), None, joint_offset_map.data_ptr(), None, 1, int(batch_size), int(horizon), int(n_joints),
+        0, int(link_map.shape[0]), int(tool_frame_map.shape[0]), 1, 0, stream_ptr(dev))
+    _lib.check(err, "launch_kinematics_forward")
+
+
+def launch_kinematics_forward_spheres_jacobian(*args, **kwargs) -> None:
+    """Jacobian-producing FK variant (cuda_core_backend/kinematics.py:180-280): not on the rollout hot path
+    (SURVEY.md section 8a lists a2-a5 only).  Raises instead of silently doing nothing."""
+    raise ValueError("b200 backend: launch_kinematics_forward_spheres_jacobian is outside the hot-path scope; "
+                     "keep the reference backend for Jacobian queries")
+
+
 def launch_kinematics_forward_spheres(
     link_pos: torch.Tensor,
     link_quat: torch.Tensor,

@@ -69,6 +69,23 @@ def test_fk_forward_vs_oracle_and_reference(robot, n):
         quat_close(rq.cpu().numpy(), quat, 1e-5)
 
 
+def test_fk_without_spheres_entry_point():
+    """launch_kinematics_forward (the no-sphere entry of the backend module) == the sphere variant's poses."""
+    from curobo_b200.backends import kinematics as kin_cu
+    rm = load_robot("franka")
+    kp = KinematicsParams.from_robot_model(rm, DEV)
+    q = T(random_q(rm, 50, seed=4))
+    st = Kinematics(rm, DEV).compute_kinematics(q.view(50, 1, -1))
+    pos = torch.zeros((50, 1, kp.num_pose_links, 3), device=DEV)
+    quat = torch.zeros((50, 1, kp.num_pose_links, 4), device=DEV)
+    cum = torch.zeros((50, 1, kp.num_links, 3, 4), device=DEV)
+    kin_cu.launch_kinematics_forward(pos, quat, None, cum, q, kp.fixed_transforms, None, kp.joint_map_type, kp.joint_map,
+                                     kp.link_map, kp.tool_frame_map, kp.joint_offset_map, 50, 1, kp.num_dof)
+    assert torch.equal(pos, st.tool_pose_position.detach()) and torch.equal(quat, st.tool_pose_quaternion.detach())
+    with pytest.raises(ValueError, match="outside the hot-path scope"):
+        kin_cu.launch_kinematics_forward_spheres_jacobian()
+
+
 def test_fk_golden_vector_on_gpu():
     rm = load_robot("franka")
     kin = Kinematics(rm, DEV)
