@@ -1649,6 +1649,67 @@ inline void align16(std::vector<unsigned char> &buf) {
 // ================================================================================================
 // C ABI
 // ================================================================================================
+// Near-minimal ball enclosing the balls (p_s, r_s [+ padding_s]) of spheres [s_begin, s_end) with radius >= 0:
+// Badoiu-Clarkson iterations from the centroid (move the centre 1/(k+1) of the way towards the farthest ball), then
+// R = max(|p - c| + r) exactly for the final centre, inflated against fp32 rounding of the world transform.
+// out = (cx, cy, cz, R); R = -1 when no sphere is enabled.  A tighter ball only prunes more; it is never unsafe.
+static void bounding_ball(const float *link_spheres, const float *padding, int s_begin, int s_end, float *out) {
+  double c[3] = {0, 0, 0};
+  int n = 0;
+  auto rad = [&](int s) { return (double)link_spheres[4 * s + 3] + (padding ? (double)padding[s] : 0.0); };
+  for (int s = s_begin; s < s_end; ++s) {
+    if (rad(s) < 0) continue;
+    for (int k = 0; k < 3; ++k) c[k] += link_spheres[4 * s + k];
+    ++n;
+  }
+  out[0] = out[1] = out[2] = 0.0f;
+  out[3] = -1.0f;
+  if (n == 0) return;
+  for (int k = 0; k < 3; ++k) c[k] /= n;
+  auto farthest = [&](const double *cc, int &arg) {
+    double best = -1;
+    arg = -1;
+    for (int s = s_begin; s < s_end; ++s) {
+      const double r = rad(s);
+      if (r < 0) continue;
+      const double dx = link_spheres[4 * s] - cc[0], dy = link_spheres[4 * s + 1] - cc[1], dz = link_spheres[4 * s + 2] - cc[2];
+      const double d = std::sqrt(dx * dx + dy * dy + dz * dz) + r;
+      if (d > best) {
+        best = d;
+        arg = s;
+      }
+    }
+    return best;
+  };
+  int arg;
+  double best_R = farthest(c, arg), best_c[3] = {c[0], c[1], c[2]};
+  for (int it = 1; it <= 200; ++it) {
+    const double R = farthest(c, arg);
+    if (R < best_R) {
+      best_R = R;
+      for (int k = 0; k < 3; ++k) best_c[k] = c[k];
+    }
+    // step towards the farthest ball's far point
+    const double dx = link_spheres[4 * arg] - c[0], dy = link_spheres[4 * arg + 1] - c[1], dz = link_spheres[4 * arg + 2] - c[2];
+    const double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+    if (d < 1e-12) break;
+    const double step = (R - 0.0) / (it + 1.0) / d * (d > 0 ? 1.0 : 0.0);
+    const double lim = d;  // never overshoot the sphere centre
+    const double mv = std::min(step * d, lim) / d;
+    c[0] += dx * mv;
+    c[1] += dy * mv;
+    c[2] += dz * mv;
+  }
+  const double Rf = farthest(best_c, arg);
+  out[0] = (float)best_c[0];
+  out[1] = (float)best_c[1];
+  out[2] = (float)best_c[2];
+  // centre was rounded to fp32: re-measure from the rounded centre
+  double cr[3] = {(double)out[0], (double)out[1], (double)out[2]};
+  const double Rr = farthest(cr, arg);
+  out[3] = (float)(std::max(Rf, Rr) * (1.0 + 1e-4) + 1e-5);
+}
+
 extern "C" {
 
 int cb200_abi_version(void) { return CB200_ABI_VERSION; }
@@ -2064,63 +2125,10 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
       for (int a = 0; a < n_cl; ++a) {
         cll[a] = (int16_t)cl_link[a];
         cls[a] = (int16_t)cl_start[a];
-        // bounding sphere of the enabled (padded radius >= 0) spheres: centroid + max(|p - c| + r)
-        double cx = 0, cy = 0, cz = 0;
-        int n = 0;
-        for (int s0 = cl_start[a]; s0 < cl_start[a + 1]; ++s0) {
-          if (link_spheres[4 * s0 + 3] + sphere_padding[s0] < 0.0f) continue;
-          cx += link_spheres[4 * s0];
-          cy += link_spheres[4 * s0 + 1];
-          cz += link_spheres[4 * s0 + 2];
-          ++n;
-        }
-        float R = -1.0f;
-        if (n > 0) {
-          cx /= n;
-          cy /= n;
-          cz /= n;
-          double r = 0;
-          for (int s0 = cl_start[a]; s0 < cl_start[a + 1]; ++s0) {
-            const double rr = (double)link_spheres[4 * s0 + 3] + sphere_padding[s0];
-            if (rr < 0) continue;
-            const double dx = link_spheres[4 * s0] - cx, dy = link_spheres[4 * s0 + 1] - cy, dz = link_spheres[4 * s0 + 2] - cz;
-            r = std::max(r, std::sqrt(dx * dx + dy * dy + dz * dz) + rr);
-          }
-          R = (float)(r * (1.0 + 1e-4) + 1e-5);  // conservative against fp32 rounding of the world transform
-        }
-        clb[4 * a] = (float)cx;
-        clb[4 * a + 1] = (float)cy;
-        clb[4 * a + 2] = (float)cz;
-        clb[4 * a + 3] = R;
-        // scene broad phase: enabled = radius >= 0, unpadded radii
-        float *cls_b = reinterpret_cast<float *>(o + h.off_cl_bound_scene);
-        double sx = 0, sy = 0, sz = 0;
-        int m = 0;
-        for (int s0 = cl_start[a]; s0 < cl_start[a + 1]; ++s0) {
-          if (link_spheres[4 * s0 + 3] < 0.0f) continue;
-          sx += link_spheres[4 * s0];
-          sy += link_spheres[4 * s0 + 1];
-          sz += link_spheres[4 * s0 + 2];
-          ++m;
-        }
-        float Rs = -1.0f;
-        if (m > 0) {
-          sx /= m;
-          sy /= m;
-          sz /= m;
-          double r = 0;
-          for (int s0 = cl_start[a]; s0 < cl_start[a + 1]; ++s0) {
-            const double rr = link_spheres[4 * s0 + 3];
-            if (rr < 0) continue;
-            const double dx = link_spheres[4 * s0] - sx, dy = link_spheres[4 * s0 + 1] - sy, dz = link_spheres[4 * s0 + 2] - sz;
-            r = std::max(r, std::sqrt(dx * dx + dy * dy + dz * dz) + rr);
-          }
-          Rs = (float)(r * (1.0 + 1e-4) + 1e-5);
-        }
-        cls_b[4 * a] = (float)sx;
-        cls_b[4 * a + 1] = (float)sy;
-        cls_b[4 * a + 2] = (float)sz;
-        cls_b[4 * a + 3] = Rs;
+        // bounding spheres of the enabled sphere balls: padded radii for self collision, raw radii for the scene
+        bounding_ball(link_spheres, sphere_padding, cl_start[a], cl_start[a + 1], clb + 4 * a);
+        bounding_ball(link_spheres, nullptr, cl_start[a], cl_start[a + 1],
+                      reinterpret_cast<float *>(o + h.off_cl_bound_scene) + 4 * a);
       }
       cls[n_cl] = (int16_t)S;
       memcpy(o + h.off_lp, lps.data(), lps.size() * 4);

@@ -259,6 +259,49 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
       const int a = q & 0xffffu, b = q >> 16;
       const int sa = rv.cl_start[a], na = rv.cl_start[a + 1] - sa;
       const int sb = rv.cl_start[b], nb = rv.cl_start[b + 1] - sb;
+      if (na <= 32 && nb <= 32) {
+        // Second-level cull (exact): a pair (i, j) with f > 0 has |p_i - c_b| < r_i + R_b and |p_j - c_a| < r_j + R_a
+        // (bounds enclose the padded sphere balls), so only spheres that reach the OTHER link's bound can matter.
+        // Most blocks that survive the bound-vs-bound test have none on one side and are dropped here; the rest are
+        // scanned over the compacted candidate lists (indices staged in the idle force/torque scratch).
+        const float4 A = es.bc[a], B = es.bc[b];
+        bool ca = false, cb = false;
+        if (lane < na) {
+          const float4 x = es.gsph[sa + lane];
+          const float dx = x.x - B.x, dy = x.y - B.y, dz = x.z - B.z, rs = x.w + B.w;
+          ca = (x.w >= 0.0f) && (dx * dx + dy * dy + dz * dz < rs * rs);
+        }
+        if (lane < nb) {
+          const float4 y = es.gsph[sb + lane];
+          const float dx = y.x - A.x, dy = y.y - A.y, dz = y.z - A.z, rs = y.w + A.w;
+          cb = (y.w >= 0.0f) && (dx * dx + dy * dy + dz * dz < rs * rs);
+        }
+        const unsigned ma = __ballot_sync(kFull, ca), mb = __ballot_sync(kFull, cb);
+        if (ma == 0u || mb == 0u) continue;
+        unsigned char *ia = reinterpret_cast<unsigned char *>(es.ft), *ib = ia + 32;
+        const unsigned lt = (1u << lane) - 1u;
+        if (ca) ia[__popc(ma & lt)] = (unsigned char)lane;
+        if (cb) ib[__popc(mb & lt)] = (unsigned char)lane;
+        __syncwarp();
+        const int na2 = __popc(ma), nb2 = __popc(mb);
+        const float inv_nb2 = 1.0f / (float)nb2;
+        #pragma unroll 1
+        for (int t = lane; t < na2 * nb2; t += 32) {
+          const int io = (int)(((float)t + 0.5f) * inv_nb2);
+          const int i = sa + ia[io], j = sb + ib[t - io * nb2];
+          const float4 x = es.gsph[i], y = es.gsph[j];
+          const float rs = x.w + y.w;
+          const float dx = x.x - y.x, dy = x.y - y.y, dz = x.z - y.z;
+          const float f = rs * rs - (dx * dx + dy * dy + dz * dz);
+          if (f > 0.0f) {  // candidates already have non-negative radii
+            const unsigned long long k = ((unsigned long long)__float_as_uint(f) << 32) |
+                                         ((unsigned long long)(0xffffu - (unsigned)i) << 16) | (0xffffu - (unsigned)j);
+            key = k > key ? k : key;
+          }
+        }
+        __syncwarp();  // the index scratch is rewritten for the next block
+        continue;
+      }
       const float inv_nb = 1.0f / (float)nb;
       #pragma unroll 1
       for (int t = lane; t < na * nb; t += 32) {
