@@ -268,7 +268,10 @@ static __host__ __device__ __noinline__ void voxel_sdf_boundary(const uint16_t *
 }
 
 // Trilinear ESDF sample + analytic gradient; feat points at the layer start (flat, z fastest).
-CB_HD SdfGrad voxel_sdf_grad(V3 p, const uint16_t *feat, int nx, int ny, int nz, float vs, float max_dist) {
+// `need_below`: the caller only uses the normal when sdf < need_below (pen = r + eta - sdf > 0), so the gradient
+// (two thirds of the arithmetic) is skipped otherwise -- the returned sdf is computed identically either way.
+CB_HD SdfGrad voxel_sdf_grad(V3 p, const uint16_t *feat, int nx, int ny, int nz, float vs, float max_dist,
+                             float need_below = 3.0e38f) {
   SdfGrad out;
   out.n = mk3(0.f, 0.f, 0.f);
   float sdf, gx, gy, gz;
@@ -306,6 +309,10 @@ CB_HD SdfGrad voxel_sdf_grad(V3 p, const uint16_t *feat, int nx, int ny, int nz,
       float s110 = load_half(b + sx + sy), s111 = load_half(b + sx + sy + 1);
       sdf = s000 * fx1 * fy1 * fz1 + s001 * fx1 * fy1 * fz + s010 * fx1 * fy * fz1 + s011 * fx1 * fy * fz +
             s100 * fx * fy1 * fz1 + s101 * fx * fy1 * fz + s110 * fx * fy * fz1 + s111 * fx * fy * fz;
+      if (!(sdf < need_below)) {
+        out.sdf = sdf >= max_dist ? max_dist : sdf;
+        return out;
+      }
       gx = ((s100 - s000) * fy1 * fz1 + (s101 - s001) * fy1 * fz + (s110 - s010) * fy * fz1 + (s111 - s011) * fy * fz) * inv;
       gy = ((s010 - s000) * fx1 * fz1 + (s011 - s001) * fx1 * fz + (s110 - s100) * fx * fz1 + (s111 - s101) * fx * fz) * inv;
       gz = ((s001 - s000) * fx1 * fy1 + (s011 - s010) * fx1 * fy + (s101 - s100) * fx * fy1 + (s111 - s110) * fx * fy) * inv;
@@ -372,11 +379,11 @@ struct Obstacle {
   float vs, max_dist;
 };
 template <int SCENE>
-CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p) {
+CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p, float need_below = 3.0e38f) {
   if (SCENE == 1) return cuboid_sdf_grad(p, o.a, o.b, o.c);
-  if (SCENE == 2) return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist);
+  if (SCENE == 2) return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below);
   if (o.kind == 0) return cuboid_sdf_grad(p, o.a, o.b, o.c);
-  return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist);
+  return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below);
 }
 
 // Iterate every enabled obstacle of env `env` (cuboids then voxel grids) and call fn(frame, obstacle).
@@ -435,7 +442,7 @@ CB_HD float sphere_scene_discrete(V3 c, float r, float eta, float w, const Cuboi
   const float radj = r + eta;
   for_each_obstacle<SCENE>(cs, vx, env, [&](const ObsFrame &f, const Obstacle &o) {
     V3 lp = qrot(f.q, c) + f.p;
-    SdfGrad sg = obstacle_sdf<SCENE>(o, lp);
+    SdfGrad sg = obstacle_sdf<SCENE>(o, lp, radj);
     float pen = radj - sg.sdf;
     if (pen > 0.0f) {
       float ac, as;
@@ -461,7 +468,7 @@ CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev,
     float csum = 0.0f;
     V3 gsum = mk3(0.f, 0.f, 0.f);
     {
-      SdfGrad sg = obstacle_sdf<SCENE>(o, lc);
+      SdfGrad sg = obstacle_sdf<SCENE>(o, lc, radj);
       float pen = radj - sg.sdf;
       if (pen > 0.0f) {
         float ac, as;
@@ -482,7 +489,7 @@ CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev,
         if (jump >= half) break;
         float t = 1.0f - 0.5f * jump * inv_half;
         V3 pt = t * lc + (1.0f - t) * ln;
-        SdfGrad sg = obstacle_sdf<SCENE>(o, pt);
+        SdfGrad sg = obstacle_sdf<SCENE>(o, pt, radj);
         float pen = radj - sg.sdf;
         if (pen > 0.0f) {
           float ac, as;

@@ -44,9 +44,16 @@ def main():
     ii, ti, si = h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("Source")
     ncu = [(r[si].strip(), int(r[ii]), int(r[ti])) for r in sec["rows"] if len(r) > ii]
     mangled = re.sub(r"[^A-Za-z0-9_]", "", kname.split("<")[0].split("::")[-1])
-    tmpl = re.search(r"<\(int\)(\d+)>", sec["name"])
+    targs = re.search(re.escape(kname.split("<")[0].split("::")[-1]) + r"<([^>]*)>", sec["name"])
+    tm = ""
+    if targs:  # "(int)2, (bool)0, (int)3" -> "ILi2ELb0ELi3EE"
+        for a in targs.group(1).split(","):
+            m2 = re.match(r"\s*\((int|bool)\)(\d+)", a)
+            if m2:
+                tm += ("Li" if m2.group(1) == "int" else "Lb") + m2.group(2) + "E"
+        tm = "I" + tm + "E"
     txt = open(sass).read().split("\n")
-    starts = [i for i, l in enumerate(txt) if l.startswith(".text.") and mangled in l and (tmpl is None or f"ILi{tmpl.group(1)}E" in l)]
+    starts = [i for i, l in enumerate(txt) if l.startswith(".text.") and mangled in l and (not tm or tm in l)]
     start = starts[0]
     end = next(i for i, l in enumerate(txt) if i > start and l.startswith("//---------------------"))
     dis, cf, cl = [], None, None
