@@ -334,3 +334,75 @@ def test_traj_full_size_mpc_properties():
     eng_d = RolloutEngine(rm, RolloutConfig(scene_weight=100000.0, scene_activation=0.0025), DEV, voxel=vox)
     c_d = eng_d.evaluate_action(qs).scene_cost
     torch.testing.assert_close(c_sw, c_d, rtol=1e-5, atol=1e-6 * float(c_d.max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# options of the fused kernel that the per-op tests cover separately: multi-env worlds, goalsets
+# ------------------------------------------------------------------------------------------------
+def _two_env_worlds():
+    """env 0: benchmark table + pillar and a 64^3 ESDF; env 1: a wall in front of the robot, disabled pillar, and a
+    different ESDF."""
+    from curobo_b200.world import CuboidWorld
+    c0 = make_benchmark_cuboid_world(max_n=4)
+    c1 = CuboidWorld.create([{"dims": [0.05, 1.5, 1.5], "pose": [0.35, 0.0, 0.5, 0.9659258, 0, 0, 0.2588190]},
+                             {"dims": [0.3, 0.3, 0.3], "pose": [0.0, 0.5, 0.4, 1, 0, 0, 0]},
+                             {"dims": [5.0, 5.0, 5.0], "pose": [0.0, 0.0, 0.0, 1, 0, 0, 0]}], max_n=4)
+    c1.enable[0, 2] = 0                                    # a disabled obstacle that would hit everything
+    cub = CuboidWorld(np.concatenate([c0.dims, c1.dims]), np.concatenate([c0.inv_pose, c1.inv_pose]),
+                      np.concatenate([c0.enable, c1.enable]), np.concatenate([c0.count, c1.count]))
+    v0, v1 = small_voxel_world(seed=3), small_voxel_world(seed=8, num_boxes=6)
+    vox = VoxelWorld(np.concatenate([v0.params, v1.params]), np.concatenate([v0.inv_pose, v1.inv_pose]),
+                     np.concatenate([v0.enable, v1.enable]), np.concatenate([v0.count, v1.count]),
+                     np.concatenate([v0.features, v1.features]), v0.max_dist)
+    return cub, vox
+
+
+@pytest.mark.parametrize("mode", ["discrete", "swept"])
+def test_fused_rollout_multi_env(mode):
+    """Rows pick their world through env_query_idx[b] (two envs with different cuboids and ESDFs)."""
+    rm = load_robot("franka")
+    B, H = 10, (1 if mode == "discrete" else 6)
+    q = random_walk_q(rm, B, H, seed=77) if H > 1 else random_q(rm, B, seed=77)[:, None, :]
+    cub, vox = _two_env_worlds()
+    env = (np.arange(B) % 2).astype(np.int32)
+    cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                        cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0),
+                        use_sweep=(mode == "swept"), use_speed_metric=False)
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    out = eng.evaluate_action(T(q), env_query_idx=T(env))
+    torch.cuda.synchronize()
+    want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(1), world_cuboid=cub, world_voxel=vox, env_query_idx=env)
+    assert want["scene_cost"].reshape(B, -1)[0::2].sum() > 0 and want["scene_cost"].reshape(B, -1)[1::2].sum() > 0
+    np.testing.assert_allclose(out.scene_cost.cpu().numpy(), want["scene_cost"], rtol=2e-4,
+                               atol=1e-5 * max(want["scene_cost"].max(), 1e-6))
+    np.testing.assert_allclose(out.cost.cpu().numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+    # the two envs really differ: evaluating every row in env 0 gives another scene cost for the odd rows
+    out0 = eng.evaluate_action(T(q), env_query_idx=T(np.zeros(B, np.int32))).scene_cost.clone()
+    assert not torch.allclose(out0[1::2], T(want["scene_cost"])[1::2])
+
+
+@pytest.mark.parametrize("lie", [False, True])
+def test_fused_rollout_goalset_and_tool_frames(lie):
+    """Goalsets (closest of 3 goals per tool frame) through the fused kernel, on the 14-tool-frame humanoid and the arm."""
+    for robot, B in (("franka", 24), ("g1_29", 6)):
+        rm = load_robot(robot)
+        q = (random_q(rm, B, seed=81) if robot == "franka" else humanoid_q(rm, B, seed=81))[:, None, :]
+        G, ngs = 4, 3
+        qg = (random_q(rm, G * ngs, seed=82) if robot == "franka" else humanoid_q(rm, G * ngs, seed=82, scale=0.5))
+        _, _, p, qt = O.fk_forward(rm, qg)                       # [G*ngs, L, 3/4]
+        L = p.shape[1]
+        gp = p.reshape(G, ngs, L, 3).transpose(0, 2, 1, 3).copy()
+        gq = qt.reshape(G, ngs, L, 4).transpose(0, 2, 1, 3).copy()
+        idx = (np.arange(B) % G).astype(np.int32)
+        cfg = RolloutConfig(self_weight=0.0, scene_weight=0.0, pose_weight=(2000.0, 100.0), pose_lie=lie,
+                            cspace_type="position", cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0))
+        eng = RolloutEngine(rm, cfg, DEV, store_fk_outputs=True)
+        eng.update_goal(T(gp), T(gq), T(idx))
+        out = eng.evaluate_action(T(q))
+        torch.cuda.synchronize()
+        want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(L), goal_pos=gp, goal_quat=gq, idxs_goal=idx)
+        np.testing.assert_allclose(out.pose_cost.cpu().numpy(), want["pose_cost"], rtol=3e-4, atol=2e-5 * want["pose_cost"].max())
+        assert np.array_equal(out.pose_goalset_idx.cpu().numpy(), want["pose_goalset_idx"].reshape(B, 1, L))
+        assert len(np.unique(want["pose_goalset_idx"])) > 1
+        grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=3e-3, scale=3e-5)
