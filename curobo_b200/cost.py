@@ -27,7 +27,10 @@ def tool_pose_distance(current_position, current_quat, goal_position, goal_quat,
         raise ValueError(f"idxs_goal must have shape ({b}, 1) but got {tuple(idxs_goal.shape)}")
     if out_distance.shape != (b, h, nl * 2):
         raise ValueError("out_distance must have shape (b, h, num_links*2)")
-    if project_distance_to_goal is not None and bool(project_distance_to_goal.any()):
+    # "Only 0 is supported for now" (wp_tool_pose.py:743-744).  The check reads the tensor back, which is illegal during
+    # CUDA-graph capture, so it is done on eager calls only (a captured call was validated by its warm-up run).
+    if (project_distance_to_goal is not None and not torch.cuda.is_current_stream_capturing()
+            and bool(project_distance_to_goal.any())):
         raise ValueError("b200 tool-pose cost: project_distance_to_goal is not supported")
     dev = current_position.device
     check_tensors(dev, torch.float32, current_position=current_position, current_quat=current_quat,
