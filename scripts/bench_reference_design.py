@@ -143,6 +143,50 @@ def run(workload, steps=200, warmup=10, device="cuda:0"):
         torch.cuda.synchronize()
         return float(np.mean([a.elapsed_time(b) for a, b in zip(st_, en_)]))
 
+    if os.environ.get("CB200_STAGE_TIMES"):
+        import time
+        stages = {}
+        def t_stage(name, fn, reps=200):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            stages[name] = a.elapsed_time(b) / reps * 1e3
+        st = lambda: _stream(dev)  # noqa: E731
+        sph4 = sph.view(B, H, S, 4)
+        t_stage("ref_fk_forward", lambda: lib.ref_kinematics_forward_spheres(
+            _p(pos), _p(quat), _p(sph), _p(com), _p(cum), _p(q), _p(kp.fixed_transforms), _p(kp.link_spheres),
+            _p(kp.link_masses_com), _p(kp.joint_map_type), _p(kp.joint_map), _p(kp.link_map), _p(kp.tool_frame_map),
+            _p(kp.link_sphere_idx_map), _p(kp.joint_offset_map), _p(eq), kp.num_envs, N, 1, kp.num_dof, kp.num_spheres,
+            kp.num_links, kp.num_pose_links, st()))
+        t_stage("ref_self_collision", lambda: lib.ref_self_collision_distance(
+            _p(sc_dist), _p(sc_vec), _p(sc_pd), _p(sc_sparse), _p(sph4), _p(padding), _p(w_self), _p(pairs), _p(sc_bv),
+            _p(sc_bi), nb, rm.max_threads_per_block, B, H, S, pairs.shape[0], 1, st()))
+        t_stage("our_scene_per_op", lambda: scene_launch(cfg.use_sweep, sph4, cbuf, scene, w_scene, eta, None, False, env0, False))
+        if has_pose:
+            t_stage("our_tool_pose_per_op", lambda: cb_cost.tool_pose_distance(
+                pos.view(B, H, L, 3), quat.view(B, H, L, 4), gp, gq, gidx, pw, ones6, ones6, zeros2, zeros2, proj, p_cost, p_pd,
+                p_rd, p_gp, p_gq, p_gi, cfg.pose_lie))
+        t_stage("our_cspace_per_op", lambda: cb_cost.cspace_position_cost(
+            q3, zeros_bhd, zd, zi, lim, efl, cs_w, cs_a, tw1, tdw, z2, zd, zd, zi, vlim, z1, cs_cost, cs_gp, cs_gt))
+        t_stage("torch_grad_add", lambda: torch.add(sc_vec.view(N, S, 4), cbuf.gradient.view(N, S, 4), out=g_sph))
+        t_stage("ref_fk_backward", lambda: lib.ref_kinematics_backward(
+            _p(g_q), _p(p_gp.view(N, L, 3) if has_pose else g_pos0), _p(p_gq.view(N, L, 4) if has_pose else g_quat0),
+            _p(g_sph), _p(g_com), _p(g_com), None, _p(cum), _p(kp.link_spheres), _p(kp.link_masses_com), _p(kp.link_map),
+            _p(kp.joint_map), _p(kp.joint_map_type), _p(kp.tool_frame_map), _p(kp.link_sphere_idx_map),
+            _p(kp.link_chain_data), _p(kp.link_chain_offsets), _p(kp.joint_links_data), _p(kp.joint_links_offsets),
+            _p(kp.joint_affects_endeffector), _p(kp.joint_offset_map), _p(eq), kp.num_envs, N, 1, kp.num_dof,
+            kp.num_spheres, kp.num_links, kp.num_pose_links, st()))
+        t_stage("our_fk_forward_per_op", lambda: __import__("curobo_b200.backends.kinematics", fromlist=["x"]).launch_kinematics_forward_spheres(
+            pos.view(B, H, L, 3), quat.view(B, H, L, 4), sph4, None, cum.view(B, H, nl, 3, 4), q, kp.fixed_transforms, kp.link_spheres,
+            None, kp.joint_map_type, kp.joint_map, kp.link_map, kp.tool_frame_map, kp.link_sphere_idx_map, kp.joint_offset_map,
+            eq, 1, N, 1, D, S))
+        print(json.dumps({"workload": workload, "stage_us_warm_L2": {k: round(v, 2) for k, v in stages.items()}}), flush=True)
     ms_unfused = time_graph(unfused)
     uc, ug = total_cost.clone(), grad_q.clone()
     ms_fused = time_graph(lambda: eng.evaluate_action(q3))
