@@ -2348,7 +2348,12 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     if (e != cudaSuccess) return ret(e);
     int best_nw = 0, best_per_sm = 0;
     double best_score = 0.0;
+    static const int force_nw = []() {  // tuning knob: pin the warps per CTA (0 = choose by residency)
+      const char *e = getenv("CB200_FORCE_NW");
+      return e ? atoi(e) : 0;
+    }();
     for (int nw = kWarpsPerCta; nw >= 1; --nw) {
+      if (force_nw > 0 && nw != force_nw) continue;
       const size_t need = (size_t)h.smem_bytes + halo_bytes + (size_t)nw * a.eval_floats * sizeof(float);
       if (need > limit) continue;
       int per_sm = 0;
