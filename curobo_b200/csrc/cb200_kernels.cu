@@ -1635,8 +1635,33 @@ inline VoxelSet to_dev(const cb200_voxel_set *v) {
   VoxelSet o{};
   if (v != nullptr && v->inv_pose != nullptr && v->max_n > 0)
     o = VoxelSet{v->params, v->inv_pose, v->enable, v->count, v->features, v->n_voxels_per_layer,
-                 v->max_n,  v->num_envs, v->max_dist};
+                 v->max_n,  v->num_envs, v->max_dist, v->mip, v->mip_stride};
   return o;
+}
+
+// Lower-bound pyramid level of the ESDF (see voxel_sdf_grad): one thread per 8x8x8 block of base corners; the block
+// of base corners [8c, 8c+7] reads fine voxels [8c, 8c+8] per axis (clipped to the grid).
+__global__ void voxel_mip_kernel(VoxelSet vs, uint16_t *mip, int n_layers) {
+  const long long per = vs.mip_stride;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < per * n_layers;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(t / per);
+    long long c = t - (long long)k * per;
+    const int nx = (int)vs.params[4 * k + 0], ny = (int)vs.params[4 * k + 1], nz = (int)vs.params[4 * k + 2];
+    const int mx = (nx + 7) >> kMipShift, my = (ny + 7) >> kMipShift, mz = (nz + 7) >> kMipShift;
+    uint16_t outv = 0x7bffu;  // largest finite half: unused tail entries never cull anything wrongly (never read)
+    if (c < (long long)mx * my * mz) {
+      const int cz = (int)(c % mz), cy = (int)((c / mz) % my), cx = (int)(c / ((long long)mz * my));
+      const uint16_t *feat = vs.features + (size_t)k * vs.n_voxels_per_layer;
+      float m = 3.0e38f;
+      const int x1 = min(8 * cx + 8, nx - 1), y1 = min(8 * cy + 8, ny - 1), z1 = min(8 * cz + 8, nz - 1);
+      for (int x = 8 * cx; x <= x1; ++x)
+        for (int y = 8 * cy; y <= y1; ++y)
+          for (int z = 8 * cz; z <= z1; ++z) m = fminf(m, load_half(feat + ((size_t)x * ny + y) * nz + z));
+      outv = __half_as_ushort(__float2half_rd(m));  // m is itself a half value: exact
+    }
+    mip[(size_t)k * per + c] = outv;
+  }
 }
 
 template <typename T>
@@ -1977,6 +2002,27 @@ static int64_t blob_layout(const cb200_robot_sizes *sz, const int16_t *link_map,
 static int lp_cap(const cb200_robot_sizes *sz) {
   const int m = std::min(sz->num_links, sz->num_spheres);
   return std::min(m * (m - 1) / 2, std::max(sz->num_pairs, 0));
+}
+
+int64_t cb200_voxel_mip_stride(const float *host_params, int num_layers) {
+  if (host_params == nullptr || num_layers < 1) return -1;
+  int64_t best = 1;
+  for (int k = 0; k < num_layers; ++k) {
+    const int64_t nx = (int64_t)host_params[4 * k], ny = (int64_t)host_params[4 * k + 1], nz = (int64_t)host_params[4 * k + 2];
+    best = std::max(best, ((nx + 7) >> kMipShift) * ((ny + 7) >> kMipShift) * ((nz + 7) >> kMipShift));
+  }
+  return best;
+}
+
+int cb200_voxel_build_mip(const cb200_voxel_set *vs, cb200_stream_t stream) {
+  if (vs == nullptr || vs->mip == nullptr || vs->mip_stride < 1 || vs->features == nullptr || vs->params == nullptr ||
+      vs->max_n < 1 || vs->num_envs < 1)
+    return ret(cudaErrorInvalidValue);
+  const int n_layers = vs->max_n * vs->num_envs;
+  const long long n = (long long)vs->mip_stride * n_layers;
+  const int grid = (int)std::min<long long>((n + 127) / 128, 148LL * 16);
+  voxel_mip_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(to_dev(vs), const_cast<uint16_t *>(vs->mip), n_layers);
+  return launch_status();
 }
 
 int64_t cb200_robot_blob_bytes(const cb200_robot_sizes *sz) {

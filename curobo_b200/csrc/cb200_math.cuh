@@ -270,8 +270,14 @@ static __host__ __device__ __noinline__ void voxel_sdf_boundary(const uint16_t *
 // Trilinear ESDF sample + analytic gradient; feat points at the layer start (flat, z fastest).
 // `need_below`: the caller only uses the normal when sdf < need_below (pen = r + eta - sdf > 0), so the gradient
 // (two thirds of the arithmetic) is skipped otherwise -- the returned sdf is computed identically either way.
+// `mip` (optional): min-pooled lower bounds, one fp16 per 8x8x8 block of base corners (cb200_voxel_build_mip).  A
+// trilinear (or validity-weighted boundary) sample is a convex combination of its valid corner values, so
+// mip[block] >= need_below proves sdf >= need_below and the eight scattered corner loads are skipped -- exact for the
+// discrete test `pen = r + eta - sdf > 0`; the returned sdf is then only a lower bound, so swept sampling (which
+// advances by the distance itself) must pass mip = nullptr.
+constexpr int kMipShift = 3;
 CB_HD SdfGrad voxel_sdf_grad(V3 p, const uint16_t *feat, int nx, int ny, int nz, float vs, float max_dist,
-                             float need_below = 3.0e38f) {
+                             float need_below = 3.0e38f, const uint16_t *mip = nullptr) {
   SdfGrad out;
   out.n = mk3(0.f, 0.f, 0.f);
   float sdf, gx, gy, gz;
@@ -300,6 +306,15 @@ CB_HD SdfGrad voxel_sdf_grad(V3 p, const uint16_t *feat, int nx, int ny, int nz,
     if (!((x0k || x1k) && (y0k || y1k) && (z0k || z1k))) {
       out.sdf = max_dist;  // all 8 corners outside the grid: weight_sum == 0 -> max_dist (data_voxel.py:1019-1020)
       return out;
+    }
+    if (mip != nullptr) {
+      const int my = (ny + 7) >> kMipShift, mz = (nz + 7) >> kMipShift;
+      const int cx = (x0 < 0 ? 0 : x0) >> kMipShift, cy = (y0 < 0 ? 0 : y0) >> kMipShift, cz = (z0 < 0 ? 0 : z0) >> kMipShift;
+      const float lb = load_half(mip + ((size_t)cx * my + cy) * mz + cz);
+      if (!(lb < need_below)) {
+        out.sdf = lb >= max_dist ? max_dist : lb;
+        return out;
+      }
     }
     if (x0k && x1k && y0k && y1k && z0k && z1k) {
       const uint16_t *b = feat + base;
@@ -349,6 +364,8 @@ struct VoxelSet {
   const uint16_t *features;
   int32_t n_voxels_per_layer, max_n, num_envs;
   float max_dist;
+  const uint16_t *mip;   // optional lower-bound pyramid level [num_envs*max_n][mip_stride], see voxel_sdf_grad
+  int32_t mip_stride;
 };
 
 CB_HD float ldgf(const float *p) {
@@ -375,15 +392,16 @@ struct Obstacle {
   int kind;  // 0 cuboid, 1 voxel
   float a, b, c;  // cuboid dims | (unused)
   const uint16_t *feat;
+  const uint16_t *mip;
   int nx, ny, nz;
   float vs, max_dist;
 };
 template <int SCENE>
-CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p, float need_below = 3.0e38f) {
+CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p, float need_below = 3.0e38f, bool use_mip = false) {
   if (SCENE == 1) return cuboid_sdf_grad(p, o.a, o.b, o.c);
-  if (SCENE == 2) return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below);
+  if (SCENE == 2) return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below, use_mip ? o.mip : nullptr);
   if (o.kind == 0) return cuboid_sdf_grad(p, o.a, o.b, o.c);
-  return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below);
+  return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below, use_mip ? o.mip : nullptr);
 }
 
 // Iterate every enabled obstacle of env `env` (cuboids then voxel grids) and call fn(frame, obstacle).
@@ -404,6 +422,7 @@ CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, F
       o.b = ldgf(cs.dims + 4 * k + 1);
       o.c = ldgf(cs.dims + 4 * k + 2);
       o.feat = nullptr;
+      o.mip = nullptr;
       o.nx = o.ny = o.nz = 0;
       o.vs = 0.f;
       o.max_dist = 0.f;
@@ -426,6 +445,7 @@ CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, F
       o.nz = (int)ldgf(vx.params + 4 * k + 2);
       o.vs = ldgf(vx.params + 4 * k + 3);
       o.feat = vx.features + (size_t)k * vx.n_voxels_per_layer;
+      o.mip = vx.mip ? vx.mip + (size_t)k * vx.mip_stride : nullptr;
       o.max_dist = vx.max_dist;
       fn(load_obs_frame(vx.inv_pose + 8 * k), o);
     }
@@ -442,7 +462,7 @@ CB_HD float sphere_scene_discrete(V3 c, float r, float eta, float w, const Cuboi
   const float radj = r + eta;
   for_each_obstacle<SCENE>(cs, vx, env, [&](const ObsFrame &f, const Obstacle &o) {
     V3 lp = qrot(f.q, c) + f.p;
-    SdfGrad sg = obstacle_sdf<SCENE>(o, lp, radj);
+    SdfGrad sg = obstacle_sdf<SCENE>(o, lp, radj, true);
     float pen = radj - sg.sdf;
     if (pen > 0.0f) {
       float ac, as;

@@ -23,7 +23,7 @@ class CuboidSet(C.Structure):
 class VoxelSet(C.Structure):
     _fields_ = [("params", C.c_void_p), ("inv_pose", C.c_void_p), ("enable", C.c_void_p), ("count", C.c_void_p),
                 ("features", C.c_void_p), ("n_voxels_per_layer", C.c_int32), ("max_n", C.c_int32),
-                ("num_envs", C.c_int32), ("max_dist", C.c_float)]
+                ("num_envs", C.c_int32), ("max_dist", C.c_float), ("mip", C.c_void_p), ("mip_stride", C.c_int32)]
 
 
 class RobotSizes(C.Structure):
@@ -80,6 +80,8 @@ _SIGS = {
     "cb200_bspline_backward": ([c_p] * 8 + [_I] * 5 + [c_p], _I),
     "cb200_lbfgs_step": ([c_p] * 8 + [C.c_float] + [_I] * 4 + [c_p] * 3 + [_I, c_p, _I, _I, c_p], _I),
     "cb200_line_search": ([c_p] * 5 + [_I, C.c_float, C.c_float] + [c_p] * 13 + [C.c_float, C.c_float] + [_I] * 5 + [c_p], _I),
+    "cb200_voxel_mip_stride": ([c_p, _I], C.c_int64),
+    "cb200_voxel_build_mip": ([C.POINTER(VoxelSet), c_p], _I),
     "cb200_robot_blob_bytes": ([C.POINTER(RobotSizes)], C.c_int64),
     "cb200_pack_robot_blob": ([c_p, C.c_int64, C.POINTER(RobotSizes)] + [c_p] * 15, C.c_int64),
     "cb200_rollout_cost_grad": ([C.POINTER(RolloutCfg), C.POINTER(RolloutIO), c_p], _I),
@@ -110,7 +112,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)       # AttributeError if the symbol is missing: fail loudly
         fn.argtypes = args
         fn.restype = res
-    if lib.cb200_abi_version() != 2:
+    if lib.cb200_abi_version() != 3:
         raise RuntimeError("libcurobo_b200.so ABI version mismatch")
     _LIB = lib
     return lib

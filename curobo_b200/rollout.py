@@ -114,7 +114,7 @@ def pack_robot_blob(rm: RobotModel) -> np.ndarray:
 class RolloutEngine:
     def __init__(self, robot: RobotModel, cfg: RolloutConfig, device="cuda:0",
                  cuboid: Optional[CuboidData] = None, voxel: Optional[VoxelData] = None,
-                 store_fk_outputs: bool = False):
+                 store_fk_outputs: bool = False, use_voxel_mip: bool = True):
         self.robot, self.cfg, self.device = robot, cfg, torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("RolloutEngine is CUDA-only (sm_100a); there is no CPU path")
@@ -122,12 +122,24 @@ class RolloutEngine:
         self._blob_host = pack_robot_blob(robot)
         self._blob = torch.from_numpy(self._blob_host.copy()).to(self.device)
         self.cuboid, self.voxel = cuboid, voxel
-        self._cs = c_cuboid_set(cuboid, self.device)
-        self._vs = c_voxel_set(voxel, self.device)
+        self.use_voxel_mip = use_voxel_mip
+        self.refresh_world()
         self.store_fk_outputs = store_fk_outputs
         self._B = self._H = -1
         self._goal = None
         self._ccfg = self._make_ccfg(1)
+
+    def refresh_world(self) -> None:
+        """Re-read the obstacle holders; call after the ESDF values (or obstacle tensors) were replaced or updated in
+        place.  Rebuilds the ESDF lower-bound pyramid level (one tiny launch) that lets discrete collision skip the
+        corner fetches of samples that are provably inactive (exact; `use_voxel_mip=False` disables it)."""
+        if self.voxel is not None and self.use_voxel_mip:
+            from .scene import build_voxel_mip
+            build_voxel_mip(self.voxel)
+        self._cs = c_cuboid_set(self.cuboid, self.device)
+        self._vs = c_voxel_set(self.voxel, self.device)
+        if self.voxel is not None and not self.use_voxel_mip and self._vs is not None:
+            self._vs.mip, self._vs.mip_stride = None, 0
 
     # -- configuration ------------------------------------------------------------------------
     def _make_ccfg(self, num_goalset: int) -> _lib.RolloutCfg:

@@ -52,6 +52,34 @@ class VoxelData:
         return cls(t(w.params), t(w.inv_pose), t(w.enable), t(w.count), t(w.features), w.max_n, w.num_envs,
                    float(w.max_dist))
 
+    def build_mip(self) -> torch.Tensor:
+        """(Re)build the optional lower-bound pyramid level of the ESDF (include/curobo_b200.h: cb200_voxel_set.mip)
+        and attach it to this object; call again after the ESDF values change.  See build_voxel_mip."""
+        return build_voxel_mip(self)
+
+
+def build_voxel_mip(d) -> torch.Tensor:
+    """One fp16 lower bound per 8x8x8 block of trilinear base corners, stored on `d` as `d.cb200_mip`
+    [num_envs * max_n, stride] so that c_voxel_set picks it up.  `d` is a VoxelData (ours or the reference's: only the
+    attributes params / features / ... are read).  Results of every operator are identical with or without it."""
+    dev = d.features.device
+    L = _lib.load()
+    params_host = d.params.detach().reshape(-1, 4).cpu().contiguous()
+    n_layers = int(params_host.shape[0])
+    stride = int(L.cb200_voxel_mip_stride(params_host.data_ptr(), n_layers))
+    if stride < 1:
+        raise ValueError("cannot size the ESDF pyramid level")
+    mip = torch.empty((n_layers, stride), dtype=torch.int16, device=dev)
+    try:
+        d.cb200_mip = None
+    except Exception:  # noqa: BLE001  (frozen holders)
+        pass
+    vs = c_voxel_set(d, dev)
+    vs.mip, vs.mip_stride = mip.data_ptr(), stride
+    _lib.check(L.cb200_voxel_build_mip(C.byref(vs), stream_ptr(dev)), "voxel_build_mip")
+    d.cb200_mip = mip
+    return mip
+
 
 @dataclass
 class SceneData:
@@ -107,8 +135,10 @@ def c_voxel_set(d: Optional[object], dev=None) -> Optional[_lib.VoxelSet]:
         check_tensors(dev, torch.uint8, voxel_enable=d.enable)
         check_tensors(dev, torch.int32, voxel_count=d.count)
     n_vox = int(d.features.shape[2])
+    mip = getattr(d, "cb200_mip", None)
     return _lib.VoxelSet(d.params.data_ptr(), d.inv_pose.data_ptr(), d.enable.data_ptr(), d.count.data_ptr(),
-                         d.features.data_ptr(), n_vox, int(d.max_n), int(d.num_envs), float(d.max_esdf_distance))
+                         d.features.data_ptr(), n_vox, int(d.max_n), int(d.num_envs), float(d.max_esdf_distance),
+                         mip.data_ptr() if mip is not None else None, int(mip.shape[1]) if mip is not None else 0)
 
 
 def _launch(sweep, query_spheres, buffer, scene, weight, activation_distance, speed_dt, enable_speed_metric,

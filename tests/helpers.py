@@ -55,7 +55,7 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def hm_scene(lib, spheres, weight, eta, sweep, speed, dt, cub: CuboidWorld = None, vox: VoxelWorld = None):
+def hm_scene(lib, spheres, weight, eta, sweep, speed, dt, cub: CuboidWorld = None, vox: VoxelWorld = None, mip=None):
     sp = np.ascontiguousarray(spheres, np.float32)
     B, H, S, _ = sp.shape
     cost = np.zeros((B, H, S), np.float32)
@@ -73,5 +73,26 @@ def hm_scene(lib, spheres, weight, eta, sweep, speed, dt, cub: CuboidWorld = Non
     else:
         args += [None, None, None, None, None, C.c_int(0), C.c_int(0), C.c_float(0)]
     args += [ptr(cost), ptr(grad)]
+    args += [ptr(mip) if mip is not None else None, C.c_int(int(mip.shape[-1]) if mip is not None else 0)]
     lib.hm_scene(*args)
     return cost, grad
+
+
+def numpy_voxel_mip(vox: VoxelWorld):
+    """Reference construction of the ESDF lower-bound level (cb200_voxel_build_mip): for every 8x8x8 block of base
+    corners [8c, 8c+7] the minimum over fine voxels [8c, 8c+8] per axis; returns uint16 [layers, stride]."""
+    layers = vox.params.reshape(-1, 4)
+    feats = vox.features.reshape(layers.shape[0], -1)
+    dims = [(int(p[0]), int(p[1]), int(p[2])) for p in layers]
+    stride = max(((nx + 7) // 8) * ((ny + 7) // 8) * ((nz + 7) // 8) for nx, ny, nz in dims)
+    out = np.full((len(dims), stride), 0x7bff, np.uint16)
+    for k, (nx, ny, nz) in enumerate(dims):
+        g = feats[k, : nx * ny * nz].astype(np.float32).reshape(nx, ny, nz)
+        mx, my, mz = (nx + 7) // 8, (ny + 7) // 8, (nz + 7) // 8
+        m = np.zeros((mx, my, mz), np.float16)
+        for cx in range(mx):
+            for cy in range(my):
+                for cz in range(mz):
+                    m[cx, cy, cz] = g[8 * cx: 8 * cx + 9, 8 * cy: 8 * cy + 9, 8 * cz: 8 * cz + 9].min()
+        out[k, : mx * my * mz] = m.reshape(-1).view(np.uint16)
+    return out

@@ -26,11 +26,11 @@ void hm_scene(const float *spheres, int B, int H, int S, float weight, float eta
               const float *cub_dims, const float *cub_inv_pose, const uint8_t *cub_enable, const int32_t *cub_count,
               int cub_max_n, const float *vox_params, const float *vox_inv_pose, const uint8_t *vox_enable,
               const int32_t *vox_count, const uint16_t *vox_feat, int vox_nvox, int vox_max_n, float vox_max_dist,
-              float *out_cost, float *out_grad) {
+              float *out_cost, float *out_grad, const uint16_t *vox_mip, int vox_mip_stride) {
   CuboidSet cs{};
   VoxelSet vs{};
   if (cub_inv_pose) cs = CuboidSet{cub_dims, cub_inv_pose, cub_enable, cub_count, cub_max_n, 1};
-  if (vox_inv_pose) vs = VoxelSet{vox_params, vox_inv_pose, vox_enable, vox_count, vox_feat, vox_nvox, vox_max_n, 1, vox_max_dist};
+  if (vox_inv_pose) vs = VoxelSet{vox_params, vox_inv_pose, vox_enable, vox_count, vox_feat, vox_nvox, vox_max_n, 1, vox_max_dist, vox_mip, vox_mip_stride};
   for (int b = 0; b < B; ++b)
     for (int h = 0; h < H; ++h)
       for (int s = 0; s < S; ++s) {

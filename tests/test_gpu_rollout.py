@@ -406,3 +406,49 @@ def test_fused_rollout_goalset_and_tool_frames(lie):
         assert np.array_equal(out.pose_goalset_idx.cpu().numpy(), want["pose_goalset_idx"].reshape(B, 1, L))
         assert len(np.unique(want["pose_goalset_idx"])) > 1
         grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=3e-3, scale=3e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# ESDF lower-bound pyramid level: built on the GPU == numpy construction; every result identical with / without
+# ------------------------------------------------------------------------------------------------
+def test_voxel_mip_build_and_exact_cull():
+    from helpers import numpy_voxel_mip
+    from curobo_b200.scene import build_voxel_mip
+    cub, vox = _two_env_worlds()                       # two 64^3 layers (multiples of 8)
+    odd = small_voxel_world(n=45, voxel=0.05, seed=5)  # 45^3: blocks clipped at the upper faces
+    for w in (vox, odd):
+        vd = VoxelData.from_world(w, DEV)
+        mip = build_voxel_mip(vd)
+        torch.cuda.synchronize()
+        want = numpy_voxel_mip(w)
+        nxyz = [tuple(int(v) for v in p[:3]) for p in w.params.reshape(-1, 4)]
+        for k, (nx, ny, nz) in enumerate(nxyz):
+            used = ((nx + 7) // 8) * ((ny + 7) // 8) * ((nz + 7) // 8)
+            assert np.array_equal(mip[k, :used].cpu().numpy().view(np.uint16), want[k, :used])
+    rm = load_robot("g1_29")
+    B = 48
+    q = humanoid_q(rm, B, seed=91)[:, None, :]
+    env = (np.arange(B) % 2).astype(np.int32)
+    cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                        cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0))
+    outs = []
+    for use in (True, False):
+        eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV), use_voxel_mip=use)
+        assert (eng._vs.mip is not None and eng._vs.mip != 0) == use
+        o = eng.evaluate_action(T(q), env_query_idx=T(env))
+        outs.append((o.cost.clone(), o.grad_q.clone(), o.scene_cost.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert float(outs[0][2].sum()) > 0
+    # per-op kernel with the level attached to the data holder
+    sph = Kinematics(rm, DEV).compute_kinematics(T(q)).robot_spheres.detach()
+    res = []
+    for use in (False, True):
+        vd = VoxelData.from_world(vox, DEV)
+        if use:
+            vd.build_mip()
+        buf = CollisionBuffer.from_shape(tuple(sph.shape), DEV)
+        d = SphereObstacleCollision.apply(sph, buf, SceneData(None, vd), T(np.array([5000.0], np.float32)),
+                                          T(np.array([0.02], np.float32)), None, T(env), True, False)
+        res.append((d.clone(), buf.gradient.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

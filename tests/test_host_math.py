@@ -102,3 +102,39 @@ def test_tool_pose_host_vs_oracle(lib, method):
         np.testing.assert_allclose(out[7:11], gq[i, 0, 0], rtol=2e-4, atol=2e-3)
         np.testing.assert_allclose(out[2], pe[i, 0, 0], rtol=2e-4, atol=1e-5)
         np.testing.assert_allclose(out[3], re[i, 0, 0], rtol=2e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# ESDF lower-bound pyramid level (cb200_voxel_set.mip): culling must not change any result
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,voxel,seed", [(40, 0.05, 1), (33, 0.06, 2), (17, 0.11, 3)])
+def test_voxel_mip_cull_is_exact_on_host(n, voxel, seed):
+    """The device sampler compiled for the host: discrete sphere-vs-ESDF cost and gradient with the numpy-built
+    lower-bound level are bit-identical to those without it (grid sizes that are and are not multiples of 8, spheres
+    inside, at the boundary of and outside the grid), and the level really culls most samples' fetches."""
+    from helpers import numpy_voxel_mip
+    rng = np.random.default_rng(seed)
+    sdf = make_box_esdf(n=n, voxel_size=voxel, num_boxes=6, seed=seed, ground_z=-0.05)
+    vox = VoxelWorld.from_grid(sdf.reshape(n, n, n), voxel)
+    half = 0.5 * n * voxel
+    B, S = 6, 200
+    sph = np.zeros((B, 1, S, 4), np.float32)
+    sph[..., :3] = rng.uniform(-1.15 * half, 1.15 * half, size=(B, 1, S, 3))
+    sph[..., 3] = rng.uniform(0.01, 0.08, size=(B, 1, S))
+    sph[0, 0, :5, 3] = -1.0                                   # disabled spheres
+    mip = numpy_voxel_mip(vox)
+    lib = hostmath()
+    c0, g0 = hm_scene(lib, sph, 5000.0, 0.02, False, False, 0.0, vox=vox)
+    c1, g1 = hm_scene(lib, sph, 5000.0, 0.02, False, False, 0.0, vox=vox, mip=mip)
+    assert np.array_equal(c0, c1) and np.array_equal(g0, g1)
+    assert (c0 > 0).any() and (c0 == 0).mean() > 0.3
+    want_c, want_g = O.scene_collision(sph, 5000.0, 0.02, None, vox, None, sweep=False, speed_dt=None)
+    np.testing.assert_allclose(c1, want_c, rtol=2e-4, atol=1e-5 * want_c.max())
+    # the bound is a true lower bound of every trilinear sample based in its block
+    feats = vox.features.reshape(-1)[: n * n * n].astype(np.float32).reshape(n, n, n)
+    m = mip[0].view(np.float16).astype(np.float32)
+    mm = (n + 7) // 8
+    for _ in range(200):
+        x0, y0, z0 = rng.integers(0, n - 1, 3)
+        corner_min = feats[x0:x0 + 2, y0:y0 + 2, z0:z0 + 2].min()
+        assert m[((x0 >> 3) * mm + (y0 >> 3)) * mm + (z0 >> 3)] <= corner_min
