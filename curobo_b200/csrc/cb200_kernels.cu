@@ -1639,8 +1639,8 @@ inline VoxelSet to_dev(const cb200_voxel_set *v) {
   return o;
 }
 
-// Lower-bound pyramid level of the ESDF (see voxel_sdf_grad): one thread per 8x8x8 block of base corners; the block
-// of base corners [8c, 8c+7] reads fine voxels [8c, 8c+8] per axis (clipped to the grid).
+// Lower-bound pyramid level of the ESDF (see voxel_sdf_grad): one thread per block of B^3 base corners (B = kMipBlock);
+// the block of base corners [Bc, Bc+B-1] reads fine voxels [Bc, Bc+B] per axis (clipped to the grid).
 __global__ void voxel_mip_kernel(VoxelSet vs, uint16_t *mip, int n_layers) {
   const long long per = vs.mip_stride;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < per * n_layers;
@@ -1648,16 +1648,17 @@ __global__ void voxel_mip_kernel(VoxelSet vs, uint16_t *mip, int n_layers) {
     const int k = (int)(t / per);
     long long c = t - (long long)k * per;
     const int nx = (int)vs.params[4 * k + 0], ny = (int)vs.params[4 * k + 1], nz = (int)vs.params[4 * k + 2];
-    const int mx = (nx + 7) >> kMipShift, my = (ny + 7) >> kMipShift, mz = (nz + 7) >> kMipShift;
+    const int mx = (nx + kMipBlock - 1) >> kMipShift, my = (ny + kMipBlock - 1) >> kMipShift, mz = (nz + kMipBlock - 1) >> kMipShift;
     uint16_t outv = 0x7bffu;  // largest finite half: unused tail entries never cull anything wrongly (never read)
     if (c < (long long)mx * my * mz) {
       const int cz = (int)(c % mz), cy = (int)((c / mz) % my), cx = (int)(c / ((long long)mz * my));
       const uint16_t *feat = vs.features + (size_t)k * vs.n_voxels_per_layer;
       float m = 3.0e38f;
-      const int x1 = min(8 * cx + 8, nx - 1), y1 = min(8 * cy + 8, ny - 1), z1 = min(8 * cz + 8, nz - 1);
-      for (int x = 8 * cx; x <= x1; ++x)
-        for (int y = 8 * cy; y <= y1; ++y)
-          for (int z = 8 * cz; z <= z1; ++z) m = fminf(m, load_half(feat + ((size_t)x * ny + y) * nz + z));
+      const int B = kMipBlock;
+      const int x1 = min(B * cx + B, nx - 1), y1 = min(B * cy + B, ny - 1), z1 = min(B * cz + B, nz - 1);
+      for (int x = B * cx; x <= x1; ++x)
+        for (int y = B * cy; y <= y1; ++y)
+          for (int z = B * cz; z <= z1; ++z) m = fminf(m, load_half(feat + ((size_t)x * ny + y) * nz + z));
       outv = __half_as_ushort(__float2half_rd(m));  // m is itself a half value: exact
     }
     mip[(size_t)k * per + c] = outv;
@@ -2004,12 +2005,14 @@ static int lp_cap(const cb200_robot_sizes *sz) {
   return std::min(m * (m - 1) / 2, std::max(sz->num_pairs, 0));
 }
 
+int cb200_voxel_mip_block(void) { return kMipBlock; }
+
 int64_t cb200_voxel_mip_stride(const float *host_params, int num_layers) {
   if (host_params == nullptr || num_layers < 1) return -1;
   int64_t best = 1;
   for (int k = 0; k < num_layers; ++k) {
     const int64_t nx = (int64_t)host_params[4 * k], ny = (int64_t)host_params[4 * k + 1], nz = (int64_t)host_params[4 * k + 2];
-    best = std::max(best, ((nx + 7) >> kMipShift) * ((ny + 7) >> kMipShift) * ((nz + 7) >> kMipShift));
+    best = std::max(best, ((nx + kMipBlock - 1) >> kMipShift) * ((ny + kMipBlock - 1) >> kMipShift) * ((nz + kMipBlock - 1) >> kMipShift));
   }
   return best;
 }

@@ -59,7 +59,7 @@ class VoxelData:
 
 
 def build_voxel_mip(d) -> torch.Tensor:
-    """One fp16 lower bound per 8x8x8 block of trilinear base corners, stored on `d` as `d.cb200_mip`
+    """One fp16 lower bound per block of cb200_voxel_mip_block()^3 trilinear base corners, stored on `d` as `d.cb200_mip`
     [num_envs * max_n, stride] so that c_voxel_set picks it up.  `d` is a VoxelData (ours or the reference's: only the
     attributes params / features / ... are read).  Results of every operator are identical with or without it."""
     dev = d.features.device

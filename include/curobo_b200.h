@@ -115,14 +115,16 @@ typedef struct {
   int32_t num_envs;
   float max_dist;
   /* Optional acceleration structure owned by the caller (NULL = none; results are identical either way): one fp16
-   * per 8x8x8 block of trilinear base corners holding the minimum ESDF value any sample based in that block can read,
+   * per block of cb200_voxel_mip_block()^3 trilinear base corners holding the minimum ESDF value any sample based in that block can read,
    * filled by cb200_voxel_build_mip after every ESDF update.  Discrete collision skips the eight corner fetches of a
    * sample whose block bound already proves sdf >= r + eta.  Layer k starts at mip + k * mip_stride. */
   const uint16_t *mip;
   int32_t mip_stride;
 } cb200_voxel_set;
 
-/* mip_stride needed for a grid set: max over layers of ceil(nx/8)*ceil(ny/8)*ceil(nz/8) (HOST params pointer). */
+/* Block edge B of the pyramid level (base corners per block and axis). */
+int cb200_voxel_mip_block(void);
+/* mip_stride needed for a grid set: max over layers of ceil(nx/B)*ceil(ny/B)*ceil(nz/B) (HOST params pointer). */
 int64_t cb200_voxel_mip_stride(const float *host_params, int num_layers);
 /* Fill vs->mip (device, num_envs*max_n*mip_stride uint16) from vs->features / vs->params on `stream`. */
 int cb200_voxel_build_mip(const cb200_voxel_set *vs, cb200_stream_t stream);

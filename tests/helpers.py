@@ -78,21 +78,28 @@ def hm_scene(lib, spheres, weight, eta, sweep, speed, dt, cub: CuboidWorld = Non
     return cost, grad
 
 
+def mip_block() -> int:
+    from curobo_b200 import lib as _l
+    return int(_l.load().cb200_voxel_mip_block())
+
+
 def numpy_voxel_mip(vox: VoxelWorld):
-    """Reference construction of the ESDF lower-bound level (cb200_voxel_build_mip): for every 8x8x8 block of base
-    corners [8c, 8c+7] the minimum over fine voxels [8c, 8c+8] per axis; returns uint16 [layers, stride]."""
+    """Reference construction of the ESDF lower-bound level (cb200_voxel_build_mip): for every block of B^3 base
+    corners [Bc, Bc+B-1] the minimum over fine voxels [Bc, Bc+B] per axis; returns uint16 [layers, stride]."""
+    Bk = mip_block()
     layers = vox.params.reshape(-1, 4)
     feats = vox.features.reshape(layers.shape[0], -1)
     dims = [(int(p[0]), int(p[1]), int(p[2])) for p in layers]
-    stride = max(((nx + 7) // 8) * ((ny + 7) // 8) * ((nz + 7) // 8) for nx, ny, nz in dims)
+    cd = lambda n: (n + Bk - 1) // Bk  # noqa: E731
+    stride = max(cd(nx) * cd(ny) * cd(nz) for nx, ny, nz in dims)
     out = np.full((len(dims), stride), 0x7bff, np.uint16)
     for k, (nx, ny, nz) in enumerate(dims):
         g = feats[k, : nx * ny * nz].astype(np.float32).reshape(nx, ny, nz)
-        mx, my, mz = (nx + 7) // 8, (ny + 7) // 8, (nz + 7) // 8
+        mx, my, mz = cd(nx), cd(ny), cd(nz)
         m = np.zeros((mx, my, mz), np.float16)
         for cx in range(mx):
             for cy in range(my):
                 for cz in range(mz):
-                    m[cx, cy, cz] = g[8 * cx: 8 * cx + 9, 8 * cy: 8 * cy + 9, 8 * cz: 8 * cz + 9].min()
+                    m[cx, cy, cz] = g[Bk * cx: Bk * cx + Bk + 1, Bk * cy: Bk * cy + Bk + 1, Bk * cz: Bk * cz + Bk + 1].min()
         out[k, : mx * my * mz] = m.reshape(-1).view(np.uint16)
     return out

@@ -412,7 +412,7 @@ def test_fused_rollout_goalset_and_tool_frames(lie):
 # ESDF lower-bound pyramid level: built on the GPU == numpy construction; every result identical with / without
 # ------------------------------------------------------------------------------------------------
 def test_voxel_mip_build_and_exact_cull():
-    from helpers import numpy_voxel_mip
+    from helpers import mip_block, numpy_voxel_mip
     from curobo_b200.scene import build_voxel_mip
     cub, vox = _two_env_worlds()                       # two 64^3 layers (multiples of 8)
     odd = small_voxel_world(n=45, voxel=0.05, seed=5)  # 45^3: blocks clipped at the upper faces
@@ -423,7 +423,8 @@ def test_voxel_mip_build_and_exact_cull():
         want = numpy_voxel_mip(w)
         nxyz = [tuple(int(v) for v in p[:3]) for p in w.params.reshape(-1, 4)]
         for k, (nx, ny, nz) in enumerate(nxyz):
-            used = ((nx + 7) // 8) * ((ny + 7) // 8) * ((nz + 7) // 8)
+            Bk = mip_block()
+            used = ((nx + Bk - 1) // Bk) * ((ny + Bk - 1) // Bk) * ((nz + Bk - 1) // Bk)
             assert np.array_equal(mip[k, :used].cpu().numpy().view(np.uint16), want[k, :used])
     rm = load_robot("g1_29")
     B = 48

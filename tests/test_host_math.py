@@ -133,8 +133,10 @@ def test_voxel_mip_cull_is_exact_on_host(n, voxel, seed):
     # the bound is a true lower bound of every trilinear sample based in its block
     feats = vox.features.reshape(-1)[: n * n * n].astype(np.float32).reshape(n, n, n)
     m = mip[0].view(np.float16).astype(np.float32)
-    mm = (n + 7) // 8
+    from helpers import mip_block
+    Bk = mip_block()
+    mm = (n + Bk - 1) // Bk
     for _ in range(200):
         x0, y0, z0 = rng.integers(0, n - 1, 3)
         corner_min = feats[x0:x0 + 2, y0:y0 + 2, z0:z0 + 2].min()
-        assert m[((x0 >> 3) * mm + (y0 >> 3)) * mm + (z0 >> 3)] <= corner_min
+        assert m[((x0 // Bk) * mm + (y0 // Bk)) * mm + (z0 // Bk)] <= corner_min
