@@ -83,6 +83,8 @@ _SIGS = {
     "cb200_voxel_mip_block": ([], _I),
     "cb200_voxel_mip_stride": ([c_p, _I], C.c_int64),
     "cb200_voxel_build_mip": ([C.POINTER(VoxelSet), c_p], _I),
+    "cb200_rnea_forward": ([c_p] * 15 + [_I] * 4 + [c_p, c_p], _I),
+    "cb200_rnea_backward": ([c_p] * 17 + [_I] * 4 + [c_p, c_p], _I),
     "cb200_robot_blob_bytes": ([C.POINTER(RobotSizes)], C.c_int64),
     "cb200_pack_robot_blob": ([c_p, C.c_int64, C.POINTER(RobotSizes)] + [c_p] * 15, C.c_int64),
     "cb200_rollout_cost_grad": ([C.POINTER(RolloutCfg), C.POINTER(RolloutIO), c_p], _I),

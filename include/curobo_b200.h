@@ -358,6 +358,36 @@ int cb200_line_search(
     int strong_wolfe, int approx_wolfe, int n_linesearch, int opt_dim, int batchsize,
     cb200_stream_t stream);
 
+/* -------------------------------------------------------------------------------------------
+ * (8f-3) RNEA inverse dynamics and its adjoint: tau = RNEA(q, qd, qdd [, f_ext]) feeds the effort terms of the STATE
+ * c-space cost; the adjoint maps d loss / d tau back to (q, qd, qdd).
+ *   cb200_rnea_forward   <- launch_rnea_forward   curobo/_src/curobolib/backends/cuda_core_backend/dynamics.py:24-131
+ *                           (kernels/dynamics/rnea_forward_kernel.cuh:54-285)
+ *   cb200_rnea_backward  <- launch_rnea_backward  cuda_core_backend/dynamics.py:134-250
+ *                           (kernels/dynamics/rnea_backward_kernel.cuh:60-460)
+ * Same tensors and meaning: q/qd/qdd/tau/grads [B, num_dof]; fixed_transforms [nl,3,4]; link_masses_com [nl,4]
+ * (cx,cy,cz,m); link_inertias [nl,8] (ixx,iyy,izz,ixy,ixz,iyz,pad,pad at the CoM); gravity [6] spatial; level_starts
+ * [n_levels+1] / level_links [nl] = CSR of links by tree depth; forward_cache [B, nl, 20] (v, a, f per link; the same
+ * layout as the reference's, so either side can consume the other's).  The reference's threads_per_batch knob has no
+ * equivalent (rows are processed serially, one thread each: deterministic sums).  Gradients are overwritten.
+ * ------------------------------------------------------------------------------------------- */
+int cb200_rnea_forward(
+    float *tau, const float *q, const float *qd, const float *qdd, const float *fixed_transforms,
+    const float *link_masses_com, const float *link_inertias, const int8_t *joint_map_type,
+    const int16_t *joint_map, const int16_t *link_map, const float *joint_offset_map,
+    const float *gravity, const int16_t *level_starts, const int16_t *level_links,
+    float *forward_cache, int batch_size, int num_links, int num_dof, int n_levels,
+    const float *f_ext, cb200_stream_t stream);
+
+int cb200_rnea_backward(
+    float *grad_q, float *grad_qd, float *grad_qdd, const float *grad_tau, const float *q,
+    const float *qd, const float *fixed_transforms, const float *link_masses_com,
+    const float *link_inertias, const int8_t *joint_map_type, const int16_t *joint_map,
+    const int16_t *link_map, const float *joint_offset_map, const float *gravity,
+    const int16_t *level_starts, const int16_t *level_links, const float *forward_cache,
+    int batch_size, int num_links, int num_dof, int n_levels, float *grad_f_ext,
+    cb200_stream_t stream);
+
 /* Host helper: pack robot constants (HOST pointers) into `out` (host buffer of
  * cb200_robot_blob_bytes(...) bytes) that the caller then copies to the device once.
  * Returns bytes written or a negative number on invalid input. */

@@ -282,3 +282,77 @@ int ref_line_search(float *best_cost, float *best_action, int16_t *best_iteratio
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// RNEA inverse dynamics kernels, serial path (threads_per_batch = 1) like
+// backends/cuda_core_backend/dynamics_config.py:118-215: shared memory per batch element = N_LINKS*12 floats (forward),
+// N_LINKS*30 floats + one N_LINKS*12 block of inertial parameters (backward); <= 48 KB per block.
+// The kernels are templated on (N_LINKS, N_DOF); the three robots of the test-suite are instantiated.
+// ------------------------------------------------------------------------------------------------
+#include "dynamics/rnea_forward_kernel.cuh"
+#include "dynamics/rnea_backward_kernel.cuh"
+
+namespace cdy = curobo::dynamics;
+
+template <int NL, int ND>
+static int ref_rnea_fwd_t(float *tau, const float *q, const float *qd, const float *qdd, const float *fixed, const float *mc,
+                          const float *inertia, const int8_t *jtype, const int16_t *jmap, const int16_t *lmap,
+                          const float *joff, const float *gravity, const int16_t *lstarts, const int16_t *llinks, float *cache,
+                          int B, int n_levels, cudaStream_t stream) {
+  const int per = NL * 12 * 4;
+  int bpb = 48 * 1024 / per;
+  if (bpb > 64) bpb = 64;
+  if (bpb >= 32) bpb = bpb / 32 * 32;
+  if (bpb < 1) return 1;
+  const int blocks = (B + bpb - 1) / bpb;
+  cdy::rnea_forward_kernel<NL, ND, 1, false><<<blocks, bpb, (size_t)bpb * per, stream>>>(
+      tau, q, qd, qdd, fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, lstarts, llinks, cache, nullptr, B, n_levels);
+  return (int)cudaGetLastError();
+}
+
+template <int NL, int ND>
+static int ref_rnea_bwd_t(float *gq, float *gqd, float *gqdd, const float *gtau, const float *q, const float *qd,
+                          const float *fixed, const float *mc, const float *inertia, const int8_t *jtype, const int16_t *jmap,
+                          const int16_t *lmap, const float *joff, const float *gravity, const int16_t *lstarts,
+                          const int16_t *llinks, const float *cache, int B, int n_levels, cudaStream_t stream) {
+  const int shared_block = NL * 12 * 4, per = NL * 30 * 4;
+  int bpb = (48 * 1024 - shared_block) / per;
+  if (bpb > 64) bpb = 64;
+  if (bpb >= 32) bpb = bpb / 32 * 32;
+  if (bpb < 1) return 1;
+  const int blocks = (B + bpb - 1) / bpb;
+  cdy::rnea_backward_kernel<NL, ND, 1, false><<<blocks, bpb, (size_t)shared_block + (size_t)bpb * per, stream>>>(
+      gq, gqd, gqdd, nullptr, gtau, q, qd, fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, lstarts, llinks, cache, B,
+      n_levels);
+  return (int)cudaGetLastError();
+}
+
+extern "C" {
+
+int ref_rnea_forward(float *tau, const float *q, const float *qd, const float *qdd, const float *fixed, const float *mc,
+                     const float *inertia, const int8_t *jtype, const int16_t *jmap, const int16_t *lmap, const float *joff,
+                     const float *gravity, const int16_t *lstarts, const int16_t *llinks, float *cache, int B, int nl, int D,
+                     int n_levels, cudaStream_t stream) {
+#define CB_FWD(NL, ND) \
+  if (nl == NL && D == ND) return ref_rnea_fwd_t<NL, ND>(tau, q, qd, qdd, fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, lstarts, llinks, cache, B, n_levels, stream);
+  CB_FWD(13, 7)
+  CB_FWD(42, 35)
+  CB_FWD(56, 49)
+#undef CB_FWD
+  return -1;
+}
+
+int ref_rnea_backward(float *gq, float *gqd, float *gqdd, const float *gtau, const float *q, const float *qd,
+                      const float *fixed, const float *mc, const float *inertia, const int8_t *jtype, const int16_t *jmap,
+                      const int16_t *lmap, const float *joff, const float *gravity, const int16_t *lstarts,
+                      const int16_t *llinks, const float *cache, int B, int nl, int D, int n_levels, cudaStream_t stream) {
+#define CB_BWD(NL, ND) \
+  if (nl == NL && D == ND) return ref_rnea_bwd_t<NL, ND>(gq, gqd, gqdd, gtau, q, qd, fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, lstarts, llinks, cache, B, n_levels, stream);
+  CB_BWD(13, 7)
+  CB_BWD(42, 35)
+  CB_BWD(56, 49)
+#undef CB_BWD
+  return -1;
+}
+
+}  // extern "C"

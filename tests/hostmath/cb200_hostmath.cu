@@ -149,3 +149,47 @@ int hm_bspline_backward(float *out, const float *gp, const float *gv, const floa
   return 0;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// RNEA inverse dynamics + adjoint, host build of curobo_b200/csrc/cb200_dynamics.cuh
+// ------------------------------------------------------------------------------------------------
+#include <vector>
+
+#include "../../curobo_b200/csrc/cb200_dynamics.cuh"
+
+namespace dy = cb200::dyn;
+
+struct HostStore {
+  std::vector<float> buf;
+  int nl;
+  HostStore(int arrays, int nl_) : buf((size_t)arrays * nl_ * 6, 0.0f), nl(nl_) {}
+  float get(int arr, int k, int c) const { return buf[((size_t)arr * nl + k) * 6 + c]; }
+  void set(int arr, int k, int c, float v) { buf[((size_t)arr * nl + k) * 6 + c] = v; }
+};
+
+extern "C" {
+void hm_rnea_forward(float *tau, float *cache, const float *q, const float *qd, const float *qdd, const float *fixed,
+                     const float *mc, const float *inertia, const int8_t *jtype, const int16_t *jmap, const int16_t *lmap,
+                     const float *joff, const float *gravity, const int16_t *lstarts, const int16_t *llinks, int B, int nl,
+                     int D, int n_levels) {
+  dy::Model M{fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, lstarts, llinks, nl, D, n_levels};
+  for (int b = 0; b < B; ++b) {
+    HostStore S(2, nl);
+    dy::rnea_forward_row(M, S, q + (size_t)b * D, qd + (size_t)b * D, qdd + (size_t)b * D, nullptr, tau + (size_t)b * D,
+                         cache + (size_t)b * nl * dy::kCacheFloatsPerLink);
+  }
+}
+
+void hm_rnea_backward(float *gq, float *gqd, float *gqdd, const float *grad_tau, const float *q, const float *qd,
+                      const float *cache, const float *fixed, const float *mc, const float *inertia, const int8_t *jtype,
+                      const int16_t *jmap, const int16_t *lmap, const float *joff, const float *gravity,
+                      const int16_t *lstarts, const int16_t *llinks, int B, int nl, int D, int n_levels) {
+  dy::Model M{fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, lstarts, llinks, nl, D, n_levels};
+  for (int b = 0; b < B; ++b) {
+    HostStore S(5, nl);
+    dy::rnea_backward_row(M, S, grad_tau + (size_t)b * D, q + (size_t)b * D, qd + (size_t)b * D,
+                          cache + (size_t)b * nl * dy::kCacheFloatsPerLink, gq + (size_t)b * D, gqd + (size_t)b * D,
+                          gqdd + (size_t)b * D, nullptr);
+  }
+}
+}

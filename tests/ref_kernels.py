@@ -146,3 +146,27 @@ def line_search(st, search_cost, search_action, search_gradient, step_direction,
         C.c_float(c_2), int(strong), int(approx), n, V, B, _stream(search_cost.device))
     assert err == 0, err
     return st
+
+
+# ------------------------------------------------------------------------------------------------
+# RNEA kernels of the reference (kernels/dynamics/), serial path
+# ------------------------------------------------------------------------------------------------
+def rnea_forward(model, q, qd, qdd, nl, D, n_levels):
+    """model = (fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, level_starts, level_links) device tensors."""
+    dev = q.device
+    B = q.shape[0]
+    tau = torch.zeros((B, D), dtype=torch.float32, device=dev)
+    cache = torch.zeros((B, nl * 20), dtype=torch.float32, device=dev)
+    err = lib().ref_rnea_forward(_p(tau), _p(q), _p(qd), _p(qdd), *[_p(m) for m in model], _p(cache), B, nl, D, n_levels, _stream(dev))
+    assert err == 0, err
+    return tau, cache
+
+
+def rnea_backward(model, grad_tau, q, qd, cache, nl, D, n_levels):
+    dev = q.device
+    B = q.shape[0]
+    g = [torch.zeros((B, D), dtype=torch.float32, device=dev) for _ in range(3)]
+    err = lib().ref_rnea_backward(*[_p(x) for x in g], _p(grad_tau), _p(q), _p(qd), *[_p(m) for m in model], _p(cache), B, nl, D,
+                                  n_levels, _stream(dev))
+    assert err == 0, err
+    return g
