@@ -50,8 +50,9 @@ struct Rp {
   float R[9], p[3];
 };
 
-// fixed * J(angle): rotation (row-major) and translation  (rnea_helpers.cuh:25-95)
-CB_HD Rp local_Rp(const float *ft, int jt, float angle) {
+// fixed * J(angle): rotation (row-major) and translation  (rnea_helpers.cuh:25-95).  sn / cs = sin / cos of the angle for a
+// revolute joint (computed by the caller: the CTA kernels take them off the serial chain); angle is the prismatic travel.
+CB_HD Rp local_Rp_sc(const float *ft, int jt, float sn, float cs, float angle) {
   Rp o;
   float f[12];
 #pragma unroll
@@ -67,9 +68,8 @@ CB_HD Rp local_Rp(const float *ft, int jt, float angle) {
   }
   if (jt < 0) return o;
   if (jt >= 3) {
-    float s, c;
-    sincosf(angle, &s, &c);
     const int ax = jt - 3;
+    const float s = sn, c = cs;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const float x = f[4 * r + 0], y = f[4 * r + 1], z = f[4 * r + 2];
@@ -85,11 +85,18 @@ CB_HD Rp local_Rp(const float *ft, int jt, float angle) {
       }
     }
   } else {
-    o.p[0] += f[jt] * angle;
-    o.p[1] += f[4 + jt] * angle;
-    o.p[2] += f[8 + jt] * angle;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float col = jt == 0 ? f[4 * r + 0] : (jt == 1 ? f[4 * r + 1] : f[4 * r + 2]);
+      o.p[r] += col * angle;
+    }
   }
   return o;
+}
+CB_HD Rp local_Rp(const float *ft, int jt, float angle) {
+  float s = 0.0f, c = 1.0f;
+  if (jt >= 3) sincosf(angle, &s, &c);
+  return local_Rp_sc(ft, jt, s, c, angle);
 }
 
 // motion transform parent -> child:  w' = R^T w,  v' = R^T (v + w x p)
@@ -142,57 +149,135 @@ CB_HD void force_cross(const float *v, const float *f, float *r) {
   r[5] = -v[1] * f[3] + v[0] * f[4];
 }
 
-// Joint-axis operators as index tables (spatial_algebra.cuh:68-110,200-252): pairs (i, j, sign)
-struct Term {
-  signed char i, j, sg;
-};
-CB_HD Term mcs_term(int s, int n) {  // motion_cross_S: out[i] = sg * v[j] * alpha
-  constexpr Term t[6][4] = {{{1, 2, 1}, {2, 1, -1}, {4, 5, 1}, {5, 4, -1}}, {{0, 2, -1}, {2, 0, 1}, {3, 5, -1}, {5, 3, 1}},
-                            {{0, 1, 1}, {1, 0, -1}, {3, 4, 1}, {4, 3, -1}}, {{1, 2, 1}, {2, 1, -1}, {0, 0, 0}, {0, 0, 0}},
-                            {{0, 2, -1}, {2, 0, 1}, {0, 0, 0}, {0, 0, 0}},  {{0, 1, 1}, {1, 0, -1}, {0, 0, 0}, {0, 0, 0}}};
-  return t[s][n];
-}
-CB_HD Term crf_term(int s, int n) {  // dot_crf_S: sum sg * a[i] * b[j]
-  constexpr Term t[6][4] = {{{1, 2, -1}, {2, 1, 1}, {4, 5, -1}, {5, 4, 1}}, {{0, 2, 1}, {2, 0, -1}, {3, 5, 1}, {5, 3, -1}},
-                            {{0, 1, -1}, {1, 0, 1}, {3, 4, -1}, {4, 3, 1}}, {{1, 5, -1}, {2, 4, 1}, {0, 0, 0}, {0, 0, 0}},
-                            {{0, 5, 1}, {2, 3, -1}, {0, 0, 0}, {0, 0, 0}},  {{0, 4, -1}, {1, 3, 1}, {0, 0, 0}, {0, 0, 0}}};
-  return t[s][n];
-}
-CB_HD Term crm_term(int s, int n) {  // dot_crm_S
-  if (s < 3) return crf_term(s, n);
-  constexpr Term t[3][4] = {{{4, 2, -1}, {5, 1, 1}, {0, 0, 0}, {0, 0, 0}},
-                            {{3, 2, 1}, {5, 0, -1}, {0, 0, 0}, {0, 0, 0}},
-                            {{3, 1, -1}, {4, 0, 1}, {0, 0, 0}, {0, 0, 0}}};
-  return t[s - 3][n];
-}
-CB_HD void motion_cross_S_add(float *acc, const float *v, int s, float alpha) {
-  const int n = s < 3 ? 4 : 2;
-  for (int k = 0; k < n; ++k) {
-    const Term t = mcs_term(s, k);
-    acc[t.i] += (float)t.sg * v[t.j] * alpha;
+// Joint-axis operators (spatial_algebra.cuh:68-110,200-252), one case per motion-subspace slot s (0..2 revolute x/y/z,
+// 3..5 prismatic x/y/z).  Written as switches over compile-time indices so every spatial vector stays in registers.
+CB_HD void motion_cross_S_add(float *acc, const float *v, int s, float alpha) {  // acc += crm(v) S alpha
+  switch (s) {
+    case 0:
+      acc[1] += v[2] * alpha;
+      acc[2] += -v[1] * alpha;
+      acc[4] += v[5] * alpha;
+      acc[5] += -v[4] * alpha;
+      break;
+    case 1:
+      acc[0] += -v[2] * alpha;
+      acc[2] += v[0] * alpha;
+      acc[3] += -v[5] * alpha;
+      acc[5] += v[3] * alpha;
+      break;
+    case 2:
+      acc[0] += v[1] * alpha;
+      acc[1] += -v[0] * alpha;
+      acc[3] += v[4] * alpha;
+      acc[4] += -v[3] * alpha;
+      break;
+    case 3:
+      acc[1] += v[2] * alpha;
+      acc[2] += -v[1] * alpha;
+      break;
+    case 4:
+      acc[0] += -v[2] * alpha;
+      acc[2] += v[0] * alpha;
+      break;
+    case 5:
+      acc[0] += v[1] * alpha;
+      acc[1] += -v[0] * alpha;
+      break;
+    default:
+      break;
   }
 }
-CB_HD float dot_crf_S(const float *a, const float *b, int s) {
+CB_HD float dot_crf_S(const float *a, const float *b, int s) {  // a . crf(S) b
   float r = 0.0f;
-  const int n = s < 3 ? 4 : 2;
-  for (int k = 0; k < n; ++k) {
-    const Term t = crf_term(s, k);
-    r += (float)t.sg * a[t.i] * b[t.j];
+  switch (s) {
+    case 0:
+      r += -a[1] * b[2];
+      r += a[2] * b[1];
+      r += -a[4] * b[5];
+      r += a[5] * b[4];
+      break;
+    case 1:
+      r += a[0] * b[2];
+      r += -a[2] * b[0];
+      r += a[3] * b[5];
+      r += -a[5] * b[3];
+      break;
+    case 2:
+      r += -a[0] * b[1];
+      r += a[1] * b[0];
+      r += -a[3] * b[4];
+      r += a[4] * b[3];
+      break;
+    case 3:
+      r += -a[1] * b[5];
+      r += a[2] * b[4];
+      break;
+    case 4:
+      r += a[0] * b[5];
+      r += -a[2] * b[3];
+      break;
+    case 5:
+      r += -a[0] * b[4];
+      r += a[1] * b[3];
+      break;
+    default:
+      break;
   }
   return r;
 }
-CB_HD float dot_crm_S(const float *a, const float *b, int s) {
+CB_HD float dot_crm_S(const float *a, const float *b, int s) {  // a . crm(S) b
   float r = 0.0f;
-  const int n = s < 3 ? 4 : 2;
-  for (int k = 0; k < n; ++k) {
-    const Term t = crm_term(s, k);
-    r += (float)t.sg * a[t.i] * b[t.j];
+  switch (s) {
+    case 0:
+      r += -a[1] * b[2];
+      r += a[2] * b[1];
+      r += -a[4] * b[5];
+      r += a[5] * b[4];
+      break;
+    case 1:
+      r += a[0] * b[2];
+      r += -a[2] * b[0];
+      r += a[3] * b[5];
+      r += -a[5] * b[3];
+      break;
+    case 2:
+      r += -a[0] * b[1];
+      r += a[1] * b[0];
+      r += -a[3] * b[4];
+      r += a[4] * b[3];
+      break;
+    case 3:
+      r += -a[4] * b[2];
+      r += a[5] * b[1];
+      break;
+    case 4:
+      r += a[3] * b[2];
+      r += -a[5] * b[0];
+      break;
+    case 5:
+      r += -a[3] * b[1];
+      r += a[4] * b[0];
+      break;
+    default:
+      break;
   }
   return r;
+}
+CB_HD float pick6(const float *a, int s) {  // a[s] without dynamic register indexing
+  float r = a[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) r = (s == i) ? a[i] : r;
+  return r;
+}
+CB_HD void add6(float *a, int s, float x) {  // a[s] += x
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (s == i) a[i] += x;
 }
 CB_HD void force_cross_S_add(float *res, int s, float alpha, const float *b) {  // res += crf(S alpha) b
-  float e[6] = {0, 0, 0, 0, 0, 0}, t[6];
-  e[s] = alpha;
+  float e[6], t[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) e[i] = (s == i) ? alpha : 0.0f;
   force_cross(e, b, t);
 #pragma unroll
   for (int i = 0; i < 6; ++i) res[i] += t[i];
@@ -277,8 +362,8 @@ CB_HD void rnea_forward_row(const Model &M, Store &S, const float *q, const floa
     }
     if (j.jt >= 0) {
       const int s = s_index(j.jt);
-      v[s] += qd_eff;
-      a[s] += qdd_eff;
+      add6(v, s, qd_eff);
+      add6(a, s, qdd_eff);
       motion_cross_S_add(a, v, s, qd_eff);
     }
     store6(S, 0, k, v);
@@ -307,7 +392,7 @@ CB_HD void rnea_forward_row(const Model &M, Store &S, const float *q, const floa
       const JointRef j = joint_ref(M, k, q);
       float f[6];
       load6(S, 1, k, f);
-      if (j.moving) tau[j.ji] += j.mul * f[s_index(j.jt)];
+      if (j.moving) tau[j.ji] += j.mul * pick6(f, s_index(j.jt));
       if (!j.root) {
         const Rp t = local_Rp(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
         float c[6], fp[6];
@@ -351,7 +436,7 @@ CB_HD void rnea_backward_row(const Model &M, Store &S, const float *grad_tau, co
     const JointRef j = joint_ref(M, k, q);
     float fk[6], fbar[6] = {0, 0, 0, 0, 0, 0};
     load6(S, 2, k, fk);
-    if (j.moving) fbar[s_index(j.jt)] += j.mul * grad_tau[j.ji];
+    if (j.moving) add6(fbar, s_index(j.jt), j.mul * grad_tau[j.ji]);
     if (!j.root) {
       const Rp t = local_Rp(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
       float fp[6], X[6];
@@ -391,10 +476,10 @@ CB_HD void rnea_backward_row(const Model &M, Store &S, const float *grad_tau, co
       const int s = j.jt >= 0 ? s_index(j.jt) : 0;
       if (j.moving) {
         const float qd_k = j.mul * qd[j.ji];
-        gqdd[j.ji] += j.mul * ab[s];
+        gqdd[j.ji] += j.mul * pick6(ab, s);
         float fx[6];
         force_cross(v, ab, fx);
-        gqd[j.ji] -= j.mul * fx[s];
+        gqd[j.ji] -= j.mul * pick6(fx, s);
         force_cross_S_add(vb, s, qd_k, ab);
       }
       const Rp t = local_Rp(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
@@ -416,7 +501,7 @@ CB_HD void rnea_backward_row(const Model &M, Store &S, const float *grad_tau, co
         Xv(t, g, X);
         gq[j.ji] -= j.mul * dot_crm_S(ab, X, s);
       }
-      if (j.moving) gqd[j.ji] += j.mul * vb[s];
+      if (j.moving) gqd[j.ji] += j.mul * pick6(vb, s);
       if (!j.root) {
         float c[6], pv[6];
         XTf(t, vb, c);

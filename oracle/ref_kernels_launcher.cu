@@ -318,8 +318,11 @@ static int ref_rnea_bwd_t(float *gq, float *gqd, float *gqdd, const float *gtau,
   const int shared_block = NL * 12 * 4, per = NL * 30 * 4;
   int bpb = (48 * 1024 - shared_block) / per;
   if (bpb > 64) bpb = 64;
-  if (bpb >= 32) bpb = bpb / 32 * 32;
   if (bpb < 1) return 1;
+  // The reference kernel returns its out-of-range threads BEFORE the block-wide load of the inertial parameters into shared
+  // memory (rnea_backward_kernel.cuh:94 vs :142-161), so a partially filled last block reads unloaded parameters for some
+  // links. The checker therefore only launches full blocks: the largest block size that divides the batch.
+  while (B % bpb) bpb--;
   const int blocks = (B + bpb - 1) / bpb;
   cdy::rnea_backward_kernel<NL, ND, 1, false><<<blocks, bpb, (size_t)shared_block + (size_t)bpb * per, stream>>>(
       gq, gqd, gqdd, nullptr, gtau, q, qd, fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, lstarts, llinks, cache, B,
