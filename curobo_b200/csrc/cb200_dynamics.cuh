@@ -36,13 +36,7 @@ struct Model {  // robot constants (device or host pointers)
   int nl, D, n_levels;
 };
 
-CB_HD float ld(const float *p) {
-#ifdef __CUDA_ARCH__
-  return __ldg(p);
-#else
-  return *p;
-#endif
-}
+CB_HD float ld(const float *p) { return *p; }  // robot constants: global memory (row kernels) or the CTA's staged copy
 
 CB_HD int s_index(int jt) { return jt >= 3 ? jt - 3 : 3 + jt; }
 

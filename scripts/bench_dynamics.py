@@ -31,7 +31,11 @@ def timed(fn, flush, iters=20, warm=3):
 
 def main():
     flush = torch.zeros(160 * 1024 * 1024 // 4, device=DEV)
-    for robot, B in (("franka", 16384), ("franka", 30720), ("g1_29", 30720)):
+    cases = (("franka", 16384), ("franka", 30720), ("g1_29", 30720))
+    if "--only" in sys.argv:
+        name = sys.argv[sys.argv.index("--only") + 1]
+        cases = tuple(c for c in cases if c[0] == name)[:1]
+    for robot, B in cases:
         c = make_case(robot, 64, 1)
         rep = B // 64
         m = model_args(c)
@@ -46,11 +50,18 @@ def main():
         # algorithmic bytes: forward reads q,qd,qdd and writes tau + the cache; the adjoint reads grad_tau,q,qd,cache, writes 3 grads
         fb = B * 4 * (4 * D + nl * 20); bb = B * 4 * (6 * D + nl * 20)
         out.update(forward_GBps=fb / ours_f / 1e6, backward_GBps=bb / ours_b / 1e6)
-        if ref_kernels.available():
-            rt, rc = ref_kernels.rnea_forward(model, q, qd, qdd, nl, D, nlev)
-            out["ref_forward_ms"] = timed(lambda: ref_kernels.rnea_forward(model, q, qd, qdd, nl, D, nlev), flush)
-            out["ref_backward_ms"] = timed(lambda: ref_kernels.rnea_backward(model, gt, q, qd, rc, nl, D, nlev), flush)
-            out["note"] = "reference timings include its output allocation+memset (the reference zeroes its gradients per call too)"
+        if ref_kernels.available() and "--no-ref" not in sys.argv:
+            rtau, rcache = torch.zeros_like(tau), torch.zeros_like(cache)
+            rg = [torch.zeros_like(x) for x in g]
+
+            def ref_bwd():  # the reference accumulates into its gradients: its host zeroes them every call
+                for x in rg:
+                    x.zero_()
+                ref_kernels.rnea_backward(model, gt, q, qd, rcache, nl, D, nlev, out=rg)
+
+            out["ref_forward_ms"] = timed(lambda: ref_kernels.rnea_forward(model, q, qd, qdd, nl, D, nlev, out=(rtau, rcache)), flush)
+            out["ref_backward_ms"] = timed(ref_bwd, flush)
+            out["note"] = "reference kernels, serial path, preallocated outputs; its backward includes the three gradient memsets it needs"
         print(json.dumps(out))
 
 

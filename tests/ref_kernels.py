@@ -151,21 +151,24 @@ def line_search(st, search_cost, search_action, search_gradient, step_direction,
 # ------------------------------------------------------------------------------------------------
 # RNEA kernels of the reference (kernels/dynamics/), serial path
 # ------------------------------------------------------------------------------------------------
-def rnea_forward(model, q, qd, qdd, nl, D, n_levels):
+def rnea_forward(model, q, qd, qdd, nl, D, n_levels, out=None):
     """model = (fixed, mc, inertia, jtype, jmap, lmap, joff, gravity, level_starts, level_links) device tensors."""
     dev = q.device
     B = q.shape[0]
-    tau = torch.zeros((B, D), dtype=torch.float32, device=dev)
-    cache = torch.zeros((B, nl * 20), dtype=torch.float32, device=dev)
+    if out is not None:
+        tau, cache = out
+    else:
+        tau = torch.zeros((B, D), dtype=torch.float32, device=dev)
+        cache = torch.zeros((B, nl * 20), dtype=torch.float32, device=dev)
     err = lib().ref_rnea_forward(_p(tau), _p(q), _p(qd), _p(qdd), *[_p(m) for m in model], _p(cache), B, nl, D, n_levels, _stream(dev))
     assert err == 0, err
     return tau, cache
 
 
-def rnea_backward(model, grad_tau, q, qd, cache, nl, D, n_levels):
+def rnea_backward(model, grad_tau, q, qd, cache, nl, D, n_levels, out=None):
     dev = q.device
     B = q.shape[0]
-    g = [torch.zeros((B, D), dtype=torch.float32, device=dev) for _ in range(3)]
+    g = out if out is not None else [torch.zeros((B, D), dtype=torch.float32, device=dev) for _ in range(3)]
     err = lib().ref_rnea_backward(*[_p(x) for x in g], _p(grad_tau), _p(q), _p(qd), *[_p(m) for m in model], _p(cache), B, nl, D,
                                   n_levels, _stream(dev))
     assert err == 0, err

@@ -95,3 +95,57 @@ def test_dynamics_operator_autograd_and_graph():
     assert torch.equal(t1, t2)
     with pytest.raises(ValueError):
         Dynamics(c["rm"], c["mc"], c["inn"], device="cpu")
+
+
+@pytest.mark.parametrize("robot,B", [("franka", 2), ("g1_29", 37)])
+def test_rnea_external_wrenches(robot, B):
+    """f_ext enters f = I a + v x* I v - f_ext (rnea_forward_kernel.cuh:206-216); tau is linear in it, so grad_f_ext of
+    <grad_tau, tau> is checked exactly (to rounding) by differencing the oracle along a few wrench components."""
+    c = make_case(robot, B, 11)
+    model = dev_model(c)
+    m = model_args(c)
+    nl, D, nlev = c["nl"], c["D"], c["n_levels"]
+    rng = np.random.default_rng(5)
+    fe = rng.normal(size=(B, nl, 6)).astype(np.float32) * 3.0
+    q, qd, qdd, gt = T(c["q"]), T(c["qd"]), T(c["qdd"]), T(c["grad_tau"])
+    tau = torch.zeros((B, D), device=DEV)
+    cache = torch.zeros((B, nl * 20), device=DEV)
+    dynamics_cu.launch_rnea_forward(tau, q, qd, qdd, *model, cache, B, nl, D, nlev, f_ext=T(fe))
+    tau_w, cache_w = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m, f_ext=fe)
+    close(tau.cpu().numpy(), tau_w, 1e-4, "tau with f_ext")
+    g = [torch.zeros((B, D), device=DEV) for _ in range(3)]
+    gfe = torch.full((B, nl, 6), float("nan"), device=DEV)
+    dynamics_cu.launch_rnea_backward(*g, gt, q, qd, *model, cache, B, nl, D, nlev, grad_f_ext=gfe)
+    want = do.rnea_backward(c["grad_tau"], c["q"], c["qd"], cache_w, *m)
+    for got, w in zip(g, want):
+        close(got.cpu().numpy(), w, 3e-4, "grads with f_ext")
+    got = gfe.cpu().numpy()
+    assert np.isfinite(got).all()
+    tau0 = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m)[0].astype(np.float64)
+    for k, i in [(nl - 1, 0), (nl - 1, 4), (nl // 2, 2), (1, 5), (0, 3)]:
+        e = np.zeros((B, nl, 6), np.float32)
+        e[:, k, i] = 1.0
+        dt = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m, f_ext=e)[0].astype(np.float64) - tau0
+        w = (c["grad_tau"].astype(np.float64) * dt).sum(-1)
+        assert np.allclose(got[:, k, i], w, rtol=2e-3, atol=2e-3 * max(1.0, np.abs(w).max())), (k, i, got[:, k, i], w)
+
+
+def test_rnea_row_kernels_match_cta_kernels(monkeypatch):
+    """CB200_RNEA_ROWS=1 selects the thread-per-row kernels (the path for trees too large for the CTA tile)."""
+    c = make_case("g1_29", 77, 13)
+    model = dev_model(c)
+    nl, D, nlev, B = c["nl"], c["D"], c["n_levels"], 77
+    q, qd, qdd, gt = T(c["q"]), T(c["qd"]), T(c["qdd"]), T(c["grad_tau"])
+    outs = []
+    for rows in (False, True):
+        if rows:
+            monkeypatch.setenv("CB200_RNEA_ROWS", "1")
+        tau = torch.zeros((B, D), device=DEV)
+        cache = torch.zeros((B, nl * 20), device=DEV)
+        dynamics_cu.launch_rnea_forward(tau, q, qd, qdd, *model, cache, B, nl, D, nlev)
+        g = [torch.zeros((B, D), device=DEV) for _ in range(3)]
+        dynamics_cu.launch_rnea_backward(*g, gt, q, qd, *model, cache, B, nl, D, nlev)
+        torch.cuda.synchronize()
+        outs.append([tau.cpu().numpy(), cache.cpu().numpy()] + [x.cpu().numpy() for x in g])
+    for a_, b_ in zip(*outs):
+        close(a_, b_, 2e-5, "row kernels vs CTA kernels")
