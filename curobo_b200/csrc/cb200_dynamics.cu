@@ -31,7 +31,6 @@ struct TileStore {  // [arr][link][comp][rows] floats in shared memory
 
 struct FwdArgs {
   Model M;
-  int stage;
   float *tau, *cache;
   const float *q, *qd, *qdd, *f_ext;
   int B;
@@ -47,7 +46,6 @@ __global__ void rnea_forward_rows(const __grid_constant__ FwdArgs a) {
 
 struct BwdArgs {
   Model M;
-  int stage;
   float *gq, *gqd, *gqdd, *grad_f_ext;
   const float *grad_tau, *q, *qd, *cache;
   int B;
@@ -97,6 +95,7 @@ __device__ __forceinline__ Model stage_model(const Model &G, float *dst) {
 }
 inline int model_smem_floats_host(int nl, int n_levels) { return (12 + 4 + 8 + 2) * nl + 6 + (3 * nl + n_levels + 2) / 2 + (nl + 3) / 4; }
 
+template <class L>
 struct Cta {
   float *T, *SC, *IO;
   int nl, D, RS, r, w;
@@ -113,14 +112,14 @@ struct Cta {
   __device__ __forceinline__ float &io(int arr, int d) const { return IO[(arr * D + d) * RS + r]; }
   __device__ __forceinline__ Rp rp(int k, int jt) const {  // local transform of link k from the staged sin/cos (or travel)
     const float x = SC[(k * 2 + 0) * RS + r], c = SC[(k * 2 + 1) * RS + r];
-    return local_Rp_sc(M.fixed_transforms + 12 * k, jt, x, c, x);
+    return local_Rp_sc<L>(M.fixed_transforms + 12 * k, jt, x, c, x);
   }
   // sin/cos (revolute) or travel (prismatic) of every link of this row; q staged in io(0, .)
   __device__ __forceinline__ void stage_joint_angles(int W) const {
     for (int k = w; k < nl; k += W) {
       const int jt = M.joint_type[k], ji = M.joint_map[k];
       float qe = 0.0f, sn = 0.0f, cs = 1.0f;
-      if (jt >= 0 && ji >= 0) qe = ld(M.joint_offset + 2 * k) * io(0, ji) + ld(M.joint_offset + 2 * k + 1);
+      if (jt >= 0 && ji >= 0) qe = L::f(M.joint_offset + 2 * k) * io(0, ji) + L::f(M.joint_offset + 2 * k + 1);
       if (jt >= 3) sincosf(qe, &sn, &cs);
       SC[(k * 2 + 0) * RS + r] = jt >= 3 ? sn : qe;
       SC[(k * 2 + 1) * RS + r] = cs;
@@ -130,15 +129,16 @@ struct Cta {
 
 template <int R>
 __global__ void __launch_bounds__(kThreads) rnea_forward_cta(const __grid_constant__ FwdArgs a) {
+  using L = LdPlain;  // constants staged into shared memory
   constexpr int RS = R + 1, W = kThreads / R;
   extern __shared__ __align__(16) float smem[];
   const int nl = a.M.nl, D = a.M.D;
-  const Model M = a.stage ? stage_model(a.M, smem + ((2 * 6 + 2) * nl + 4 * D) * RS) : a.M;
-  Cta S{smem, smem + 2 * nl * 6 * RS, smem + (2 * 6 + 2) * nl * RS, nl, D, RS, (int)threadIdx.x % R, (int)threadIdx.x / R, M};
+  const Model M = stage_model(a.M, smem + ((2 * 6 + 2) * nl + 4 * D) * RS);
+  Cta<L> S{smem, smem + 2 * nl * 6 * RS, smem + (2 * 6 + 2) * nl * RS, nl, D, RS, (int)threadIdx.x % R, (int)threadIdx.x / R, M};
   __syncthreads();
   float g[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) g[i] = ld(M.gravity + i);
+  for (int i = 0; i < 6; ++i) g[i] = L::f(M.gravity + i);
   for (long long row0 = (long long)blockIdx.x * R; row0 < a.B; row0 += (long long)gridDim.x * R) {
     const int nrows = (int)((a.B - row0) < R ? (a.B - row0) : R);
     const bool live = S.r < nrows;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads) rnea_forward_cta(const __grid_consta
       for (int idx = M.level_starts[lv] + S.w; idx < M.level_starts[lv + 1]; idx += W) {
         const int k = M.level_links[idx], jt = M.joint_type[k], ji = M.joint_map[k], par = M.link_map[k];
         const bool root = (par < 0) || (par == k), moving = (jt >= 0) && (ji >= 0);
-        const float mul = moving ? ld(M.joint_offset + 2 * k) : 1.0f;
+        const float mul = moving ? L::f(M.joint_offset + 2 * k) : 1.0f;
         const float qd_eff = moving ? mul * S.io(1, ji) : 0.0f, qdd_eff = moving ? mul * S.io(2, ji) : 0.0f;
         const Rp t = S.rp(k, jt);
         float v[6], ac[6], tmp[6];
@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(kThreads) rnea_forward_cta(const __grid_consta
         ck[1] = make_float4(v[4], v[5], ac[0], ac[1]);
         ck[2] = make_float4(ac[2], ac[3], ac[4], ac[5]);
       }
-      inertia_times(M.masses_com + 4 * k, M.inertias + 8 * k, ac, Ia);
-      inertia_times(M.masses_com + 4 * k, M.inertias + 8 * k, v, Iv);
+      inertia_times<L>(M.masses_com + 4 * k, M.inertias + 8 * k, ac, Ia);
+      inertia_times<L>(M.masses_com + 4 * k, M.inertias + 8 * k, v, Iv);
       force_cross(v, Iv, x);
       const float *fe = (a.f_ext != nullptr && live) ? a.f_ext + ((size_t)(row0 + S.r) * nl + k) * 6 : nullptr;
 #pragma unroll
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) rnea_forward_cta(const __grid_consta
         ck[1] = make_float4(f[4], f[5], 0.0f, 0.0f);
       }
       const int jt = M.joint_type[k], ji = M.joint_map[k];
-      if (jt >= 0 && ji >= 0) atomicAdd(&S.io(3, ji), ld(M.joint_offset + 2 * k) * pick6(f, s_index(jt)));
+      if (jt >= 0 && ji >= 0) atomicAdd(&S.io(3, ji), L::f(M.joint_offset + 2 * k) * pick6(f, s_index(jt)));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nrows * D; i += kThreads) {
@@ -246,15 +246,15 @@ __global__ void __launch_bounds__(kThreads) rnea_forward_cta(const __grid_consta
 
 template <int R>
 __global__ void __launch_bounds__(kThreads) rnea_backward_cta(const __grid_constant__ BwdArgs a) {
+  using L = LdNc;  // constants read in place through the read-only path (measured faster than staging for the adjoint)
   constexpr int RS = R + 1, W = kThreads / R;
   extern __shared__ __align__(16) float smem[];
   const int nl = a.M.nl, D = a.M.D;
-  const Model M = a.stage ? stage_model(a.M, smem + ((5 * 6 + 2) * nl + 6 * D) * RS) : a.M;
-  Cta S{smem, smem + 5 * nl * 6 * RS, smem + (5 * 6 + 2) * nl * RS, nl, D, RS, (int)threadIdx.x % R, (int)threadIdx.x / R, M};
-  __syncthreads();
+  const Model &M = a.M;
+  Cta<L> S{smem, smem + 5 * nl * 6 * RS, smem + (5 * 6 + 2) * nl * RS, nl, D, RS, (int)threadIdx.x % R, (int)threadIdx.x / R, M};
   float g[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) g[i] = ld(M.gravity + i);
+  for (int i = 0; i < 6; ++i) g[i] = L::f(M.gravity + i);
   for (long long row0 = (long long)blockIdx.x * R; row0 < a.B; row0 += (long long)gridDim.x * R) {
     const int nrows = (int)((a.B - row0) < R ? (a.B - row0) : R);
     const bool live = S.r < nrows;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kThreads) rnea_backward_cta(const __grid_const
       for (int idx = M.level_starts[lv] + S.w; idx < M.level_starts[lv + 1]; idx += W) {
         const int k = M.level_links[idx], jt = M.joint_type[k], ji = M.joint_map[k], par = M.link_map[k];
         const bool root = (par < 0) || (par == k), moving = (jt >= 0) && (ji >= 0);
-        const float mul = moving ? ld(M.joint_offset + 2 * k) : 1.0f;
+        const float mul = moving ? L::f(M.joint_offset + 2 * k) : 1.0f;
         const int s = jt >= 0 ? s_index(jt) : 0;
         float fk[6], fbar[6] = {0, 0, 0, 0, 0, 0}, gq1 = 0.0f;
         S.load(2, k, fk);
@@ -318,13 +318,13 @@ __global__ void __launch_bounds__(kThreads) rnea_backward_cta(const __grid_const
 #pragma unroll
         for (int i = 0; i < 6; ++i) ge[i] = -fbar[i];
       }
-      inertia_times(mc, in, fbar, ab);  // a_bar += I f_bar
-      inertia_times(mc, in, v, t1);
+      inertia_times<L>(mc, in, fbar, ab);  // a_bar += I f_bar
+      inertia_times<L>(mc, in, v, t1);
       force_cross(fbar, t1, t2);  // v_bar -= crf(f_bar) I v
 #pragma unroll
       for (int i = 0; i < 6; ++i) vb[i] = 0.0f - t2[i];
       motion_cross(v, fbar, t1);
-      inertia_times(mc, in, t1, t2);  // v_bar -= I crm(v) f_bar
+      inertia_times<L>(mc, in, t1, t2);  // v_bar -= I crm(v) f_bar
 #pragma unroll
       for (int i = 0; i < 6; ++i) vb[i] -= t2[i];
       S.store(3, k, ab);
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(kThreads) rnea_backward_cta(const __grid_const
           ab[i] += x[i];
           vb[i] += y[i];
         }
-        if (jt >= 0 && ji >= 0) force_cross_S_add(vb, s_index(jt), ld(M.joint_offset + 2 * k) * S.io(1, ji), ab);
+        if (jt >= 0 && ji >= 0) force_cross_S_add(vb, s_index(jt), L::f(M.joint_offset + 2 * k) * S.io(1, ji), ab);
         S.store(3, k, ab);
         S.store(4, k, vb);
       }
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kThreads) rnea_backward_cta(const __grid_const
       const int jt = M.joint_type[k], ji = M.joint_map[k], par = M.link_map[k];
       if (jt < 0 || ji < 0) continue;
       const bool root = (par < 0) || (par == k);
-      const float mul = ld(M.joint_offset + 2 * k);
+      const float mul = L::f(M.joint_offset + 2 * k);
       const int s = s_index(jt);
       float v[6], ab[6], vb[6], fx[6], X[6], u[6];
       S.load(0, k, v);
@@ -441,10 +441,6 @@ bool allow_smem(K kern, int smem) {
   (void)cudaGetLastError();
   return false;
 }
-inline int stage_knob() {
-  const char *e = getenv("CB200_RNEA_STAGE");
-  return e == nullptr ? 1 : atoi(e);
-}
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // rows per CTA: the largest of 128 / 64 / 32 whose tile leaves room for two CTAs per SM
@@ -494,7 +490,7 @@ int cb200_rnea_forward(float *tau, const float *q, const float *qd, const float 
       batch_size < 0)
     return status(cudaErrorInvalidValue);
   if (batch_size == 0) return status(cudaSuccess);
-  FwdArgs a{M, stage_knob(), tau, forward_cache, q, qd, qdd, f_ext, batch_size};
+  FwdArgs a{M, tau, forward_cache, q, qd, qdd, f_ext, batch_size};
   const CtaPlan p = plan_cta(batch_size, (2 * 6 + 2) * num_links + 4 * num_dof, model_smem_floats_host(num_links, n_levels), false);
   if (p.R != 0 && aligned16(forward_cache) && getenv("CB200_RNEA_ROWS") == nullptr) {
     const cudaStream_t st = (cudaStream_t)stream;
@@ -528,8 +524,8 @@ int cb200_rnea_backward(float *grad_q, float *grad_qd, float *grad_qdd, const fl
       qd == nullptr || forward_cache == nullptr || batch_size < 0)
     return status(cudaErrorInvalidValue);
   if (batch_size == 0) return status(cudaSuccess);
-  BwdArgs a{M, stage_knob(), grad_q, grad_qd, grad_qdd, grad_f_ext, grad_tau, q, qd, forward_cache, batch_size};
-  const CtaPlan p = plan_cta(batch_size, (5 * 6 + 2) * num_links + 6 * num_dof, model_smem_floats_host(num_links, n_levels), true);
+  BwdArgs a{M, grad_q, grad_qd, grad_qdd, grad_f_ext, grad_tau, q, qd, forward_cache, batch_size};
+  const CtaPlan p = plan_cta(batch_size, (5 * 6 + 2) * num_links + 6 * num_dof, 0, true);
   if (p.R != 0 && aligned16(forward_cache) && getenv("CB200_RNEA_ROWS") == nullptr) {
     const cudaStream_t st = (cudaStream_t)stream;
     if (p.R == 32 && allow_smem(rnea_backward_cta<32>, p.smem)) {

@@ -36,7 +36,22 @@ struct Model {  // robot constants (device or host pointers)
   int nl, D, n_levels;
 };
 
-CB_HD float ld(const float *p) { return *p; }  // robot constants: global memory (row kernels) or the CTA's staged copy
+// How the robot's constants are read: through the read-only (non-coherent) path when they sit in global memory -- the
+// compiler may then hoist and reorder those loads across the shared-memory traffic of the recursion -- or as plain loads
+// when a CTA has staged them into shared memory.
+struct LdNc {
+  static CB_HD float f(const float *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+  }
+};
+struct LdPlain {
+  static CB_HD float f(const float *p) { return *p; }
+};
+CB_HD float ld(const float *p) { return LdNc::f(p); }
 
 CB_HD int s_index(int jt) { return jt >= 3 ? jt - 3 : 3 + jt; }
 
@@ -46,11 +61,12 @@ struct Rp {
 
 // fixed * J(angle): rotation (row-major) and translation  (rnea_helpers.cuh:25-95).  sn / cs = sin / cos of the angle for a
 // revolute joint (computed by the caller: the CTA kernels take them off the serial chain); angle is the prismatic travel.
+template <class L = LdNc>
 CB_HD Rp local_Rp_sc(const float *ft, int jt, float sn, float cs, float angle) {
   Rp o;
   float f[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) f[i] = ld(ft + i);
+  for (int i = 0; i < 12; ++i) f[i] = L::f(ft + i);
   o.p[0] = f[3];
   o.p[1] = f[7];
   o.p[2] = f[11];
@@ -278,9 +294,10 @@ CB_HD void force_cross_S_add(float *res, int s, float alpha, const float *b) {  
 }
 
 // spatial inertia about the link origin times a motion vector (spatial_algebra.cuh:129-163)
+template <class L = LdNc>
 CB_HD void inertia_times(const float *mc, const float *in, const float *u, float *r) {
-  const float cx = ld(mc), cy = ld(mc + 1), cz = ld(mc + 2), m = ld(mc + 3);
-  const float ixx = ld(in), iyy = ld(in + 1), izz = ld(in + 2), ixy = ld(in + 3), ixz = ld(in + 4), iyz = ld(in + 5);
+  const float cx = L::f(mc), cy = L::f(mc + 1), cz = L::f(mc + 2), m = L::f(mc + 3);
+  const float ixx = L::f(in), iyy = L::f(in + 1), izz = L::f(in + 2), ixy = L::f(in + 3), ixz = L::f(in + 4), iyz = L::f(in + 5);
   const float w0 = u[0], w1 = u[1], w2 = u[2];
   const float h0 = u[3] + w1 * cz - w2 * cy;
   const float h1 = u[4] + w2 * cx - w0 * cz;
