@@ -175,6 +175,54 @@ def ik_solve_bench(device, problems=512, seeds=32, iters=100, repeats=5):
 # ------------------------------------------------------------------------------------------------
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
+def rnea_bench(device, peak, cases=(("franka", 16384), ("franka", 30720), ("g1_29", 30720)), iters=20):
+    """RNEA inverse dynamics + adjoint over (seed x waypoint) rows, through the backend module
+    (C ABI). Inputs resident in HBM, a 160 MB write between iterations flushes L2, CUDA events on the launching stream.
+    Inertial parameters are synthetic (random, physically plausible); the kinematic trees are the real robots'."""
+    from curobo_b200.backends import dynamics as dynamics_cu
+    from curobo_b200.dynamics import tree_levels
+    from curobo_b200.robot_model import load_robot
+    out = {}
+    flush = torch.zeros(160 * 1024 * 1024 // 4, device=device)
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).to(device)  # noqa: E731
+    for robot, B in cases:
+        rm = load_robot(robot)
+        nl, D = rm.num_links, rm.num_dof
+        rng = np.random.default_rng(7)
+        mc = np.concatenate([rng.uniform(-0.05, 0.05, (nl, 3)), rng.uniform(0.2, 3.0, (nl, 1))], 1)
+        inn = np.zeros((nl, 8))
+        inn[:, :3] = rng.uniform(0.002, 0.01, (nl, 3))
+        starts, order = tree_levels(rm.link_map)
+        model = (t(rm.fixed_transforms, np.float32), t(mc, np.float32), t(inn, np.float32), t(rm.joint_map_type, np.int8),
+                 t(rm.joint_map, np.int16), t(rm.link_map, np.int16), t(rm.joint_offset_map, np.float32),
+                 t([0, 0, 0, 0, 0, 9.81], np.float32), t(starts, np.int16), t(order, np.int16))
+        nlev = len(starts) - 1
+        q, qd, qdd, gt = (t(rng.uniform(-1.5, 1.5, (B, D)), np.float32) for _ in range(4))
+        tau = torch.zeros((B, D), device=device)
+        cache = torch.zeros((B, nl * 20), device=device)
+        g = [torch.zeros((B, D), device=device) for _ in range(3)]
+        fwd = lambda: dynamics_cu.launch_rnea_forward(tau, q, qd, qdd, *model, cache, B, nl, D, nlev)  # noqa: E731
+        bwd = lambda: dynamics_cu.launch_rnea_backward(*g, gt, q, qd, *model, cache, B, nl, D, nlev)  # noqa: E731
+        res = {}
+        for name, fn, nbytes in (("forward", fwd, B * 4 * (4 * D + nl * 20)), ("backward", bwd, B * 4 * (6 * D + nl * 20))):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(iters):
+                flush.add_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
+            res[name] = {"kernel_ms": ms, "rows_per_s": B / (ms * 1e-3), "bytes_per_row": nbytes // B,
+                         "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+        out[f"{robot}_{B}"] = res
+    return out
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -343,6 +391,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ik-solve", type=int, default=1,
                     help="1: also time a complete 100-iteration L-BFGS IK solve (512 goals x 32 seeds), reported under 'ik_solve'")
+    ap.add_argument("--rnea", type=int, default=1, help="1: also time the RNEA inverse-dynamics kernels, reported under 'rnea'")
     ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,franka_mpc_knots_1024x30_esdf_swept,franka_mpc_knots_inkernel_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
                     help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
     args = ap.parse_args()
@@ -511,6 +560,11 @@ def main():
                     line["ik_solve"] = ik_solve_bench(device)
                 except Exception as ex:                                               # noqa: BLE001
                     line["ik_solve"] = {"error": repr(ex)}
+            if args.rnea:
+                try:
+                    line["rnea"] = rnea_bench(device, peak)
+                except Exception as ex:                                               # noqa: BLE001
+                    line["rnea"] = {"error": repr(ex)}
             if not args.no_cpu_baseline:
                 v, cores, sample = cpu_baseline(args.workload, target_seconds=12.0, procs=1)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
