@@ -179,6 +179,7 @@ def rnea_bench(device, peak, cases=(("franka", 16384), ("franka", 30720), ("g1_2
     """RNEA inverse dynamics + adjoint over (seed x waypoint) rows, through the backend module
     (C ABI). Inputs resident in HBM, a 160 MB write between iterations flushes L2, CUDA events on the launching stream.
     Inertial parameters are synthetic (random, physically plausible); the kinematic trees are the real robots'."""
+    import torch
     from curobo_b200.backends import dynamics as dynamics_cu
     from curobo_b200.dynamics import tree_levels
     from curobo_b200.robot_model import load_robot
