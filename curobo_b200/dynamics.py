@@ -83,3 +83,72 @@ class Dynamics:
         if q2.shape[0] > self._n:
             self.setup_batch_size(q2.shape[0])
         return RNEAFunction.apply(q2, qd2, qdd2, self).view(shape)
+
+
+class DynamicsStateCost:
+    """The dynamics-aware STATE c-space cost, unfused: what `RobotStateTransition.compute_augmented_state`
+    (transition/robot_state_transition.py:380-389: joint_torque = robot_dynamics.compute_inverse_dynamics(state)) followed
+    by `StateCSpaceFunction` (cost/wp_cspace_state.py:21-285, effort channel: bound hinge, squared-L2 and the energy term
+    (tau qd dt)^2) and autograd's walk back through the RNEA adjoint compute -- as three launches and three in-place adds,
+    no autograd graph, CUDA-graph capturable:
+
+        tau = RNEA(q, qd, qdd)                                   cb200_rnea_forward
+        cost, g_p, g_v, g_a, g_j, g_tau = cspace_state(...)      cb200_cspace_state_cost
+        g_p, g_v, g_a += RNEA^T(g_tau)                           cb200_rnea_backward
+
+    All tensors [batch, horizon, dof]; `limits` = dict p / v / a / j / tau -> [2, dof] device tensors; weight,
+    activation_distance, reg_weights are the five-element vectors of the reference's cost config.
+    """
+
+    def __init__(self, dynamics: Dynamics, limits: dict, weight, activation_distance, reg_weights,
+                 retime_weights: bool = True, retime_regularization_weights: bool = True):
+        from . import cost as _cost
+        self._cost = _cost
+        self.dyn = dynamics
+        dev = dynamics.device
+        f = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, np.float32))).to(dev)  # noqa: E731
+        self.limits = {k: f(v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in limits.items()}
+        self.weight, self.act, self.reg = f(weight), f(activation_distance), f(reg_weights)
+        self.retime_w, self.retime_r = bool(retime_weights), bool(retime_regularization_weights)
+        D = dynamics.num_dof
+        self._zero_w, self._one = f([0.0]), f([1.0])
+        self._dof_w = f(np.ones(D))
+        self._target = f(np.zeros((1, D)))
+        self._shape = None
+
+    def _setup(self, shape):
+        B, H, D = shape
+        dev = self.dyn.device
+        z = lambda: torch.zeros(shape, dtype=torch.float32, device=dev)  # noqa: E731
+        self.out_cost, self.g_p, self.g_v, self.g_a, self.g_j, self.g_tau = (z() for _ in range(6))
+        self._idx = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.dyn.setup_batch_size(B, H)
+        self._shape = tuple(shape)
+
+    def evaluate(self, pos, vel, acc, jerk, state_dt, target_joint_position: Optional[torch.Tensor] = None,
+                 idxs_target: Optional[torch.Tensor] = None, target_weight: Optional[torch.Tensor] = None,
+                 non_terminal_factor: Optional[torch.Tensor] = None, target_dof_weight: Optional[torch.Tensor] = None):
+        """-> (cost [B,H,D], grad_p, grad_v, grad_a, grad_j, tau); buffers are reused between calls."""
+        if self._shape != tuple(pos.shape):
+            self._setup(pos.shape)
+        B, H, D = pos.shape
+        dyn, n = self.dyn, B * H
+        q2, qd2, qdd2 = (x.reshape(n, D) for x in (pos, vel, acc))
+        tau = dyn._tau[:n]
+        dynamics_cu.launch_rnea_forward(tau, q2, qd2, qdd2, *dyn._model, dyn._cache[:n], n, dyn.num_links, D, dyn.n_levels)
+        lim = self.limits
+        self._cost.cspace_state_cost(
+            pos, vel, acc, jerk, tau.view(B, H, D), state_dt,
+            self._target if target_joint_position is None else target_joint_position,
+            self._idx if idxs_target is None else idxs_target, lim["p"], lim["v"], lim["a"], lim["j"], lim["tau"],
+            self.weight, self.act, self.reg, self._zero_w if target_weight is None else target_weight,
+            self._one if non_terminal_factor is None else non_terminal_factor,
+            self._dof_w if target_dof_weight is None else target_dof_weight, self.out_cost, self.g_p, self.g_v, self.g_a,
+            self.g_j, self.g_tau, self.retime_w, self.retime_r)
+        gq, gqd, gqdd = dyn._gq[:n], dyn._gqd[:n], dyn._gqdd[:n]
+        dynamics_cu.launch_rnea_backward(gq, gqd, gqdd, self.g_tau.view(n, D), q2, qd2, *dyn._model, dyn._cache[:n], n,
+                                         dyn.num_links, D, dyn.n_levels)
+        self.g_p.view(n, D).add_(gq)
+        self.g_v.view(n, D).add_(gqd)
+        self.g_a.view(n, D).add_(gqdd)
+        return self.out_cost, self.g_p, self.g_v, self.g_a, self.g_j, tau.view(B, H, D)

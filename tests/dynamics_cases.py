@@ -42,3 +42,35 @@ def pack_cache(cache, nl):
 
 
 CASES = [("franka", 9, 1), ("g1_29", 5, 2), ("g1_43", 3, 3)]
+
+
+def effort_cost_oracle(c, shape, jerk, dt, limits, weight, act, reg):
+    """Dynamics-aware STATE cost composed from the two oracles: tau = RNEA(q, qd, qdd) feeds the effort channel of
+    cspace_state_cost; grad_tau walks back through the RNEA adjoint (robot_state_transition.py:380-389 +
+    wp_cspace_state.py:21-285).  Returns cost [B,H,D], (g_p, g_v, g_a, g_j), tau."""
+    from oracle import rollout_oracle as O
+    B, H, D = shape
+    m = model_args(c)
+    tau, cache = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m)
+    r = lambda x: np.asarray(x, np.float32).reshape(B, H, D)  # noqa: E731
+    cost, g = O.cspace_state_cost(r(c["q"]), r(c["qd"]), r(c["qdd"]), jerk, dt, limits, weight, act, reg, True, True,
+                                  effort=r(tau))
+    gq, gqd, gqdd = do.rnea_backward(g[4].reshape(B * H, D), c["q"], c["qd"], cache, *m)
+    return cost, (g[0] + r(gq), g[1] + r(gqd), g[2] + r(gqdd), g[3]), r(tau)
+
+
+def effort_cost_setup(robot="franka", B=6, H=5, seed=21):
+    c = make_case(robot, B * H, seed)
+    rm = c["rm"]
+    rng = np.random.default_rng(seed + 1)
+    D = c["D"]
+    jerk = rng.normal(0, 50.0, size=(B, H, D)).astype(np.float32)
+    dt = rng.uniform(0.02, 0.1, size=B).astype(np.float32)
+    tau0 = do.rnea_forward(c["q"], c["qd"], c["qdd"], *model_args(c))[0]
+    # effort limits placed inside the range of the torques of this case so that the hinge is active on a good fraction
+    elim = np.stack([np.quantile(tau0, 0.2, axis=0), np.quantile(tau0, 0.8, axis=0)]).astype(np.float32)
+    limits = dict(p=rm.position_limits, v=rm.velocity_limits, a=rm.acceleration_limits, j=rm.jerk_limits, tau=elim)
+    weight = np.array([5000.0, 500.0, 50.0, 5.0, 20.0], np.float32)
+    act = np.array([0.01, 0.01, 0.01, 0.01, 0.5], np.float32)
+    reg = np.array([10.0, 1.0, 0.01, 0.05, 0.3], np.float32)
+    return c, (B, H, D), jerk, dt, limits, weight, act, reg

@@ -83,3 +83,27 @@ def test_host_math_vs_oracle(robot, B, seed):
     got = hm_backward(c, cache)
     for g, w in zip(got, want):
         assert np.allclose(g, w, rtol=2e-4, atol=5e-5 * np.abs(w).max())
+
+
+def test_effort_cost_composition_gradient_by_finite_differences():
+    """tau = RNEA(q, qd, qdd) -> effort channel of the STATE cost -> RNEA adjoint: the composed gradient is the derivative
+    of the summed cost (float64 central differences along random directions of q, qd, qdd)."""
+    from dynamics_cases import effort_cost_oracle, effort_cost_setup
+    c, shape, jerk, dt, limits, weight, act, reg = effort_cost_setup(B=3, H=4)
+    cost, g, tau = effort_cost_oracle(c, shape, jerk, dt, limits, weight, act, reg)
+    assert (np.abs(g[0]).sum() > 0) and np.isfinite(cost).all()
+    # the effort hinge is active somewhere and the energy term contributes
+    assert ((tau < limits["tau"][0] + act[4]) | (tau > limits["tau"][1] - act[4])).mean() > 0.1
+    rng = np.random.default_rng(0)
+    for key, gi in (("q", 0), ("qd", 1), ("qdd", 2)):
+        d = rng.normal(size=c[key].shape)
+        d /= np.linalg.norm(d)
+        eps = 2e-3
+        vals = []
+        for sgn in (+1, -1):
+            c2 = dict(c)
+            c2[key] = (c[key].astype(np.float64) + sgn * eps * d).astype(np.float32)
+            vals.append(float(effort_cost_oracle(c2, shape, jerk, dt, limits, weight, act, reg)[0].astype(np.float64).sum()))
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        an = float((g[gi].reshape(d.shape).astype(np.float64) * d).sum())
+        assert abs(fd - an) <= 2e-2 * max(abs(an), abs(fd), 1.0), (key, fd, an)
