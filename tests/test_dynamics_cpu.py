@@ -98,7 +98,7 @@ def test_effort_cost_composition_gradient_by_finite_differences():
     for key, gi in (("q", 0), ("qd", 1), ("qdd", 2)):
         d = rng.normal(size=c[key].shape)
         d /= np.linalg.norm(d)
-        eps = 2e-3
+        eps = 1.6e-2  # the oracle is float32: smaller steps drown in the rounding of the summed cost
         vals = []
         for sgn in (+1, -1):
             c2 = dict(c)
@@ -106,4 +106,4 @@ def test_effort_cost_composition_gradient_by_finite_differences():
             vals.append(float(effort_cost_oracle(c2, shape, jerk, dt, limits, weight, act, reg)[0].astype(np.float64).sum()))
         fd = (vals[0] - vals[1]) / (2 * eps)
         an = float((g[gi].reshape(d.shape).astype(np.float64) * d).sum())
-        assert abs(fd - an) <= 2e-2 * max(abs(an), abs(fd), 1.0), (key, fd, an)
+        assert abs(fd - an) <= 1.5e-2 * max(abs(an), abs(fd), 1.0), (key, fd, an)
