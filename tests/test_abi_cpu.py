@@ -130,3 +130,36 @@ def test_cpu_tensors_are_refused():
     with pytest.raises(ValueError):
         geometry.self_collision_distance(t, t, t, t.to(torch.uint8), t, t, t, t.to(torch.int16), t, t.to(torch.int16),
                                          1, 64, 1, 1, 1, 1, False, True)
+
+
+def test_entry_points_reject_bad_arguments_before_touching_a_device(L):
+    """Error behaviour of the boundary (the reference launchers raise on bad arguments before launching,
+    cuda_core_backend/optimization.py:173-176, launch_helper.py:13-19): null pointers / out-of-range sizes return
+    cudaErrorInvalidValue (1) from the argument checks, which run before any CUDA call -- so this runs without a GPU."""
+    raw = C.CDLL(cblib.lib_path())
+    INVALID = 1
+    nul = C.c_void_p(None)
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    raw.cb200_rnea_forward.restype = C.c_int
+    raw.cb200_rnea_forward.argtypes = [C.c_void_p] * 15 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    assert raw.cb200_rnea_forward(*([nul] * 15), 4, 3, 2, 1, nul, nul) == INVALID          # null tensors
+    assert raw.cb200_rnea_forward(*([p] * 15), -1, 3, 2, 1, nul, nul) == INVALID           # negative batch
+    assert raw.cb200_rnea_forward(*([p] * 15), 4, 0, 2, 1, nul, nul) == INVALID            # no links
+    raw.cb200_rnea_backward.restype = C.c_int
+    raw.cb200_rnea_backward.argtypes = [C.c_void_p] * 17 + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    assert raw.cb200_rnea_backward(*([nul] * 17), 4, 3, 2, 1, nul, nul) == INVALID
+    raw.cb200_lbfgs_step.restype = C.c_int
+    raw.cb200_lbfgs_step.argtypes = ([C.c_void_p] * 8 + [C.c_float] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int, C.c_void_p,
+                                     C.c_int, C.c_int, C.c_void_p])
+    ok8 = [p] * 8
+    assert raw.cb200_lbfgs_step(*([nul] * 8), 0.01, 4, 7, 7, 1, nul, nul, nul, 0, nul, 0, 0, nul) == INVALID
+    assert raw.cb200_lbfgs_step(*ok8, 0.01, 4, 32, 7, 1, nul, nul, nul, 0, nul, 0, 0, nul) == INVALID    # history > 31
+    assert raw.cb200_lbfgs_step(*ok8, 0.01, 4, 7, 2000, 1, nul, nul, nul, 0, nul, 0, 0, nul) == INVALID  # v_dim > 1024
+    assert raw.cb200_lbfgs_step(*ok8, 0.01, 4, 7, 7, 1, p, p, nul, 4, nul, 0, 0, nul) == INVALID         # x_set without magnitudes
+    raw.cb200_rollout_cost_grad.restype = C.c_int
+    raw.cb200_rollout_cost_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    assert raw.cb200_rollout_cost_grad(nul, nul, nul) == INVALID
+    # the Python layer turns a non-zero status into an exception that names the call
+    with pytest.raises(cblib.CudaCallError, match="probe"):
+        cblib.check(INVALID, "probe")
