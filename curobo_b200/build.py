@@ -62,7 +62,7 @@ def build_product(force: bool = False, verbose: bool = False, minb: int = 0) -> 
            "-Xptxas", "-v" if verbose else "-O3", *([f"-DCB200_MINB={minb}"] if minb > 0 else []),
            "-o", out, "-lcudart"]
     # three translation units (rollout, trajectory and optimizer kernels), compiled concurrently then linked
-    units = ["cb200_kernels.cu", "cb200_trajectory.cu", "cb200_optim.cu", "cb200_dynamics.cu"]
+    units = ["cb200_kernels.cu", "cb200_trajectory.cu", "cb200_optim.cu", "cb200_dynamics.cu", "cb200_edt.cu"]
     objs = [os.path.join(LIBDIR, (u[:-3] + (f"_mb{minb}" if minb > 0 else "") + ".o")) for u in units]
     flags = [c for c in cmd[1:] if c not in ("-shared", "-o", out, "-lcudart")]
     procs = [subprocess.Popen([cmd[0], *flags, "-c", os.path.join(CSRC, u), "-o", o], stdout=subprocess.PIPE,
@@ -82,7 +82,7 @@ def build_product(force: bool = False, verbose: bool = False, minb: int = 0) -> 
 def build_hostmath(force: bool = False, verbose: bool = False) -> str:
     src = os.path.join(ROOT, "tests", "hostmath", "cb200_hostmath.cu")
     deps = [src, os.path.join(CSRC, "cb200_math.cuh"), os.path.join(CSRC, "cb200_bspline.cuh"),
-            os.path.join(CSRC, "cb200_dynamics.cuh")]
+            os.path.join(CSRC, "cb200_dynamics.cuh"), os.path.join(CSRC, "cb200_edt.cuh")]
     if not force and _newer(HOSTMATH_SO, deps):
         return HOSTMATH_SO
     cmd = [_nvcc(), "-std=c++17", "-O2", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared", src, "-o", HOSTMATH_SO,
@@ -106,7 +106,7 @@ def build_reference_kernels(force: bool = False, verbose: bool = False):
            "-I", os.path.join(kdir, "kinematics"), "-I", os.path.join(kdir, "geometry", "self_collision"),
            "-I", os.path.join(kdir, "trajectory"), "-I", os.path.join(kdir, "trajectory", "bspline"),
            "-I", os.path.join(kdir, "optimization", "lbfgs"), "-I", os.path.join(kdir, "optimization", "line_search"),
-           "-I", os.path.join(kdir, "dynamics"),
+           "-I", os.path.join(kdir, "dynamics"), "-I", os.path.join(kdir, "parallel_banding"),
            src, "-o", REF_SO, "-lcudart"]
     _run(cmd, verbose)
     return REF_SO

@@ -1,0 +1,70 @@
+"""Host mirror of the reference's exact Euclidean distance transform operator.
+
+  ParallelBandingEDT  <- curobo/_src/perception/mapper/esdf/edt_parallel_banding.py:21-80 (same constructor and
+                         `propagate(site_index)`; the class keeps the reference's name although the kernels underneath are a
+                         three-pass in-place transform, not PBA+)
+  seed_sites_from_occupancy / unsigned_distance: the steps either side of `propagate` in
+                         BlockSparseESDFIntegrator._compute_esdf_impl (integrator_esdf.py:692-704) for a dense occupancy
+                         grid -- the reference seeds from its block-sparse TSDF and signs the distance with it; both need
+                         the TSDF hash, which is out of scope.
+CUDA only.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from .backends import pba as pba_cu
+
+MAX_DIM = 1023  # 10-bit packed coordinates (perception/mapper/util/utils_quantization.py:33-34)
+
+
+def validate_grid_size(grid_shape: Tuple[int, int, int], class_name: str) -> int:
+    """esdf/kernel/wp_jfa.py:28-38, plus the 10-bit coordinate limit of the packing."""
+    nx, ny, nz = (int(v) for v in grid_shape)
+    n = nx * ny * nz
+    if min(nx, ny, nz) < 1 or max(nx, ny, nz) > MAX_DIM:
+        raise ValueError(f"{class_name}: grid dimensions must be in [1, {MAX_DIM}], got {grid_shape}")
+    if n > 2 ** 31 - 1:
+        raise ValueError(f"Grid too large for int32 site_index: {nx}x{ny}x{nz} = {n:,} voxels")
+    return n
+
+
+def seed_sites_from_occupancy(occupancy: torch.Tensor) -> torch.Tensor:
+    """[nx, ny, nz] bool -> int32 site_index: packed own coordinates at occupied voxels, -1 elsewhere."""
+    nx, ny, nz = occupancy.shape
+    dev = occupancy.device
+    x = torch.arange(nx, device=dev, dtype=torch.int32).view(nx, 1, 1)
+    y = torch.arange(ny, device=dev, dtype=torch.int32).view(1, ny, 1)
+    z = torch.arange(nz, device=dev, dtype=torch.int32).view(1, 1, nz)
+    packed = (z << 20) | (y << 10) | x
+    return torch.where(occupancy.bool(), packed, torch.full_like(packed, -1)).contiguous()
+
+
+class ParallelBandingEDT:
+    """Exact 3-D EDT: after `propagate`, every voxel of `site_index` holds the packed coordinates of a nearest site."""
+
+    def __init__(self, grid_shape: Tuple[int, int, int], voxel_size: float, device: torch.device, m3: int = 2):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise ValueError(f"ParallelBandingEDT requires CUDA device, got {device}")
+        self.grid_shape = tuple(int(v) for v in grid_shape)
+        self.voxel_size = float(voxel_size)
+        self.device = device
+        self.m3 = m3
+        self.n_voxels = validate_grid_size(self.grid_shape, "ParallelBandingEDT")
+        # the reference's scratch buffer: part of its launcher signature; the kernels here work in place
+        self._buffer = torch.empty(self.n_voxels, dtype=torch.int32, device=device)
+
+    def propagate(self, site_index: torch.Tensor) -> None:
+        nx, ny, nz = self.grid_shape
+        pba_cu.launch_pba3d(site_index.view(-1), self._buffer, nx, ny, nz, m3=self.m3)
+
+    def unsigned_distance(self, site_index: torch.Tensor, out: torch.Tensor = None, empty_value: float = 1e4) -> torch.Tensor:
+        """fp16 [nx, ny, nz] distance field [m] from a propagated site_index."""
+        nx, ny, nz = self.grid_shape
+        if out is None:
+            out = torch.empty(self.grid_shape, dtype=torch.float16, device=self.device)
+        pba_cu.launch_edt_unsigned_distance(site_index.view(-1), out.view(-1), nx, ny, nz, self.voxel_size, empty_value)
+        return out

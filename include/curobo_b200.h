@@ -369,7 +369,8 @@ int cb200_line_search(
  * (cx,cy,cz,m); link_inertias [nl,8] (ixx,iyy,izz,ixy,ixz,iyz,pad,pad at the CoM); gravity [6] spatial; level_starts
  * [n_levels+1] / level_links [nl] = CSR of links by tree depth; forward_cache [B, nl, 20] (v, a, f per link; the same
  * layout as the reference's, so either side can consume the other's).  The reference's threads_per_batch knob has no
- * equivalent (rows are processed serially, one thread each: deterministic sums).  Gradients are overwritten.
+ * equivalent (the launcher picks rows / workers per CTA itself; sums keep the reference's serial order).  Gradients are
+ * overwritten.  level arrays must be depth levels (children of a level-l link are level-(l+1) links).
  * ------------------------------------------------------------------------------------------- */
 int cb200_rnea_forward(
     float *tau, const float *q, const float *qd, const float *qdd, const float *fixed_transforms,
@@ -387,6 +388,23 @@ int cb200_rnea_backward(
     const int16_t *level_starts, const int16_t *level_links, const float *forward_cache,
     int batch_size, int num_links, int num_dof, int n_levels, float *grad_f_ext,
     cb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (8f-4) Exact 3-D nearest-site transform (Euclidean distance transform), the producer side of the ESDF wire format.
+ *   cb200_pba3d  <- launch_pba3d  cuda_core_backend/pba.py:60-124  (kernels/parallel_banding/pba3d_kernel.cuh,
+ *                   driven by perception/mapper/esdf/edt_parallel_banding.py:63-80)
+ * site_index [nx, ny, nz] int32, z contiguous: a site holds its own packed coordinates (z << 20) | (y << 10) | x
+ * (perception/mapper/util/utils_quantization.py:40-54), anything negative is "no site".  In place: afterwards every
+ * voxel holds the packed coordinates of a nearest site (exact; which of several equidistant sites is unspecified, as in
+ * the reference where it depends on the sweep order), or 0x80000000 when the grid holds no site.  nx, ny, nz <= 1023.
+ * `buffer` (the reference's ping-pong scratch) and `m3` (its colour-kernel block height) are accepted and unused.
+ *   cb200_edt_unsigned_distance: fp16(|voxel - site| * voxel_size) per voxel, fp16(empty_value) where no site exists --
+ *   the distance step of compute_esdf_from_min_tsdf (kernel/builder/builder_esdf.py:434-446) without the TSDF sign.
+ * ------------------------------------------------------------------------------------------- */
+int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, int m3, cb200_stream_t stream);
+
+int cb200_edt_unsigned_distance(const int32_t *site_index, uint16_t *distance_fp16, int nx, int ny, int nz,
+                                float voxel_size, float empty_value, cb200_stream_t stream);
 
 /* Host helper: pack robot constants (HOST pointers) into `out` (host buffer of
  * cb200_robot_blob_bytes(...) bytes) that the caller then copies to the device once.

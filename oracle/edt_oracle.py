@@ -1,0 +1,165 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's exact 3-D nearest-site transform (PBA+ 3-D EDT).
+
+Follows curobo/_src/curobolib/kernels/parallel_banding/pba3d_kernel.cuh phase by phase:
+    flood_axis      <- kernel_flood_z           :67-104   (bidirectional 1-D sweep along the first axis)
+    maurer_axis     <- kernel_maurer_axis       :160-222  (stack of Voronoi-dominant sites, is_voronoi_dominated :119-142)
+    color_axis      <- kernel_color_axis        :235-350  (walk the stack from the far end, nearest site per row)
+    pba3d           <- launch_pba3d, backends/cuda_core_backend/pba.py:60-124 (FloodZ, Maurer+Color on Y, Maurer+Color on X)
+Packing: site = (z << 20) | (y << 10) | x in cuRobo indices (perception/mapper/util/utils_quantization.py:40-54,
+site_encoding.cuh:13-19 with the kernels' (sx, sy, sz) = (nz, ny, nx)); non-sites are negative; the transform leaves
+0x80000000 where no site exists at all.  Grid layout [nx, ny, nz], x slowest.
+
+The reference sweeps cuRobo-x first, then y, then z (through two transposes); the transform is separable, so the ORDER of the
+axes only changes which of several equidistant sites is reported -- never the distance.  `pba3d(order=...)` takes the order
+so the tests can restate both the reference's order ("xyz") and the product kernels' order ("zyx", which needs no transpose
+because z is the contiguous axis).  Parity is therefore defined on the squared distance to the reported site (integer, exact)
+plus "the reported site is a site"; pinned against scipy.ndimage.distance_transform_edt (an independent exact EDT) and brute
+force in tests/test_edt_cpu.py.  Pure-Python loops: for small grids only.
+"""
+import numpy as np
+
+EMPTY = -(2 ** 31)
+MASK = 0x3FF
+SHIFT = {"x": 0, "y": 10, "z": 20}
+
+
+def pack(x, y, z):
+    return (np.asarray(z, np.int64) << 20 | np.asarray(y, np.int64) << 10 | np.asarray(x, np.int64)).astype(np.int32)
+
+
+def unpack(v):
+    v = np.asarray(v, np.int64)
+    return v & MASK, (v >> 10) & MASK, (v >> 20) & MASK
+
+
+def seed_grid(occupancy):
+    """occupancy [nx,ny,nz] bool -> site_index int32: own packed coordinates at sites, -1 elsewhere
+    (integrator_esdf.py:526 fill_(-1) + the seeding kernels)."""
+    occ = np.asarray(occupancy, bool)
+    x, y, z = np.meshgrid(*[np.arange(n) for n in occ.shape], indexing="ij")
+    return np.where(occ, pack(x, y, z), np.int32(-1)).astype(np.int32)
+
+
+def _coord(v, axis):
+    return (int(v) >> SHIFT[axis]) & MASK
+
+
+def flood_axis(col, axis):
+    """kernel_flood_z on one column (list of packed ints along `axis`)."""
+    n = len(col)
+    out = [EMPTY] * n
+    carry = EMPTY
+    for i in range(n):                                   # forward :79-84
+        if col[i] >= 0:
+            carry = int(col[i])
+        out[i] = carry
+    big = 2 ** 31 - 1
+    for i in range(n - 2, -1, -1):                       # backward :91-103 (ties keep the backward site)
+        db = abs((_coord(carry, axis) if carry >= 0 else big) - i)
+        f = out[i]
+        df = abs((_coord(f, axis) if f >= 0 else big) - i)
+        if df < db:
+            carry = f
+        out[i] = carry
+    return out
+
+
+def _h(v, axis, q):
+    """squared distance from site v to the column through q, measured off-axis."""
+    sx, sy, sz = int(v) & MASK, (int(v) >> 10) & MASK, (int(v) >> 20) & MASK
+    d = 0
+    if axis != "x":
+        d += (sx - q[0]) ** 2
+    if axis != "y":
+        d += (sy - q[1]) ** 2
+    if axis != "z":
+        d += (sz - q[2]) ** 2
+    return d
+
+
+def maurer_color_axis(col, axis, q):
+    """kernel_maurer_axis + kernel_color_axis on one column.  col[r] = nearest site of row r within the axes already done (or
+    negative).  Stack entries are (row, site); a new site pops every top entry B for which the parabolas of the entry below (A)
+    and the new site (C) meet before B's row range (is_voronoi_dominated, written here with g = row^2 + h:
+    (gB - gA)(rC - rB) > (gC - gB)(rB - rA), identical to the reference's lhs > rhs after expanding its sums of coordinates)."""
+    stack = []
+    for r, v in enumerate(col):
+        if v < 0:
+            continue
+        gc = r * r + _h(v, axis, q)
+        while len(stack) >= 2:
+            (ra, va), (rb, vb) = stack[-2], stack[-1]
+            ga, gb = ra * ra + _h(va, axis, q), rb * rb + _h(vb, axis, q)
+            if (gb - ga) * (r - rb) > (gc - gb) * (rb - ra):
+                stack.pop()
+            else:
+                break
+        stack.append((r, int(v)))
+    n = len(col)
+    out = [EMPTY] * n
+    if not stack:
+        return out
+    k = len(stack) - 1                                    # color: from the last row down, pop while the entry below is
+    for t in range(n - 1, -1, -1):                        # at least as close (:303-322, `cand_sq > min_dist_sq -> break`)
+        best = (stack[k][0] - t) ** 2 + _h(stack[k][1], axis, q)
+        while k > 0:
+            cand = (stack[k - 1][0] - t) ** 2 + _h(stack[k - 1][1], axis, q)
+            if cand > best:
+                break
+            best = cand
+            k -= 1
+        out[t] = stack[k][1]
+    return out
+
+
+def pba3d(site_index, order="xyz"):
+    """Nearest-site transform of site_index [nx,ny,nz] int32 (negative = no site).  order[0] is flooded, order[1:] use
+    Maurer stacks; "xyz" is the reference's schedule (pba.py:86-124)."""
+    g = np.array(site_index, dtype=np.int64).copy()
+    assert g.ndim == 3 and max(g.shape) <= 1023
+    g[g < 0] = EMPTY
+    ax_id = {"x": 0, "y": 1, "z": 2}
+    for step, axis in enumerate(order):
+        a = ax_id[axis]
+        others = [i for i in range(3) if i != a]
+        for i in range(g.shape[others[0]]):
+            for j in range(g.shape[others[1]]):
+                idx = [0, 0, 0]
+                idx[others[0]], idx[others[1]] = i, j
+                sl = [i, j]
+                sl.insert(a, slice(None))
+                col = [int(v) for v in g[tuple(sl)]]
+                res = flood_axis(col, axis) if step == 0 else maurer_color_axis(col, axis, idx)
+                g[tuple(sl)] = res
+    return g.astype(np.int32)
+
+
+def squared_distance(result, shape=None):
+    """d^2 (voxel units) from every voxel to its reported site; -1 where the transform reports no site."""
+    r = np.asarray(result)
+    x, y, z = np.meshgrid(*[np.arange(n) for n in r.shape], indexing="ij")
+    sx, sy, sz = unpack(r)
+    d2 = (sx - x) ** 2 + (sy - y) ** 2 + (sz - z) ** 2
+    return np.where(r < 0, -1, d2).astype(np.int64)
+
+
+def brute_force_squared_distance(occupancy):
+    occ = np.asarray(occupancy, bool)
+    pts = np.argwhere(occ)
+    if len(pts) == 0:
+        return np.full(occ.shape, -1, np.int64)
+    x, y, z = np.meshgrid(*[np.arange(n) for n in occ.shape], indexing="ij")
+    q = np.stack([x, y, z], -1).reshape(-1, 1, 3)
+    best = np.full(q.shape[0], np.iinfo(np.int64).max, np.int64)
+    for s in range(0, len(pts), 512):
+        d = ((q - pts[None, s:s + 512]) ** 2).sum(-1)
+        best = np.minimum(best, d.min(1))
+    return best.reshape(occ.shape)
+
+
+def unsigned_distance_fp16(result, voxel_size, empty_value=1e4):
+    """The distance step of the ESDF builder without the TSDF sign (builder_esdf.py:434-446): fp16(|voxel - site| * voxel_size),
+    fp16(1e4) where no site exists."""
+    d2 = squared_distance(result)
+    d = np.sqrt(np.maximum(d2, 0).astype(np.float32)) * np.float32(voxel_size)
+    return np.where(d2 < 0, np.float32(empty_value), d).astype(np.float16)

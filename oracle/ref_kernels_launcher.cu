@@ -359,3 +359,24 @@ int ref_rnea_backward(float *gq, float *gqd, float *gqdd, const float *gtau, con
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// PBA+ 3-D EDT kernels: the five launches + final copy of
+// backends/cuda_core_backend/pba.py:86-124 with the launch shapes of pba_config.py:51-83.
+// ------------------------------------------------------------------------------------------------
+#include "parallel_banding/pba3d_kernel.cuh"
+
+namespace cpb = curobo::parallel_banding;
+
+extern "C" int ref_pba3d(int *site_index, int *buffer, int nx, int ny, int nz, int m3, cudaStream_t stream) {
+  const int sx = nz, sy = ny, sz = nx;
+  auto cdiv = [](int a, int b) { return (a + b - 1) / b; };
+  int *buf0 = site_index, *buf1 = buffer;
+  cpb::kernel_flood_z<<<dim3(cdiv(sx, 32), cdiv(sy, 4)), dim3(32, 4), 0, stream>>>(buf0, buf1, sx, sy, sz);
+  cpb::kernel_maurer_axis<<<dim3(cdiv(sx, 32), cdiv(sz, 4)), dim3(32, 4), 0, stream>>>(buf1, buf0, sx, sy, sz);
+  cpb::kernel_color_axis<<<dim3(cdiv(sx, 32), sz), dim3(32, m3), 0, stream>>>(buf0, buf1, sx, sy, sz);
+  cpb::kernel_maurer_axis<<<dim3(cdiv(sy, 32), cdiv(sz, 4)), dim3(32, 4), 0, stream>>>(buf1, buf0, sy, sx, sz);
+  cpb::kernel_color_axis<<<dim3(cdiv(sy, 32), sz), dim3(32, m3), 0, stream>>>(buf0, buf1, sy, sx, sz);
+  cudaMemcpyAsync(site_index, buffer, (size_t)nx * ny * nz * sizeof(int), cudaMemcpyDeviceToDevice, stream);
+  return (int)cudaGetLastError();
+}

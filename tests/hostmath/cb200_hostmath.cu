@@ -193,3 +193,39 @@ void hm_rnea_backward(float *gq, float *gqd, float *gqdd, const float *grad_tau,
   }
 }
 }
+
+// ---- exact nearest-site transform (cb200_edt.cuh): the three passes of cb200_pba3d with the same column routines, the
+// shared-memory tile replaced by a scratch column and the coalesced global column by a strided view of the grid ---------
+#include "../../curobo_b200/csrc/cb200_edt.cuh"
+namespace ed = cb200::edt;
+namespace {
+struct HostCol {
+  int *base;
+  long long stride;
+  int get(int r) const { return base[(long long)r * stride]; }
+  void set(int r, int v) const { base[(long long)r * stride] = v; }
+};
+}  // namespace
+extern "C" {
+void hm_pba3d(int32_t *grid, int nx, int ny, int nz) {
+  std::vector<int> scratch((size_t)(nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz)));
+  for (long long row = 0; row < (long long)nx * ny; ++row) {  // pass 1: flood along z, in place
+    HostCol c{grid + row * nz, 1};
+    ed::flood_column<2>(c, nz);
+  }
+  const long long plane = (long long)ny * nz;
+  for (int x = 0; x < nx; ++x)  // pass 2: envelope along y; the column is staged (the stack is built in place over it)
+    for (int z = 0; z < nz; ++z) {
+      int *base = grid + x * plane + z;
+      for (int r = 0; r < ny; ++r) scratch[r] = base[(long long)r * nz];
+      HostCol c{scratch.data(), 1}, o{base, nz};
+      ed::envelope_column<1>(c, o, ny, ed::Voxel{x, 0, z});
+    }
+  for (long long col = 0; col < plane; ++col) {  // pass 3: envelope along x
+    int *base = grid + col;
+    for (int r = 0; r < nx; ++r) scratch[r] = base[(long long)r * plane];
+    HostCol c{scratch.data(), 1}, o{base, plane};
+    ed::envelope_column<0>(c, o, nx, ed::Voxel{0, (int)(col / nz), (int)(col % nz)});
+  }
+}
+}

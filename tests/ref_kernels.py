@@ -173,3 +173,16 @@ def rnea_backward(model, grad_tau, q, qd, cache, nl, D, n_levels, out=None):
                                   n_levels, _stream(dev))
     assert err == 0, err
     return g
+
+
+# ------------------------------------------------------------------------------------------------
+# PBA+ 3-D EDT of the reference (kernels/parallel_banding/), its five launches + copy
+# ------------------------------------------------------------------------------------------------
+def pba3d(site_index, m3=2):
+    """site_index [nx,ny,nz] int32 device tensor -> new tensor with the reference's nearest-site transform."""
+    nx, ny, nz = site_index.shape
+    out = site_index.contiguous().clone()
+    buf = torch.empty_like(out)
+    err = lib().ref_pba3d(_p(out), _p(buf), nx, ny, nz, m3, _stream(out.device))
+    assert err == 0, err
+    return out

@@ -1,0 +1,86 @@
+"""CPU pins of the exact nearest-site transform: the oracle (oracle/edt_oracle.py, a restatement of the
+reference's PBA+ phases) against brute force and scipy's exact EDT; the product's column routines compiled for the host
+(tests/hostmath) against the oracle and scipy.  Parity is on the squared distance to the reported site (integer, bit exact) and
+on "the reported site is a site": which of several equidistant sites is reported depends on the sweep order, in the reference
+too."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy import ndimage
+
+from edt_cases import MEDIUM, SMALL, occupancy
+from helpers import hostmath
+from oracle import edt_oracle as E
+
+
+def hm_pba3d(sites):
+    g = np.ascontiguousarray(sites, np.int32).copy()
+    nx, ny, nz = g.shape
+    hostmath().hm_pba3d(g.ctypes.data_as(C.c_void_p), C.c_int(nx), C.c_int(ny), C.c_int(nz))
+    return g
+
+
+def check_result(res, occ):
+    d2 = E.squared_distance(res)
+    if not occ.any():
+        assert (res == E.EMPTY).all()
+        return
+    assert (res >= 0).all()
+    sx, sy, sz = E.unpack(res)
+    assert (sx < occ.shape[0]).all() and (sy < occ.shape[1]).all() and (sz < occ.shape[2]).all()
+    assert occ[sx, sy, sz].all(), "a reported site is not a site"
+    want = ndimage.distance_transform_edt(~occ) ** 2
+    assert np.array_equal(d2, np.rint(want).astype(np.int64)), "squared distances differ from the exact EDT"
+    assert (d2[occ] == 0).all()
+
+
+@pytest.mark.parametrize("kind,shape,p", SMALL)
+@pytest.mark.parametrize("order", ["xyz", "zyx"])
+def test_oracle_is_exact(kind, shape, p, order):
+    occ = occupancy(kind, shape, seed=3, p=p)
+    res = E.pba3d(E.seed_grid(occ), order)
+    check_result(res, occ)
+    assert np.array_equal(E.squared_distance(res), E.brute_force_squared_distance(occ))
+
+
+@pytest.mark.parametrize("kind,shape,p", SMALL + MEDIUM)
+def test_host_compiled_column_routines_are_exact(kind, shape, p):
+    occ = occupancy(kind, shape, seed=5, p=p)
+    sites = E.seed_grid(occ)
+    res = hm_pba3d(sites)
+    check_result(res, occ)
+    if np.prod(shape) <= 2000:
+        assert np.array_equal(E.squared_distance(res), E.squared_distance(E.pba3d(sites, "zyx")))
+
+
+def test_non_sites_may_be_any_negative_value_and_input_is_not_required_to_be_minus_one():
+    occ = occupancy("random", (9, 8, 7), seed=1, p=0.05)
+    sites = E.seed_grid(occ)
+    rng = np.random.default_rng(0)
+    noisy = np.where(sites < 0, -rng.integers(1, 2 ** 31, sites.shape), sites).astype(np.int32)
+    assert np.array_equal(hm_pba3d(noisy), hm_pba3d(sites))
+    assert np.array_equal(E.pba3d(noisy), E.pba3d(sites))
+
+
+def test_maximum_coordinate_range_and_64_bit_dominance_products():
+    """A 1023-long axis: coordinates use all 10 bits and the dominance products exceed 32 bits."""
+    occ = np.zeros((1023, 2, 3), bool)
+    occ[0, 0, 0] = occ[1022, 1, 2] = occ[511, 0, 1] = True
+    check_result(hm_pba3d(E.seed_grid(occ)), occ)
+    occ = np.zeros((2, 1023, 2), bool)
+    occ[1, 1022, 1] = occ[0, 3, 0] = True
+    check_result(hm_pba3d(E.seed_grid(occ)), occ)
+    occ = np.zeros((2, 2, 1023), bool)
+    occ[1, 1, 1000] = occ[0, 0, 17] = True
+    check_result(hm_pba3d(E.seed_grid(occ)), occ)
+
+
+def test_unsigned_distance_step():
+    occ = occupancy("shells", (12, 10, 9), seed=2)
+    res = E.pba3d(E.seed_grid(occ), "zyx")
+    d = E.unsigned_distance_fp16(res, 0.02)
+    assert d.dtype == np.float16 and (d[occ] == 0).all()
+    want = (ndimage.distance_transform_edt(~occ) * 0.02).astype(np.float16)
+    assert np.array_equal(d, want)
+    assert (E.unsigned_distance_fp16(E.pba3d(E.seed_grid(np.zeros((3, 3, 3), bool))), 0.02) == np.float16(1e4)).all()
