@@ -224,6 +224,39 @@ def rnea_bench(device, peak, cases=(("franka", 16384), ("franka", 30720), ("g1_2
     return out
 
 
+def edt_bench(device, peak, n=256, iters=10):
+    """exact nearest-site transform of an n^3 grid (box shells + sparse noise as sites) through the
+    backend module, in place; algorithmic traffic = 3 passes x (4 B read + 4 B write) per voxel; the grid is re-seeded (one
+    device copy, outside the timed region) before every iteration; n^3 x 4 B = 64 MiB at n = 256, so every pass streams HBM."""
+    import torch
+    from curobo_b200.esdf import ParallelBandingEDT, seed_sites_from_occupancy
+    g = torch.Generator(device="cpu").manual_seed(0)
+    occ = torch.rand((n, n, n), generator=g) < 2e-4
+    for lo, hi in (((40, 60, 30), (120, 140, 90)), ((150, 30, 100), (220, 110, 200))):
+        box = torch.zeros_like(occ)
+        box[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = True
+        box[lo[0] + 1:hi[0] - 1, lo[1] + 1:hi[1] - 1, lo[2] + 1:hi[2] - 1] = False
+        occ |= box
+    fresh = seed_sites_from_occupancy(occ.to(device))
+    work = fresh.clone()
+    edt = ParallelBandingEDT((n, n, n), 0.01, torch.device(device))
+    ts = []
+    for i in range(iters + 2):
+        work.copy_(fresh)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        edt.propagate(work)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    nbytes = 3 * 8 * n ** 3
+    return {"grid": [n, n, n], "sites": int(occ.sum()), "transform_ms": ms, "voxels_per_s": n ** 3 / (ms * 1e-3),
+            "bytes_per_voxel": 24, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "launches": 3,
+            "note": "first measurement of this row; kernels not yet profiled"}
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -392,6 +425,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ik-solve", type=int, default=1,
                     help="1: also time a complete 100-iteration L-BFGS IK solve (512 goals x 32 seeds), reported under 'ik_solve'")
+    ap.add_argument("--edt", type=int, default=1, help="1: also time the exact nearest-site transform (256^3), reported under 'edt'")
     ap.add_argument("--rnea", type=int, default=1, help="1: also time the RNEA inverse-dynamics kernels, reported under 'rnea'")
     ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,franka_mpc_knots_1024x30_esdf_swept,franka_mpc_knots_inkernel_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
                     help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
@@ -566,6 +600,11 @@ def main():
                     line["rnea"] = rnea_bench(device, peak)
                 except Exception as ex:                                               # noqa: BLE001
                     line["rnea"] = {"error": repr(ex)}
+            if args.edt:
+                try:
+                    line["edt"] = edt_bench(device, peak)
+                except Exception as ex:                                               # noqa: BLE001
+                    line["edt"] = {"error": repr(ex)}
             if not args.no_cpu_baseline:
                 v, cores, sample = cpu_baseline(args.workload, target_seconds=12.0, procs=1)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

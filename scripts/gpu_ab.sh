@@ -3,7 +3,7 @@
 for mode in "CB200_ARM_REGCAP=0" "CB200_ARM_REGCAP=1"; do
   echo "$mode"
   for w in franka_ik_512x32_cuboid franka_16384_esdf; do
-  env $mode timeout 200 python bench.py --workload $w --steps 300 --warmup 20 --no-cpu-baseline --ik-solve 0 --rnea 0 --extra-workloads "" 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('   $w evals/s %.4g  ms %.4f e2e %.4g' % (d['value'], d['ms_per_step'], d['e2e']['value']))"
+  env $mode timeout 200 python bench.py --workload $w --steps 300 --warmup 20 --no-cpu-baseline --ik-solve 0 --rnea 0 --edt 0 --extra-workloads "" 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('   $w evals/s %.4g  ms %.4f e2e %.4g' % (d['value'], d['ms_per_step'], d['e2e']['value']))"
   done
 done
 CB200_ARM_REGCAP=0 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --ik-solve 1 --extra-workloads "" 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('regcap0 ik_solve', d['ik_solve'])"

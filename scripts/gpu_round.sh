@@ -10,13 +10,13 @@ nvidia-smi -L > gpurun_out/gpu.txt
 (timeout 600 python bench.py --impl reference --steps 20 --warmup 3) > gpurun_out/bench_reference.log 2>&1
 if [ "$1" != "noprof" ]; then
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --ik-solve 0 --rnea 0 --extra-workloads "") > gpurun_out/ncu_launches.log 2>&1
+   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --ik-solve 0 --rnea 0 --edt 0 --extra-workloads "") > gpurun_out/ncu_launches.log 2>&1
 (timeout 900 ncu --set full --clock-control none --import-source on -k regex:rollout_fused -s 3 -c 1 -o gpurun_out/prof_fused_ik -f \
-   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --ik-solve 0 --rnea 0 --extra-workloads "") > gpurun_out/ncu_full.log 2>&1
+   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --ik-solve 0 --rnea 0 --edt 0 --extra-workloads "") > gpurun_out/ncu_full.log 2>&1
 (timeout 900 ncu --set full --clock-control none --import-source on -k regex:rollout_fused -s 3 -c 1 -o gpurun_out/prof_fused_g1 -f \
-   python bench.py --workload g1_29_8192_esdf --steps 3 --warmup 3 --no-cpu-baseline --ik-solve 0 --rnea 0 --extra-workloads "") > gpurun_out/ncu_full_g1.log 2>&1
+   python bench.py --workload g1_29_8192_esdf --steps 3 --warmup 3 --no-cpu-baseline --ik-solve 0 --rnea 0 --edt 0 --extra-workloads "") > gpurun_out/ncu_full_g1.log 2>&1
 (timeout 900 ncu --set full --clock-control none --import-source on -k regex:rollout_traj -s 3 -c 1 -o gpurun_out/prof_traj_mpc -f \
-   python bench.py --workload franka_mpc_1024x30_esdf_swept --steps 3 --warmup 3 --no-cpu-baseline --ik-solve 0 --rnea 0 --extra-workloads "") > gpurun_out/ncu_full_mpc.log 2>&1
+   python bench.py --workload franka_mpc_1024x30_esdf_swept --steps 3 --warmup 3 --no-cpu-baseline --ik-solve 0 --rnea 0 --edt 0 --extra-workloads "") > gpurun_out/ncu_full_mpc.log 2>&1
 fi
 tail -3 gpurun_out/smoke.log; tail -5 gpurun_out/gpu_tests.log; tail -2 gpurun_out/rollout_tile.log; tail -2 gpurun_out/rollout_lane.log
 tail -1 gpurun_out/bench.log | cut -c1-3000; tail -1 gpurun_out/bench_reference.log | cut -c1-400
