@@ -84,3 +84,20 @@ def test_unsigned_distance_step():
     want = (ndimage.distance_transform_edt(~occ) * 0.02).astype(np.float16)
     assert np.array_equal(d, want)
     assert (E.unsigned_distance_fp16(E.pba3d(E.seed_grid(np.zeros((3, 3, 3), bool))), 0.02) == np.float16(1e4)).all()
+
+
+def test_host_mirror_seeding_and_grid_validation():
+    """curobo_b200.esdf: the seeding helper (plain torch, device-agnostic) packs like the oracle; grid validation follows
+    esdf/kernel/wp_jfa.py:28-38 plus the 10-bit coordinate limit; the operator refuses a CPU device like the reference."""
+    import torch
+    from curobo_b200 import esdf
+    occ = occupancy("random", (5, 9, 7), seed=4, p=0.2)
+    got = esdf.seed_sites_from_occupancy(torch.as_tensor(occ))
+    assert got.dtype == torch.int32 and got.is_contiguous()
+    assert np.array_equal(got.numpy(), E.seed_grid(occ))
+    assert esdf.validate_grid_size((1023, 2, 3), "t") == 1023 * 6
+    for bad in ((1024, 2, 2), (0, 4, 4), (4, 4, -1)):
+        with pytest.raises(ValueError):
+            esdf.validate_grid_size(bad, "t")
+    with pytest.raises(ValueError):
+        esdf.ParallelBandingEDT((8, 8, 8), 0.02, torch.device("cpu"))
