@@ -25,75 +25,29 @@ inline int status(cudaError_t e) {
   return (int)e;
 }
 
-struct TileCol {  // one column of a shared-memory tile: row r at base[r * stride]
-  int *base;
-  int stride;
-  __device__ __forceinline__ int get(int r) const { return base[r * stride]; }
-  __device__ __forceinline__ void set(int r, int v) const { base[r * stride] = v; }
-};
-struct GlobalCol {  // the same column in the grid
-  int *base;
-  long long stride;
-  __device__ __forceinline__ void set(int r, int v) const { base[(long long)r * stride] = v; }
-};
-
-constexpr int kLanes = 32;
-constexpr int kPad = 33;  // padded row length of the transposed tile of the z pass
-
-// pass 1: nearest site along z.  Tile = 32 consecutive (x, y) rows of nz ints, stored transposed [nz][33]
-__global__ void __launch_bounds__(kLanes) edt_flood_z_kernel(int *__restrict__ grid, int nz, long long nrows) {
+// The per-lane work of every pass lives in cb200_edt.cuh (FloodZ, Envelope<AXIS>: also executed lane by lane by the host
+// emulation in tests/hostmath); a kernel is the grid-stride loop over tiles plus the warp barriers.  One warp per CTA.
+__global__ void __launch_bounds__(kLanes) edt_flood_z_kernel(const __grid_constant__ FloodZ pass) {
   extern __shared__ int tile[];
   const int lane = threadIdx.x;
-  const long long ntiles = (nrows + kLanes - 1) / kLanes;
+  const long long ntiles = pass.ntiles();
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const long long row0 = t * kLanes;
-    const int live_rows = (int)((nrows - row0) < kLanes ? (nrows - row0) : kLanes);
-    for (int rr = 0; rr < live_rows; ++rr) {
-      const int *src = grid + (row0 + rr) * nz;
-      for (int z = lane; z < nz; z += kLanes) tile[z * kPad + rr] = src[z];
-    }
+    pass.load(tile, t, lane);
     __syncwarp();
-    if (lane < live_rows) {
-      TileCol c{tile + lane, kPad};
-      flood_column<2>(c, nz);
-    }
+    pass.compute(tile, t, lane);
     __syncwarp();
-    for (int rr = 0; rr < live_rows; ++rr) {
-      int *dst = grid + (row0 + rr) * nz;
-      for (int z = lane; z < nz; z += kLanes) dst[z] = tile[z * kPad + rr];
-    }
+    pass.store(tile, t, lane);
     __syncwarp();
   }
 }
 
-// passes 2 and 3: lower envelope along AXIS (1 = y, 0 = x).  Columns are indexed by (outer, inner) with `inner` contiguous in
-// memory: AXIS 1: outer = x, inner = z; AXIS 0: outer = 0, inner = y * nz + z.  Tile = [n][32] (row r of the tile = 32 ints
-// adjacent in memory).
 template <int AXIS>
-__global__ void __launch_bounds__(kLanes) edt_envelope_kernel(int *__restrict__ grid, int n, long long row_stride, int inner,
-                                                               int n_outer, long long outer_stride, int nz) {
+__global__ void __launch_bounds__(kLanes) edt_envelope_kernel(const __grid_constant__ Envelope<AXIS> pass) {
   extern __shared__ int tile[];
   const int lane = threadIdx.x;
-  const int tiles_per_outer = (inner + kLanes - 1) / kLanes;
-  const long long ntiles = (long long)tiles_per_outer * n_outer;
+  const long long ntiles = pass.ntiles();
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int outer = (int)(t / tiles_per_outer);
-    const int col = (int)(t - (long long)outer * tiles_per_outer) * kLanes + lane;
-    const bool live = col < inner;
-    int *base = grid + (long long)outer * outer_stride + (live ? col : 0);
-#pragma unroll 8
-    for (int r = 0; r < n; ++r) tile[r * kLanes + lane] = live ? base[(long long)r * row_stride] : kEmpty;
-    if (live) {
-      Voxel q;
-      if (AXIS == 1) {
-        q.x = outer, q.y = 0, q.z = col;
-      } else {
-        q.x = 0, q.y = col / nz, q.z = col - (col / nz) * nz;
-      }
-      TileCol c{tile + lane, kLanes};
-      GlobalCol o{base, row_stride};
-      envelope_column<AXIS>(c, o, n, q);
-    }
+    pass.run(tile, t, lane);
     __syncwarp();
   }
 }
@@ -134,18 +88,15 @@ int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, in
   (void)m3;      // the reference's colour-kernel block height
   if (site_index == nullptr || !dims_ok(nx, ny, nz)) return status(cudaErrorInvalidValue);
   const cudaStream_t st = (cudaStream_t)stream;
-  const int smem_z = nz * kPad * (int)sizeof(int), smem_y = ny * kLanes * (int)sizeof(int),
-            smem_x = nx * kLanes * (int)sizeof(int);
+  const Plan p = make_plan(site_index, nx, ny, nz);
+  const int smem_z = p.z.tile_ints() * (int)sizeof(int), smem_y = p.y.tile_ints() * (int)sizeof(int),
+            smem_x = p.x.tile_ints() * (int)sizeof(int);
   if (!allow_smem(edt_flood_z_kernel, smem_z) || !allow_smem(edt_envelope_kernel<1>, smem_y) ||
       !allow_smem(edt_envelope_kernel<0>, smem_x))
     return status(cudaErrorInvalidConfiguration);
-  const long long nrows = (long long)nx * ny;
-  edt_flood_z_kernel<<<grid_for((nrows + kLanes - 1) / kLanes), kLanes, smem_z, st>>>(site_index, nz, nrows);
-  const long long plane = (long long)ny * nz;
-  edt_envelope_kernel<1><<<grid_for((long long)((nz + kLanes - 1) / kLanes) * nx), kLanes, smem_y, st>>>(
-      site_index, ny, (long long)nz, nz, nx, plane, nz);
-  edt_envelope_kernel<0><<<grid_for((plane + kLanes - 1) / kLanes), kLanes, smem_x, st>>>(site_index, nx, plane, (int)plane, 1, 0,
-                                                                                         nz);
+  edt_flood_z_kernel<<<grid_for(p.z.ntiles()), kLanes, smem_z, st>>>(p.z);
+  edt_envelope_kernel<1><<<grid_for(p.y.ntiles()), kLanes, smem_y, st>>>(p.y);
+  edt_envelope_kernel<0><<<grid_for(p.x.ntiles()), kLanes, smem_x, st>>>(p.x);
   return status(cudaGetLastError());
 }
 

@@ -140,6 +140,109 @@ CB_HD int envelope_column(Col &c, Out &out, int n, const Voxel &q) {
   return m;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-tile schedule of the three passes.  These are the functions a lane executes on the GPU (cb200_edt.cu) AND the
+// functions the host emulation executes lane by lane (tests/hostmath: hm_pba3d_tiles), so the index arithmetic of the
+// kernels is covered by the CPU tests; the kernels themselves only add the grid-stride loop and the warp barriers.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kLanes = 32;
+constexpr int kPad = 33;  // padded row length of the transposed tile of the z pass
+
+struct TileCol {  // one column of a tile: row r at base[r * stride]
+  int *base;
+  int stride;
+  CB_HD int get(int r) const { return base[r * stride]; }
+  CB_HD void set(int r, int v) const { base[r * stride] = v; }
+};
+struct GridCol {  // the same column in the grid
+  int *base;
+  long long stride;
+  CB_HD void set(int r, int v) const { base[(long long)r * stride] = v; }
+};
+
+// pass 1: nearest site along z.  Tile t = 32 consecutive (x, y) rows of nz ints, staged transposed as [nz][33].
+struct FloodZ {
+  int *grid;
+  int nz;
+  long long nrows;  // nx * ny
+  CB_HD long long ntiles() const { return (nrows + kLanes - 1) / kLanes; }
+  CB_HD int tile_ints() const { return nz * kPad; }
+  CB_HD int live_rows(long long t) const {
+    const long long left = nrows - t * kLanes;
+    return (int)(left < kLanes ? left : kLanes);
+  }
+  CB_HD void load(int *tile, long long t, int lane) const {  // lane copies column-slices z = lane, lane+32, .. of every row
+    const int rows = live_rows(t);
+    for (int rr = 0; rr < rows; ++rr) {
+      const int *src = grid + (t * kLanes + rr) * nz;
+      for (int z = lane; z < nz; z += kLanes) tile[z * kPad + rr] = src[z];
+    }
+  }
+  CB_HD void compute(int *tile, long long t, int lane) const {  // lane owns row `lane` of the tile
+    if (lane < live_rows(t)) {
+      TileCol c{tile + lane, kPad};
+      flood_column<2>(c, nz);
+    }
+  }
+  CB_HD void store(const int *tile, long long t, int lane) const {
+    const int rows = live_rows(t);
+    for (int rr = 0; rr < rows; ++rr) {
+      int *dst = grid + (t * kLanes + rr) * nz;
+      for (int z = lane; z < nz; z += kLanes) dst[z] = tile[z * kPad + rr];
+    }
+  }
+};
+
+// passes 2 and 3: lower envelope along AXIS (1 = y, 0 = x).  Columns are indexed by (outer, inner) with `inner` contiguous in
+// memory -- AXIS 1: outer = x, inner = z; AXIS 0: outer = 0, inner = y * nz + z.  Tile = [n][32]: row r of the tile is 32 ints
+// adjacent in memory.  A lane stages its own column, builds the stack in place and writes its rows back: no lane reads
+// another lane's column, so the pass needs no barrier.
+template <int AXIS>
+struct Envelope {
+  int *grid;
+  int n;                 // extent along AXIS
+  long long row_stride;  // elements between consecutive rows of a column
+  int inner, n_outer;
+  long long outer_stride;
+  int nz;
+  CB_HD int tiles_per_outer() const { return (inner + kLanes - 1) / kLanes; }
+  CB_HD long long ntiles() const { return (long long)tiles_per_outer() * n_outer; }
+  CB_HD int tile_ints() const { return n * kLanes; }
+  CB_HD void run(int *tile, long long t, int lane) const {
+    const int outer = (int)(t / tiles_per_outer());
+    const int col = (int)(t - (long long)outer * tiles_per_outer()) * kLanes + lane;
+    if (col >= inner) return;
+    int *base = grid + (long long)outer * outer_stride + col;
+#ifdef __CUDA_ARCH__
+#pragma unroll 8
+#endif
+    for (int r = 0; r < n; ++r) tile[r * kLanes + lane] = base[(long long)r * row_stride];
+    Voxel q;
+    if (AXIS == 1) {
+      q.x = outer, q.y = 0, q.z = col;
+    } else {
+      q.x = 0, q.y = col / nz, q.z = col - (col / nz) * nz;
+    }
+    TileCol c{tile + lane, kLanes};
+    GridCol o{base, row_stride};
+    envelope_column<AXIS>(c, o, n, q);
+  }
+};
+
+struct Plan {  // the three passes of one transform of a [nx, ny, nz] grid
+  FloodZ z;
+  Envelope<1> y;
+  Envelope<0> x;
+};
+CB_HD Plan make_plan(int *grid, int nx, int ny, int nz) {
+  const long long plane = (long long)ny * nz;
+  Plan p;
+  p.z = FloodZ{grid, nz, (long long)nx * ny};
+  p.y = Envelope<1>{grid, ny, (long long)nz, nz, nx, plane, nz};
+  p.x = Envelope<0>{grid, nx, plane, (int)plane, 1, 0, nz};
+  return p;
+}
+
 // |voxel - site| * voxel_size as fp16 bits are produced by the caller; this is the integer part
 CB_HD int site_distance_sq(int v, int x, int y, int z) {
   const int dx = coord<0>(v) - x, dy = coord<1>(v) - y, dz = coord<2>(v) - z;

@@ -196,6 +196,8 @@ void hm_rnea_backward(float *gq, float *gqd, float *gqdd, const float *grad_tau,
 
 // ---- exact nearest-site transform (cb200_edt.cuh): the three passes of cb200_pba3d with the same column routines, the
 // shared-memory tile replaced by a scratch column and the coalesced global column by a strided view of the grid ---------
+#include <algorithm>
+
 #include "../../curobo_b200/csrc/cb200_edt.cuh"
 namespace ed = cb200::edt;
 namespace {
@@ -227,5 +229,24 @@ void hm_pba3d(int32_t *grid, int nx, int ny, int nz) {
     HostCol c{scratch.data(), 1}, o{base, plane};
     ed::envelope_column<0>(c, o, nx, ed::Voxel{0, (int)(col / nz), (int)(col % nz)});
   }
+}
+
+// The kernels' own schedule, emulated: `n_ctas` one-warp CTAs stride over the tiles of each pass exactly like
+// edt_flood_z_kernel / edt_envelope_kernel do; the lanes of a warp run one after the other between the barriers.
+void hm_pba3d_tiles(int32_t *grid, int nx, int ny, int nz, int n_ctas) {
+  const ed::Plan p = ed::make_plan(grid, nx, ny, nz);
+  std::vector<int> tile((size_t)std::max(p.z.tile_ints(), std::max(p.y.tile_ints(), p.x.tile_ints())));
+  for (int cta = 0; cta < n_ctas; ++cta)
+    for (long long t = cta; t < p.z.ntiles(); t += n_ctas) {
+      for (int lane = 0; lane < ed::kLanes; ++lane) p.z.load(tile.data(), t, lane);
+      for (int lane = 0; lane < ed::kLanes; ++lane) p.z.compute(tile.data(), t, lane);
+      for (int lane = 0; lane < ed::kLanes; ++lane) p.z.store(tile.data(), t, lane);
+    }
+  for (int cta = 0; cta < n_ctas; ++cta)
+    for (long long t = cta; t < p.y.ntiles(); t += n_ctas)
+      for (int lane = 0; lane < ed::kLanes; ++lane) p.y.run(tile.data(), t, lane);
+  for (int cta = 0; cta < n_ctas; ++cta)
+    for (long long t = cta; t < p.x.ntiles(); t += n_ctas)
+      for (int lane = 0; lane < ed::kLanes; ++lane) p.x.run(tile.data(), t, lane);
 }
 }

@@ -21,6 +21,13 @@ def hm_pba3d(sites):
     return g
 
 
+def hm_pba3d_tiles(sites, n_ctas=3):
+    g = np.ascontiguousarray(sites, np.int32).copy()
+    nx, ny, nz = g.shape
+    hostmath().hm_pba3d_tiles(g.ctypes.data_as(C.c_void_p), C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_int(n_ctas))
+    return g
+
+
 def check_result(res, occ):
     d2 = E.squared_distance(res)
     if not occ.any():
@@ -52,6 +59,19 @@ def test_host_compiled_column_routines_are_exact(kind, shape, p):
     check_result(res, occ)
     if np.prod(shape) <= 2000:
         assert np.array_equal(E.squared_distance(res), E.squared_distance(E.pba3d(sites, "zyx")))
+
+
+@pytest.mark.parametrize("kind,shape,p", SMALL + MEDIUM)
+def test_kernel_tile_schedule_emulated_on_the_host(kind, shape, p):
+    """The per-lane functions the CUDA kernels execute (FloodZ / Envelope<AXIS>::run, cb200_edt.cuh), driven by a host loop
+    that strides CTAs over tiles and runs the 32 lanes between barriers: covers the kernels' index arithmetic (tile -> rows /
+    columns, partial tiles, the transposed z tile) without a GPU.  Same result as the plain column-by-column driver."""
+    occ = occupancy(kind, shape, seed=9, p=p)
+    sites = E.seed_grid(occ)
+    res = hm_pba3d_tiles(sites, n_ctas=3)
+    check_result(res, occ)
+    assert np.array_equal(res, hm_pba3d(sites)), "tile schedule and column driver disagree"
+    assert np.array_equal(res, hm_pba3d_tiles(sites, n_ctas=1000)), "result depends on the number of CTAs"
 
 
 def test_non_sites_may_be_any_negative_value_and_input_is_not_required_to_be_minus_one():
