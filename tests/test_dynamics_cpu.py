@@ -107,3 +107,38 @@ def test_effort_cost_composition_gradient_by_finite_differences():
         fd = (vals[0] - vals[1]) / (2 * eps)
         an = float((g[gi].reshape(d.shape).astype(np.float64) * d).sum())
         assert abs(fd - an) <= 1.5e-2 * max(abs(an), abs(fd), 1.0), (key, fd, an)
+
+
+@pytest.mark.parametrize("nl,B,seed,mimic", __import__("dynamics_cases").RANDOM_TREES)
+def test_host_math_vs_oracle_on_random_trees(nl, B, seed, mimic):
+    """Synthetic trees with every joint type, fixed links, negative multipliers, offsets and mimic joints (links sharing a
+    joint index): the product's row functions against the oracle, forward and adjoint."""
+    from dynamics_cases import random_tree_case
+    c = random_tree_case(nl, B, seed, mimic)
+    m = model_args(c)
+    tau_w, cache_w = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m)
+    tau, cache = hm_forward(c)
+    assert np.allclose(tau, tau_w, rtol=1e-4, atol=3e-5 * np.abs(tau_w).max())
+    cw = pack_cache(cache_w, c["nl"])
+    assert np.allclose(cache, cw, rtol=1e-4, atol=3e-5 * np.abs(cw).max())
+    want = do.rnea_backward(c["grad_tau"], c["q"], c["qd"], cache_w, *m)
+    got = hm_backward(c, cache)
+    for g, w in zip(got, want):
+        assert np.allclose(g, w, rtol=3e-4, atol=1e-4 * max(np.abs(w).max(), 1e-6))
+
+
+def test_oracle_qdd_adjoint_on_a_mimic_tree_by_finite_differences():
+    """tau is linear in qdd (tau = M(q) qdd + ...), so d<grad_tau, tau>/d qdd is exact by differencing -- with mimic joints
+    the same column of M collects several links."""
+    from dynamics_cases import random_tree_case
+    c = random_tree_case(40, 2, 33, True)
+    assert int((c["rm"].joint_map >= 0).sum()) > c["D"], "the case must contain mimic links"
+    m = model_args(c)
+    tau, cache = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m)
+    gqdd = do.rnea_backward(c["grad_tau"], c["q"], c["qd"], cache, *m)[2]
+    for d in range(0, c["D"], 3):
+        e = np.zeros_like(c["qdd"])
+        e[:, d] = 1.0
+        t1 = do.rnea_forward(c["q"], c["qd"], c["qdd"] + e, *m)[0].astype(np.float64)
+        num = ((t1 - tau.astype(np.float64)) * c["grad_tau"]).sum(1)
+        assert np.allclose(num, gqdd[:, d], rtol=5e-3, atol=5e-3 * np.abs(gqdd).max()), d

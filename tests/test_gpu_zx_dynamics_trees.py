@@ -1,0 +1,48 @@
+"""RNEA kernels on synthetic trees (every joint type, fixed links, negative multipliers / offsets, mimic joints that make tau and
+the gradients accumulate over several links): CTA-phased kernels and thread-per-row kernels against the oracle.  The oracle and
+the product's row functions agree on these trees on the CPU (tests/test_dynamics_cpu.py).  Written after round 1's GPU budget was
+spent -- not yet run on a B200; ordered late in the suite for that reason."""
+import numpy as np
+import pytest
+import torch
+
+from dynamics_cases import RANDOM_TREES, model_args, pack_cache, random_tree_case
+from curobo_b200.backends import dynamics as dynamics_cu
+from oracle import dynamics_oracle as do
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("nl,B,seed,mimic", RANDOM_TREES + [(23, 70, 41, True)])
+@pytest.mark.parametrize("rows", [False, True])
+def test_rnea_on_random_trees(nl, B, seed, mimic, rows, monkeypatch):
+    if rows:
+        monkeypatch.setenv("CB200_RNEA_ROWS", "1")
+    c = random_tree_case(nl, B, seed, mimic)
+    m = model_args(c)
+    model = tuple(T(x) for x in m) + (T(c["starts"]), T(c["order"]))
+    D, nlev = c["D"], c["n_levels"]
+    q, qd, qdd, gt = T(c["q"]), T(c["qd"]), T(c["qdd"]), T(c["grad_tau"])
+    tau = torch.full((B, D), float("nan"), device=DEV)
+    cache = torch.zeros((B, nl * 20), device=DEV)
+    dynamics_cu.launch_rnea_forward(tau, q, qd, qdd, *model, cache, B, nl, D, nlev)
+    g = [torch.full((B, D), float("nan"), device=DEV) for _ in range(3)]
+    dynamics_cu.launch_rnea_backward(*g, gt, q, qd, *model, cache, B, nl, D, nlev)
+    torch.cuda.synchronize()
+    tau_w, cache_w = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m)
+    want = do.rnea_backward(c["grad_tau"], c["q"], c["qd"], cache_w, *m)
+
+    def close(got, w, rtol, what):
+        got = got.cpu().numpy()
+        assert np.isfinite(got).all(), what
+        assert np.allclose(got, w, rtol=rtol, atol=rtol * max(float(np.abs(w).max()), 1e-6)), (what, float(np.abs(got - w).max()))
+
+    close(tau, tau_w, 2e-4, "tau")
+    close(cache.view(B, nl, 20)[:, :, :18], pack_cache(cache_w, nl).reshape(B, nl, 20)[:, :, :18], 2e-4, "cache")
+    for got, w, n in zip(g, want, ("grad_q", "grad_qd", "grad_qdd")):
+        close(got, w, 5e-4, n)
