@@ -46,3 +46,28 @@ def test_rnea_on_random_trees(nl, B, seed, mimic, rows, monkeypatch):
     close(cache.view(B, nl, 20)[:, :, :18], pack_cache(cache_w, nl).reshape(B, nl, 20)[:, :, :18], 2e-4, "cache")
     for got, w, n in zip(g, want, ("grad_q", "grad_qd", "grad_qdd")):
         close(got, w, 5e-4, n)
+
+
+@pytest.mark.parametrize("robot,B", [("franka", 100), ("g1_29", 70)])
+@pytest.mark.parametrize("R", [8, 16, 32])
+def test_rnea_every_rows_per_cta_variant(robot, B, R, monkeypatch):
+    """The launcher picks 8 / 16 / 32 rows per CTA from the batch size; small test batches always land on 8.  Force each
+    variant (CB200_RNEA_R) on a batch that is not a multiple of any of them."""
+    from dynamics_cases import make_case
+    monkeypatch.setenv("CB200_RNEA_R", str(R))
+    c = make_case(robot, B, 17)
+    m = model_args(c)
+    model = tuple(T(x) for x in m) + (T(c["starts"]), T(c["order"]))
+    nl, D, nlev = c["nl"], c["D"], c["n_levels"]
+    q, qd, qdd, gt = T(c["q"]), T(c["qd"]), T(c["qdd"]), T(c["grad_tau"])
+    tau = torch.full((B, D), float("nan"), device=DEV)
+    cache = torch.zeros((B, nl * 20), device=DEV)
+    dynamics_cu.launch_rnea_forward(tau, q, qd, qdd, *model, cache, B, nl, D, nlev)
+    g = [torch.full((B, D), float("nan"), device=DEV) for _ in range(3)]
+    dynamics_cu.launch_rnea_backward(*g, gt, q, qd, *model, cache, B, nl, D, nlev)
+    torch.cuda.synchronize()
+    tau_w, cache_w = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m)
+    want = do.rnea_backward(c["grad_tau"], c["q"], c["qd"], cache_w, *m)
+    assert np.allclose(tau.cpu().numpy(), tau_w, rtol=2e-4, atol=2e-4 * np.abs(tau_w).max())
+    for got, w in zip(g, want):
+        assert np.allclose(got.cpu().numpy(), w, rtol=5e-4, atol=5e-4 * np.abs(w).max())
