@@ -5,7 +5,9 @@ ncu's CLI prints per-SASS-instruction counters (`--page source --csv`) but not t
 SASS stream is aligned (instruction by instruction, same order) with `nvdisasm -g` line info of a cubin built
 from the SAME sources with the SAME flags.
 
-    python scripts/ncu_lines.py <report.ncu-rep> <kernel-substring> <evals-per-launch> [--top N]
+    python scripts/ncu_lines.py <report.ncu-rep> <kernel-substring> <evals-per-launch> [--top N] [--src cb200_edt.cu]
+
+`--src` names the translation unit under curobo_b200/csrc/ that holds the kernel (default cb200_kernels.cu).
 """
 import collections
 import csv
@@ -26,7 +28,8 @@ def main():
     srcdir = os.path.join(ROOT, "curobo_b200", "csrc")
     tmp = tempfile.mkdtemp()
     cubin, sass = os.path.join(tmp, "k.cubin"), os.path.join(tmp, "k.sass")
-    subprocess.check_call(["nvcc", *FLAGS, "-cubin", "-o", cubin, os.path.join(srcdir, "cb200_kernels.cu")])
+    unit = sys.argv[sys.argv.index("--src") + 1] if "--src" in sys.argv else "cb200_kernels.cu"
+    subprocess.check_call(["nvcc", *FLAGS, "-cubin", "-o", cubin, os.path.join(srcdir, unit)])
     open(sass, "w").write(subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
