@@ -14,10 +14,16 @@ Pinning status (see DESIGN.md "Oracle"):
   * FK backward,   pinned on the GPU box against oracle/_ref (reference kinematics_backward_kernel,
     self-collision self_collision_max_distance_kernel) and by finite differences.
   * scene collision / tool pose / c-space: the reference implements these in NVIDIA Warp (third-party,
-    `warp-lang>=0.10`, pyproject.toml:37, not vendored, not installable here).  These parts follow the
-    Python source of the reference's @wp.func bodies and are pinned only by the reference's property
-    tests (tests/_src/geom/sdf/test_voxel_collision.py:636-1156) restated in tests/ -> "parity unpinned"
-    numerically for those three terms.
+    `warp-lang>=0.10`, pyproject.toml:37, not vendored, not installable here), so its kernels cannot be
+    compiled or run.  They are pinned on the reference's own SOURCE instead: tests/golden/make_warp_golden.py
+    imports the reference's @wp.kernel / @wp.func Python bodies and executes them on the CPU, one thread at
+    a time, under a pure-Python stand-in for Warp's builtins (oracle/warp_shim); the resulting fixture
+    (tests/golden/warp_reference_golden.npz: discrete / multi-env / swept collision, speed metric, tool pose
+    axis-angle and Lie, c-space STATE with a live effort channel, c-space POSITION) is reproduced by this
+    module to float32 rounding (tests/test_warp_reference_golden_cpu.py).  What remains restated is the
+    stand-in's ~35 builtins (quaternion / transform algebra per Warp's documentation, C integer division);
+    the reference's property tests (tests/_src/geom/sdf/test_voxel_collision.py:636-1156) are restated in
+    tests/ as well.
 """
 from __future__ import annotations
 

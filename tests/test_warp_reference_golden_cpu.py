@@ -84,3 +84,95 @@ def test_cspace_position_cost_matches_the_reference_source():
                                      target_weight=float(c["target_weight"][0]), target_dof_weight=c["dof_weight"])
     close(cost, c["cost"], 1e-6, "cost")
     close(g, c["grad_p"], 1e-6, "grad_p")
+
+
+@pytest.mark.parametrize("name", ["collision_discrete", "collision_swept", "collision_swept_speed"])
+def test_product_scene_math_compiled_for_the_host_matches_the_reference_source(name):
+    """No oracle in between: the product's __host__ __device__ scene-collision arithmetic (curobo_b200/csrc/cb200_math.cuh,
+    compiled for the host by tests/hostmath) against the reference-source fixture, including the exact ESDF cull level."""
+    from helpers import hm_scene, hostmath, numpy_voxel_mip
+    c = case(name)
+    cub, vox = worlds(c)
+    speed = "speed_dt" in c
+    for mip in (None, numpy_voxel_mip(vox)):
+        cost, grad = hm_scene(hostmath(), c["spheres"], float(c["weight"]), float(c["eta"]), "swept" in name, speed,
+                              float(c["speed_dt"]) if speed else 0.0, cub=cub, vox=vox, mip=mip)
+        close(cost, c["cost"], 1e-4, "cost")
+        close(grad, c["grad"], 5e-4, "gradient")
+        assert np.array_equal(cost > 0, c["cost"] > 0)
+
+
+def test_warp_stand_in_semantics():
+    """The stand-in's own rules: C integer division, float32 arithmetic, xyzw quaternions, transform algebra."""
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "warp_shim")
+    sys.path.insert(0, shim)
+    try:
+        import warp as wp
+        assert wp.int32(7) / wp.int32(2) == 3 and isinstance(wp.int32(7) / 2, wp.int32) and (-wp.int32(7)) / 2 == -3
+        assert 9 / wp.int32(2) == 4 and wp.int32(7) % 4 == 3 and wp.int32(2.9) == 2
+        x = wp.float32(0.1) * 3.0
+        assert isinstance(x, np.float32)
+        assert wp.sign(wp.float32(0.0)) == 1 and wp.sign(wp.float32(-2.0)) == -1
+        q = wp.quat(0.0, 0.0, np.sin(np.pi / 4), np.cos(np.pi / 4))           # 90 degrees about z
+        v = wp.quat_rotate(q, wp.vec3(1.0, 0.0, 0.0))
+        assert np.allclose(v.v, [0, 1, 0], atol=1e-6)
+        t = wp.transform(wp.vec3(1.0, 2.0, 3.0), q)
+        p = wp.transform_point(t, wp.vec3(1.0, 0.0, 0.0))
+        assert np.allclose(p.v, [1, 3, 3], atol=1e-6)
+        back = wp.transform_point(wp.transform_inverse(t), p)
+        assert np.allclose(back.v, [1, 0, 0], atol=1e-6)
+        assert np.allclose((q * wp.quat_inverse(q)).v, [0, 0, 0, 1], atol=1e-6)
+        s = wp.float32(2.0) * wp.vec3(1.0, 2.0, 3.0)                          # numpy scalar on the left defers to the vector
+        assert isinstance(s, wp.vec3) and np.allclose(s.v, [2, 4, 6])
+        a = wp.from_numpy(np.zeros(4, np.float32))
+        wp.atomic_add(a, 2, wp.float32(1.5))
+        wp.atomic_add(a, 2, wp.float32(1.0))
+        assert a.data[2] == 2.5
+        seen = []
+
+        @wp.kernel
+        def k(out: wp.array(dtype=wp.int32), n: wp.int32):
+            t_ = wp.tid()
+            out[t_] = t_ / n
+            seen.append(type(t_))
+
+        o = wp.from_numpy(np.zeros(6, np.int32), dtype=wp.int32)
+        wp.launch(k, dim=6, inputs=[o, 4])
+        assert list(o.data) == [0, 0, 0, 0, 1, 1] and seen[0] is wp.int32
+    finally:
+        sys.path.remove(shim)
+        sys.modules.pop("warp", None)
+        for n in [n for n in sys.modules if n.startswith("warp.")]:
+            sys.modules.pop(n)
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_product_tool_pose_math_compiled_for_the_host_matches_the_reference_source(method):
+    """The product's tool_pose_cost (cb200_math.cuh, host build) per (batch, horizon, link) against the reference-source fixture."""
+    import ctypes as C
+    from helpers import hostmath, ptr
+    c = case(f"tool_pose_method{method}")
+    lib = hostmath()
+    B, H, L, _ = c["pos"].shape
+    NG = c["goal_pos"].shape[2]
+    for b in range(B):
+        for h in range(H):
+            term = (h == H - 1) or H == 1
+            for l in range(L):
+                axes = np.ascontiguousarray((c["axes_t"] if term else c["axes_nt"])[l], np.float32)
+                tol = (c["tol_t"] if term else c["tol_nt"])[l]
+                g = int(c["idxs_goal"][b])
+                out = np.zeros(12, np.float32)
+                idx = C.c_int(-1)
+                lib.hm_tool_pose(ptr(np.ascontiguousarray(c["pos"][b, h, l])), ptr(np.ascontiguousarray(c["quat"][b, h, l])),
+                                 ptr(np.ascontiguousarray(c["goal_pos"][g, l])), ptr(np.ascontiguousarray(c["goal_quat"][g, l])),
+                                 C.c_int(NG), C.c_float(c["weight"][0]), C.c_float(c["weight"][1]), ptr(axes), C.c_float(tol[0]),
+                                 C.c_float(tol[1]), C.c_int(method), ptr(out), C.byref(idx))
+                assert idx.value == c["goalset_idx"][b, h, l]
+                sc = max(float(np.abs(c["distance"]).max()), 1.0)
+                assert np.allclose(out[0:2], c["distance"][b, h, 2 * l:2 * l + 2], rtol=2e-4, atol=1e-5 * sc)
+                assert np.allclose(out[2], c["pos_dist"][b, h, l], rtol=2e-4, atol=1e-5)
+                assert np.allclose(out[3], c["rot_dist"][b, h, l], rtol=2e-4, atol=1e-5)
+                assert np.allclose(out[4:7], c["grad_pos"][b, h, l], rtol=5e-4, atol=1e-4 * float(np.abs(c["grad_pos"]).max()))
+                assert np.allclose(out[7:11], c["grad_quat"][b, h, l], rtol=2e-3, atol=2e-4 * float(np.abs(c["grad_quat"]).max()))
