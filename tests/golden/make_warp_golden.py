@@ -219,9 +219,44 @@ def gen_collision():
         save_world(case, cub, vox)
 
 
+def gen_collision_edges():
+    """Branch coverage: sphere centres inside cuboids (inside-gradient branch), on faces / edges, far away; an ESDF grid with a
+    rotated, offset pose, spheres outside the grid, on its border voxels and deep inside the box; large radii (both activation
+    regimes: pen < eta quadratic, pen >= eta linear); stationary and fast-moving trajectories for the sweep."""
+    rng = np.random.default_rng(5)
+    w, eta = 250.0, 0.04
+    cub = CuboidWorld.create([{"dims": [0.4, 0.3, 0.2], "pose": [0.1, 0.0, 0.1, 0.9, 0.1, 0.3, -0.2]},
+                              {"dims": [0.2, 0.6, 0.3], "pose": [-0.2, 0.2, 0.0, 0.6, -0.5, 0.4, 0.3]}], max_n=3)
+    vox = make_single_box_esdf(grid_dims=(0.6, 0.5, 0.4), voxel_size=0.025, grid_center=(0.05, -0.1, 0.15),
+                               box_half=(0.12, 0.1, 0.08), pose_quat=(0.85, 0.2, -0.3, 0.35)) if "pose_quat" in \
+        make_single_box_esdf.__code__.co_varnames else None
+    if vox is None:                                          # build the rotated grid by hand from an axis-aligned one
+        base = make_single_box_esdf(grid_dims=(0.6, 0.5, 0.4), voxel_size=0.025)
+        from curobo_b200.world import _inv_pose_from_pose
+        vox = VoxelWorld(base.params, _inv_pose_from_pose([0.05, -0.1, 0.15, 0.85, 0.2, -0.3, 0.35]).reshape(1, 1, 8), base.enable,
+                         base.count, base.features, base.max_dist)
+    B, H, S = 2, 5, 26
+    sph = np.zeros((B, H, S, 4), np.float32)
+    centres = np.concatenate([rng.uniform(-0.45, 0.45, size=(S - 8, 3)),
+                              np.array([[0.1, 0.0, 0.1], [0.12, 0.02, 0.11], [-0.2, 0.2, 0.0], [0.05, -0.1, 0.15],
+                                        [0.06, -0.09, 0.16], [2.0, 2.0, 2.0], [0.3, 0.0, 0.1], [0.05, -0.1, 0.33]])]).astype(np.float32)
+    sph[0, :, :, :3] = centres[None]                         # batch 0: stationary (swept == discrete there)
+    sph[1, 0, :, :3] = centres
+    for h in range(1, H):
+        sph[1, h, :, :3] = sph[1, h - 1, :, :3] + rng.normal(0, 0.12, size=(S, 3))   # batch 1: long jumps between waypoints
+    sph[..., 3] = rng.uniform(0.01, 0.15, size=(1, 1, S))
+    structs = [(cuboid_struct(cub), cub.max_n), (voxel_struct(vox), vox.max_n)]
+    for case, sweep, sdt in (("collision_edge_discrete", False, None), ("collision_edge_swept", True, None),
+                             ("collision_edge_swept_speed", True, 0.02)):
+        d, g = run_collision(sph, w, eta, structs, None, sweep, sdt)
+        put(case, spheres=sph, weight=np.float32(w), eta=np.float32(eta), cost=d, grad=g,
+            **({"speed_dt": np.float32(sdt)} if sdt is not None else {}))
+        save_world(case, cub, vox)
+
+
 if __name__ == "__main__":
     import time
-    for fn in (gen_cspace_state, gen_cspace_position, gen_tool_pose, gen_collision):
+    for fn in (gen_cspace_state, gen_cspace_position, gen_tool_pose, gen_collision, gen_collision_edges):
         t = time.time()
         fn()
         print(f"{fn.__name__}: {time.time() - t:.1f} s")

@@ -38,7 +38,8 @@ def worlds(c):
     return cub, vox
 
 
-@pytest.mark.parametrize("name", ["collision_discrete", "collision_multi_env", "collision_swept", "collision_swept_speed"])
+@pytest.mark.parametrize("name", ["collision_discrete", "collision_multi_env", "collision_swept", "collision_swept_speed",
+                                  "collision_edge_discrete", "collision_edge_swept", "collision_edge_swept_speed"])
 def test_scene_collision_matches_the_reference_source(name):
     c = case(name)
     cub, vox = worlds(c)
@@ -86,7 +87,8 @@ def test_cspace_position_cost_matches_the_reference_source():
     close(g, c["grad_p"], 1e-6, "grad_p")
 
 
-@pytest.mark.parametrize("name", ["collision_discrete", "collision_swept", "collision_swept_speed"])
+@pytest.mark.parametrize("name", ["collision_discrete", "collision_swept", "collision_swept_speed", "collision_edge_discrete",
+                                  "collision_edge_swept", "collision_edge_swept_speed"])
 def test_product_scene_math_compiled_for_the_host_matches_the_reference_source(name):
     """No oracle in between: the product's __host__ __device__ scene-collision arithmetic (curobo_b200/csrc/cb200_math.cuh,
     compiled for the host by tests/hostmath) against the reference-source fixture, including the exact ESDF cull level."""
