@@ -24,7 +24,7 @@ def launch_bspline_interpolation_forward_kernel(
     out_acceleration: torch.Tensor,
     out_jerk: torch.Tensor,
     out_dt: torch.Tensor,
-    knots: torch.Tensor,
+    u_position: torch.Tensor,
     start_position: torch.Tensor,
     start_velocity: torch.Tensor,
     start_acceleration: torch.Tensor,
@@ -38,16 +38,17 @@ def launch_bspline_interpolation_forward_kernel(
     traj_dt: torch.Tensor,
     use_implicit_goal_state: torch.Tensor,
     batch_size: int,
-    padded_horizon: int,
+    horizon: int,
     dof: int,
     n_knots: int,
     bspline_degree: int,
 ) -> None:
-    """knots [B,n_knots,D] -> position / velocity / acceleration / jerk [B,padded_horizon,D] (in place)."""
+    """u_position = knots [B,n_knots,D] -> position / velocity / acceleration / jerk [B,horizon,D] (in place); `horizon` is the
+    padded horizon.  Parameter names are the reference's (cuda_core_backend/trajectory.py:28-52)."""
     _check_degree(bspline_degree)
-    dev = knots.device
+    dev = u_position.device
     check_tensors(dev, torch.float32, out_position=out_position, out_velocity=out_velocity,
-                  out_acceleration=out_acceleration, out_jerk=out_jerk, out_dt=out_dt, knots=knots,
+                  out_acceleration=out_acceleration, out_jerk=out_jerk, out_dt=out_dt, u_position=u_position,
                   start_position=start_position, start_velocity=start_velocity, start_acceleration=start_acceleration,
                   start_jerk=start_jerk, goal_position=goal_position, goal_velocity=goal_velocity,
                   goal_acceleration=goal_acceleration, goal_jerk=goal_jerk, traj_dt=traj_dt)
@@ -56,10 +57,10 @@ def launch_bspline_interpolation_forward_kernel(
     L = _lib.load()
     err = L.cb200_bspline_forward(
         out_position.data_ptr(), out_velocity.data_ptr(), out_acceleration.data_ptr(), out_jerk.data_ptr(),
-        out_dt.data_ptr(), knots.data_ptr(), start_position.data_ptr(), start_velocity.data_ptr(),
+        out_dt.data_ptr(), u_position.data_ptr(), start_position.data_ptr(), start_velocity.data_ptr(),
         start_acceleration.data_ptr(), start_jerk.data_ptr(), goal_position.data_ptr(), goal_velocity.data_ptr(),
         goal_acceleration.data_ptr(), goal_jerk.data_ptr(), start_idx.data_ptr(), goal_idx.data_ptr(),
-        traj_dt.data_ptr(), use_implicit_goal_state.data_ptr(), int(batch_size), int(padded_horizon), int(dof),
+        traj_dt.data_ptr(), use_implicit_goal_state.data_ptr(), int(batch_size), int(horizon), int(dof),
         int(n_knots), int(bspline_degree), stream_ptr(dev))
     _lib.check(err, "launch_bspline_interpolation_forward_kernel")
 
