@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(kThreads) rnea_backward_cta(const __grid_const
   }
 }
 
+#ifndef CB200_SIMT_EMULATION  // everything below launches kernels: not part of the host emulation build (tests/simt)
 struct CtaPlan {
   int R = 0, smem = 0, grid = 0;
 };
@@ -475,8 +476,10 @@ bool model_ok(const Model &M) {
   return M.fixed_transforms && M.masses_com && M.inertias && M.joint_type && M.joint_map && M.link_map && M.joint_offset &&
          M.gravity && M.level_starts && M.level_links && M.nl >= 1 && M.nl <= 1024 && M.D >= 1 && M.n_levels >= 1;
 }
+#endif  // CB200_SIMT_EMULATION
 }  // namespace
 
+#ifndef CB200_SIMT_EMULATION
 extern "C" {
 
 int cb200_rnea_forward(float *tau, const float *q, const float *qd, const float *qdd, const float *fixed_transforms,
@@ -547,3 +550,4 @@ int cb200_rnea_backward(float *grad_q, float *grad_qd, float *grad_qdd, const fl
 }
 
 }  // extern "C"
+#endif  // CB200_SIMT_EMULATION

@@ -10,7 +10,9 @@
 // memory, one dependent load per row -- and the only HBM traffic is one coalesced read and one coalesced write of the grid
 // per pass: 3 x 8 B per voxel (the reference moves 6 x 8 B plus its stack look-ups).  Every pass is in place (a tile is
 // fully staged before its first row is written back), so the scratch `buffer` of the reference interface is not touched.
+#ifndef CB200_SIMT_EMULATION
 #include <cuda_fp16.h>
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(kLanes) edt_envelope_kernel(const __grid_const
   }
 }
 
+#ifndef CB200_SIMT_EMULATION  // fp16 output and everything that launches: not part of the host emulation build (tests/simt)
 __global__ void __launch_bounds__(256) edt_distance_kernel(const int *__restrict__ sites, __half *__restrict__ out, int ny, int nz,
                                                             long long total, float voxel_size, float empty_value) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -79,8 +82,10 @@ bool dims_ok(int nx, int ny, int nz) {
   return nx >= 1 && ny >= 1 && nz >= 1 && nx <= kMaxDim && ny <= kMaxDim && nz <= kMaxDim &&
          (long long)nx * ny * nz <= 2147483647LL;
 }
+#endif  // CB200_SIMT_EMULATION
 }  // namespace
 
+#ifndef CB200_SIMT_EMULATION
 extern "C" {
 
 int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, int m3, cb200_stream_t stream) {
@@ -112,3 +117,4 @@ int cb200_edt_unsigned_distance(const int32_t *site_index, uint16_t *distance_fp
 }
 
 }  // extern "C"
+#endif  // CB200_SIMT_EMULATION

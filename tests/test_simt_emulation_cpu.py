@@ -1,0 +1,99 @@
+"""Whole CUDA kernels executed on the CPU: tests/simt compiles a kernel translation unit of curobo_b200/csrc as ordinary C++
+(kernels become functions, threadIdx & co. are thread-local, __syncthreads() is a real barrier between the std::threads that
+play a CTA's threads, shared memory is a static buffer, atomicAdd is a real atomic) and runs CTAs one after another.  This
+value-checks kernel instantiations and schedules that the GPU tests of the last GPU session did not reach -- here every
+rows-per-CTA variant of the RNEA CTA kernels (the launcher resolves small test batches to 8 rows per CTA; the bench sizes use
+16 and 32) -- and exercises the barriers with genuinely concurrent threads."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from dynamics_cases import RANDOM_TREES, make_case, model_args, pack_cache, random_tree_case
+from helpers import ptr
+from oracle import dynamics_oracle as do
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMT = os.path.join(ROOT, "tests", "simt")
+
+
+def build(name, src_deps):
+    so = os.path.join(SIMT, f"libsimt_{name}.so")
+    deps = [os.path.join(SIMT, f"simt_{name}.cpp"), os.path.join(SIMT, "cuda_runtime.h")] + src_deps
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-w", "-I", SIMT, deps[0], "-o", so], check=True)
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    csrc = os.path.join(ROOT, "curobo_b200", "csrc")
+    return build("dynamics", [os.path.join(csrc, "cb200_dynamics.cu"), os.path.join(csrc, "cb200_dynamics.cuh")])
+
+
+def run(emu, c, R, grid):
+    B, nl, D, nlev = c["B"], c["nl"], c["D"], c["n_levels"]
+    m = [np.ascontiguousarray(x) for x in model_args(c)]
+    model = [ptr(x) for x in m] + [ptr(c["starts"]), ptr(c["order"])]
+    tau = np.full((B, D), np.nan, np.float32)
+    cache = np.zeros((B, nl * 20), np.float32)
+    assert emu.em_rnea_forward(R, grid, ptr(tau), ptr(c["q"]), ptr(c["qd"]), ptr(c["qdd"]), *model, ptr(cache), B, nl, D, nlev,
+                               None) == 0
+    g = [np.full((B, D), np.nan, np.float32) for _ in range(3)]
+    assert emu.em_rnea_backward(R, grid, *[ptr(x) for x in g], ptr(c["grad_tau"]), ptr(c["q"]), ptr(c["qd"]), *model, ptr(cache), B,
+                                nl, D, nlev, None) == 0
+    return tau, cache, g
+
+
+def check(c, tau, cache, g):
+    m = model_args(c)
+    tau_w, cache_w = do.rnea_forward(c["q"], c["qd"], c["qdd"], *m)
+    want = do.rnea_backward(c["grad_tau"], c["q"], c["qd"], cache_w, *m)
+    assert np.isfinite(tau).all() and all(np.isfinite(x).all() for x in g)
+    assert np.allclose(tau, tau_w, rtol=2e-4, atol=3e-5 * np.abs(tau_w).max())
+    cw = pack_cache(cache_w, c["nl"]).reshape(c["B"], c["nl"], 20)[:, :, :18]
+    assert np.allclose(cache.reshape(c["B"], c["nl"], 20)[:, :, :18], cw, rtol=2e-4, atol=3e-5 * np.abs(cw).max())
+    for got, w in zip(g, want):
+        assert np.allclose(got, w, rtol=5e-4, atol=1e-4 * max(float(np.abs(w).max()), 1e-6))
+
+
+@pytest.mark.parametrize("robot,B", [("franka", 70), ("g1_29", 37)])
+@pytest.mark.parametrize("R", [8, 16, 32])
+def test_rnea_cta_kernels_every_rows_per_cta_variant(emu, robot, B, R):
+    c = make_case(robot, B, 17)
+    grid = max(1, (B + R - 1) // R - 1)          # one CTA fewer than tiles: the grid-stride loop over row blocks is exercised
+    check(c, *run(emu, c, R, grid))
+
+
+@pytest.mark.parametrize("nl,B,seed,mimic", RANDOM_TREES)
+def test_rnea_cta_kernels_on_synthetic_trees(emu, nl, B, seed, mimic):
+    c = random_tree_case(nl, B + 9, seed, mimic)
+    check(c, *run(emu, c, 16, 1))
+
+
+# ------------------------------------------------------------------------------------------------ nearest-site transform
+@pytest.fixture(scope="module")
+def emu_edt():
+    csrc = os.path.join(ROOT, "curobo_b200", "csrc")
+    return build("edt", [os.path.join(csrc, "cb200_edt.cu"), os.path.join(csrc, "cb200_edt.cuh")])
+
+
+def test_edt_kernels_executed_by_threads(emu_edt):
+    """edt_flood_z_kernel / edt_envelope_kernel<1> / <0> themselves (not a restatement of their schedule): 32 std::threads per
+    one-warp CTA, __syncwarp() as a real barrier, the grid-stride loop over tiles with fewer CTAs than tiles."""
+    from scipy import ndimage
+    from edt_cases import MEDIUM, SMALL, occupancy
+    from oracle import edt_oracle as E
+    for kind, shape, p in SMALL + MEDIUM[:3]:
+        occ = occupancy(kind, shape, seed=13, p=p)
+        g = np.ascontiguousarray(E.seed_grid(occ))
+        assert emu_edt.em_pba3d(g.ctypes.data_as(C.c_void_p), *[int(v) for v in shape], 3) == 0
+        d2 = E.squared_distance(g)
+        if not occ.any():
+            assert (g == E.EMPTY).all()
+            continue
+        sx, sy, sz = E.unpack(g)
+        assert (g >= 0).all() and occ[sx, sy, sz].all()
+        assert np.array_equal(d2, np.rint(ndimage.distance_transform_edt(~occ) ** 2).astype(np.int64)), (kind, shape)
