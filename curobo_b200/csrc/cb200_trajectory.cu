@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) bspline_backward_kernel(const __grid_cons
   }
 }
 
+#ifndef CB200_SIMT_EMULATION  // everything below launches kernels: not part of the host emulation build (tests/simt)
 int grid_for(long long n, int block) {
   long long g = (n + block - 1) / block;
   int dev = 0, sms = 148;
@@ -114,8 +115,10 @@ int launch_forward(const FwdArgs &a, int degree, cudaStream_t stream) {
   }
   return status(cudaGetLastError());
 }
+#endif  // CB200_SIMT_EMULATION
 }  // namespace
 
+#ifndef CB200_SIMT_EMULATION
 extern "C" {
 
 int cb200_bspline_forward(float *out_position, float *out_velocity, float *out_acceleration, float *out_jerk, float *out_dt,
@@ -170,3 +173,4 @@ int cb200_bspline_backward(float *out_grad_knots, const float *grad_position, co
 }
 
 }  // extern "C"
+#endif  // CB200_SIMT_EMULATION

@@ -3,6 +3,7 @@
 // are thread-local, __syncthreads() is a real barrier across the std::threads that play the CTA's threads, shared memory is a
 // static buffer (CTAs run one after another), atomicAdd is a real atomic.  Races between barriers are therefore real races.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <barrier>
 #include <cmath>
@@ -24,6 +25,9 @@
 #ifndef __restrict__
 #define __restrict__ __restrict
 #endif
+
+using std::max;
+using std::min;
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;

@@ -97,3 +97,34 @@ def test_edt_kernels_executed_by_threads(emu_edt):
         sx, sy, sz = E.unpack(g)
         assert (g >= 0).all() and occ[sx, sy, sz].all()
         assert np.array_equal(d2, np.rint(ndimage.distance_transform_edt(~occ) ** 2).astype(np.int64)), (kind, shape)
+
+
+# ------------------------------------------------------------------------------------------------ B-spline kernels
+@pytest.fixture(scope="module")
+def emu_traj():
+    csrc = os.path.join(ROOT, "curobo_b200", "csrc")
+    return build("trajectory", [os.path.join(csrc, "cb200_trajectory.cu"), os.path.join(csrc, "cb200_bspline.cuh")])
+
+
+def test_bspline_kernels_executed_by_threads(emu_traj):
+    """bspline_forward_kernel<3|4|5> and bspline_backward_kernel<3|4|5> themselves against the B-spline oracle (all boundary
+    modes, mixed implicit goals, non power-of-two steps), with a grid smaller than the work so the grid-stride loops run."""
+    from bspline_cases import CASES, make_case
+    from oracle import bspline_oracle as bo
+    for kw in CASES:
+        c = make_case(**kw)
+        B, T, D, nk, deg = c["B"], c["T"], c["D"], c["nk"], c["degree"]
+        outs = [np.full((B, T, D), np.nan, np.float32) for _ in range(4)]
+        odt = np.zeros(B, np.float32)
+        assert emu_traj.em_bspline_forward(2, *[ptr(o) for o in outs], ptr(odt), ptr(c["knots"]), *[ptr(x) for x in c["start"]],
+                                           *[ptr(x) for x in c["goal"]], ptr(c["start_idx"]), ptr(c["goal_idx"]), ptr(c["traj_dt"]),
+                                           ptr(c["implicit"]), None, B, T, D, nk, deg) == 0
+        want = bo.bspline_forward(c["knots"], c["start"], c["goal"], c["start_idx"], c["goal_idx"], c["traj_dt"], c["implicit"], T, deg)
+        for got, w in zip(outs, want[:4]):
+            assert np.allclose(got, w, rtol=2e-5, atol=2e-5 * max(1.0, float(np.abs(w).max()))), kw
+        assert np.allclose(odt, c["traj_dt"][c["goal_idx"]])
+        gk = np.full((B, nk, D), np.nan, np.float32)
+        assert emu_traj.em_bspline_backward(2, ptr(gk), *[ptr(np.ascontiguousarray(g)) for g in c["grads"]], ptr(c["traj_dt"]),
+                                            ptr(c["goal_idx"]), ptr(c["implicit"]), B, T, D, nk, deg) == 0
+        wk = bo.bspline_backward(*c["grads"], c["traj_dt"], c["goal_idx"], c["implicit"], nk, deg)
+        assert np.allclose(gk, wk, rtol=1e-4, atol=1e-5 * float(np.abs(wk).max())), kw
