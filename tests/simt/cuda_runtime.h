@@ -52,8 +52,16 @@ inline thread_local int t_lane_group = 0;
 #define blockDim (simt::t_blockDim)
 #define gridDim (simt::t_gridDim)
 
+#ifdef CB200_SIMT_DROP_BARRIERS  // mutation switch for the race-detector self-test: barriers do nothing
+inline void __syncthreads() {}
+#else
 inline void __syncthreads() { simt::t_barrier->arrive_and_wait(); }
+#endif
+#ifdef CB200_SIMT_DROP_BARRIERS
+inline void __syncwarp() {}
+#else
 inline void __syncwarp() { simt::t_barrier->arrive_and_wait(); }  // conservative: a CTA-wide barrier (used with 1-warp CTAs only)
+#endif
 inline float atomicAdd(float *p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 template <class T>
 inline T __ldg(const T *p) { return *p; }

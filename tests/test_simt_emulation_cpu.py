@@ -128,3 +128,65 @@ def test_bspline_kernels_executed_by_threads(emu_traj):
                                             ptr(c["goal_idx"]), ptr(c["implicit"]), B, T, D, nk, deg) == 0
         wk = bo.bspline_backward(*c["grads"], c["traj_dt"], c["goal_idx"], c["implicit"], nk, deg)
         assert np.allclose(gk, wk, rtol=1e-4, atol=1e-5 * float(np.abs(wk).max())), kw
+
+
+# ------------------------------------------------------------------------------------------------ race detection
+def test_rnea_cta_kernels_are_race_free_under_thread_sanitizer(tmp_path):
+    """The same kernels, instrumented with ThreadSanitizer: with CTA threads as real threads and __syncthreads() as a real barrier,
+    a missing barrier in the kernel source (two phases touching the same shared-memory slot without a barrier between them)
+    is a data race TSan reports.  All three rows-per-CTA variants, forward and adjoint, on a synthetic tree with mimic joints."""
+    exe = os.path.join(SIMT, "tsan_dynamics")
+    src = os.path.join(SIMT, "tsan_dynamics_main.cpp")
+    csrc = os.path.join(ROOT, "curobo_b200", "csrc")
+    deps = [src, os.path.join(SIMT, "simt_dynamics.cpp"), os.path.join(SIMT, "cuda_runtime.h"), os.path.join(csrc, "cb200_dynamics.cu"),
+            os.path.join(csrc, "cb200_dynamics.cuh")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-w", "-I", SIMT, src, "-o", exe],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("ThreadSanitizer build not available: " + r.stderr[-300:])
+    c = random_tree_case(17, 21, 32, True)
+    m = [np.ascontiguousarray(x) for x in model_args(c)]
+
+    def pad(a):
+        b = np.ascontiguousarray(a).tobytes()
+        return b + b"\0" * ((16 - len(b) % 16) % 16)
+
+    blob = b"".join(pad(x) for x in [np.array([c["B"], c["nl"], c["D"], c["n_levels"]], np.int32), c["q"], c["qd"], c["qdd"],
+                                     c["grad_tau"], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], c["starts"], c["order"]])
+    path = tmp_path / "case.bin"
+    path.write_bytes(blob)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66 report_signal_unsafe=0")
+    r = subprocess.run([exe, str(path)], capture_output=True, text=True, env=env, timeout=600)
+    if r.returncode != 0 and "FATAL: ThreadSanitizer" in r.stderr and "data race" not in r.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this environment: " + r.stderr[-200:])
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.returncode, r.stdout[-200:], r.stderr[-1500:])
+
+
+def _tsan_build(src_name, exe_name, extra=()):
+    exe, src = os.path.join(SIMT, exe_name), os.path.join(SIMT, src_name)
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-w", *extra, "-I", SIMT, src, "-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("ThreadSanitizer build not available: " + r.stderr[-300:])
+    return exe
+
+
+def _tsan_run(cmd):
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66 report_signal_unsafe=0")
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    if r.returncode != 0 and "FATAL: ThreadSanitizer" in r.stderr and "data race" not in r.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this environment: " + r.stderr[-200:])
+    return r
+
+
+def test_edt_kernels_are_race_free_under_thread_sanitizer():
+    r = _tsan_run([_tsan_build("tsan_edt_main.cpp", "tsan_edt")])
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.returncode, r.stdout[-200:], r.stderr[-1500:])
+
+
+def test_race_detector_has_teeth():
+    """Mutation: the same EDT kernels with every barrier compiled out (-DCB200_SIMT_DROP_BARRIERS): the flood pass then reads
+    tile rows other lanes are still writing, and ThreadSanitizer must say so (exit code 66)."""
+    r = _tsan_run([_tsan_build("tsan_edt_main.cpp", "tsan_edt_nobarrier", ("-DCB200_SIMT_DROP_BARRIERS",))])
+    assert r.returncode == 66 and "data race" in r.stderr, (r.returncode, r.stderr[-500:])
