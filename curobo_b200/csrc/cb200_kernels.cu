@@ -21,6 +21,7 @@
 #include "../../include/curobo_b200.h"
 #include "cb200_blob.h"
 #include "cb200_bspline.cuh"
+#include "cb200_launch.h"
 #include "cb200_math.cuh"
 #include "cb200_warp.cuh"
 
@@ -1770,7 +1771,7 @@ int cb200_kinematics_forward_spheres(float *link_pos, float *link_quat, float *b
     if (e != cudaSuccess) return ret(e);
   }
   const int grid = persistent_grid(kin_forward_kernel, kWarpsPerCta * 32, smem, (batch_size + kWarpsPerCta - 1) / kWarpsPerCta);
-  kin_forward_kernel<<<grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(kin_forward_kernel, grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream, a);
   return launch_status();
 }
 
@@ -1808,7 +1809,7 @@ int cb200_kinematics_backward(float *grad_out, const float *grad_nlinks_pos, con
     if (e != cudaSuccess) return ret(e);
   }
   const int grid = persistent_grid(kin_backward_kernel, kWarpsPerCta * 32, smem, (batch_size + kWarpsPerCta - 1) / kWarpsPerCta);
-  kin_backward_kernel<<<grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(kin_backward_kernel, grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream, a);
   return launch_status();
 }
 
@@ -1834,11 +1835,11 @@ int cb200_self_collision_distance(float *out_distance, float *out_vec, float *pa
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(self_collision_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return ret(e);
     const int grid = persistent_grid(self_collision_kernel<32>, 256, smem, (N + 7) / 8);
-    self_collision_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    CB200_LAUNCH(self_collision_kernel<32>, grid, 256, smem, (cudaStream_t)stream, a);
   } else {
     const size_t smem = (size_t)nspheres * 16;
     const int grid = persistent_grid(self_collision_kernel<256>, 256, smem, N);
-    self_collision_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+    CB200_LAUNCH(self_collision_kernel<256>, grid, 256, smem, (cudaStream_t)stream, a);
   }
   return launch_status();
 }
@@ -1853,7 +1854,7 @@ static int scene_launch(float *distance, float *gradient, const float *spheres, 
   SceneArgs a{distance, gradient, spheres, weight, eta, speed_dt, to_dev(cuboids), to_dev(voxels), env_query_idx,
               B, H, S, use_multi_env && env_query_idx != nullptr, sweep, speed_metric};
   const int grid = persistent_grid(scene_collision_kernel, 128, 0, (total + 127) / 128);
-  scene_collision_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(scene_collision_kernel, grid, 128, 0, (cudaStream_t)stream, a);
   return launch_status();
 }
 
@@ -1892,7 +1893,7 @@ int cb200_tool_pose_distance(float *out_distance, float *out_position_distance, 
              terminal_pose_convergence_tolerance, non_terminal_pose_convergence_tolerance, idxs_goal, batch_size,
              horizon, num_links, num_goalset, rotation_method};
   const int grid = persistent_grid(tool_pose_kernel, 128, 0, (total + 127) / 128);
-  tool_pose_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(tool_pose_kernel, grid, 128, 0, (cudaStream_t)stream, a);
   return launch_status();
 }
 
@@ -1915,7 +1916,7 @@ int cb200_cspace_state_cost(float *out_cost, float *out_grad_p, float *out_grad_
                 cspace_target_dof_weight, idxs_target_joint_position, write_grad, batch_size, horizon, dof,
                 retime_weights, retime_regularization_weights};
   const int grid = persistent_grid(cspace_state_kernel, 128, 0, (total + 127) / 128);
-  cspace_state_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(cspace_state_kernel, grid, 128, 0, (cudaStream_t)stream, a);
   return launch_status();
 }
 
@@ -1935,7 +1936,7 @@ int cb200_cspace_position_cost(float *out_cost, float *out_grad_p, float *out_gr
               current_position, current_velocity, v_b, state_dt, cspace_target_idx, idxs_current_state, write_grad,
               batch_size, horizon, dof};
   const int grid = persistent_grid(cspace_position_kernel, 128, 0, (total + 127) / 128);
-  cspace_position_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(cspace_position_kernel, grid, 128, 0, (cudaStream_t)stream, a);
   return launch_status();
 }
 
@@ -2024,7 +2025,7 @@ int cb200_voxel_build_mip(const cb200_voxel_set *vs, cb200_stream_t stream) {
   const int n_layers = vs->max_n * vs->num_envs;
   const long long n = (long long)vs->mip_stride * n_layers;
   const int grid = (int)std::min<long long>((n + 127) / 128, 148LL * 16);
-  voxel_mip_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(to_dev(vs), const_cast<uint16_t *>(vs->mip), n_layers);
+  CB200_LAUNCH(voxel_mip_kernel, grid, 128, 0, (cudaStream_t)stream, to_dev(vs), const_cast<uint16_t *>(vs->mip), n_layers);
   return launch_status();
 }
 
@@ -2333,7 +2334,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       const long long need = (N + kLaneThreads - 1) / kLaneThreads;
       long long g = (long long)d.sm_count * lane_per_sm[scene];
       if (g > need) g = need;
-      lk<<<(int)g, kLaneThreads, ll.total_bytes, (cudaStream_t)stream>>>(a);
+      CB200_LAUNCH(lk, (int)g, kLaneThreads, ll.total_bytes, (cudaStream_t)stream, a);
       return launch_status();
     }
   }
@@ -2364,7 +2365,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       const long long n_tiles = (N + tl.T - 1) / tl.T;
       long long g = (long long)d.sm_count * tile_per_sm[scene];
       if (g > n_tiles) g = n_tiles;
-      tk<<<(int)g, kWarpsPerCta * 32, tl.total_bytes, (cudaStream_t)stream>>>(a);
+      CB200_LAUNCH(tk, (int)g, kWarpsPerCta * 32, tl.total_bytes, (cudaStream_t)stream, a);
       return launch_status();
     }
   }
@@ -2429,7 +2430,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   const long long need_ctas = traj ? (long long)io->batch_size * ((io->horizon + nw - 1) / nw) : (N + nw - 1) / nw;
   if (grid_ll > need_ctas) grid_ll = need_ctas;
   const int grid = (int)(grid_ll < 1 ? 1 : grid_ll);
-  kern<<<grid, nw * 32, smem, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(kern, grid, nw * 32, smem, (cudaStream_t)stream, a);
   return finish();
 }
 

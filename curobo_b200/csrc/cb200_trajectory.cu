@@ -12,6 +12,7 @@
 
 #include "../../include/curobo_b200.h"
 #include "cb200_bspline.cuh"
+#include "cb200_launch.h"
 
 namespace {
 using namespace cb200::bspline;
@@ -92,7 +93,6 @@ __global__ void __launch_bounds__(256) bspline_backward_kernel(const __grid_cons
   }
 }
 
-#ifndef CB200_SIMT_EMULATION  // everything below launches kernels: not part of the host emulation build (tests/simt)
 int grid_for(long long n, int block) {
   long long g = (n + block - 1) / block;
   int dev = 0, sms = 148;
@@ -108,17 +108,15 @@ int launch_forward(const FwdArgs &a, int degree, cudaStream_t stream) {
   const long long n = (long long)a.B * a.T * a.D;
   const int grid = grid_for(n, 256);
   switch (degree) {
-    case 3: bspline_forward_kernel<3><<<grid, 256, 0, stream>>>(a); break;
-    case 4: bspline_forward_kernel<4><<<grid, 256, 0, stream>>>(a); break;
-    case 5: bspline_forward_kernel<5><<<grid, 256, 0, stream>>>(a); break;
+    case 3: CB200_LAUNCH(bspline_forward_kernel<3>, grid, 256, 0, stream, a); break;
+    case 4: CB200_LAUNCH(bspline_forward_kernel<4>, grid, 256, 0, stream, a); break;
+    case 5: CB200_LAUNCH(bspline_forward_kernel<5>, grid, 256, 0, stream, a); break;
     default: return status(cudaErrorInvalidValue);
   }
   return status(cudaGetLastError());
 }
-#endif  // CB200_SIMT_EMULATION
 }  // namespace
 
-#ifndef CB200_SIMT_EMULATION
 extern "C" {
 
 int cb200_bspline_forward(float *out_position, float *out_velocity, float *out_acceleration, float *out_jerk, float *out_dt,
@@ -165,12 +163,11 @@ int cb200_bspline_backward(float *out_grad_knots, const float *grad_position, co
   const long long n = (long long)batch_size * n_knots * dof;
   const int grid = grid_for(n, 128);
   switch (bspline_degree) {
-    case 3: bspline_backward_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(a); break;
-    case 4: bspline_backward_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(a); break;
-    default: bspline_backward_kernel<5><<<grid, 128, 0, (cudaStream_t)stream>>>(a); break;
+    case 3: CB200_LAUNCH(bspline_backward_kernel<3>, grid, 128, 0, (cudaStream_t)stream, a); break;
+    case 4: CB200_LAUNCH(bspline_backward_kernel<4>, grid, 128, 0, (cudaStream_t)stream, a); break;
+    default: CB200_LAUNCH(bspline_backward_kernel<5>, grid, 128, 0, (cudaStream_t)stream, a); break;
   }
   return status(cudaGetLastError());
 }
 
 }  // extern "C"
-#endif  // CB200_SIMT_EMULATION

@@ -498,6 +498,15 @@ __device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, con
 // ----------------------------------------------------------------------------------------------
 // Bulk async copy (TMA 1-D) of the blob prefix into shared memory, completion on an mbarrier.
 // ----------------------------------------------------------------------------------------------
+#ifdef CB200_SIMT_EMULATION
+// host emulation build (tests/simt): no TMA engine -- the CTA's threads copy the blob and meet at a barrier
+__device__ __forceinline__ void stage_blob_to_smem(unsigned char *dst, const unsigned char *src, uint32_t bytes,
+                                                   unsigned long long *mbar) {
+  (void)mbar;
+  for (uint32_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void stage_blob_to_smem(unsigned char *dst, const unsigned char *src, uint32_t bytes,
@@ -526,5 +535,6 @@ __device__ __forceinline__ void stage_blob_to_smem(unsigned char *dst, const uns
         : "memory");
   }
 }
+#endif  // CB200_SIMT_EMULATION
 
 }  // namespace cb200

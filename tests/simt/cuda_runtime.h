@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -33,6 +34,36 @@ typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorInvalidConfiguration = 9 };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated error"; }
+// a small imaginary device: 2 SMs, B200-sized shared memory, two resident CTAs per SM for every kernel
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaFuncAttributes {
+  size_t sharedSizeBytes = 0, constSizeBytes = 0, localSizeBytes = 0;
+  int maxThreadsPerBlock = 1024, numRegs = 64, maxDynamicSharedSizeBytes = 232448;
+};
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) {
+  *v = a == cudaDevAttrMultiProcessorCount ? 2 : 232448;
+  return cudaSuccess;
+}
+template <class K>
+inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class K>
+inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, K) { *a = cudaFuncAttributes(); return cudaSuccess; }
+template <class K>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 2; return cudaSuccess; }
+
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 
 struct float4 {
   float x, y, z, w;
@@ -44,8 +75,14 @@ struct uint3 {
 
 namespace simt {
 inline thread_local uint3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
-inline thread_local std::barrier<> *t_barrier = nullptr;
-inline thread_local int t_lane_group = 0;
+inline thread_local std::barrier<> *t_barrier = nullptr;       // the CTA
+struct Warp {                                                  // one per 32 consecutive CTA threads
+  std::barrier<> bar;
+  unsigned long long slot[32];
+  explicit Warp(int lanes) : bar(lanes) {}
+};
+inline thread_local Warp *t_warp = nullptr;
+inline thread_local int t_lane = 0;
 }  // namespace simt
 #define threadIdx (simt::t_threadIdx)
 #define blockIdx (simt::t_blockIdx)
@@ -58,10 +95,70 @@ inline void __syncthreads() {}
 inline void __syncthreads() { simt::t_barrier->arrive_and_wait(); }
 #endif
 #ifdef CB200_SIMT_DROP_BARRIERS
-inline void __syncwarp() {}
+inline void __syncwarp(unsigned = 0xffffffffu) {}
 #else
-inline void __syncwarp() { simt::t_barrier->arrive_and_wait(); }  // conservative: a CTA-wide barrier (used with 1-warp CTAs only)
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::t_warp->bar.arrive_and_wait(); }
 #endif
+
+// Warp collectives, full-mask and convergent (the only form the kernels of this repository use): every lane publishes its
+// value, the warp meets, every lane reads, the warp meets again so the slots can be reused.
+namespace simt {
+template <class T>
+inline unsigned long long to_bits(T v) {
+  static_assert(sizeof(T) <= 8, "collective payload");
+  unsigned long long b = 0;
+  std::memcpy(&b, &v, sizeof(T));
+  return b;
+}
+template <class T>
+inline T from_bits(unsigned long long b) {
+  T v;
+  std::memcpy(&v, &b, sizeof(T));
+  return v;
+}
+template <class T, class F>
+inline T exchange(T v, F pick) {
+  Warp &w = *t_warp;
+  w.slot[t_lane] = to_bits(v);
+  w.bar.arrive_and_wait();
+  const T r = pick(w.slot);
+  w.bar.arrive_and_wait();
+  return r;
+}
+}  // namespace simt
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+  const int base = simt::t_lane & ~(width - 1);
+  return simt::exchange(v, [&](const unsigned long long *s) { return simt::from_bits<T>(s[base + (src & (width - 1))]); });
+}
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask, int width = 32) {
+  const int src = simt::t_lane ^ lane_mask;
+  const bool ok = (src & ~(width - 1)) == (simt::t_lane & ~(width - 1));
+  return simt::exchange(v, [&](const unsigned long long *s) { return simt::from_bits<T>(s[ok ? src : simt::t_lane]); });
+}
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, unsigned delta, int width = 32) {
+  const int src = simt::t_lane + (int)delta;
+  const bool ok = (src & ~(width - 1)) == (simt::t_lane & ~(width - 1));
+  return simt::exchange(v, [&](const unsigned long long *s) { return simt::from_bits<T>(s[ok ? src : simt::t_lane]); });
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  return simt::exchange((unsigned)(pred != 0), [&](const unsigned long long *s) {
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= (unsigned)(s[i] & 1ull) << i;
+    return m;
+  });
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+  return simt::exchange(v, [&](const unsigned long long *s) { unsigned r = 0; for (int i = 0; i < 32; ++i) r += (unsigned)s[i]; return r; });
+}
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  return simt::exchange(v, [&](const unsigned long long *s) { unsigned r = ~0u; for (int i = 0; i < 32; ++i) r = std::min(r, (unsigned)s[i]); return r; });
+}
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+  return simt::exchange(v, [&](const unsigned long long *s) { unsigned r = 0; for (int i = 0; i < 32; ++i) r = std::max(r, (unsigned)s[i]); return r; });
+}
 inline float atomicAdd(float *p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
@@ -71,16 +168,26 @@ inline T __ldg(const T *p) { return *p; }
 // (a block-scope `extern` inside a kernel in an unnamed namespace names a member of that namespace: the kernels of this
 // repository all live in unnamed namespaces, so the buffers do too)
 namespace {
+#ifdef CB200_SIMT_SMEM_DECL
+CB200_SIMT_SMEM_DECL
+#else
 alignas(16) float smem[96 * 1024];
 alignas(16) int tile[96 * 1024];
+#endif
 }  // namespace
 
 namespace simt {
-// run `grid` CTAs of `block` threads one CTA after another; every CTA thread is a std::thread
-template <class Kernel, class Args>
-void launch(Kernel kern, int grid, int block, const Args &args) {
+// run `grid` CTAs of `block` threads one CTA after another; every CTA thread is a std::thread.  Inactive slots of the last
+// (partial) warp hold zero in collectives: the kernels of this repository launch whole warps whenever they use collectives.
+template <class Kernel, class... Args>
+void launch(Kernel kern, int grid, int block, const Args &...args) {
   for (int b = 0; b < grid; ++b) {
     std::barrier<> bar(block);
+    std::vector<std::unique_ptr<Warp>> warps;
+    for (int w = 0; w * 32 < block; ++w) {
+      warps.emplace_back(new Warp(std::min(32, block - w * 32)));
+      std::memset(warps.back()->slot, 0, sizeof(warps.back()->slot));
+    }
     std::vector<std::thread> ts;
     ts.reserve(block);
     for (int t = 0; t < block; ++t)
@@ -90,8 +197,11 @@ void launch(Kernel kern, int grid, int block, const Args &args) {
         t_blockDim = uint3{(unsigned)block, 1, 1};
         t_gridDim = uint3{(unsigned)grid, 1, 1};
         t_barrier = &bar;
-        kern(args);
-        bar.arrive_and_drop();  // a thread that has left the kernel no longer takes part in barriers
+        t_warp = warps[t / 32].get();
+        t_lane = t % 32;
+        kern(args...);
+        t_warp->bar.arrive_and_drop();  // a thread that has left the kernel no longer takes part in barriers
+        bar.arrive_and_drop();
       });
     for (auto &th : ts) th.join();
   }

@@ -19,11 +19,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIMT = os.path.join(ROOT, "tests", "simt")
 
 
-def build(name, src_deps):
+def build(name, src_deps, extra_units=()):
     so = os.path.join(SIMT, f"libsimt_{name}.so")
-    deps = [os.path.join(SIMT, f"simt_{name}.cpp"), os.path.join(SIMT, "cuda_runtime.h")] + src_deps
+    units = [os.path.join(SIMT, f"simt_{name}.cpp")] + [os.path.join(SIMT, u) for u in extra_units]
+    deps = units + [os.path.join(SIMT, "cuda_runtime.h")] + src_deps
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-w", "-I", SIMT, deps[0], "-o", so], check=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-w", "-I", SIMT, *units, "-o", so], check=True)
     return C.CDLL(so)
 
 
@@ -190,3 +191,70 @@ def test_race_detector_has_teeth():
     tile rows other lanes are still writing, and ThreadSanitizer must say so (exit code 66)."""
     r = _tsan_run([_tsan_build("tsan_edt_main.cpp", "tsan_edt_nobarrier", ("-DCB200_SIMT_DROP_BARRIERS",))])
     assert r.returncode == 66 and "data race" in r.stderr, (r.returncode, r.stderr[-500:])
+
+
+# ------------------------------------------------------------------------------------------------ the fused rollout kernels
+@pytest.fixture(scope="module")
+def emu_main():
+    """The product's main translation unit (fused kernels + per-operator kernels + blob packer + the whole C ABI with its launch
+    logic) as a host library: same cb200_* symbols and signatures as libcurobo_b200.so, host pointers instead of device pointers."""
+    from curobo_b200 import lib as cblib
+    csrc = os.path.join(ROOT, "curobo_b200", "csrc")
+    deps = [os.path.join(csrc, f) for f in ("cb200_kernels.cu", "cb200_trajectory.cu", "cb200_warp.cuh", "cb200_math.cuh",
+                                            "cb200_blob.h", "cb200_bspline.cuh", "cb200_launch.h")] + [os.path.join(SIMT, "cuda_fp16.h")]
+    L = build("kernels", deps, extra_units=("simt_trajectory_abi.cpp",))
+    for name, (args, res) in cblib._SIGS.items():
+        if hasattr(L, name):
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = args, res
+    assert L.cb200_abi_version() == 3
+    return L
+
+
+def host_engine(emu_main, monkeypatch, rm, cfg, cuboid=None, voxel=None):
+    """A RolloutEngine whose native library is the emulated one and whose tensors live on the host.  Built around __init__
+    (which refuses non-CUDA devices: the product has no CPU path and this does not add one -- the swap exists only here)."""
+    import torch
+    from curobo_b200 import rollout as R
+    from curobo_b200.scene import c_cuboid_set, c_voxel_set
+    monkeypatch.setattr(R, "check_tensors", lambda *a, **k: None)
+    monkeypatch.setattr(R, "stream_ptr", lambda d: 0)
+    eng = R.RolloutEngine.__new__(R.RolloutEngine)
+    eng.robot, eng.cfg, eng.device = rm, cfg, torch.device("cpu")
+    eng._lib = emu_main
+    eng._blob_host = R.pack_robot_blob(rm)
+    eng._blob = torch.from_numpy(eng._blob_host.copy())
+    eng.cuboid, eng.voxel, eng.use_voxel_mip = cuboid, voxel, False
+    eng._cs, eng._vs = c_cuboid_set(cuboid, None), c_voxel_set(voxel, None)
+    eng.store_fk_outputs = False
+    eng._B = eng._H = -1
+    eng._goal = None
+    eng._ccfg = eng._make_ccfg(1)
+    return eng
+
+
+def test_fused_ik_rollout_kernel_executed_by_threads(emu_main, monkeypatch):
+    """rollout_fused_kernel (warp per evaluation: FK, spheres, self-collision, cuboid collision, tool pose, c-space, J^T backward,
+    with its shuffles / ballots / warp reductions and the blob staging) and the launcher around it, on the smoke() problem."""
+    import torch
+    from curobo_b200.robot_model import load_robot
+    from curobo_b200.rollout import RolloutConfig
+    from curobo_b200.scene import CuboidData
+    from curobo_b200.world import make_benchmark_cuboid_world
+    from helpers import random_q
+    from oracle import rollout_oracle as O
+    rm = load_robot("franka")
+    B = 40
+    q = random_q(rm, B, seed=3)[:, None, :]
+    _, _, gp, gq = O.fk_forward(rm, random_q(rm, 4, seed=4))
+    goal = (gp[:, :, None, :].copy(), gq[:, :, None, :].copy())
+    idx = (np.arange(B) % 4).astype(np.int32)
+    cub = make_benchmark_cuboid_world()
+    cfg = RolloutConfig.ik()
+    eng = host_engine(emu_main, monkeypatch, rm, cfg, cuboid=CuboidData.from_world(cub, "cpu"))
+    eng.update_goal(torch.as_tensor(goal[0]), torch.as_tensor(goal[1]), torch.as_tensor(idx))
+    out = eng.evaluate_action(torch.as_tensor(q))
+    want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(1), world_cuboid=cub, goal_pos=goal[0], goal_quat=goal[1], idxs_goal=idx)
+    np.testing.assert_allclose(out.cost.numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    g = want["grad_q"]
+    np.testing.assert_allclose(out.grad_q.numpy(), g, rtol=2e-3, atol=2e-5 * np.abs(g).max())
