@@ -166,6 +166,7 @@ def test_rnea_cta_kernels_are_race_free_under_thread_sanitizer(tmp_path):
 
 def _tsan_build(src_name, exe_name, extra=()):
     exe, src = os.path.join(SIMT, exe_name), os.path.join(SIMT, src_name)
+    extra = [os.path.join(ROOT, e) if e.endswith(".cpp") else e for e in extra]
     r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-w", *extra, "-I", SIMT, src, "-o", exe],
                        capture_output=True, text=True)
     if r.returncode != 0:
@@ -258,3 +259,124 @@ def test_fused_ik_rollout_kernel_executed_by_threads(emu_main, monkeypatch):
     np.testing.assert_allclose(out.cost.numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
     g = want["grad_q"]
     np.testing.assert_allclose(out.grad_q.numpy(), g, rtol=2e-3, atol=2e-5 * np.abs(g).max())
+
+
+@pytest.mark.parametrize("B,H,speed", [(2, 9, True), (2, 5, False)])
+def test_trajectory_rollout_kernel_executed_by_threads(emu_main, monkeypatch, B, H, speed):
+    """rollout_traj_kernel (CTA per trajectory chunk, neighbour waypoints through shared memory, swept collision over cuboids and
+    an fp16 ESDF, speed metric, STATE c-space with retimed weights, terminal-only pose) + the launcher's trajectory path."""
+    import torch
+    from curobo_b200.robot_model import load_robot
+    from curobo_b200.rollout import RolloutConfig
+    from curobo_b200.scene import CuboidData, VoxelData
+    from curobo_b200.world import make_benchmark_cuboid_world
+    from helpers import random_q, random_walk_q, small_voxel_world
+    from oracle import rollout_oracle as O
+    rm = load_robot("franka")
+    q = random_walk_q(rm, B, H, seed=60 + H)
+    rng = np.random.default_rng(H)
+    dt = np.full(B, 0.05, np.float32)
+    v = np.gradient(q, axis=1).astype(np.float32) / 0.05
+    a_ = rng.normal(0, 5.0, size=q.shape).astype(np.float32)
+    j_ = rng.normal(0, 200.0, size=q.shape).astype(np.float32)
+    cfg = RolloutConfig.trajopt()
+    cfg.use_speed_metric = speed
+    cub, vox = make_benchmark_cuboid_world(), small_voxel_world()
+    _, _, p, qt = O.fk_forward(rm, random_q(rm, B, seed=61))
+    gp, gq = p[:, :, None, :].copy(), qt[:, :, None, :].copy()
+    idx = np.arange(B, dtype=np.int32)
+    eng = host_engine(emu_main, monkeypatch, rm, cfg, cuboid=CuboidData.from_world(cub, "cpu"), voxel=VoxelData.from_world(vox, "cpu"))
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x))  # noqa: E731
+    eng.update_goal(t(gp), t(gq), t(idx), non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32))
+    out = eng.evaluate_action(t(q), vel=t(v), acc=t(a_), jerk=t(j_), dt=t(dt))
+    ocfg = cfg.to_oracle_cfg(1)
+    ocfg["pose_non_terminal_axes"] = np.zeros((1, 6), np.float32)
+    want = O.rollout_cost_grad(rm, q, ocfg, world_cuboid=cub, world_voxel=vox, goal_pos=gp, goal_quat=gq, idxs_goal=idx, vel=v,
+                               acc=a_, jerk=j_, dt=dt)
+    np.testing.assert_allclose(out.scene_cost.numpy(), want["scene_cost"], rtol=2e-4, atol=1e-5 * max(want["scene_cost"].max(), 1e-6))
+    np.testing.assert_allclose(out.cost.numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    g = want["grad_q"]
+    np.testing.assert_allclose(out.grad_q.numpy(), g, rtol=2e-3, atol=2e-5 * np.abs(g).max())
+
+
+def test_humanoid_rollout_kernel_executed_by_threads(emu_main, monkeypatch):
+    """G1-29 (400 spheres, 55,414 collision pairs, the link-level broad phase and the second-level cull with ballot compaction,
+    ESDF collision, tool pose) through the same kernel family."""
+    import torch
+    from curobo_b200.robot_model import load_robot
+    from curobo_b200.rollout import RolloutConfig
+    from curobo_b200.scene import VoxelData
+    from helpers import humanoid_q, small_voxel_world
+    from oracle import rollout_oracle as O
+    rm = load_robot("g1_29")
+    q = humanoid_q(rm, 5, seed=45)[:, None, :]
+    _, _, p, qt = O.fk_forward(rm, humanoid_q(rm, 3, seed=46, scale=0.5))
+    gp, gq = p[:, :, None, :].copy(), qt[:, :, None, :].copy()
+    idx = (np.arange(q.shape[0]) % 3).astype(np.int32)
+    cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                        cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0), pose_weight=(2000.0, 100.0))
+    vox = small_voxel_world()
+    eng = host_engine(emu_main, monkeypatch, rm, cfg, voxel=VoxelData.from_world(vox, "cpu"))
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x))  # noqa: E731
+    eng.update_goal(t(gp), t(gq), t(idx))
+    out = eng.evaluate_action(t(q))
+    want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(rm.num_tool_frames), world_voxel=vox, goal_pos=gp, goal_quat=gq, idxs_goal=idx)
+    np.testing.assert_allclose(out.self_cost.numpy(), want["self_cost"], rtol=1e-4, atol=1e-6 * max(want["self_cost"].max(), 1e-6))
+    np.testing.assert_allclose(out.cost.numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    g = want["grad_q"]
+    np.testing.assert_allclose(out.grad_q.numpy(), g, rtol=2e-3, atol=2e-5 * np.abs(g).max())
+
+
+def _write_sections(path, sections):
+    with open(path, "wb") as f:
+        f.write(np.int32(len(sections)).tobytes())
+        for name, data in sections.items():
+            b = data if isinstance(data, bytes) else np.ascontiguousarray(data).tobytes()
+            f.write(name.encode().ljust(24, b"\0"))
+            f.write(np.int64(len(b)).tobytes())
+            f.write(b + b"\0" * ((16 - len(b) % 16) % 16))
+
+
+@pytest.mark.parametrize("mode", ["ik", "trajectory"])
+def test_fused_rollout_kernels_are_race_free_under_thread_sanitizer(mode, tmp_path):
+    """The fused kernels are warp-synchronous code: lanes exchange data through shuffles and through shared memory followed by
+    __syncwarp().  Here lanes are real threads, so an exchange through shared memory that lacks its barrier is a data race that
+    ThreadSanitizer reports (and the emulated collectives are barriers themselves, as the hardware's are)."""
+    from curobo_b200.robot_model import load_robot
+    from curobo_b200.rollout import RolloutConfig, RolloutEngine, pack_robot_blob
+    from curobo_b200.world import make_benchmark_cuboid_world
+    from helpers import random_q, random_walk_q, small_voxel_world
+    from oracle import rollout_oracle as O
+    exe = _tsan_build("tsan_rollout_main.cpp", "tsan_rollout", ("tests/simt/simt_trajectory_abi.cpp",))
+    rm = load_robot("franka")
+    cub = make_benchmark_cuboid_world()
+    S, L, D = rm.num_spheres, rm.num_tool_frames, rm.num_dof
+    sec = {"blob": pack_robot_blob(rm), "cub_dims": cub.dims, "cub_inv_pose": cub.inv_pose, "cub_enable": cub.enable, "cub_count": cub.count}
+    vox_dims = (0, 0, 0)
+    if mode == "ik":
+        B, H = 12, 1
+        cfg = RolloutConfig.ik()
+        q = random_q(rm, B, seed=3)[:, None, :]
+    else:
+        B, H = 2, 7
+        cfg = RolloutConfig.trajopt()
+        q = random_walk_q(rm, B, H, seed=63)
+        rng = np.random.default_rng(2)
+        vox = small_voxel_world()
+        sec.update(vel=np.gradient(q, axis=1).astype(np.float32) / 0.05, acc=rng.normal(0, 5.0, size=q.shape).astype(np.float32),
+                   jerk=rng.normal(0, 200.0, size=q.shape).astype(np.float32), dt=np.full(B, 0.05, np.float32),
+                   vox_params=vox.params, vox_inv_pose=vox.inv_pose, vox_enable=vox.enable, vox_count=vox.count,
+                   vox_features=vox.features.view(np.uint16), vox_max_dist=np.float32(vox.max_dist),
+                   axes_nt=np.zeros((L, 6), np.float32))
+        vox_dims = (vox.max_n, vox.num_envs, vox.features.shape[2])
+    _, _, p, qt = O.fk_forward(rm, random_q(rm, B, seed=61))
+    fake = type("E", (), {"cfg": cfg})()
+    ccfg = RolloutEngine._make_ccfg(fake, 1)
+    sec.update(cfg=bytes(ccfg), q=q.astype(np.float32), goal_pos=p[:, :, None, :].astype(np.float32),
+               goal_quat=qt[:, :, None, :].astype(np.float32), idxs_goal=np.arange(B, dtype=np.int32),
+               dims=np.array([B, H, D, S, L, cub.max_n, cub.num_envs, *vox_dims], np.int32))
+    path = tmp_path / "case.bin"
+    _write_sections(path, sec)
+    r = _tsan_run([exe, str(path)])
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.returncode, r.stdout[-200:], r.stderr[-2500:])
+    assert float(r.stdout.split()[1]) > 0 and float(r.stdout.split()[2]) > 0
