@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "../../include/curobo_b200.h"
+#include "cb200_launch.h"
 #include "cb200_dynamics.cuh"
 
 namespace {
@@ -36,7 +37,7 @@ struct FwdArgs {
   int B;
 };
 __global__ void rnea_forward_rows(const __grid_constant__ FwdArgs a) {
-  extern __shared__ float smem[];
+  CB200_EXTERN_SHARED float smem[];
   TileStore S{smem, (int)blockDim.x, (int)threadIdx.x, a.M.nl};
   const int D = a.M.D, nl = a.M.nl;
   for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < a.B; row += (long long)gridDim.x * blockDim.x)
@@ -51,7 +52,7 @@ struct BwdArgs {
   int B;
 };
 __global__ void rnea_backward_rows(const __grid_constant__ BwdArgs a) {
-  extern __shared__ float smem[];
+  CB200_EXTERN_SHARED float smem[];
   TileStore S{smem, (int)blockDim.x, (int)threadIdx.x, a.M.nl};
   const int D = a.M.D, nl = a.M.nl;
   for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < a.B; row += (long long)gridDim.x * blockDim.x)
@@ -131,7 +132,7 @@ template <int R>
 __global__ void __launch_bounds__(kThreads) rnea_forward_cta(const __grid_constant__ FwdArgs a) {
   using L = LdPlain;  // constants staged into shared memory
   constexpr int RS = R + 1, W = kThreads / R;
-  extern __shared__ __align__(16) float smem[];
+  CB200_EXTERN_SHARED __align__(16) float smem[];
   const int nl = a.M.nl, D = a.M.D;
   const Model M = stage_model(a.M, smem + ((2 * 6 + 2) * nl + 4 * D) * RS);
   Cta<L> S{smem, smem + 2 * nl * 6 * RS, smem + (2 * 6 + 2) * nl * RS, nl, D, RS, (int)threadIdx.x % R, (int)threadIdx.x / R, M};
@@ -248,7 +249,7 @@ template <int R>
 __global__ void __launch_bounds__(kThreads) rnea_backward_cta(const __grid_constant__ BwdArgs a) {
   using L = LdNc;  // constants read in place through the read-only path (measured faster than staging for the adjoint)
   constexpr int RS = R + 1, W = kThreads / R;
-  extern __shared__ __align__(16) float smem[];
+  CB200_EXTERN_SHARED __align__(16) float smem[];
   const int nl = a.M.nl, D = a.M.D;
   const Model &M = a.M;
   Cta<L> S{smem, smem + 5 * nl * 6 * RS, smem + (5 * 6 + 2) * nl * RS, nl, D, RS, (int)threadIdx.x % R, (int)threadIdx.x / R, M};
@@ -404,7 +405,6 @@ __global__ void __launch_bounds__(kThreads) rnea_backward_cta(const __grid_const
   }
 }
 
-#ifndef CB200_SIMT_EMULATION  // everything below launches kernels: not part of the host emulation build (tests/simt)
 struct CtaPlan {
   int R = 0, smem = 0, grid = 0;
 };
@@ -444,14 +444,14 @@ bool allow_smem(K kern, int smem) {
 }
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// rows per CTA: the largest of 128 / 64 / 32 whose tile leaves room for two CTAs per SM
+// rows per CTA: the largest of 128 / 64 / 32 whose tile leaves room for two CTAs per SM, else the largest of 32 .. 4 that fits
 template <class K>
 int pick_rows(K kern, int floats_per_row, int &smem_out) {
   int dev = 0, max_smem = 227 * 1024;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  for (int rows = 128; rows >= 32; rows >>= 1) {
+  for (int rows = 128; rows >= 4; rows >>= 1) {  // below a warp for very large trees: correctness first on this path
     const int smem = floats_per_row * rows * (int)sizeof(float);
-    if (smem * 2 + 4096 <= max_smem || rows == 32) {
+    if (smem * 2 + 4096 <= max_smem || (rows <= 32 && smem <= max_smem) || rows == 4) {
       if (smem > max_smem) return 0;
       if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -476,10 +476,8 @@ bool model_ok(const Model &M) {
   return M.fixed_transforms && M.masses_com && M.inertias && M.joint_type && M.joint_map && M.link_map && M.joint_offset &&
          M.gravity && M.level_starts && M.level_links && M.nl >= 1 && M.nl <= 1024 && M.D >= 1 && M.n_levels >= 1;
 }
-#endif  // CB200_SIMT_EMULATION
 }  // namespace
 
-#ifndef CB200_SIMT_EMULATION
 extern "C" {
 
 int cb200_rnea_forward(float *tau, const float *q, const float *qd, const float *qdd, const float *fixed_transforms,
@@ -498,20 +496,20 @@ int cb200_rnea_forward(float *tau, const float *q, const float *qd, const float 
   if (p.R != 0 && aligned16(forward_cache) && getenv("CB200_RNEA_ROWS") == nullptr) {
     const cudaStream_t st = (cudaStream_t)stream;
     if (p.R == 32 && allow_smem(rnea_forward_cta<32>, p.smem)) {
-      rnea_forward_cta<32><<<p.grid, kThreads, p.smem, st>>>(a);
+      CB200_LAUNCH(rnea_forward_cta<32>, p.grid, kThreads, p.smem, st, a);
       return status(cudaGetLastError());
     } else if (p.R == 16 && allow_smem(rnea_forward_cta<16>, p.smem)) {
-      rnea_forward_cta<16><<<p.grid, kThreads, p.smem, st>>>(a);
+      CB200_LAUNCH(rnea_forward_cta<16>, p.grid, kThreads, p.smem, st, a);
       return status(cudaGetLastError());
     } else if (p.R == 8 && allow_smem(rnea_forward_cta<8>, p.smem)) {
-      rnea_forward_cta<8><<<p.grid, kThreads, p.smem, st>>>(a);
+      CB200_LAUNCH(rnea_forward_cta<8>, p.grid, kThreads, p.smem, st, a);
       return status(cudaGetLastError());
     }
   }
   int smem = 0;  // very large trees: one thread per row over a two-array tile
   const int rows = pick_rows(rnea_forward_rows, 2 * num_links * 6, smem);
   if (rows == 0) return status(cudaErrorInvalidConfiguration);
-  rnea_forward_rows<<<grid_for(batch_size, rows), rows, smem, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(rnea_forward_rows, grid_for(batch_size, rows), rows, smem, (cudaStream_t)stream, a);
   return status(cudaGetLastError());
 }
 
@@ -532,22 +530,21 @@ int cb200_rnea_backward(float *grad_q, float *grad_qd, float *grad_qdd, const fl
   if (p.R != 0 && aligned16(forward_cache) && getenv("CB200_RNEA_ROWS") == nullptr) {
     const cudaStream_t st = (cudaStream_t)stream;
     if (p.R == 32 && allow_smem(rnea_backward_cta<32>, p.smem)) {
-      rnea_backward_cta<32><<<p.grid, kThreads, p.smem, st>>>(a);
+      CB200_LAUNCH(rnea_backward_cta<32>, p.grid, kThreads, p.smem, st, a);
       return status(cudaGetLastError());
     } else if (p.R == 16 && allow_smem(rnea_backward_cta<16>, p.smem)) {
-      rnea_backward_cta<16><<<p.grid, kThreads, p.smem, st>>>(a);
+      CB200_LAUNCH(rnea_backward_cta<16>, p.grid, kThreads, p.smem, st, a);
       return status(cudaGetLastError());
     } else if (p.R == 8 && allow_smem(rnea_backward_cta<8>, p.smem)) {
-      rnea_backward_cta<8><<<p.grid, kThreads, p.smem, st>>>(a);
+      CB200_LAUNCH(rnea_backward_cta<8>, p.grid, kThreads, p.smem, st, a);
       return status(cudaGetLastError());
     }
   }
   int smem = 0;
   const int rows = pick_rows(rnea_backward_rows, 5 * num_links * 6, smem);
   if (rows == 0) return status(cudaErrorInvalidConfiguration);
-  rnea_backward_rows<<<grid_for(batch_size, rows), rows, smem, (cudaStream_t)stream>>>(a);
+  CB200_LAUNCH(rnea_backward_rows, grid_for(batch_size, rows), rows, smem, (cudaStream_t)stream, a);
   return status(cudaGetLastError());
 }
 
 }  // extern "C"
-#endif  // CB200_SIMT_EMULATION

@@ -10,13 +10,12 @@
 // memory, one dependent load per row -- and the only HBM traffic is one coalesced read and one coalesced write of the grid
 // per pass: 3 x 8 B per voxel (the reference moves 6 x 8 B plus its stack look-ups).  Every pass is in place (a tile is
 // fully staged before its first row is written back), so the scratch `buffer` of the reference interface is not touched.
-#ifndef CB200_SIMT_EMULATION
 #include <cuda_fp16.h>
-#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/curobo_b200.h"
+#include "cb200_launch.h"
 #include "cb200_edt.cuh"
 
 namespace {
@@ -30,7 +29,7 @@ inline int status(cudaError_t e) {
 // The per-lane work of every pass lives in cb200_edt.cuh (FloodZ, Envelope<AXIS>: also executed lane by lane by the host
 // emulation in tests/hostmath); a kernel is the grid-stride loop over tiles plus the warp barriers.  One warp per CTA.
 __global__ void __launch_bounds__(kLanes) edt_flood_z_kernel(const __grid_constant__ FloodZ pass) {
-  extern __shared__ int tile[];
+  CB200_EXTERN_SHARED int tile[];
   const int lane = threadIdx.x;
   const long long ntiles = pass.ntiles();
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -45,7 +44,7 @@ __global__ void __launch_bounds__(kLanes) edt_flood_z_kernel(const __grid_consta
 
 template <int AXIS>
 __global__ void __launch_bounds__(kLanes) edt_envelope_kernel(const __grid_constant__ Envelope<AXIS> pass) {
-  extern __shared__ int tile[];
+  CB200_EXTERN_SHARED int tile[];
   const int lane = threadIdx.x;
   const long long ntiles = pass.ntiles();
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -54,7 +53,6 @@ __global__ void __launch_bounds__(kLanes) edt_envelope_kernel(const __grid_const
   }
 }
 
-#ifndef CB200_SIMT_EMULATION  // fp16 output and everything that launches: not part of the host emulation build (tests/simt)
 __global__ void __launch_bounds__(256) edt_distance_kernel(const int *__restrict__ sites, __half *__restrict__ out, int ny, int nz,
                                                             long long total, float voxel_size, float empty_value) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -82,10 +80,8 @@ bool dims_ok(int nx, int ny, int nz) {
   return nx >= 1 && ny >= 1 && nz >= 1 && nx <= kMaxDim && ny <= kMaxDim && nz <= kMaxDim &&
          (long long)nx * ny * nz <= 2147483647LL;
 }
-#endif  // CB200_SIMT_EMULATION
 }  // namespace
 
-#ifndef CB200_SIMT_EMULATION
 extern "C" {
 
 int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, int m3, cb200_stream_t stream) {
@@ -99,9 +95,9 @@ int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, in
   if (!allow_smem(edt_flood_z_kernel, smem_z) || !allow_smem(edt_envelope_kernel<1>, smem_y) ||
       !allow_smem(edt_envelope_kernel<0>, smem_x))
     return status(cudaErrorInvalidConfiguration);
-  edt_flood_z_kernel<<<grid_for(p.z.ntiles()), kLanes, smem_z, st>>>(p.z);
-  edt_envelope_kernel<1><<<grid_for(p.y.ntiles()), kLanes, smem_y, st>>>(p.y);
-  edt_envelope_kernel<0><<<grid_for(p.x.ntiles()), kLanes, smem_x, st>>>(p.x);
+  CB200_LAUNCH(edt_flood_z_kernel, grid_for(p.z.ntiles()), kLanes, smem_z, st, p.z);
+  CB200_LAUNCH(edt_envelope_kernel<1>, grid_for(p.y.ntiles()), kLanes, smem_y, st, p.y);
+  CB200_LAUNCH(edt_envelope_kernel<0>, grid_for(p.x.ntiles()), kLanes, smem_x, st, p.x);
   return status(cudaGetLastError());
 }
 
@@ -111,10 +107,9 @@ int cb200_edt_unsigned_distance(const int32_t *site_index, uint16_t *distance_fp
     return status(cudaErrorInvalidValue);
   const long long total = (long long)nx * ny * nz;
   const long long blocks = (total + 255) / 256;
-  edt_distance_kernel<<<grid_for(blocks), 256, 0, (cudaStream_t)stream>>>(site_index, reinterpret_cast<__half *>(distance_fp16), ny,
-                                                                        nz, total, voxel_size, empty_value);
+  CB200_LAUNCH(edt_distance_kernel, grid_for(blocks), 256, 0, (cudaStream_t)stream, site_index, reinterpret_cast<__half *>(distance_fp16),
+               ny, nz, total, voxel_size, empty_value);
   return status(cudaGetLastError());
 }
 
 }  // extern "C"
-#endif  // CB200_SIMT_EMULATION

@@ -406,7 +406,7 @@ static __device__ __noinline__ void phase_b2_ool(const FusedArgs *a, const unsig
 
 template <int SCENE, bool SPLINE, int MINB = CB200_MINB>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(const __grid_constant__ FusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
 // ------------------------------------------------------------------------------------------------
 template <int SCENE, bool SPLINE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
   const RobotView rv = make_robot_view(smem, a.blob);
@@ -555,7 +555,7 @@ __host__ __device__ inline TileLayout tile_layout(int blob_smem_bytes, int nwarp
 
 template <int SCENE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_tile_kernel(const __grid_constant__ FusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
   const RobotView rv = make_robot_view(smem, a.blob);
@@ -830,7 +830,7 @@ constexpr int kLaneThreads = 64;
 
 template <int SCENE>
 __global__ void __launch_bounds__(kLaneThreads, 4) rollout_lane_kernel(const __grid_constant__ FusedArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
   const RobotView rv = make_robot_view(smem, a.blob);
@@ -1124,7 +1124,7 @@ struct KinFwdArgs {
 };
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) kin_forward_kernel(const __grid_constant__ KinFwdArgs a) {
-  extern __shared__ __align__(16) float fsm[];
+  CB200_EXTERN_SHARED __align__(16) float fsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *cumul = fsm + (size_t)warp * a.nl * 12;
   for (int e = blockIdx.x * kWarpsPerCta + warp; e < a.N; e += gridDim.x * kWarpsPerCta) {
@@ -1192,7 +1192,7 @@ struct KinBwdArgs {
 };
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) kin_backward_kernel(const __grid_constant__ KinBwdArgs a) {
-  extern __shared__ __align__(16) float fsm[];
+  CB200_EXTERN_SHARED __align__(16) float fsm[];
   // CTA-shared: ancestor masks [nl] (uint64)
   unsigned long long *anc = reinterpret_cast<unsigned long long *>(fsm);
   const int anc_floats = (2 * a.nl + 3) & ~3, per_warp = (a.nl * 12 + a.nl * 8 + a.nl + a.D + 3) & ~3;  // keep float4 alignment
@@ -1297,7 +1297,7 @@ struct SelfArgs {
 
 template <int TPE>
 __global__ void __launch_bounds__(256) self_collision_kernel(const __grid_constant__ SelfArgs a) {
-  extern __shared__ __align__(16) float fsm[];
+  CB200_EXTERN_SHARED __align__(16) float fsm[];
   __shared__ unsigned long long red[8];
   constexpr int EPB = 256 / TPE;  // evals per block
   const int sub = threadIdx.x / TPE, t = threadIdx.x % TPE;

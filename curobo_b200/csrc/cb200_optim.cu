@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include "../../include/curobo_b200.h"
+#include "cb200_launch.h"
 
 namespace {
 
@@ -108,7 +109,7 @@ __device__ __forceinline__ float gamma_scale(float numerator, float denominator,
 
 template <int G>
 __global__ void __launch_bounds__(128) lbfgs_step_group_kernel(const __grid_constant__ LbfgsArgs a) {
-  extern __shared__ float smem[];
+  CB200_EXTERN_SHARED float smem[];
   constexpr int P = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane / G, t = lane % G;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(128) lbfgs_step_group_kernel(const __grid_cons
 
 // v_dim > 32: CTA per problem, thread per variable; history re-read from L1/L2 after the roll.
 __global__ void lbfgs_step_block_kernel(const __grid_constant__ LbfgsArgs a) {
-  extern __shared__ float smem[];  // alpha[m] + rho[m]
+  CB200_EXTERN_SHARED float smem[];  // alpha[m] + rho[m]
   __shared__ float data[32];
   const int t = threadIdx.x, m = a.m, V = a.V;
   const int b = blockIdx.x;
@@ -438,7 +439,7 @@ int launch_lbfgs_group(const LbfgsArgs &a, cudaStream_t stream) {
   }
   const long long groups = ((long long)a.B + P - 1) / P;
   const int grid = persistent_grid(lbfgs_step_group_kernel<G>, block, smem, (groups + nwarps - 1) / nwarps);
-  lbfgs_step_group_kernel<G><<<grid, block, smem, stream>>>(a);
+  CB200_LAUNCH(lbfgs_step_group_kernel<G>, grid, block, smem, stream, a);
   return status(cudaGetLastError());
 }
 template <int G>
@@ -447,7 +448,7 @@ int launch_ls_group(const LineSearchArgs &a, cudaStream_t stream) {
   const int block = 128, nwarps = block / 32;
   const long long groups = ((long long)a.B + P - 1) / P;
   const int grid = persistent_grid(line_search_group_kernel<G>, block, 0, (groups + nwarps - 1) / nwarps);
-  line_search_group_kernel<G><<<grid, block, 0, stream>>>(a);
+  CB200_LAUNCH(line_search_group_kernel<G>, grid, block, 0, stream, a);
   return status(cudaGetLastError());
 }
 }  // namespace
@@ -475,7 +476,7 @@ int cb200_lbfgs_step(float *step_vec, float *rho_buffer, float *y_buffer, float 
   if (v_dim <= 16) return launch_lbfgs_group<16>(a, st);
   if (v_dim <= 32) return launch_lbfgs_group<32>(a, st);
   const int block = (v_dim + 31) / 32 * 32;
-  lbfgs_step_block_kernel<<<batch_size, block, 2 * history_m * sizeof(float), st>>>(a);
+  CB200_LAUNCH(lbfgs_step_block_kernel, batch_size, block, 2 * history_m * sizeof(float), st, a);
   return status(cudaGetLastError());
 }
 
@@ -508,7 +509,7 @@ int cb200_line_search(float *best_cost, float *best_action, int16_t *best_iterat
   if (opt_dim <= 16) return launch_ls_group<16>(a, st);
   if (opt_dim <= 32) return launch_ls_group<32>(a, st);
   const int block = (opt_dim + 31) / 32 * 32;
-  line_search_block_kernel<<<batchsize, block, 0, st>>>(a);
+  CB200_LAUNCH(line_search_block_kernel, batchsize, block, 0, st, a);
   return status(cudaGetLastError());
 }
 

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .backends import dynamics as dynamics_cu
+from .backends import tensor_checks as _tc
 from .robot_model import RobotModel
 
 
@@ -57,8 +58,7 @@ class Dynamics:
 
     def __init__(self, robot: RobotModel, link_masses_com, link_inertias, gravity=(0.0, 0.0, -9.81), device="cuda:0"):
         self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise ValueError("Dynamics is CUDA-only; there is no CPU path")
+        _tc.require_cuda(self.device, "Dynamics is CUDA-only; there is no CPU path")
         t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).to(self.device)  # noqa: E731
         self.num_links, self.num_dof = robot.num_links, robot.num_dof
         starts, order = tree_levels(robot.link_map)

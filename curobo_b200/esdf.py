@@ -16,6 +16,7 @@ from typing import Tuple
 import torch
 
 from .backends import pba as pba_cu
+from .backends import tensor_checks as _tc
 
 MAX_DIM = 1023  # 10-bit packed coordinates (perception/mapper/util/utils_quantization.py:33-34)
 
@@ -47,8 +48,7 @@ class ParallelBandingEDT:
 
     def __init__(self, grid_shape: Tuple[int, int, int], voxel_size: float, device: torch.device, m3: int = 2):
         device = torch.device(device)
-        if device.type != "cuda":
-            raise ValueError(f"ParallelBandingEDT requires CUDA device, got {device}")
+        _tc.require_cuda(device, f"ParallelBandingEDT requires CUDA device, got {device}")
         self.grid_shape = tuple(int(v) for v in grid_shape)
         self.voxel_size = float(voxel_size)
         self.device = device

@@ -23,6 +23,7 @@ from typing import Callable, List, Optional, Tuple
 import torch
 
 from .backends import optimization as optimization_cu
+from .backends import tensor_checks as _tc
 
 
 class LBFGScu(torch.autograd.Function):
@@ -98,8 +99,7 @@ class LBFGSOpt:
                  action_bound_lows: torch.Tensor, action_bound_highs: torch.Tensor,
                  cost_grad_fn: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]], device="cuda:0"):
         self.cfg, self.device = cfg, torch.device(device)
-        if self.device.type != "cuda":
-            raise ValueError("LBFGSOpt is CUDA-only")
+        _tc.require_cuda(self.device, "LBFGSOpt is CUDA-only")
         self.B, self.H, self.D = num_problems, action_horizon, action_dim
         self.V = action_horizon * action_dim
         if cfg.history > self.V:

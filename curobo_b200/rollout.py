@@ -18,6 +18,7 @@ import torch
 
 from . import lib as _lib
 from .backends.tensor_checks import check_tensors, stream_ptr
+from .backends import tensor_checks as _tc
 from .robot_model import RobotModel
 from .scene import CuboidData, VoxelData, c_cuboid_set, c_voxel_set
 
@@ -116,8 +117,7 @@ class RolloutEngine:
                  cuboid: Optional[CuboidData] = None, voxel: Optional[VoxelData] = None,
                  store_fk_outputs: bool = False, use_voxel_mip: bool = True):
         self.robot, self.cfg, self.device = robot, cfg, torch.device(device)
-        if self.device.type != "cuda":
-            raise ValueError("RolloutEngine is CUDA-only (sm_100a); there is no CPU path")
+        _tc.require_cuda(self.device, "RolloutEngine is CUDA-only (sm_100a); there is no CPU path")
         self._lib = _lib.load()
         self._blob_host = pack_robot_blob(robot)
         self._blob = torch.from_numpy(self._blob_host.copy()).to(self.device)

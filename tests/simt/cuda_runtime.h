@@ -19,7 +19,7 @@
 #define __global__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
-#define __shared__
+#define __shared__ static   // a kernel-local __shared__ array is one array per CTA; CTAs are emulated one at a time
 #define __align__(n)
 #define __launch_bounds__(...)
 #define __grid_constant__

@@ -1,0 +1,220 @@
+"""The GPU test-suite, re-run without a GPU: the test FUNCTIONS of tests/test_gpu_*.py are called here with `DEV = "cpu"` against the
+product library compiled for the host SIMT emulation (tests/simt: every translation unit of curobo_b200/csrc as C++, CTA threads
+and warp lanes played by std::threads, the product's own cb200_* entry points and launch logic).  The Python host layer is the
+product's, unmodified; the swap consists of (1) curobo_b200.lib.load returning the emulated library and (2)
+backends.tensor_checks.require_cuda / _stream_of being neutralised -- both exist only inside this fixture.  Full-size property tests,
+CUDA-graph captures and the comparisons with the reference's compiled CUDA kernels need a real GPU and are not re-run.
+
+This is what value-checks, before any B200 time is spent on them, the GPU tests that were written after the last GPU session
+(files test_gpu_zx_*, zy_*, zz_*)."""
+import ctypes as C
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMT = os.path.join(ROOT, "tests", "simt")
+UNITS = ["simt_kernels.cpp", "simt_trajectory_abi.cpp", "simt_dynamics.cpp", "simt_edt.cpp", "simt_optim_abi.cpp"]
+
+
+@pytest.fixture(scope="module")
+def emulated_library():
+    from curobo_b200 import lib as cblib
+    so = os.path.join(SIMT, "libsimt_full.so")
+    csrc = os.path.join(ROOT, "curobo_b200", "csrc")
+    deps = [os.path.join(SIMT, u) for u in UNITS] + [os.path.join(SIMT, h) for h in ("cuda_runtime.h", "cuda_fp16.h")] + \
+        [os.path.join(csrc, f) for f in sorted(os.listdir(csrc))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-w", "-I", SIMT, *[os.path.join(SIMT, u) for u in UNITS],
+                        "-o", so], check=True)
+    L = C.CDLL(so)
+    for name, (args, res) in cblib._SIGS.items():
+        fn = getattr(L, name)                     # every ABI symbol must exist in the emulated library too
+        fn.argtypes, fn.restype = args, res
+    assert L.cb200_abi_version() == 3
+    return L
+
+
+@pytest.fixture
+def run(monkeypatch, emulated_library):
+    from curobo_b200 import lib as cblib
+    from curobo_b200.backends import tensor_checks as tc
+    import ref_kernels
+    monkeypatch.setattr(cblib, "_LIB", emulated_library)
+    monkeypatch.setattr(cblib, "load", lambda: emulated_library)
+    monkeypatch.setattr(tc, "require_cuda", lambda device, message: None)
+    monkeypatch.setattr(tc, "_stream_of", lambda device: 0)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    monkeypatch.setattr(ref_kernels, "available", lambda: False)
+
+    def call(module, test, *args, **kwargs):
+        mod = importlib.import_module(module)
+        monkeypatch.setattr(mod, "DEV", "cpu")
+        if hasattr(mod, "T") and not getattr(mod.T, "_copies", False):
+            orig = mod.T                          # torch.as_tensor(x).to("cpu") aliases the numpy input; on a GPU .to() copies
+
+            def T(a, *r, **k):
+                return orig(np.array(a, copy=True), *r, **k)
+            T._copies = True
+            monkeypatch.setattr(mod, "T", T)
+        return getattr(mod, test)(*args, **kwargs)
+    return call
+
+
+# ------------------------------------------------------------------------------------------------ drop-in operators
+@pytest.mark.parametrize("robot,n", [("franka", 64), ("g1_29", 12)])
+def test_fk_forward(run, robot, n):
+    run("test_gpu_parity", "test_fk_forward_vs_oracle_and_reference", robot, n)
+
+
+def test_fk_misc(run):
+    run("test_gpu_parity", "test_fk_without_spheres_entry_point")
+    run("test_gpu_parity", "test_fk_golden_vector_on_gpu")
+    run("test_gpu_parity", "test_fk_forward_golden_fixture")
+    run("test_gpu_parity", "test_fk_multi_sphere_configs")
+
+
+@pytest.mark.parametrize("robot,n,sparse", [("franka", 40, False), ("franka", 40, True), ("g1_29", 8, True)])
+def test_fk_backward(run, robot, n, sparse):
+    run("test_gpu_parity", "test_fk_backward_vs_oracle_and_reference", robot, n, sparse)
+    if robot == "franka" and not sparse:
+        run("test_gpu_parity", "test_fk_backward_mimic_and_negative_axis")
+
+
+@pytest.mark.parametrize("robot,n", [("franka", 48), ("g1_29", 6)])
+def test_self_collision(run, robot, n):
+    run("test_gpu_parity", "test_self_collision_vs_oracle_and_reference", robot, n)
+
+
+def test_self_collision_lazy_zeroing(run):
+    run("test_gpu_parity", "test_self_collision_lazy_zeroing_and_golden")
+
+
+@pytest.mark.parametrize("mode", ["discrete", "swept", "swept_speed"])
+@pytest.mark.parametrize("world", ["cuboid", "voxel", "both"])
+def test_scene_collision(run, mode, world):
+    run("test_gpu_parity", "test_scene_collision_vs_oracle", mode, world)
+
+
+def test_scene_misc(run):
+    run("test_gpu_parity", "test_empty_scene_zero_and_cuboid_world")
+    run("test_gpu_parity", "test_swept_golden_fixture_and_multi_env")
+    mod = importlib.import_module("test_gpu_parity")
+    for case in mod.cases():
+        run("test_gpu_parity", "test_voxel_property_cases_gpu", case)
+
+
+@pytest.mark.parametrize("lie", [False, True])
+def test_tool_pose(run, lie):
+    run("test_gpu_parity", "test_tool_pose_vs_oracle", lie)
+
+
+def test_cspace_costs(run):
+    run("test_gpu_parity", "test_cspace_costs_vs_oracle")
+
+
+# ------------------------------------------------------------------------------------------------ fused rollout
+def test_fused_ik(run):
+    run("test_gpu_rollout", "test_franka_ik_rollout_vs_oracle_and_golden")
+    run("test_gpu_rollout", "test_franka_esdf_horizon_rollout_terminal_weights")
+    run("test_gpu_rollout", "test_state_cspace_rollout_vs_oracle")
+
+
+@pytest.mark.parametrize("B,H,speed", [(4, 12, True), (5, 5, False), (6, 1, True), (3, 9, True)])
+def test_fused_trajectory(run, B, H, speed):
+    run("test_gpu_rollout", "test_traj_rollout_vs_oracle", B, H, speed)
+
+
+@pytest.mark.parametrize("robot,n", [("g1_29", 6), ("g1_43", 4)])
+def test_fused_humanoid(run, robot, n):
+    run("test_gpu_rollout", "test_humanoid_esdf_rollout_vs_oracle", robot, n)
+
+
+@pytest.mark.parametrize("mode", ["discrete", "swept"])
+def test_fused_multi_env(run, mode):
+    run("test_gpu_rollout", "test_fused_rollout_multi_env", mode)
+
+
+@pytest.mark.parametrize("lie", [False, True])
+def test_fused_goalset_and_tool_frames(run, lie):
+    run("test_gpu_rollout", "test_fused_rollout_goalset_and_tool_frames", lie)
+
+
+def test_fused_voxel_mip(run):
+    run("test_gpu_rollout", "test_voxel_mip_build_and_exact_cull")
+
+
+# ------------------------------------------------------------------------------------------------ B-spline, optimizer, dynamics
+def test_bspline(run):
+    mod = importlib.import_module("test_gpu_bspline")
+    for kw in mod.CASES:
+        run("test_gpu_bspline", "test_forward_vs_oracle_and_reference", kw)
+        run("test_gpu_bspline", "test_backward_vs_oracle_and_reference", kw)
+    run("test_gpu_bspline", "test_single_dt_vs_oracle_and_reference")
+    # test_error_behaviour checks that host tensors are refused: exactly the rule this fixture switches off
+    for implicit in (False, True):
+        run("test_gpu_bspline", "test_autograd_function_and_state_transition", implicit)
+
+
+@pytest.mark.parametrize("mode", ["trajopt_swept", "discrete"])
+@pytest.mark.parametrize("degree,steps,implicit", [(4, 4, False), (3, 2, True)])
+def test_fused_knots(run, mode, degree, steps, implicit):
+    run("test_gpu_bspline", "test_fused_knots_rollout_vs_oracle_chain", mode, degree, steps, implicit)
+
+
+def test_optimizer_kernels(run):
+    mod = importlib.import_module("test_gpu_optim")
+    for kw in mod.LBFGS_CASES:
+        run("test_gpu_optim", "test_lbfgs_step_vs_oracle_and_reference", kw)
+    for kw in mod.LS_CASES:
+        for strong, approx in ((False, True), (False, False), (True, False)):
+            run("test_gpu_optim", "test_line_search_vs_oracle_and_reference", kw, strong, approx)
+    run("test_gpu_optim", "test_lbfgs_autograd_function_and_search_points")
+    run("test_gpu_optim", "test_lbfgs_opt_solves_quadratics")
+
+
+@pytest.mark.parametrize("robot,B,seed", [("franka", 9, 1), ("g1_29", 5, 2), ("g1_43", 3, 3), ("franka", 200, 4)])
+def test_rnea(run, robot, B, seed):
+    run("test_gpu_dynamics", "test_rnea_vs_oracle_and_reference", robot, B, seed)
+
+
+@pytest.mark.parametrize("robot,B", [("franka", 2), ("g1_29", 37)])
+def test_rnea_external_wrenches(run, robot, B):
+    run("test_gpu_dynamics", "test_rnea_external_wrenches", robot, B)
+
+
+def test_rnea_row_kernels(run, monkeypatch):
+    run("test_gpu_dynamics", "test_rnea_row_kernels_match_cta_kernels", monkeypatch)
+
+
+# ------------------------------------------------------------------------------------------------ written after the last GPU session
+def test_pending_rnea_trees(run, monkeypatch):
+    mod = importlib.import_module("test_gpu_zx_dynamics_trees")
+    from dynamics_cases import RANDOM_TREES
+    for nl, B, seed, mimic in RANDOM_TREES + [(23, 70, 41, True)]:
+        for rows in (False, True):
+            with monkeypatch.context() as m:
+                run("test_gpu_zx_dynamics_trees", "test_rnea_on_random_trees", nl, B, seed, mimic, rows, m)
+    for robot, B in (("franka", 100), ("g1_29", 70)):
+        for R in (8, 16, 32):
+            with monkeypatch.context() as m:
+                run("test_gpu_zx_dynamics_trees", "test_rnea_every_rows_per_cta_variant", robot, B, R, m)
+    assert mod.DEV == "cpu"
+
+
+@pytest.mark.parametrize("robot,B,H", [("franka", 6, 5), ("g1_29", 3, 4)])
+def test_pending_dynamics_state_cost(run, robot, B, H):
+    run("test_gpu_zy_effort_cost", "test_dynamics_state_cost_vs_oracle", robot, B, H)
+
+
+def test_pending_edt(run):
+    mod = importlib.import_module("test_gpu_zz_edt")
+    from edt_cases import MEDIUM, SMALL
+    for kind, shape, p in SMALL + MEDIUM[:4]:
+        run("test_gpu_zz_edt", "test_nearest_site_transform_is_exact", kind, shape, p)
+    run("test_gpu_zz_edt", "test_operator_argument_checks_emulated") if hasattr(mod, "test_operator_argument_checks_emulated") else None
