@@ -218,3 +218,10 @@ def test_pending_edt(run):
     for kind, shape, p in SMALL + MEDIUM[:4]:
         run("test_gpu_zz_edt", "test_nearest_site_transform_is_exact", kind, shape, p)
     run("test_gpu_zz_edt", "test_operator_argument_checks_emulated") if hasattr(mod, "test_operator_argument_checks_emulated") else None
+
+
+@pytest.mark.skipif(os.environ.get("CB200_EMULATE_LONG") != "1", reason="~5 min of emulated launches: set CB200_EMULATE_LONG=1 (passes)")
+def test_complete_ik_solve(run):
+    """24 goals x 16 seeds x 100 L-BFGS iterations, 3 kernel launches per iteration (step + search points, fused rollout on the
+    expanded batch, line search + bookkeeping): >= 90 % of the goals solved to 5 mm -- every launch an emulated one."""
+    run("test_gpu_optim", "test_ik_solve_end_to_end")
