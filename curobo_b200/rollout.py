@@ -128,6 +128,27 @@ class RolloutEngine:
         self._B = self._H = -1
         self._goal = None
         self._ccfg = self._make_ccfg(1)
+        self._effort_cost = None
+
+    def attach_dynamics(self, dynamics, effort_limits=None) -> None:
+        """Make the STATE c-space cost dynamics-aware: after the fused launch, tau = RNEA(q, qd, qdd) is
+        evaluated for every row and the effort channel of the STATE cost -- bound hinge (cspace_weight[4], cspace_activation[4]),
+        squared-L2 (cspace_reg[3]) and the energy term (cspace_reg[4]) -- is added to cost / cspace_cost, its gradient to
+        grad_q / grad_vel / grad_acc through the RNEA adjoint (curobo_b200.dynamics.DynamicsStateCost: three more launches).
+        The fused kernel evaluates those terms with tau = 0, where they vanish (what the reference does without
+        `compute_inverse_dynamics`, transition/robot_state_transition.py:380-396), so nothing is counted twice.
+        Applies to evaluate_action with vel / acc / jerk / dt given; `dynamics` is a curobo_b200.dynamics.Dynamics."""
+        from .dynamics import DynamicsStateCost
+        if self.cfg.cspace_type != "state":
+            raise ValueError("attach_dynamics needs the STATE c-space cost")
+        rm = self.robot
+        w = [0.0, 0.0, 0.0, 0.0, float(self.cfg.cspace_weight[4])]
+        reg = [0.0, 0.0, 0.0, float(self.cfg.cspace_reg[3]), float(self.cfg.cspace_reg[4])]
+        lim = dict(p=rm.position_limits, v=rm.velocity_limits, a=rm.acceleration_limits, j=rm.jerk_limits,
+                   tau=rm.effort_limits if effort_limits is None else effort_limits)
+        self._effort_cost = DynamicsStateCost(dynamics, lim, w, list(self.cfg.cspace_activation), reg,
+                                              retime_weights=self.cfg.retime_weights,
+                                              retime_regularization_weights=self.cfg.retime_reg)
 
     def refresh_world(self) -> None:
         """Re-read the obstacle holders; call after the ESDF values (or obstacle tensors) were replaced or updated in
@@ -211,7 +232,15 @@ class RolloutEngine:
             if t is not None:
                 check_tensors(dev, torch.float32, **{name: t})
                 setattr(io, name, t.data_ptr())
-        return self._launch(io, B, H, env_query_idx)
+        out = self._launch(io, B, H, env_query_idx)
+        if self._effort_cost is not None and vel is not None and acc is not None and jerk is not None and dt is not None:
+            c, gp, gv, ga, _, _ = self._effort_cost.evaluate(q, vel, acc, jerk, dt)
+            out.cspace_cost.add_(c)
+            out.cost.add_(c.sum(-1))
+            out.grad_q.add_(gp)
+            out.grad_vel.add_(gv)
+            out.grad_acc.add_(ga)
+        return out
 
     def evaluate_knots(self, knots: torch.Tensor, start_state, start_state_idx: torch.Tensor, goal_state,
                        goal_state_idx: torch.Tensor, use_implicit_goal_state: torch.Tensor, bspline_degree: int = 4,

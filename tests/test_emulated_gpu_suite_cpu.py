@@ -244,3 +244,7 @@ def test_bench_side_entries_execute(run, monkeypatch):
     assert set(r["franka_64"]) == {"forward", "backward"} and r["franka_64"]["forward"]["bytes_per_row"] == 4 * (4 * 7 + 13 * 20)
     e = bench.edt_bench("cpu", 6500.0, n=24, iters=1)
     assert e["grid"] == [24, 24, 24] and e["launches"] == 3 and e["sites"] > 0
+
+
+def test_pending_dynamics_aware_rollout(run):
+    run("test_gpu_zy_effort_cost", "test_dynamics_aware_rollout_vs_oracle")

@@ -43,3 +43,64 @@ def test_dynamics_state_cost_vs_oracle(robot, B, H):
     torch.cuda.synchronize()
     for a_, b_ in zip(first, again[:5]):
         assert torch.equal(a_, b_)
+
+
+def test_dynamics_aware_rollout_vs_oracle():
+    """RolloutEngine.attach_dynamics: the fused trajectory rollout (swept ESDF + cuboid collision, speed metric, pose, STATE c-space)
+    plus the effort channel fed by RNEA.  Oracle = rollout oracle (torque-free) + the effort-only STATE cost composed with the RNEA
+    oracle and its adjoint; costs and the gradients w.r.t. position, velocity and acceleration must be the sums."""
+    from curobo_b200.rollout import RolloutConfig, RolloutEngine
+    from curobo_b200.scene import CuboidData, VoxelData
+    from curobo_b200.world import make_benchmark_cuboid_world
+    from dynamics_cases import make_case, model_args
+    from helpers import random_q, random_walk_q, small_voxel_world
+    from oracle import dynamics_oracle as do
+    from oracle import rollout_oracle as O
+    B, H = 3, 7
+    c = make_case("franka", B * H, 31)
+    rm = c["rm"]
+    D = c["D"]
+    q = random_walk_q(rm, B, H, seed=71)
+    rng = np.random.default_rng(3)
+    dt = np.full(B, 0.05, np.float32)
+    v = (np.gradient(q, axis=1) / 0.05).astype(np.float32)
+    a_ = rng.normal(0, 3.0, size=q.shape).astype(np.float32)
+    j_ = rng.normal(0, 100.0, size=q.shape).astype(np.float32)
+    m = model_args(c)
+    tau, cache = do.rnea_forward(q.reshape(-1, D), v.reshape(-1, D), a_.reshape(-1, D), *m)
+    elim = np.stack([np.quantile(tau, 0.25, axis=0), np.quantile(tau, 0.75, axis=0)]).astype(np.float32)
+    cfg = RolloutConfig.trajopt()
+    cfg.cspace_reg = (1000.0, 10000.0, 5.0, 0.05, 40.0)
+    cfg.cspace_activation = (0.01, 0.01, 0.01, 0.01, 0.05)
+    cub, vox = make_benchmark_cuboid_world(), small_voxel_world()
+    _, _, p, qt = O.fk_forward(rm, random_q(rm, B, seed=72))
+    gp, gq = p[:, :, None, :].copy(), qt[:, :, None, :].copy()
+    idx = np.arange(B, dtype=np.int32)
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    eng.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32, device=DEV))
+    base = eng.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
+    base_cost, base_gq = base.cost.clone(), base.grad_q.clone()
+    eng.attach_dynamics(Dynamics(rm, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV), effort_limits=elim)
+    out = eng.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
+    torch.cuda.synchronize()
+    ocfg = cfg.to_oracle_cfg(1)
+    ocfg["pose_non_terminal_axes"] = np.zeros((1, 6), np.float32)
+    want = O.rollout_cost_grad(rm, q, ocfg, world_cuboid=cub, world_voxel=vox, goal_pos=gp, goal_quat=gq, idxs_goal=idx, vel=v,
+                               acc=a_, jerk=j_, dt=dt)
+    lim = dict(p=rm.position_limits, v=rm.velocity_limits, a=rm.acceleration_limits, j=rm.jerk_limits, tau=elim)
+    w_eff = np.array([0, 0, 0, 0, cfg.cspace_weight[4]], np.float32)
+    r_eff = np.array([0, 0, 0, cfg.cspace_reg[3], cfg.cspace_reg[4]], np.float32)
+    ec, eg = O.cspace_state_cost(q, v, a_, j_, dt, lim, w_eff, np.asarray(cfg.cspace_activation, np.float32), r_eff, True, True,
+                                 effort=tau.reshape(B, H, D))
+    bq, bqd, bqdd = do.rnea_backward(eg[4].reshape(-1, D), q.reshape(-1, D), v.reshape(-1, D), cache, *m)
+    r = lambda x: np.asarray(x, np.float32).reshape(B, H, D)  # noqa: E731
+    assert float(ec.sum()) > 1e-3 * float(want["cost_bh"].sum()), "the effort terms must matter in this case"
+    total = want["cost_bh"] + ec.sum(-1)
+    assert np.allclose(out.cost.cpu().numpy(), total, rtol=3e-4, atol=1e-5 * total.max())
+    assert not torch.equal(out.cost, base_cost) and not torch.equal(out.grad_q, base_gq)
+    g = want["grad_q"] + eg[0] + r(bq)
+    assert np.allclose(out.grad_q.cpu().numpy(), g, rtol=3e-3, atol=3e-5 * np.abs(g).max())
+    gv = want["cspace_grads"][1] + eg[1] + r(bqd)
+    ga = want["cspace_grads"][2] + eg[2] + r(bqdd)
+    assert np.allclose(out.grad_vel.cpu().numpy(), gv, rtol=3e-3, atol=3e-5 * np.abs(gv).max())
+    assert np.allclose(out.grad_acc.cpu().numpy(), ga, rtol=3e-3, atol=3e-5 * np.abs(ga).max())
