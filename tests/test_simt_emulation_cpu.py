@@ -213,25 +213,16 @@ def emu_main():
 
 
 def host_engine(emu_main, monkeypatch, rm, cfg, cuboid=None, voxel=None):
-    """A RolloutEngine whose native library is the emulated one and whose tensors live on the host.  Built around __init__
-    (which refuses non-CUDA devices: the product has no CPU path and this does not add one -- the swap exists only here)."""
-    import torch
+    """A RolloutEngine whose native library is the emulated one and whose tensors live on the host: the product refuses non-CUDA
+    devices in exactly one function (backends.tensor_checks.require_cuda); it and the library loader are swapped here, only here."""
+    from curobo_b200 import lib as cblib
     from curobo_b200 import rollout as R
-    from curobo_b200.scene import c_cuboid_set, c_voxel_set
-    monkeypatch.setattr(R, "check_tensors", lambda *a, **k: None)
-    monkeypatch.setattr(R, "stream_ptr", lambda d: 0)
-    eng = R.RolloutEngine.__new__(R.RolloutEngine)
-    eng.robot, eng.cfg, eng.device = rm, cfg, torch.device("cpu")
-    eng._lib = emu_main
-    eng._blob_host = R.pack_robot_blob(rm)
-    eng._blob = torch.from_numpy(eng._blob_host.copy())
-    eng.cuboid, eng.voxel, eng.use_voxel_mip = cuboid, voxel, False
-    eng._cs, eng._vs = c_cuboid_set(cuboid, None), c_voxel_set(voxel, None)
-    eng.store_fk_outputs = False
-    eng._B = eng._H = -1
-    eng._goal = None
-    eng._ccfg = eng._make_ccfg(1)
-    return eng
+    from curobo_b200.backends import tensor_checks as tc
+    monkeypatch.setattr(cblib, "_LIB", emu_main)
+    monkeypatch.setattr(cblib, "load", lambda: emu_main)
+    monkeypatch.setattr(tc, "require_cuda", lambda device, message: None)
+    monkeypatch.setattr(tc, "_stream_of", lambda device: 0)
+    return R.RolloutEngine(rm, cfg, "cpu", cuboid, voxel, use_voxel_mip=False)
 
 
 def test_fused_ik_rollout_kernel_executed_by_threads(emu_main, monkeypatch):
