@@ -24,13 +24,14 @@ UNITS = ["simt_kernels.cpp", "simt_trajectory_abi.cpp", "simt_dynamics.cpp", "si
 @pytest.fixture(scope="module")
 def emulated_library():
     from curobo_b200 import lib as cblib
-    so = os.path.join(SIMT, "libsimt_full.so")
+    tsan = os.environ.get("CB200_SIMT_TSAN") == "1"   # race-detector build: run pytest with LD_PRELOAD=libtsan.so (see below)
+    so = os.path.join(SIMT, "libsimt_full_tsan.so" if tsan else "libsimt_full.so")
     csrc = os.path.join(ROOT, "curobo_b200", "csrc")
     deps = [os.path.join(SIMT, u) for u in UNITS] + [os.path.join(SIMT, h) for h in ("cuda_runtime.h", "cuda_fp16.h")] + \
         [os.path.join(csrc, f) for f in sorted(os.listdir(csrc))]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-w", "-I", SIMT, *[os.path.join(SIMT, u) for u in UNITS],
-                        "-o", so], check=True)
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-w", *(["-g", "-fsanitize=thread"] if tsan else []),
+                        "-I", SIMT, *[os.path.join(SIMT, u) for u in UNITS], "-o", so], check=True)
     L = C.CDLL(so)
     for name, (args, res) in cblib._SIGS.items():
         fn = getattr(L, name)                     # every ABI symbol must exist in the emulated library too
