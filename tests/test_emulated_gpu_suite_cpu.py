@@ -122,6 +122,7 @@ def test_cspace_costs(run):
 # ------------------------------------------------------------------------------------------------ fused rollout
 def test_fused_ik(run):
     run("test_gpu_rollout", "test_franka_ik_rollout_vs_oracle_and_golden")
+    run("test_gpu_rollout", "test_franka_ik_rollout_larger_batch")
     run("test_gpu_rollout", "test_franka_esdf_horizon_rollout_terminal_weights")
     run("test_gpu_rollout", "test_state_cspace_rollout_vs_oracle")
 
@@ -163,7 +164,7 @@ def test_bspline(run):
 
 
 @pytest.mark.parametrize("mode", ["trajopt_swept", "discrete"])
-@pytest.mark.parametrize("degree,steps,implicit", [(4, 4, False), (3, 2, True)])
+@pytest.mark.parametrize("degree,steps,implicit", [(4, 4, False), (3, 2, True), (5, 1, False)])
 def test_fused_knots(run, mode, degree, steps, implicit):
     run("test_gpu_bspline", "test_fused_knots_rollout_vs_oracle_chain", mode, degree, steps, implicit)
 
