@@ -21,6 +21,7 @@
 #include "../../include/curobo_b200.h"
 #include "cb200_blob.h"
 #include "cb200_bspline.cuh"
+#include "cb200_dynamics.cuh"
 #include "cb200_launch.h"
 #include "cb200_math.cuh"
 #include "cb200_warp.cuh"
@@ -60,6 +61,11 @@ struct FusedArgs {
     float *out_p, *out_v, *out_a, *out_j;
     int32_t n_knots, degree, steps;
   } spl;
+  // Inverse dynamics inside the trajectory kernel (8f-3): inertial parameters of the links (the kinematic tree is the blob's).
+  // Only read by the DYN instantiations of rollout_traj_kernel.
+  struct Dyn {
+    const float *masses_com, *inertias, *gravity;
+  } dyn;
 };
 
 // State (q, qd, qdd, qddd) of row (b, h), dof d.  Spline mode evaluates the knots in place (one out-of-line copy
@@ -161,7 +167,18 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
 //   phase A: q load + c-space cost, FK, spheres (+ padded copy), tool poses + tool-pose cost
 //   phase B: self collision, scene collision (discrete | swept + speed metric), J^T backward, row cost
 // ------------------------------------------------------------------------------------------------
-template <bool SPLINE>
+// Per-row accessor of the RNEA row functions (cb200_dynamics.cuh) over a plain [array][link][6] scratch.
+struct DynRowStore {
+  float *t;
+  int nl;
+  __device__ __forceinline__ float get(int arr, int k, int c) const { return t[(arr * nl + k) * 6 + c]; }
+  __device__ __forceinline__ void set(int arr, int k, int c, float v) { t[(arr * nl + k) * 6 + c] = v; }
+};
+// floats of row scratch the in-kernel inverse dynamics borrows from the row's own FK / sphere buffers (not live yet in phase A)
+__host__ __device__ inline int dyn_scratch_floats(int nl, int D) { return ((7 * D + 3) & ~3) + 20 * nl + 30 * nl; }
+__host__ __device__ inline int dyn_scratch_available(int nl, int S) { return nl * 12 + S * 8 + nl * 8; }
+
+template <bool SPLINE, bool DYN = false>
 __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
                                             int b, int h, float &cs_cost, float &pose_c) {
   const cb200_rollout_cfg &cfg = a.cfg;
@@ -176,8 +193,58 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
     es.gqv[d] = gp;
     cs_cost += c;
     if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
+    if constexpr (DYN) {  // velocity / acceleration of the row for the inverse dynamics below
+      es.cumul[d] = st.v;
+      es.cumul[D + d] = st.a;
+    }
   }
   __syncwarp();
+  if constexpr (DYN) {
+    // Dynamics-aware STATE cost: tau = RNEA(q, qd, qdd) for this row, the effort channel of the STATE
+    // cost on it (bound hinge, squared-L2, energy (tau qd dt)^2: wp_cspace_state.py:209-275), and the RNEA adjoint of
+    // d cost / d tau onto the position / velocity / acceleration gradients -- tau never leaves the SM.  The recursion is
+    // sequential along the tree: lane 0 walks it (cb200_dynamics.cuh row functions) while the row's FK / sphere buffers,
+    // not live yet, hold its scratch; the per-dof terms are done by the lanes.
+    float *sc = es.cumul;
+    float *qd_s = sc, *qdd_s = sc + D, *tau_s = sc + 2 * D, *gt_s = sc + 3 * D, *gq_s = sc + 4 * D, *gqd_s = sc + 5 * D,
+          *gqdd_s = sc + 6 * D;
+    float *cache = sc + ((7 * D + 3) & ~3);
+    DynRowStore st{cache + 20 * rv.nl, rv.nl};
+    const dyn::Model M{rv.fixed, a.dyn.masses_com, a.dyn.inertias, rv.joint_type, rv.joint_map, rv.link_map, rv.joff,
+                       a.dyn.gravity, rv.level_off, rv.level_links, rv.nl, D, rv.n_levels};
+    if (lane == 0) dyn::rnea_forward_row(M, st, es.qv, qd_s, qdd_s, nullptr, tau_s, cache);
+    __syncwarp();
+    const float dt = seed_dt(a, b);
+    float w_b = cfg.cspace_weight[4], w_l2 = cfg.cspace_reg[3], w_en = cfg.cspace_reg[4];
+    if (cfg.retime_regularization_weights) w_en = dt * w_en;
+    const float *lim = rv.limits;
+    #pragma unroll 1
+    for (int d = lane; d < D; d += 32) {
+      const float tau = tau_s[d], v = qd_s[d];
+      float c = 0.0f, gt = 0.0f;
+      bound_cost(tau, lim[8 * D + d], lim[9 * D + d], cfg.cspace_activation[4], w_b, c, gt);
+      l2_reg(tau, w_l2, c, gt);
+      if (w_en > 0.0f) {
+        const float ce = tau * v * dt;
+        c += w_en * ce * ce;
+        gt += 2.0f * w_en * ce * v * dt;
+        if (a.grad_vel) a.grad_vel[(size_t)e * D + d] += 2.0f * w_en * ce * tau * dt;
+      }
+      gt_s[d] = gt;
+      cs_cost += c;
+      if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] += c;
+    }
+    __syncwarp();
+    if (lane == 0) dyn::rnea_backward_row(M, st, gt_s, es.qv, qd_s, cache, gq_s, gqd_s, gqdd_s, nullptr);
+    __syncwarp();
+    #pragma unroll 1
+    for (int d = lane; d < D; d += 32) {
+      es.gqv[d] += gq_s[d];
+      if (a.grad_vel) a.grad_vel[(size_t)e * D + d] += gqd_s[d];
+      if (a.grad_acc) a.grad_acc[(size_t)e * D + d] += gqdd_s[d];
+    }
+    __syncwarp();
+  }
   warp_fk(rv, es, lane);
   warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr);
   pose_c = 0.0f;
@@ -440,7 +507,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
 // waypoint (warp 0 / the last warp also compute the halo waypoints' spheres), the CTA synchronises, then
 // every warp runs phase B reading its neighbours' sphere positions from shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int SCENE, bool SPLINE>
+template <int SCENE, bool SPLINE, bool DYN = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
   CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
@@ -486,7 +553,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
     const int e = b * a.H + h;
     float cs_cost = 0.0f, pose_c = 0.0f;
     RowB1 r{0.0f, 0.0f, 0.0f, 0, 0, 0};
-    if (active) row_phase_a<SPLINE>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    if (active) row_phase_a<SPLINE, DYN>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
     __syncthreads();
     if (active) {
       const float4 *prev = nullptr, *next = nullptr;
@@ -2371,6 +2438,20 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   }
   int variant = (traj ? 1 : 0) + (a.spl.knots != nullptr ? 3 : 0);
   KernelT kern = table[variant][scene];
+  if (io->dynamics != nullptr) {
+    // inverse dynamics inside the trajectory kernel: rows must come from caller-provided states (or the expanded spline
+    // schedule, which arrives here with a.spl.knots == nullptr) and the STATE c-space cost must be on
+    const cb200_dynamics_params *dp = io->dynamics;
+    if (dp->link_masses_com == nullptr || dp->link_inertias == nullptr || dp->gravity == nullptr || !traj ||
+        cfg->cspace_type != 2 || a.spl.knots != nullptr || a.vel == nullptr || a.acc == nullptr)
+      return ret(cudaErrorInvalidValue);
+    if (dyn_scratch_floats(h.nl, h.D) > dyn_scratch_available(h.nl, h.S)) return ret(cudaErrorInvalidConfiguration);
+    static KernelT const dyn_table[4] = {rollout_traj_kernel<0, false, true>, rollout_traj_kernel<1, false, true>,
+                                         rollout_traj_kernel<2, false, true>, rollout_traj_kernel<3, false, true>};
+    a.dyn = FusedArgs::Dyn{dp->link_masses_com, dp->link_inertias, dp->gravity};
+    kern = dyn_table[scene];
+    variant = 6;
+  }
   if (variant == 0 && arm_regcap != 0 && scene <= 1 && h.nl <= 24 && h.S <= 128) {  // ESDF variants spill at 80: -3 %
     kern = arm_table[scene];
     variant = 5;
@@ -2382,7 +2463,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     long long key = -1;
     int nw = 0, per_sm = 0;
   };
-  static thread_local Plan plans[6][4];
+  static thread_local Plan plans[7][4];
   Plan &pl = plans[variant][scene];
   const size_t halo_bytes = traj ? (size_t)2 * h.S * sizeof(float4) : 0;
   const long long key = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ (long long)minb ^

@@ -48,6 +48,10 @@ class SplineInput(C.Structure):
                 ("out_dt", c_p)]
 
 
+class DynamicsParams(C.Structure):
+    _fields_ = [("link_masses_com", c_p), ("link_inertias", c_p), ("gravity", c_p)]
+
+
 class RolloutIO(C.Structure):
     _fields_ = [("q", c_p), ("vel", c_p), ("acc", c_p), ("jerk", c_p), ("dt", c_p),
                 ("robot_blob", c_p), ("robot_blob_host", c_p), ("robot_blob_bytes", C.c_int32),
@@ -58,7 +62,8 @@ class RolloutIO(C.Structure):
                 ("cost", c_p), ("grad_q", c_p), ("self_cost", c_p), ("scene_cost", c_p), ("pose_cost", c_p),
                 ("cspace_cost", c_p), ("grad_vel", c_p), ("grad_acc", c_p), ("grad_jerk", c_p),
                 ("link_pos", c_p), ("link_quat", c_p), ("robot_spheres", c_p), ("pose_goalset_idx", c_p),
-                ("batch_size", C.c_int32), ("horizon", C.c_int32), ("spline", C.POINTER(SplineInput))]
+                ("batch_size", C.c_int32), ("horizon", C.c_int32), ("spline", C.POINTER(SplineInput)),
+                ("dynamics", C.POINTER(DynamicsParams))]
 
 
 _I = C.c_int
@@ -117,7 +122,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)       # AttributeError if the symbol is missing: fail loudly
         fn.argtypes = args
         fn.restype = res
-    if lib.cb200_abi_version() != 3:
+    if lib.cb200_abi_version() != 4:
         raise RuntimeError("libcurobo_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -129,8 +129,9 @@ class RolloutEngine:
         self._goal = None
         self._ccfg = self._make_ccfg(1)
         self._effort_cost = None
+        self._dyn_params = None
 
-    def attach_dynamics(self, dynamics, effort_limits=None) -> None:
+    def attach_dynamics(self, dynamics, effort_limits=None, fused: bool = True) -> None:
         """Make the STATE c-space cost dynamics-aware: after the fused launch, tau = RNEA(q, qd, qdd) is
         evaluated for every row and the effort channel of the STATE cost -- bound hinge (cspace_weight[4], cspace_activation[4]),
         squared-L2 (cspace_reg[3]) and the energy term (cspace_reg[4]) -- is added to cost / cspace_cost, its gradient to
@@ -142,6 +143,16 @@ class RolloutEngine:
         if self.cfg.cspace_type != "state":
             raise ValueError("attach_dynamics needs the STATE c-space cost")
         rm = self.robot
+        # fused = the trajectory kernel evaluates RNEA, the effort terms and the RNEA adjoint for its own rows (swept mode;
+        # effort limits = the robot's, which are part of the packed robot blob); otherwise -- and for custom limits or
+        # discrete mode -- the same terms are added by three more launches after the fused one.
+        self._dyn_params = None
+        if fused and effort_limits is None and self.cfg.use_sweep:
+            m = dynamics._model       # (fixed, masses_com, inertias, joint types, joint map, link map, offsets, gravity, ...)
+            self._dyn_keepalive = (m[1], m[2], m[7])
+            self._dyn_params = _lib.DynamicsParams(m[1].data_ptr(), m[2].data_ptr(), m[7].data_ptr())
+            self._effort_cost = None
+            return
         w = [0.0, 0.0, 0.0, 0.0, float(self.cfg.cspace_weight[4])]
         reg = [0.0, 0.0, 0.0, float(self.cfg.cspace_reg[3]), float(self.cfg.cspace_reg[4])]
         lim = dict(p=rm.position_limits, v=rm.velocity_limits, a=rm.acceleration_limits, j=rm.jerk_limits,
@@ -330,6 +341,8 @@ class RolloutEngine:
             if t is not None:
                 setattr(io, name, t.data_ptr())
         io.batch_size, io.horizon = B, H
+        if self._dyn_params is not None and io.vel and io.acc and not bool(io.spline):
+            io.dynamics = C.pointer(self._dyn_params)
         err = self._lib.cb200_rollout_cost_grad(C.byref(self._ccfg), C.byref(io), stream_ptr(dev))
         _lib.check(err, "rollout_cost_grad")
         return o

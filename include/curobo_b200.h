@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st *cb200_stream_t; /* == cudaStream_t */
 
-#define CB200_ABI_VERSION 3
+#define CB200_ABI_VERSION 4
 
 /* Library / build identity.  cb200_abi_version() == CB200_ABI_VERSION; cb200_sm_arch() == 100. */
 int cb200_abi_version(void);
@@ -250,6 +250,19 @@ typedef struct {
    *                            never leaves the SM; out_position.. are then optional dumps). */
 } cb200_spline_input;
 
+/* Optional inverse dynamics inside the trajectory kernel (reference: joint_torque =
+ * robot_dynamics.compute_inverse_dynamics(state), transition/robot_state_transition.py:380-389, consumed by the effort
+ * channel of the STATE c-space cost, cost/wp_cspace_state.py:209-275).  When io->dynamics is given (swept / trajectory mode,
+ * STATE c-space cost, io->vel and io->acc present) every row evaluates tau = RNEA(q, qd, qdd) on chip, adds the effort terms
+ * (bound hinge with the blob's effort limits, cspace_weight[4] / cspace_activation[4]; squared-L2 cspace_reg[3]; energy
+ * cspace_reg[4]) to cost / cspace_cost and their gradients -- through the RNEA adjoint -- to grad_q / grad_vel / grad_acc.
+ * DEVICE pointers; layouts as in cb200_rnea_forward. */
+typedef struct {
+  const float *link_masses_com;   /* [nl,4] cx,cy,cz,m */
+  const float *link_inertias;     /* [nl,8] ixx,iyy,izz,ixy,ixz,iyz,pad,pad */
+  const float *gravity;           /* [6] spatial */
+} cb200_dynamics_params;
+
 typedef struct {
   /* inputs */
   const float *q;                 /* [B,H,D] */
@@ -279,6 +292,7 @@ typedef struct {
   int32_t *pose_goalset_idx;              /* optional [B,H,L] */
   int32_t batch_size, horizon;
   const cb200_spline_input *spline;       /* optional B-spline front end (host pointer); NULL = rows come from q */
+  const cb200_dynamics_params *dynamics;  /* optional (host pointer): dynamics-aware STATE cost, see cb200_dynamics_params */
 } cb200_rollout_io;
 
 int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io,

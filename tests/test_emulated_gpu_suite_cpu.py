@@ -36,7 +36,7 @@ def emulated_library():
     for name, (args, res) in cblib._SIGS.items():
         fn = getattr(L, name)                     # every ABI symbol must exist in the emulated library too
         fn.argtypes, fn.restype = args, res
-    assert L.cb200_abi_version() == 3
+    assert L.cb200_abi_version() == 4
     return L
 
 

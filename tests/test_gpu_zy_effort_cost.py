@@ -104,3 +104,18 @@ def test_dynamics_aware_rollout_vs_oracle():
     ga = want["cspace_grads"][2] + eg[2] + r(bqdd)
     assert np.allclose(out.grad_vel.cpu().numpy(), gv, rtol=3e-3, atol=3e-5 * np.abs(gv).max())
     assert np.allclose(out.grad_acc.cpu().numpy(), ga, rtol=3e-3, atol=3e-5 * np.abs(ga).max())
+    # the same terms evaluated INSIDE the trajectory kernel (cb200_rollout_io.dynamics): the effort limits are the blob's, so the
+    # engine is built on a robot model that carries the limits of this case
+    import dataclasses
+    rm2 = dataclasses.replace(rm, effort_limits=elim)
+    eng2 = RolloutEngine(rm2, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    eng2.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32, device=DEV))
+    eng2.attach_dynamics(Dynamics(rm2, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV))
+    assert eng2._dyn_params is not None and eng2._effort_cost is None
+    fused = eng2.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
+    torch.cuda.synchronize()
+    assert np.allclose(fused.cost.cpu().numpy(), total, rtol=3e-4, atol=1e-5 * total.max())
+    assert np.allclose(fused.grad_q.cpu().numpy(), g, rtol=3e-3, atol=3e-5 * np.abs(g).max())
+    assert np.allclose(fused.grad_vel.cpu().numpy(), gv, rtol=3e-3, atol=3e-5 * np.abs(gv).max())
+    assert np.allclose(fused.grad_acc.cpu().numpy(), ga, rtol=3e-3, atol=3e-5 * np.abs(ga).max())
+    assert np.allclose(fused.cspace_cost.cpu().numpy(), want["cspace_cost"] + ec, rtol=3e-4, atol=1e-5 * float((want["cspace_cost"] + ec).max()))

@@ -208,7 +208,7 @@ def emu_main():
         if hasattr(L, name):
             fn = getattr(L, name)
             fn.argtypes, fn.restype = args, res
-    assert L.cb200_abi_version() == 3
+    assert L.cb200_abi_version() == 4
     return L
 
 
