@@ -40,6 +40,19 @@ UNIT = "evals/s"
 # workloads
 # ------------------------------------------------------------------------------------------------
 def make_workload(name: str, seed_offset: int = 0):
+    """`<workload>_dynamics` / `<workload>_dynamics_host`: the same rows with the dynamics-aware STATE cost,
+    evaluated inside the trajectory kernel or by the three extra launches of the host composition (synthetic inertial parameters)."""
+    mode = None
+    for suffix, m in (("_dynamics_host", "host"), ("_dynamics", "fused")):
+        if name.endswith(suffix):
+            name, mode = name[:-len(suffix)], m
+            break
+    wl = _make_workload(name, seed_offset)
+    wl["dynamics"] = mode
+    return wl
+
+
+def _make_workload(name: str, seed_offset: int = 0):
     """Returns dict(robot, cfg, B, H, q [B,H,D] np, goal (pos, quat, idx) or None, cuboid world, voxel spec, bytes_per_eval)."""
     from curobo_b200.robot_model import load_robot
     from curobo_b200.rollout import RolloutConfig
@@ -122,6 +135,14 @@ def build_engine(wl, device):
     if wl["goal"] is not None:
         gp, gq, idx = wl["goal"]
         eng.update_goal(torch.as_tensor(gp).to(device), torch.as_tensor(gq).to(device), torch.as_tensor(idx).to(device))
+    if wl.get("dynamics"):
+        from curobo_b200.dynamics import Dynamics
+        rm = wl["robot"]
+        rng = np.random.default_rng(7)
+        mc = np.concatenate([rng.uniform(-0.05, 0.05, (rm.num_links, 3)), rng.uniform(0.2, 3.0, (rm.num_links, 1))], 1)
+        inn = np.zeros((rm.num_links, 8))
+        inn[:, :3] = rng.uniform(0.002, 0.01, (rm.num_links, 3))
+        eng.attach_dynamics(Dynamics(rm, mc, inn, device=device), fused=wl["dynamics"] == "fused")
     return eng
 
 
@@ -427,7 +448,7 @@ def main():
                     help="1: also time a complete 100-iteration L-BFGS IK solve (512 goals x 32 seeds), reported under 'ik_solve'")
     ap.add_argument("--edt", type=int, default=1, help="1: also time the exact nearest-site transform (256^3), reported under 'edt'")
     ap.add_argument("--rnea", type=int, default=1, help="1: also time the RNEA inverse-dynamics kernels, reported under 'rnea'")
-    ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,franka_mpc_knots_1024x30_esdf_swept,franka_mpc_knots_inkernel_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
+    ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_mpc_1024x30_esdf_swept,franka_mpc_1024x30_esdf_swept_dynamics,franka_mpc_1024x30_esdf_swept_dynamics_host,franka_mpc_knots_1024x30_esdf_swept,franka_mpc_knots_inkernel_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf",
                     help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -250,3 +250,27 @@ def test_bench_side_entries_execute(run, monkeypatch):
 
 def test_pending_dynamics_aware_rollout(run):
     run("test_gpu_zy_effort_cost", "test_dynamics_aware_rollout_vs_oracle")
+
+
+def test_bench_dynamics_workloads_execute_and_agree(run):
+    """bench.py's `<mpc>_dynamics` (torque inside the trajectory kernel) and `<mpc>_dynamics_host` (three extra launches) workloads,
+    shrunk to two trajectories and a 64^3 ESDF: both build, run, and give the same costs and gradients."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    outs = {}
+    for name in ("franka_mpc_1024x30_esdf_swept_dynamics", "franka_mpc_1024x30_esdf_swept_dynamics_host", "franka_mpc_1024x30_esdf_swept"):
+        wl = bench.make_workload(name)
+        wl["B"] = 2
+        wl["q"] = wl["q"][:2]
+        wl["extra"] = {k: v[:2] for k, v in wl["extra"].items()}
+        wl["goal"] = (wl["goal"][0][:2], wl["goal"][1][:2], wl["goal"][2][:2])
+        wl["voxel"]["n"], wl["voxel"]["voxel"] = 64, 0.04
+        eng = bench.build_engine(wl, "cpu")
+        kw = {k: torch.as_tensor(v) for k, v in wl["extra"].items()}
+        o = eng.evaluate_action(torch.as_tensor(wl["q"]), **kw)
+        outs[name] = (o.cost.clone(), o.grad_q.clone(), o.grad_vel.clone(), o.grad_acc.clone())
+    f, h, plain = (outs[k] for k in outs)
+    for a_, b_ in zip(f, h):
+        assert torch.allclose(a_, b_, rtol=2e-3, atol=2e-5 * float(b_.abs().max()))
+    assert not torch.allclose(f[0], plain[0])        # the effort terms are live in this workload
