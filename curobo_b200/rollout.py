@@ -310,6 +310,15 @@ class RolloutEngine:
                 sp.out_dt = self._state_dt.data_ptr()
         io = _lib.RolloutIO()
         io.spline = C.pointer(sp)
+        # dynamics-aware cost with the expanded schedule: the trajectory kernel reads the spline states like caller-provided
+        # ones, its RNEA-adjoint gradients flow into grad_knots through the spline adjoint behind it
+        if self._dyn_params is not None and not in_kernel_spline:
+            io.dynamics = C.pointer(self._dyn_params)
+        if self._effort_cost is not None:
+            raise ValueError("evaluate_knots supports the dynamics-aware cost only inside the kernel (attach_dynamics(fused=True), "
+                             "swept mode, in_kernel_spline=False)")
+        if self._dyn_params is not None and in_kernel_spline:
+            raise ValueError("the dynamics-aware cost needs the expanded spline schedule (in_kernel_spline=False)")
         return self._launch(io, B, H, env_query_idx)
 
     def _launch(self, io, B: int, H: int, env_query_idx) -> RolloutOutput:

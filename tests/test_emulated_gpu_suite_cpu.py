@@ -274,3 +274,7 @@ def test_bench_dynamics_workloads_execute_and_agree(run):
     for a_, b_ in zip(f, h):
         assert torch.allclose(a_, b_, rtol=2e-3, atol=2e-5 * float(b_.abs().max()))
     assert not torch.allclose(f[0], plain[0])        # the effort terms are live in this workload
+
+
+def test_pending_dynamics_aware_knots(run):
+    run("test_gpu_zy_effort_cost", "test_dynamics_aware_knots_rollout_is_consistent")

@@ -119,3 +119,60 @@ def test_dynamics_aware_rollout_vs_oracle():
     assert np.allclose(fused.grad_vel.cpu().numpy(), gv, rtol=3e-3, atol=3e-5 * np.abs(gv).max())
     assert np.allclose(fused.grad_acc.cpu().numpy(), ga, rtol=3e-3, atol=3e-5 * np.abs(ga).max())
     assert np.allclose(fused.cspace_cost.cpu().numpy(), want["cspace_cost"] + ec, rtol=3e-4, atol=1e-5 * float((want["cspace_cost"] + ec).max()))
+
+
+def test_dynamics_aware_knots_rollout_is_consistent():
+    """evaluate_knots with the in-kernel inverse dynamics (expanded spline schedule): cost and d cost / d knots equal the chain
+    spline -> dynamics-aware evaluate_action on the spline states -> spline adjoint, i.e. the RNEA-adjoint gradients reach the knots."""
+    import dataclasses
+    from curobo_b200.backends import trajectory as trajectory_cu
+    from curobo_b200.rollout import RolloutConfig, RolloutEngine
+    from curobo_b200.scene import CuboidData, VoxelData
+    from curobo_b200.trajectory import JointState
+    from curobo_b200.world import make_benchmark_cuboid_world
+    from dynamics_cases import make_case
+    from helpers import random_q, random_walk_q, small_voxel_world
+    from oracle import rollout_oracle as O
+    B, nk, degree, steps = 2, 8, 4, 2
+    H = (nk + degree + 1) * steps + 1
+    c = make_case("franka", 4, 33)
+    rm = dataclasses.replace(c["rm"], effort_limits=np.stack([np.full(c["D"], -8.0), np.full(c["D"], 8.0)]).astype(np.float32))
+    D = c["D"]
+    knots = random_walk_q(rm, B, nk, seed=81)
+    z = np.zeros((B, D), np.float32)
+    cfg = RolloutConfig.trajopt()
+    cfg.cspace_reg = (1000.0, 10000.0, 5.0, 0.05, 40.0)
+    cub, vox = make_benchmark_cuboid_world(), small_voxel_world()
+    _, _, p, qt = O.fk_forward(rm, random_q(rm, B, seed=82))
+
+    def engine():
+        e = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+        e.update_goal(T(p[:, :, None, :].copy()), T(qt[:, :, None, :].copy()), T(np.arange(B, dtype=np.int32)),
+                      non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32, device=DEV))
+        e.attach_dynamics(Dynamics(rm, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV))
+        return e
+
+    ks = JointState(T(knots[:, 0].copy()), T(z), T(z), T(z))
+    kg = JointState(T(knots[:, -1].copy()), T(z), T(z), T(z), dt=T(np.full(B, 0.05, np.float32)))
+    kidx = torch.arange(B, dtype=torch.int32, device=DEV)
+    kimp = torch.zeros(B, dtype=torch.uint8, device=DEV)
+    e1 = engine()
+    o1 = e1.evaluate_knots(T(knots), ks, kidx, kg, kidx, kimp, degree, steps)
+    torch.cuda.synchronize()
+    cost1, gk1 = o1.cost.clone(), o1.grad_knots.clone()
+    st = [x.clone() for x in e1._state]
+    e2 = engine()
+    o2 = e2.evaluate_action(st[0], vel=st[1], acc=st[2], jerk=st[3], dt=e1._state_dt.clone())
+    gk2 = torch.zeros_like(gk1)
+    trajectory_cu.launch_bspline_interpolation_backward_kernel(gk2, o2.grad_q, o2.grad_vel, o2.grad_acc, o2.grad_jerk, kg.dt, kidx,
+                                                               kimp, B, H, D, nk, degree)
+    torch.cuda.synchronize()
+    assert torch.allclose(cost1, o2.cost, rtol=1e-5, atol=1e-6 * float(o2.cost.abs().max()))
+    assert torch.allclose(gk1, gk2, rtol=1e-4, atol=1e-6 * float(gk2.abs().max()))
+    e3 = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    e3.update_goal(T(p[:, :, None, :].copy()), T(qt[:, :, None, :].copy()), T(np.arange(B, dtype=np.int32)),
+                   non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32, device=DEV))
+    o3 = e3.evaluate_knots(T(knots), ks, kidx, kg, kidx, kimp, degree, steps)
+    assert not torch.allclose(o3.grad_knots, gk1), "the dynamics terms must reach the knots"
+    with pytest.raises(ValueError):
+        e1.evaluate_knots(T(knots), ks, kidx, kg, kidx, kimp, degree, steps, in_kernel_spline=True)
