@@ -248,8 +248,9 @@ def test_bench_side_entries_execute(run, monkeypatch):
     assert e["grid"] == [24, 24, 24] and e["launches"] == 3 and e["sites"] > 0
 
 
-def test_pending_dynamics_aware_rollout(run):
-    run("test_gpu_zy_effort_cost", "test_dynamics_aware_rollout_vs_oracle")
+@pytest.mark.parametrize("robot,B,H", [("franka", 3, 7), ("g1_29", 2, 4)])
+def test_pending_dynamics_aware_rollout(run, robot, B, H):
+    run("test_gpu_zy_effort_cost", "test_dynamics_aware_rollout_vs_oracle", robot, B, H)
 
 
 def test_bench_dynamics_workloads_execute_and_agree(run):

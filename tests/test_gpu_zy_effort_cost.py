@@ -45,7 +45,8 @@ def test_dynamics_state_cost_vs_oracle(robot, B, H):
         assert torch.equal(a_, b_)
 
 
-def test_dynamics_aware_rollout_vs_oracle():
+@pytest.mark.parametrize("robot,B,H", [("franka", 3, 7), ("g1_29", 2, 4)])
+def test_dynamics_aware_rollout_vs_oracle(robot, B, H):
     """RolloutEngine.attach_dynamics: the fused trajectory rollout (swept ESDF + cuboid collision, speed metric, pose, STATE c-space)
     plus the effort channel fed by RNEA.  Oracle = rollout oracle (torque-free) + the effort-only STATE cost composed with the RNEA
     oracle and its adjoint; costs and the gradients w.r.t. position, velocity and acceleration must be the sums."""
@@ -56,8 +57,7 @@ def test_dynamics_aware_rollout_vs_oracle():
     from helpers import random_q, random_walk_q, small_voxel_world
     from oracle import dynamics_oracle as do
     from oracle import rollout_oracle as O
-    B, H = 3, 7
-    c = make_case("franka", B * H, 31)
+    c = make_case(robot, B * H, 31)
     rm = c["rm"]
     D = c["D"]
     q = random_walk_q(rm, B, H, seed=71)
@@ -77,14 +77,15 @@ def test_dynamics_aware_rollout_vs_oracle():
     gp, gq = p[:, :, None, :].copy(), qt[:, :, None, :].copy()
     idx = np.arange(B, dtype=np.int32)
     eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
-    eng.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32, device=DEV))
+    eng.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=torch.zeros((rm.num_tool_frames, 6), dtype=torch.float32, device=DEV))
     base = eng.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
     base_cost, base_gq = base.cost.clone(), base.grad_q.clone()
     eng.attach_dynamics(Dynamics(rm, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV), effort_limits=elim)
     out = eng.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
     torch.cuda.synchronize()
-    ocfg = cfg.to_oracle_cfg(1)
-    ocfg["pose_non_terminal_axes"] = np.zeros((1, 6), np.float32)
+    Lt = rm.num_tool_frames
+    ocfg = cfg.to_oracle_cfg(Lt)
+    ocfg["pose_non_terminal_axes"] = np.zeros((Lt, 6), np.float32)
     want = O.rollout_cost_grad(rm, q, ocfg, world_cuboid=cub, world_voxel=vox, goal_pos=gp, goal_quat=gq, idxs_goal=idx, vel=v,
                                acc=a_, jerk=j_, dt=dt)
     lim = dict(p=rm.position_limits, v=rm.velocity_limits, a=rm.acceleration_limits, j=rm.jerk_limits, tau=elim)
@@ -109,7 +110,7 @@ def test_dynamics_aware_rollout_vs_oracle():
     import dataclasses
     rm2 = dataclasses.replace(rm, effort_limits=elim)
     eng2 = RolloutEngine(rm2, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
-    eng2.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32, device=DEV))
+    eng2.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=torch.zeros((rm.num_tool_frames, 6), dtype=torch.float32, device=DEV))
     eng2.attach_dynamics(Dynamics(rm2, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV))
     assert eng2._dyn_params is not None and eng2._effort_cost is None
     fused = eng2.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
