@@ -103,10 +103,11 @@ CB_HD Rp local_Rp_sc(const float *ft, int jt, float sn, float cs, float angle) {
   }
   return o;
 }
+template <class L = LdNc>
 CB_HD Rp local_Rp(const float *ft, int jt, float angle) {
   float s = 0.0f, c = 1.0f;
   if (jt >= 3) sincosf(angle, &s, &c);
-  return local_Rp_sc(ft, jt, s, c, angle);
+  return local_Rp_sc<L>(ft, jt, s, c, angle);
 }
 
 // motion transform parent -> child:  w' = R^T w,  v' = R^T (v + w x p)
@@ -331,6 +332,7 @@ struct JointRef {
   bool root, moving;
   float mul, q_eff;
 };
+template <class L = LdNc>
 CB_HD JointRef joint_ref(const Model &M, int k, const float *q_row) {
   JointRef j;
   j.jt = M.joint_type[k];
@@ -341,25 +343,25 @@ CB_HD JointRef joint_ref(const Model &M, int k, const float *q_row) {
   j.mul = 1.0f;
   j.q_eff = 0.0f;
   if (j.moving) {
-    j.mul = ld(M.joint_offset + 2 * k);
-    j.q_eff = j.mul * q_row[j.ji] + ld(M.joint_offset + 2 * k + 1);
+    j.mul = L::f(M.joint_offset + 2 * k);
+    j.q_eff = j.mul * q_row[j.ji] + L::f(M.joint_offset + 2 * k + 1);
   }
   return j;
 }
 
 // tau[D] (accumulated into; zeroed here) and the row's cache [nl*20].  q / qd / qdd: this row's [D].
-template <class Store>
+template <class Store, class L = LdNc>
 CB_HD void rnea_forward_row(const Model &M, Store &S, const float *q, const float *qd, const float *qdd, const float *f_ext,
                             float *tau, float *cache) {
   for (int d = 0; d < M.D; ++d) tau[d] = 0.0f;
   float g[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) g[i] = ld(M.gravity + i);
+  for (int i = 0; i < 6; ++i) g[i] = L::f(M.gravity + i);
   for (int idx = 0; idx < M.nl; ++idx) {  // level order: parents before children
     const int k = M.level_links[idx];
-    const JointRef j = joint_ref(M, k, q);
+    const JointRef j = joint_ref<L>(M, k, q);
     const float qd_eff = j.moving ? j.mul * qd[j.ji] : 0.0f, qdd_eff = j.moving ? j.mul * qdd[j.ji] : 0.0f;
-    const Rp t = local_Rp(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
+    const Rp t = local_Rp<L>(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
     float v[6], a[6], tmp[6];
     if (j.root) {
 #pragma unroll
@@ -390,8 +392,8 @@ CB_HD void rnea_forward_row(const Model &M, Store &S, const float *q, const floa
       ck[i] = v[i];
       ck[6 + i] = a[i];
     }
-    inertia_times(M.masses_com + 4 * k, M.inertias + 8 * k, a, Ia);
-    inertia_times(M.masses_com + 4 * k, M.inertias + 8 * k, v, Iv);
+    inertia_times<L>(M.masses_com + 4 * k, M.inertias + 8 * k, a, Ia);
+    inertia_times<L>(M.masses_com + 4 * k, M.inertias + 8 * k, v, Iv);
     force_cross(v, Iv, x);
 #pragma unroll
     for (int i = 0; i < 6; ++i) a[i] = Ia[i] + x[i] - (f_ext ? f_ext[6 * k + i] : 0.0f);
@@ -400,12 +402,12 @@ CB_HD void rnea_forward_row(const Model &M, Store &S, const float *q, const floa
   for (int lv = M.n_levels - 1; lv >= 0; --lv) {  // leaves -> root: torques, wrench propagation
     for (int idx = M.level_starts[lv]; idx < M.level_starts[lv + 1]; ++idx) {
       const int k = M.level_links[idx];
-      const JointRef j = joint_ref(M, k, q);
+      const JointRef j = joint_ref<L>(M, k, q);
       float f[6];
       load6(S, 1, k, f);
       if (j.moving) tau[j.ji] += j.mul * pick6(f, s_index(j.jt));
       if (!j.root) {
-        const Rp t = local_Rp(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
+        const Rp t = local_Rp<L>(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
         float c[6], fp[6];
         XTf(t, f, c);
         load6(S, 1, j.par, fp);
@@ -423,13 +425,13 @@ CB_HD void rnea_forward_row(const Model &M, Store &S, const float *q, const floa
 }
 
 // grad_q / grad_qd / grad_qdd [D] (overwritten) from grad_tau [D] and the row's forward cache.
-template <class Store>
+template <class Store, class L = LdNc>
 CB_HD void rnea_backward_row(const Model &M, Store &S, const float *grad_tau, const float *q, const float *qd,
                              const float *cache, float *gq, float *gqd, float *gqdd, float *grad_f_ext) {
   for (int d = 0; d < M.D; ++d) gq[d] = gqd[d] = gqdd[d] = 0.0f;
   float g[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) g[i] = ld(M.gravity + i);
+  for (int i = 0; i < 6; ++i) g[i] = L::f(M.gravity + i);
   for (int k = 0; k < M.nl; ++k) {
     const float *ck = cache + (size_t)k * kCacheFloatsPerLink;
 #pragma unroll
@@ -444,12 +446,12 @@ CB_HD void rnea_backward_row(const Model &M, Store &S, const float *grad_tau, co
   // pass 1, root -> leaves: f_bar
   for (int idx = 0; idx < M.nl; ++idx) {
     const int k = M.level_links[idx];
-    const JointRef j = joint_ref(M, k, q);
+    const JointRef j = joint_ref<L>(M, k, q);
     float fk[6], fbar[6] = {0, 0, 0, 0, 0, 0};
     load6(S, 2, k, fk);
     if (j.moving) add6(fbar, s_index(j.jt), j.mul * grad_tau[j.ji]);
     if (!j.root) {
-      const Rp t = local_Rp(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
+      const Rp t = local_Rp<L>(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
       float fp[6], X[6];
       load6(S, 2, j.par, fp);
       Xv(t, fp, X);
@@ -466,22 +468,22 @@ CB_HD void rnea_backward_row(const Model &M, Store &S, const float *grad_tau, co
   for (int lv = M.n_levels - 1; lv >= 0; --lv) {
     for (int idx = M.level_starts[lv]; idx < M.level_starts[lv + 1]; ++idx) {
       const int k = M.level_links[idx];
-      const JointRef j = joint_ref(M, k, q);
+      const JointRef j = joint_ref<L>(M, k, q);
       const float *mc = M.masses_com + 4 * k, *in = M.inertias + 8 * k;
       float v[6], fbar[6], ab[6], vb[6], t1[6], t2[6];
       load6(S, 0, k, v);
       load6(S, 2, k, fbar);
       load6(S, 3, k, ab);
       load6(S, 4, k, vb);
-      inertia_times(mc, in, fbar, t1);
+      inertia_times<L>(mc, in, fbar, t1);
 #pragma unroll
       for (int i = 0; i < 6; ++i) ab[i] += t1[i];
-      inertia_times(mc, in, v, t1);
+      inertia_times<L>(mc, in, v, t1);
       force_cross(fbar, t1, t2);
 #pragma unroll
       for (int i = 0; i < 6; ++i) vb[i] -= t2[i];
       motion_cross(v, fbar, t1);
-      inertia_times(mc, in, t1, t2);
+      inertia_times<L>(mc, in, t1, t2);
 #pragma unroll
       for (int i = 0; i < 6; ++i) vb[i] -= t2[i];
       const int s = j.jt >= 0 ? s_index(j.jt) : 0;
@@ -493,7 +495,7 @@ CB_HD void rnea_backward_row(const Model &M, Store &S, const float *grad_tau, co
         gqd[j.ji] -= j.mul * pick6(fx, s);
         force_cross_S_add(vb, s, qd_k, ab);
       }
-      const Rp t = local_Rp(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
+      const Rp t = local_Rp<L>(M.fixed_transforms + 12 * k, j.jt, j.q_eff);
       if (!j.root) {
         float c[6], pa[6];
         XTf(t, ab, c);

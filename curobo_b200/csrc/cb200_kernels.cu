@@ -212,7 +212,9 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
     DynRowStore st{cache + 20 * rv.nl, rv.nl};
     const dyn::Model M{rv.fixed, a.dyn.masses_com, a.dyn.inertias, rv.joint_type, rv.joint_map, rv.link_map, rv.joff,
                        a.dyn.gravity, rv.level_off, rv.level_links, rv.nl, D, rv.n_levels};
-    if (lane == 0) dyn::rnea_forward_row(M, st, es.qv, qd_s, qdd_s, nullptr, tau_s, cache);
+    // LdPlain: the tree part of M (fixed transforms, joint offsets) points into the shared-memory copy of the robot blob, which
+    // the read-only global path (__ldg) must not be used on
+    if (lane == 0) dyn::rnea_forward_row<DynRowStore, dyn::LdPlain>(M, st, es.qv, qd_s, qdd_s, nullptr, tau_s, cache);
     __syncwarp();
     const float dt = seed_dt(a, b);
     float w_b = cfg.cspace_weight[4], w_l2 = cfg.cspace_reg[3], w_en = cfg.cspace_reg[4];
@@ -235,7 +237,7 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
       if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] += c;
     }
     __syncwarp();
-    if (lane == 0) dyn::rnea_backward_row(M, st, gt_s, es.qv, qd_s, cache, gq_s, gqd_s, gqdd_s, nullptr);
+    if (lane == 0) dyn::rnea_backward_row<DynRowStore, dyn::LdPlain>(M, st, gt_s, es.qv, qd_s, cache, gq_s, gqd_s, gqdd_s, nullptr);
     __syncwarp();
     #pragma unroll 1
     for (int d = lane; d < D; d += 32) {
