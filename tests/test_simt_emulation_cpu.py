@@ -167,6 +167,11 @@ def test_rnea_cta_kernels_are_race_free_under_thread_sanitizer(tmp_path):
 def _tsan_build(src_name, exe_name, extra=()):
     exe, src = os.path.join(SIMT, exe_name), os.path.join(SIMT, src_name)
     extra = [os.path.join(ROOT, e) if e.endswith(".cpp") else e for e in extra]
+    csrc = os.path.join(ROOT, "curobo_b200", "csrc")
+    deps = [src] + [e for e in extra if e.endswith(".cpp")] + [os.path.join(SIMT, f) for f in os.listdir(SIMT) if f.endswith((".h", ".cpp"))] + \
+        [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if os.path.exists(exe) and all(os.path.getmtime(d) <= os.path.getmtime(exe) for d in deps):
+        return exe
     r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-w", *extra, "-I", SIMT, src, "-o", exe],
                        capture_output=True, text=True)
     if r.returncode != 0:
