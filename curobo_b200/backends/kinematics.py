@@ -33,20 +33,22 @@ def launch_kinematics_forward(
     n_joints: int,
     compute_com: bool = False,
 ) -> None:
-    """FK without sphere output (cuda_core_backend/kinematics.py:21-88): tool poses + cumulative transforms."""
-    if compute_com:
-        raise ValueError("b200 backend: compute_com is outside the hot-path scope (SURVEY.md section 8)")
+    """FK without sphere output (cuda_core_backend/kinematics.py:21-88): tool poses + cumulative transforms
+    (+ batch_center_of_mass [B*H, 4] = world CoM xyz, total mass, when compute_com)."""
     dev = joint_vec.device
+    if compute_com:
+        check_tensors(dev, torch.float32, batch_center_of_mass=batch_center_of_mass, link_masses_com=link_masses_com)
     check_tensors(dev, torch.float32, link_pos=link_pos, link_quat=link_quat, global_cumul_mat=global_cumul_mat,
                   joint_vec=joint_vec, fixed_transform=fixed_transform, joint_offset_map=joint_offset_map)
     check_tensors(dev, torch.int8, joint_map_type=joint_map_type)
     check_tensors(dev, torch.int16, joint_map=joint_map, link_map=link_map, tool_frame_map=tool_frame_map)
     L = _lib.load()
     err = L.cb200_kinematics_forward_spheres(
-        link_pos.data_ptr(), link_quat.data_ptr(), None, None, global_cumul_mat.data_ptr(), joint_vec.data_ptr(),
-        fixed_transform.data_ptr(), None, None, joint_map_type.data_ptr(), joint_map.data_ptr(), link_map.data_ptr(),
+        link_pos.data_ptr(), link_quat.data_ptr(), None, batch_center_of_mass.data_ptr() if compute_com else None,
+        global_cumul_mat.data_ptr(), joint_vec.data_ptr(), fixed_transform.data_ptr(), None,
+        link_masses_com.data_ptr() if compute_com else None, joint_map_type.data_ptr(), joint_map.data_ptr(), link_map.data_ptr(),
         tool_frame_map.data_ptr(), None, joint_offset_map.data_ptr(), None, 1, int(batch_size), int(horizon), int(n_joints),
-        0, int(link_map.shape[0]), int(tool_frame_map.shape[0]), 1, 0, stream_ptr(dev))
+        0, int(link_map.shape[0]), int(tool_frame_map.shape[0]), 1, int(bool(compute_com)), stream_ptr(dev))
     _lib.check(err, "launch_kinematics_forward")
 
 
@@ -86,9 +88,9 @@ def launch_kinematics_forward_spheres(
     """FK + spheres + tool poses; outputs are the passed-in buffers (written in place)."""
     if output_threads_per_batch not in (32, 64, 128):
         raise ValueError("output_threads_per_batch must be one of 32, 64, or 128")
-    if compute_com:
-        raise ValueError("b200 backend: compute_com is outside the hot-path scope (SURVEY.md section 8)")
     dev = joint_vec.device
+    if compute_com:
+        check_tensors(dev, torch.float32, batch_center_of_mass=batch_center_of_mass, link_masses_com=link_masses_com)
     check_tensors(dev, torch.float32, link_pos=link_pos, link_quat=link_quat,
                   batch_robot_spheres=batch_robot_spheres, global_cumul_mat=global_cumul_mat, joint_vec=joint_vec,
                   fixed_transform=fixed_transform, robot_spheres=robot_spheres, joint_offset_map=joint_offset_map)
@@ -105,7 +107,7 @@ def launch_kinematics_forward_spheres(
         joint_map_type.data_ptr(), joint_map.data_ptr(), link_map.data_ptr(), tool_frame_map.data_ptr(),
         link_sphere_map.data_ptr(), joint_offset_map.data_ptr(), env_query_idx.data_ptr(),
         int(num_envs), int(batch_size), int(horizon), int(n_joints), int(num_spheres), int(link_map.shape[0]),
-        int(tool_frame_map.shape[0]), int(bool(write_global_cumul)), 0, stream_ptr(dev))
+        int(tool_frame_map.shape[0]), int(bool(write_global_cumul)), int(bool(compute_com)), stream_ptr(dev))
     _lib.check(err, "launch_kinematics_forward_spheres")
 
 
@@ -141,9 +143,12 @@ def launch_kinematics_backward(
     compute_jacobian_grad: bool = False,
 ) -> None:
     """grad_out[B*H, D] (overwritten) from sphere / tool-pose gradients and the saved cumul matrices."""
-    if compute_com or compute_jacobian_grad:
-        raise ValueError("b200 backend: CoM / Jacobian-output gradients are outside the hot-path scope")
+    if compute_jacobian_grad:
+        raise ValueError("b200 backend: Jacobian-output gradients are outside the hot-path scope")
     dev = grad_out.device
+    if compute_com:
+        check_tensors(dev, torch.float32, grad_center_of_mass=grad_center_of_mass, batch_center_of_mass=batch_center_of_mass,
+                      link_masses_com=link_masses_com)
     check_tensors(dev, torch.float32, grad_out=grad_out, grad_nlinks_pos=grad_nlinks_pos,
                   grad_nlinks_quat=grad_nlinks_quat, grad_spheres=grad_spheres, global_cumul_mat=global_cumul_mat,
                   robot_spheres=robot_spheres, joint_offset_map=joint_offset_map)
@@ -164,5 +169,6 @@ def launch_kinematics_backward(
         joint_map_type.data_ptr(), tool_frame_map.data_ptr(), link_sphere_map.data_ptr(), p(link_chain_data),
         p(link_chain_offsets), p(joint_links_data), p(joint_links_offsets), p(joint_affects_endeffector),
         joint_offset_map.data_ptr(), env_query_idx.data_ptr(), int(num_envs), int(batch_size), int(horizon),
-        int(n_joints), int(num_spheres), int(link_map.shape[0]), int(tool_frame_map.shape[0]), 0, 0, stream_ptr(dev))
+        int(n_joints), int(num_spheres), int(link_map.shape[0]), int(tool_frame_map.shape[0]), int(bool(compute_com)), 0,
+        stream_ptr(dev))
     _lib.check(err, "launch_kinematics_backward")

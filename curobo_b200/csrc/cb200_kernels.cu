@@ -1190,8 +1190,12 @@ struct KinFwdArgs {
   const int16_t *jmap, *lmap, *tool_map, *sph_link;
   const int32_t *env_query_idx;
   int num_envs, N, horizon, D, S, nl, L, write_cumul;
+  // centre of mass (COM instantiation only): link_masses_com [nl,4] = local CoM xyz, mass; com_out [N,4] = world CoM xyz, total mass
+  const float *masses_com;
+  float *com_out;
 };
 
+template <bool COM = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) kin_forward_kernel(const __grid_constant__ KinFwdArgs a) {
   CB200_EXTERN_SHARED __align__(16) float fsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1244,6 +1248,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) kin_forward_kernel(const __
       o[2] = T[11];
       *reinterpret_cast<float4 *>(a.link_quat + ((size_t)e * a.L + t) * 4) = make_float4(qt.w, qt.x, qt.y, qt.z);
     }
+    if constexpr (COM) {  // mass-weighted mean of the links' centres of mass (kinematics_forward_helper.cuh:538-601)
+      float sx = 0.0f, sy = 0.0f, sz = 0.0f, sm = 0.0f;
+      for (int l = lane; l < a.nl; l += 32) {
+        const float4 mc = __ldg(reinterpret_cast<const float4 *>(a.masses_com) + l);
+        if (mc.w > 0.0f) {
+          const float *T = cumul + 12 * l;
+          sx += mc.w * (T[0] * mc.x + T[1] * mc.y + T[2] * mc.z + T[3]);
+          sy += mc.w * (T[4] * mc.x + T[5] * mc.y + T[6] * mc.z + T[7]);
+          sz += mc.w * (T[8] * mc.x + T[9] * mc.y + T[10] * mc.z + T[11]);
+          sm += mc.w;
+        }
+      }
+      sx = warp_sum(sx), sy = warp_sum(sy), sz = warp_sum(sz), sm = warp_sum(sm);
+      if (lane == 0) {
+        float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (sm > 0.0f) o = make_float4(sx / sm, sy / sm, sz / sm, sm);
+        *reinterpret_cast<float4 *>(a.com_out + (size_t)e * 4) = o;
+      }
+    }
     __syncwarp();
   }
 }
@@ -1258,8 +1281,11 @@ struct KinBwdArgs {
   const int8_t *jtype;
   const int32_t *env_query_idx;
   int num_envs, N, horizon, D, S, nl, L;
+  // centre-of-mass gradient (COM instantiation only): g_com [N,4] (w ignored), com [N,4] (w = total mass), masses_com [nl,4]
+  const float *g_com, *com, *masses_com;
 };
 
+template <bool COM = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) kin_backward_kernel(const __grid_constant__ KinBwdArgs a) {
   CB200_EXTERN_SHARED __align__(16) float fsm[];
   // CTA-shared: ancestor masks [nl] (uint64)
@@ -1312,6 +1338,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) kin_backward_kernel(const _
           const Q4 qt = quat_from_transform(Tk);
           F = F + g;
           T = T + quat_grad_to_omega(qt, gqv.x, gqv.y, gqv.z, gqv.w);
+        }
+      }
+      if constexpr (COM) {
+        // d loss / d CoM acts on link k as the force g * m_k / M applied at the link's world centre of mass
+        // (kinematics_backward_helper.cuh:187-260: compute_center_of_mass_gradients walks the same chain as a sphere)
+        const float4 mc = __ldg(reinterpret_cast<const float4 *>(a.masses_com) + k);
+        const float M = __ldg(a.com + (size_t)e * 4 + 3);
+        const V3 gc = mk3(__ldg(a.g_com + (size_t)e * 4), __ldg(a.g_com + (size_t)e * 4 + 1), __ldg(a.g_com + (size_t)e * 4 + 2));
+        if (mc.w > 0.0f && M > 0.0f && !(gc.x == 0.0f && gc.y == 0.0f && gc.z == 0.0f)) {
+          const float sc = mc.w / M;
+          const V3 g = mk3(gc.x * sc, gc.y * sc, gc.z * sc);
+          const V3 rel = mk3(Tk[0] * mc.x + Tk[1] * mc.y + Tk[2] * mc.z, Tk[4] * mc.x + Tk[5] * mc.y + Tk[6] * mc.z,
+                             Tk[8] * mc.x + Tk[9] * mc.y + Tk[10] * mc.z);
+          F = F + g;
+          T = T + cross(rel, g);
         }
       }
       ft[8 * k + 0] = F.x;
@@ -1827,20 +1868,21 @@ int cb200_kinematics_forward_spheres(float *link_pos, float *link_quat, float *b
                                      const int32_t *env_query_idx, int num_envs, int batch_size, int horizon,
                                      int n_joints, int num_spheres, int num_links, int n_tool_frames,
                                      int write_global_cumul, int compute_com, cb200_stream_t stream) {
-  (void)batch_center_of_mass;
-  (void)link_masses_com;
-  if (compute_com != 0 || batch_size < 0 || num_links < 1 || horizon < 1) return ret(cudaErrorInvalidValue);
+  if (batch_size < 0 || num_links < 1 || horizon < 1) return ret(cudaErrorInvalidValue);
+  if (compute_com != 0 && (batch_center_of_mass == nullptr || link_masses_com == nullptr)) return ret(cudaErrorInvalidValue);
   if (batch_size == 0) return ret(cudaSuccess);
   KinFwdArgs a{link_pos, link_quat, batch_robot_spheres, global_cumul_mat, joint_vec, fixed_transform, robot_spheres,
                joint_offset_map, joint_map_type, joint_map, link_map, tool_frame_map, link_sphere_map, env_query_idx,
-               num_envs, batch_size, horizon, n_joints, num_spheres, num_links, n_tool_frames, write_global_cumul};
+               num_envs, batch_size, horizon, n_joints, num_spheres, num_links, n_tool_frames, write_global_cumul,
+               link_masses_com, batch_center_of_mass};
   const size_t smem = (size_t)kWarpsPerCta * num_links * 12 * sizeof(float);
+  void (*kern)(const KinFwdArgs) = compute_com != 0 ? kin_forward_kernel<true> : kin_forward_kernel<false>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kin_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return ret(e);
   }
-  const int grid = persistent_grid(kin_forward_kernel, kWarpsPerCta * 32, smem, (batch_size + kWarpsPerCta - 1) / kWarpsPerCta);
-  CB200_LAUNCH(kin_forward_kernel, grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream, a);
+  const int grid = persistent_grid(kern, kWarpsPerCta * 32, smem, (batch_size + kWarpsPerCta - 1) / kWarpsPerCta);
+  CB200_LAUNCH(kern, grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream, a);
   return launch_status();
 }
 
@@ -1856,29 +1898,29 @@ int cb200_kinematics_backward(float *grad_out, const float *grad_nlinks_pos, con
                               const int32_t *env_query_idx, int num_envs, int batch_size, int horizon, int n_joints,
                               int num_spheres, int num_links, int n_tool_frames, int compute_com,
                               int compute_jacobian_grad, cb200_stream_t stream) {
-  (void)grad_center_of_mass;
-  (void)batch_center_of_mass;
   (void)grad_jacobian;
-  (void)link_masses_com;
   (void)link_chain_data;
   (void)link_chain_offsets;
   (void)joint_links_data;
   (void)joint_links_offsets;
   (void)joint_affects_endeffector;
-  if (compute_com != 0 || compute_jacobian_grad != 0 || num_links < 1 || num_links > kMaxLinks || horizon < 1)
+  if (compute_jacobian_grad != 0 || num_links < 1 || num_links > kMaxLinks || horizon < 1) return ret(cudaErrorInvalidValue);
+  if (compute_com != 0 && (grad_center_of_mass == nullptr || batch_center_of_mass == nullptr || link_masses_com == nullptr))
     return ret(cudaErrorInvalidValue);
   if (batch_size == 0) return ret(cudaSuccess);
   KinBwdArgs a{grad_out, grad_nlinks_pos, grad_nlinks_quat, num_spheres > 0 ? grad_spheres : nullptr, global_cumul_mat,
                robot_spheres, joint_offset_map, link_map, joint_map, tool_frame_map, link_sphere_map, joint_map_type,
-               env_query_idx, num_envs, batch_size, horizon, n_joints, num_spheres, num_links, n_tool_frames};
+               env_query_idx, num_envs, batch_size, horizon, n_joints, num_spheres, num_links, n_tool_frames,
+               grad_center_of_mass, batch_center_of_mass, link_masses_com};
+  void (*kern)(const KinBwdArgs) = compute_com != 0 ? kin_backward_kernel<true> : kin_backward_kernel<false>;
   const size_t per_warp = ((size_t)num_links * 12 + num_links * 8 + num_links + n_joints + 3) & ~(size_t)3;
   const size_t smem = ((((size_t)2 * num_links + 3) & ~(size_t)3) + kWarpsPerCta * per_warp) * sizeof(float);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kin_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return ret(e);
   }
-  const int grid = persistent_grid(kin_backward_kernel, kWarpsPerCta * 32, smem, (batch_size + kWarpsPerCta - 1) / kWarpsPerCta);
-  CB200_LAUNCH(kin_backward_kernel, grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream, a);
+  const int grid = persistent_grid(kern, kWarpsPerCta * 32, smem, (batch_size + kWarpsPerCta - 1) / kWarpsPerCta);
+  CB200_LAUNCH(kern, grid, kWarpsPerCta * 32, smem, (cudaStream_t)stream, a);
   return launch_status();
 }
 

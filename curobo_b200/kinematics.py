@@ -114,20 +114,64 @@ class KinematicsFusedFunction(torch.autograd.Function):
         return (grad_out,) + (None,) * 12
 
 
+class KinematicsComFunction(torch.autograd.Function):
+    """KinematicsFusedFunction with `compute_com=True` (cuda_ops/kinematics.py:93-356): the forward pass also writes the
+    centre of mass [B,H,4] (world xyz, total mass), the backward pass takes its gradient (xyz; the mass slot is ignored,
+    kinematics_backward_helper.cuh:187-260).  A separate class so that the path without CoM stays exactly as it is."""
+
+    @staticmethod
+    def forward(ctx, joint_seq, batch_link_position, batch_link_quaternion, batch_robot_spheres, batch_com,
+                batch_cumul_mat, kp: KinematicsParams, grad_out, grad_in_link_pos, grad_in_link_quat,
+                grad_in_robot_spheres, grad_in_com, env_query_idx, horizon: int):
+        b_size = batch_link_position.shape[0] * batch_link_position.shape[1]
+        ctx.set_materialize_grads(False)
+        kinematics_cu.launch_kinematics_forward_spheres(
+            batch_link_position, batch_link_quaternion, batch_robot_spheres, batch_com, batch_cumul_mat,
+            joint_seq.detach(), kp.fixed_transforms, kp.link_spheres, kp.link_masses_com, kp.joint_map_type,
+            kp.joint_map, kp.link_map, kp.tool_frame_map, kp.link_sphere_idx_map, kp.joint_offset_map, env_query_idx,
+            kp.num_envs, b_size, horizon, joint_seq.shape[-1], batch_robot_spheres.shape[2], 32, True, True)
+        ctx.kp, ctx.horizon, ctx.env_query_idx = kp, horizon, env_query_idx
+        ctx.bufs = (grad_out, grad_in_link_pos, grad_in_link_quat, grad_in_robot_spheres, grad_in_com)
+        ctx.save_for_backward(batch_cumul_mat, batch_com)
+        ctx.mark_non_differentiable(batch_cumul_mat)
+        return batch_link_position, batch_link_quaternion, batch_robot_spheres, batch_cumul_mat, batch_com
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_pos, g_quat, g_sph, g_cumul, g_com):
+        cumul, batch_com = ctx.saved_tensors
+        kp = ctx.kp
+        grad_out, z_pos, z_quat, z_sph, z_com = ctx.bufs
+        g_pos = z_pos if g_pos is None else g_pos.contiguous()
+        g_quat = z_quat if g_quat is None else g_quat.contiguous()
+        g_sph = z_sph if g_sph is None else g_sph.contiguous()
+        g_com = z_com if g_com is None else g_com.contiguous()
+        b_size = cumul.shape[0] * cumul.shape[1]
+        kinematics_cu.launch_kinematics_backward(
+            grad_out, g_pos, g_quat, g_sph, g_com, batch_com, None, cumul, kp.link_spheres, kp.link_masses_com,
+            kp.link_map, kp.joint_map, kp.joint_map_type, kp.tool_frame_map, kp.link_sphere_idx_map,
+            kp.link_chain_data, kp.link_chain_offsets, kp.joint_links_data, kp.joint_links_offsets,
+            kp.joint_affects_endeffector, kp.joint_offset_map, ctx.env_query_idx, kp.num_envs, b_size, ctx.horizon,
+            kp.num_dof, g_sph.shape[2], True, False)
+        return (grad_out,) + (None,) * 13
+
+
 @dataclass
 class KinematicsState:
     tool_pose_position: torch.Tensor      # [B,H,L,3]
     tool_pose_quaternion: torch.Tensor    # [B,H,L,4] wxyz
     robot_spheres: torch.Tensor           # [B,H,S,4]
     cumul_mat: torch.Tensor               # [B,H,nl,3,4]
+    center_of_mass: Optional[torch.Tensor] = None   # [B,H,4] world xyz, total mass (Kinematics(compute_com=True))
 
 
 class Kinematics:
     """`Kinematics.compute_kinematics` of the reference (robot/kinematics/kinematics.py:172-198)."""
 
-    def __init__(self, robot: RobotModel, device="cuda:0"):
+    def __init__(self, robot: RobotModel, device="cuda:0", compute_com: bool = False):
         self.device = torch.device(device)
         self.robot = robot
+        self.compute_com = bool(compute_com)
         self.params = KinematicsParams.from_robot_model(robot, self.device)
         self._shape = None
         self._env0 = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -146,6 +190,14 @@ class Kinematics:
         self.update_batch_size(b, h)
         B = self._bufs
         eq = env_query_idx if env_query_idx is not None else self._env0
+        if self.compute_com:
+            if "grad_in_com" not in B:
+                B["grad_in_com"] = torch.zeros((b, h, 4), dtype=torch.float32, device=self.device)
+            pos, quat, sph, cum, com = KinematicsComFunction.apply(
+                q, B["batch_link_position"], B["batch_link_quaternion"], B["batch_robot_spheres"], B["batch_com"],
+                B["batch_cumul_mat"], self.params, B["grad_out_q"], B["grad_in_link_pos"], B["grad_in_link_quat"],
+                B["grad_in_robot_spheres"], B["grad_in_com"], eq, h)
+            return KinematicsState(pos, quat, sph, cum, com)
         pos, quat, sph, cum = KinematicsFusedFunction.apply(
             q, B["batch_link_position"], B["batch_link_quaternion"], B["batch_robot_spheres"], B["batch_com"],
             B["batch_cumul_mat"], self.params, B["grad_out_q"], B["grad_in_link_pos"], B["grad_in_link_quat"],

@@ -42,7 +42,8 @@ const char *cb200_error_string(int err);
  *   (kernel kinematics_forward_spheres_kernel, kernels/kinematics/kinematics_forward_kernel.cuh:131-261).
  * batch_size is B*H (cuda_ops/kinematics.py:115).  env_query_idx [B] selects the sphere set
  * robot_spheres[num_envs, S, 4] for batch row n via env_query_idx[n / horizon] when num_envs > 1.
- * batch_center_of_mass / link_masses_com are accepted for signature parity; compute_com must be 0.
+ * compute_com != 0: batch_center_of_mass [B*H, 4] = mass-weighted mean of the links' world centres of mass (xyz) and the total mass
+ * (w), from link_masses_com [nl, 4] = local CoM xyz, mass; links with mass <= 0 are skipped (kinematics_forward_helper.cuh:538-601).
  * global_cumul_mat is written iff write_global_cumul != 0.
  * ------------------------------------------------------------------------------------------- */
 int cb200_kinematics_forward_spheres(
@@ -60,7 +61,9 @@ int cb200_kinematics_forward_spheres(
  *   curobo/_src/curobolib/backends/cuda_core_backend/kinematics.py:282-379
  *   (kernel kinematics_backward_kernel, kernels/kinematics/kinematics_backward_kernel.cuh:34-160).
  * link_chain_*, joint_links_*, joint_affects_endeffector are accepted for signature parity (the tree
- * is re-derived from link_map).  compute_com and compute_jacobian_grad must be 0.
+ * is re-derived from link_map).  compute_com != 0 adds the gradient of the centre of mass (grad_center_of_mass [B*H, 4], w ignored;
+ * batch_center_of_mass carries the total mass): the force g m_k / M at each link's world CoM, walked down the chain like a sphere
+ * gradient (kinematics_backward_helper.cuh:187-260).  compute_jacobian_grad must be 0.
  * ------------------------------------------------------------------------------------------- */
 int cb200_kinematics_backward(
     float *grad_out, const float *grad_nlinks_pos, const float *grad_nlinks_quat,

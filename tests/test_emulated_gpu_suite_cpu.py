@@ -281,3 +281,8 @@ def test_bench_dynamics_workloads_execute_and_agree(run):
 
 def test_pending_dynamics_aware_knots(run):
     run("test_gpu_zy_effort_cost", "test_dynamics_aware_knots_rollout_is_consistent")
+
+
+@pytest.mark.parametrize("robot,n", [("franka", 33), ("g1_29", 9)])
+def test_pending_center_of_mass(run, robot, n):
+    run("test_gpu_zw_center_of_mass", "test_center_of_mass_and_its_gradient", robot, n)
