@@ -380,3 +380,80 @@ extern "C" int ref_pba3d(int *site_index, int *buffer, int nx, int ny, int nz, i
   cudaMemcpyAsync(site_index, buffer, (size_t)nx * ny * nz * sizeof(int), cudaMemcpyDeviceToDevice, stream);
   return (int)cudaGetLastError();
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// FK with the centre-of-mass output and its gradient (COMPUTE_COM = true instantiations of the same reference kernels),
+// launch shapes as in ref_kinematics_forward_spheres / ref_kinematics_backward above.
+// ------------------------------------------------------------------------------------------------
+template <int MAXJ>
+static void launch_bwd_com(int blocks, int threads, size_t smem, cudaStream_t stream, float *grad_out, const float *g_pos,
+                           const float *g_quat, const float *g_sph, const float *g_com, const float *b_com, const float *cumul,
+                           const float *robot_spheres, const float *masses, const int8_t *jtype, const int16_t *jmap,
+                           const int16_t *lmap, const int16_t *tool, const int16_t *sphl, const int32_t *envq, const int16_t *cd,
+                           const int16_t *co, const int16_t *jd, const int16_t *jo, const bool *jae, const float *joff, int batch,
+                           int horizon, int ns, int nl, int nj, int nt, int nenv, int tpb) {
+  ck::kinematics_backward_kernel<float, float, MAXJ, true, true, false><<<blocks, threads, smem, stream>>>(
+      grad_out, g_pos, g_quat, g_sph, g_com, b_com, nullptr, cumul, robot_spheres, masses, jtype, jmap, lmap, tool, sphl, envq, cd,
+      co, jd, jo, jae, joff, batch, horizon, ns, nl, nj, nt, nenv, tpb);
+}
+
+extern "C" {
+
+int ref_kinematics_forward_spheres_com(float *link_pos, float *link_quat, float *batch_robot_spheres, float *batch_com,
+                                       float *global_cumul_mat, const float *q, const float *fixed_transform,
+                                       const float *robot_spheres, const float *link_masses_com, const int8_t *joint_map_type,
+                                       const int16_t *joint_map, const int16_t *link_map, const int16_t *tool_frame_map,
+                                       const int16_t *link_sphere_map, const float *joint_offset_map,
+                                       const int32_t *env_query_idx, int num_envs, int batch_size, int horizon, int n_joints,
+                                       int num_spheres, int num_links, int n_tool_frames, cudaStream_t stream) {
+  const int tpb = 32, max_threads = 256;
+  int bpb = 8;
+  const int smem_per = num_links * 12 * 4 * 2;
+  if (bpb > 48 * 1024 / smem_per) bpb = 48 * 1024 / smem_per;
+  if (bpb * tpb > max_threads) bpb = max_threads / tpb;
+  if (bpb < 1) bpb = 1;
+  if (bpb > batch_size) bpb = batch_size;
+  const int threads = bpb * tpb;
+  const int blocks = (batch_size + bpb - 1) / bpb;
+  ck::kinematics_forward_spheres_kernel<-1, 32, true, true><<<blocks, threads, (size_t)bpb * smem_per, stream>>>(
+      link_pos, link_quat, batch_robot_spheres, batch_com, global_cumul_mat, q, fixed_transform, robot_spheres,
+      link_masses_com, joint_map_type, joint_map, link_map, tool_frame_map, link_sphere_map, joint_offset_map,
+      env_query_idx, batch_size, horizon, num_spheres, num_envs, num_links, n_joints, n_tool_frames);
+  return (int)cudaGetLastError();
+}
+
+int ref_kinematics_backward_com(float *grad_out, const float *g_pos, const float *g_quat, const float *g_sph, const float *g_com,
+                                const float *b_com, const float *cumul, const float *robot_spheres, const float *masses,
+                                const int16_t *lmap, const int16_t *jmap, const int8_t *jtype, const int16_t *tool,
+                                const int16_t *sphl, const int16_t *cd, const int16_t *co, const int16_t *jd, const int16_t *jo,
+                                const uint8_t *jae, const float *joff, const int32_t *envq, int num_envs, int batch_size,
+                                int horizon, int n_joints, int num_spheres, int num_links, int n_tool_frames,
+                                cudaStream_t stream) {
+  const int max_threads = 128, tpb = 32;
+  int bpb = 32;
+  const int smem_per = num_links * 12 * 4;
+  if (bpb > 48 * 1024 / smem_per) bpb = 48 * 1024 / smem_per;
+  if (bpb * tpb > max_threads) bpb = max_threads / tpb;
+  if (bpb < 1) bpb = 1;
+  if (bpb > batch_size) bpb = batch_size;
+  const int threads = bpb * tpb;
+  const int blocks = (batch_size * tpb + threads - 1) / threads;
+  const size_t smem = (size_t)bpb * smem_per;
+  const bool *jb = reinterpret_cast<const bool *>(jae);
+  if (n_joints < 16)
+    launch_bwd_com<16>(blocks, threads, smem, stream, grad_out, g_pos, g_quat, g_sph, g_com, b_com, cumul, robot_spheres, masses,
+                       jtype, jmap, lmap, tool, sphl, envq, cd, co, jd, jo, jb, joff, batch_size, horizon, num_spheres, num_links,
+                       n_joints, n_tool_frames, num_envs, tpb);
+  else if (n_joints < 64)
+    launch_bwd_com<64>(blocks, threads, smem, stream, grad_out, g_pos, g_quat, g_sph, g_com, b_com, cumul, robot_spheres, masses,
+                       jtype, jmap, lmap, tool, sphl, envq, cd, co, jd, jo, jb, joff, batch_size, horizon, num_spheres, num_links,
+                       n_joints, n_tool_frames, num_envs, tpb);
+  else
+    launch_bwd_com<128>(blocks, threads, smem, stream, grad_out, g_pos, g_quat, g_sph, g_com, b_com, cumul, robot_spheres, masses,
+                        jtype, jmap, lmap, tool, sphl, envq, cd, co, jd, jo, jb, joff, batch_size, horizon, num_spheres, num_links,
+                        n_joints, n_tool_frames, num_envs, tpb);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

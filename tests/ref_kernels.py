@@ -186,3 +186,38 @@ def pba3d(site_index, m3=2):
     err = lib().ref_pba3d(_p(out), _p(buf), nx, ny, nz, m3, _stream(out.device))
     assert err == 0, err
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# FK with the centre of mass (COMPUTE_COM = true instantiations of the reference kernels)
+# ------------------------------------------------------------------------------------------------
+def fk_forward_com(kp, q, horizon=1):
+    """q [N,D] -> (spheres, cumul, com [N,4]) through kinematics_forward_spheres_kernel<.., COMPUTE_COM=true>."""
+    dev = q.device
+    N = q.shape[0]
+    z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+    pos, quat = z(N, kp.num_pose_links, 3), z(N, kp.num_pose_links, 4)
+    sph, com, cum = z(N, kp.num_spheres, 4), z(N, 4), z(N, kp.num_links, 3, 4)
+    eq = torch.zeros(1, dtype=torch.int32, device=dev)
+    err = lib().ref_kinematics_forward_spheres_com(
+        _p(pos), _p(quat), _p(sph), _p(com), _p(cum), _p(q), _p(kp.fixed_transforms), _p(kp.link_spheres),
+        _p(kp.link_masses_com), _p(kp.joint_map_type), _p(kp.joint_map), _p(kp.link_map), _p(kp.tool_frame_map),
+        _p(kp.link_sphere_idx_map), _p(kp.joint_offset_map), _p(eq), kp.num_envs, N, horizon, kp.num_dof,
+        kp.num_spheres, kp.num_links, kp.num_pose_links, _stream(dev))
+    assert err == 0, err
+    return sph, cum, com
+
+
+def fk_backward_com(kp, cumul, com, g_pos, g_quat, g_sph, g_com, horizon=1):
+    dev = cumul.device
+    N = cumul.shape[0]
+    out = torch.zeros((N, kp.num_dof), dtype=torch.float32, device=dev)
+    eq = torch.zeros(1, dtype=torch.int32, device=dev)
+    err = lib().ref_kinematics_backward_com(
+        _p(out), _p(g_pos), _p(g_quat), _p(g_sph), _p(g_com), _p(com), _p(cumul), _p(kp.link_spheres), _p(kp.link_masses_com),
+        _p(kp.link_map), _p(kp.joint_map), _p(kp.joint_map_type), _p(kp.tool_frame_map), _p(kp.link_sphere_idx_map),
+        _p(kp.link_chain_data), _p(kp.link_chain_offsets), _p(kp.joint_links_data), _p(kp.joint_links_offsets),
+        _p(kp.joint_affects_endeffector), _p(kp.joint_offset_map), _p(eq), kp.num_envs, N, horizon, kp.num_dof, kp.num_spheres,
+        kp.num_links, kp.num_pose_links, _stream(dev))
+    assert err == 0, err
+    return out
