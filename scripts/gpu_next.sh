@@ -7,7 +7,7 @@
 #   3. timings: EDT vs the reference's PBA+ kernels, RNEA, the dynamics-aware MPC workloads (bench.py extras),
 #   4. one ncu --set full capture per new kernel family.
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_gpu_zw_center_of_mass.py tests/test_gpu_zx_dynamics_trees.py tests/test_gpu_zy_effort_cost.py tests/test_gpu_zz_edt.py -m gpu -q -p no:cacheprovider) > gpurun_out/new_rows_tests.log 2>&1
+(timeout 900 python -m pytest tests/test_gpu_zx_dynamics_trees.py tests/test_gpu_zy_effort_cost.py tests/test_gpu_zz_edt.py tests/test_gpu_zzz_center_of_mass.py -m gpu -q -p no:cacheprovider) > gpurun_out/new_rows_tests.log 2>&1
 (timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_zy_effort_cost.py -m gpu -q -p no:cacheprovider -k "dynamics_aware") > gpurun_out/dyn_memcheck.log 2>&1
 (timeout 300 compute-sanitizer --tool memcheck python scripts/bench_edt.py 64 --no-ref) > gpurun_out/edt_memcheck.log 2>&1
 (timeout 300 python scripts/bench_edt.py 128 256) > gpurun_out/edt_bench.jsonl 2>&1

@@ -285,4 +285,4 @@ def test_pending_dynamics_aware_knots(run):
 
 @pytest.mark.parametrize("robot,n", [("franka", 33), ("g1_29", 9)])
 def test_pending_center_of_mass(run, robot, n):
-    run("test_gpu_zw_center_of_mass", "test_center_of_mass_and_its_gradient", robot, n)
+    run("test_gpu_zzz_center_of_mass", "test_center_of_mass_and_its_gradient", robot, n)
