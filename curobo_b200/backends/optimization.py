@@ -90,6 +90,7 @@ def launch_lbfgs_step(
     search_magnitudes: Optional[torch.Tensor] = None,
     action_step_max: Optional[torch.Tensor] = None,
     fix_terminal_action: bool = False,
+    action_dim: int = 0,
 ) -> List[torch.Tensor]:
     """L-BFGS two-loop step + history roll, in place.  Returns [step_vec, rho_buffer, y_buffer, s_buffer, x_0, grad_0]
     like the reference.  `use_shared_buffers` is accepted for signature parity (the history is always staged on
@@ -111,6 +112,10 @@ def launch_lbfgs_step(
         if action_step_max is not None:
             check_tensors(dev, torch.float32, action_step_max=action_step_max)
             adim = int(action_step_max.numel())
+        if action_dim > 0:   # explicit: the terminal action is frozen whether or not the step is clamped
+            if action_step_max is not None and int(action_step_max.numel()) != int(action_dim):
+                raise ValueError("action_step_max must have action_dim entries")
+            adim = int(action_dim)
     L = _lib.load()
     p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
     err = L.cb200_lbfgs_step(

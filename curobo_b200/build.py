@@ -51,13 +51,47 @@ def _run(cmd, verbose):
         print(r.stdout + r.stderr)
 
 
+def _digest(paths) -> str:
+    """Content hash of the sources: unlike mtimes it survives the copy onto the GPU box unchanged."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def build_product(force: bool = False, verbose: bool = False, minb: int = 0) -> str:
-    """minb > 0 builds a tuning variant libcurobo_b200_mb<minb>.so (register cap = 65536 / (256 * minb))."""
+    """minb > 0 builds a tuning variant libcurobo_b200_mb<minb>.so (register cap = 65536 / (256 * minb)).
+    Up to date <=> the stamp next to the library holds the content hash of the sources (so an edited csrc/ never runs
+    a stale binary, and a fresh copy of the tree with new mtimes does not rebuild)."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "curobo_b200.h")]
     out = PRODUCT_SO if minb <= 0 else PRODUCT_SO.replace(".so", f"_mb{minb}.so")
-    if not force and _newer(out, srcs):
+    stamp = out + ".stamp"
+    digest = _digest(srcs)
+
+    def fresh() -> bool:
+        if not os.path.exists(out) or not os.path.exists(stamp):
+            return False
+        with open(stamp) as f:
+            return f.read().strip() == digest
+    if not force and fresh():
         return out
     os.makedirs(LIBDIR, exist_ok=True)
+    import fcntl
+    lock = open(os.path.join(LIBDIR, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)          # several ranks may start at once: one builds, the others wait and re-check
+    try:
+        if not force and fresh():
+            return out
+        return _build_product_locked(out, stamp, digest, verbose, minb)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_product_locked(out: str, stamp: str, digest: str, verbose: bool, minb: int) -> str:
     cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", *ARCH, *NUMERIC, "-Xcompiler", "-fPIC", "-shared",
            "-Xptxas", "-v" if verbose else "-O3", *([f"-DCB200_MINB={minb}"] if minb > 0 else []),
            "-o", out, "-lcudart"]
@@ -73,7 +107,11 @@ def build_product(force: bool = False, verbose: bool = False, minb: int = 0) -> 
     if any(p.returncode != 0 for p in procs):
         sys.stderr.write("\n".join(logs))
         raise RuntimeError("build failed: nvcc -c " + " ".join(units))
-    _run([cmd[0], *ARCH, "-shared", "-Xcompiler", "-fPIC", *objs, "-o", out, "-lcudart"], verbose)
+    tmp = out + ".tmp"
+    _run([cmd[0], *ARCH, "-shared", "-Xcompiler", "-fPIC", *objs, "-o", tmp, "-lcudart"], verbose)
+    os.replace(tmp, out)
+    with open(stamp, "w") as f:
+        f.write(digest)
     for o in objs:
         os.remove(o)
     return out

@@ -52,7 +52,8 @@ struct BlobHeader {
   int32_t off_fk_sched;     // uint32[2*n_fk_steps]  per (step, slot): byte offset of the link's 3x4 (lo16, 0xFFFF = idle) | parent's (hi16)
   int32_t off_cl_bound_scene;  // float4[n_cl]  like cl_bound but over spheres with r >= 0 and unpadded radii (scene broad phase)
   int32_t off_sph_cl;       // uint8 [S]  collision-link index of each sphere (valid when n_lp > 0)
-  int32_t reserved[11];
+  int32_t n_sphere_cfgs;    // link-sphere configurations the broad-phase bounds cover (>= 1); config 0 is the staged set
+  int32_t reserved[10];
 };
 static_assert(sizeof(BlobHeader) == 192, "BlobHeader must be 192 bytes");
 

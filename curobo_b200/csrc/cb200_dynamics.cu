@@ -485,6 +485,7 @@ int cb200_rnea_forward(float *tau, const float *q, const float *qd, const float 
                        const int16_t *joint_map, const int16_t *link_map, const float *joint_offset_map,
                        const float *gravity, const int16_t *level_starts, const int16_t *level_links, float *forward_cache,
                        int batch_size, int num_links, int num_dof, int n_levels, const float *f_ext, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(tau);
   Model M{fixed_transforms, link_masses_com, link_inertias, joint_map_type, joint_map, link_map, joint_offset_map, gravity,
           level_starts,     level_links,     num_links,     num_dof,        n_levels};
   if (!model_ok(M) || tau == nullptr || q == nullptr || qd == nullptr || qdd == nullptr || forward_cache == nullptr ||
@@ -519,6 +520,7 @@ int cb200_rnea_backward(float *grad_q, float *grad_qd, float *grad_qdd, const fl
                         const int16_t *link_map, const float *joint_offset_map, const float *gravity,
                         const int16_t *level_starts, const int16_t *level_links, const float *forward_cache, int batch_size,
                         int num_links, int num_dof, int n_levels, float *grad_f_ext, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(grad_q);
   Model M{fixed_transforms, link_masses_com, link_inertias, joint_map_type, joint_map, link_map, joint_offset_map, gravity,
           level_starts,     level_links,     num_links,     num_dof,        n_levels};
   if (!model_ok(M) || grad_q == nullptr || grad_qd == nullptr || grad_qdd == nullptr || grad_tau == nullptr || q == nullptr ||

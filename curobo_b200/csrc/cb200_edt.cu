@@ -85,6 +85,7 @@ bool dims_ok(int nx, int ny, int nz) {
 extern "C" {
 
 int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, int m3, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(site_index);
   (void)buffer;  // the reference's ping-pong scratch: every pass here is in place
   (void)m3;      // the reference's colour-kernel block height
   if (site_index == nullptr || !dims_ok(nx, ny, nz)) return status(cudaErrorInvalidValue);
@@ -103,6 +104,7 @@ int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, in
 
 int cb200_edt_unsigned_distance(const int32_t *site_index, uint16_t *distance_fp16, int nx, int ny, int nz, float voxel_size,
                                 float empty_value, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(distance_fp16);
   if (site_index == nullptr || distance_fp16 == nullptr || !dims_ok(nx, ny, nz) || !(voxel_size > 0.0f))
     return status(cudaErrorInvalidValue);
   const long long total = (long long)nx * ny * nz;

@@ -66,7 +66,45 @@ struct FusedArgs {
   struct Dyn {
     const float *masses_com, *inertias, *gravity;
   } dyn;
+  // c-space target term (a14): target rows [n, D], row index per seed (null = row 0), per-dof weight (null = 1)
+  const float *cs_target;
+  const int32_t *cs_target_idx;
+  const float *cs_target_dofw;
+  // link-sphere configurations (a2, num_envs > 1): [n_cfg, S] float4 in global memory; null = the blob's set
+  const float4 *sphere_cfgs;
+  int32_t n_sphere_cfgs;
 };
+
+// link-frame sphere set of seed b: the blob's (shared memory) unless the caller passed several configurations
+__device__ __forceinline__ const float4 *row_sphere_cfg(const FusedArgs &a, int b, int S) {
+  if (a.sphere_cfgs == nullptr) return nullptr;
+  int cfg = a.env_query_idx != nullptr ? __ldg(a.env_query_idx + b) : 0;
+  if (cfg < 0 || cfg >= a.n_sphere_cfgs) cfg = 0;
+  return a.sphere_cfgs + (size_t)cfg * S;
+}
+
+// c-space target term for one dof (wp_cspace_state.py:84-89,220-226; wp_cspace_position.py target block).
+// STATE: the weight is tested before the per-dof factor is applied and non-terminal waypoints scale it;
+// POSITION: the product weight * dof weight is tested.
+__device__ __forceinline__ void cspace_target_term(const FusedArgs &a, int b, int h, int d, int D, float x, float &cost,
+                                                   float &gp) {
+  const cb200_rollout_cfg &c = a.cfg;
+  if (a.cs_target == nullptr) return;
+  float tw = c.cspace_target_weight;
+  const float dofw = a.cs_target_dofw != nullptr ? __ldg(a.cs_target_dofw + d) : 1.0f;
+  if (c.cspace_type == 2) {
+    if (h < a.H - 1) tw *= c.cspace_non_terminal_weight_factor;
+    if (!(tw > 0.0f)) return;
+    tw *= dofw;
+  } else {
+    tw *= dofw;
+    if (!(tw > 0.0f)) return;
+  }
+  const int row = a.cs_target_idx != nullptr ? __ldg(a.cs_target_idx + b) : 0;
+  const float err = x - __ldg(a.cs_target + (size_t)row * D + d);
+  cost += tw * err * err;
+  gp += 2.0f * tw * err;
+}
 
 // State (q, qd, qdd, qddd) of row (b, h), dof d.  Spline mode evaluates the knots in place (one out-of-line copy
 // for the three degrees); otherwise the caller's [B,H,D] arrays are read.
@@ -112,7 +150,7 @@ __device__ __forceinline__ float seed_dt(const FusedArgs &a, int b) {
 }
 
 // c-space cost for one dof; returns cost, writes gradient wrt position into gp (and v/a/j grads to global)
-__device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView &rv, int e, int b, int d,
+__device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView &rv, int e, int b, int h, int d,
                                             const bspline::State4 &st, float &gp) {
   const float qd = st.p;
   const cb200_rollout_cfg &c = a.cfg;
@@ -122,6 +160,7 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
   gp = 0.0f;
   if (c.cspace_type == 1) {
     bound_cost(qd, lim[d], lim[D + d], c.cspace_activation[0], c.cspace_weight[0], cost, gp);
+    cspace_target_term(a, b, h, d, D, qd, cost, gp);
   } else if (c.cspace_type == 2) {
     const size_t idx = (size_t)e * D + d;
     const float dt = seed_dt(a, b);
@@ -152,6 +191,7 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
     bound_cost(ac, lim[4 * D + d], lim[5 * D + d], c.cspace_activation[2], wb[2], cost, ga);
     bound_cost(jk, lim[6 * D + d], lim[7 * D + d], c.cspace_activation[3], wb[3], cost, gj);
     // effort = 0 in this path: bound/regularisation/energy terms on torque vanish
+    cspace_target_term(a, b, h, d, D, qd, cost, gp);
     l2_reg(v, wr[0], cost, gv);
     l2_reg(ac, wr[1], cost, ga);
     l2_reg(jk, wr[2], cost, gj);
@@ -189,7 +229,7 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
     const bspline::State4 st = load_row_state<SPLINE>(a, e, b, h, d, D);
     es.qv[d] = st.p;
     float gp;
-    const float c = cspace_dof(a, rv, e, b, d, st, gp);
+    const float c = cspace_dof(a, rv, e, b, h, d, st, gp);
     es.gqv[d] = gp;
     cs_cost += c;
     if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
@@ -248,7 +288,8 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
     __syncwarp();
   }
   warp_fk(rv, es, lane);
-  warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr);
+  warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr,
+               row_sphere_cfg(a, b, S));
   pose_c = 0.0f;
   const bool do_pose = (a.goal_position != nullptr);
   #pragma unroll 1
@@ -544,9 +585,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
         es.qv[d] = SPLINE ? spline_row_state(a.spl, b, hh, d, D).p : __ldg(a.q + eh * D + d);
       __syncwarp();
       warp_fk(rv, es, lane);
+      const float4 *cfg_sph = row_sphere_cfg(a, b, S);
       for (int s = lane; s < S; s += 32) {
         const float *T = es.cumul + 12 * rv.sph_link[s];
-        const float4 p = rv.spheres[s];
+        const float4 p = cfg_sph != nullptr ? __ldg(cfg_sph + s) : rv.spheres[s];
         hdst[s] = make_float4(T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3], T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7],
                               T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11], p.w);
       }
@@ -664,7 +706,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) rollout_tile_kernel(cons
         const bspline::State4 st = load_row_state<false>(a, e1, b, h, d, D);
         qs[d * T + t] = st.p;
         float gp;
-        const float c = cspace_dof(a, rv, e1, b, d, st, gp);
+        const float c = cspace_dof(a, rv, e1, b, h, d, st, gp);
         gqs[d * T + t] = gp;
         cs_cost += c;
         if (a.cspace_cost) a.cspace_cost[(size_t)e1 * D + d] = c;
@@ -946,7 +988,7 @@ __global__ void __launch_bounds__(kLaneThreads, 4) rollout_lane_kernel(const __g
       const bspline::State4 st = load_row_state<false>(a, e, b, h, d, D);
       qs[d * T] = st.p;
       float gp;
-      const float c = cspace_dof(a, rv, e, b, d, st, gp);
+      const float c = cspace_dof(a, rv, e, b, h, d, st, gp);
       gqs[d * T] = gp;
       cs_cost += c;
       if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
@@ -1707,19 +1749,23 @@ inline int ret(cudaError_t e) {
 }
 inline int launch_status() { return ret(cudaGetLastError()); }
 
+// Properties of the CURRENT device (the host layer makes the tensors' device current around every call), cached per
+// ordinal: one process may drive several GPUs, and cudaFuncSetAttribute / occupancy results are per device.
 struct DevInfo {
-  int sm_count = 0, max_smem = 0;
+  int sm_count = 0, max_smem = 0, ordinal = 0;
   bool ok = false;
 };
+constexpr int kMaxDevices = 64;
 DevInfo &dev_info() {
-  static thread_local DevInfo d;
+  static thread_local DevInfo table[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  DevInfo &d = table[dev];
   if (!d.ok) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) {
-      cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
-      cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-      d.ok = d.sm_count > 0;
-    }
+    d.ordinal = dev;
+    cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    d.ok = d.sm_count > 0;
   }
   return d;
 }
@@ -1790,30 +1836,41 @@ inline void align16(std::vector<unsigned char> &buf) {
 // Badoiu-Clarkson iterations from the centroid (move the centre 1/(k+1) of the way towards the farthest ball), then
 // R = max(|p - c| + r) exactly for the final centre, inflated against fp32 rounding of the world transform.
 // out = (cx, cy, cz, R); R = -1 when no sphere is enabled.  A tighter ball only prunes more; it is never unsafe.
-static void bounding_ball(const float *link_spheres, const float *padding, int s_begin, int s_end, float *out) {
-  double c[3] = {0, 0, 0};
-  int n = 0;
-  auto rad = [&](int s) { return (double)link_spheres[4 * s + 3] + (padding ? (double)padding[s] : 0.0); };
-  for (int s = s_begin; s < s_end; ++s) {
-    if (rad(s) < 0) continue;
-    for (int k = 0; k < 3; ++k) c[k] += link_spheres[4 * s + k];
-    ++n;
+static void bounding_ball(const float *link_spheres, const float *padding, int s_begin, int s_end, float *out, int n_cfg = 1,
+                          int S = 0) {
+  // the balls of every configuration of spheres [s_begin, s_end): (centre, radius) with radius >= 0
+  std::vector<double> bx, by, bz, br;
+  for (int c = 0; c < (n_cfg < 1 ? 1 : n_cfg); ++c) {
+    const float *ls = link_spheres + (size_t)c * S * 4;
+    for (int s = s_begin; s < s_end; ++s) {
+      const double r = (double)ls[4 * s + 3] + (padding ? (double)padding[s] : 0.0);
+      if (r < 0) continue;
+      bx.push_back(ls[4 * s]);
+      by.push_back(ls[4 * s + 1]);
+      bz.push_back(ls[4 * s + 2]);
+      br.push_back(r);
+    }
   }
+  const int n = (int)bx.size();
+  double c[3] = {0, 0, 0};
   out[0] = out[1] = out[2] = 0.0f;
   out[3] = -1.0f;
   if (n == 0) return;
+  for (int i = 0; i < n; ++i) {
+    c[0] += bx[i];
+    c[1] += by[i];
+    c[2] += bz[i];
+  }
   for (int k = 0; k < 3; ++k) c[k] /= n;
   auto farthest = [&](const double *cc, int &arg) {
     double best = -1;
     arg = -1;
-    for (int s = s_begin; s < s_end; ++s) {
-      const double r = rad(s);
-      if (r < 0) continue;
-      const double dx = link_spheres[4 * s] - cc[0], dy = link_spheres[4 * s + 1] - cc[1], dz = link_spheres[4 * s + 2] - cc[2];
-      const double d = std::sqrt(dx * dx + dy * dy + dz * dz) + r;
+    for (int i = 0; i < n; ++i) {
+      const double dx = bx[i] - cc[0], dy = by[i] - cc[1], dz = bz[i] - cc[2];
+      const double d = std::sqrt(dx * dx + dy * dy + dz * dz) + br[i];
       if (d > best) {
         best = d;
-        arg = s;
+        arg = i;
       }
     }
     return best;
@@ -1826,13 +1883,11 @@ static void bounding_ball(const float *link_spheres, const float *padding, int s
       best_R = R;
       for (int k = 0; k < 3; ++k) best_c[k] = c[k];
     }
-    // step towards the farthest ball's far point
-    const double dx = link_spheres[4 * arg] - c[0], dy = link_spheres[4 * arg + 1] - c[1], dz = link_spheres[4 * arg + 2] - c[2];
+    // step towards the farthest ball's centre, 1/(it+1) of the current radius, never past the centre
+    const double dx = bx[arg] - c[0], dy = by[arg] - c[1], dz = bz[arg] - c[2];
     const double d = std::sqrt(dx * dx + dy * dy + dz * dz);
     if (d < 1e-12) break;
-    const double step = (R - 0.0) / (it + 1.0) / d * (d > 0 ? 1.0 : 0.0);
-    const double lim = d;  // never overshoot the sphere centre
-    const double mv = std::min(step * d, lim) / d;
+    const double mv = std::min(R / (it + 1.0), d) / d;
     c[0] += dx * mv;
     c[1] += dy * mv;
     c[2] += dz * mv;
@@ -1868,6 +1923,7 @@ int cb200_kinematics_forward_spheres(float *link_pos, float *link_quat, float *b
                                      const int32_t *env_query_idx, int num_envs, int batch_size, int horizon,
                                      int n_joints, int num_spheres, int num_links, int n_tool_frames,
                                      int write_global_cumul, int compute_com, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(joint_vec);
   if (batch_size < 0 || num_links < 1 || horizon < 1) return ret(cudaErrorInvalidValue);
   if (compute_com != 0 && (batch_center_of_mass == nullptr || link_masses_com == nullptr)) return ret(cudaErrorInvalidValue);
   if (batch_size == 0) return ret(cudaSuccess);
@@ -1898,6 +1954,7 @@ int cb200_kinematics_backward(float *grad_out, const float *grad_nlinks_pos, con
                               const int32_t *env_query_idx, int num_envs, int batch_size, int horizon, int n_joints,
                               int num_spheres, int num_links, int n_tool_frames, int compute_com,
                               int compute_jacobian_grad, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(grad_out);
   (void)grad_jacobian;
   (void)link_chain_data;
   (void)link_chain_offsets;
@@ -1930,6 +1987,7 @@ int cb200_self_collision_distance(float *out_distance, float *out_vec, float *pa
                                   int16_t *block_batch_max_index, int num_blocks_per_batch, int max_threads_per_block,
                                   int batch_size, int horizon, int nspheres, int num_collision_pairs,
                                   int store_pair_distance, int compute_grad, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(out_distance);
   (void)block_batch_max_value;
   (void)block_batch_max_index;
   (void)num_blocks_per_batch;
@@ -1959,6 +2017,7 @@ static int scene_launch(float *distance, float *gradient, const float *spheres, 
                         const cb200_voxel_set *voxels, const float *weight, const float *eta, const float *speed_dt,
                         int speed_metric, const int32_t *env_query_idx, int B, int H, int S, int use_multi_env, int sweep,
                         cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(distance);
   const long long total = (long long)B * H * S;
   if (total == 0) return ret(cudaSuccess);
   if (total < 0 || (speed_metric && speed_dt == nullptr)) return ret(cudaErrorInvalidValue);
@@ -1995,6 +2054,7 @@ int cb200_tool_pose_distance(float *out_distance, float *out_position_distance, 
                              const float *terminal_pose_convergence_tolerance,
                              const float *non_terminal_pose_convergence_tolerance, int batch_size, int horizon,
                              int num_links, int num_goalset, int rotation_method, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(out_distance);
   const int total = batch_size * horizon * num_links;
   if (total == 0) return ret(cudaSuccess);
   if (total < 0 || num_goalset < 1 || rotation_method < 0 || rotation_method > 1) return ret(cudaErrorInvalidValue);
@@ -2018,6 +2078,7 @@ int cb200_cspace_state_cost(float *out_cost, float *out_grad_p, float *out_grad_
                             const float *cspace_non_terminal_weight_factor, const float *cspace_target_dof_weight,
                             int write_grad, int batch_size, int horizon, int dof, int retime_weights,
                             int retime_regularization_weights, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(out_cost);
   const int total = batch_size * horizon * dof;
   if (total == 0) return ret(cudaSuccess);
   if (total < 0) return ret(cudaErrorInvalidValue);
@@ -2039,6 +2100,7 @@ int cb200_cspace_position_cost(float *out_cost, float *out_grad_p, float *out_gr
                                const float *current_position, const float *current_velocity,
                                const int32_t *idxs_current_state, const float *v_b, const float *state_dt,
                                int write_grad, int batch_size, int horizon, int dof, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(out_cost);
   const int total = batch_size * horizon * dof;
   if (total == 0) return ret(cudaSuccess);
   if (total < 0) return ret(cudaErrorInvalidValue);
@@ -2130,6 +2192,7 @@ int64_t cb200_voxel_mip_stride(const float *host_params, int num_layers) {
 }
 
 int cb200_voxel_build_mip(const cb200_voxel_set *vs, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD((vs != nullptr ? vs->mip : nullptr));
   if (vs == nullptr || vs->mip == nullptr || vs->mip_stride < 1 || vs->features == nullptr || vs->params == nullptr ||
       vs->max_n < 1 || vs->num_envs < 1)
     return ret(cudaErrorInvalidValue);
@@ -2157,6 +2220,8 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
   if (total < 0) return total;
   if (out_bytes < total) return -3;
   const int nl = h.nl, D = h.D, S = h.S, L = h.L, P = h.P;
+  const int n_cfg = sz->num_sphere_configs > 1 ? sz->num_sphere_configs : 1;  // link_spheres is [n_cfg, S, 4]
+  h.n_sphere_cfgs = n_cfg;
   unsigned char *o = static_cast<unsigned char *>(out);
   memset(o, 0, (size_t)total);
   memcpy(o, &h, sizeof(h));
@@ -2287,9 +2352,9 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
         cll[a] = (int16_t)cl_link[a];
         cls[a] = (int16_t)cl_start[a];
         // bounding spheres of the enabled sphere balls: padded radii for self collision, raw radii for the scene
-        bounding_ball(link_spheres, sphere_padding, cl_start[a], cl_start[a + 1], clb + 4 * a);
+        bounding_ball(link_spheres, sphere_padding, cl_start[a], cl_start[a + 1], clb + 4 * a, n_cfg, S);
         bounding_ball(link_spheres, nullptr, cl_start[a], cl_start[a + 1],
-                      reinterpret_cast<float *>(o + h.off_cl_bound_scene) + 4 * a);
+                      reinterpret_cast<float *>(o + h.off_cl_bound_scene) + 4 * a, n_cfg, S);
       }
       cls[n_cl] = (int16_t)S;
       memcpy(o + h.off_lp, lps.data(), lps.size() * 4);
@@ -2300,6 +2365,7 @@ int64_t cb200_pack_robot_blob(void *out, int64_t out_bytes, const cb200_robot_si
 }
 
 int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD((io != nullptr ? io->cost : nullptr));
   if (cfg == nullptr || io == nullptr || io->robot_blob == nullptr || io->cost == nullptr || io->grad_q == nullptr ||
       io->batch_size < 0 || io->horizon < 1)
     return ret(cudaErrorInvalidValue);
@@ -2360,6 +2426,18 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   a.pose_goalset_idx = io->pose_goalset_idx;
   a.B = io->batch_size;
   a.H = io->horizon;
+  if (cfg->cspace_target_weight > 0.0f && cfg->cspace_type != 0) {
+    if (io->cspace_target == nullptr) return ret(cudaErrorInvalidValue);
+    a.cs_target = io->cspace_target;
+    a.cs_target_idx = io->idxs_cspace_target;
+    a.cs_target_dofw = io->cspace_target_dof_weight;
+  }
+  if (io->sphere_configs != nullptr && io->num_sphere_configs > 1) {
+    // the broad-phase bounds in the blob must cover every configuration
+    if (h.n_sphere_cfgs != io->num_sphere_configs) return ret(cudaErrorInvalidValue);
+    a.sphere_cfgs = reinterpret_cast<const float4 *>(io->sphere_configs);
+    a.n_sphere_cfgs = io->num_sphere_configs;
+  }
   a.blob_smem_bytes = h.smem_bytes;
   a.eval_floats = eval_smem_floats(h.nl, h.D, h.S, h.L, h.n_cl);
   static const int phase_sync_env = []() {
@@ -2425,21 +2503,22 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     const char *e = getenv("CB200_LANE");
     return e ? atoi(e) : 0;  // off by default: measured 2.3x slower than warp-per-row (profiles/r01_c)
   }();
-  if (!traj && lane_env != 0 && h.nl <= 24 && h.S <= 128 && a.spl.knots == nullptr) {
+  if (!traj && lane_env != 0 && h.nl <= 24 && h.S <= 128 && a.spl.knots == nullptr && a.sphere_cfgs == nullptr) {
     static KernelT const lane_table[4] = {rollout_lane_kernel<0>, rollout_lane_kernel<1>, rollout_lane_kernel<2>,
                                           rollout_lane_kernel<3>};
     const LaneLayout ll = lane_layout(h.smem_bytes, kLaneThreads, h.nl, h.D, h.n_cl);
     KernelT lk = lane_table[scene];
     static thread_local size_t lane_cfg[4] = {0, 0, 0, 0};
     static thread_local int lane_per_sm[4] = {0, 0, 0, 0};
-    if (lane_cfg[scene] != ll.total_bytes) {
+    const size_t lane_key = ll.total_bytes ^ ((size_t)(d.ordinal + 1) << 48);
+    if (lane_cfg[scene] != lane_key) {
       int per_sm = 0;
       if (cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll.total_bytes) == cudaSuccess)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk, kLaneThreads, ll.total_bytes);
       else
         (void)cudaGetLastError();
       lane_per_sm[scene] = per_sm;
-      lane_cfg[scene] = ll.total_bytes;
+      lane_cfg[scene] = lane_key;
     }
     if (lane_per_sm[scene] >= 2) {
       const long long need = (N + kLaneThreads - 1) / kLaneThreads;
@@ -2454,13 +2533,14 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     const char *e = getenv("CB200_TILE");
     return e ? atoi(e) : 0;
   }();
-  if (!traj && tile_env != 0 && a.spl.knots == nullptr) {
+  if (!traj && tile_env != 0 && a.spl.knots == nullptr && a.sphere_cfgs == nullptr) {
     const TileLayout tl = tile_layout(h.smem_bytes, kWarpsPerCta, h.nl, h.D, h.S, h.L, h.n_cl);
     KernelT tk = table[2][scene];
     static thread_local size_t tile_cfg[4] = {0, 0, 0, 0};
     static thread_local int tile_per_sm[4] = {0, 0, 0, 0};
     cudaFuncAttributes fa;
-    if (tile_cfg[scene] != tl.total_bytes) {
+    const size_t tile_key = tl.total_bytes ^ ((size_t)(d.ordinal + 1) << 48);
+    if (tile_cfg[scene] != tile_key) {
       if (cudaFuncGetAttributes(&fa, tk) == cudaSuccess && 2 * (tl.total_bytes + fa.sharedSizeBytes + 1024) <= (size_t)d.max_smem + 4096 &&
           cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.total_bytes) == cudaSuccess) {
         int per_sm = 0;
@@ -2470,7 +2550,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
         tile_per_sm[scene] = 0;
         (void)cudaGetLastError();
       }
-      tile_cfg[scene] = tl.total_bytes;
+      tile_cfg[scene] = tile_key;
     }
     if (tile_per_sm[scene] >= 2) {
       const long long n_tiles = (N + tl.T - 1) / tl.T;
@@ -2511,7 +2591,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   Plan &pl = plans[variant][scene];
   const size_t halo_bytes = traj ? (size_t)2 * h.S * sizeof(float4) : 0;
   const long long key = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ (long long)minb ^
-                        (traj ? ((long long)io->horizon << 40) : 0);
+                        (traj ? ((long long)io->horizon << 40) : 0) ^ ((long long)(d.ordinal + 1) << 56);
   if (key != pl.key) {
     cudaFuncAttributes fa;
     cudaError_t e0 = cudaFuncGetAttributes(&fa, kern);

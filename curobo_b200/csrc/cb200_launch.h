@@ -14,3 +14,36 @@
 #else
 #define CB200_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) kernel<<<(grid), (block), (smem_bytes), (stream)>>>(__VA_ARGS__)
 #endif
+
+// Every launching entry point runs on the device that OWNS its output buffer, whatever the caller's current device is:
+// occupancy queries, cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the launch itself are per device, and the host
+// layer passes raw pointers + the tensor's stream without entering a device context.  CB200_DEVICE_GUARD(ptr) looks the
+// pointer's device up (cudaPointerGetAttributes: no synchronisation, legal during graph capture), switches to it when it
+// differs from the current one and switches back on scope exit.
+#ifdef CB200_SIMT_EMULATION
+#define CB200_DEVICE_GUARD(ptr) (void)(ptr)
+#else
+namespace cb200 {
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const void *p) {
+    if (p == nullptr) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return;
+    }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    if (prev != at.device && cudaSetDevice(at.device) == cudaSuccess) switched = true;
+  }
+  ~DeviceGuard() {
+    if (switched) (void)cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+}  // namespace cb200
+#define CB200_DEVICE_GUARD(ptr) ::cb200::DeviceGuard cb200_device_guard_(ptr)
+#endif

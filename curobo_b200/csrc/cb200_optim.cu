@@ -459,6 +459,7 @@ int cb200_lbfgs_step(float *step_vec, float *rho_buffer, float *y_buffer, float 
                      const float *grad_q, float *x_0, float *grad_0, float epsilon, int batch_size, int history_m,
                      int v_dim, int stable_mode, float *x_set, float *step_scaled, const float *search_magnitudes, int n_linesearch,
                      const float *action_step_max, int action_dim, int fix_terminal_action, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(step_vec);
   // argument checks of the reference launcher (cuda_core_backend/optimization.py:173-176; lbfgs.py:171-173)
   if (step_vec == nullptr || rho_buffer == nullptr || y_buffer == nullptr || s_buffer == nullptr || q == nullptr ||
       grad_q == nullptr || x_0 == nullptr || grad_0 == nullptr || batch_size < 0 || v_dim < 1 || v_dim > 1024 ||
@@ -489,6 +490,7 @@ int cb200_line_search(float *best_cost, float *best_action, int16_t *best_iterat
                       const float *search_magnitudes, float armijo_threshold_c_1, float curvature_threshold_c_2,
                       int strong_wolfe, int approx_wolfe, int n_linesearch, int opt_dim, int batchsize,
                       cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(best_cost);
   if (best_cost == nullptr || best_action == nullptr || best_iteration == nullptr || current_iteration == nullptr ||
       converged_global == nullptr || exploration_cost == nullptr || exploration_action == nullptr ||
       exploration_gradient == nullptr || exploration_idx == nullptr || selected_cost == nullptr ||

@@ -126,6 +126,7 @@ int cb200_bspline_forward(float *out_position, float *out_velocity, float *out_a
                           const int32_t *start_idx, const int32_t *goal_idx, const float *traj_dt,
                           const uint8_t *use_implicit_goal_state, int batch_size, int padded_horizon, int dof, int n_knots,
                           int bspline_degree, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(out_position);
   FwdArgs a{out_position, out_velocity, out_acceleration, out_jerk, out_dt, u_position, start_position, start_velocity,
             start_acceleration, start_jerk, goal_position, goal_velocity, goal_acceleration, goal_jerk, start_idx, goal_idx,
             traj_dt, use_implicit_goal_state, nullptr, batch_size, padded_horizon, dof, n_knots};
@@ -140,6 +141,7 @@ int cb200_bspline_single_dt(float *out_position, float *out_velocity, float *out
                             const float *interpolation_dt, const uint8_t *use_implicit_goal_state,
                             const int32_t *interpolation_horizon, int batch_size, int max_out_tsteps, int dof, int n_knots,
                             int bspline_degree, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(out_position);
   (void)knot_dt;  // carried by the reference signature, never read by its kernel (bspline_kernel.cuh:216-270)
   if (interpolation_horizon == nullptr) return status(cudaErrorInvalidValue);
   FwdArgs a{out_position, out_velocity, out_acceleration, out_jerk, out_dt, u_position, start_position, start_velocity,
@@ -152,6 +154,7 @@ int cb200_bspline_backward(float *out_grad_knots, const float *grad_position, co
                            const float *grad_acceleration, const float *grad_jerk, const float *traj_dt,
                            const int32_t *dt_idx, const uint8_t *use_implicit_goal_state, int batch_size, int padded_horizon,
                            int dof, int n_knots, int bspline_degree, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(out_grad_knots);
   const int horizon = padded_horizon - 1;
   // same argument checks as the reference launcher (trajectory_kernel_launch.cu:592-627)
   if (batch_size <= 0 || dof <= 0 || n_knots <= 0 || horizon < 5) return status(cudaErrorInvalidValue);

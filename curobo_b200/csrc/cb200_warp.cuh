@@ -167,11 +167,14 @@ __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es,
 
 // Spheres: world position of every robot sphere; also the self-collision (padded radius) copy in gsph.
 // Reference: kinematics_forward_helper.cuh:218-254, kinematics_util.cuh:39-49.
-__device__ __forceinline__ void warp_spheres(const RobotView &rv, const EvalSmem &es, int lane, float4 *out_global) {
+// `cfg_spheres` != nullptr: the row's link-sphere configuration in global memory (num_envs > 1,
+// kinematics_forward_helper.cuh:232-233) instead of the blob's set.
+__device__ __forceinline__ void warp_spheres(const RobotView &rv, const EvalSmem &es, int lane, float4 *out_global,
+                                             const float4 *cfg_spheres = nullptr) {
   #pragma unroll 1
   for (int s = lane; s < rv.S; s += 32) {
     const float *T = es.cumul + 12 * rv.sph_link[s];
-    const float4 p = rv.spheres[s];
+    const float4 p = cfg_spheres != nullptr ? __ldg(cfg_spheres + s) : rv.spheres[s];
     const float4 r0 = *reinterpret_cast<const float4 *>(T), r1 = *reinterpret_cast<const float4 *>(T + 4),
                  r2 = *reinterpret_cast<const float4 *>(T + 8);
     float4 w;

@@ -28,7 +28,7 @@ class VoxelSet(C.Structure):
 
 class RobotSizes(C.Structure):
     _fields_ = [("num_links", C.c_int32), ("num_dof", C.c_int32), ("num_spheres", C.c_int32),
-                ("num_tool_frames", C.c_int32), ("num_pairs", C.c_int32)]
+                ("num_tool_frames", C.c_int32), ("num_pairs", C.c_int32), ("num_sphere_configs", C.c_int32)]
 
 
 class RolloutCfg(C.Structure):
@@ -36,7 +36,8 @@ class RolloutCfg(C.Structure):
                 ("use_sweep", C.c_int32), ("use_speed_metric", C.c_int32), ("pose_weight", C.c_float * 2),
                 ("pose_rotation_method", C.c_int32), ("cspace_type", C.c_int32), ("cspace_weight", C.c_float * 5),
                 ("cspace_activation", C.c_float * 5), ("cspace_reg", C.c_float * 5), ("retime_weights", C.c_int32),
-                ("retime_regularization_weights", C.c_int32), ("num_goalset", C.c_int32)]
+                ("retime_regularization_weights", C.c_int32), ("num_goalset", C.c_int32),
+                ("cspace_target_weight", C.c_float), ("cspace_non_terminal_weight_factor", C.c_float)]
 
 
 class SplineInput(C.Structure):
@@ -63,7 +64,9 @@ class RolloutIO(C.Structure):
                 ("cspace_cost", c_p), ("grad_vel", c_p), ("grad_acc", c_p), ("grad_jerk", c_p),
                 ("link_pos", c_p), ("link_quat", c_p), ("robot_spheres", c_p), ("pose_goalset_idx", c_p),
                 ("batch_size", C.c_int32), ("horizon", C.c_int32), ("spline", C.POINTER(SplineInput)),
-                ("dynamics", C.POINTER(DynamicsParams))]
+                ("dynamics", C.POINTER(DynamicsParams)),
+                ("cspace_target", c_p), ("idxs_cspace_target", c_p), ("cspace_target_dof_weight", c_p),
+                ("sphere_configs", c_p), ("num_sphere_configs", C.c_int32)]
 
 
 _I = C.c_int
@@ -114,15 +117,21 @@ def load() -> C.CDLL:
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if not os.path.exists(path):
+    if not os.environ.get("CB200_LIB_VARIANT"):
+        # rebuild when a source is newer than the library (cheap mtime check); a box without nvcc -- the GPU box
+        # receives the prebuilt library -- uses what is there and fails loudly below if nothing is
         from . import build
-        build.build_product()
+        try:
+            build.build_product()
+        except RuntimeError:
+            if not os.path.exists(path):
+                raise
     lib = C.CDLL(path)
     for name, (args, res) in _SIGS.items():
         fn = getattr(lib, name)       # AttributeError if the symbol is missing: fail loudly
         fn.argtypes = args
         fn.restype = res
-    if lib.cb200_abi_version() != 4:
+    if lib.cb200_abi_version() != 5:
         raise RuntimeError("libcurobo_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -17,7 +17,7 @@ CUDA only; no CPU path.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 from typing import Callable, List, Optional, Tuple
 
 import torch
@@ -98,6 +98,7 @@ class LBFGSOpt:
     def __init__(self, cfg: LBFGSOptCfg, num_problems: int, action_horizon: int, action_dim: int,
                  action_bound_lows: torch.Tensor, action_bound_highs: torch.Tensor,
                  cost_grad_fn: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]], device="cuda:0"):
+        cfg = replace(cfg, line_search_scale=list(cfg.line_search_scale))   # never mutate the caller's config
         self.cfg, self.device = cfg, torch.device(device)
         _tc.require_cuda(self.device, "LBFGSOpt is CUDA-only")
         self.B, self.H, self.D = num_problems, action_horizon, action_dim
@@ -164,7 +165,7 @@ class LBFGSOpt:
             qn.step_q_buffer, qn.rho, qn.y, qn.s, self.exploration_action, self.exploration_gradient, qn.x_0, qn.grad_0,
             cfg.epsilon, self.B, cfg.history, self.V, cfg.stable_mode, True, x_set=self.x_set, step_scaled=self.step_scaled,
             search_magnitudes=self.magnitudes, action_step_max=self.step_max if self.clamp_step else None,
-            fix_terminal_action=cfg.fix_terminal_action)
+            fix_terminal_action=cfg.fix_terminal_action, action_dim=self.D)
 
     def step(self) -> None:
         """One optimizer iteration: step direction + search points, rollout, line search."""

@@ -74,7 +74,7 @@ class RobotModel:
 
     @property
     def num_spheres(self) -> int:
-        return int(self.link_spheres.shape[0])
+        return int(self.link_spheres.shape[-2])
 
     @property
     def num_tool_frames(self) -> int:

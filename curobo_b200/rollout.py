@@ -39,6 +39,8 @@ class RolloutConfig:
     cspace_reg: Sequence[float] = (0.0,) * 5
     retime_weights: bool = True
     retime_reg: bool = True
+    cspace_target_weight: float = 0.0                    # needs RolloutEngine.update_cspace_target
+    cspace_non_terminal_weight_factor: float = 1.0       # STATE cost only (waypoints h < H-1)
 
     # shipped task configs of the reference -------------------------------------------------
     @classmethod
@@ -56,12 +58,24 @@ class RolloutConfig:
                    cspace_weight=(10000.0, 10000.0, 100.0, 50.0, 100.0), cspace_activation=(0.01,) * 5,
                    cspace_reg=(1000.0, 10000.0, 5.0, 0.0, 10000.0))
 
+    @classmethod
+    def mpc(cls) -> "RolloutConfig":
+        """content/configs/task/mpc/lbfgs_mpc.yml:4-52 (c-space target term at weight 1000, 0.05 on non-terminal
+        waypoints; bound weights not retimed, regularisation weights retimed)."""
+        return cls(self_weight=100000.0, scene_weight=10000.0, scene_activation=0.01, use_sweep=True,
+                   use_speed_metric=True, pose_weight=(5000.0, 200.0), cspace_type="state",
+                   cspace_weight=(1000.0, 1000.0, 1000.0, 100.0, 0.0), cspace_activation=(0.01,) * 5,
+                   cspace_reg=(0.01, 10000.0, 10.0, 0.0, 0.0), retime_weights=False, retime_reg=True,
+                   cspace_target_weight=1000.0, cspace_non_terminal_weight_factor=0.05)
+
     def to_oracle_cfg(self, num_tool_frames: int) -> dict:
         d = dict(self_weight=self.self_weight, scene_weight=self.scene_weight, scene_eta=self.scene_activation,
                  sweep=self.use_sweep, speed_metric=self.use_speed_metric, pose_lie=self.pose_lie,
                  cspace_type=self.cspace_type, cspace_weight=list(self.cspace_weight),
                  cspace_activation=list(self.cspace_activation), cspace_reg=list(self.cspace_reg),
-                 retime_weights=self.retime_weights, retime_reg=self.retime_reg)
+                 retime_weights=self.retime_weights, retime_reg=self.retime_reg,
+                 cspace_target_weight=self.cspace_target_weight,
+                 cspace_non_terminal_weight_factor=self.cspace_non_terminal_weight_factor)
         if self.pose_weight is not None:
             d["pose_weight"] = list(self.pose_weight)
         return d
@@ -88,7 +102,9 @@ class RolloutOutput:
 def pack_robot_blob(rm: RobotModel) -> np.ndarray:
     """Robot constants -> one byte blob (layout: curobo_b200/csrc/cb200_blob.h), packed by the C helper."""
     L = _lib.load()
-    sz = _lib.RobotSizes(rm.num_links, rm.num_dof, rm.num_spheres, rm.num_tool_frames, int(rm.collision_pairs.shape[0]))
+    ls = rm.link_spheres if rm.link_spheres.ndim == 3 else rm.link_spheres[None]     # [n_cfg, S, 4]
+    sz = _lib.RobotSizes(rm.num_links, rm.num_dof, rm.num_spheres, rm.num_tool_frames, int(rm.collision_pairs.shape[0]),
+                         int(ls.shape[0]))
     nbytes = L.cb200_robot_blob_bytes(C.byref(sz))
     if nbytes <= 0:
         raise ValueError(f"robot does not fit the blob format (code {nbytes}); links <= 64 required")
@@ -99,7 +115,6 @@ def pack_robot_blob(rm: RobotModel) -> np.ndarray:
         keep.append(a)
         return a.ctypes.data
     keep = []
-    ls = rm.link_spheres if rm.link_spheres.ndim == 2 else rm.link_spheres[0]
     n = L.cb200_pack_robot_blob(
         out.ctypes.data, nbytes, C.byref(sz), p(rm.fixed_transforms, np.float32), p(rm.link_map, np.int16),
         p(rm.joint_map, np.int16), p(rm.joint_map_type, np.int8), p(rm.joint_offset_map, np.float32),
@@ -115,12 +130,17 @@ def pack_robot_blob(rm: RobotModel) -> np.ndarray:
 class RolloutEngine:
     def __init__(self, robot: RobotModel, cfg: RolloutConfig, device="cuda:0",
                  cuboid: Optional[CuboidData] = None, voxel: Optional[VoxelData] = None,
-                 store_fk_outputs: bool = False, use_voxel_mip: bool = True):
+                 store_fk_outputs: bool = False, use_voxel_mip: bool = False):
         self.robot, self.cfg, self.device = robot, cfg, torch.device(device)
         _tc.require_cuda(self.device, "RolloutEngine is CUDA-only (sm_100a); there is no CPU path")
         self._lib = _lib.load()
         self._blob_host = pack_robot_blob(robot)
         self._blob = torch.from_numpy(self._blob_host.copy()).to(self.device)
+        # several link-sphere configurations (attached objects per environment): rows pick theirs through env_query_idx
+        self._sphere_cfgs = None
+        if robot.link_spheres.ndim == 3 and robot.link_spheres.shape[0] > 1:
+            self._sphere_cfgs = torch.from_numpy(np.ascontiguousarray(robot.link_spheres, np.float32)).to(self.device)
+        self._cs_target = None
         self.cuboid, self.voxel = cuboid, voxel
         self.use_voxel_mip = use_voxel_mip
         self.refresh_world()
@@ -163,8 +183,10 @@ class RolloutEngine:
 
     def refresh_world(self) -> None:
         """Re-read the obstacle holders; call after the ESDF values (or obstacle tensors) were replaced or updated in
-        place.  Rebuilds the ESDF lower-bound pyramid level (one tiny launch) that lets discrete collision skip the
-        corner fetches of samples that are provably inactive (exact; `use_voxel_mip=False` disables it)."""
+        place.  With `use_voxel_mip=True` (opt-in) it rebuilds the ESDF lower-bound pyramid level (one tiny launch) that
+        lets discrete collision skip the corner fetches of samples that are provably inactive.  Exact while the level
+        matches the grid: torch-side updates of `features` are detected (version stamp; the level is rebuilt on the next
+        call), updates through raw pointers by foreign kernels are not -- call this after each of those."""
         if self.voxel is not None and self.use_voxel_mip:
             from .scene import build_voxel_mip
             build_voxel_mip(self.voxel)
@@ -189,7 +211,26 @@ class RolloutEngine:
             cc.cspace_reg[i] = float(c.cspace_reg[i]) if i < len(c.cspace_reg) else 0.0
         cc.retime_weights, cc.retime_regularization_weights = int(c.retime_weights), int(c.retime_reg)
         cc.num_goalset = num_goalset
+        cc.cspace_target_weight = float(c.cspace_target_weight)
+        cc.cspace_non_terminal_weight_factor = float(c.cspace_non_terminal_weight_factor)
         return cc
+
+    def update_cspace_target(self, target: torch.Tensor, idxs_target: Optional[torch.Tensor] = None,
+                             dof_weight: Optional[torch.Tensor] = None) -> None:
+        """C-space target of the cost (`target_joint_position [n, D]`, `idxs_target_joint_position [B]` int32,
+        `cspace_target_dof_weight [D]`; cost/cost_cspace_state.py, wp_cspace_state.py:84-89,220-226).  Read when
+        cfg.cspace_target_weight > 0."""
+        dev, D = self.device, self.robot.num_dof
+        check_tensors(dev, torch.float32, cspace_target=target)
+        if target.ndim != 2 or target.shape[1] != D:
+            raise ValueError(f"cspace target must be [n, {D}], got {tuple(target.shape)}")
+        if idxs_target is not None:
+            check_tensors(dev, torch.int32, idxs_cspace_target=idxs_target)
+        if dof_weight is not None:
+            check_tensors(dev, torch.float32, cspace_target_dof_weight=dof_weight)
+            if tuple(dof_weight.shape) != (D,):
+                raise ValueError(f"cspace_target_dof_weight must be [{D}]")
+        self._cs_target = (target, idxs_target, dof_weight)
 
     def setup_batch_tensors(self, batch: int, horizon: int) -> None:
         """Allocate every output once per (B, H) -- never inside evaluate_action."""
@@ -330,6 +371,13 @@ class RolloutEngine:
             io.cuboids = C.pointer(self._cs)
         if self._vs is not None:
             io.voxels = C.pointer(self._vs)
+        if self.voxel is not None and self.use_voxel_mip:
+            from .scene import voxel_mip_is_fresh
+            if not voxel_mip_is_fresh(self.voxel):      # the ESDF tensor was updated or replaced since the level was built
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("the ESDF changed since refresh_world(); call it before capturing a graph")
+                self.refresh_world()
+                io.voxels = C.pointer(self._vs)
         if env_query_idx is not None:
             check_tensors(dev, torch.int32, env_query_idx=env_query_idx)
             io.env_query_idx = env_query_idx.data_ptr()
@@ -342,6 +390,19 @@ class RolloutEngine:
                                ("pose_tol_terminal", "terminal_tol"), ("pose_tol_non_terminal", "non_terminal_tol")):
                 if extra[key] is not None:
                     setattr(io, cname, extra[key].data_ptr())
+        if self.cfg.cspace_target_weight > 0.0 and self.cfg.cspace_type is not None:
+            if self._cs_target is None:
+                raise ValueError("cspace_target_weight > 0 needs update_cspace_target(...) first")
+            tgt, tidx, tdw = self._cs_target
+            if tidx is not None and tidx.shape[0] != B:
+                raise ValueError("idxs_cspace_target must have one entry per batch row")
+            io.cspace_target = tgt.data_ptr()
+            if tidx is not None:
+                io.idxs_cspace_target = tidx.data_ptr()
+            if tdw is not None:
+                io.cspace_target_dof_weight = tdw.data_ptr()
+        if self._sphere_cfgs is not None:
+            io.sphere_configs, io.num_sphere_configs = self._sphere_cfgs.data_ptr(), int(self._sphere_cfgs.shape[0])
         io.cost, io.grad_q = o.cost.data_ptr(), o.grad_q.data_ptr()
         io.self_cost, io.scene_cost = o.self_cost.data_ptr(), o.scene_cost.data_ptr()
         io.pose_cost, io.cspace_cost = o.pose_cost.data_ptr(), o.cspace_cost.data_ptr()
@@ -360,16 +421,18 @@ class RolloutEngine:
 class FusedRolloutFunction(torch.autograd.Function):
     """cost[B] = sum_h rollout cost; backward returns the gradient computed in the same launch
     (the reference's own pattern: forward writes the gradient buffer, backward hands it out,
-    cuda_ops/geometry.py:95-104, wp_autograd.py:103-110; upstream gradient is all-ones,
-    gradient_opt_core.py:478)."""
+    cuda_ops/geometry.py:95-104, wp_autograd.py:103-110; the optimizer's upstream gradient is all-ones,
+    gradient_opt_core.py:478).  Unlike the reference's Functions with use_grad_input=False the upstream gradient IS
+    applied (per seed), so `cost.mean()` or a weighted sum differentiates correctly, and the gradient is saved as a
+    copy: a second forward before backward does not disturb the first one's gradient."""
 
     @staticmethod
     def forward(ctx, q: torch.Tensor, engine: RolloutEngine):
         out = engine.evaluate_action(q.detach())
-        ctx.save_for_backward(out.grad_q)
+        ctx.save_for_backward(out.grad_q.clone())
         return out.cost.sum(dim=1)
 
     @staticmethod
     def backward(ctx, grad_cost):
         (g,) = ctx.saved_tensors
-        return g, None
+        return g * grad_cost.reshape(-1, 1, 1), None

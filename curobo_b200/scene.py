@@ -78,7 +78,21 @@ def build_voxel_mip(d) -> torch.Tensor:
     vs.mip, vs.mip_stride = mip.data_ptr(), stride
     _lib.check(L.cb200_voxel_build_mip(C.byref(vs), stream_ptr(dev)), "voxel_build_mip")
     d.cb200_mip = mip
+    d.cb200_mip_stamp = _features_stamp(d)
     return mip
+
+
+def _features_stamp(d):
+    """Identity of the ESDF values a pyramid level was built from: storage pointer, shape and torch's in-place version counter.
+    Any torch-side update of `features` (copy_, index writes, replacement of the tensor) changes it.  Writes through raw
+    pointers by foreign kernels do not -- which is why the level is opt-in and owners of such grids call build_mip() /
+    RolloutEngine.refresh_world() after every update."""
+    f = d.features
+    return (int(f.data_ptr()), tuple(f.shape), int(getattr(f, "_version", 0)))
+
+
+def voxel_mip_is_fresh(d) -> bool:
+    return getattr(d, "cb200_mip", None) is not None and getattr(d, "cb200_mip_stamp", None) == _features_stamp(d)
 
 
 @dataclass
@@ -135,7 +149,8 @@ def c_voxel_set(d: Optional[object], dev=None) -> Optional[_lib.VoxelSet]:
         check_tensors(dev, torch.uint8, voxel_enable=d.enable)
         check_tensors(dev, torch.int32, voxel_count=d.count)
     n_vox = int(d.features.shape[2])
-    mip = getattr(d, "cb200_mip", None)
+    # an attached lower-bound level is handed to the kernels only while it provably matches the grid it was built from
+    mip = getattr(d, "cb200_mip", None) if voxel_mip_is_fresh(d) else None
     return _lib.VoxelSet(d.params.data_ptr(), d.inv_pose.data_ptr(), d.enable.data_ptr(), d.count.data_ptr(),
                          d.features.data_ptr(), n_vox, int(d.max_n), int(d.num_envs), float(d.max_esdf_distance),
                          mip.data_ptr() if mip is not None else None, int(mip.shape[1]) if mip is not None else 0)

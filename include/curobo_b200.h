@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st *cb200_stream_t; /* == cudaStream_t */
 
-#define CB200_ABI_VERSION 4
+#define CB200_ABI_VERSION 5
 
 /* Library / build identity.  cb200_abi_version() == CB200_ABI_VERSION; cb200_sm_arch() == 100. */
 int cb200_abi_version(void);
@@ -215,6 +215,7 @@ int cb200_cspace_position_cost(
 /* Size in bytes of the packed robot blob for the given sizes (host helper; 16-byte multiple). */
 typedef struct {
   int32_t num_links, num_dof, num_spheres, num_tool_frames, num_pairs;
+  int32_t num_sphere_configs; /* 0 or 1: link_spheres is [S,4]; n > 1: [n,S,4] (config 0 is staged, bounds cover all) */
 } cb200_robot_sizes;
 
 typedef struct {
@@ -228,6 +229,11 @@ typedef struct {
   float cspace_weight[5], cspace_activation[5], cspace_reg[5];
   int32_t retime_weights, retime_regularization_weights;
   int32_t num_goalset;
+  /* c-space target term (cost/wp_cspace_state.py:84-89,220-226; cost/wp_cspace_position.py target block): adds
+   * w_d * (q_d - target[idxs_cspace_target[b], d])^2 with w_d = cspace_target_weight * cspace_target_dof_weight[d];
+   * STATE cost: non-terminal waypoints (h < H-1) scale the weight by cspace_non_terminal_weight_factor
+   * (content/configs/task/mpc/lbfgs_mpc.yml:28-29).  Needs io->cspace_target; 0 disables. */
+  float cspace_target_weight, cspace_non_terminal_weight_factor;
 } cb200_rollout_cfg;
 
 /* Optional B-spline front end of the fused rollout: the rows of the rollout are the
@@ -296,6 +302,15 @@ typedef struct {
   int32_t batch_size, horizon;
   const cb200_spline_input *spline;       /* optional B-spline front end (host pointer); NULL = rows come from q */
   const cb200_dynamics_params *dynamics;  /* optional (host pointer): dynamics-aware STATE cost, see cb200_dynamics_params */
+  /* c-space target (retract / MPC reference configuration), read when cfg->cspace_target_weight > 0 */
+  const float *cspace_target;             /* [n_target, D] or null */
+  const int32_t *idxs_cspace_target;      /* [B] rows of cspace_target; null = row 0 */
+  const float *cspace_target_dof_weight;  /* [D] or null (= 1) */
+  /* link-sphere configurations (attached objects per environment; kinematics_forward_helper.cuh:232-233): row b uses
+   * sphere_configs[env_query_idx[b]] instead of the blob's set when num_sphere_configs > 1.  The blob must have been
+   * packed with the same configurations (cb200_robot_sizes.num_sphere_configs) so its broad-phase bounds cover all. */
+  const float *sphere_configs;            /* [num_sphere_configs, S, 4] or null */
+  int32_t num_sphere_configs;
 } cb200_rollout_io;
 
 int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io,

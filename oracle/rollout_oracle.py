@@ -709,7 +709,8 @@ def cspace_state_cost(pos, vel, acc, jerk, dt, limits, weight, activation, reg_w
 # ==========================================================================================
 
 def rollout_cost_grad(rm, q, cfg, world_cuboid=None, world_voxel=None, goal_pos=None, goal_quat=None,
-                      idxs_goal=None, env_query_idx=None, vel=None, acc=None, jerk=None, dt=None):
+                      idxs_goal=None, env_query_idx=None, vel=None, acc=None, jerk=None, dt=None,
+                      cspace_target=None, idxs_cspace_target=None, cspace_target_dof_weight=None):
     """One rollout cost+gradient evaluation for q [B,H,D].
 
     = RobotRollout.evaluate_action + sum + backward(ones) of
@@ -720,12 +721,17 @@ def rollout_cost_grad(rm, q, cfg, world_cuboid=None, world_voxel=None, goal_pos=
         pose_weight(2,), pose_terminal_axes[L,6], pose_non_terminal_axes[L,6], pose_terminal_tol[L,2],
         pose_non_terminal_tol[L,2], pose_lie(bool),
         cspace_type ("position"|"state"), cspace_weight, cspace_activation, cspace_reg (state only),
-        retime_weights, retime_reg
+        retime_weights, retime_reg, cspace_target_weight, cspace_non_terminal_weight_factor
+    cspace_target [n,D] / idxs_cspace_target [B] / cspace_target_dof_weight [D]: the c-space target term
+    (wp_cspace_state.py:84-89,220-226; wp_cspace_position.py).  Several link-sphere configurations
+    (rm.link_spheres [n_cfg,S,4]) are selected per seed through env_query_idx like the world.
     Returns dict(cost[B] (sum over h and terms), cost_bh[B,H], grad_q[B,H,D], + per-term outputs)."""
     q = np.asarray(q, F)
     B, H, D = q.shape
     N = B * H
-    cum, sph, lpos, lquat = fk_forward(rm, q.reshape(N, D))
+    multi_cfg = np.asarray(rm.link_spheres).ndim == 3 and np.asarray(rm.link_spheres).shape[0] > 1
+    cfg_idx = (np.zeros(B, np.int64) if env_query_idx is None else np.asarray(env_query_idx)) if multi_cfg else None
+    cum, sph, lpos, lquat = fk_forward(rm, q.reshape(N, D), cfg_idx, H)
     out = {"cumul": cum, "spheres": sph.reshape(B, H, -1, 4), "link_pos": lpos.reshape(B, H, -1, 3),
            "link_quat": lquat.reshape(B, H, -1, 4)}
     g_sph = np.zeros_like(sph)
@@ -758,10 +764,14 @@ def rollout_cost_grad(rm, q, cfg, world_cuboid=None, world_voxel=None, goal_pos=
                    pose_pos_err=pe, pose_rot_err=re)
         cost_bh += np.sum(c, axis=-1)
         g_pos, g_quat = g_pos.reshape(N, L, 3), g_quat.reshape(N, L, 4)
-    gq = fk_backward(rm, cum, g_sph, g_pos, g_quat).reshape(B, H, D)
+    gq = fk_backward(rm, cum, g_sph, g_pos, g_quat, cfg_idx, H).reshape(B, H, D)
     ctype = cfg.get("cspace_type")
+    tgt_w = float(cfg.get("cspace_target_weight", 0.0)) if cspace_target is not None else 0.0
+    tgt_idx = np.zeros(B, np.int64) if idxs_cspace_target is None else idxs_cspace_target
     if ctype == "position":
-        c, gp = cspace_position_cost(q, rm.position_limits, cfg["cspace_weight"], cfg["cspace_activation"])
+        c, gp = cspace_position_cost(q, rm.position_limits, cfg["cspace_weight"], cfg["cspace_activation"],
+                                     target=cspace_target if tgt_w > 0 else None, idxs_target=tgt_idx,
+                                     target_weight=tgt_w, target_dof_weight=cspace_target_dof_weight)
         out["cspace_cost"], out["cspace_grad_p"] = c, gp
         cost_bh += np.sum(c, axis=-1)
         gq = (gq + gp).astype(F)
@@ -772,7 +782,10 @@ def rollout_cost_grad(rm, q, cfg, world_cuboid=None, world_voxel=None, goal_pos=
         c, gs = cspace_state_cost(q, z if vel is None else vel, z if acc is None else acc,
                                   z if jerk is None else jerk, np.ones(B, F) if dt is None else dt, lim,
                                   cfg["cspace_weight"], cfg["cspace_activation"], cfg["cspace_reg"],
-                                  cfg.get("retime_weights", True), cfg.get("retime_reg", True))
+                                  cfg.get("retime_weights", True), cfg.get("retime_reg", True),
+                                  target=cspace_target if tgt_w > 0 else None, idxs_target=tgt_idx, target_weight=tgt_w,
+                                  non_terminal_factor=float(cfg.get("cspace_non_terminal_weight_factor", 1.0)),
+                                  target_dof_weight=cspace_target_dof_weight)
         out["cspace_cost"], out["cspace_grads"] = c, gs
         cost_bh += np.sum(c, axis=-1)
         gq = (gq + gs[0]).astype(F)

@@ -21,3 +21,18 @@ def _seed():
         torch.manual_seed(42)
     except Exception:
         pass
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a CUDA device: the gpu-marked tests are skipped, not failed."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA GPU (B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -36,7 +36,7 @@ def emulated_library():
     for name, (args, res) in cblib._SIGS.items():
         fn = getattr(L, name)                     # every ABI symbol must exist in the emulated library too
         fn.argtypes, fn.restype = args, res
-    assert L.cb200_abi_version() == 4
+    assert L.cb200_abi_version() == 5
     return L
 
 
@@ -131,6 +131,24 @@ def test_fused_ik(run):
 @pytest.mark.parametrize("B,H,speed", [(4, 12, True), (5, 5, False), (6, 1, True), (3, 9, True)])
 def test_fused_trajectory(run, B, H, speed):
     run("test_gpu_rollout", "test_traj_rollout_vs_oracle", B, H, speed)
+
+
+@pytest.mark.parametrize("B,H,with_dofw", [(5, 30, True), (3, 7, False), (4, 1, True)])
+def test_fused_mpc_config(run, B, H, with_dofw):
+    run("test_gpu_rollout", "test_mpc_config_rollout_vs_oracle", B, H, with_dofw)
+
+
+def test_fused_position_target_and_sphere_configs(run):
+    run("test_gpu_rollout", "test_ik_position_cspace_target_vs_oracle")
+    run("test_gpu_rollout", "test_fused_rollout_sphere_configs", "discrete")
+    run("test_gpu_rollout", "test_fused_rollout_sphere_configs", "swept")
+
+
+def test_rollout_protocol_adapter(run):
+    run("test_gpu_rollout_protocol", "test_protocol_surface")
+    run("test_gpu_rollout_protocol", "test_ik_rollout_through_optimizer_contract_vs_oracle")
+    run("test_gpu_rollout_protocol", "test_mpc_position_actions_with_state")
+    run("test_gpu_rollout_protocol", "test_bspline_action_space_gradient_wrt_knots")
 
 
 @pytest.mark.parametrize("robot,n", [("g1_29", 6), ("g1_43", 4)])

@@ -453,3 +453,164 @@ def test_voxel_mip_build_and_exact_cull():
                                           T(np.array([0.02], np.float32)), None, T(env), True, False)
         res.append((d.clone(), buf.gradient.clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+# ------------------------------------------------------------------------------------------------
+# the shipped MPC cost (content/configs/task/mpc/lbfgs_mpc.yml): c-space target term at weight 1000 with the 0.05
+# non-terminal factor, un-retimed bound weights, swept collision + speed metric, pose cost on every waypoint
+# ------------------------------------------------------------------------------------------------
+def _mpc_inputs(rm, B, H, seed):
+    q = random_walk_q(rm, B, H, seed=seed)
+    rng = np.random.default_rng(seed)
+    dt = np.full(B, 0.05, np.float32)
+    v = (np.gradient(q, axis=1).astype(np.float32) / 0.05) if H > 1 else np.zeros_like(q)
+    a_ = rng.normal(0, 5.0, size=q.shape).astype(np.float32)
+    j_ = rng.normal(0, 200.0, size=q.shape).astype(np.float32)
+    target = random_q(rm, 3, seed=seed + 1, scale=0.5)
+    tidx = (np.arange(B) % 3).astype(np.int32)
+    dofw = np.linspace(0.5, 1.5, rm.num_dof).astype(np.float32)
+    dofw[2] = 0.0                                            # a dof the target ignores
+    return q, v, a_, j_, dt, target, tidx, dofw
+
+
+@pytest.mark.parametrize("B,H", [(5, 30), (3, 7), (4, 1)])
+@pytest.mark.parametrize("with_dofw", [True, False])
+def test_mpc_config_rollout_vs_oracle(B, H, with_dofw):
+    rm = load_robot("franka")
+    q, v, a_, j_, dt, target, tidx, dofw = _mpc_inputs(rm, B, H, 90 + H)
+    if not with_dofw:
+        dofw = None
+    cfg = RolloutConfig.mpc()
+    assert cfg.cspace_target_weight == 1000.0 and cfg.cspace_non_terminal_weight_factor == 0.05 and not cfg.retime_weights
+    cub, vox = make_benchmark_cuboid_world(), small_voxel_world()
+    gp, gq = goal_from_q(rm, random_q(rm, B, seed=92))
+    idx = np.arange(B, dtype=np.int32)
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    eng.update_goal(T(gp), T(gq), T(idx))
+    with pytest.raises(ValueError):
+        eng.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))   # target weight > 0 but no target given
+    eng.update_cspace_target(T(target), T(tidx), None if dofw is None else T(dofw))
+    out = eng.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
+    torch.cuda.synchronize()
+    want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(1), world_cuboid=cub, world_voxel=vox, goal_pos=gp, goal_quat=gq,
+                               idxs_goal=idx, vel=v, acc=a_, jerk=j_, dt=dt, cspace_target=target, idxs_cspace_target=tidx,
+                               cspace_target_dof_weight=dofw)
+    cost_close(out.cspace_cost.cpu().numpy(), want["cspace_cost"], rtol=2e-4)
+    np.testing.assert_allclose(out.cost.cpu().numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+    for got, wantg in zip((out.grad_vel, out.grad_acc, out.grad_jerk), want["cspace_grads"][1:4]):
+        grad_close(got.cpu().numpy(), wantg)
+    # the target term is live and the non-terminal factor applies: without it the c-space cost is smaller, and the terminal
+    # waypoint carries 1 / 0.05 of a non-terminal waypoint's weight
+    cfg0 = RolloutConfig(**{**cfg.__dict__, "cspace_target_weight": 0.0})
+    eng0 = RolloutEngine(rm, cfg0, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
+    eng0.update_goal(T(gp), T(gq), T(idx))
+    c0 = eng0.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt)).cspace_cost.clone()
+    diff = (out.cspace_cost - c0).cpu().numpy()                         # = tw_h * dofw_d * err^2
+    dw = np.ones(rm.num_dof, np.float32) if dofw is None else dofw
+    err2 = (q - target[tidx][:, None, :]) ** 2
+    tw = np.full(H, 1000.0 * 0.05, np.float32)
+    tw[-1] = 1000.0
+    np.testing.assert_allclose(diff, tw[None, :, None] * dw[None, None, :] * err2, rtol=2e-3, atol=2e-3 * np.abs(diff).max())
+
+
+def test_ik_position_cspace_target_vs_oracle():
+    """POSITION c-space cost with a live target term (wp_cspace_position.py target block; retract configuration of IK)."""
+    rm = load_robot("franka")
+    B = 40
+    q = random_q(rm, B, seed=95)[:, None, :]
+    cfg = RolloutConfig.ik()
+    cfg.cspace_target_weight = 25.0
+    target = random_q(rm, 2, seed=96, scale=0.3)
+    tidx = (np.arange(B) % 2).astype(np.int32)
+    dofw = np.array([1, 1, 0, 2, 1, 0.5, 1], np.float32)
+    gp, gq = goal_from_q(rm, random_q(rm, 4, seed=97))
+    idx = (np.arange(B) % 4).astype(np.int32)
+    cub = make_benchmark_cuboid_world()
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV))
+    eng.update_goal(T(gp), T(gq), T(idx))
+    eng.update_cspace_target(T(target), T(tidx), T(dofw))
+    out = eng.evaluate_action(T(q))
+    want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(1), world_cuboid=cub, goal_pos=gp, goal_quat=gq, idxs_goal=idx,
+                               cspace_target=target, idxs_cspace_target=tidx, cspace_target_dof_weight=dofw)
+    cost_close(out.cspace_cost.cpu().numpy(), want["cspace_cost"], rtol=2e-4)
+    np.testing.assert_allclose(out.cost.cpu().numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+    assert float(out.cspace_cost[:, :, 2].abs().max()) == float(T(want["cspace_cost"])[:, :, 2].abs().max())
+
+
+def test_mpc_full_size_sampled_seeds_vs_oracle():
+    """BASELINE config 4 as the reference defines it: 1024 particles x 30 waypoints, shipped MPC weights, 256^3 ESDF;
+    whole trajectories of sampled seeds against the oracle, plus determinism and a CUDA-graph replay."""
+    rm = load_robot("franka")
+    B, H = 1024, 30
+    sdf = make_box_esdf(n=256, voxel_size=0.01, num_boxes=12, seed=0, xp=torch)
+    vox = VoxelData(T(np.array([[[256, 256, 256, 0.01]]], np.float32)), T(np.array([[[0, 0, 0, 1, 0, 0, 0, 0]]], np.float32)),
+                    torch.ones((1, 1), dtype=torch.uint8, device=DEV), torch.ones(1, dtype=torch.int32, device=DEV),
+                    sdf.reshape(1, 1, -1).contiguous(), 1, 1, 100.0)
+    q, v, a_, j_, dt, target, tidx, dofw = _mpc_inputs(rm, B, H, 98)
+    cfg = RolloutConfig.mpc()
+    gp, gq = goal_from_q(rm, random_q(rm, 8, seed=99))
+    idx = (np.arange(B) % 8).astype(np.int32)
+    eng = RolloutEngine(rm, cfg, DEV, voxel=vox)
+    eng.update_goal(T(gp), T(gq), T(idx))
+    eng.update_cspace_target(T(target), T(tidx), T(dofw))
+    tq, tv, ta, tj, tdt = T(q), T(v), T(a_), T(j_), T(dt)
+    o = eng.evaluate_action(tq, vel=tv, acc=ta, jerk=tj, dt=tdt)
+    c1, g1 = o.cost.clone(), o.grad_q.clone()
+    o = eng.evaluate_action(tq, vel=tv, acc=ta, jerk=tj, dt=tdt)
+    assert torch.equal(c1, o.cost) and torch.equal(g1, o.grad_q) and torch.isfinite(g1).all()
+    sel = np.arange(0, B, 128)
+    vw = VoxelWorld(vox.params.cpu().numpy(), vox.inv_pose.cpu().numpy(), np.ones((1, 1), np.uint8), np.ones(1, np.int32),
+                    sdf.reshape(1, 1, -1).cpu().numpy(), 100.0)
+    want = O.rollout_cost_grad(rm, q[sel], cfg.to_oracle_cfg(1), world_voxel=vw, goal_pos=gp, goal_quat=gq, idxs_goal=idx[sel],
+                               vel=v[sel], acc=a_[sel], jerk=j_[sel], dt=dt[sel], cspace_target=target,
+                               idxs_cspace_target=tidx[sel], cspace_target_dof_weight=dofw)
+    np.testing.assert_allclose(c1.cpu().numpy()[sel], want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(g1.cpu().numpy()[sel], want["grad_q"], rtol=2e-3, scale=2e-5)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        eng.evaluate_action(tq, vel=tv, acc=ta, jerk=tj, dt=tdt)
+    eng.out.cost.zero_()
+    eng.out.grad_q.zero_()
+    gr.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(eng.out.cost, c1) and torch.equal(eng.out.grad_q, g1)
+
+
+@pytest.mark.parametrize("mode", ["discrete", "swept"])
+def test_fused_rollout_sphere_configs(mode):
+    """Several link-sphere configurations (attached objects per environment, kinematics_forward_helper.cuh:232-233): a row
+    uses robot_spheres[env_query_idx[b]]; config 1 grows / moves some spheres and disables others."""
+    import copy
+    rm = copy.copy(load_robot("franka"))
+    ls0 = np.asarray(rm.link_spheres, np.float32).reshape(-1, 4)
+    ls1 = ls0.copy()
+    ls1[-4:, 3] = 0.08                                   # an attached object: big spheres on the last link
+    ls1[-4:, :3] += np.array([0.0, 0.0, 0.12], np.float32)
+    ls1[5:8, 3] = -1.0                                   # disabled spheres
+    ls2 = ls0.copy()
+    ls2[:, 3] = np.where(ls0[:, 3] >= 0, ls0[:, 3] * 1.3, ls0[:, 3])
+    rm.link_spheres = np.stack([ls0, ls1, ls2])
+    B, H = 12, (1 if mode == "discrete" else 5)
+    q = random_walk_q(rm, B, H, seed=101) if H > 1 else random_q(rm, B, seed=101)[:, None, :]
+    cub, vox = _two_env_worlds()
+    cub3 = type(cub)(np.concatenate([cub.dims, cub.dims[:1]]), np.concatenate([cub.inv_pose, cub.inv_pose[:1]]),
+                     np.concatenate([cub.enable, cub.enable[:1]]), np.concatenate([cub.count, cub.count[:1]]))
+    env = (np.arange(B) % 3).astype(np.int32)
+    cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                        cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0),
+                        use_sweep=(mode == "swept"), use_speed_metric=False)
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub3, DEV), store_fk_outputs=True)
+    out = eng.evaluate_action(T(q), env_query_idx=T(env))
+    torch.cuda.synchronize()
+    want = O.rollout_cost_grad(rm, q, cfg.to_oracle_cfg(1), world_cuboid=cub3, env_query_idx=env)
+    np.testing.assert_allclose(out.robot_spheres.cpu().numpy(), want["spheres"], atol=1e-5)
+    cost_close(out.self_cost.cpu().numpy(), want["self_cost"])
+    np.testing.assert_allclose(out.scene_cost.cpu().numpy(), want["scene_cost"], rtol=2e-4,
+                               atol=1e-5 * max(want["scene_cost"].max(), 1e-6))
+    np.testing.assert_allclose(out.cost.cpu().numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+    assert np.abs(want["spheres"][1, :, -4:, 3] - 0.08).max() < 1e-6 and (want["spheres"][1, :, 5:8, 3] < 0).all()
+    assert want["scene_cost"].sum() + want["self_cost"].sum() > 0
