@@ -11,10 +11,14 @@ no data-path collective; one NCCL all_gather of per-seed costs after the timed r
 it happens once per solve, not per iteration).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events per step on the
-launching stream, L2 flushed between steps, max over ranks); `e2e` = same metric through the public
-API with pinned-host inputs and host read-back inside the timed region; `roofline` = algorithmic bytes
-per eval x evals / kernel time vs the measured HBM peak; `cpu_baseline` = the
-numpy oracle (a port of the reference arithmetic; the reference has no CPU path) on a bounded sample.
+launching stream, L2 flushed between steps, max over ranks; `value_warm_l2` = the same loop without the
+flush); `e2e` = same metric through the public API with pinned-host inputs and host read-back inside the
+timed region (one CUDA graph per step: H2D, kernel, D2H; no flush -- the inputs arrive by H2D every step);
+`roofline` = algorithmic bytes per eval x evals / kernel time vs the measured HBM
+peak; `cpu_baseline` = the numpy oracle (a port of the reference arithmetic; the reference has no CPU
+path) on a bounded sample.  `sharded` = BASELINE configs 4 and 5 STRONG-scaled over the N ranks (total rows
+fixed, rows / N per rank): rollout-only and a complete seed-sharded L-BFGS solve with the end-of-solve
+all_gather inside the timed region.  `baseline_configs` (last key, compact) = configs 2-5 on one line.
 """
 from __future__ import annotations
 
@@ -49,6 +53,12 @@ def make_workload(name: str, seed_offset: int = 0):
             break
     wl = _make_workload(name, seed_offset)
     wl["dynamics"] = mode
+    if mode is not None and "mpc" in name:
+        # the effort channel has zero weight in lbfgs_mpc.yml; the dynamics-aware variants keep the trajopt weights
+        # (effort bound 100, energy 10000) they were introduced with
+        from curobo_b200.rollout import RolloutConfig
+        wl["cfg"] = RolloutConfig.trajopt()
+        wl.pop("cs_target", None)
     return wl
 
 
@@ -93,9 +103,15 @@ def _make_workload(name: str, seed_offset: int = 0):
         goal = (gp[:, :, None, :].copy(), gq[:, :, None, :].copy(), np.arange(B, dtype=np.int32))
         D, S, L = rm.num_dof, rm.num_spheres, rm.num_tool_frames
         bpe = 4 * D + 4 * D + 4 * (S + 1 + 2 * L + D) + 16 * S * 7 + 3 * 4 * D * 2   # swept worst case n_s = 7; v/a/j in + grads out
-        return dict(robot=rm, cfg=RolloutConfig.trajopt(), B=B, H=H, q=q, goal=goal, cuboid=None,
-                    voxel=dict(n=256, voxel=0.01, boxes=12, seed=0), bytes_per_eval=bpe,
-                    extra=dict(vel=vel, acc=acc, jerk=jerk, dt=np.full(B, 0.05, np.float32)))
+        # config 4 (MPC) runs the shipped MPC weights (lbfgs_mpc.yml: c-space target term at 1000, x0.05 on non-terminal
+        # waypoints); config 3 (trajopt) the shipped B-spline trajopt weights
+        mpc = "mpc" in name
+        wl = dict(robot=rm, cfg=RolloutConfig.mpc() if mpc else RolloutConfig.trajopt(), B=B, H=H, q=q, goal=goal, cuboid=None,
+                  voxel=dict(n=256, voxel=0.01, boxes=12, seed=0), bytes_per_eval=bpe,
+                  extra=dict(vel=vel, acc=acc, jerk=jerk, dt=np.full(B, 0.05, np.float32)))
+        if mpc:
+            wl["cs_target"] = (random_q(rm, 4, seed=13).astype(np.float32), (np.arange(B) % 4).astype(np.int32))
+        return wl
     if name in ("franka_mpc_knots_1024x30_esdf_swept", "franka_mpc_knots_inkernel_1024x30_esdf_swept"):
         # config 4 driven the way the reference's MPC/trajopt drives it: the action is 24 B-spline knots per seed
         # (degree 4, 1 interpolation step -> 30 rows); one C call = knots -> row costs + d cost / d knots
@@ -131,10 +147,14 @@ def build_engine(wl, device):
         vox = VoxelData(t([[[v["n"], v["n"], v["n"], v["voxel"]]]], np.float32), t([[[0, 0, 0, 1, 0, 0, 0, 0]]], np.float32),
                         torch.ones((1, 1), dtype=torch.uint8, device=device), torch.ones(1, dtype=torch.int32, device=device),
                         sdf.reshape(1, 1, -1).contiguous().to(device), 1, 1, 100.0)
-    eng = RolloutEngine(wl["robot"], wl["cfg"], device, cub, vox)
+    # static synthetic ESDF: the exact lower-bound level is built once (refresh_world) and stays fresh; discrete mode only
+    eng = RolloutEngine(wl["robot"], wl["cfg"], device, cub, vox, use_voxel_mip=vox is not None and not wl["cfg"].use_sweep)
     if wl["goal"] is not None:
         gp, gq, idx = wl["goal"]
         eng.update_goal(torch.as_tensor(gp).to(device), torch.as_tensor(gq).to(device), torch.as_tensor(idx).to(device))
+    if wl.get("cs_target") is not None:
+        tgt, tidx = wl["cs_target"]
+        eng.update_cspace_target(torch.as_tensor(tgt).to(device), torch.as_tensor(tidx).to(device))
     if wl.get("dynamics"):
         from curobo_b200.dynamics import Dynamics
         rm = wl["robot"]
@@ -178,6 +198,13 @@ def ik_solve_bench(device, problems=512, seeds=32, iters=100, repeats=5):
     for _ in range(repeats):
         q_sol = opt.optimize(x0)
     torch.cuda.synchronize(device)
+    dt_eager = (time.perf_counter() - t0) / repeats
+    opt.optimize_graphed(x0)                                            # capture: the whole solve = one CUDA-graph launch
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        q_sol = opt.optimize_graphed(x0)
+    torch.cuda.synchronize(device)
     dt = (time.perf_counter() - t0) / repeats
     q_sol = q_sol.view(B, D)
     st = Kinematics(rm, device).compute_kinematics(q_sol.view(B, 1, D))
@@ -188,9 +215,11 @@ def ik_solve_bench(device, problems=512, seeds=32, iters=100, repeats=5):
     rerr = 2.0 * np.arccos(dotq)
     ok = ((perr < 5e-3) & (rerr < 0.05)).any(axis=1)
     return {"problems": problems, "seeds": seeds, "iterations": iters, "line_search_candidates": n,
-            "launches_per_iteration": 3, "solve_ms": dt * 1e3, "ik_solves_per_s": problems / dt,
+            "launches_per_iteration": 3, "solve_ms": dt * 1e3, "solve_ms_eager_python_loop": dt_eager * 1e3,
+            "schedule": "LBFGSOpt.optimize_graphed: initial evaluation + 100 iterations replayed as ONE CUDA graph",
+            "ik_solves_per_s": problems / dt,
             "rollout_evals_per_s": B * n * (iters + 1) / dt, "success_rate": float(ok.mean()),
-            "median_position_error_mm": float(np.median(perr.min(axis=1)) * 1e3), "timer": "wall clock incl. Python loop"}
+            "median_position_error_mm": float(np.median(perr.min(axis=1)) * 1e3), "timer": "wall clock around the call"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -373,6 +402,8 @@ def _oracle_eval(args):
         kw = dict(goal_pos=gp, goal_quat=gq, idxs_goal=idx[lo:hi])
     for k, v in wl.get("extra", {}).items():
         kw[k] = v[lo:hi]
+    if wl.get("cs_target") is not None:
+        kw.update(cspace_target=wl["cs_target"][0], idxs_cspace_target=wl["cs_target"][1][lo:hi])
     t0 = time.perf_counter()
     O.rollout_cost_grad(wl["robot"], q, wl["cfg"].to_oracle_cfg(wl["robot"].num_tool_frames), world_cuboid=wl["cuboid"],
                         world_voxel=vox, **kw)
@@ -402,14 +433,36 @@ def cpu_baseline(wl_name: str, target_seconds: float = 12.0, procs: int = 1):
 
 
 # ------------------------------------------------------------------------------------------------
+def workload_config(name, wl):
+    """The `config` object -- identical in both arms (the driver compares them)."""
+    return {"workload": name, "robot": wl["robot"].name, "batch_per_gpu": wl["B"], "horizon": wl["H"],
+            "evals_per_step_per_gpu": wl["B"] * wl["H"],
+            "world": "cuboids" if wl["cuboid"] is not None else "esdf_256^3_fp16",
+            "cache": "GPU arm: L2 flushed (256 MiB write) between timed steps", "timer": "GPU arm: cuda events per step, max over ranks"}
+
+
+def _limit_blas_threads():
+    """One BLAS / OpenMP thread per worker process: 128 forked numpy workers each spinning up a 128-thread pool is what made the
+    CPU arm swing 4x between boxes in round 1."""
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:                                                     # noqa: BLE001
+        pass
+
+
 def run_reference_arm(args):
     """--impl reference: the reference has no CPU implementation of this path (DeviceCfg defaults to cuda,
-    kernels are CUDA/Warp only), so the CPU arm is the oracle port on all host cores.  Each step evaluates a
-    bounded sample of the workload (one slice per core); the whole run is sized to end within ~2 minutes."""
+    kernels are CUDA/Warp only), so the CPU arm is the oracle port (numpy, float32; NOT PyTorch: the port is written in numpy)
+    on all host cores, one single-threaded process per core.  Each step evaluates a bounded sample of the workload (one slice
+    per core); the whole run is sized to end within ~2 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    _limit_blas_threads()
     cores = os.cpu_count() or 1
     wl = make_workload(args.workload)
     _oracle_eval((args.workload, 0, 64))                       # import + warm caches in the parent (fork shares them)
@@ -426,14 +479,48 @@ def run_reference_arm(args):
             if i >= args.warmup:
                 vals.append(n / dt)
     value = float(np.mean(vals))
-    sample = f"{n} of {wl['B'] * wl['H']} evals of {args.workload} per step, numpy oracle, {cores} processes"
+    sample = f"{n} of {wl['B'] * wl['H']} evals of {args.workload} per step, numpy (not torch) oracle, {cores} single-threaded processes"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "robot": wl["robot"].name, "batch": wl["B"], "horizon": wl["H"]},
+            "config": workload_config(args.workload, wl),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def pin_to_gpu_numa_node(local_rank: int):
+    """Bind this rank's host threads to the CPUs NVML reports as local to its GPU (GPUs 4-7 sit on NUMA node 1 on the 8-GPU
+    boxes; an unpinned rank that lands on the other socket pays a cross-socket hop on every launch and pinned copy)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:                                                     # noqa: BLE001
+        pass
+    return 0
+
+
+def shard_workload(wl, lo, hi):
+    """Rows [lo, hi) of a workload (strong scaling: the total is fixed, a rank evaluates its slice)."""
+    w = dict(wl)
+    w["B"] = hi - lo
+    w["q"] = wl["q"][lo:hi]
+    if wl["goal"] is not None:
+        gp, gq, idx = wl["goal"]
+        w["goal"] = (gp, gq, idx[lo:hi].copy())
+    if "extra" in wl:
+        w["extra"] = {k: v[lo:hi] for k, v in wl["extra"].items()}
+    if wl.get("cs_target") is not None:
+        w["cs_target"] = (wl["cs_target"][0], wl["cs_target"][1][lo:hi].copy())
+    return w
 
 
 def main():
@@ -448,6 +535,11 @@ def main():
                     help="1: also time a complete 100-iteration L-BFGS IK solve (512 goals x 32 seeds), reported under 'ik_solve'")
     ap.add_argument("--edt", type=int, default=1, help="1: also time the exact nearest-site transform (256^3), reported under 'edt'")
     ap.add_argument("--rnea", type=int, default=1, help="1: also time the RNEA inverse-dynamics kernels, reported under 'rnea'")
+    ap.add_argument("--sharded", type=int, default=1,
+                    help="1: also strong-scale BASELINE configs 4 and 5 over the N ranks (rollout + sharded solve), under 'sharded'")
+    ap.add_argument("--reference-design", type=int, default=1,
+                    help="1 (N=1 only): time the reference's own kernels compiled for sm_100a, chained unfused from a CUDA graph "
+                         "(scripts/bench_reference_design.py, separate process), under 'reference_design_gpu'")
     ap.add_argument("--extra-workloads", default="franka_16384_esdf,franka_trajopt_32x32_esdf_swept,franka_mpc_1024x30_esdf_swept,franka_mpc_knots_1024x30_esdf_swept,franka_mpc_knots_inkernel_1024x30_esdf_swept,g1_29_8192_esdf,g1_43_8192_esdf,franka_mpc_1024x30_esdf_swept_dynamics_host,franka_mpc_1024x30_esdf_swept_dynamics,franka_mpc_knots_1024x30_esdf_swept_dynamics",
                     help="comma list, measured briefly on rank 0 at N=1 and reported under 'other_workloads'")
     args = ap.parse_args()
@@ -462,185 +554,263 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA GPU: the rollout path has no CPU fallback")
+    pinned_cpus = pin_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    from curobo_b200.rollout import HostRolloutPipeline
+    # clocks are sampled from here to the end of the e2e loop (pre-roll, timed steps, e2e): the timed region alone
+    # (K x 77 us) is shorter than nvidia-smi's 100 ms period
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
 
-    def timed_run(wl_name, steps, warmup, sample_clocks):
-        wl = make_workload(wl_name, seed_offset=rank)
-        eng = build_engine(wl, device)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def make_run(wl, eng, q):
         kw = {k: torch.as_tensor(v).to(device) for k, v in wl.get("extra", {}).items()}
         if "knots" in wl:
             from curobo_b200.trajectory import JointState
             kn = wl["knots"]
             td = lambda a: torch.as_tensor(a).to(device)  # noqa: E731
-            q = td(kn["knots"])
+            kq = td(kn["knots"])
             ks = JointState(*[td(x) for x in kn["start"]])
             kg = JointState(*[td(x) for x in kn["goal"]], dt=td(kn["dt"]))
             kidx = torch.arange(wl["B"], dtype=torch.int32, device=device)
             kimp = torch.zeros(wl["B"], dtype=torch.uint8, device=device)
-            run = lambda: eng.evaluate_knots(q, ks, kidx, kg, kidx, kimp, kn["degree"], kn["steps"],  # noqa: E731
-                                             in_kernel_spline=kn["in_kernel"])
-        else:
-            q = torch.as_tensor(wl["q"]).to(device)
-            run = lambda: eng.evaluate_action(q, **kw)  # noqa: E731
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)       # 2x the 126 MB L2
+            return (lambda: eng.evaluate_knots(kq, ks, kidx, kg, kidx, kimp, kn["degree"], kn["steps"],
+                                               in_kernel_spline=kn["in_kernel"])), kw
+        return (lambda: eng.evaluate_action(q, **kw)), kw
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)       # 2x the 126 MB L2
+
+    def timed_steps(run, steps, do_flush):
         stream = torch.cuda.current_stream(device)
-        for _ in range(warmup):
-            run()
-        torch.cuda.synchronize(device)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        if world > 1:
-            dist.barrier()
+        barrier()
         torch.cuda.synchronize(device)
-        if sampler:
-            sampler.start()
         for i in range(steps):
-            flush.fill_(i & 0xFF)                           # evict L2 between timed steps (outside the event pair)
+            if do_flush:
+                flush.fill_(i & 0xFF)                       # evict L2 between timed steps (outside the event pair)
             starts[i].record(stream)
             run()
             ends[i].record(stream)
         torch.cuda.synchronize(device)
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop() if sampler else None
-        ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        barrier()
+        return [s.elapsed_time(e) for s, e in zip(starts, ends)]
+
+    def timed_run(wl_or_name, steps, warmup, preroll_s=0.0, warm_too=False):
+        wl = make_workload(wl_or_name, seed_offset=rank) if isinstance(wl_or_name, str) else wl_or_name
+        eng = build_engine(wl, device)
+        q = torch.as_tensor(wl["q"]).to(device) if wl.get("q") is not None else None
+        run, kw = make_run(wl, eng, q)
+        for _ in range(warmup):
+            run()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < preroll_s:          # untimed pre-roll: clocks settle, the sampler gets samples under load
+            for _ in range(50):
+                run()
+            torch.cuda.synchronize(device)
+        ms = timed_steps(run, steps, True)
+        ms_warm = timed_steps(run, steps, False) if warm_too else None
         wl["kw"] = kw
-        return wl, eng, q, float(sum(ms)), ms, clocks
+        return wl, eng, q, ms, ms_warm
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     if "knots" in args.workload:
         raise SystemExit("the B-spline knots workload is measured under other_workloads (--extra-workloads) only")
-    wl, eng, q, total_ms, ms_list, clocks = timed_run(args.workload, args.steps, args.warmup, rank == 0)
+    wl, eng, q, ms_list, ms_warm = timed_run(args.workload, args.steps, args.warmup, preroll_s=0.5, warm_too=True)
     evals_per_step = wl["B"] * wl["H"]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(float(sum(ms_list)))
     value = world * evals_per_step * args.steps / (total_ms_max * 1e-3)
+    value_warm = world * evals_per_step * args.steps / (max_over_ranks(float(sum(ms_warm))) * 1e-3)
 
     # ---- e2e: what a user of the public API does per optimizer iteration with HOST data: pinned host q -> H2D ->
-    # RolloutEngine.evaluate_action -> D2H of cost + grad_q.  Every step's copies are inside the timed region; the
-    # three stages run on three streams with double buffering (two engines = two output buffer sets), the usual
-    # way to drive a copy-compute-copy loop, so step i+1's upload overlaps step i's kernel.
+    # RolloutEngine.evaluate_action -> D2H of cost + grad_q, through curobo_b200.rollout.HostRolloutPipeline: every step is ONE
+    # CUDA-graph launch (copy, kernel, copies) on one of two slots (two streams, two engines = two buffer sets), so step
+    # i+1's upload overlaps step i's kernel.  Every step's copies are inside the timed region.
     D = wl["robot"].num_dof
-    engs = [eng, build_engine(wl, device)]
-    q_host = torch.as_tensor(wl["q"]).pin_memory()
-    q_dev = [torch.empty_like(q) for _ in range(2)]
-    cost_host = [torch.empty((wl["B"], wl["H"]), dtype=torch.float32).pin_memory() for _ in range(2)]
-    grad_host = [torch.empty((wl["B"], wl["H"], D), dtype=torch.float32).pin_memory() for _ in range(2)]
-    s_in, s_comp, s_out = (torch.cuda.Stream(device) for _ in range(3))
-    for g in engs:                                       # allocate per-(B,H) buffers outside the pipeline
-        g.evaluate_action(q, **wl["kw"])
-    torch.cuda.synchronize(device)
-
-    def e2e_loop(n):
-        in_done = [torch.cuda.Event() for _ in range(2)]
-        comp_done = [torch.cuda.Event() for _ in range(2)]
-        out_done = [torch.cuda.Event() for _ in range(2)]
-        for i in range(n):
-            k = i & 1
-            with torch.cuda.stream(s_in):
-                if i >= 2:
-                    s_in.wait_event(comp_done[k])            # q_dev[k] is free once step i-2's kernel has read it
-                q_dev[k].copy_(q_host, non_blocking=True)
-                in_done[k].record(s_in)
-            with torch.cuda.stream(s_comp):
-                s_comp.wait_event(in_done[k])
-                if i >= 2:
-                    s_comp.wait_event(out_done[k])           # outputs of engine k were read back (step i-2)
-                o = engs[k].evaluate_action(q_dev[k], **wl["kw"])
-                comp_done[k].record(s_comp)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(comp_done[k])
-                cost_host[k].copy_(o.cost, non_blocking=True)
-                grad_host[k].copy_(o.grad_q, non_blocking=True)
-                out_done[k].record(s_out)
-
-    e2e_loop(4)
-    torch.cuda.synchronize(device)
-    if world > 1:
-        dist.barrier()
+    pipe = HostRolloutPipeline([eng, build_engine(wl, device)], wl["B"], wl["H"], **wl["kw"])
+    for sl in pipe.slots:
+        sl.q_host.copy_(torch.as_tensor(wl["q"]))
+    for i in range(4):
+        pipe.submit(i & 1)
+    pipe.wait_all()
+    barrier()
     t0 = time.perf_counter()
-    e2e_loop(args.steps)
-    torch.cuda.synchronize(device)
-    te = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * evals_per_step * args.steps / (float(te.item()) * 1e-3)
-    h2d = int(q_host.numel() * 4)
-    d2h = int(cost_host[0].numel() * 4 + grad_host[0].numel() * 4)
+    for i in range(args.steps):
+        pipe.submit(i & 1)
+    pipe.wait_all()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = world * evals_per_step * args.steps / (e2e_ms * 1e-3)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     # sanity: the host copy of the last step's result is the device result
-    assert torch.equal(cost_host[(args.steps - 1) & 1], engs[(args.steps - 1) & 1].out.cost.cpu())
+    last = pipe.slots[(args.steps - 1) & 1]
+    assert torch.equal(last.cost_host, last.engine.out.cost.cpu())
+    clocks = sampler.stop() if sampler else None
 
-    # ---- the one real exchange of the sharded path: per-seed cost all_gather (once per solve; untimed)
-    if world > 1:
-        from curobo_b200.sharded import gather_seed_costs_and_best
-        gather_seed_costs_and_best(eng.out.cost.sum(dim=1), q.view(wl["B"], -1), wl["B"] * world)
+    # ---- BASELINE configs 4 and 5, strong-scaled over the ranks: total rows fixed, this rank evaluates rows / N.
+    # (a) rollout only: K2 timed steps (events, L2 flushed), max over ranks; (b) a complete seed-sharded solve through
+    # curobo_b200.sharded.ShardedSolver: per-rank L-BFGS (one CUDA graph) + the end-of-solve all_gather, all inside the timed region.
+    sharded = {}
+    if args.sharded:
+        from curobo_b200.optim import LBFGSOptCfg
+        from curobo_b200.sharded import ShardedSolver, shard_rows
+        for key, name, max_world, iters in (("config5_g1_29_8192_esdf", "g1_29_8192_esdf", 8, 20),
+                                            ("config4_franka_mpc_1024x30", "franka_mpc_1024x30_esdf_swept", 4, 10)):
+            if world > max_world:
+                sharded[key] = {"skipped": f"BASELINE shards this config over at most {max_world} GPUs"}
+                continue
+            try:
+                full = make_workload(name)
+                lo, hi = shard_rows(full["B"], rank, world)
+                part = shard_workload(full, lo, hi)
+                k2 = max(5, min(50, args.steps))
+                w2, e2, _, ms2, _ = timed_run(part, k2, 3)
+                roll_ms = max_over_ranks(float(np.mean(ms2)))
+                res = {"total_rows": full["B"], "horizon": full["H"], "rows_per_gpu": hi - lo,
+                       "rollout_ms_per_step": roll_ms, "rollout_evals_per_s": full["B"] * full["H"] / (roll_ms * 1e-3)}
+                # the solve: every seed's waypoint positions are the optimisation variable, 4 line-search candidates per seed
+                cfg_o = LBFGSOptCfg(num_iters=iters)
+                n = len(cfg_o.line_search_scale)
+                rep = lambda a: np.repeat(a, n, axis=0)  # noqa: E731
+                cand = dict(part, B=part["B"] * n, q=rep(part["q"]))
+                if part["goal"] is not None:
+                    cand["goal"] = (part["goal"][0], part["goal"][1], rep(part["goal"][2]))
+                if part.get("cs_target") is not None:
+                    cand["cs_target"] = (part["cs_target"][0], rep(part["cs_target"][1]))
+                cand.pop("extra", None)                           # vel / acc / jerk: finite differences inside the kernel
+                eng_s = build_engine(cand, device)
+                kw_s = {}
+                if full["H"] > 1:
+                    kw_s["dt"] = torch.full((cand["B"],), 0.05, device=device)
+                solver = ShardedSolver(eng_s, full["B"], full["H"], cfg_o, eval_kwargs=kw_s)
+                x0 = torch.as_tensor(part["q"]).to(device)
+                solver.solve(x0)                                  # warm-up + graph capture
+                torch.cuda.synchronize(device)
+                ts = []
+                for _ in range(3):
+                    barrier()
+                    torch.cuda.synchronize(device)
+                    t0 = time.perf_counter()
+                    cost_all, best_row, _ = solver.solve(x0)
+                    torch.cuda.synchronize(device)
+                    ts.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+                sm = float(np.median(ts))
+                res.update({"solve_ms": sm, "solve_iterations": iters, "line_search_candidates": n,
+                            "solve_rollout_evals_per_s": full["B"] * full["H"] * n * (iters + 1) / (sm * 1e-3),
+                            "solve_includes": "per-rank L-BFGS (one CUDA graph) + all_gather of seed costs + best action",
+                            "best_row": int(best_row), "best_cost": float(cost_all[best_row])})
+                sharded[key] = res
+                del solver, eng_s, e2
+            except Exception as ex:                                               # noqa: BLE001
+                sharded[key] = {"error": repr(ex)[:300]}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         kernel_ms = float(np.mean(ms_list))
         achieved = wl["bytes_per_eval"] * evals_per_step / (kernel_ms * 1e-3) / 1e9
+        cfg_obj = workload_config(args.workload, wl)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "robot": wl["robot"].name, "batch_per_gpu": wl["B"], "horizon": wl["H"],
-                       "evals_per_step_per_gpu": evals_per_step, "sharding": f"seeds x{world} (no data-path collective)",
-                       "cache": "L2 flushed (256 MiB write) between timed steps", "timer": "cuda events per step, max over ranks"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "config": cfg_obj,
+            "sharding": f"seeds x{world} (no data-path collective); ranks pinned to their GPU's NUMA cpus: {pinned_cpus}",
+            "value_warm_l2": value_warm,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "cache": "no flush (inputs arrive by H2D every step); compare with value_warm_l2",
+                    "api": "curobo_b200.rollout.HostRolloutPipeline: one CUDA graph per step = H2D + rollout kernel + D2H"},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "rollout_fused_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "bytes_per_eval": wl["bytes_per_eval"], "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "note": "path is FP32-issue/latency bound by construction (working set is L2-resident); see DESIGN.md"},
+            "sharded": sharded,
         }
+        others = {}
         if world == 1:
-            others = {}
 
             def extra(name):
                 try:
-                    w2, _, _, tot2, ms2, _ = timed_run(name, max(5, args.steps // 5), 3, False)
+                    w2, _, _, ms2, _ = timed_run(name, max(5, args.steps // 5), 3)
                     k_ms = float(np.mean(ms2))
                     ach = w2["bytes_per_eval"] * w2["B"] * w2["H"] / (k_ms * 1e-3) / 1e9
-                    others[name] = {"value": w2["B"] * w2["H"] / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms,
+                    others[name] = {"value": w2["B"] * w2["H"] / (k_ms * 1e-3), "kernel_ms": k_ms,
                                     "bytes_per_eval": w2["bytes_per_eval"], "hbm_frac": ach / peak}
                 except Exception as ex:                                           # noqa: BLE001
-                    others[name] = {"error": repr(ex)}
+                    others[name] = {"error": repr(ex)[:200]}
 
-            names = [w for w in args.extra_workloads.split(",") if w]
-            first_run = [w for w in names if "_dynamics" in w]   # kernels that have not run on a B200 yet go last (see below)
-            for name in names:
-                if name not in first_run:
-                    extra(name)
+            for name in [w for w in args.extra_workloads.split(",") if w]:
+                extra(name)
             line["other_workloads"] = others
             if args.ik_solve:
                 try:
                     line["ik_solve"] = ik_solve_bench(device)
                 except Exception as ex:                                               # noqa: BLE001
-                    line["ik_solve"] = {"error": repr(ex)}
+                    line["ik_solve"] = {"error": repr(ex)[:200]}
             if args.rnea:
                 try:
                     line["rnea"] = rnea_bench(device, peak)
                 except Exception as ex:                                               # noqa: BLE001
-                    line["rnea"] = {"error": repr(ex)}
-            for name in first_run:      # after everything measured before: a fault here cannot take those numbers with it
-                extra(name)
+                    line["rnea"] = {"error": repr(ex)[:200]}
             if args.edt:
                 try:
                     line["edt"] = edt_bench(device, peak)
                 except Exception as ex:                                               # noqa: BLE001
-                    line["edt"] = {"error": repr(ex)}
+                    line["edt"] = {"error": repr(ex)[:200]}
+            if args.reference_design:
+                line["reference_design_gpu"] = reference_design_leg()
             if not args.no_cpu_baseline:
+                _limit_blas_threads()
                 v, cores, sample = cpu_baseline(args.workload, target_seconds=12.0, procs=1)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        # compact, LAST: BASELINE.json configs on one short object (the driver keeps the tail of the line)
+        bc = {"c2_franka_ik_512x32_cuboid": {"evals_per_s": round(value), "ms": round(kernel_ms, 4), "e2e_evals_per_s": round(e2e_value)}}
+        for key, name in (("c3_franka_trajopt_32x32_esdf", "franka_trajopt_32x32_esdf_swept"),
+                          ("c4_franka_mpc_1024x30_esdf", "franka_mpc_1024x30_esdf_swept"), ("c5_g1_29_8192_esdf", "g1_29_8192_esdf")):
+            if name in others and "value" in others[name]:
+                bc[key] = {"evals_per_s": round(others[name]["value"]), "ms": round(others[name]["kernel_ms"], 4)}
+        for key, short in (("config4_franka_mpc_1024x30", "c4_sharded"), ("config5_g1_29_8192_esdf", "c5_sharded")):
+            r = sharded.get(key, {})
+            if "rollout_evals_per_s" in r:
+                bc[short] = {"n": world, "evals_per_s": round(r["rollout_evals_per_s"]), "ms": round(r["rollout_ms_per_step"], 4),
+                             "solve_ms": round(r.get("solve_ms", 0.0), 3)}
+        rd = line.get("reference_design_gpu")
+        if isinstance(rd, dict) and "workloads" in rd:
+            bc["ref_design_gpu_ms"] = {k: round(v["reference_design_ms"], 4) for k, v in rd["workloads"].items()}
+        if "ik_solve" in line and "solve_ms" in line["ik_solve"]:
+            bc["ik_solve_ms"] = round(line["ik_solve"]["solve_ms"], 3)
+        line["baseline_configs"] = bc
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_design_leg():
+    """The kernel to beat, on the same GPU: the reference's own CUDA kernels (compiled for sm_100a under oracle/_ref) chained
+    unfused with stand-alone scene / pose / c-space kernels and replayed from a CUDA graph (scripts/bench_reference_design.py).
+    Runs in its own process -- the product path in this process never loads oracle/_ref."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_reference_design.py"), "--json"],
+                           capture_output=True, text=True, timeout=600)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as ex:                                                       # noqa: BLE001
+        return {"error": repr(ex)[:200]}
 
 
 if __name__ == "__main__":

@@ -185,3 +185,25 @@ class LBFGSOpt:
         for _ in range(num_iters if num_iters is not None else self.cfg.num_iters):
             self.step()
         return self.best_action.view(self.B, self.H, self.D)
+
+    def optimize_graphed(self, x0: torch.Tensor, num_iters: Optional[int] = None) -> torch.Tensor:
+        """The whole solve -- initial evaluation + `num_iters` x (step direction, rollout, line search) -- as ONE CUDA-graph
+        launch ("whole _opt_iters as one launch", gradient_opt_core.py:334-400, which the reference
+        also replays from a graph, one graph per iteration block).  The first call runs one eager solve (allocations, launch-plan
+        caches), captures the loop on a side stream and replays it; later calls copy x0 into the captured input and replay.
+        Every buffer the loop touches is owned by this object or by the cost function's engine, so the replay is allocation
+        free; `cost_grad_fn` must launch on the current stream and must not synchronise (RolloutEngine does neither)."""
+        n_it = num_iters if num_iters is not None else self.cfg.num_iters
+        g = getattr(self, "_graph", None)
+        if g is None or self._graph_iters != n_it:
+            self._graph_x0 = torch.empty((self.B, self.V), device=self.device, dtype=torch.float32)
+            self._graph_x0.copy_(x0.reshape(self.B, self.V))
+            self.optimize(self._graph_x0, n_it)                          # eager warm-up, same buffers
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.device(self.device), torch.cuda.graph(g):
+                self.optimize(self._graph_x0, n_it)
+            self._graph, self._graph_iters = g, n_it
+        self._graph_x0.copy_(x0.reshape(self.B, self.V))
+        self._graph.replay()
+        return self.best_action.view(self.B, self.H, self.D)

@@ -436,3 +436,66 @@ class FusedRolloutFunction(torch.autograd.Function):
     def backward(ctx, grad_cost):
         (g,) = ctx.saved_tensors
         return g * grad_cost.reshape(-1, 1, 1), None
+
+
+class HostRolloutPipeline:
+    """`evaluate_action` for HOST-resident inputs, the way an optimizer that keeps its iterate on the host (or another
+    process feeding joint batches) drives the kernel: per step  pinned q -> H2D -> fused rollout -> D2H of cost + grad_q.
+
+    Each slot owns an engine (= one set of output buffers), pinned host buffers and ONE captured CUDA graph holding the
+    three stages, replayed on the slot's own stream: a step costs the host a single graph launch, and with two slots the
+    upload of step i+1 overlaps the kernel of step i (stream order inside a slot makes buffer reuse safe).
+
+        pipe = HostRolloutPipeline([eng_a, eng_b], B, H, dt=dt)
+        pipe.slots[k].q_host[...] = ...      # fill the pinned input of slot k
+        pipe.submit(k)                       # H2D + kernel + D2H, asynchronous
+        cost, grad = pipe.result(k)          # waits for slot k; pinned host tensors
+    """
+
+    class Slot:
+        def __init__(self, engine, B, H, D, device):
+            self.engine = engine
+            self.stream = torch.cuda.Stream(device)
+            self.q_host = torch.empty((B, H, D), dtype=torch.float32).pin_memory()
+            self.cost_host = torch.empty((B, H), dtype=torch.float32).pin_memory()
+            self.grad_host = torch.empty((B, H, D), dtype=torch.float32).pin_memory()
+            self.q_dev = torch.empty((B, H, D), dtype=torch.float32, device=device)
+            self.graph = None
+
+    def __init__(self, engines: Sequence[RolloutEngine], batch: int, horizon: int, **eval_kwargs):
+        if not engines:
+            raise ValueError("at least one engine")
+        self.device = engines[0].device
+        D = engines[0].robot.num_dof
+        self._kw = eval_kwargs
+        self.slots = [HostRolloutPipeline.Slot(e, batch, horizon, D, self.device) for e in engines]
+        self.h2d_bytes = int(self.slots[0].q_host.numel() * 4)
+        self.d2h_bytes = int((self.slots[0].cost_host.numel() + self.slots[0].grad_host.numel()) * 4)
+        for s in self.slots:
+            s.q_host.zero_()
+            self._stages(s)                                    # eager once: output allocation, launch-plan caches
+        torch.cuda.synchronize(self.device)
+        for s in self.slots:
+            s.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.device(self.device), torch.cuda.graph(s.graph, stream=s.stream):
+                self._stages(s)
+
+    def _stages(self, s) -> None:
+        s.q_dev.copy_(s.q_host, non_blocking=True)
+        out = s.engine.evaluate_action(s.q_dev, **self._kw)
+        s.cost_host.copy_(out.cost, non_blocking=True)
+        s.grad_host.copy_(out.grad_q, non_blocking=True)
+
+    def submit(self, k: int) -> None:
+        s = self.slots[k]
+        with torch.cuda.stream(s.stream):
+            s.graph.replay()
+
+    def result(self, k: int):
+        s = self.slots[k]
+        s.stream.synchronize()
+        return s.cost_host, s.grad_host
+
+    def wait_all(self) -> None:
+        for s in self.slots:
+            s.stream.synchronize()

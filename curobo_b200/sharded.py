@@ -31,6 +31,11 @@ def gather_seed_costs_and_best(cost_local: torch.Tensor, action_local: torch.Ten
     cost_local [b_local] per-seed final cost, action_local [b_local, ...] per-seed action of this rank.
     Returns (cost_all [total_rows], best_global_row, best_action) identical on every rank.
     One all_gather of padded costs + one all_gather of each rank's local-best action."""
+    if not (dist.is_available() and dist.is_initialized()):       # single process: the gather is the identity
+        if cost_local.shape[0] != total_rows:
+            raise ValueError(f"single process owns all {total_rows} rows but got {cost_local.shape[0]} costs")
+        li = int(torch.argmin(cost_local))
+        return cost_local.clone(), li, action_local[li].contiguous()
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     s, e = shard_rows(total_rows, rank, world)
@@ -53,3 +58,67 @@ def gather_seed_costs_and_best(cost_local: torch.Tensor, action_local: torch.Ten
     best_row = int(torch.argmin(cost_all))
     owner = next(r for r in range(world) if shard_rows(total_rows, r, world)[0] <= best_row < shard_rows(total_rows, r, world)[1])
     return cost_all, best_row, bests[owner]
+
+
+def _rank_world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def local_rows_of(t: torch.Tensor, total_rows: int, group=None) -> torch.Tensor:
+    """This rank's slice of a per-seed tensor [total_rows, ...] (GoalRegistry rows: idxs_goal, env_query_idx, seeds;
+    rollout/goal_registry.py:27-58)."""
+    rank, world = _rank_world(group)
+    lo, hi = shard_rows(total_rows, rank, world)
+    return t[lo:hi].contiguous()
+
+
+class ShardedSolver:
+    """A seed-sharded solve as ONE call ("ShardedRollout / solver wrapper that slices GoalRegistry rows").
+
+    `total_rows` seeds (particles) of horizon H are split over the ranks of `group`; rank r runs the complete L-BFGS loop
+    (curobo_b200.optim.LBFGSOpt: step direction -> fused rollout on rows x line-search candidates -> Wolfe line search)
+    on its rows [lo, hi) only -- captured in one CUDA graph -- and the single exchange of the path happens at the end:
+    `gather_seed_costs_and_best` (two KB-scale all_gathers over NCCL / NVLink).  No per-iteration communication.
+
+    `engine` must already hold this rank's per-row inputs, repeated per line-search candidate (row order = seed-major,
+    candidate-minor, the layout LBFGSOpt evaluates): use `candidate_rows(local_rows_of(idxs_goal, total), n)`.
+    `eval_kwargs` are passed to RolloutEngine.evaluate_action on every call (dt, env_query_idx, ...)."""
+
+    def __init__(self, engine, total_rows: int, horizon: int, opt_cfg=None, group=None, eval_kwargs=None):
+        from .optim import LBFGSOpt, LBFGSOptCfg
+        self.engine, self.total_rows, self.H, self.group = engine, int(total_rows), int(horizon), group
+        self.rank, self.world = _rank_world(group)
+        self.lo, self.hi = shard_rows(self.total_rows, self.rank, self.world)
+        self.b = self.hi - self.lo
+        if self.b <= 0:
+            raise ValueError(f"rank {self.rank} of {self.world} owns no rows of {total_rows}")
+        cfg = opt_cfg if opt_cfg is not None else LBFGSOptCfg()
+        rm, dev = engine.robot, engine.device
+        self.D = rm.num_dof
+        self.n = len(cfg.line_search_scale)
+        self._kw = dict(eval_kwargs or {})
+        lim = torch.as_tensor(rm.position_limits, dtype=torch.float32, device=dev)
+        self.opt = LBFGSOpt(cfg, self.b, self.H, self.D, lim[0].contiguous(), lim[1].contiguous(), self._cost_grad, dev)
+
+    def _cost_grad(self, x: torch.Tensor):
+        rows = self.b * self.n
+        out = self.engine.evaluate_action(x.view(rows, self.H, self.D), **self._kw)
+        cost = out.cost.view(rows) if self.H == 1 else out.cost.sum(dim=1)
+        return cost, out.grad_q.view(rows, self.H * self.D)
+
+    def solve(self, x0_local: torch.Tensor, num_iters: Optional[int] = None, graphed: bool = True):
+        """x0_local [hi - lo, H, D].  Returns (cost_all [total_rows], best_global_row, best_action [H, D]) -- identical on
+        every rank."""
+        if x0_local.shape[0] != self.b:
+            raise ValueError(f"rank {self.rank} owns rows [{self.lo}, {self.hi}) but got {x0_local.shape[0]} seeds")
+        run = self.opt.optimize_graphed if graphed else self.opt.optimize
+        q = run(x0_local, num_iters)
+        cost_all, row, best = gather_seed_costs_and_best(self.opt.best_cost, q.reshape(self.b, -1), self.total_rows, self.group)
+        return cost_all, row, best.view(self.H, self.D)
+
+
+def candidate_rows(t: torch.Tensor, n_candidates: int) -> torch.Tensor:
+    """Repeat a per-seed tensor for the n line-search candidates of each seed (seed-major, candidate-minor)."""
+    return t.repeat_interleave(n_candidates, dim=0).contiguous()

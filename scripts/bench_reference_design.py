@@ -39,7 +39,7 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def run(workload, steps=200, warmup=10, device="cuda:0"):
+def run(workload, steps=200, warmup=10, device="cuda:0", quiet=False):
     dev = torch.device(device)
     wl = bench.make_workload(workload)
     rm, cfg = wl["robot"], wl["cfg"]
@@ -194,16 +194,26 @@ def run(workload, steps=200, warmup=10, device="cuda:0"):
     dc = float((uc - fc).abs().max() / fc.abs().max())
     dg = float((ug - fg).abs().max() / fg.abs().max())
     n_launch = 8 + (1 if has_pose else 0) + 3 + (1 if has_pose else 0)
-    print(json.dumps({"workload": workload, "rows": N, "reference_design_unfused_ms": ms_unfused,
-                      "reference_design_evals_per_s": N / (ms_unfused * 1e-3), "fused_ms": ms_fused,
-                      "fused_evals_per_s": N / (ms_fused * 1e-3), "speedup": ms_unfused / ms_fused,
-                      "launches_unfused_approx": n_launch, "launches_fused": 1, "max_rel_diff_cost": dc,
-                      "max_rel_diff_grad": dg, "timer": "cuda events around a CUDA-graph replay, L2 flushed between steps"}),
-          flush=True)
+    res = {"workload": workload, "rows": N, "reference_design_unfused_ms": ms_unfused,
+           "reference_design_evals_per_s": N / (ms_unfused * 1e-3), "fused_ms": ms_fused,
+           "fused_evals_per_s": N / (ms_fused * 1e-3), "speedup": ms_unfused / ms_fused,
+           "launches_unfused_approx": n_launch, "launches_fused": 1, "max_rel_diff_cost": dc,
+           "max_rel_diff_grad": dg, "timer": "cuda events around a CUDA-graph replay, L2 flushed between steps"}
+    if not quiet:
+        print(json.dumps(res), flush=True)
+    return res
 
 
 if __name__ == "__main__":
     if not ref_kernels.available():
         raise SystemExit("oracle/_ref/libcurobo_ref.so is missing (build it where /root/reference exists)")
-    for w in (sys.argv[1:] or ["franka_ik_512x32_cuboid", "franka_16384_esdf", "g1_29_8192_esdf"]):
-        run(w)
+    as_json = "--json" in sys.argv
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["franka_ik_512x32_cuboid", "franka_16384_esdf", "g1_29_8192_esdf"]
+    out = {}
+    for w in names:
+        r = run(w, quiet=as_json)
+        out[w] = {"reference_design_ms": r["reference_design_unfused_ms"], "fused_ms": r["fused_ms"], "speedup": r["speedup"],
+                  "max_rel_diff_cost": r["max_rel_diff_cost"], "max_rel_diff_grad": r["max_rel_diff_grad"]}
+    if as_json:    # one line for bench.py's reference_design_gpu leg
+        print(json.dumps({"what": "the reference's own CUDA kernels (sm_100a, oracle/_ref) chained unfused from a CUDA graph vs the "
+                                  "fused kernel, same inputs, L2 flushed between steps", "workloads": out}), flush=True)

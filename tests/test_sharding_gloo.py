@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from curobo_b200.sharded import gather_seed_costs_and_best, shard_rows
+from curobo_b200.sharded import candidate_rows, gather_seed_costs_and_best, local_rows_of, shard_rows
 
 
 def test_shard_rows_partition():
@@ -32,6 +32,10 @@ def _worker(rank, world, port, total, q):
         s, e = shard_rows(total, rank, world)
         cost_all, row, best = gather_seed_costs_and_best(cost[s:e].clone(), act[s:e].clone(), total)
         ok = torch.equal(cost_all, cost) and row == int(torch.argmin(cost)) and torch.equal(best, act[row])
+        # the GoalRegistry-row slicing the sharded solver uses: this rank's rows, repeated per line-search candidate
+        mine = local_rows_of(act, total)
+        ok = ok and torch.equal(mine, act[s:e]) and torch.equal(candidate_rows(mine, 4)[::4], mine) \
+            and candidate_rows(mine, 4).shape[0] == 4 * (e - s)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -51,3 +55,12 @@ def test_gather_best_world_size_2(total):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_gather_single_process_is_identity():
+    cost = torch.tensor([3.0, 1.0, 2.0])
+    act = torch.arange(6, dtype=torch.float32).view(3, 2)
+    cost_all, row, best = gather_seed_costs_and_best(cost, act, 3)
+    assert torch.equal(cost_all, cost) and row == 1 and torch.equal(best, act[1])
+    with pytest.raises(ValueError):
+        gather_seed_costs_and_best(cost, act, 4)
