@@ -22,6 +22,7 @@
 #include "cb200_blob.h"
 #include "cb200_bspline.cuh"
 #include "cb200_dynamics.cuh"
+#include "cb200_dynamics_tile.cuh"
 #include "cb200_launch.h"
 #include "cb200_math.cuh"
 #include "cb200_warp.cuh"
@@ -62,7 +63,7 @@ struct FusedArgs {
     int32_t n_knots, degree, steps;
   } spl;
   // Inverse dynamics inside the trajectory kernel (8f-3): inertial parameters of the links (the kinematic tree is the blob's).
-  // Only read by the DYN instantiations of rollout_traj_kernel.
+  // Only read by rollout_traj_dyn_kernel.
   struct Dyn {
     const float *masses_com, *inertias, *gravity;
   } dyn;
@@ -207,18 +208,7 @@ __device__ __forceinline__ float cspace_dof(const FusedArgs &a, const RobotView 
 //   phase A: q load + c-space cost, FK, spheres (+ padded copy), tool poses + tool-pose cost
 //   phase B: self collision, scene collision (discrete | swept + speed metric), J^T backward, row cost
 // ------------------------------------------------------------------------------------------------
-// Per-row accessor of the RNEA row functions (cb200_dynamics.cuh) over a plain [array][link][6] scratch.
-struct DynRowStore {
-  float *t;
-  int nl;
-  __device__ __forceinline__ float get(int arr, int k, int c) const { return t[(arr * nl + k) * 6 + c]; }
-  __device__ __forceinline__ void set(int arr, int k, int c, float v) { t[(arr * nl + k) * 6 + c] = v; }
-};
-// floats of row scratch the in-kernel inverse dynamics borrows from the row's own FK / sphere buffers (not live yet in phase A)
-__host__ __device__ inline int dyn_scratch_floats(int nl, int D) { return ((7 * D + 3) & ~3) + 20 * nl + 30 * nl; }
-__host__ __device__ inline int dyn_scratch_available(int nl, int S) { return nl * 12 + S * 8 + nl * 8; }
-
-template <bool SPLINE, bool DYN = false>
+template <bool SPLINE>
 __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
                                             int b, int h, float &cs_cost, float &pose_c) {
   const cb200_rollout_cfg &cfg = a.cfg;
@@ -233,60 +223,8 @@ __device__ __forceinline__ void row_phase_a(const FusedArgs &a, const RobotView 
     es.gqv[d] = gp;
     cs_cost += c;
     if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
-    if constexpr (DYN) {  // velocity / acceleration of the row for the inverse dynamics below
-      es.cumul[d] = st.v;
-      es.cumul[D + d] = st.a;
-    }
   }
   __syncwarp();
-  if constexpr (DYN) {
-    // Dynamics-aware STATE cost: tau = RNEA(q, qd, qdd) for this row, the effort channel of the STATE
-    // cost on it (bound hinge, squared-L2, energy (tau qd dt)^2: wp_cspace_state.py:209-275), and the RNEA adjoint of
-    // d cost / d tau onto the position / velocity / acceleration gradients -- tau never leaves the SM.  The recursion is
-    // sequential along the tree: lane 0 walks it (cb200_dynamics.cuh row functions) while the row's FK / sphere buffers,
-    // not live yet, hold its scratch; the per-dof terms are done by the lanes.
-    float *sc = es.cumul;
-    float *qd_s = sc, *qdd_s = sc + D, *tau_s = sc + 2 * D, *gt_s = sc + 3 * D, *gq_s = sc + 4 * D, *gqd_s = sc + 5 * D,
-          *gqdd_s = sc + 6 * D;
-    float *cache = sc + ((7 * D + 3) & ~3);
-    DynRowStore st{cache + 20 * rv.nl, rv.nl};
-    const dyn::Model M{rv.fixed, a.dyn.masses_com, a.dyn.inertias, rv.joint_type, rv.joint_map, rv.link_map, rv.joff,
-                       a.dyn.gravity, rv.level_off, rv.level_links, rv.nl, D, rv.n_levels};
-    // LdPlain: the tree part of M (fixed transforms, joint offsets) points into the shared-memory copy of the robot blob, which
-    // the read-only global path (__ldg) must not be used on
-    if (lane == 0) dyn::rnea_forward_row<DynRowStore, dyn::LdPlain>(M, st, es.qv, qd_s, qdd_s, nullptr, tau_s, cache);
-    __syncwarp();
-    const float dt = seed_dt(a, b);
-    float w_b = cfg.cspace_weight[4], w_l2 = cfg.cspace_reg[3], w_en = cfg.cspace_reg[4];
-    if (cfg.retime_regularization_weights) w_en = dt * w_en;
-    const float *lim = rv.limits;
-    #pragma unroll 1
-    for (int d = lane; d < D; d += 32) {
-      const float tau = tau_s[d], v = qd_s[d];
-      float c = 0.0f, gt = 0.0f;
-      bound_cost(tau, lim[8 * D + d], lim[9 * D + d], cfg.cspace_activation[4], w_b, c, gt);
-      l2_reg(tau, w_l2, c, gt);
-      if (w_en > 0.0f) {
-        const float ce = tau * v * dt;
-        c += w_en * ce * ce;
-        gt += 2.0f * w_en * ce * v * dt;
-        if (a.grad_vel) a.grad_vel[(size_t)e * D + d] += 2.0f * w_en * ce * tau * dt;
-      }
-      gt_s[d] = gt;
-      cs_cost += c;
-      if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] += c;
-    }
-    __syncwarp();
-    if (lane == 0) dyn::rnea_backward_row<DynRowStore, dyn::LdPlain>(M, st, gt_s, es.qv, qd_s, cache, gq_s, gqd_s, gqdd_s, nullptr);
-    __syncwarp();
-    #pragma unroll 1
-    for (int d = lane; d < D; d += 32) {
-      es.gqv[d] += gq_s[d];
-      if (a.grad_vel) a.grad_vel[(size_t)e * D + d] += gqd_s[d];
-      if (a.grad_acc) a.grad_acc[(size_t)e * D + d] += gqdd_s[d];
-    }
-    __syncwarp();
-  }
   warp_fk(rv, es, lane);
   warp_spheres(rv, es, lane, a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr,
                row_sphere_cfg(a, b, S));
@@ -550,7 +488,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
 // waypoint (warp 0 / the last warp also compute the halo waypoints' spheres), the CTA synchronises, then
 // every warp runs phase B reading its neighbours' sphere positions from shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int SCENE, bool SPLINE, bool DYN = false>
+template <int SCENE, bool SPLINE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
   CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
@@ -597,7 +535,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
     const int e = b * a.H + h;
     float cs_cost = 0.0f, pose_c = 0.0f;
     RowB1 r{0.0f, 0.0f, 0.0f, 0, 0, 0};
-    if (active) row_phase_a<SPLINE, DYN>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    if (active) row_phase_a<SPLINE>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
     __syncthreads();
     if (active) {
       const float4 *prev = nullptr, *next = nullptr;
@@ -607,6 +545,147 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
     }
     __syncthreads();
     if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Trajectory mode with the dynamics-aware STATE cost: tau = RNEA(q, qd, qdd) of every row, the
+// effort channel of the STATE cost on it (bound hinge, squared-L2, energy (tau qd dt)^2: wp_cspace_state.py:209-275) and
+// the RNEA adjoint of d cost / d tau onto the position / velocity / acceleration gradients -- tau never leaves the SM.
+//
+// A CTA owns a CHUNK of R consecutive waypoints of one seed (R = 32 / 16 / 8, a multiple of the warp count) and alternates
+// between two mappings:
+//   dynamics phase   thread = (row r = tid % R, worker w = tid / R): the lanes of a warp are different rows walking the same
+//                    link (cb200_dynamics_tile.cuh: level-synchronous recursions, everything else over (link, row) pairs,
+//                    the row state in a transposed shared-memory tile); results stay in the tile's IO rows
+//   tile phase       the chunk's waypoints, nwarps at a time, exactly as rollout_traj_kernel (warp per waypoint, halo
+//                    waypoints either side), each row adding its dynamics terms from the IO rows.
+// Round 1 ran the recursion on lane 0 of the row's warp inside phase A: 1.26 ms vs 0.33 ms for the plain kernel on the MPC
+// workload; the host composition (three more launches, HBM round trip of the 80 B / link cache) took 0.47 ms.
+// ------------------------------------------------------------------------------------------------
+template <int SCENE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_dyn_kernel(const __grid_constant__ FusedArgs a,
+                                                                                         const int R) {
+  CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
+  __shared__ unsigned long long mbar;
+  stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
+  const RobotView rv = make_robot_view(smem, a.blob);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float *all = reinterpret_cast<float *>(smem + a.blob_smem_bytes);
+  const EvalSmem es = carve_eval_smem(all + (size_t)warp * a.eval_floats, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  float4 *halo_prev = reinterpret_cast<float4 *>(all + (size_t)nwarps * a.eval_floats);
+  float4 *halo_next = halo_prev + rv.S;
+  const int D = rv.D, S = rv.S, nl = rv.nl, RS = R + 1;
+  float *dynbase = reinterpret_cast<float *>(halo_next + S);
+  // the tree part of the model points into the shared-memory copy of the robot blob (plain loads: the read-only global path
+  // must not be used on shared addresses); the inertial parameters are the caller's arrays in global memory
+  const dyn::Model M{rv.fixed, a.dyn.masses_com, a.dyn.inertias, rv.joint_type, rv.joint_map, rv.link_map, rv.joff,
+                     a.dyn.gravity, rv.level_off, rv.level_links, nl, D, rv.n_levels};
+  const dyn::Tile<dyn::LdPlain> T{dynbase, dynbase + 5 * nl * 6 * RS, dynbase + (5 * 6 + 2) * nl * RS, nl, D, RS,
+                                  (int)threadIdx.x % R, (int)threadIdx.x / R, (int)blockDim.x / R, M};
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int chunks_per_seed = (a.H + R - 1) / R;
+  const long long n_chunks = (long long)a.B * chunks_per_seed;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int b = (int)(chunk / chunks_per_seed);
+    const int c0 = (int)(chunk - (long long)b * chunks_per_seed) * R;
+    const int rows = (a.H - c0) < R ? (a.H - c0) : R;
+    const size_t e0 = (size_t)b * a.H + c0;
+    // ---------------- dynamics phase
+    for (int i = threadIdx.x; i < R * D; i += blockDim.x) {  // coalesced: the chunk's rows are contiguous in q / vel / acc
+      const int rr = i / D, d = i - rr * D;
+      const bool ok = rr < rows;
+      const size_t gi = e0 * D + i;
+      T.IO[(0 * D + d) * RS + rr] = ok ? __ldg(a.q + gi) : 0.0f;
+      T.IO[(1 * D + d) * RS + rr] = ok ? __ldg(a.vel + gi) : 0.0f;
+      T.IO[(2 * D + d) * RS + rr] = ok ? __ldg(a.acc + gi) : 0.0f;
+      T.IO[(3 * D + d) * RS + rr] = 0.0f;
+    }
+    __syncthreads();
+    dyn::tile_rnea_forward(T);
+    {
+      const float dt = seed_dt(a, b);
+      float w_b = cfg.cspace_weight[4], w_l2 = cfg.cspace_reg[3], w_en = cfg.cspace_reg[4];
+      if (cfg.retime_regularization_weights) w_en = dt * w_en;
+      const float *lim = rv.limits;
+      for (int i = threadIdx.x; i < R * D; i += blockDim.x) {  // effort terms per (row, dof)
+        const int rr = i / D, d = i - rr * D;
+        const float tau = T.IO[(3 * D + d) * RS + rr], v = T.IO[(1 * D + d) * RS + rr];
+        float c = 0.0f, gt = 0.0f, gve = 0.0f;
+        bound_cost(tau, lim[8 * D + d], lim[9 * D + d], cfg.cspace_activation[4], w_b, c, gt);
+        l2_reg(tau, w_l2, c, gt);
+        if (w_en > 0.0f) {
+          const float ce = tau * v * dt;
+          c += w_en * ce * ce;
+          gt += 2.0f * w_en * ce * v * dt;
+          gve = 2.0f * w_en * ce * tau * dt;
+        }
+        T.IO[(3 * D + d) * RS + rr] = gt;
+        T.IO[(4 * D + d) * RS + rr] = 0.0f;
+        T.IO[(5 * D + d) * RS + rr] = gve;
+        T.IO[(6 * D + d) * RS + rr] = 0.0f;
+        T.IO[(7 * D + d) * RS + rr] = c;
+      }
+    }
+    __syncthreads();
+    dyn::tile_rnea_backward(T);
+    // ---------------- tile phase: the chunk's waypoints, nwarps at a time
+    for (int t0 = 0; t0 < rows; t0 += nwarps) {
+      const int h0 = c0 + t0;
+      const int h = h0 + warp;
+      const bool active = h < a.H;
+      int hh = -1;
+      float4 *hdst = nullptr;
+      if (warp == 0 && h0 > 0) {
+        hh = h0 - 1;
+        hdst = halo_prev;
+      } else if (warp == nwarps - 1 && h0 + nwarps < a.H) {
+        hh = h0 + nwarps;
+        hdst = halo_next;
+      }
+      if (hh >= 0) {
+        const size_t eh = (size_t)b * a.H + hh;
+        for (int d = lane; d < D; d += 32) es.qv[d] = __ldg(a.q + eh * D + d);
+        __syncwarp();
+        warp_fk(rv, es, lane);
+        const float4 *cfg_sph = row_sphere_cfg(a, b, S);
+        for (int s = lane; s < S; s += 32) {
+          const float *Tm = es.cumul + 12 * rv.sph_link[s];
+          const float4 p = cfg_sph != nullptr ? __ldg(cfg_sph + s) : rv.spheres[s];
+          hdst[s] = make_float4(Tm[0] * p.x + Tm[1] * p.y + Tm[2] * p.z + Tm[3], Tm[4] * p.x + Tm[5] * p.y + Tm[6] * p.z + Tm[7],
+                                Tm[8] * p.x + Tm[9] * p.y + Tm[10] * p.z + Tm[11], p.w);
+        }
+        __syncwarp();
+      }
+      const int e = b * a.H + h;
+      float cs_cost = 0.0f, pose_c = 0.0f;
+      RowB1 r{0.0f, 0.0f, 0.0f, 0, 0, 0};
+      if (active) {
+        row_phase_a<false>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+        const int rr = t0 + warp;  // this row's column of the dynamics tile; lane d owns dof d here and in cspace_dof
+#pragma unroll 1
+        for (int d = lane; d < D; d += 32) {
+          es.gqv[d] += T.IO[(4 * D + d) * RS + rr];
+          const float c = T.IO[(7 * D + d) * RS + rr];
+          cs_cost += c;
+          const size_t gi = (size_t)e * D + d;
+          if (a.cspace_cost) a.cspace_cost[gi] += c;
+          if (a.grad_vel) a.grad_vel[gi] += T.IO[(5 * D + d) * RS + rr];
+          if (a.grad_acc) a.grad_acc[gi] += T.IO[(6 * D + d) * RS + rr];
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      if (active) {
+        const float4 *prev = nullptr, *next = nullptr;
+        if (h > 0) prev = (warp > 0) ? reinterpret_cast<const float4 *>(all + (size_t)(warp - 1) * a.eval_floats + rv.nl * 12) : halo_prev;
+        if (h < a.H - 1) next = (warp < nwarps - 1) ? reinterpret_cast<const float4 *>(all + (size_t)(warp + 1) * a.eval_floats + rv.nl * 12) : halo_next;
+        r = row_phase_b1<true, SCENE>(a, rv, es, lane, e, b, prev, next);
+      }
+      __syncthreads();
+      if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+    }
+    __syncthreads();  // the next chunk's dynamics phase rewrites the tile the last rows just read
   }
 }
 
@@ -2569,12 +2648,58 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     if (dp->link_masses_com == nullptr || dp->link_inertias == nullptr || dp->gravity == nullptr || !traj ||
         cfg->cspace_type != 2 || a.spl.knots != nullptr || a.vel == nullptr || a.acc == nullptr)
       return ret(cudaErrorInvalidValue);
-    if (dyn_scratch_floats(h.nl, h.D) > dyn_scratch_available(h.nl, h.S)) return ret(cudaErrorInvalidConfiguration);
-    static KernelT const dyn_table[4] = {rollout_traj_kernel<0, false, true>, rollout_traj_kernel<1, false, true>,
-                                         rollout_traj_kernel<2, false, true>, rollout_traj_kernel<3, false, true>};
     a.dyn = FusedArgs::Dyn{dp->link_masses_com, dp->link_inertias, dp->gravity};
-    kern = dyn_table[scene];
-    variant = 6;
+    // chunked kernel: (warps per CTA, rows per dynamics chunk) that keeps the most warps resident; R is a multiple of the warp
+    // count so a chunk is a whole number of waypoint tiles.  Cached per (scene variant, geometry, horizon, device).
+    using DynKernelT = void (*)(const FusedArgs, const int);
+    static DynKernelT const dyn_table[4] = {rollout_traj_dyn_kernel<0>, rollout_traj_dyn_kernel<1>, rollout_traj_dyn_kernel<2>,
+                                            rollout_traj_dyn_kernel<3>};
+    DynKernelT dk = dyn_table[scene];
+    struct DynPlan {
+      long long key = -1;
+      int nw = 0, R = 0, per_sm = 0;
+      size_t smem = 0;
+    };
+    static thread_local DynPlan dplans[4];
+    DynPlan &dpl = dplans[scene];
+    const size_t halo = (size_t)2 * h.S * sizeof(float4);
+    const long long dkey = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ ((long long)io->horizon << 40) ^
+                           ((long long)(d.ordinal + 1) << 56);
+    if (dkey != dpl.key) {
+      cudaFuncAttributes fa;
+      cudaError_t e0 = cudaFuncGetAttributes(&fa, dk);
+      if (e0 != cudaSuccess) return ret(e0);
+      const size_t limit = (size_t)d.max_smem - fa.sharedSizeBytes;
+      cudaError_t e1 = cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+      if (e1 != cudaSuccess) return ret(e1);
+      double best = 0.0;
+      DynPlan cand;
+      for (int nw = kWarpsPerCta; nw >= 1; nw >>= 1) {
+        for (int R = 32; R >= 8 && R >= nw; R >>= 1) {
+          const size_t need = (size_t)h.smem_bytes + halo + (size_t)nw * a.eval_floats * sizeof(float) +
+                              (size_t)dyn::tile_floats(h.nl, h.D, R) * sizeof(float);
+          if (need > limit) continue;
+          int per_sm = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dk, nw * 32, need) != cudaSuccess || per_sm < 1) continue;
+          // resident warps, discounted for idle rows of the last tile / chunk of a trajectory and for short dynamics chunks
+          // (the recursion's serial depth is paid once per chunk whatever its width)
+          const int chunks = (io->horizon + R - 1) / R;
+          double score = (double)per_sm * nw * ((double)io->horizon / ((double)chunks * R)) * (0.75 + 0.25 * R / 32.0);
+          if (score > best) {
+            best = score;
+            cand.nw = nw, cand.R = R, cand.per_sm = per_sm, cand.smem = need;
+          }
+        }
+      }
+      if (cand.nw == 0) return ret(cudaErrorInvalidConfiguration);
+      cand.key = dkey;
+      dpl = cand;
+    }
+    long long grid_ll = (long long)d.sm_count * dpl.per_sm;
+    const long long need_ctas = (long long)io->batch_size * ((io->horizon + dpl.R - 1) / dpl.R);
+    if (grid_ll > need_ctas) grid_ll = need_ctas;
+    CB200_LAUNCH(dk, (int)(grid_ll < 1 ? 1 : grid_ll), dpl.nw * 32, dpl.smem, (cudaStream_t)stream, a, dpl.R);
+    return finish();
   }
   if (variant == 0 && arm_regcap != 0 && scene <= 1 && h.nl <= 24 && h.S <= 128) {  // ESDF variants spill at 80: -3 %
     kern = arm_table[scene];
@@ -2587,7 +2712,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     long long key = -1;
     int nw = 0, per_sm = 0;
   };
-  static thread_local Plan plans[7][4];
+  static thread_local Plan plans[6][4];
   Plan &pl = plans[variant][scene];
   const size_t halo_bytes = traj ? (size_t)2 * h.S * sizeof(float4) : 0;
   const long long key = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ (long long)minb ^

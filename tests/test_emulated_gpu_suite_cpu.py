@@ -281,11 +281,7 @@ def test_bench_dynamics_workloads_execute_and_agree(run):
     import bench
     outs = {}
     for name in ("franka_mpc_1024x30_esdf_swept_dynamics", "franka_mpc_1024x30_esdf_swept_dynamics_host", "franka_mpc_1024x30_esdf_swept"):
-        wl = bench.make_workload(name)
-        wl["B"] = 2
-        wl["q"] = wl["q"][:2]
-        wl["extra"] = {k: v[:2] for k, v in wl["extra"].items()}
-        wl["goal"] = (wl["goal"][0][:2], wl["goal"][1][:2], wl["goal"][2][:2])
+        wl = bench.shard_workload(bench.make_workload(name), 0, 2)
         wl["voxel"]["n"], wl["voxel"]["voxel"] = 64, 0.04
         eng = bench.build_engine(wl, "cpu")
         kw = {k: torch.as_tensor(v) for k, v in wl["extra"].items()}
@@ -294,7 +290,8 @@ def test_bench_dynamics_workloads_execute_and_agree(run):
     f, h, plain = (outs[k] for k in outs)
     for a_, b_ in zip(f, h):
         assert torch.allclose(a_, b_, rtol=2e-3, atol=2e-5 * float(b_.abs().max()))
-    assert not torch.allclose(f[0], plain[0])        # the effort terms are live in this workload
+    # the effort terms are live in the dynamics workloads (which keep the trajopt weights; the plain MPC workload runs lbfgs_mpc.yml)
+    assert float(f[0].sum()) > 0 and not torch.allclose(f[0], plain[0])
 
 
 def test_pending_dynamics_aware_knots(run):
