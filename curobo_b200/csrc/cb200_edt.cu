@@ -2,14 +2,16 @@
 //
 // Replaces the reference's five PBA+ launches + final copy (backends/cuda_core_backend/pba.py:60-124) with three in-place
 // passes and no transposes: z is the contiguous axis of the [nx, ny, nz] grid, so
-//   pass 1  floods along z           rows are contiguous: a warp stages 32 rows through a padded shared-memory tile,
-//   pass 2  envelopes along y        32 columns adjacent in z per warp: every row of the tile is one 128-byte line,
-//   pass 3  envelopes along x        columns adjacent in (y, z): same.
-// A warp owns a tile of 32 columns held entirely in shared memory; a lane runs the sequential column algorithm
-// (cb200_edt.cuh) on its own column at shared-memory latency -- the reference's threads walk their columns through global
-// memory, one dependent load per row -- and the only HBM traffic is one coalesced read and one coalesced write of the grid
-// per pass: 3 x 8 B per voxel (the reference moves 6 x 8 B plus its stack look-ups).  Every pass is in place (a tile is
-// fully staged before its first row is written back), so the scratch `buffer` of the reference interface is not touched.
+//   pass 1  floods along z      a WARP per row: 32 consecutive voxels per step, the nearest site on either side found with
+//                               one ballot + bit scan + shuffle per 32 voxels (no serial walk, fully coalesced),
+//   pass 2  envelopes along y   32 columns adjacent in z per CTA: every row of the shared-memory tile is one 128-byte line,
+//   pass 3  envelopes along x   columns adjacent in (y, z): same.
+// The envelope passes run the BANDED schedule of cb200_edt.cuh: a CTA of 8 warps owns a tile of 32 columns, thread
+// (band, column) builds the hull of its band's rows, one thread per column joins the band hulls by their common tangents,
+// thread (band, column) fills its band's rows.  Round 1 ran one thread per column (0.18 + 0.18 + 0.35 ms at 256^3, 6 warps
+// resident per SM: 9 % of the HBM bound).  The only HBM traffic is one coalesced read and one coalesced write of the grid per
+// pass: 3 x 8 B per voxel (the reference moves 6 x 8 B plus its stack look-ups).  Every pass is in place (a tile is fully
+// staged before its first row is written back), so the scratch `buffer` of the reference interface is not touched.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,30 +28,65 @@ inline int status(cudaError_t e) {
   return (int)e;
 }
 
-// The per-lane work of every pass lives in cb200_edt.cuh (FloodZ, Envelope<AXIS>: also executed lane by lane by the host
-// emulation in tests/hostmath); a kernel is the grid-stride loop over tiles plus the warp barriers.  One warp per CTA.
-__global__ void __launch_bounds__(kLanes) edt_flood_z_kernel(const __grid_constant__ FloodZ pass) {
-  CB200_EXTERN_SHARED int tile[];
-  const int lane = threadIdx.x;
-  const long long ntiles = pass.ntiles();
-  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    pass.load(tile, t, lane);
-    __syncwarp();
-    pass.compute(tile, t, lane);
-    __syncwarp();
-    pass.store(tile, t, lane);
-    __syncwarp();
+// pass 1.  One warp per z-row; CHUNKS x 32 >= nz.  v[c] = the row's voxels c * 32 + lane.  Forward: the last site at or
+// before a voxel = highest set bit of the chunk's site ballot at or below the lane (else the carry of the earlier chunks);
+// backward: the first site at or after it = lowest set bit at or above the lane (else the carry of the later chunks).  The
+// nearer of the two wins, ties go to the later site (flood_column's rule, i.e. the reference's backward sweep).
+template <int CHUNKS>
+__global__ void __launch_bounds__(256) edt_flood_z_kernel(int *__restrict__ grid, int nz, long long nrows) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < nrows; row += nwarps) {
+    int *p = grid + row * nz;
+    int v[CHUNKS], f[CHUNKS];
+    int carry = kEmpty;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int i = c * 32 + lane;
+      v[c] = (c * 32 < nz && i < nz) ? p[i] : -1;
+      const unsigned m = __ballot_sync(0xffffffffu, v[c] >= 0);
+      const unsigned below = m & (0xffffffffu >> (31 - lane));
+      const int src = below ? 31 - __clz((int)below) : 0;
+      const int got = __shfl_sync(0xffffffffu, v[c], src);
+      f[c] = below ? got : carry;
+      if (m) carry = __shfl_sync(0xffffffffu, v[c], 31 - __clz((int)m));
+    }
+    carry = kEmpty;
+#pragma unroll
+    for (int c = CHUNKS - 1; c >= 0; --c) {
+      const int i = c * 32 + lane;
+      const unsigned m = __ballot_sync(0xffffffffu, v[c] >= 0);
+      const unsigned above = m >> lane;
+      const int src = above ? lane + __ffs((int)above) - 1 : 0;
+      const int got = __shfl_sync(0xffffffffu, v[c], src);
+      const int nb = above ? got : carry;
+      if (m) carry = __shfl_sync(0xffffffffu, v[c], __ffs((int)m) - 1);
+      if (c * 32 < nz && i < nz) {
+        const int fw = f[c];
+        const int db = nb < 0 ? 0x7fffffff : (coord<2>(nb) > i ? coord<2>(nb) - i : i - coord<2>(nb));
+        const int df = fw < 0 ? 0x7fffffff : (coord<2>(fw) > i ? coord<2>(fw) - i : i - coord<2>(fw));
+        const int r = df < db ? fw : nb;
+        p[i] = r < 0 ? kEmpty : r;
+      }
+    }
   }
 }
 
+// passes 2 and 3: the banded schedule (cb200_edt.cuh).  The per-thread work of every phase is a member of BandedEnvelope --
+// the host emulation (tests/hostmath) executes the same members thread by thread between the same barriers.
 template <int AXIS>
-__global__ void __launch_bounds__(kLanes) edt_envelope_kernel(const __grid_constant__ Envelope<AXIS> pass) {
+__global__ void __launch_bounds__(kBands *kLanes) edt_envelope_kernel(const __grid_constant__ BandedEnvelope<AXIS> pass) {
   CB200_EXTERN_SHARED int tile[];
-  const int lane = threadIdx.x;
-  const long long ntiles = pass.ntiles();
+  const int lane = threadIdx.x & 31, band = threadIdx.x >> 5;
+  const long long ntiles = pass.e.ntiles();
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    pass.run(tile, t, lane);
-    __syncwarp();
+    pass.phase_load_and_hull(tile, t, band, lane);
+    __syncthreads();
+    pass.phase_join(tile, t, band, lane);
+    __syncthreads();
+    pass.phase_fill(tile, t, band, lane);
+    __syncthreads();
   }
 }
 
@@ -91,14 +128,24 @@ int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, in
   if (site_index == nullptr || !dims_ok(nx, ny, nz)) return status(cudaErrorInvalidValue);
   const cudaStream_t st = (cudaStream_t)stream;
   const Plan p = make_plan(site_index, nx, ny, nz);
-  const int smem_z = p.z.tile_ints() * (int)sizeof(int), smem_y = p.y.tile_ints() * (int)sizeof(int),
-            smem_x = p.x.tile_ints() * (int)sizeof(int);
-  if (!allow_smem(edt_flood_z_kernel, smem_z) || !allow_smem(edt_envelope_kernel<1>, smem_y) ||
-      !allow_smem(edt_envelope_kernel<0>, smem_x))
+  const BandedEnvelope<1> by{p.y};
+  const BandedEnvelope<0> bx{p.x};
+  const int smem_y = by.smem_ints() * (int)sizeof(int), smem_x = bx.smem_ints() * (int)sizeof(int);
+  if (!allow_smem(edt_envelope_kernel<1>, smem_y) || !allow_smem(edt_envelope_kernel<0>, smem_x))
     return status(cudaErrorInvalidConfiguration);
-  CB200_LAUNCH(edt_flood_z_kernel, grid_for(p.z.ntiles()), kLanes, smem_z, st, p.z);
-  CB200_LAUNCH(edt_envelope_kernel<1>, grid_for(p.y.ntiles()), kLanes, smem_y, st, p.y);
-  CB200_LAUNCH(edt_envelope_kernel<0>, grid_for(p.x.ntiles()), kLanes, smem_x, st, p.x);
+  const long long nrows = (long long)nx * ny;
+  const int zgrid = grid_for((nrows + 7) / 8);
+  if (nz <= 128) {
+    CB200_LAUNCH(edt_flood_z_kernel<4>, zgrid, 256, 0, st, site_index, nz, nrows);
+  } else if (nz <= 256) {
+    CB200_LAUNCH(edt_flood_z_kernel<8>, zgrid, 256, 0, st, site_index, nz, nrows);
+  } else if (nz <= 512) {
+    CB200_LAUNCH(edt_flood_z_kernel<16>, zgrid, 256, 0, st, site_index, nz, nrows);
+  } else {
+    CB200_LAUNCH(edt_flood_z_kernel<32>, zgrid, 256, 0, st, site_index, nz, nrows);
+  }
+  CB200_LAUNCH(edt_envelope_kernel<1>, grid_for(by.e.ntiles()), kBands * kLanes, smem_y, st, by);
+  CB200_LAUNCH(edt_envelope_kernel<0>, grid_for(bx.e.ntiles()), kBands * kLanes, smem_x, st, bx);
   return status(cudaGetLastError());
 }
 

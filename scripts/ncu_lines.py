@@ -46,6 +46,10 @@ def main():
     h = sec["hdr"]
     ii, ti, si = h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("Source")
     ncu = [(r[si].strip(), int(r[ii]), int(r[ti])) for r in sec["rows"] if len(r) > ii]
+    want_samples = "--samples" in sys.argv           # rank source lines by warp-stall samples (where the time goes) instead
+    if want_samples:
+        sa, sb = h.index("# Samples"), h.index("stall_barrier")
+        ncu = [(r[si].strip(), int(r[sa]), int(r[sb])) for r in sec["rows"] if len(r) > ii]
     mangled = re.sub(r"[^A-Za-z0-9_]", "", kname.split("<")[0].split("::")[-1])
     targs = re.search(re.escape(kname.split("<")[0].split("::")[-1]) + r"<([^>]*)>", sec["name"])
     tm = ""
@@ -75,6 +79,12 @@ def main():
         lanes[dis[k]] += ncu[k][2]
     tot = sum(agg.values())
     src = {f: open(os.path.join(srcdir, f)).read().split("\n") for f in os.listdir(srcdir)}
+    if want_samples:
+        print(f"kernel: {sec['name']}\nstall samples: {tot}; columns: samples, share, of which at a barrier")
+        for (f, l), c in agg.most_common(top):
+            code = src[f][l - 1].strip()[:100] if f in src and l else ""
+            print(f"{c:10d} {100 * c / tot:5.1f}% {lanes[(f, l)]:6d}  {f}:{l}  {code}")
+        return
     print(f"kernel: {sec['name']}\nwarp-instructions per eval: {tot / evals:.1f}  (total {tot}, {evals} evals)")
     print(f"{'instr/eval':>10} {'share':>6} {'lanes':>5}  source")
     for (f, l), c in agg.most_common(top):

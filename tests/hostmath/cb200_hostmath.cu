@@ -208,6 +208,22 @@ struct HostCol {
   void set(int r, int v) const { base[(long long)r * stride] = v; }
 };
 }  // namespace
+// The kernels' own schedule, emulated: `n_ctas` CTAs stride over the tiles of each envelope pass exactly like
+// edt_envelope_kernel does; the kBands x 32 threads of a CTA run one after the other between the barriers (phase by phase).
+// The z pass is the sequential statement of the warp-scan kernel (the kernel itself runs under tests/simt).
+template <int AXIS>
+static void hm_banded_pass(const ed::BandedEnvelope<AXIS> &bp, std::vector<int> &tile, int n_ctas) {
+  tile.assign((size_t)bp.smem_ints(), 0);
+  for (int cta = 0; cta < n_ctas; ++cta)
+    for (long long t = cta; t < bp.e.ntiles(); t += n_ctas) {
+      for (int band = 0; band < ed::kBands; ++band)
+        for (int lane = 0; lane < ed::kLanes; ++lane) bp.phase_load_and_hull(tile.data(), t, band, lane);
+      for (int band = 0; band < ed::kBands; ++band)
+        for (int lane = 0; lane < ed::kLanes; ++lane) bp.phase_join(tile.data(), t, band, lane);
+      for (int band = 0; band < ed::kBands; ++band)
+        for (int lane = 0; lane < ed::kLanes; ++lane) bp.phase_fill(tile.data(), t, band, lane);
+    }
+}
 extern "C" {
 void hm_pba3d(int32_t *grid, int nx, int ny, int nz) {
   std::vector<int> scratch((size_t)(nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz)));
@@ -231,22 +247,14 @@ void hm_pba3d(int32_t *grid, int nx, int ny, int nz) {
   }
 }
 
-// The kernels' own schedule, emulated: `n_ctas` one-warp CTAs stride over the tiles of each pass exactly like
-// edt_flood_z_kernel / edt_envelope_kernel do; the lanes of a warp run one after the other between the barriers.
 void hm_pba3d_tiles(int32_t *grid, int nx, int ny, int nz, int n_ctas) {
   const ed::Plan p = ed::make_plan(grid, nx, ny, nz);
-  std::vector<int> tile((size_t)std::max(p.z.tile_ints(), std::max(p.y.tile_ints(), p.x.tile_ints())));
-  for (int cta = 0; cta < n_ctas; ++cta)
-    for (long long t = cta; t < p.z.ntiles(); t += n_ctas) {
-      for (int lane = 0; lane < ed::kLanes; ++lane) p.z.load(tile.data(), t, lane);
-      for (int lane = 0; lane < ed::kLanes; ++lane) p.z.compute(tile.data(), t, lane);
-      for (int lane = 0; lane < ed::kLanes; ++lane) p.z.store(tile.data(), t, lane);
-    }
-  for (int cta = 0; cta < n_ctas; ++cta)
-    for (long long t = cta; t < p.y.ntiles(); t += n_ctas)
-      for (int lane = 0; lane < ed::kLanes; ++lane) p.y.run(tile.data(), t, lane);
-  for (int cta = 0; cta < n_ctas; ++cta)
-    for (long long t = cta; t < p.x.ntiles(); t += n_ctas)
-      for (int lane = 0; lane < ed::kLanes; ++lane) p.x.run(tile.data(), t, lane);
+  for (long long row = 0; row < p.z.nrows; ++row) {
+    HostCol c{grid + row * nz, 1};
+    ed::flood_column<2>(c, nz);
+  }
+  std::vector<int> tile;
+  hm_banded_pass(ed::BandedEnvelope<1>{p.y}, tile, n_ctas);
+  hm_banded_pass(ed::BandedEnvelope<0>{p.x}, tile, n_ctas);
 }
 }
