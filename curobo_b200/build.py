@@ -150,7 +150,23 @@ def build_reference_kernels(force: bool = False, verbose: bool = False):
     return REF_SO
 
 
+def build_reference_callsites(force: bool = False, verbose: bool = False):
+    """oracle/_ref/pyref: the reference's Python call sites of the kernel backends (cuda_ops/*.py and their import closure)
+    compiled to byte code from the sources where they lie (recipe: oracle/build_pyref.py; test infrastructure, git-ignored,
+    travels to the GPU box).  Returns the directory, or None when /root/reference is absent and nothing was built before."""
+    out = os.path.join(ROOT, "oracle", "_ref", "pyref")
+    manifest = os.path.join(out, "MANIFEST.json")
+    recipe = os.path.join(ROOT, "oracle", "build_pyref.py")
+    if not os.path.isdir(REFERENCE) or not os.path.exists(recipe):
+        return out if os.path.exists(manifest) else None
+    if not force and _newer(manifest, [recipe]):
+        return out
+    _run([sys.executable, recipe], verbose)          # own process: the recipe installs import stubs
+    return out
+
+
 def build_all(force: bool = False, verbose: bool = False):
+    build_reference_callsites(force, verbose)
     return build_product(force, verbose), build_hostmath(force, verbose), build_reference_kernels(force, verbose)
 
 

@@ -43,16 +43,19 @@ class _StubFinder(importlib.abc.MetaPathFinder):
 _ready = False
 
 
-def prepare():
+def prepare(root=None):
+    """`root`: where the `curobo` package is imported from -- the reference tree (default; authoring container only) or
+    oracle/_ref/pyref, the byte-code build of the reference's call sites that travels to the GPU box (oracle/build_pyref.py)."""
     global _ready
     if _ready:
         return
-    if not os.path.isdir(REFERENCE):
-        raise RuntimeError("the reference tree is not present: golden fixtures can only be regenerated in the authoring container")
+    root = REFERENCE if root is None else root
+    if not os.path.isdir(root):
+        raise RuntimeError(f"{root} is not present: golden fixtures can only be regenerated in the authoring container")
     import numpy  # noqa: F401
     import torch  # noqa: F401  (before the reference: its modules import torch lazily in odd orders)
     sys.path.insert(0, os.path.join(ROOT, "oracle", "warp_shim"))
-    sys.path.insert(0, REFERENCE)
+    sys.path.insert(0, root)
     sys.meta_path.append(_StubFinder())   # after the real finders: only packages that are really absent get stubbed
     _ready = True
 

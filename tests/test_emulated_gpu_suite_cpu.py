@@ -234,6 +234,19 @@ def test_pending_dynamics_state_cost(run, robot, B, H):
     run("test_gpu_zy_effort_cost", "test_dynamics_state_cost_vs_oracle", robot, B, H)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pyref", "MANIFEST.json")),
+                    reason="oracle/_ref/pyref not built")
+def test_reference_call_sites_over_b200_backend(run):
+    """The reference's own autograd Functions (byte code under oracle/_ref/pyref) over curobo_b200.backends, here over the emulated
+    library: the same test functions the GPU box runs (tests/test_gpu_reference_callsites.py)."""
+    mod = importlib.import_module("test_gpu_reference_callsites")
+    ref = mod.load_reference()
+    run("test_gpu_reference_callsites", "test_reference_kinematics_function_over_b200_backend", ref, "franka", 16)
+    run("test_gpu_reference_callsites", "test_reference_self_collision_function_over_b200_backend", ref, "franka", 12)
+    run("test_gpu_reference_callsites", "test_reference_bspline_function_over_b200_backend", ref, True)
+    run("test_gpu_reference_callsites", "test_reference_lbfgs_function_over_b200_backend", ref)
+
+
 def test_pending_edt(run):
     mod = importlib.import_module("test_gpu_zz_edt")
     from edt_cases import MEDIUM, SMALL
