@@ -100,6 +100,53 @@ __global__ void __launch_bounds__(256) edt_distance_kernel(const int *__restrict
   }
 }
 
+// The stages either side of the transform for a DENSE signed-distance source at the ESDF's own resolution (the reference reads
+// its block-sparse TSDF through a hash table at the same places: builder_esdf.py:193-404 seeding, :410-503 distance + sign).
+// sdf > 1e9 = unobserved.
+__global__ void __launch_bounds__(256) esdf_seed_sites_kernel(const float *__restrict__ sdf, int *__restrict__ sites, int ny, int nz,
+                                                               long long total, float voxel_size, float truncation) {
+  const float surface = voxel_size * 0.9f, trunc_edge = -(truncation - voxel_size * 1.1f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float d = sdf[i];
+    int out = -1;
+    if (!(d > 1e9f) && (fabsf(d) <= surface || d < trunc_edge)) {  // surface voxel or truncation boundary (builder_esdf.py:255-261)
+      const int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((long long)nz * ny));
+      out = pack(x, y, z);
+    }
+    sites[i] = out;
+  }
+}
+
+__device__ __forceinline__ float round_half_away(float v) { return v < 0.0f ? -floorf(0.5f - v) : floorf(v + 0.5f); }
+
+__global__ void __launch_bounds__(256) esdf_signed_distance_kernel(const int *__restrict__ sites, const float *__restrict__ static_sdf,
+                                                                    const float *__restrict__ combined_sdf, __half *__restrict__ out,
+                                                                    int nx, int ny, int nz, long long total, float voxel_size,
+                                                                    float skip_steps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = sites[i];
+    if (v < 0) {
+      out[i] = __float2half_rn(1e4f);
+      continue;
+    }
+    const int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((long long)nz * ny));
+    const int sx = coord<0>(v), sy = coord<1>(v), sz = coord<2>(v);
+    const float dx = (float)(x - sx), dy = (float)(y - sy), dz = (float)(z - sz);
+    const float dist_voxels = sqrtf(dx * dx + dy * dy + dz * dz);
+    float edt = dist_voxels * voxel_size;
+    float sgn_src = 1e10f;
+    if (dist_voxels > 1.0f && skip_steps > 0.0f && static_sdf != nullptr) {  // the voxel next to the site, towards the query
+      const float inv = 1.0f / dist_voxels;
+      const int ax = sx + (int)round_half_away(dx * inv * skip_steps), ay = sy + (int)round_half_away(dy * inv * skip_steps),
+                az = sz + (int)round_half_away(dz * inv * skip_steps);
+      if (ax >= 0 && ax < nx && ay >= 0 && ay < ny && az >= 0 && az < nz) sgn_src = static_sdf[((long long)ax * ny + ay) * nz + az];
+    }
+    if (sgn_src > 1e9f && combined_sdf != nullptr) sgn_src = combined_sdf[i];
+    if (!(sgn_src > 1e9f) && sgn_src < 0.0f) edt = -edt;
+    out[i] = __float2half_rn(edt);
+  }
+}
+
 template <class K>
 bool allow_smem(K kern, int smem) {
   if (smem <= 48 * 1024) return true;
@@ -158,6 +205,29 @@ int cb200_edt_unsigned_distance(const int32_t *site_index, uint16_t *distance_fp
   const long long blocks = (total + 255) / 256;
   CB200_LAUNCH(edt_distance_kernel, grid_for(blocks), 256, 0, (cudaStream_t)stream, site_index, reinterpret_cast<__half *>(distance_fp16),
                ny, nz, total, voxel_size, empty_value);
+  return status(cudaGetLastError());
+}
+
+int cb200_esdf_seed_sites(const float *combined_sdf, int32_t *site_index, int nx, int ny, int nz, float voxel_size,
+                          float truncation_distance, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(site_index);
+  if (combined_sdf == nullptr || site_index == nullptr || !dims_ok(nx, ny, nz) || !(voxel_size > 0.0f))
+    return status(cudaErrorInvalidValue);
+  const long long total = (long long)nx * ny * nz;
+  CB200_LAUNCH(esdf_seed_sites_kernel, grid_for((total + 255) / 256), 256, 0, (cudaStream_t)stream, combined_sdf, site_index, ny, nz,
+               total, voxel_size, truncation_distance);
+  return status(cudaGetLastError());
+}
+
+int cb200_esdf_signed_distance(const int32_t *site_index, const float *static_sdf, const float *combined_sdf,
+                               uint16_t *distance_fp16, int nx, int ny, int nz, float voxel_size, float adjacent_skip_steps,
+                               cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(distance_fp16);
+  if (site_index == nullptr || distance_fp16 == nullptr || !dims_ok(nx, ny, nz) || !(voxel_size > 0.0f))
+    return status(cudaErrorInvalidValue);
+  const long long total = (long long)nx * ny * nz;
+  CB200_LAUNCH(esdf_signed_distance_kernel, grid_for((total + 255) / 256), 256, 0, (cudaStream_t)stream, site_index, static_sdf,
+               combined_sdf, reinterpret_cast<__half *>(distance_fp16), nx, ny, nz, total, voxel_size, adjacent_skip_steps);
   return status(cudaGetLastError());
 }
 

@@ -7,6 +7,9 @@
                          BlockSparseESDFIntegrator._compute_esdf_impl (integrator_esdf.py:692-704) for a dense occupancy
                          grid -- the reference seeds from its block-sparse TSDF and signs the distance with it; both need
                          the TSDF hash, which is out of scope.
+  DenseESDFBuilder    <- BlockSparseESDFIntegrator._compute_esdf_impl (integrator_esdf.py:640-704: seed -> propagate -> signed
+                         distance) for a DENSE signed-distance source at the ESDF's resolution: the same three stages as
+                         three launch groups, producing the fp16 [nx, ny, nz] grid the collision kernels read (VoxelData).
 CUDA only.
 """
 from __future__ import annotations
@@ -68,3 +71,28 @@ class ParallelBandingEDT:
             out = torch.empty(self.grid_shape, dtype=torch.float16, device=self.device)
         pba_cu.launch_edt_unsigned_distance(site_index.view(-1), out.view(-1), nx, ny, nz, self.voxel_size, empty_value)
         return out
+
+
+class DenseESDFBuilder:
+    """seed -> exact nearest-site transform -> signed fp16 distance, from dense SDF grids [nx, ny, nz] float32 (> 1e9 =
+    unobserved): `combined_sdf` (seeding + sign fallback at the voxel) and `static_sdf` (sign next to the site).  All
+    buffers are allocated once; `compute` is CUDA-graph capturable.  The result is the `features` layout of VoxelData
+    (z fastest, fp16)."""
+
+    def __init__(self, grid_shape: Tuple[int, int, int], voxel_size: float, truncation_distance: float, device,
+                 adjacent_skip_steps: float = 1.0):
+        self.edt = ParallelBandingEDT(grid_shape, voxel_size, torch.device(device))
+        self.truncation_distance = float(truncation_distance)
+        self.adjacent_skip_steps = float(adjacent_skip_steps)
+        self.site_index = torch.empty(self.edt.grid_shape, dtype=torch.int32, device=self.edt.device)
+        self.dist_field = torch.empty(self.edt.grid_shape, dtype=torch.float16, device=self.edt.device)
+
+    def compute(self, combined_sdf: torch.Tensor, static_sdf: torch.Tensor = None) -> torch.Tensor:
+        nx, ny, nz = self.edt.grid_shape
+        pba_cu.launch_esdf_seed_sites(combined_sdf.view(-1), self.site_index.view(-1), nx, ny, nz, self.edt.voxel_size,
+                                      self.truncation_distance)
+        self.edt.propagate(self.site_index)
+        pba_cu.launch_esdf_signed_distance(self.site_index.view(-1), None if static_sdf is None else static_sdf.view(-1),
+                                           combined_sdf.view(-1), self.dist_field.view(-1), nx, ny, nz, self.edt.voxel_size,
+                                           self.adjacent_skip_steps)
+        return self.dist_field

@@ -95,6 +95,8 @@ _SIGS = {
     "cb200_rnea_backward": ([c_p] * 17 + [_I] * 4 + [c_p, c_p], _I),
     "cb200_pba3d": ([c_p, c_p, _I, _I, _I, _I, c_p], _I),
     "cb200_edt_unsigned_distance": ([c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),
+    "cb200_esdf_seed_sites": ([c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),
+    "cb200_esdf_signed_distance": ([c_p, c_p, c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),
     "cb200_robot_blob_bytes": ([C.POINTER(RobotSizes)], C.c_int64),
     "cb200_pack_robot_blob": ([c_p, C.c_int64, C.POINTER(RobotSizes)] + [c_p] * 15, C.c_int64),
     "cb200_rollout_cost_grad": ([C.POINTER(RolloutCfg), C.POINTER(RolloutIO), c_p], _I),

@@ -437,6 +437,21 @@ int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, in
 
 int cb200_edt_unsigned_distance(const int32_t *site_index, uint16_t *distance_fp16, int nx, int ny, int nz,
                                 float voxel_size, float empty_value, cb200_stream_t stream);
+/* The stages either side of the transform in BlockSparseESDFIntegrator._compute_esdf_impl (perception/mapper/integrator_esdf.py:
+ * 640-704) for a DENSE signed-distance source at the ESDF's own resolution ([nx, ny, nz] f32, z contiguous, > 1e9 = unobserved;
+ * the reference reads its block-sparse TSDF through a hash table at the same places):
+ *   cb200_esdf_seed_sites       <- seed_esdf_sites_gather_kernel  kernel/builder/builder_esdf.py:308-404 (seed rule :255-261):
+ *                                  site = own packed coordinates where |sdf| <= 0.9 voxel or sdf < -(truncation - 1.1 voxel),
+ *                                  -1 elsewhere (every voxel is written: no pre-clear).
+ *   cb200_esdf_signed_distance  <- compute_esdf_from_min_tsdf_kernel  builder_esdf.py:410-503: fp16(+-|voxel - site| * voxel),
+ *                                  sign from the static SDF one `adjacent_skip_steps` step from the site towards the voxel
+ *                                  (dist > 1 voxel), else from the combined SDF at the voxel, unsigned when both are
+ *                                  unobserved; fp16(1e4) where the grid has no site.  Either SDF pointer may be NULL. */
+int cb200_esdf_seed_sites(const float *combined_sdf, int32_t *site_index, int nx, int ny, int nz, float voxel_size,
+                          float truncation_distance, cb200_stream_t stream);
+int cb200_esdf_signed_distance(const int32_t *site_index, const float *static_sdf, const float *combined_sdf,
+                               uint16_t *distance_fp16, int nx, int ny, int nz, float voxel_size, float adjacent_skip_steps,
+                               cb200_stream_t stream);
 
 /* Host helper: pack robot constants (HOST pointers) into `out` (host buffer of
  * cb200_robot_blob_bytes(...) bytes) that the caller then copies to the device once.

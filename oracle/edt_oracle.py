@@ -163,3 +163,46 @@ def unsigned_distance_fp16(result, voxel_size, empty_value=1e4):
     d2 = squared_distance(result)
     d = np.sqrt(np.maximum(d2, 0).astype(np.float32)) * np.float32(voxel_size)
     return np.where(d2 < 0, np.float32(empty_value), d).astype(np.float16)
+
+
+def seed_sites_from_sdf(sdf, voxel_size, truncation):
+    """Seed rule of the ESDF builder for a dense SDF at the ESDF's resolution (builder_esdf.py:255-261, 286-300): a voxel is a
+    site when it is observed (sdf <= 1e9) and |sdf| <= 0.9 voxel (surface) or sdf < -(truncation - 1.1 voxel) (truncation
+    boundary); sites hold their own packed coordinates, everything else -1."""
+    sdf = np.asarray(sdf, np.float32)
+    vs, tr = np.float32(voxel_size), np.float32(truncation)
+    seed = ~(sdf > np.float32(1e9)) & ((np.abs(sdf) <= vs * np.float32(0.9)) | (sdf < -(tr - vs * np.float32(1.1))))
+    return seed_grid(seed)
+
+
+def _round_half_away(v):
+    return np.where(v < 0, -np.floor(np.float32(0.5) - v), np.floor(v + np.float32(0.5)))
+
+
+def signed_distance_fp16(result, static_sdf, combined_sdf, voxel_size, skip_steps=1.0):
+    """compute_esdf_from_min_tsdf_kernel (builder_esdf.py:410-503) with the TSDF hash look-ups replaced by dense arrays at the
+    ESDF's resolution: distance to the reported site, sign from the static SDF one skip step from the site towards the voxel when
+    the voxel is more than one voxel away, else / if unobserved from the combined SDF at the voxel, unsigned if that is
+    unobserved too; fp16(1e4) where no site exists.  wp.round = round half away from zero."""
+    r = np.asarray(result)
+    nx, ny, nz = r.shape
+    x, y, z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    sx, sy, sz = unpack(r)
+    dx, dy, dz = (x - sx).astype(np.float32), (y - sy).astype(np.float32), (z - sz).astype(np.float32)
+    dist = np.sqrt(dx * dx + dy * dy + dz * dz).astype(np.float32)
+    edt = (dist * np.float32(voxel_size)).astype(np.float32)
+    src = np.full(r.shape, np.float32(1e10), np.float32)
+    if static_sdf is not None and skip_steps > 0.0:
+        far = (r >= 0) & (dist > 1.0)
+        inv = np.where(far, np.float32(1.0) / np.where(far, dist, 1).astype(np.float32), 0).astype(np.float32)
+        k = np.float32(skip_steps)
+        ax = sx + _round_half_away(dx * inv * k).astype(np.int64)
+        ay = sy + _round_half_away(dy * inv * k).astype(np.int64)
+        az = sz + _round_half_away(dz * inv * k).astype(np.int64)
+        ok = far & (ax >= 0) & (ax < nx) & (ay >= 0) & (ay < ny) & (az >= 0) & (az < nz)
+        st = np.asarray(static_sdf, np.float32)
+        src = np.where(ok, st[np.clip(ax, 0, nx - 1), np.clip(ay, 0, ny - 1), np.clip(az, 0, nz - 1)], src)
+    if combined_sdf is not None:
+        src = np.where(src > 1e9, np.asarray(combined_sdf, np.float32), src)
+    signed = np.where(~(src > 1e9) & (src < 0), -edt, edt)
+    return np.where(r < 0, np.float32(1e4), signed).astype(np.float16)

@@ -139,3 +139,27 @@ def test_random_shapes_and_densities_property():
         check_result(hm_pba3d_tiles(E.seed_grid(occ), n_ctas=int(rng.integers(1, 9))), occ)
 
     run()
+
+
+def test_signed_distance_oracle_properties():
+    """The oracle's restatement of the seeding rule and of compute_esdf_from_min_tsdf_kernel on an analytic ball: seeds lie on the
+    surface shell, the signed field is negative exactly inside the ball (away from the one-voxel shell where the reference
+    looks at the voxel itself), and |field| is the exact distance to the nearest seed."""
+    n, voxel, r = 24, 0.05, 7.0
+    g = np.stack(np.meshgrid(*[np.arange(n)] * 3, indexing="ij"), -1).astype(np.float32)
+    d = (np.linalg.norm(g - (n - 1) / 2.0, axis=-1) - r).astype(np.float32)
+    trunc = 4 * voxel
+    sdf = np.clip(d * voxel, -trunc, trunc).astype(np.float32)
+    seeds = E.seed_sites_from_sdf(sdf, voxel, trunc)
+    shell = np.abs(sdf) <= np.float32(voxel) * np.float32(0.9)
+    deep = sdf < -(np.float32(trunc) - np.float32(voxel) * np.float32(1.1))
+    assert np.array_equal(seeds >= 0, shell | deep) and shell.sum() > 0 and deep.sum() > 0
+    res = E.pba3d(seeds, "zyx") if n ** 3 <= 4000 else hm_pba3d(seeds)
+    f = E.signed_distance_fp16(res, sdf, sdf, voxel, 1.0).astype(np.float32)
+    want_abs = (ndimage.distance_transform_edt(seeds < 0) * voxel).astype(np.float16).astype(np.float32)
+    assert np.array_equal(np.abs(f), want_abs)
+    clear = np.abs(d) > 1.5
+    assert ((f < 0) == (d < 0))[clear & (seeds < 0)].all()
+    unknown = np.full_like(sdf, 1e10)
+    assert (E.signed_distance_fp16(res, unknown, unknown, voxel, 1.0).astype(np.float32) >= 0).all()
+    assert (E.signed_distance_fp16(np.full((3, 3, 3), E.EMPTY, np.int32), None, None, voxel) == np.float16(1e4)).all()

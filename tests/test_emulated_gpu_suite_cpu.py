@@ -253,6 +253,8 @@ def test_pending_edt(run):
     for kind, shape, p in SMALL + MEDIUM[:4]:
         run("test_gpu_zz_edt", "test_nearest_site_transform_is_exact", kind, shape, p)
     run("test_gpu_zz_edt", "test_operator_argument_checks_emulated") if hasattr(mod, "test_operator_argument_checks_emulated") else None
+    for shape, skip in (((24, 20, 28), 1.0), ((16, 16, 16), 0.0), ((20, 31, 12), 2.0)):
+        run("test_gpu_zz_edt", "test_dense_esdf_builder_vs_oracle", shape, skip)
 
 
 @pytest.mark.skipif(os.environ.get("CB200_EMULATE_LONG") != "1", reason="~5 min of emulated launches: set CB200_EMULATE_LONG=1 (passes)")

@@ -2,7 +2,7 @@
 curobo_b200.esdf.ParallelBandingEDT) against scipy's exact EDT, the oracle and the REFERENCE's own PBA+ kernels compiled into
 oracle/_ref.  Integer work: the squared distance to the reported site must be bit exact and the reported site must be a site
 (which of several equidistant sites is reported is unspecified in the reference too).  Written after this round's GPU budget
-was spent: it has not run on a B200 yet and is ordered last in the suite for that reason."""
+was spent: first run on a B200 in round 2 (banded schedule)."""
 import numpy as np
 import pytest
 import torch
@@ -11,7 +11,7 @@ from scipy import ndimage
 import ref_kernels
 from edt_cases import MEDIUM, SMALL, occupancy
 from curobo_b200.backends import pba as pba_cu
-from curobo_b200.esdf import ParallelBandingEDT, seed_sites_from_occupancy
+from curobo_b200.esdf import DenseESDFBuilder, ParallelBandingEDT, seed_sites_from_occupancy
 from oracle import edt_oracle as E
 
 pytestmark = pytest.mark.gpu
@@ -95,3 +95,51 @@ def test_operator_argument_checks():
         pba_cu.launch_pba3d(sites, torch.empty(10, dtype=torch.int32, device=DEV), 4, 4, 4)
     with pytest.raises(ValueError):
         pba_cu.launch_pba3d(sites.float(), torch.empty(64, dtype=torch.int32, device=DEV), 4, 4, 4)
+
+
+def dense_sdf_scene(shape, voxel, seed=0, unobserved=0.15):
+    """Signed distance [m] to two balls and a slab, truncated like a TSDF, with a random unobserved region (> 1e9)."""
+    rng = np.random.default_rng(seed)
+    g = np.stack(np.meshgrid(*[np.arange(n) for n in shape], indexing="ij"), -1).astype(np.float32)
+    c1, c2 = np.array(shape, np.float32) * 0.35, np.array(shape, np.float32) * 0.7
+    r1, r2 = min(shape) * 0.22, min(shape) * 0.15
+    d = np.minimum(np.linalg.norm(g - c1, axis=-1) - r1, np.linalg.norm(g - c2, axis=-1) - r2)
+    d = np.minimum(d, np.abs(g[..., 2] - 1.0) - 0.8)                       # a thin slab near z = 1
+    sdf = (d * voxel).astype(np.float32)
+    trunc = np.float32(4.0 * voxel)
+    sdf = np.clip(sdf, -trunc, trunc)
+    combined = sdf.copy()
+    combined[rng.random(shape) < unobserved] = np.float32(1e10)
+    static = sdf.copy()
+    static[rng.random(shape) < unobserved] = np.float32(1e10)
+    return static, combined, float(trunc)
+
+
+@pytest.mark.parametrize("shape,skip", [((24, 20, 28), 1.0), ((33, 17, 40), 1.0), ((16, 16, 16), 0.0), ((20, 31, 12), 2.0)])
+def test_dense_esdf_builder_vs_oracle(shape, skip):
+    """seed -> transform -> signed distance (DenseESDFBuilder = the three stages of _compute_esdf_impl) against the oracle's
+    restatement of the seeding rule and of compute_esdf_from_min_tsdf_kernel: sites identical, signs identical, fp16 values
+    within one fp16 ulp (the kernel's sqrt / reciprocal are the fast ones)."""
+    voxel = 0.02
+    static, combined, trunc = dense_sdf_scene(shape, voxel, seed=sum(shape))
+    b = DenseESDFBuilder(shape, voxel, trunc, DEV, adjacent_skip_steps=skip)
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    field = b.compute(T(combined), T(static)).cpu().numpy()
+    torch.cuda.synchronize()
+    seeds = E.seed_sites_from_sdf(combined, voxel, trunc)
+    assert (seeds >= 0).sum() > 0
+    res = b.site_index.cpu().numpy()
+    assert np.array_equal(E.squared_distance(res), E.squared_distance(E.pba3d(seeds, "zyx")) if np.prod(shape) <= 4000 else
+                          np.rint(ndimage.distance_transform_edt(seeds < 0) ** 2).astype(np.int64))
+    want = E.signed_distance_fp16(res, static, combined, voxel, skip)
+    gf, wf = field.astype(np.float32), want.astype(np.float32)
+    assert np.array_equal(np.sign(gf), np.sign(wf)), f"{int((np.sign(gf) != np.sign(wf)).sum())} signs differ"
+    assert np.abs(gf - wf).max() <= 2e-3 * max(1.0, float(np.abs(wf).max()))
+    assert (wf < 0).sum() > 0 and (wf > 0).sum() > 0, "the scene must have an inside and an outside"
+    # unsigned variant: no SDF at all
+    b2 = DenseESDFBuilder(shape, voxel, trunc, DEV)
+    from curobo_b200.backends import pba as pba_cu2
+    out = torch.empty(shape, dtype=torch.float16, device=DEV)
+    pba_cu2.launch_esdf_signed_distance(b.site_index.view(-1), None, None, out.view(-1), *shape, voxel, 1.0)
+    assert np.array_equal(np.abs(gf) >= 0, np.ones(shape, bool)) and (out.cpu().numpy().astype(np.float32) >= 0).all()
+    assert b2.dist_field.shape == tuple(shape)
