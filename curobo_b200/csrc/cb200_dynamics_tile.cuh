@@ -25,6 +25,15 @@ constexpr int kTileIo = 8;
 __host__ __device__ inline int tile_floats(int nl, int D, int R) { return (5 * 6 * nl + 2 * nl + kTileIo * D) * (R + 1); }
 
 #if defined(__CUDACC__) || defined(CB200_SIMT_EMULATION)
+// who meets at the phase boundaries: the whole CTA (every thread runs the tile functions) or one warp (a producer warp runs
+// them alone while the other warps of the CTA do something else)
+struct SyncCta {
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+struct SyncWarp {
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
 template <class L>
 struct Tile {
   float *T, *SC, *IO;
@@ -47,8 +56,8 @@ struct Tile {
 };
 
 // tau = RNEA(q, qd, qdd) of every row of the tile.  In: IO 0..2; IO 3 must be zero.  Out: IO 3 = tau; T 0/1/2 = v, a, f.
-// Called by every thread of the CTA; ends with a barrier.
-template <class L>
+// Called by every thread of the Sync group (CTA or warp); ends with a barrier of that group.
+template <class Sync, class L>
 __device__ __forceinline__ void tile_rnea_forward(const Tile<L> &S) {
   const Model &M = S.M;
   const int nl = S.nl, W = S.W;
@@ -63,7 +72,7 @@ __device__ __forceinline__ void tile_rnea_forward(const Tile<L> &S) {
     S.SC[(k * 2 + 0) * S.RS + S.r] = jt >= 3 ? sn : qe;
     S.SC[(k * 2 + 1) * S.RS + S.r] = cs;
   }
-  __syncthreads();
+  Sync::sync();
   for (int lv = 0; lv < M.n_levels; ++lv) {  // root -> leaves: v, a
     for (int idx = M.level_starts[lv] + S.w; idx < M.level_starts[lv + 1]; idx += W) {
       const int k = M.level_links[idx], jt = M.joint_type[k], ji = M.joint_map[k], par = M.link_map[k];
@@ -91,7 +100,7 @@ __device__ __forceinline__ void tile_rnea_forward(const Tile<L> &S) {
       S.store(0, k, v);
       S.store(1, k, ac);
     }
-    __syncthreads();
+    Sync::sync();
   }
   for (int k = S.w; k < nl; k += W) {  // every (link, row): f = I a + v x* (I v)
     float v[6], ac[6], Ia[6], Iv[6], x[6];
@@ -104,7 +113,7 @@ __device__ __forceinline__ void tile_rnea_forward(const Tile<L> &S) {
     for (int i = 0; i < 6; ++i) Ia[i] += x[i];
     S.store(2, k, Ia);
   }
-  __syncthreads();
+  Sync::sync();
   for (int lv = M.n_levels - 2; lv >= 0; --lv) {  // leaves -> root: a link pulls its children's wrenches
     const int c0 = M.level_starts[lv + 1], c1 = M.level_starts[lv + 2];
     for (int idx = M.level_starts[lv] + S.w; idx < c0; idx += W) {
@@ -125,18 +134,18 @@ __device__ __forceinline__ void tile_rnea_forward(const Tile<L> &S) {
       }
       if (any) S.store(2, k, f);
     }
-    __syncthreads();
+    Sync::sync();
   }
   for (int k = S.w; k < nl; k += W) {  // joint torques (several links share a joint only through mimic joints)
     const int jt = M.joint_type[k], ji = M.joint_map[k];
     if (jt >= 0 && ji >= 0) atomicAdd(&S.io(3, ji), L::f(M.joint_offset + 2 * k) * S.at(2, k, s_index(jt)));
   }
-  __syncthreads();
+  Sync::sync();
 }
 
 // Adjoint.  In: IO 0 (q), 1 (qd), 3 (d cost / d tau), T 0/1/2 from tile_rnea_forward; IO 4..6 hold the values the three
 // gradients are ADDED to (zero, or terms the caller already owns).  Out: IO 4 / 5 / 6 += grad_q / grad_qd / grad_qdd.
-template <class L>
+template <class Sync, class L>
 __device__ __forceinline__ void tile_rnea_backward(const Tile<L> &S) {
   const Model &M = S.M;
   const int nl = S.nl, W = S.W;
@@ -164,7 +173,7 @@ __device__ __forceinline__ void tile_rnea_backward(const Tile<L> &S) {
       S.store(2, k, fbar);
       S.at(3, k, 0) = gq1;
     }
-    __syncthreads();
+    Sync::sync();
   }
   for (int k = S.w; k < nl; k += W) {  // every (link, row): the adjoint terms that do not involve the children
     const float *mc = M.masses_com + 4 * k, *in = M.inertias + 8 * k;
@@ -185,7 +194,7 @@ __device__ __forceinline__ void tile_rnea_backward(const Tile<L> &S) {
     S.store(4, k, vb);
     S.at(2, k, 0) = gq1;
   }
-  __syncthreads();
+  Sync::sync();
   for (int lv = M.n_levels - 1; lv >= 0; --lv) {  // leaves -> root: a link pulls its children's a_bar, v_bar
     const int c0 = M.level_starts[lv + 1], c1 = (lv + 1 < M.n_levels) ? M.level_starts[lv + 2] : c0;
     for (int idx = M.level_starts[lv] + S.w; idx < c0; idx += W) {
@@ -215,7 +224,7 @@ __device__ __forceinline__ void tile_rnea_backward(const Tile<L> &S) {
       S.store(3, k, ab);
       S.store(4, k, vb);
     }
-    __syncthreads();
+    Sync::sync();
   }
   for (int k = S.w; k < nl; k += W) {  // every moving (link, row): the three joint-space gradients
     const int jt = M.joint_type[k], ji = M.joint_map[k], par = M.link_map[k];
@@ -247,7 +256,7 @@ __device__ __forceinline__ void tile_rnea_backward(const Tile<L> &S) {
     atomicAdd(&S.io(5, ji), gqd);
     atomicAdd(&S.io(6, ji), gqdd);
   }
-  __syncthreads();
+  Sync::sync();
 }
 #endif  // __CUDACC__ || CB200_SIMT_EMULATION
 
