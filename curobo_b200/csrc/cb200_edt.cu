@@ -28,48 +28,66 @@ inline int status(cudaError_t e) {
   return (int)e;
 }
 
-// pass 1.  One warp per z-row; CHUNKS x 32 >= nz.  v[c] = the row's voxels c * 32 + lane.  Forward: the last site at or
+// pass 1.  A warp per z-row; CHUNKS x 32 >= nz.  v[c] = the row's voxels c * 32 + lane.  Forward: the last site at or
 // before a voxel = highest set bit of the chunk's site ballot at or below the lane (else the carry of the earlier chunks);
 // backward: the first site at or after it = lowest set bit at or above the lane (else the carry of the later chunks).  The
 // nearer of the two wins, ties go to the later site (flood_column's rule, i.e. the reference's backward sweep).
+template <int CHUNKS>
+__device__ __forceinline__ void flood_row_load(const int *p, int nz, int lane, int (&v)[CHUNKS]) {
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int i = c * 32 + lane;
+    v[c] = (c * 32 < nz && i < nz) ? p[i] : -1;
+  }
+}
+template <int CHUNKS>
+__device__ __forceinline__ void flood_row_solve(int *p, int nz, int lane, const int (&v)[CHUNKS]) {
+  int f[CHUNKS];
+  int carry = kEmpty;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const unsigned m = __ballot_sync(0xffffffffu, v[c] >= 0);
+    const unsigned below = m & (0xffffffffu >> (31 - lane));
+    const int src = below ? 31 - __clz((int)below) : 0;
+    const int got = __shfl_sync(0xffffffffu, v[c], src);
+    f[c] = below ? got : carry;
+    if (m) carry = __shfl_sync(0xffffffffu, v[c], 31 - __clz((int)m));
+  }
+  carry = kEmpty;
+#pragma unroll
+  for (int c = CHUNKS - 1; c >= 0; --c) {
+    const int i = c * 32 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, v[c] >= 0);
+    const unsigned above = m >> lane;
+    const int src = above ? lane + __ffs((int)above) - 1 : 0;
+    const int got = __shfl_sync(0xffffffffu, v[c], src);
+    const int nb = above ? got : carry;
+    if (m) carry = __shfl_sync(0xffffffffu, v[c], __ffs((int)m) - 1);
+    if (c * 32 < nz && i < nz) {
+      const int fw = f[c];
+      const int db = nb < 0 ? 0x7fffffff : (coord<2>(nb) > i ? coord<2>(nb) - i : i - coord<2>(nb));
+      const int df = fw < 0 ? 0x7fffffff : (coord<2>(fw) > i ? coord<2>(fw) - i : i - coord<2>(fw));
+      const int r = df < db ? fw : nb;
+      p[i] = r < 0 ? kEmpty : r;
+    }
+  }
+}
+// A warp takes TWO rows per step (both rows' loads in flight before either is solved): the pass is a pure stream, and the loads
+// in flight per SM are what bound it.
 template <int CHUNKS>
 __global__ void __launch_bounds__(256) edt_flood_z_kernel(int *__restrict__ grid, int nz, long long nrows) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = warp0; row < nrows; row += nwarps) {
-    int *p = grid + row * nz;
-    int v[CHUNKS], f[CHUNKS];
-    int carry = kEmpty;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-      const int i = c * 32 + lane;
-      v[c] = (c * 32 < nz && i < nz) ? p[i] : -1;
-      const unsigned m = __ballot_sync(0xffffffffu, v[c] >= 0);
-      const unsigned below = m & (0xffffffffu >> (31 - lane));
-      const int src = below ? 31 - __clz((int)below) : 0;
-      const int got = __shfl_sync(0xffffffffu, v[c], src);
-      f[c] = below ? got : carry;
-      if (m) carry = __shfl_sync(0xffffffffu, v[c], 31 - __clz((int)m));
-    }
-    carry = kEmpty;
-#pragma unroll
-    for (int c = CHUNKS - 1; c >= 0; --c) {
-      const int i = c * 32 + lane;
-      const unsigned m = __ballot_sync(0xffffffffu, v[c] >= 0);
-      const unsigned above = m >> lane;
-      const int src = above ? lane + __ffs((int)above) - 1 : 0;
-      const int got = __shfl_sync(0xffffffffu, v[c], src);
-      const int nb = above ? got : carry;
-      if (m) carry = __shfl_sync(0xffffffffu, v[c], __ffs((int)m) - 1);
-      if (c * 32 < nz && i < nz) {
-        const int fw = f[c];
-        const int db = nb < 0 ? 0x7fffffff : (coord<2>(nb) > i ? coord<2>(nb) - i : i - coord<2>(nb));
-        const int df = fw < 0 ? 0x7fffffff : (coord<2>(fw) > i ? coord<2>(fw) - i : i - coord<2>(fw));
-        const int r = df < db ? fw : nb;
-        p[i] = r < 0 ? kEmpty : r;
-      }
-    }
+  for (long long row = 2 * warp0; row < nrows; row += 2 * nwarps) {
+    int *p0 = grid + row * nz;
+    const bool two = row + 1 < nrows;  // warp-uniform
+    int *p1 = two ? p0 + nz : p0;
+    int v0[CHUNKS], v1[CHUNKS];
+    flood_row_load<CHUNKS>(p0, nz, lane, v0);
+    if (two) flood_row_load<CHUNKS>(p1, nz, lane, v1);
+    flood_row_solve<CHUNKS>(p0, nz, lane, v0);
+    if (two) flood_row_solve<CHUNKS>(p1, nz, lane, v1);
   }
 }
 
@@ -181,7 +199,7 @@ int cb200_pba3d(int32_t *site_index, int32_t *buffer, int nx, int ny, int nz, in
   if (!allow_smem(edt_envelope_kernel<1>, smem_y) || !allow_smem(edt_envelope_kernel<0>, smem_x))
     return status(cudaErrorInvalidConfiguration);
   const long long nrows = (long long)nx * ny;
-  const int zgrid = grid_for((nrows + 7) / 8);
+  const int zgrid = grid_for((nrows + 15) / 16);  // 8 warps per CTA, two rows per warp and step
   if (nz <= 128) {
     CB200_LAUNCH(edt_flood_z_kernel<4>, zgrid, 256, 0, st, site_index, nz, nrows);
   } else if (nz <= 256) {

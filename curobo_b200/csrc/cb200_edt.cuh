@@ -226,6 +226,12 @@ CB_HD bool hull_dominated(const HullPoint &a, const HullPoint &u, const HullPoin
   return (long long)(u.g - a.g) * (long long)(c.r - u.r) > (long long)(c.g - u.g) * (long long)(u.r - a.r);
 }
 
+// The same test inside one band: row differences are at most ceil(1023 / kBands) = 128 and g differences below 3.2e6
+// (g = r^2 + h <= 3 * 1023^2), so both products stay under 2^31 and plain 32-bit multiplies are exact.
+CB_HD bool hull_dominated_in_band(const HullPoint &a, const HullPoint &u, const HullPoint &c) {
+  return (u.g - a.g) * (c.r - u.r) > (c.g - u.g) * (u.r - a.r);
+}
+
 // step 1: hull of rows [r0, r1), written to positions r0 .. r0 + m - 1; returns m
 template <int AXIS, class Col>
 CB_HD int band_hull(Col &c, int r0, int r1, const Voxel &q) {
@@ -235,7 +241,7 @@ CB_HD int band_hull(Col &c, int r0, int r1, const Voxel &q) {
     const int v = c.get(r);
     if (v < 0) continue;
     const HullPoint p{r, r * r + off_axis_sq<AXIS>(v, q)};
-    while (m >= 2 && hull_dominated(below, top, p)) {
+    while (m >= 2 && hull_dominated_in_band(below, top, p)) {
       --m;
       top = below;
       if (m >= 2) below = hull_point<AXIS>(c, r0 + m - 2, q);

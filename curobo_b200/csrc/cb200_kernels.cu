@@ -74,6 +74,8 @@ struct FusedArgs {
   // link-sphere configurations (a2, num_envs > 1): [n_cfg, S] float4 in global memory; null = the blob's set
   const float4 *sphere_cfgs;
   int32_t n_sphere_cfgs;
+  // big-robot kernel: row ticket counter [2] (zero between launches; null = static striding)
+  int32_t *work_counter;
 };
 
 // link-frame sphere set of seed b: the blob's (shared memory) unless the caller passed several configurations
@@ -479,6 +481,196 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
     const RowB1 r = phase_b1_ool<SCENE>(&a, smem, base, lane, e, b);
     phase_b2_ool(&a, smem, base, lane, e, r, pa.cs_cost, pa.pose_c);
 #endif
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE fused kernel for big robots (humanoids), discrete scene collision.  Same phases and arithmetic as rollout_fused_kernel;
+// what changes is how many rows an SM keeps in flight.  The kernel is latency bound (profiles/r02: issue slots 30 % busy, 2.3
+// warps per scheduler, no pipe above 40 %) and shared memory caps the resident warps: a G1-29 row is 17.3 KB, of which 12.8 KB
+// are two [S] float4 arrays -- the padded copy of the spheres for the pair phase and the dense sphere gradients.  Here
+//   * the pair phase rebuilds padded radii from the padding table (one extra shared load per sphere read),
+//   * sphere gradients go to a short list (the spheres that collide are a handful) that feeds the sparse J^T directly; a row
+//     that overflows the list drains it into per-link force / torque accumulators and finishes with the dense up-sweep,
+//   * one CTA of up to 16 warps per SM (the robot blob is staged once), rows handed out by a ticket counter instead of
+//     static striding (rows differ in cost; 8192 rows over 2368 warps is 3.5 rounds: the last one is half empty otherwise).
+// Row: 10.9 KB (G1-29), 16.4 KB (G1-43) -> 16 / 11 rows in flight per SM instead of 10 / 7.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBigWarps = 16;
+
+template <int SCENE>
+__device__ __forceinline__ RowB1 row_phase_b1_list(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
+                                                   int b, int &n_list, bool &dense) {
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int S = rv.S;
+  RowB1 r{0.0f, 0.0f, 0.0f, 0, 0, 0};
+  n_list = 0;
+  dense = false;
+  if (cfg.self_weight > 0.0f && rv.P > 0) {
+    r.fmax = warp_self_collision_tiles<false>(rv, es, lane, r.bi, r.bj);
+    r.self_c = (r.fmax > 0.0f) ? 0.5f * cfg.self_weight * r.fmax : 0.0f;
+  }
+  if (a.self_cost && lane == 0) a.self_cost[e] = r.self_c;
+  __syncwarp();
+  const bool do_scene = SCENE != 0 && cfg.scene_weight > 0.0f;
+  const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
+  int ce = 0, ncub = 0;
+  bool cull = false;
+  if ((SCENE & 1) && do_scene) {  // cuboid broad phase, as in row_phase_b1
+    ce = env < a.cuboids.num_envs ? env : 0;
+    ncub = a.cuboids.count[ce];
+    if (ncub > a.cuboids.max_n) ncub = a.cuboids.max_n;
+    cull = rv.n_lp > 0 && ncub <= 32;
+    if (cull) {
+#pragma unroll 1
+      for (int ca = lane; ca < rv.n_cl; ca += 32) {
+        const float4 cb = rv.cl_bound_scene[ca];
+        uint32_t mask = 0u;
+        if (cb.w >= 0.0f) {
+          const float *Tk = es.cumul + 12 * rv.cl_link[ca];
+          const V3 cw = mk3(Tk[0] * cb.x + Tk[1] * cb.y + Tk[2] * cb.z + Tk[3], Tk[4] * cb.x + Tk[5] * cb.y + Tk[6] * cb.z + Tk[7],
+                            Tk[8] * cb.x + Tk[9] * cb.y + Tk[10] * cb.z + Tk[11]);
+#pragma unroll 1
+          for (int i = 0; i < ncub; ++i) {
+            const int kk = ce * a.cuboids.max_n + i;
+            if (a.cuboids.enable[kk] != 1) continue;
+            const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
+            const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cw) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                                               ldgf(a.cuboids.dims + 4 * kk + 2));
+            if (sg.sdf < cb.w + cfg.scene_activation) mask |= (1u << i);
+          }
+        }
+        es.cmask[ca] = mask;
+      }
+      __syncwarp();
+    }
+  }
+  bool ft_live = false;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int base = 0; base < S; base += 32) {  // uniform trip count: the list append below is a warp collective
+    const int s = base + lane;
+    V3 g = mk3(0, 0, 0);
+    float c = 0.0f;
+    if (s < S && do_scene) {
+      const float4 sp = es.sph[s];
+      const V3 cen = mk3(sp.x, sp.y, sp.z);
+      if (sp.w >= 0.0f) {
+        if (SCENE & 1) {
+          uint32_t m = cull ? es.cmask[rv.sph_cl[s]] : 0xffffffffu;
+          const float radj = sp.w + cfg.scene_activation;
+#pragma unroll 1
+          for (int i = 0; i < ncub && m != 0u; ++i) {
+            if (cull && !((m >> i) & 1u)) continue;
+            if (cull) m &= ~(1u << i);
+            const int kk = ce * a.cuboids.max_n + i;
+            if (a.cuboids.enable[kk] != 1) continue;
+            const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
+            const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cen) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                                               ldgf(a.cuboids.dims + 4 * kk + 2));
+            const float pen = radj - sg.sdf;
+            if (pen > 0.0f) {
+              float ac, as;
+              collision_activation(pen, cfg.scene_activation, ac, as);
+              c += cfg.scene_weight * ac;
+              g = g + (cfg.scene_weight * as) * qrot(qconj(f.q), sg.n);
+            }
+          }
+        }
+        if (SCENE & 2) {
+          const CuboidSet none{};
+          c += sphere_scene_discrete<2>(cen, sp.w, cfg.scene_activation, cfg.scene_weight, none, a.voxels, env, g);
+        }
+      }
+    }
+    const bool nz = (g.x != 0.0f) || (g.y != 0.0f) || (g.z != 0.0f);
+    const unsigned m = __ballot_sync(kFull, nz);
+    if (m) {
+      const int cnt = __popc(m);
+      if (n_list + cnt > kGradListCap - 2) {  // (two slots stay free for the self-collision pair)
+        if (!ft_live) {
+          warp_zero_ft(rv, es, lane);
+          ft_live = true;
+        }
+        warp_drain_list_to_ft(rv, es, lane, n_list);
+        n_list = 0;
+        dense = true;
+      }
+      if (nz) es.glist[n_list + __popc(m & lt)] = make_float4(g.x, g.y, g.z, __int_as_float(s));
+      n_list += cnt;
+      __syncwarp();
+    }
+    r.scene_c += c;
+    if (a.scene_cost && s < S) a.scene_cost[(size_t)e * S + s] = c;
+  }
+  if (dense && !ft_live) warp_zero_ft(rv, es, lane);
+  return r;
+}
+
+__device__ __forceinline__ void row_phase_b2_list(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
+                                                  const RowB1 &r, float cs_cost, float pose_c, int n_list, bool dense) {
+  if (r.fmax > 0.0f) {  // the worst pair's gradient: two more list entries
+    if (lane == 0) {
+      const float4 pi = es.sph[r.bi], pj = es.sph[r.bj];
+      const float w = a.cfg.self_weight;
+      const float gx = w * (pj.x - pi.x), gy = w * (pj.y - pi.y), gz = w * (pj.z - pi.z);
+      es.glist[n_list] = make_float4(gx, gy, gz, __int_as_float(r.bi));
+      es.glist[n_list + 1] = make_float4(-gx, -gy, -gz, __int_as_float(r.bj));
+    }
+    n_list += 2;
+    __syncwarp();
+  }
+  float *gq = a.grad_q + (size_t)e * rv.D;
+  if (!dense) {
+    warp_fk_backward_list(rv, es, lane, gq, n_list);
+  } else {
+    warp_drain_list_to_ft(rv, es, lane, n_list);
+    warp_fk_backward_from_ft(rv, es, lane, gq);
+  }
+  const float tot = warp_sum(cs_cost + pose_c + r.scene_c) + r.self_c;
+  if (lane == 0) a.cost[e] = tot;
+  __syncwarp();
+}
+
+template <int SCENE>
+__global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_big_kernel(const __grid_constant__ FusedArgs a) {
+  CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
+  __shared__ unsigned long long mbar;
+  stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float *base = reinterpret_cast<float *>(smem + a.blob_smem_bytes) + (size_t)warp * a.eval_floats;
+  const RobotView rv = make_robot_view(smem, a.blob);
+  const EvalSmem es = carve_big_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  const int N = a.B * a.H;
+  const int total_warps = gridDim.x * nwarps;
+  int e = blockIdx.x * nwarps + warp;  // first row: static; afterwards rows come from the ticket counter
+  while (e < N) {
+    int b = e, h = 0;
+    if (a.H != 1) {
+      b = e / a.H;
+      h = e - b * a.H;
+    }
+    float cs_cost = 0.0f, pose_c = 0.0f;
+    row_phase_a<false>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
+    int n_list;
+    bool dense;
+    const RowB1 r = row_phase_b1_list<SCENE>(a, rv, es, lane, e, b, n_list, dense);
+    row_phase_b2_list(a, rv, es, lane, e, r, cs_cost, pose_c, n_list, dense);
+    if (a.work_counter != nullptr) {
+      int nxt = 0;
+      if (lane == 0) nxt = total_warps + atomicAdd(a.work_counter, 1);
+      e = __shfl_sync(kFull, nxt, 0);
+    } else {
+      e += total_warps;
+    }
+  }
+  // the last warp to leave re-arms the counter for the next launch on this stream
+  if (a.work_counter != nullptr && lane == 0) {
+    __threadfence();
+    if (atomicAdd(a.work_counter + 1, 1) == total_warps - 1) {
+      a.work_counter[0] = 0;
+      a.work_counter[1] = 0;
+    }
   }
 }
 
@@ -2664,6 +2856,64 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       if (g > n_tiles) g = n_tiles;
       CB200_LAUNCH(tk, (int)g, kWarpsPerCta * 32, tl.total_bytes, (cudaStream_t)stream, a);
       return launch_status();
+    }
+  }
+  // big robots (humanoids), discrete mode: the list-based kernel with up to 16 warps per SM (see rollout_fused_big_kernel).
+  // CB200_BIG = 0 / 1 forces it off / on (default: on when a row of the standard layout exceeds 8 KB).
+  const char *big_str = getenv("CB200_BIG");  // read per call: tests switch it inside one process
+  const int big_env = big_str ? atoi(big_str) : -1;
+  const bool big_fit = !traj && a.spl.knots == nullptr && h.n_lp > 0 && h.P > 0;
+  const bool big_want = big_env >= 0 ? big_env != 0 : (size_t)a.eval_floats * sizeof(float) > 8192;
+  if (big_fit && big_want) {
+    static KernelT const big_table[4] = {rollout_fused_big_kernel<0>, rollout_fused_big_kernel<1>, rollout_fused_big_kernel<2>,
+                                         rollout_fused_big_kernel<3>};
+    KernelT bk = big_table[scene];
+    struct BigPlan {
+      long long key = -1;
+      int nw = 0, per_sm = 0;
+    };
+    static thread_local BigPlan bplans[4];
+    BigPlan &bp = bplans[scene];
+    const int big_floats = big_smem_floats(h.nl, h.D, h.S, h.L, h.n_cl);
+    const long long bkey = ((long long)h.smem_bytes << 32) ^ ((long long)big_floats << 8) ^ ((long long)(d.ordinal + 1) << 56);
+    if (bkey != bp.key) {
+      cudaFuncAttributes fa;
+      cudaError_t e0 = cudaFuncGetAttributes(&fa, bk);
+      if (e0 != cudaSuccess) return ret(e0);
+      const size_t limit = (size_t)d.max_smem - fa.sharedSizeBytes;
+      cudaError_t e1 = cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+      if (e1 != cudaSuccess) return ret(e1);
+      static const int force_nw = []() {
+        const char *e = getenv("CB200_FORCE_NW");
+        return e ? atoi(e) : 0;
+      }();
+      int best = 0;
+      BigPlan cand;
+      for (int nw = kBigWarps; nw >= 1; --nw) {
+        if (force_nw > 0 && nw != force_nw) continue;
+        const size_t need = (size_t)h.smem_bytes + (size_t)nw * big_floats * sizeof(float);
+        if (need > limit) continue;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk, nw * 32, need) != cudaSuccess || per_sm < 1) continue;
+        if (per_sm * nw > best) {
+          best = per_sm * nw;
+          cand.nw = nw, cand.per_sm = per_sm;
+        }
+      }
+      if (cand.nw > 0) {
+        cand.key = bkey;
+        bp = cand;
+      }
+    }
+    if (bp.key == bkey) {
+      a.eval_floats = big_floats;
+      a.work_counter = io->work_counter;
+      const size_t smem_b = (size_t)h.smem_bytes + (size_t)bp.nw * big_floats * sizeof(float);
+      long long g = (long long)d.sm_count * bp.per_sm;
+      const long long need_ctas = (N + bp.nw - 1) / bp.nw;
+      if (g > need_ctas) g = need_ctas;
+      CB200_LAUNCH(bk, (int)(g < 1 ? 1 : g), bp.nw * 32, smem_b, (cudaStream_t)stream, a);
+      return finish();
     }
   }
   int variant = (traj ? 1 : 0) + (a.spl.knots != nullptr ? 3 : 0);

@@ -96,6 +96,7 @@ struct EvalSmem {
   float *pose_g;  // [L*8]  g_pos.xyz,_, omega.xyz,_
   float4 *bc;     // [n_cl] world-frame bounding spheres of the collision links (self-collision broad phase)
   uint32_t *cmask;  // [n_cl] scene broad phase: bit i set <=> cuboid i may touch a sphere of the link
+  float4 *glist;    // big-robot layout only: (g.xyz, sphere index) of the spheres with a non-zero gradient; gsph == nullptr there
 };
 __host__ __device__ inline int eval_smem_floats(int nl, int D, int S, int L, int n_cl) {
   int n = nl * 12 + S * 8 + nl * 8 + n_cl * 4;   // float4-aligned part
@@ -110,6 +111,32 @@ __device__ __forceinline__ EvalSmem carve_eval_smem(float *base, int nl, int D, 
   e.ft = base + nl * 12 + S * 8;
   e.bc = reinterpret_cast<float4 *>(e.ft + nl * 8);
   e.contrib = e.ft + nl * 8 + n_cl * 4;
+  e.qv = e.contrib + nl;
+  e.gqv = e.qv + D;
+  e.pose_g = e.gqv + D;
+  e.cmask = reinterpret_cast<uint32_t *>(e.pose_g + L * 8);
+  e.glist = nullptr;
+  return e;
+}
+
+// Row state of the big-robot kernel (humanoids): no dense sphere-gradient array and no padded sphere copy -- the two [S] float4
+// arrays that make a humanoid row 17-27 KB -- but a short list of the spheres that actually carry a gradient.  6.4 KB less per
+// row for G1-29, 10.8 KB for G1-43: 16 instead of 10 resident rows per SM.
+constexpr int kGradListCap = 96;
+__host__ __device__ inline int big_smem_floats(int nl, int D, int S, int L, int n_cl) {
+  int n = nl * 12 + S * 4 + nl * 8 + n_cl * 4 + kGradListCap * 4;  // float4-aligned part
+  n += nl + D + D + L * 8 + n_cl;
+  return (n + 3) & ~3;
+}
+__device__ __forceinline__ EvalSmem carve_big_smem(float *base, int nl, int D, int S, int L, int n_cl) {
+  EvalSmem e;
+  e.cumul = base;
+  e.sph = reinterpret_cast<float4 *>(base + nl * 12);
+  e.gsph = nullptr;
+  e.ft = base + nl * 12 + S * 4;
+  e.bc = reinterpret_cast<float4 *>(e.ft + nl * 8);
+  e.glist = e.bc + n_cl;
+  e.contrib = reinterpret_cast<float *>(e.glist + kGradListCap);
   e.qv = e.contrib + nl;
   e.gqv = e.qv + D;
   e.pose_g = e.gqv + D;
@@ -129,10 +156,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Reference semantics: kinematics_forward_helper.cuh:316-512.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es, int lane) {
-  // local transforms go to a scratch buffer (the not-yet-used sphere-gradient area) when it is large enough,
+  // local transforms go to a scratch buffer (the not-yet-written world-sphere area) when it is large enough,
   // so a compose step needs one warp barrier instead of two; otherwise they are composed in place.
   const bool scratch = rv.S * 4 >= rv.nl * 12;
-  float *loc = scratch ? reinterpret_cast<float *>(es.gsph) : es.cumul;
+  float *loc = scratch ? reinterpret_cast<float *>(es.sph) : es.cumul;
   #pragma unroll 1
   for (int l = lane; l < rv.nl; l += 32) {
     int jt = rv.joint_type[l];
@@ -184,8 +211,10 @@ __device__ __forceinline__ void warp_spheres(const RobotView &rv, const EvalSmem
     w.w = p.w;
     es.sph[s] = w;
     if (out_global != nullptr) out_global[s] = w;
-    w.w = p.w + rv.padding[s];
-    es.gsph[s] = w;
+    if (es.gsph != nullptr) {
+      w.w = p.w + rv.padding[s];
+      es.gsph[s] = w;
+    }
   }
 }
 
@@ -233,6 +262,16 @@ __device__ __forceinline__ float warp_self_collision_pairs(const float4 *psph, c
 // is identical to scanning the whole list.  Lanes test 32 link pairs at a time; surviving blocks are scanned
 // with lanes over the flattened |a| x |b| tile.
 // ----------------------------------------------------------------------------------------------
+// PADDED_COPY = false (big-robot layout): the padded sphere is rebuilt from the world sphere + the padding table on every read.
+template <bool PADDED_COPY>
+__device__ __forceinline__ float4 padded_sphere(const RobotView &rv, const EvalSmem &es, int i) {
+  if (PADDED_COPY) return es.gsph[i];
+  float4 x = es.sph[i];
+  x.w += rv.padding[i];
+  return x;
+}
+
+template <bool PADDED_COPY = true>
 __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, const EvalSmem &es, int lane, int &bi,
                                                            int &bj) {
   #pragma unroll 1
@@ -271,12 +310,12 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
         const float4 A = es.bc[a], B = es.bc[b];
         bool ca = false, cb = false;
         if (lane < na) {
-          const float4 x = es.gsph[sa + lane];
+          const float4 x = padded_sphere<PADDED_COPY>(rv, es, sa + lane);
           const float dx = x.x - B.x, dy = x.y - B.y, dz = x.z - B.z, rs = x.w + B.w;
           ca = (x.w >= 0.0f) && (dx * dx + dy * dy + dz * dz < rs * rs);
         }
         if (lane < nb) {
-          const float4 y = es.gsph[sb + lane];
+          const float4 y = padded_sphere<PADDED_COPY>(rv, es, sb + lane);
           const float dx = y.x - A.x, dy = y.y - A.y, dz = y.z - A.z, rs = y.w + A.w;
           cb = (y.w >= 0.0f) && (dx * dx + dy * dy + dz * dz < rs * rs);
         }
@@ -293,7 +332,7 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
         for (int t = lane; t < na2 * nb2; t += 32) {
           const int io = (int)(((float)t + 0.5f) * inv_nb2);
           const int i = sa + ia[io], j = sb + ib[t - io * nb2];
-          const float4 x = es.gsph[i], y = es.gsph[j];
+          const float4 x = padded_sphere<PADDED_COPY>(rv, es, i), y = padded_sphere<PADDED_COPY>(rv, es, j);
           const float rs = x.w + y.w;
           const float dx = x.x - y.x, dy = x.y - y.y, dz = x.z - y.z;
           const float f = rs * rs - (dx * dx + dy * dy + dz * dz);
@@ -311,7 +350,7 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
       for (int t = lane; t < na * nb; t += 32) {
         const int io = (int)(((float)t + 0.5f) * inv_nb);
         const int i = sa + io, j = sb + (t - io * nb);
-        const float4 x = es.gsph[i], y = es.gsph[j];
+        const float4 x = padded_sphere<PADDED_COPY>(rv, es, i), y = padded_sphere<PADDED_COPY>(rv, es, j);
         const float rs = x.w + y.w;
         const float dx = x.x - y.x, dy = x.y - y.y, dz = x.z - y.z;
         const float f = rs * rs - (dx * dx + dy * dy + dz * dz);
@@ -344,6 +383,7 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
 // kinematics_joint_util.cuh:12-67): g.(a x (p-o_j)) = a.((p-o_j) x g).
 // gq_out[d] = gqv[d] + sum over links driven by joint d.
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_fk_upsweep(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out);
 __device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out) {
   #pragma unroll 1
   for (int k = lane; k < rv.nl; k += 32) {
@@ -374,6 +414,11 @@ __device__ __forceinline__ void warp_fk_backward(const RobotView &rv, const Eval
     ft[6] = T.z;
   }
   __syncwarp();
+  warp_fk_upsweep(rv, es, lane, gq_out);
+}
+
+// second half of the J^T backward: per-link (F, T) accumulators in es.ft -> joint gradients
+__device__ __forceinline__ void warp_fk_upsweep(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out) {
   #pragma unroll 1
   for (int j = lane; j < rv.nl; j += 32) {
     const int jt = rv.joint_type[j];
@@ -496,6 +541,112 @@ __device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, con
     gq_out[d] = g;
   }
   return true;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Big-robot layout: the sphere gradients of a row live in a short list (es.glist: g.xyz + sphere index, in sphere order) instead
+// of a dense [S] array.  The list is consumed either by the sparse J^T (lanes own links, entries broadcast) or -- when a row
+// fills it -- drained into the per-link (F, T) accumulators, deterministically in list order.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_zero_ft(const RobotView &rv, const EvalSmem &es, int lane) {
+  for (int k = lane; k < rv.nl * 2; k += 32) reinterpret_cast<float4 *>(es.ft)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_drain_list_to_ft(const RobotView &rv, const EvalSmem &es, int lane, int n) {
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const float4 g4 = es.glist[i];
+    const int s = __float_as_int(g4.w);
+    const float4 p4 = es.sph[s];
+    const int k = rv.sph_link[s];
+    const float *Tk = es.cumul + 12 * k;
+    const V3 g = mk3(g4.x, g4.y, g4.z);
+    const V3 tq = cross(mk3(p4.x - Tk[3], p4.y - Tk[7], p4.z - Tk[11]), g);
+    if (lane < 6) {
+      const float v = lane == 0 ? g.x : lane == 1 ? g.y : lane == 2 ? g.z : lane == 3 ? tq.x : lane == 4 ? tq.y : tq.z;
+      es.ft[8 * k + lane + (lane >= 3 ? 1 : 0)] += v;
+    }
+    __syncwarp();
+  }
+}
+// dense finish: tool-frame gradients into the accumulators (one lane, frame order), then the up-sweep
+__device__ __forceinline__ void warp_fk_backward_from_ft(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out) {
+  if (lane == 0) {
+    for (int t = 0; t < rv.L; ++t) {
+      float *ft = es.ft + 8 * rv.tool_map[t];
+      const float *pg = es.pose_g + 8 * t;
+      ft[0] += pg[0];
+      ft[1] += pg[1];
+      ft[2] += pg[2];
+      ft[4] += pg[4];
+      ft[5] += pg[5];
+      ft[6] += pg[6];
+    }
+  }
+  __syncwarp();
+  warp_fk_upsweep(rv, es, lane, gq_out);
+}
+// sparse J^T over the list (the transposed chain walk of warp_fk_backward_sparse with the list as the source)
+__device__ __forceinline__ void warp_fk_backward_list(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out, int n) {
+  const int nu = rv.nl > 32 ? 2 : 1;
+  V3 ax[2], og[2];
+  float sc[2];
+  int jt[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = lane + 32 * u;
+    jt[u] = -1;
+    if (u >= nu) continue;
+    sc[u] = 0.0f;
+    ax[u] = og[u] = mk3(0, 0, 0);
+    if (j < rv.nl) {
+      jt[u] = rv.joint_type[j];
+      if (jt[u] >= 0) {
+        const float *Tj = es.cumul + 12 * j;
+        const int a = (jt[u] >= JT_XR) ? jt[u] - JT_XR : jt[u];
+        ax[u] = mk3(Tj[a], Tj[4 + a], Tj[8 + a]);
+        og[u] = mk3(Tj[3], Tj[7], Tj[11]);
+        sc[u] = rv.joff[2 * j];
+      }
+    }
+  }
+  float acc[2] = {0.0f, 0.0f};
+  auto add = [&](unsigned long long mask, V3 p, V3 g, V3 om) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = lane + 32 * u;
+      if (u < nu && jt[u] >= 0 && ((mask >> j) & 1ull)) {
+        acc[u] += (jt[u] >= JT_XR) ? sc[u] * (dot(ax[u], cross(p - og[u], g)) + dot(ax[u], om)) : sc[u] * dot(ax[u], g);
+      }
+    }
+  };
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const float4 g4 = es.glist[i];
+    const int s = __float_as_int(g4.w);
+    const float4 p4 = es.sph[s];
+    add(rv.anc_mask[rv.sph_link[s]], mk3(p4.x, p4.y, p4.z), mk3(g4.x, g4.y, g4.z), mk3(0, 0, 0));
+  }
+#pragma unroll 1
+  for (int t = 0; t < rv.L; ++t) {
+    const float *pg = es.pose_g + 8 * t;
+    const V3 g = mk3(pg[0], pg[1], pg[2]), om = mk3(pg[4], pg[5], pg[6]);
+    if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && om.x == 0.0f && om.y == 0.0f && om.z == 0.0f) continue;
+    const int k = rv.tool_map[t];
+    const float *Tk = es.cumul + 12 * k;
+    add(rv.anc_mask[k], mk3(Tk[3], Tk[7], Tk[11]), g, om);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = lane + 32 * u;
+    if (j < rv.nl) es.contrib[j] = acc[u];
+  }
+  __syncwarp();
+  for (int d = lane; d < rv.D; d += 32) {
+    float g = es.gqv[d];
+    for (int i = rv.jl_off[d]; i < rv.jl_off[d + 1]; ++i) g += es.contrib[rv.jl_idx[i]];
+    gq_out[d] = g;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------

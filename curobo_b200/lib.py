@@ -66,7 +66,7 @@ class RolloutIO(C.Structure):
                 ("batch_size", C.c_int32), ("horizon", C.c_int32), ("spline", C.POINTER(SplineInput)),
                 ("dynamics", C.POINTER(DynamicsParams)),
                 ("cspace_target", c_p), ("idxs_cspace_target", c_p), ("cspace_target_dof_weight", c_p),
-                ("sphere_configs", c_p), ("num_sphere_configs", C.c_int32)]
+                ("sphere_configs", c_p), ("num_sphere_configs", C.c_int32), ("work_counter", c_p)]
 
 
 _I = C.c_int
@@ -133,7 +133,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)       # AttributeError if the symbol is missing: fail loudly
         fn.argtypes = args
         fn.restype = res
-    if lib.cb200_abi_version() != 5:
+    if lib.cb200_abi_version() != 6:
         raise RuntimeError("libcurobo_b200.so ABI version mismatch")
     _LIB = lib
     return lib

@@ -150,6 +150,8 @@ class RolloutEngine:
         self._ccfg = self._make_ccfg(1)
         self._effort_cost = None
         self._dyn_params = None
+        # row ticket counter of the humanoid kernel (zero between launches; this engine's launches are stream ordered)
+        self._work_counter = torch.zeros(2, dtype=torch.int32, device=self.device)
 
     def attach_dynamics(self, dynamics, effort_limits=None, fused: bool = True) -> None:
         """Make the STATE c-space cost dynamics-aware: after the fused launch, tau = RNEA(q, qd, qdd) is
@@ -411,6 +413,7 @@ class RolloutEngine:
             if t is not None:
                 setattr(io, name, t.data_ptr())
         io.batch_size, io.horizon = B, H
+        io.work_counter = self._work_counter.data_ptr()
         if self._dyn_params is not None and io.vel and io.acc and not bool(io.spline):
             io.dynamics = C.pointer(self._dyn_params)
         err = self._lib.cb200_rollout_cost_grad(C.byref(self._ccfg), C.byref(io), stream_ptr(dev))

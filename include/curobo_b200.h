@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st *cb200_stream_t; /* == cudaStream_t */
 
-#define CB200_ABI_VERSION 5
+#define CB200_ABI_VERSION 6
 
 /* Library / build identity.  cb200_abi_version() == CB200_ABI_VERSION; cb200_sm_arch() == 100. */
 int cb200_abi_version(void);
@@ -311,6 +311,10 @@ typedef struct {
    * packed with the same configurations (cb200_robot_sizes.num_sphere_configs) so its broad-phase bounds cover all. */
   const float *sphere_configs;            /* [num_sphere_configs, S, 4] or null */
   int32_t num_sphere_configs;
+  /* Row ticket counter of the big-robot (humanoid) kernel: int32[2], zero on entry, zero again when the launch has finished
+   * (the kernel re-arms it), owned by ONE stream at a time -- concurrent launches need one counter each.  Null: rows are
+   * strided statically over the resident warps. */
+  int32_t *work_counter;
 } cb200_rollout_io;
 
 int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io *io,

@@ -178,6 +178,8 @@ inline unsigned __reduce_max_sync(unsigned, unsigned v) {
   return simt::exchange(v, [&](const unsigned long long *s) { unsigned r = 0; for (int i = 0; i < 32; ++i) r = std::max(r, (unsigned)s[i]); return r; });
 }
 inline float atomicAdd(float *p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
+inline int atomicAdd(int *p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_acq_rel); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
 

@@ -13,13 +13,13 @@ extern "C" int em_pba3d(int32_t *site_index, int nx, int ny, int nz, int n_ctas)
   auto grid = [&](long long tiles) { return (int)(tiles < n_ctas ? (tiles < 1 ? 1 : tiles) : n_ctas); };
   const long long nrows = (long long)nx * ny;
   if (nz <= 128) {
-    simt::launch(edt_flood_z_kernel<4>, grid((nrows + 7) / 8), 256, site_index, nz, nrows);
+    simt::launch(edt_flood_z_kernel<4>, grid((nrows + 15) / 16), 256, site_index, nz, nrows);
   } else if (nz <= 256) {
-    simt::launch(edt_flood_z_kernel<8>, grid((nrows + 7) / 8), 256, site_index, nz, nrows);
+    simt::launch(edt_flood_z_kernel<8>, grid((nrows + 15) / 16), 256, site_index, nz, nrows);
   } else if (nz <= 512) {
-    simt::launch(edt_flood_z_kernel<16>, grid((nrows + 7) / 8), 256, site_index, nz, nrows);
+    simt::launch(edt_flood_z_kernel<16>, grid((nrows + 15) / 16), 256, site_index, nz, nrows);
   } else {
-    simt::launch(edt_flood_z_kernel<32>, grid((nrows + 7) / 8), 256, site_index, nz, nrows);
+    simt::launch(edt_flood_z_kernel<32>, grid((nrows + 15) / 16), 256, site_index, nz, nrows);
   }
   simt::launch(edt_envelope_kernel<1>, grid(by.e.ntiles()), kBands * kLanes, by);
   simt::launch(edt_envelope_kernel<0>, grid(bx.e.ntiles()), kBands * kLanes, bx);

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(L):
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/curobo_b200.h but not exported"
     assert set(names) == set(cblib.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
-    assert L.cb200_abi_version() == 5 and L.cb200_sm_arch() == 100
+    assert L.cb200_abi_version() == 6 and L.cb200_sm_arch() == 100
 
 
 def test_library_contains_sm100a_sass_and_tma_bulk_copy():

@@ -36,7 +36,7 @@ def emulated_library():
     for name, (args, res) in cblib._SIGS.items():
         fn = getattr(L, name)                     # every ABI symbol must exist in the emulated library too
         fn.argtypes, fn.restype = args, res
-    assert L.cb200_abi_version() == 5
+    assert L.cb200_abi_version() == 6
     return L
 
 
@@ -232,6 +232,11 @@ def test_pending_rnea_trees(run, monkeypatch):
 @pytest.mark.parametrize("robot,B,H", [("franka", 6, 5), ("g1_29", 3, 4)])
 def test_pending_dynamics_state_cost(run, robot, B, H):
     run("test_gpu_zy_effort_cost", "test_dynamics_state_cost_vs_oracle", robot, B, H)
+
+
+@pytest.mark.parametrize("robot,n,buried", [("g1_29", 5, False), ("g1_29", 3, True), ("franka", 6, True)])
+def test_big_robot_kernel(run, monkeypatch, robot, n, buried):
+    run("test_gpu_rollout", "test_big_robot_kernel_matches_standard_kernel_and_oracle", monkeypatch, robot, n, buried)
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pyref", "MANIFEST.json")),

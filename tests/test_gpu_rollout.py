@@ -614,3 +614,43 @@ def test_fused_rollout_sphere_configs(mode):
     grad_close(out.grad_q.cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
     assert np.abs(want["spheres"][1, :, -4:, 3] - 0.08).max() < 1e-6 and (want["spheres"][1, :, 5:8, 3] < 0).all()
     assert want["scene_cost"].sum() + want["self_cost"].sum() > 0
+
+
+@pytest.mark.parametrize("robot,n,buried", [("g1_29", 24, False), ("g1_29", 10, True), ("g1_43", 8, True), ("franka", 32, True)])
+def test_big_robot_kernel_matches_standard_kernel_and_oracle(monkeypatch, robot, n, buried):
+    """rollout_fused_big_kernel (gradient list instead of the dense sphere-gradient array, padded radii rebuilt on the fly,
+    ticket-counter row queue) against rollout_fused_kernel on the same rows and against the oracle.  `buried`: the world is solid
+    around the robot, every sphere collides, the list overflows and the row finishes through the dense force / torque
+    accumulators -- both J^T forms of the new kernel are covered.  CB200_BIG forces the variant (default: big for humanoids)."""
+    from curobo_b200.world import VoxelWorld
+    rm = load_robot(robot)
+    cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                        cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0), pose_weight=(2000.0, 100.0))
+    q = (humanoid_q(rm, n, seed=61) if robot != "franka" else random_q(rm, n, seed=61))[:, None, :]
+    gp, gq = goal_from_q(rm, (humanoid_q(rm, 2, seed=62, scale=0.5) if robot != "franka" else random_q(rm, 2, seed=62)))
+    idx = (np.arange(n) % 2).astype(np.int32)
+    if buried:
+        g = np.stack(np.meshgrid(*[np.arange(48)] * 3, indexing="ij"), -1).astype(np.float32)
+        sdf = (np.linalg.norm(g - 23.5, axis=-1) * 0.06 - 1.2).astype(np.float32)      # a solid ball of radius 1.2 m around the base
+        vox = VoxelWorld.from_grid(sdf, 0.06)
+    else:
+        vox = small_voxel_world()
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CB200_BIG", flag)
+        out, want = check_against_oracle(rm, cfg, q, vox=vox, goal=(gp, gq), idx=idx)
+        outs[flag] = (out.cost.clone(), out.grad_q.clone(), out.scene_cost.clone(), out.self_cost.clone())
+    if buried:
+        assert int((want["scene_cost"] > 0).sum(-1).min()) > (96 if robot != "franka" else 40), "every row must overflow the list"
+    a, b = outs["0"], outs["1"]
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])          # per-term costs: same arithmetic, bit for bit
+    assert torch.allclose(a[0], b[0], rtol=1e-6, atol=0.0)
+    assert torch.allclose(a[1], b[1], rtol=2e-4, atol=2e-6 * float(a[1].abs().max()))     # different summation order in J^T
+    # the ticket counter is re-armed by every launch
+    eng = RolloutEngine(rm, cfg, DEV, None, VoxelData.from_world(vox, DEV))
+    eng.update_goal(T(gp), T(gq), T(idx))
+    first = eng.evaluate_action(T(q)).grad_q.clone()
+    for _ in range(3):
+        again = eng.evaluate_action(T(q)).grad_q
+    torch.cuda.synchronize()
+    assert torch.equal(first, again) and int(eng._work_counter.abs().sum()) == 0

@@ -213,7 +213,7 @@ def emu_main():
         if hasattr(L, name):
             fn = getattr(L, name)
             fn.argtypes, fn.restype = args, res
-    assert L.cb200_abi_version() == 5
+    assert L.cb200_abi_version() == 6
     return L
 
 
