@@ -304,7 +304,32 @@ def edt_bench(device, peak, n=256, iters=10):
     nbytes = 3 * 8 * n ** 3
     return {"grid": [n, n, n], "sites": int(occ.sum()), "transform_ms": ms, "voxels_per_s": n ** 3 / (ms * 1e-3),
             "bytes_per_voxel": 24, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "launches": 3,
-            "note": "first measurement of this row; kernels not yet profiled"}
+            "esdf_builder": esdf_builder_bench(device, n)}
+
+
+def esdf_builder_bench(device, n=256, iters=10):
+    """The whole producer side of the ESDF wire format: dense SDF -> seed sites -> exact transform ->
+    signed fp16 distance (curobo_b200.esdf.DenseESDFBuilder = _compute_esdf_impl's three stages), 5 launches."""
+    import torch
+    from curobo_b200.esdf import DenseESDFBuilder
+    from curobo_b200.world import make_box_esdf
+    voxel = 2.56 / n                                      # the same 2.56 m world at every grid size
+    sdf = make_box_esdf(n=n, voxel_size=voxel, num_boxes=12, seed=0, xp=torch).to(torch.float32).reshape(n, n, n).to(device)
+    trunc = 4 * voxel
+    sdf = sdf.clamp(-trunc, trunc).contiguous()
+    b = DenseESDFBuilder((n, n, n), voxel, trunc, device)
+    ts = []
+    for i in range(iters + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        b.compute(sdf, sdf)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    return {"build_ms": ms, "voxels_per_s": n ** 3 / (ms * 1e-3), "stages": "seed + 3-pass transform + signed fp16 distance",
+            "sites": int((b.site_index >= 0).sum())}
 
 
 class ClockSampler:
@@ -430,6 +455,26 @@ def cpu_baseline(wl_name: str, target_seconds: float = 12.0, procs: int = 1):
         pool.map(_oracle_eval, [(wl_name, i * chunk, (i + 1) * chunk) for i in range(procs)])
         dt = time.perf_counter() - t0
     return n / dt, procs, f"{n} of {wl['B'] * wl['H']} evals of {wl_name}, numpy oracle, {procs} processes"
+
+
+def measured_swept_samples(wl_name: str, seeds: int = 6):
+    """Mean number of ESDF samples per (sphere, waypoint) of a swept workload ("n_s in [1, 7], report the measured
+    mean"): the oracle's adaptive sweep counted on the first `seeds` trajectories of the workload against the same analytic world
+    (128^3 instead of 256^3: the sample count depends on the geometry, not on the grid pitch)."""
+    from curobo_b200.world import VoxelWorld, make_box_esdf
+    from oracle import rollout_oracle as O
+    wl = make_workload(wl_name)
+    if wl.get("q") is None or wl["voxel"] is None:
+        return None
+    v, n = wl["voxel"], 128
+    sdf = make_box_esdf(n=n, voxel_size=v["voxel"] * v["n"] / n, num_boxes=v["boxes"], seed=v["seed"])
+    vox = VoxelWorld.from_grid(np.asarray(sdf).reshape(n, n, n), v["voxel"] * v["n"] / n)
+    q = wl["q"][:seeds]
+    B, H, D = q.shape
+    _, sph, _, _ = O.fk_forward(wl["robot"], q.reshape(B * H, D))
+    stats = {}
+    O.scene_collision(sph.reshape(B, H, -1, 4), 1.0, wl["cfg"].scene_activation, None, vox, None, sweep=True, stats=stats)
+    return stats["samples"] / max(1, stats["sphere_obstacle_pairs"])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -685,6 +730,14 @@ def main():
                 n = len(cfg_o.line_search_scale)
                 rep = lambda a: np.repeat(a, n, axis=0)  # noqa: E731
                 cand = dict(part, B=part["B"] * n, q=rep(part["q"]))
+                if part["goal"] is None:
+                    # whole-body IK: every seed pulls the robot's tool frames towards the poses of one reference posture
+                    from curobo_b200.rollout import RolloutConfig
+                    from helpers import humanoid_q
+                    from oracle import rollout_oracle as O
+                    _, _, gp, gq = O.fk_forward(full["robot"], humanoid_q(full["robot"], 1, seed=77, scale=0.5))
+                    part = dict(part, goal=(gp[:, :, None, :].copy(), gq[:, :, None, :].copy(), np.zeros(part["B"], np.int32)))
+                    cand["cfg"] = RolloutConfig(**{**part["cfg"].__dict__, "pose_weight": (2000.0, 100.0)})
                 if part["goal"] is not None:
                     cand["goal"] = (part["goal"][0], part["goal"][1], rep(part["goal"][2]))
                 if part.get("cs_target") is not None:
@@ -749,6 +802,14 @@ def main():
                     ach = w2["bytes_per_eval"] * w2["B"] * w2["H"] / (k_ms * 1e-3) / 1e9
                     others[name] = {"value": w2["B"] * w2["H"] / (k_ms * 1e-3), "kernel_ms": k_ms,
                                     "bytes_per_eval": w2["bytes_per_eval"], "hbm_frac": ach / peak}
+                    if w2["cfg"].use_sweep and w2.get("q") is not None and name in ("franka_mpc_1024x30_esdf_swept",
+                                                                                     "franka_trajopt_32x32_esdf_swept"):
+                        ns = measured_swept_samples(name)       # bytes_per_eval above bounds n_s with 7; this is the measured mean
+                        if ns is not None:
+                            S_ = w2["robot"].num_spheres
+                            bpe_m = w2["bytes_per_eval"] - 16 * S_ * 7 + 16 * S_ * ns
+                            others[name].update({"n_s_mean_measured": ns, "bytes_per_eval_measured": bpe_m,
+                                                 "hbm_frac_measured": bpe_m * w2["B"] * w2["H"] / (k_ms * 1e-3) / 1e9 / peak})
                 except Exception as ex:                                           # noqa: BLE001
                     others[name] = {"error": repr(ex)[:200]}
 

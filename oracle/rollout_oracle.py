@@ -424,14 +424,16 @@ def _obstacles(world_cuboid, world_voxel, env):
 
 
 def scene_collision(spheres, weight, eta, world_cuboid=None, world_voxel=None, env_query_idx=None,
-                    sweep=False, speed_dt=None, sweep_steps=3):
+                    sweep=False, speed_dt=None, sweep_steps=3, stats=None):
     """Per-sphere scene-collision cost [B,H,S] and gradient [B,H,S,4] summed over obstacles.
 
     discrete: geom/collision/wp_collision_kernel.py:70-166
     swept:    geom/collision/wp_sweep_collision_kernel.py:83-260 (<=3 adaptive samples toward h-1 and h+1,
               accumulated in the obstacle frame, rotated once)
     speed metric (if speed_dt is not None): geom/collision/wp_speed_metric.py:10-93
-    Spheres with r < 0 are skipped.  pen = (r + eta) - sdf."""
+    Spheres with r < 0 are skipped.  pen = (r + eta) - sdf.
+    `stats` (dict, optional): accumulates "samples" = SDF evaluations an adaptive implementation performs (1 at the sphere +
+    one per live sweep step) and "sphere_obstacle_pairs", for the measured mean n_s of SURVEY.md 8d."""
     sph = np.asarray(spheres, F)
     B, H, S, _ = sph.shape
     w, eta = F(weight), F(eta)
@@ -452,6 +454,9 @@ def scene_collision(spheres, weight, eta, world_cuboid=None, world_voxel=None, e
             sdf, n = sdf_fn(loc)
             pen = (radj - sdf).astype(F)
             c, k = collision_activation(pen, eta)
+            if stats is not None:
+                stats["samples"] = stats.get("samples", 0) + int(active.sum())
+                stats["sphere_obstacle_pairs"] = stats.get("sphere_obstacle_pairs", 0) + int(active.sum())
             if not sweep:
                 hit = active & (pen > 0)
                 gw = _quat_rotate(fq_b, n)
@@ -477,6 +482,8 @@ def scene_collision(spheres, weight, eta, world_cuboid=None, world_voxel=None, e
                 alive = has.copy()
                 for _ in range(sweep_steps):
                     alive = alive & ~(jump >= half)
+                    if stats is not None:
+                        stats["samples"] += int((alive & active).sum())
                     t = (F(1.0) - F(0.5) * jump * inv_half).astype(F)
                     pt = (t[..., None] * loc + (F(1.0) - t)[..., None] * nb).astype(F)
                     sdf2, n2 = sdf_fn(pt)
