@@ -463,7 +463,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
   float *base = reinterpret_cast<float *>(smem + a.blob_smem_bytes) + (size_t)warp * a.eval_floats;
   const int N = a.B * a.H;
   const int stride = gridDim.x * nwarps;
-  for (int e = blockIdx.x * nwarps + warp; e < N; e += stride) {
+  // rows: the first one statically, the rest from the ticket counter when the caller provides one (rows differ in cost and
+  // 16,384 rows over 3,552 resident warps is 4.6 rounds: with static striding the last round is half empty)
+  int e = blockIdx.x * nwarps + warp;
+  while (e < N) {
     int b = e, h = 0;
     if (a.H != 1) {  // integer division is ~60 instructions: skip it for H == 1 (IK)
       b = e / a.H;
@@ -481,6 +484,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
     const RowB1 r = phase_b1_ool<SCENE>(&a, smem, base, lane, e, b);
     phase_b2_ool(&a, smem, base, lane, e, r, pa.cs_cost, pa.pose_c);
 #endif
+    if (a.work_counter != nullptr) {
+      int nxt = 0;
+      if (lane == 0) nxt = stride + atomicAdd(a.work_counter, 1);
+      e = __shfl_sync(kFull, nxt, 0);
+    } else {
+      e += stride;
+    }
+  }
+  if (a.work_counter != nullptr && lane == 0) {  // the last warp to leave re-arms the counter for the next launch
+    __threadfence();
+    if (atomicAdd(a.work_counter + 1, 1) == stride - 1) {
+      a.work_counter[0] = 0;
+      a.work_counter[1] = 0;
+    }
   }
 }
 
@@ -632,8 +649,8 @@ __device__ __forceinline__ void row_phase_b2_list(const FusedArgs &a, const Robo
   __syncwarp();
 }
 
-template <int SCENE>
-__global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_big_kernel(const __grid_constant__ FusedArgs a) {
+template <int SCENE, int MAXW = kBigWarps>
+__global__ void __launch_bounds__(MAXW * 32, 1) rollout_fused_big_kernel(const __grid_constant__ FusedArgs a) {
   CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
@@ -745,96 +762,88 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
 // effort channel of the STATE cost on it (bound hinge, squared-L2, energy (tau qd dt)^2: wp_cspace_state.py:209-275) and
 // the RNEA adjoint of d cost / d tau onto the position / velocity / acceleration gradients -- tau never leaves the SM.
 //
-// WARP-SPECIALISED: the CTA's last warp is the DYNAMICS warp, the others are ROW warps.  Work is cut into chunks of R
-// consecutive waypoints of one seed (R <= 32, a multiple of the row-warp count).
-//   dynamics warp   runs the inverse dynamics + adjoint of chunk c + 1: its LANES are the chunk's rows walking the same link
-//                   (cb200_dynamics_tile.cuh, the mapping of the stand-alone RNEA kernels; the recursion is sequential in
-//                   the links, so one warp carries 32 rows through it at the cost of one), state in a transposed
-//                   shared-memory tile, results in one of two IO buffers;
-//   row warps       run the rollout of chunk c exactly as rollout_traj_kernel (warp per waypoint, halo waypoints either
-//                   side, named barrier among themselves) and add their rows' dynamics terms from the other IO buffer.
-// One CTA barrier per chunk hands the buffers over.  The dynamics of a chunk (~13 links x 4 recursions, latency bound) is
-// shorter than its rollout, so it is hidden behind it.
-// History: round 1 ran the recursion on lane 0 of every row's warp (1.26 ms on the MPC workload, plain kernel 0.34 ms, host
-// composition with three more launches 0.47 ms); a CTA-wide dynamics phase before each chunk's rollout took 0.52 ms (seven of
-// eight warps parked at the level barriers for a third of the time).
+// A CTA owns a CHUNK of R consecutive waypoints of one seed (R = 32 / 16 / 8, a multiple of the warp count) and alternates
+// between two mappings:
+//   dynamics phase   thread = (row r = tid % R, worker w = tid / R): the lanes of a warp are different rows walking the same
+//                    link (cb200_dynamics_tile.cuh: level-synchronous recursions, everything else over (link, row) pairs,
+//                    the row state in a transposed shared-memory tile); results stay in the tile's IO rows
+//   tile phase       the chunk's waypoints, nwarps at a time, exactly as rollout_traj_kernel (warp per waypoint, halo
+//                    waypoints either side), each row adding its dynamics terms from the IO rows.
+// Measured on the MPC workload (1024 x 30, B200): plain trajectory kernel 0.34 ms; this kernel 0.52 ms; the host composition
+// (three more launches, HBM round trip of the 80 B / link cache) 0.47 ms -- which is why RolloutEngine.attach_dynamics defaults
+// to the host composition.  Round 1 ran the recursion on lane 0 of every row's warp inside phase A: 1.26 ms.  A warp-specialised
+// pipeline (one dynamics warp producing chunk c + 1 while the row warps roll out chunk c) was built and measured at 0.65 ms: the
+// dynamics of a chunk is ~32 k warp-instructions, which a single warp issues more slowly than eight warps roll the chunk out
+// (profiles/r02_b_dynamics.md).
 // ------------------------------------------------------------------------------------------------
-template <int SCENE, int NWARPS, int MINB>
-__global__ void __launch_bounds__(NWARPS * 32, MINB) rollout_traj_dyn_kernel(const __grid_constant__ FusedArgs a, const int R) {
+template <int SCENE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_dyn_kernel(const __grid_constant__ FusedArgs a,
+                                                                                         const int R) {
   CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
   const RobotView rv = make_robot_view(smem, a.blob);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nrw = (blockDim.x >> 5) - 1;  // row warps; warp nrw is the dynamics warp
-  const bool is_dyn = warp == nrw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float *all = reinterpret_cast<float *>(smem + a.blob_smem_bytes);
-  const EvalSmem es = carve_eval_smem(all + (size_t)(is_dyn ? 0 : warp) * a.eval_floats, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
-  float4 *halo_prev = reinterpret_cast<float4 *>(all + (size_t)nrw * a.eval_floats);
+  const EvalSmem es = carve_eval_smem(all + (size_t)warp * a.eval_floats, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  float4 *halo_prev = reinterpret_cast<float4 *>(all + (size_t)nwarps * a.eval_floats);
   float4 *halo_next = halo_prev + rv.S;
   const int D = rv.D, S = rv.S, nl = rv.nl, RS = R + 1;
   float *dynbase = reinterpret_cast<float *>(halo_next + S);
-  float *io0 = dynbase + (5 * 6 + 2) * nl * RS, *io1 = io0 + dyn::kTileIo * D * RS;
-  const cb200_rollout_cfg &cfg = a.cfg;
-  const int chunks_per_seed = (a.H + R - 1) / R;
-  const long long n_chunks = (long long)a.B * chunks_per_seed;
   // the tree part of the model points into the shared-memory copy of the robot blob (plain loads: the read-only global path
   // must not be used on shared addresses); the inertial parameters are the caller's arrays in global memory
   const dyn::Model M{rv.fixed, a.dyn.masses_com, a.dyn.inertias, rv.joint_type, rv.joint_map, rv.link_map, rv.joff,
                      a.dyn.gravity, rv.level_off, rv.level_links, nl, D, rv.n_levels};
-
-  // ---- the dynamics warp's job for one chunk: rows on lanes (R < 32: 32 / R workers share the links)
-  auto dynamics_of_chunk = [&](long long chunk, float *IO) {
-    // R rows x W workers on the warp's lanes; lanes beyond R * W own no (link, row) pair (worker index past every loop bound)
-    const int W = 32 / R, spare = lane >= R * W;
-    const dyn::Tile<dyn::LdPlain> T{dynbase, dynbase + 5 * nl * 6 * RS, IO, nl, D, RS, spare ? 0 : lane % R, spare ? 0x3fff : lane / R, W, M};
+  const dyn::Tile<dyn::LdPlain> T{dynbase, dynbase + 5 * nl * 6 * RS, dynbase + (5 * 6 + 2) * nl * RS, nl, D, RS,
+                                  (int)threadIdx.x % R, (int)threadIdx.x / R, (int)blockDim.x / R, M};
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int chunks_per_seed = (a.H + R - 1) / R;
+  const long long n_chunks = (long long)a.B * chunks_per_seed;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const int b = (int)(chunk / chunks_per_seed);
     const int c0 = (int)(chunk - (long long)b * chunks_per_seed) * R;
     const int rows = (a.H - c0) < R ? (a.H - c0) : R;
     const size_t e0 = (size_t)b * a.H + c0;
-    for (int i = lane; i < R * D; i += 32) {  // coalesced: the chunk's rows are contiguous in q / vel / acc
+    // ---------------- dynamics phase
+    for (int i = threadIdx.x; i < R * D; i += blockDim.x) {  // coalesced: the chunk's rows are contiguous in q / vel / acc
       const int rr = i / D, d = i - rr * D;
       const bool ok = rr < rows;
       const size_t gi = e0 * D + i;
-      IO[(0 * D + d) * RS + rr] = ok ? __ldg(a.q + gi) : 0.0f;
-      IO[(1 * D + d) * RS + rr] = ok ? __ldg(a.vel + gi) : 0.0f;
-      IO[(2 * D + d) * RS + rr] = ok ? __ldg(a.acc + gi) : 0.0f;
-      IO[(3 * D + d) * RS + rr] = 0.0f;
+      T.IO[(0 * D + d) * RS + rr] = ok ? __ldg(a.q + gi) : 0.0f;
+      T.IO[(1 * D + d) * RS + rr] = ok ? __ldg(a.vel + gi) : 0.0f;
+      T.IO[(2 * D + d) * RS + rr] = ok ? __ldg(a.acc + gi) : 0.0f;
+      T.IO[(3 * D + d) * RS + rr] = 0.0f;
     }
-    __syncwarp();
-    dyn::tile_rnea_forward<dyn::SyncWarp>(T);
-    const float dt = seed_dt(a, b);
-    float w_b = cfg.cspace_weight[4], w_l2 = cfg.cspace_reg[3], w_en = cfg.cspace_reg[4];
-    if (cfg.retime_regularization_weights) w_en = dt * w_en;
-    const float *lim = rv.limits;
-    for (int i = lane; i < R * D; i += 32) {  // effort terms per (row, dof)
-      const int rr = i / D, d = i - rr * D;
-      const float tau = IO[(3 * D + d) * RS + rr], v = IO[(1 * D + d) * RS + rr];
-      float c = 0.0f, gt = 0.0f, gve = 0.0f;
-      bound_cost(tau, lim[8 * D + d], lim[9 * D + d], cfg.cspace_activation[4], w_b, c, gt);
-      l2_reg(tau, w_l2, c, gt);
-      if (w_en > 0.0f) {
-        const float ce = tau * v * dt;
-        c += w_en * ce * ce;
-        gt += 2.0f * w_en * ce * v * dt;
-        gve = 2.0f * w_en * ce * tau * dt;
+    __syncthreads();
+    dyn::tile_rnea_forward<dyn::SyncCta>(T);
+    {
+      const float dt = seed_dt(a, b);
+      float w_b = cfg.cspace_weight[4], w_l2 = cfg.cspace_reg[3], w_en = cfg.cspace_reg[4];
+      if (cfg.retime_regularization_weights) w_en = dt * w_en;
+      const float *lim = rv.limits;
+      for (int i = threadIdx.x; i < R * D; i += blockDim.x) {  // effort terms per (row, dof)
+        const int rr = i / D, d = i - rr * D;
+        const float tau = T.IO[(3 * D + d) * RS + rr], v = T.IO[(1 * D + d) * RS + rr];
+        float c = 0.0f, gt = 0.0f, gve = 0.0f;
+        bound_cost(tau, lim[8 * D + d], lim[9 * D + d], cfg.cspace_activation[4], w_b, c, gt);
+        l2_reg(tau, w_l2, c, gt);
+        if (w_en > 0.0f) {
+          const float ce = tau * v * dt;
+          c += w_en * ce * ce;
+          gt += 2.0f * w_en * ce * v * dt;
+          gve = 2.0f * w_en * ce * tau * dt;
+        }
+        T.IO[(3 * D + d) * RS + rr] = gt;
+        T.IO[(4 * D + d) * RS + rr] = 0.0f;
+        T.IO[(5 * D + d) * RS + rr] = gve;
+        T.IO[(6 * D + d) * RS + rr] = 0.0f;
+        T.IO[(7 * D + d) * RS + rr] = c;
       }
-      IO[(3 * D + d) * RS + rr] = gt;
-      IO[(4 * D + d) * RS + rr] = 0.0f;
-      IO[(5 * D + d) * RS + rr] = gve;
-      IO[(6 * D + d) * RS + rr] = 0.0f;
-      IO[(7 * D + d) * RS + rr] = c;
     }
-    __syncwarp();
-    dyn::tile_rnea_backward<dyn::SyncWarp>(T);
-  };
-
-  // ---- the row warps' job for one chunk
-  auto rollout_of_chunk = [&](long long chunk, const float *IO) {
-    const int b = (int)(chunk / chunks_per_seed);
-    const int c0 = (int)(chunk - (long long)b * chunks_per_seed) * R;
-    const int rows = (a.H - c0) < R ? (a.H - c0) : R;
-    for (int t0 = 0; t0 < rows; t0 += nrw) {
+    __syncthreads();
+    dyn::tile_rnea_backward<dyn::SyncCta>(T);
+    // ---------------- tile phase: the chunk's waypoints, nwarps at a time
+    for (int t0 = 0; t0 < rows; t0 += nwarps) {
       const int h0 = c0 + t0;
       const int h = h0 + warp;
       const bool active = h < a.H;
@@ -843,8 +852,8 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) rollout_traj_dyn_kernel(con
       if (warp == 0 && h0 > 0) {
         hh = h0 - 1;
         hdst = halo_prev;
-      } else if (warp == nrw - 1 && h0 + nrw < a.H) {
-        hh = h0 + nrw;
+      } else if (warp == nwarps - 1 && h0 + nwarps < a.H) {
+        hh = h0 + nwarps;
         hdst = halo_next;
       }
       if (hh >= 0) {
@@ -869,42 +878,27 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) rollout_traj_dyn_kernel(con
         const int rr = t0 + warp;  // this row's column of the dynamics tile; lane d owns dof d here and in cspace_dof
 #pragma unroll 1
         for (int d = lane; d < D; d += 32) {
-          es.gqv[d] += IO[(4 * D + d) * RS + rr];
-          const float c = IO[(7 * D + d) * RS + rr];
+          es.gqv[d] += T.IO[(4 * D + d) * RS + rr];
+          const float c = T.IO[(7 * D + d) * RS + rr];
           cs_cost += c;
           const size_t gi = (size_t)e * D + d;
           if (a.cspace_cost) a.cspace_cost[gi] += c;
-          if (a.grad_vel) a.grad_vel[gi] += IO[(5 * D + d) * RS + rr];
-          if (a.grad_acc) a.grad_acc[gi] += IO[(6 * D + d) * RS + rr];
+          if (a.grad_vel) a.grad_vel[gi] += T.IO[(5 * D + d) * RS + rr];
+          if (a.grad_acc) a.grad_acc[gi] += T.IO[(6 * D + d) * RS + rr];
         }
         __syncwarp();
       }
-      CB200_NAMED_BARRIER(1, nrw * 32);
+      __syncthreads();
       if (active) {
         const float4 *prev = nullptr, *next = nullptr;
         if (h > 0) prev = (warp > 0) ? reinterpret_cast<const float4 *>(all + (size_t)(warp - 1) * a.eval_floats + rv.nl * 12) : halo_prev;
-        if (h < a.H - 1) next = (warp < nrw - 1) ? reinterpret_cast<const float4 *>(all + (size_t)(warp + 1) * a.eval_floats + rv.nl * 12) : halo_next;
+        if (h < a.H - 1) next = (warp < nwarps - 1) ? reinterpret_cast<const float4 *>(all + (size_t)(warp + 1) * a.eval_floats + rv.nl * 12) : halo_next;
         r = row_phase_b1<true, SCENE>(a, rv, es, lane, e, b, prev, next);
       }
-      CB200_NAMED_BARRIER(1, nrw * 32);
+      __syncthreads();
       if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
     }
-  };
-
-  // software pipeline over this CTA's chunks: in step k the dynamics warp produces chunk k while the row warps consume chunk
-  // k - 1; one CTA barrier per step hands the IO buffers over (and frees the row state of the last tile)
-  const long long first = blockIdx.x;
-  for (long long k = 0;; ++k) {
-    const long long produce = first + k * gridDim.x, consume = produce - gridDim.x;
-    if (produce >= n_chunks && (k == 0 || consume >= n_chunks)) break;
-    float *io_p = (k & 1) ? io1 : io0;
-    const float *io_c = (k & 1) ? io0 : io1;
-    if (is_dyn) {
-      if (produce < n_chunks) dynamics_of_chunk(produce, io_p);
-    } else if (k > 0 && consume < n_chunks) {
-      rollout_of_chunk(consume, io_c);
-    }
-    __syncthreads();
+    __syncthreads();  // the next chunk's dynamics phase rewrites the tile the last rows just read
   }
 }
 
@@ -2867,13 +2861,17 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   if (big_fit && big_want) {
     static KernelT const big_table[4] = {rollout_fused_big_kernel<0>, rollout_fused_big_kernel<1>, rollout_fused_big_kernel<2>,
                                          rollout_fused_big_kernel<3>};
-    KernelT bk = big_table[scene];
+    // tuning knob CB200_BIG_MAXW=18: the 576-thread build of the ESDF variant (112 registers) for rows small enough to fit 18
+    static KernelT const big18 = rollout_fused_big_kernel<2, 18>;
+    const char *mw = getenv("CB200_BIG_MAXW");
+    const int maxw = (mw && atoi(mw) == 18 && scene == 2) ? 18 : kBigWarps;
+    KernelT bk = maxw == 18 ? big18 : big_table[scene];
     struct BigPlan {
       long long key = -1;
       int nw = 0, per_sm = 0;
     };
-    static thread_local BigPlan bplans[4];
-    BigPlan &bp = bplans[scene];
+    static thread_local BigPlan bplans[5];
+    BigPlan &bp = bplans[maxw == 18 ? 4 : scene];
     const int big_floats = big_smem_floats(h.nl, h.D, h.S, h.L, h.n_cl);
     const long long bkey = ((long long)h.smem_bytes << 32) ^ ((long long)big_floats << 8) ^ ((long long)(d.ordinal + 1) << 56);
     if (bkey != bp.key) {
@@ -2889,7 +2887,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       }();
       int best = 0;
       BigPlan cand;
-      for (int nw = kBigWarps; nw >= 1; --nw) {
+      for (int nw = maxw; nw >= 1; --nw) {
         if (force_nw > 0 && nw != force_nw) continue;
         const size_t need = (size_t)h.smem_bytes + (size_t)nw * big_floats * sizeof(float);
         if (need > limit) continue;
@@ -2907,7 +2905,10 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     }
     if (bp.key == bkey) {
       a.eval_floats = big_floats;
-      a.work_counter = io->work_counter;
+      {
+        const char *qs = getenv("CB200_QUEUE");
+        a.work_counter = (qs && atoi(qs) == 0) ? nullptr : io->work_counter;
+      }
       const size_t smem_b = (size_t)h.smem_bytes + (size_t)bp.nw * big_floats * sizeof(float);
       long long g = (long long)d.sm_count * bp.per_sm;
       const long long need_ctas = (N + bp.nw - 1) / bp.nw;
@@ -2929,20 +2930,13 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     // chunked kernel: (warps per CTA, rows per dynamics chunk) that keeps the most warps resident; R is a multiple of the warp
     // count so a chunk is a whole number of waypoint tiles.  Cached per (scene variant, geometry, horizon, device).
     using DynKernelT = void (*)(const FusedArgs, const int);
-    // two builds: 8 row warps + the dynamics warp (288 threads, 112 registers) and 7 + 1 (256 threads, 128 registers)
-    static DynKernelT const dyn_table9[4] = {rollout_traj_dyn_kernel<0, kWarpsPerCta + 1, CB200_MINB>, rollout_traj_dyn_kernel<1, kWarpsPerCta + 1, CB200_MINB>,
-                                             rollout_traj_dyn_kernel<2, kWarpsPerCta + 1, CB200_MINB>, rollout_traj_dyn_kernel<3, kWarpsPerCta + 1, CB200_MINB>};
-    static DynKernelT const dyn_table8[4] = {rollout_traj_dyn_kernel<0, kWarpsPerCta, CB200_MINB>, rollout_traj_dyn_kernel<1, kWarpsPerCta, CB200_MINB>,
-                                             rollout_traj_dyn_kernel<2, kWarpsPerCta, CB200_MINB>, rollout_traj_dyn_kernel<3, kWarpsPerCta, CB200_MINB>};
-    static const int dyn_rows_env = []() {  // tuning knob: CB200_DYN_ROW_WARPS = 8 (default) or <= 7
-      const char *e = getenv("CB200_DYN_ROW_WARPS");
-      return e ? atoi(e) : 8;
-    }();
+    static DynKernelT const dyn_table[4] = {rollout_traj_dyn_kernel<0>, rollout_traj_dyn_kernel<1>, rollout_traj_dyn_kernel<2>,
+                                            rollout_traj_dyn_kernel<3>};
+    DynKernelT dk = dyn_table[scene];
     struct DynPlan {
       long long key = -1;
-      int nw = 0, R = 0, per_sm = 0;   // nw = ROW warps; the CTA has nw + 1
+      int nw = 0, R = 0, per_sm = 0;
       size_t smem = 0;
-      DynKernelT kern = nullptr;
     };
     static thread_local DynPlan dplans[4];
     DynPlan &dpl = dplans[scene];
@@ -2950,36 +2944,28 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     const long long dkey = ((long long)h.smem_bytes << 32) ^ ((long long)a.eval_floats << 8) ^ ((long long)io->horizon << 40) ^
                            ((long long)(d.ordinal + 1) << 56);
     if (dkey != dpl.key) {
+      cudaFuncAttributes fa;
+      cudaError_t e0 = cudaFuncGetAttributes(&fa, dk);
+      if (e0 != cudaSuccess) return ret(e0);
+      const size_t limit = (size_t)d.max_smem - fa.sharedSizeBytes;
+      cudaError_t e1 = cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+      if (e1 != cudaSuccess) return ret(e1);
       double best = 0.0;
       DynPlan cand;
-      for (int nw = kWarpsPerCta; nw >= 1; --nw) {
-        if (nw > dyn_rows_env) continue;
-        DynKernelT dk = nw == kWarpsPerCta ? dyn_table9[scene] : dyn_table8[scene];
-        cudaFuncAttributes fa;
-        cudaError_t e0 = cudaFuncGetAttributes(&fa, dk);
-        if (e0 != cudaSuccess) return ret(e0);
-        const size_t limit = (size_t)d.max_smem - fa.sharedSizeBytes;
-        cudaError_t e1 = cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
-        if (e1 != cudaSuccess) return ret(e1);
-        for (int R = 32; R >= 4; --R) {
-          if (R % nw != 0) continue;  // a chunk is a whole number of waypoint tiles
+      for (int nw = kWarpsPerCta; nw >= 1; nw >>= 1) {
+        for (int R = 32; R >= 8 && R >= nw; R >>= 1) {
           const size_t need = (size_t)h.smem_bytes + halo + (size_t)nw * a.eval_floats * sizeof(float) +
-                              (size_t)(dyn::tile_floats(h.nl, h.D, R) + dyn::kTileIo * h.D * (R + 1)) * sizeof(float);
+                              (size_t)dyn::tile_floats(h.nl, h.D, R) * sizeof(float);
           if (need > limit) continue;
           int per_sm = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dk, (nw + 1) * 32, need) != cudaSuccess || per_sm < 1) continue;
-          // resident ROW warps, discounted for idle rows of the last tile / chunk of a trajectory; wide chunks amortise the
-          // serial depth of the recursion over more rows
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dk, nw * 32, need) != cudaSuccess || per_sm < 1) continue;
+          // resident warps, discounted for idle rows of the last tile / chunk of a trajectory and for short dynamics chunks
+          // (the recursion's serial depth is paid once per chunk whatever its width)
           const int chunks = (io->horizon + R - 1) / R;
-          int slots = 0;
-          for (int c = 0; c < chunks; ++c) {
-            const int rows = std::min(R, io->horizon - c * R);
-            slots += ((rows + nw - 1) / nw) * nw;
-          }
-          const double score = (double)per_sm * nw * ((double)io->horizon / (double)slots) * (0.75 + 0.25 * R / 32.0);
+          double score = (double)per_sm * nw * ((double)io->horizon / ((double)chunks * R)) * (0.75 + 0.25 * R / 32.0);
           if (score > best) {
             best = score;
-            cand.nw = nw, cand.R = R, cand.per_sm = per_sm, cand.smem = need, cand.kern = dk;
+            cand.nw = nw, cand.R = R, cand.per_sm = per_sm, cand.smem = need;
           }
         }
       }
@@ -2990,8 +2976,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     long long grid_ll = (long long)d.sm_count * dpl.per_sm;
     const long long need_ctas = (long long)io->batch_size * ((io->horizon + dpl.R - 1) / dpl.R);
     if (grid_ll > need_ctas) grid_ll = need_ctas;
-    DynKernelT dk = dpl.kern;
-    CB200_LAUNCH(dk, (int)(grid_ll < 1 ? 1 : grid_ll), (dpl.nw + 1) * 32, dpl.smem, (cudaStream_t)stream, a, dpl.R);
+    CB200_LAUNCH(dk, (int)(grid_ll < 1 ? 1 : grid_ll), dpl.nw * 32, dpl.smem, (cudaStream_t)stream, a, dpl.R);
     return finish();
   }
   if (variant == 0 && arm_regcap != 0 && scene <= 1 && h.nl <= 24 && h.S <= 128) {  // ESDF variants spill at 80: -3 %
@@ -3048,6 +3033,10 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     pl.per_sm = best_per_sm;
   }
   const int nw = pl.nw;
+  {
+    const char *qs = getenv("CB200_QUEUE");  // tuning knob: 0 = static striding even when a counter is given
+    a.work_counter = (!traj && !(qs && atoi(qs) == 0)) ? io->work_counter : nullptr;
+  }
   const size_t smem = (size_t)h.smem_bytes + halo_bytes + (size_t)nw * a.eval_floats * sizeof(float);
   long long grid_ll = (long long)d.sm_count * pl.per_sm;
   const long long need_ctas = traj ? (long long)io->batch_size * ((io->horizon + nw - 1) / nw) : (N + nw - 1) / nw;

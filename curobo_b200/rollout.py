@@ -153,7 +153,7 @@ class RolloutEngine:
         # row ticket counter of the humanoid kernel (zero between launches; this engine's launches are stream ordered)
         self._work_counter = torch.zeros(2, dtype=torch.int32, device=self.device)
 
-    def attach_dynamics(self, dynamics, effort_limits=None, fused: bool = True) -> None:
+    def attach_dynamics(self, dynamics, effort_limits=None, fused: bool = False) -> None:
         """Make the STATE c-space cost dynamics-aware: after the fused launch, tau = RNEA(q, qd, qdd) is
         evaluated for every row and the effort channel of the STATE cost -- bound hinge (cspace_weight[4], cspace_activation[4]),
         squared-L2 (cspace_reg[3]) and the energy term (cspace_reg[4]) -- is added to cost / cspace_cost, its gradient to
@@ -167,7 +167,8 @@ class RolloutEngine:
         rm = self.robot
         # fused = the trajectory kernel evaluates RNEA, the effort terms and the RNEA adjoint for its own rows (swept mode;
         # effort limits = the robot's, which are part of the packed robot blob); otherwise -- and for custom limits or
-        # discrete mode -- the same terms are added by three more launches after the fused one.
+        # discrete mode -- the same terms are added by three more launches after the fused one.  Default: the host
+        # composition, measured faster on B200 (MPC 1024 x 30: 0.47 ms vs 0.52 ms in-kernel, plain kernel 0.34 ms).
         self._dyn_params = None
         if fused and effort_limits is None and self.cfg.use_sweep:
             m = dynamics._model       # (fixed, masses_com, inertias, joint types, joint map, link map, offsets, gravity, ...)

@@ -111,7 +111,7 @@ def test_dynamics_aware_rollout_vs_oracle(robot, B, H):
     rm2 = dataclasses.replace(rm, effort_limits=elim)
     eng2 = RolloutEngine(rm2, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
     eng2.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=torch.zeros((rm.num_tool_frames, 6), dtype=torch.float32, device=DEV))
-    eng2.attach_dynamics(Dynamics(rm2, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV))
+    eng2.attach_dynamics(Dynamics(rm2, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV), fused=True)
     assert eng2._dyn_params is not None and eng2._effort_cost is None
     fused = eng2.evaluate_action(T(q), vel=T(v), acc=T(a_), jerk=T(j_), dt=T(dt))
     torch.cuda.synchronize()
@@ -150,7 +150,7 @@ def test_dynamics_aware_knots_rollout_is_consistent():
         e = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV), VoxelData.from_world(vox, DEV))
         e.update_goal(T(p[:, :, None, :].copy()), T(qt[:, :, None, :].copy()), T(np.arange(B, dtype=np.int32)),
                       non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32, device=DEV))
-        e.attach_dynamics(Dynamics(rm, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV))
+        e.attach_dynamics(Dynamics(rm, c["mc"], c["inn"], gravity=(0.0, 0.0, -9.81), device=DEV), fused=True)
         return e
 
     ks = JointState(T(knots[:, 0].copy()), T(z), T(z), T(z))
