@@ -649,8 +649,8 @@ __device__ __forceinline__ void row_phase_b2_list(const FusedArgs &a, const Robo
   __syncwarp();
 }
 
-template <int SCENE, int MAXW = kBigWarps>
-__global__ void __launch_bounds__(MAXW * 32, 1) rollout_fused_big_kernel(const __grid_constant__ FusedArgs a) {
+template <int SCENE>
+__global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_big_kernel(const __grid_constant__ FusedArgs a) {
   CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
   stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
@@ -2852,26 +2852,26 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       return launch_status();
     }
   }
-  // big robots (humanoids), discrete mode: the list-based kernel with up to 16 warps per SM (see rollout_fused_big_kernel).
-  // CB200_BIG = 0 / 1 forces it off / on (default: on when a row of the standard layout exceeds 8 KB).
+  // big robots (humanoids) and ESDF scenes, discrete mode: the list-based kernel with up to 16 warps per SM (see
+  // rollout_fused_big_kernel).  CB200_BIG = 0 / 1 forces it off / on.  Default: on when a row of the standard layout exceeds
+  // 8 KB, and for any robot against an ESDF (Franka + 256^3 ESDF: 0.089 ms vs 0.096 ms; with cuboids only the 80-register arm
+  // build of the standard kernel is faster, 0.076 ms vs 0.082 ms).
   const char *big_str = getenv("CB200_BIG");  // read per call: tests switch it inside one process
   const int big_env = big_str ? atoi(big_str) : -1;
   const bool big_fit = !traj && a.spl.knots == nullptr && h.n_lp > 0 && h.P > 0;
-  const bool big_want = big_env >= 0 ? big_env != 0 : (size_t)a.eval_floats * sizeof(float) > 8192;
+  const bool big_want = big_env >= 0 ? big_env != 0 : ((size_t)a.eval_floats * sizeof(float) > 8192 || (scene & 2) != 0);
   if (big_fit && big_want) {
     static KernelT const big_table[4] = {rollout_fused_big_kernel<0>, rollout_fused_big_kernel<1>, rollout_fused_big_kernel<2>,
                                          rollout_fused_big_kernel<3>};
-    // tuning knob CB200_BIG_MAXW=18: the 576-thread build of the ESDF variant (112 registers) for rows small enough to fit 18
-    static KernelT const big18 = rollout_fused_big_kernel<2, 18>;
-    const char *mw = getenv("CB200_BIG_MAXW");
-    const int maxw = (mw && atoi(mw) == 18 && scene == 2) ? 18 : kBigWarps;
-    KernelT bk = maxw == 18 ? big18 : big_table[scene];
+    // (an 18-warp build -- 576 threads, 96 registers, small spills -- measured 0.237 ms on G1-29 against 0.219 ms for 16 warps)
+    const int maxw = kBigWarps;
+    KernelT bk = big_table[scene];
     struct BigPlan {
       long long key = -1;
       int nw = 0, per_sm = 0;
     };
-    static thread_local BigPlan bplans[5];
-    BigPlan &bp = bplans[maxw == 18 ? 4 : scene];
+    static thread_local BigPlan bplans[4];
+    BigPlan &bp = bplans[scene];
     const int big_floats = big_smem_floats(h.nl, h.D, h.S, h.L, h.n_cl);
     const long long bkey = ((long long)h.smem_bytes << 32) ^ ((long long)big_floats << 8) ^ ((long long)(d.ordinal + 1) << 56);
     if (bkey != bp.key) {
