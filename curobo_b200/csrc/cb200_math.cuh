@@ -390,15 +390,24 @@ CB_HD ObsFrame load_obs_frame(const float *inv_pose8) {
 
 // One obstacle abstraction so discrete and swept code is written once.
 struct Obstacle {
-  int kind;  // 0 cuboid, 1 voxel
-  float a, b, c;  // cuboid dims | (unused)
+  int kind;  // 0 cuboid, 1 voxel, 2 mesh
+  float a, b, c;  // cuboid dims | mesh bounding-box extents
   const uint16_t *feat;
   const uint16_t *mip;
   int nx, ny, nz;
   float vs, max_dist;
+  const float4 *mnodes, *mtris;  // mesh BVH (cb200_mesh.cuh)
 };
+struct MeshSet;
+// mesh SDF through the BVH (cb200_mesh.cuh); declared here so that obstacle_sdf can dispatch to it
+CB_HD SdfGrad mesh_sdf_grad(const float4 *nodes, const float4 *tris, V3 p, float max_distance);
 template <int SCENE>
 CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p, float need_below = 3.0e38f, bool use_mip = false) {
+  if ((SCENE & 4) && (SCENE == 4 || o.kind == 2)) {
+    // data_mesh.py:671-677: max_distance = max(half the bounding-box diagonal, the query's radius + activation distance)
+    const float half_diag = 0.5f * sqrtf(o.a * o.a + o.b * o.b + o.c * o.c);
+    return mesh_sdf_grad(o.mnodes, o.mtris, p, fmaxf(half_diag, o.max_dist));
+  }
   if (SCENE == 1) return cuboid_sdf_grad(p, o.a, o.b, o.c);
   if (SCENE == 2) return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below, use_mip ? o.mip : nullptr);
   if (o.kind == 0) return cuboid_sdf_grad(p, o.a, o.b, o.c);
