@@ -25,6 +25,7 @@
 #include "cb200_dynamics_tile.cuh"
 #include "cb200_launch.h"
 #include "cb200_math.cuh"
+#include "cb200_mesh.cuh"
 #include "cb200_warp.cuh"
 
 using namespace cb200;
@@ -1860,6 +1861,62 @@ __global__ void __launch_bounds__(128) scene_collision_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Mesh obstacles: the same sphere / swept-sphere collision against triangle meshes through the BVH of
+// cb200_mesh.cuh.  The reference launches its generic collision kernel once per obstacle TYPE and accumulates with atomics
+// (checker_collision.py:76-184); here the mesh type is one more launch that ADDS to the buffers the cuboid / ESDF launch
+// wrote (accumulate = 1) or overwrites them when meshes are the only obstacles.  The speed metric is linear in (cost, gradient),
+// so applying it per obstacle type and summing equals applying it to the sum.
+// ------------------------------------------------------------------------------------------------
+struct MeshSceneArgs {
+  float *distance, *gradient;
+  const float *spheres, *weight, *eta, *speed_dt;
+  MeshSet meshes;
+  const int32_t *env_query_idx;
+  int B, H, S, use_multi_env, sweep, speed_metric, accumulate;
+};
+
+__global__ void __launch_bounds__(128) mesh_collision_kernel(const __grid_constant__ MeshSceneArgs a) {
+  const long long total = (long long)a.B * a.H * a.S;
+  const float w = __ldg(a.weight), eta = __ldg(a.eta);
+  const CuboidSet no_cuboids{};
+  const VoxelSet no_voxels{};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / ((long long)a.H * a.S));
+    const int h = (int)((i - (long long)b * a.H * a.S) / a.S);
+    const int env = a.use_multi_env ? __ldg(a.env_query_idx + b) : 0;
+    const float4 sp = __ldg(reinterpret_cast<const float4 *>(a.spheres) + i);
+    const V3 c = mk3(sp.x, sp.y, sp.z);
+    V3 g = mk3(0, 0, 0);
+    float cost;
+    if (!a.sweep) {
+      cost = sphere_scene_discrete<4>(c, sp.w, eta, w, no_cuboids, no_voxels, env, g, &a.meshes);
+    } else {
+      const bool hp = h > 0, hn = h < a.H - 1;
+      V3 pv = c, nx = c;
+      if (hp) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(a.spheres) + i - a.S);
+        pv = mk3(t.x, t.y, t.z);
+      }
+      if (hn) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(a.spheres) + i + a.S);
+        nx = mk3(t.x, t.y, t.z);
+      }
+      cost = sphere_scene_swept<4>(c, sp.w, eta, w, hp, pv, hn, nx, no_cuboids, no_voxels, env, g, &a.meshes);
+      if (a.speed_metric && hp && hn) speed_metric(pv, c, nx, __ldg(a.speed_dt), cost, g);
+    }
+    float4 *gp = reinterpret_cast<float4 *>(a.gradient + 4 * i);
+    if (a.accumulate) {
+      const float4 g0 = *gp;
+      a.distance[i] += cost;
+      *gp = make_float4(g0.x + g.x, g0.y + g.y, g0.z + g.z, 0.0f);
+    } else {
+      a.distance[i] = cost;
+      *gp = make_float4(g.x, g.y, g.z, 0.0f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Drop-in tool pose cost: thread per (b,h,l)
 // ------------------------------------------------------------------------------------------------
 struct PoseArgs {
@@ -2335,6 +2392,26 @@ int cb200_swept_sphere_obstacle_collision(float *distance, float *gradient, cons
                                           int horizon, int num_spheres, int use_multi_env, cb200_stream_t stream) {
   return scene_launch(distance, gradient, spheres, cuboids, voxels, weight, activation_distance, speed_dt,
                       enable_speed_metric, env_query_idx, batch_size, horizon, num_spheres, use_multi_env, 1, stream);
+}
+
+int cb200_sphere_mesh_collision(float *distance, float *gradient, const float *spheres, const cb200_mesh_set *meshes,
+                                const float *weight, const float *activation_distance, const float *speed_dt,
+                                int enable_speed_metric, const int32_t *env_query_idx, int batch_size, int horizon,
+                                int num_spheres, int use_multi_env, int sweep, int accumulate, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(distance);
+  const long long total = (long long)batch_size * horizon * num_spheres;
+  if (total == 0) return ret(cudaSuccess);
+  if (total < 0 || meshes == nullptr || meshes->nodes == nullptr || meshes->triangles == nullptr ||
+      (enable_speed_metric && speed_dt == nullptr))
+    return ret(cudaErrorInvalidValue);
+  MeshSet ms{reinterpret_cast<const float4 *>(meshes->nodes), reinterpret_cast<const float4 *>(meshes->triangles),
+             meshes->node_offset, meshes->triangle_offset, meshes->dims, meshes->inv_pose, meshes->enable, meshes->count,
+             meshes->max_n, meshes->num_envs};
+  MeshSceneArgs a{distance, gradient, spheres, weight, activation_distance, speed_dt, ms, env_query_idx, batch_size, horizon,
+                  num_spheres, use_multi_env && env_query_idx != nullptr, sweep, enable_speed_metric, accumulate};
+  const int grid = persistent_grid(mesh_collision_kernel, 128, 0, (total + 127) / 128);
+  CB200_LAUNCH(mesh_collision_kernel, grid, 128, 0, (cudaStream_t)stream, a);
+  return launch_status();
 }
 
 int cb200_tool_pose_distance(float *out_distance, float *out_position_distance, float *out_rotation_distance,

@@ -404,9 +404,10 @@ CB_HD SdfGrad mesh_sdf_grad(const float4 *nodes, const float4 *tris, V3 p, float
 template <int SCENE>
 CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p, float need_below = 3.0e38f, bool use_mip = false) {
   if ((SCENE & 4) && (SCENE == 4 || o.kind == 2)) {
-    // data_mesh.py:671-677: max_distance = max(half the bounding-box diagonal, the query's radius + activation distance)
+    // data_mesh.py:671-677: max_distance = max(half the bounding-box diagonal, query_distance); the callers pass the query
+    // distance (sphere radius + activation distance) as `need_below`
     const float half_diag = 0.5f * sqrtf(o.a * o.a + o.b * o.b + o.c * o.c);
-    return mesh_sdf_grad(o.mnodes, o.mtris, p, fmaxf(half_diag, o.max_dist));
+    return mesh_sdf_grad(o.mnodes, o.mtris, p, fmaxf(half_diag, need_below));
   }
   if (SCENE == 1) return cuboid_sdf_grad(p, o.a, o.b, o.c);
   if (SCENE == 2) return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below, use_mip ? o.mip : nullptr);
@@ -416,8 +417,9 @@ CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p, float need_below = 3.0e38f, 
 
 // Iterate every enabled obstacle of env `env` (cuboids then voxel grids) and call fn(frame, obstacle).
 // SCENE is a compile-time mask (bit 0: cuboids, bit 1: voxel grids) so specialised kernels carry no dead code.
-template <int SCENE, typename Fn>
-CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, Fn fn) {
+// Mesh obstacles (SCENE bit 2) come through `ms`, a pointer to a MeshSet (cb200_mesh.cuh) or null.
+template <int SCENE, typename Fn, typename Meshes = MeshSet>
+CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, Fn fn, const Meshes *ms = nullptr) {
   if ((SCENE & 1) && cs.inv_pose != nullptr) {
     int ce = env < cs.num_envs ? env : 0;
     int n = cs.count[ce];
@@ -460,13 +462,38 @@ CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, F
       fn(load_obs_frame(vx.inv_pose + 8 * k), o);
     }
   }
+  if constexpr ((SCENE & 4) != 0) {
+    if (ms != nullptr && ms->inv_pose != nullptr) {
+      int me = env < ms->num_envs ? env : 0;
+      int n = ms->count[me];
+      if (n > ms->max_n) n = ms->max_n;
+      #pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        int k = me * ms->max_n + i;
+        if (ms->enable[k] != 1) continue;
+        Obstacle o;
+        o.kind = 2;
+        o.a = ldgf(ms->dims + 4 * k + 0);
+        o.b = ldgf(ms->dims + 4 * k + 1);
+        o.c = ldgf(ms->dims + 4 * k + 2);
+        o.feat = nullptr;
+        o.mip = nullptr;
+        o.nx = o.ny = o.nz = 0;
+        o.vs = 0.f;
+        o.max_dist = 0.f;
+        o.mnodes = ms->nodes + 2 * (size_t)ms->node_off[k];
+        o.mtris = ms->tris + 8 * (size_t)ms->tri_off[k];
+        fn(load_obs_frame(ms->inv_pose + 8 * k), o);
+      }
+    }
+  }
 }
 
 // Discrete sphere-vs-scene: returns weighted cost, adds weighted world-frame gradient to g.
 // (wp_collision_kernel.py:112-166)
-template <int SCENE = 3>
+template <int SCENE = 3, typename Meshes = MeshSet>
 CB_HD float sphere_scene_discrete(V3 c, float r, float eta, float w, const CuboidSet &cs, const VoxelSet &vx, int env,
-                                  V3 &g) {
+                                  V3 &g, const Meshes *ms = nullptr) {
   float cost = 0.0f;
   if (r < 0.0f) return 0.0f;
   const float radj = r + eta;
@@ -481,15 +508,15 @@ CB_HD float sphere_scene_discrete(V3 c, float r, float eta, float w, const Cuboi
       cost += w * ac;
       g = g + (w * as) * gw;
     }
-  });
+  }, ms);
   return cost;
 }
 
 // Swept sphere-vs-scene (wp_sweep_collision_kernel.py:137-260).  prev/next are the same sphere at
 // h-1 / h+1 (has_prev / has_next false at the trajectory ends).
-template <int SCENE = 3>
+template <int SCENE = 3, typename Meshes = MeshSet>
 CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev, V3 prev, bool has_next, V3 next,
-                               const CuboidSet &cs, const VoxelSet &vx, int env, V3 &g) {
+                               const CuboidSet &cs, const VoxelSet &vx, int env, V3 &g, const Meshes *ms = nullptr) {
   float cost = 0.0f;
   if (r < 0.0f) return 0.0f;
   const float radj = r + eta;
@@ -536,7 +563,7 @@ CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev,
       cost += w * csum;
       g = g + w * qrot(qconj(f.q), gsum);
     }
-  });
+  }, ms);
   return cost;
 }
 

@@ -26,6 +26,12 @@ class VoxelSet(C.Structure):
                 ("num_envs", C.c_int32), ("max_dist", C.c_float), ("mip", C.c_void_p), ("mip_stride", C.c_int32)]
 
 
+class MeshSet(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("triangles", C.c_void_p), ("node_offset", C.c_void_p), ("triangle_offset", C.c_void_p),
+                ("dims", C.c_void_p), ("inv_pose", C.c_void_p), ("enable", C.c_void_p), ("count", C.c_void_p),
+                ("max_n", C.c_int32), ("num_envs", C.c_int32)]
+
+
 class RobotSizes(C.Structure):
     _fields_ = [("num_links", C.c_int32), ("num_dof", C.c_int32), ("num_spheres", C.c_int32),
                 ("num_tool_frames", C.c_int32), ("num_pairs", C.c_int32), ("num_sphere_configs", C.c_int32)]
@@ -94,6 +100,7 @@ _SIGS = {
     "cb200_rnea_forward": ([c_p] * 15 + [_I] * 4 + [c_p, c_p], _I),
     "cb200_rnea_backward": ([c_p] * 17 + [_I] * 4 + [c_p, c_p], _I),
     "cb200_pba3d": ([c_p, c_p, _I, _I, _I, _I, c_p], _I),
+    "cb200_sphere_mesh_collision": ([c_p, c_p, c_p, C.POINTER(MeshSet), c_p, c_p, c_p, _I, c_p, _I, _I, _I, _I, _I, _I, c_p], _I),
     "cb200_edt_unsigned_distance": ([c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),
     "cb200_esdf_seed_sites": ([c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),
     "cb200_esdf_signed_distance": ([c_p, c_p, c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),

@@ -99,9 +99,10 @@ def voxel_mip_is_fresh(d) -> bool:
 class SceneData:
     cuboid: Optional[CuboidData] = None
     voxel: Optional[VoxelData] = None
+    mesh: Optional[object] = None          # curobo_b200.mesh.MeshData
 
     def get_valid_data(self) -> List[object]:
-        return [d for d in (self.cuboid, self.voxel) if d is not None]
+        return [d for d in (self.cuboid, self.voxel, self.mesh) if d is not None]
 
 
 @dataclass
@@ -118,15 +119,17 @@ class CollisionBuffer:
 
 
 def _split_scene(scene):
-    cub = vox = None
+    cub = vox = mesh = None
     for d in scene.get_valid_data():
         if hasattr(d, "features"):
             vox = d
+        elif hasattr(d, "triangles"):
+            mesh = d
         elif hasattr(d, "dims"):
             cub = d
         else:
-            raise ValueError("b200 scene collision supports cuboid and voxel (ESDF) obstacles; mesh is out of scope")
-    return cub, vox
+            raise ValueError("b200 scene collision supports cuboid, voxel (ESDF) and mesh obstacles")
+    return cub, vox, mesh
 
 
 def c_cuboid_set(d: Optional[object], dev=None) -> Optional[_lib.CuboidSet]:
@@ -162,7 +165,7 @@ def _launch(sweep, query_spheres, buffer, scene, weight, activation_distance, sp
     b, h, n, _ = query_spheres.shape
     check_tensors(dev, torch.float32, query_spheres=query_spheres, distance=buffer.distance,
                   gradient=buffer.gradient, weight=weight, activation_distance=activation_distance)
-    cub, vox = _split_scene(scene)
+    cub, vox, mesh = _split_scene(scene)
     cs, vs = c_cuboid_set(cub, dev), c_voxel_set(vox, dev)
     cp = C.byref(cs) if cs is not None else None
     vp = C.byref(vs) if vs is not None else None
@@ -183,6 +186,16 @@ def _launch(sweep, query_spheres, buffer, scene, weight, activation_distance, sp
             weight.data_ptr(), activation_distance.data_ptr(), speed_dt.data_ptr() if speed_dt is not None else None,
             int(bool(enable_speed_metric)), eq, b, h, n, int(bool(use_multi_env)), stream_ptr(dev))
     _lib.check(err, "sphere_obstacle_collision")
+    if mesh is not None:
+        # one more launch for the mesh obstacle type, adding to the buffers the launch above wrote (it zero-fills them when
+        # there are no cuboids / grids) -- the reference launches its generic kernel once per obstacle type too
+        from .mesh import c_mesh_set
+        ms = c_mesh_set(mesh, dev)
+        err = L.cb200_sphere_mesh_collision(
+            buffer.distance.data_ptr(), buffer.gradient.data_ptr(), query_spheres.data_ptr(), C.byref(ms), weight.data_ptr(),
+            activation_distance.data_ptr(), speed_dt.data_ptr() if (sweep and speed_dt is not None) else None,
+            int(bool(sweep and enable_speed_metric)), eq, b, h, n, int(bool(use_multi_env)), int(bool(sweep)), 1, stream_ptr(dev))
+        _lib.check(err, "sphere_mesh_collision")
 
 
 class SphereObstacleCollision(torch.autograd.Function):

@@ -129,6 +129,29 @@ typedef struct {
 int cb200_voxel_mip_block(void);
 /* mip_stride needed for a grid set: max over layers of ceil(nx/B)*ceil(ny/B)*ceil(nz/B) (HOST params pointer). */
 int64_t cb200_voxel_mip_stride(const float *host_params, int num_layers);
+/* Mesh obstacles (curobo/_src/geom/data/data_mesh.py:40-520 MeshData; the Warp mesh handles are replaced by BVHs built on the
+ * host by curobo_b200/mesh.py).  Node = 2 float4 (box min, skip link) (box max, leaf word); triangle = 8 float4 (a, b, c, face
+ * normal, edge pseudo-normals ab / bc / ca, vertex pseudo-normals in the w lanes): curobo_b200/csrc/cb200_mesh.cuh. */
+typedef struct cb200_mesh_set {
+  const float *nodes;             /* all meshes' BVH nodes, 8 floats each */
+  const float *triangles;         /* all meshes' triangles, 32 floats each */
+  const int32_t *node_offset;     /* [num_envs * max_n] first node of mesh k */
+  const int32_t *triangle_offset; /* [num_envs * max_n] first triangle of mesh k */
+  const float *dims;              /* [num_envs * max_n, 4] bounding-box extents */
+  const float *inv_pose;          /* [num_envs * max_n, 8] x y z qw qx qy qz pad */
+  const uint8_t *enable;          /* [num_envs * max_n] */
+  const int32_t *count;           /* [num_envs] */
+  int32_t max_n, num_envs;
+} cb200_mesh_set;
+
+/* Sphere / swept-sphere collision against mesh obstacles: the reference's generic collision kernels instantiated for MeshData
+ * (geom/collision/wp_collision_kernel.py:70-166, wp_sweep_collision_kernel.py:83-260 with data_mesh.py:643-700 as the SDF).
+ * accumulate = 1 adds to distance / gradient (after the cuboid / ESDF launch), 0 overwrites. */
+int cb200_sphere_mesh_collision(float *distance, float *gradient, const float *spheres, const cb200_mesh_set *meshes,
+                                const float *weight, const float *activation_distance, const float *speed_dt,
+                                int enable_speed_metric, const int32_t *env_query_idx, int batch_size, int horizon,
+                                int num_spheres, int use_multi_env, int sweep, int accumulate, cb200_stream_t stream);
+
 /* Fill vs->mip (device, num_envs*max_n*mip_stride uint16) from vs->features / vs->params on `stream`. */
 int cb200_voxel_build_mip(const cb200_voxel_set *vs, cb200_stream_t stream);
 

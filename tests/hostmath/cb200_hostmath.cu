@@ -258,3 +258,16 @@ void hm_pba3d_tiles(int32_t *grid, int nx, int ny, int nz, int n_ctas) {
   hm_banded_pass(ed::BandedEnvelope<0>{p.x}, tile, n_ctas);
 }
 }
+
+// ---- mesh obstacles (cb200_mesh.cuh): the device routine over a host-built BVH -----------------------------------------
+#include "../../curobo_b200/csrc/cb200_mesh.cuh"
+extern "C" void hm_mesh_sdf(const float *nodes, const float *tris, const float *points, int n, float max_distance, float *out) {
+  for (int i = 0; i < n; ++i) {
+    const cb200::SdfGrad r = cb200::mesh_sdf_grad(reinterpret_cast<const float4 *>(nodes), reinterpret_cast<const float4 *>(tris),
+                                                  cb200::mk3(points[3 * i], points[3 * i + 1], points[3 * i + 2]), max_distance);
+    out[4 * i] = r.sdf;
+    out[4 * i + 1] = r.n.x;
+    out[4 * i + 2] = r.n.y;
+    out[4 * i + 3] = r.n.z;
+  }
+}

@@ -252,6 +252,16 @@ def test_reference_call_sites_over_b200_backend(run):
     run("test_gpu_reference_callsites", "test_reference_lbfgs_function_over_b200_backend", ref)
 
 
+def test_mesh_obstacles(run):
+    """Mesh obstacles through the emulated mesh_collision_kernel: box mesh == cuboid (the reference's regression), brute-force
+    oracle, mesh + cuboid accumulation / multi-env / disabled slots."""
+    run("test_gpu_mesh", "test_box_mesh_costs_what_the_cuboid_costs", False)
+    run("test_gpu_mesh", "test_box_mesh_costs_what_the_cuboid_costs", True)
+    run("test_gpu_mesh", "test_mesh_collision_vs_brute_force_oracle", "icosphere")
+    run("test_gpu_mesh", "test_mesh_collision_vs_brute_force_oracle", "box")
+    run("test_gpu_mesh", "test_mesh_with_cuboids_multi_env_and_disabled_slots")
+
+
 def test_pending_edt(run):
     mod = importlib.import_module("test_gpu_zz_edt")
     from edt_cases import MEDIUM, SMALL
