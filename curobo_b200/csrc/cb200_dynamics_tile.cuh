@@ -25,13 +25,9 @@ constexpr int kTileIo = 8;
 __host__ __device__ inline int tile_floats(int nl, int D, int R) { return (5 * 6 * nl + 2 * nl + kTileIo * D) * (R + 1); }
 
 #if defined(__CUDACC__) || defined(CB200_SIMT_EMULATION)
-// who meets at the phase boundaries: the whole CTA (every thread runs the tile functions) or one warp (a producer warp runs
-// them alone while the other warps of the CTA do something else)
+// who meets at the phase boundaries: the whole CTA (every thread of the CTA runs the tile functions)
 struct SyncCta {
   static __device__ __forceinline__ void sync() { __syncthreads(); }
-};
-struct SyncWarp {
-  static __device__ __forceinline__ void sync() { __syncwarp(); }
 };
 
 template <class L>

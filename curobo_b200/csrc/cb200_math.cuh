@@ -400,14 +400,14 @@ struct Obstacle {
 };
 struct MeshSet;
 // mesh SDF through the BVH (cb200_mesh.cuh); declared here so that obstacle_sdf can dispatch to it
-CB_HD SdfGrad mesh_sdf_grad(const float4 *nodes, const float4 *tris, V3 p, float max_distance);
+CB_HD SdfGrad mesh_sdf_grad(const float4 *nodes, const float4 *tris, V3 p, float max_distance, float need_below);
 template <int SCENE>
 CB_HD SdfGrad obstacle_sdf(const Obstacle &o, V3 p, float need_below = 3.0e38f, bool use_mip = false) {
   if ((SCENE & 4) && (SCENE == 4 || o.kind == 2)) {
     // data_mesh.py:671-677: max_distance = max(half the bounding-box diagonal, query_distance); the callers pass the query
     // distance (sphere radius + activation distance) as `need_below`
     const float half_diag = 0.5f * sqrtf(o.a * o.a + o.b * o.b + o.c * o.c);
-    return mesh_sdf_grad(o.mnodes, o.mtris, p, fmaxf(half_diag, need_below));
+    return mesh_sdf_grad(o.mnodes, o.mtris, p, fmaxf(half_diag, need_below), need_below);
   }
   if (SCENE == 1) return cuboid_sdf_grad(p, o.a, o.b, o.c);
   if (SCENE == 2) return voxel_sdf_grad(p, o.feat, o.nx, o.ny, o.nz, o.vs, o.max_dist, need_below, use_mip ? o.mip : nullptr);

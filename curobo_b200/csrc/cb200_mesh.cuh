@@ -92,8 +92,23 @@ CB_HD V3 tri_normal(const float4 *t, int feat) {
   return mk3(ld4(t + 6).w, l.x, l.y);
 }
 
-// signed distance + local gradient, data_mesh.py:643-700
-CB_HD SdfGrad mesh_sdf_grad(const float4 *nodes, const float4 *tris, V3 p, float max_distance) {
+// signed distance + local gradient, data_mesh.py:643-700.
+// `need_below`: the caller only acts on sdf < need_below (penetration = radius + activation distance - sdf > 0).  A point whose
+// distance to the mesh's bounding box is already >= need_below cannot get there (it is outside the mesh and farther from every
+// triangle than from the box), so the traversal is skipped -- exact for the collision cost, and what makes a mesh cheap for the
+// many spheres that are nowhere near it.
+CB_HD SdfGrad mesh_sdf_grad(const float4 *nodes, const float4 *tris, V3 p, float max_distance, float need_below = 3.0e38f) {
+  {
+    const float4 lo = ld4(nodes), hi = ld4(nodes + 1);
+    const float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.0f), dy = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.0f),
+                dz = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.0f);
+    if (need_below < 1.0e37f && dx * dx + dy * dy + dz * dz >= need_below * need_below) {
+      SdfGrad far;
+      far.sdf = need_below;
+      far.n = mk3(0.f, 0.f, 0.f);
+      return far;
+    }
+  }
   float best2 = max_distance * max_distance;
   int best_t = -1, best_f = 0;
   V3 best_c = p;
