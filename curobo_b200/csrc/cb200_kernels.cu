@@ -325,7 +325,7 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
             const int kk = ce * a.cuboids.max_n + i;
             if (a.cuboids.enable[kk] != 1) continue;
             const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
-            const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cw) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+            const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, cw), ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
                                                ldgf(a.cuboids.dims + 4 * kk + 2));
             if (sg.sdf < cb.w + cfg.scene_activation) mask |= (1u << i);
           }
@@ -354,14 +354,14 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
               const int kk = ce * a.cuboids.max_n + i;
               if (a.cuboids.enable[kk] != 1) continue;
               const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
-              const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cen) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+              const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, cen), ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
                                                  ldgf(a.cuboids.dims + 4 * kk + 2));
               const float pen = radj - sg.sdf;
               if (pen > 0.0f) {
                 float ac, as;
                 collision_activation(pen, cfg.scene_activation, ac, as);
                 c += cfg.scene_weight * ac;
-                g = g + (cfg.scene_weight * as) * qrot(qconj(f.q), sg.n);
+                g = g + (cfg.scene_weight * as) * from_obstacle(f, sg.n);
               }
             }
           }
@@ -553,7 +553,7 @@ __device__ __forceinline__ RowB1 row_phase_b1_list(const FusedArgs &a, const Rob
             const int kk = ce * a.cuboids.max_n + i;
             if (a.cuboids.enable[kk] != 1) continue;
             const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
-            const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cw) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+            const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, cw), ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
                                                ldgf(a.cuboids.dims + 4 * kk + 2));
             if (sg.sdf < cb.w + cfg.scene_activation) mask |= (1u << i);
           }
@@ -584,14 +584,14 @@ __device__ __forceinline__ RowB1 row_phase_b1_list(const FusedArgs &a, const Rob
             const int kk = ce * a.cuboids.max_n + i;
             if (a.cuboids.enable[kk] != 1) continue;
             const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
-            const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cen) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+            const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, cen), ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
                                                ldgf(a.cuboids.dims + 4 * kk + 2));
             const float pen = radj - sg.sdf;
             if (pen > 0.0f) {
               float ac, as;
               collision_activation(pen, cfg.scene_activation, ac, as);
               c += cfg.scene_weight * ac;
-              g = g + (cfg.scene_weight * as) * qrot(qconj(f.q), sg.n);
+              g = g + (cfg.scene_weight * as) * from_obstacle(f, sg.n);
             }
           }
         }
@@ -1448,7 +1448,7 @@ __global__ void __launch_bounds__(kLaneThreads, 4) rollout_lane_kernel(const __g
                 const int kk = ce * a.cuboids.max_n + i;
                 if (a.cuboids.enable[kk] != 1) continue;
                 const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
-                const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, cw) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, cw), ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
                                                    ldgf(a.cuboids.dims + 4 * kk + 2));
                 if (sg.sdf < cb.w + cfg.scene_activation) cmask |= (1u << i);
               }
@@ -1471,14 +1471,14 @@ __global__ void __launch_bounds__(kLaneThreads, 4) rollout_lane_kernel(const __g
                 const int kk = ce * a.cuboids.max_n + i;
                 if (a.cuboids.enable[kk] != 1) continue;
                 const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
-                const SdfGrad sg = cuboid_sdf_grad(qrot(f.q, pw) + f.p, ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, pw), ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
                                                    ldgf(a.cuboids.dims + 4 * kk + 2));
                 const float pen = radj - sg.sdf;
                 if (pen > 0.0f) {
                   float ac, as;
                   collision_activation(pen, cfg.scene_activation, ac, as);
                   c += cfg.scene_weight * ac;
-                  g = g + (cfg.scene_weight * as) * qrot(qconj(f.q), sg.n);
+                  g = g + (cfg.scene_weight * as) * from_obstacle(f, sg.n);
                 }
               }
             }

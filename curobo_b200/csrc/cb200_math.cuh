@@ -380,13 +380,19 @@ CB_HD float ldgf(const float *p) {
 struct ObsFrame {  // world -> obstacle transform
   V3 p;
   Q4 q;
+  bool ident;  // q == (0, 0, 0, 1): the obstacle is axis-aligned with the world (the usual case for ESDF grids and tables)
 };
 CB_HD ObsFrame load_obs_frame(const float *inv_pose8) {
   ObsFrame f;
   f.p = mk3(ldgf(inv_pose8 + 0), ldgf(inv_pose8 + 1), ldgf(inv_pose8 + 2));
   f.q = Q4{ldgf(inv_pose8 + 4), ldgf(inv_pose8 + 5), ldgf(inv_pose8 + 6), ldgf(inv_pose8 + 3)};
+  f.ident = f.q.x == 0.0f && f.q.y == 0.0f && f.q.z == 0.0f && f.q.w == 1.0f;
   return f;
 }
+// world point -> obstacle frame, obstacle-frame vector -> world.  With the identity rotation qrot returns its argument bit for bit
+// (v * 1 + 0 + 0), so skipping it changes no result; the branch is uniform (every lane looks at the same obstacle).
+CB_HD V3 to_obstacle(const ObsFrame &f, V3 pw) { return f.ident ? pw + f.p : qrot(f.q, pw) + f.p; }
+CB_HD V3 from_obstacle(const ObsFrame &f, V3 v) { return f.ident ? v : qrot(qconj(f.q), v); }
 
 // One obstacle abstraction so discrete and swept code is written once.
 struct Obstacle {
@@ -498,13 +504,13 @@ CB_HD float sphere_scene_discrete(V3 c, float r, float eta, float w, const Cuboi
   if (r < 0.0f) return 0.0f;
   const float radj = r + eta;
   for_each_obstacle<SCENE>(cs, vx, env, [&](const ObsFrame &f, const Obstacle &o) {
-    V3 lp = qrot(f.q, c) + f.p;
+    V3 lp = to_obstacle(f, c);
     SdfGrad sg = obstacle_sdf<SCENE>(o, lp, radj, true);
     float pen = radj - sg.sdf;
     if (pen > 0.0f) {
       float ac, as;
       collision_activation(pen, eta, ac, as);
-      V3 gw = qrot(qconj(f.q), sg.n);
+      V3 gw = from_obstacle(f, sg.n);
       cost += w * ac;
       g = g + (w * as) * gw;
     }
@@ -521,7 +527,7 @@ CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev,
   if (r < 0.0f) return 0.0f;
   const float radj = r + eta;
   for_each_obstacle<SCENE>(cs, vx, env, [&](const ObsFrame &f, const Obstacle &o) {
-    V3 lc = qrot(f.q, c) + f.p;
+    V3 lc = to_obstacle(f, c);
     float csum = 0.0f;
     V3 gsum = mk3(0.f, 0.f, 0.f);
     {
@@ -537,7 +543,7 @@ CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev,
 #pragma unroll 1
     for (int dir = 0; dir < 2; ++dir) {
       if (!(dir == 0 ? has_prev : has_next)) continue;
-      V3 ln = qrot(f.q, dir == 0 ? prev : next) + f.p;
+      V3 ln = to_obstacle(f, dir == 0 ? prev : next);
       float half = norm(ln - lc) * 0.5f;
       float inv_half = 1.0f / fmaxf(half, 0.001f);
       float jump = 0.0f;
@@ -561,7 +567,7 @@ CB_HD float sphere_scene_swept(V3 c, float r, float eta, float w, bool has_prev,
     }
     if (csum > 0.0f) {
       cost += w * csum;
-      g = g + w * qrot(qconj(f.q), gsum);
+      g = g + w * from_obstacle(f, gsum);
     }
   }, ms);
   return cost;
