@@ -565,61 +565,12 @@ __device__ __forceinline__ RowB1 row_phase_b1_list(const FusedArgs &a, const Rob
   }
   bool ft_live = false;
   const unsigned lt = (1u << lane) - 1u;
-  // ESDF-only scenes with ONE grid that carries the lower-bound level: a cull pre-pass with four spheres' look-ups in flight per
-  // lane.  The level entry alone decides "cannot be active" (exactly the test voxel_sdf_grad makes first); only the survivors
-  // (a handful per row in free space) take the full path below.  Four independent L2 loads per lane instead of a chain of
-  // dependent ones: the sphere loop of a humanoid row is 13 passes long and each pass used to wait for its own look-up.
-  bool fast_cull = false;
-  ObsFrame vf{};
-  int vnx = 0, vny = 0, vnz = 0;
-  float vvs = 0.0f;
-  const uint16_t *vmip = nullptr;
-  if (SCENE == 2 && do_scene && a.voxels.mip != nullptr && a.voxels.inv_pose != nullptr) {
-    const int ve = env < a.voxels.num_envs ? env : 0;
-    if (a.voxels.count[ve] == 1 && a.voxels.enable[ve * a.voxels.max_n] == 1) {
-      const int k = ve * a.voxels.max_n;
-      vf = load_obs_frame(a.voxels.inv_pose + 8 * k);
-      vnx = (int)ldgf(a.voxels.params + 4 * k), vny = (int)ldgf(a.voxels.params + 4 * k + 1), vnz = (int)ldgf(a.voxels.params + 4 * k + 2);
-      vvs = ldgf(a.voxels.params + 4 * k + 3);
-      vmip = a.voxels.mip + (size_t)k * a.voxels.mip_stride;
-      fast_cull = true;
-    }
-  }
 #pragma unroll 1
-  for (int base4 = 0; base4 < S; base4 += 128) {
-    unsigned keep = 0xfu;  // bit u: sphere base4 + 32 u + lane needs the full evaluation
-    if (fast_cull) {
-      const uint16_t *ent[4];
-      float radj[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int s = base4 + 32 * u + lane;
-        ent[u] = nullptr;
-        radj[u] = -1.0f;
-        if (s < S) {
-          const float4 sp = es.sph[s];
-          if (sp.w >= 0.0f) {
-            radj[u] = sp.w + cfg.scene_activation;
-            ent[u] = voxel_mip_entry(to_obstacle(vf, mk3(sp.x, sp.y, sp.z)), vnx, vny, vnz, vvs, vmip);
-          }
-        }
-      }
-      float lb[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) lb[u] = ent[u] != nullptr ? load_half(ent[u]) : -3.0e38f;  // undecidable -> full path
-      keep = 0u;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (radj[u] >= 0.0f && lb[u] < radj[u]) keep |= 1u << u;  // disabled spheres (radius < 0) cost nothing either way
-    }
-#pragma unroll 1
-    for (int u = 0; u < 4; ++u) {
-    const int base = base4 + 32 * u;
-    if (base >= S) break;
+  for (int base = 0; base < S; base += 32) {  // uniform trip count: the list append below is a warp collective
     const int s = base + lane;
     V3 g = mk3(0, 0, 0);
     float c = 0.0f;
-    if (s < S && do_scene && ((keep >> u) & 1u)) {
+    if (s < S && do_scene) {
       const float4 sp = es.sph[s];
       const V3 cen = mk3(sp.x, sp.y, sp.z);
       if (sp.w >= 0.0f) {
@@ -669,7 +620,6 @@ __device__ __forceinline__ RowB1 row_phase_b1_list(const FusedArgs &a, const Rob
     }
     r.scene_c += c;
     if (a.scene_cost && s < S) a.scene_cost[(size_t)e * S + s] = c;
-    }
   }
   if (dense && !ft_live) warp_zero_ft(rv, es, lane);
   return r;

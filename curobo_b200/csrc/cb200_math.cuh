@@ -495,23 +495,6 @@ CB_HD void for_each_obstacle(const CuboidSet &cs, const VoxelSet &vx, int env, F
   }
 }
 
-// Address of the lower-bound level entry that decides whether the ESDF sample at local point p can be active (the test
-// inside voxel_sdf_grad, split off so that a caller can put several spheres' look-ups in flight before acting on any of them).
-// Returns nullptr when the level cannot decide (sample outside the grid, degenerate grid): the caller then takes the full path.
-CB_HD const uint16_t *voxel_mip_entry(V3 p, int nx, int ny, int nz, float vs, const uint16_t *mip) {
-  if (mip == nullptr || nx < 2 || ny < 2 || nz < 2) return nullptr;
-  const float inv = 1.0f / vs;
-  const float vx = p.x * inv + (float)nx * 0.5f - 0.5f, vy = p.y * inv + (float)ny * 0.5f - 0.5f,
-              vz = p.z * inv + (float)nz * 0.5f - 0.5f;
-  const int x0 = (int)floorf(vx), y0 = (int)floorf(vy), z0 = (int)floorf(vz);
-  const bool xk = (x0 >= 0 && x0 < nx) || (x0 + 1 >= 0 && x0 + 1 < nx), yk = (y0 >= 0 && y0 < ny) || (y0 + 1 >= 0 && y0 + 1 < ny),
-             zk = (z0 >= 0 && z0 < nz) || (z0 + 1 >= 0 && z0 + 1 < nz);
-  if (!(xk && yk && zk)) return nullptr;
-  const int my = (ny + kMipBlock - 1) >> kMipShift, mz = (nz + kMipBlock - 1) >> kMipShift;
-  const int cx = (x0 < 0 ? 0 : x0) >> kMipShift, cy = (y0 < 0 ? 0 : y0) >> kMipShift, cz = (z0 < 0 ? 0 : z0) >> kMipShift;
-  return mip + ((size_t)cx * my + cy) * mz + cz;
-}
-
 // Discrete sphere-vs-scene: returns weighted cost, adds weighted world-frame gradient to g.
 // (wp_collision_kernel.py:112-166)
 template <int SCENE = 3, typename Meshes = MeshSet>
