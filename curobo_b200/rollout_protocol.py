@@ -207,6 +207,11 @@ class B200RobotRollout:
     def sum_horizon(self) -> bool:
         return self._sum_horizon
 
+    @sum_horizon.setter
+    def sum_horizon(self, value: bool) -> None:
+        # the reference's optimizer core sets this on the rollout it drives (gradient_opt_core.py:113)
+        self._sum_horizon = bool(value)
+
     @property
     def batch_size(self) -> int:
         return self._batch_size

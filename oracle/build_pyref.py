@@ -23,7 +23,9 @@ REFERENCE = "/root/reference"
 OUT = os.path.join(ROOT, "oracle", "_ref", "pyref")
 CALL_SITES = ["curobo._src.curobolib.cuda_ops.kinematics", "curobo._src.curobolib.cuda_ops.geometry",
               "curobo._src.curobolib.cuda_ops.trajectory", "curobo._src.curobolib.cuda_ops.optimization",
-              "curobo._src.curobolib.cuda_ops.dynamics", "curobo._src.curobolib.backends"]
+              "curobo._src.curobolib.cuda_ops.dynamics", "curobo._src.curobolib.backends",
+              # the optimizer that drives the Rollout protocol (its step direction and line search call the backends too)
+              "curobo._src.optim.gradient.lbfgs"]
 
 
 def build(verbose: bool = False) -> str:

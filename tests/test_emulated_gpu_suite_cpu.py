@@ -250,6 +250,8 @@ def test_reference_call_sites_over_b200_backend(run):
     run("test_gpu_reference_callsites", "test_reference_self_collision_function_over_b200_backend", ref, "franka", 12)
     run("test_gpu_reference_callsites", "test_reference_bspline_function_over_b200_backend", ref, True)
     run("test_gpu_reference_callsites", "test_reference_lbfgs_function_over_b200_backend", ref)
+    # the reference's optimizer on top of the Rollout-protocol adapter (25 iterations, 6 problems here; 100 x 24 on the GPU)
+    run("test_gpu_reference_callsites", "test_reference_lbfgs_optimizer_drives_the_b200_rollout", ref, 25, 6)
 
 
 def test_mesh_obstacles(run):

@@ -71,6 +71,7 @@ def load_reference():
         geometry = importlib.import_module("curobo._src.curobolib.cuda_ops.geometry")
         trajectory = importlib.import_module("curobo._src.curobolib.cuda_ops.trajectory")
         optimization = importlib.import_module("curobo._src.curobolib.cuda_ops.optimization")
+        lbfgs = importlib.import_module("curobo._src.optim.gradient.lbfgs")
         params = importlib.import_module("curobo._src.robot.types.kinematics_params")
         device_cfg = importlib.import_module("curobo._src.types.device_cfg")
     assert cb.get_backend_name() == "b200"
@@ -211,3 +212,55 @@ def test_reference_lbfgs_function_over_b200_backend(ref):
         rstep = torch.zeros_like(step)
         ref_kernels.lbfgs_step(rstep, r["rho"], r["Y"], r["S"], r["q"], r["x_0"], r["grad_0"], r["grad_q"], 0.01, True, True)
         assert np.allclose(out.cpu().numpy().reshape(B, V), rstep.cpu().numpy(), rtol=1e-6, atol=1e-7 * np.abs(w_step).max())
+
+
+def test_reference_lbfgs_optimizer_drives_the_b200_rollout(ref, iters=100, problems=24):
+    """One level up: the reference's own optimizer -- LBFGSOpt + GradientOptCore (optim/gradient/lbfgs.py:157-400,
+    optim/components/gradient_opt_core.py:255-480: line-search strategy, best tracker, `_compute_cost_constraint_and_gradient`) --
+    is constructed on two `B200RobotRollout` instances (the `Rollout` protocol, rollout/rollout_protocol.py:35-176) and solves a batch
+    of IK problems.  Everything below its Python is this repository: the fused rollout kernel behind `evaluate_action`, and
+    `launch_lbfgs_step` / `launch_line_search` behind its LBFGScu / line-search calls (backend overlay).  It must solve what
+    this repository's own LBFGSOpt solves with the same settings."""
+    from curobo_b200.kinematics import Kinematics
+    from curobo_b200.optim import LBFGSOpt as OurLBFGS, LBFGSOptCfg as OurCfg
+    from curobo_b200.robot_model import load_robot
+    from curobo_b200.rollout import RolloutConfig
+    from curobo_b200.rollout_protocol import B200RobotRollout
+    from curobo_b200.scene import CuboidData
+    from curobo_b200.world import make_benchmark_cuboid_world
+    rm = load_robot("franka")
+    P, n, D = problems, 4, rm.num_dof
+    scales = [0.0, 0.1, 0.5, 1.0]
+    cub = make_benchmark_cuboid_world()
+    rollouts = [B200RobotRollout(rm, RolloutConfig.ik(), DEV, cuboid=CuboidData.from_world(cub, DEV), horizon=1) for _ in range(2)]
+    dc = ref.device_cfg.DeviceCfg(device=torch.device(DEV))
+    cfg = ref.lbfgs.LBFGSOptCfg(num_iters=iters, inner_iters=25, num_problems=P, device_cfg=dc, line_search_scale=scales,
+                                step_scale=0.98, history=7, epsilon=0.01, initial_step_scale=0.001)
+    opt = ref.lbfgs.LBFGSOpt(cfg, rollouts, use_cuda_graph=False)
+    _, _, gp, gq = O.fk_forward(rm, random_q(rm, P, seed=11) * 0.8)
+    idx = np.repeat(np.arange(P), n).astype(np.int32)                       # rows: problem-major, particle-minor
+    for ro in rollouts:
+        ro.update_params(goal_position=T(gp[:, :, None, :]), goal_quat=T(gq[:, :, None, :]), idxs_goal=T(idx))
+    x0 = T(random_q(rm, P, seed=12)).view(P, 1, D)
+    # the CUDA event timer around optimize() needs a device; the emulated run calls the loop underneath it
+    q_ref = (opt.optimize(x0) if DEV != "cpu" else opt._core._optimize_impl(x0)).reshape(P, D).clone()
+
+    def pos_err(q):
+        st = Kinematics(rm, DEV).compute_kinematics(q.view(P, 1, D))
+        return np.linalg.norm(st.tool_pose_position.reshape(P, -1, 3)[:, 0].detach().cpu().numpy() - gp[:, 0], axis=-1)
+
+    e0, e_ref = pos_err(x0.reshape(P, D)), pos_err(q_ref)
+    assert np.median(e_ref) < (0.05 if iters >= 100 else 0.3) * np.median(e0), (np.median(e0), np.median(e_ref))
+    # this repository's optimizer, same settings, same rollout engine
+    eng = rollouts[0].engine
+
+    def cost_grad(x):
+        out = eng.evaluate_action(x.view(P * n, 1, D))
+        return out.cost.view(-1), out.grad_q.view(P * n, D)
+
+    ours = OurLBFGS(OurCfg(num_iters=iters, line_search_scale=scales, initial_step_scale=0.001), P, 1, D,
+                    T(rm.position_limits[0]), T(rm.position_limits[1]), cost_grad, DEV)
+    e_ours = pos_err(ours.optimize(x0.reshape(P, D)).reshape(P, D))
+    assert np.median(e_ref) <= 2.0 * np.median(e_ours) + 2e-3, (np.median(e_ref), np.median(e_ours))
+    if iters >= 100:
+        assert (e_ref < 5e-3).mean() >= 0.6 and abs((e_ref < 5e-3).mean() - (e_ours < 5e-3).mean()) <= 0.2, (e_ref, e_ours)
