@@ -693,6 +693,319 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_big_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small-batch variant of the big-robot kernel: a TEAM of warps per row.
+//
+// When a GPU holds fewer rows than resident warps -- BASELINE config 5 on eight GPUs is 1,024 humanoid rows for 2,368 warp
+// slots -- the launch takes one row's latency (0.11 ms for G1-29) however idle the SMs are.  Here TEAM (2 or 4) warps share one
+// row's state and split its parallel phases: local link transforms, spheres, link bounds, the link-pair scan, the ESDF sphere
+// loop and the list-based J^T are strided over TEAM x 32 lanes; the serial parts (c-space, the level-scheduled FK compose) run
+// on the team's first warp, the tool-pose cost on its last; teams meet at named barriers (one id per team), every team has its
+// own gradient-list segment (full length: no overflow case; deterministic: segment order = warp order) and partial J^T
+// accumulators.  Measured (profiles/r02_a_round2.md section 9): G1-29, 1,024 rows 104 -> 58 us; the host picks the variant by rows
+// vs resident warp slots.
+// ------------------------------------------------------------------------------------------------
+template <int TEAM>
+struct TeamScratch {  // per team, behind the row state
+  unsigned long long key[TEAM];
+  float scene_c[TEAM];
+  float cs_cost, pose_c;
+  int next_row, pad;
+};
+// list entries per WARP of a team: every sphere the warp visits may carry a gradient, + the self-collision pair.  A team kernel
+// keeps 16 / TEAM rows per SM instead of 16, so the full-length list fits and a row can never overflow it.
+__host__ __device__ inline int team_seg(int team, int S) { return ((S + team * 32 - 1) / (team * 32)) * 32 + 2; }
+__host__ __device__ inline int team_extra_floats(int team, int nl, int S) {
+  return team * nl + 28 + 4 * team + team * team_seg(team, S) * 4;
+}
+
+template <int SCENE, int TEAM>
+__global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_team_kernel(const __grid_constant__ FusedArgs a) {
+  CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
+  __shared__ unsigned long long mbar;
+  stage_blob_to_smem(smem, a.blob, (uint32_t)a.blob_smem_bytes, &mbar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int team = warp / TEAM, tw = warp - team * TEAM, nteams = nwarps / TEAM;
+  const int tlane = tw * 32 + lane, tsize = TEAM * 32;  // lane index / lane count inside the team
+  if (team >= nteams) return;                             // (blockDim is a multiple of TEAM * 32; kept for safety)
+  float *base = reinterpret_cast<float *>(smem + a.blob_smem_bytes) + (size_t)team * a.eval_floats;
+  const RobotView rv = make_robot_view(smem, a.blob);
+  const EvalSmem es = carve_big_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  float *extra = base + big_smem_floats(rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  float *partial = extra;                                   // [TEAM][nl] J^T accumulators
+  TeamScratch<TEAM> *ts = reinterpret_cast<TeamScratch<TEAM> *>(extra + ((TEAM * rv.nl + 1) & ~1));
+  float4 *my_list = reinterpret_cast<float4 *>(extra + ((TEAM * rv.nl + 24 + 4 * TEAM + 3) & ~3)) + tw * team_seg(TEAM, rv.S);
+  const int bar_id = 1 + team;
+  const cb200_rollout_cfg &cfg = a.cfg;
+  const int N = a.B * a.H, S = rv.S, D = rv.D, L = rv.L;
+  const int total_teams = gridDim.x * nteams;
+  int e = blockIdx.x * nteams + team;
+  while (e < N) {
+    int b = e, h = 0;
+    if (a.H != 1) {
+      b = e / a.H;
+      h = e - b * a.H;
+    }
+    // ---------------- phase A
+    if (tw == 0) {
+      float cs = 0.0f;
+#pragma unroll 1
+      for (int d = lane; d < D; d += 32) {
+        const bspline::State4 st = load_row_state<false>(a, e, b, h, d, D);
+        es.qv[d] = st.p;
+        float gp;
+        const float c = cspace_dof(a, rv, e, b, h, d, st, gp);
+        es.gqv[d] = gp;
+        cs += c;
+        if (a.cspace_cost) a.cspace_cost[(size_t)e * D + d] = c;
+      }
+      cs = warp_sum(cs);
+      if (lane == 0) ts->cs_cost = cs;
+    }
+    CB200_NAMED_BARRIER(bar_id, tsize);
+    {  // local link transforms over the whole team (scratch = the not-yet-written sphere area, as warp_fk)
+      const bool scratch = rv.S * 4 >= rv.nl * 12;
+      float *loc = scratch ? reinterpret_cast<float *>(es.sph) : es.cumul;
+      if (scratch || tw == 0) {
+#pragma unroll 1
+        for (int l = scratch ? tlane : lane; l < rv.nl; l += scratch ? tsize : 32) {
+          const int jt = rv.joint_type[l];
+          float th = 0.0f;
+          if (jt >= 0) th = rv.joff[2 * l] * es.qv[rv.joint_map[l]] + rv.joff[2 * l + 1];
+          local_link_transform(rv.fixed + 12 * l, jt, th, (l == 0 ? es.cumul : loc) + 12 * l);
+        }
+      }
+    }
+    CB200_NAMED_BARRIER(bar_id, tsize);
+    if (tw == 0) warp_fk_compose(rv, es, lane);
+    CB200_NAMED_BARRIER(bar_id, tsize);
+    {
+      const float4 *cfg_sph = row_sphere_cfg(a, b, S);
+      float4 *out_global = a.robot_spheres ? reinterpret_cast<float4 *>(a.robot_spheres) + (size_t)e * S : nullptr;
+#pragma unroll 1
+      for (int s = tlane; s < S; s += tsize) {
+        const float *T = es.cumul + 12 * rv.sph_link[s];
+        const float4 p = cfg_sph != nullptr ? __ldg(cfg_sph + s) : rv.spheres[s];
+        const float4 w = make_float4(T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3], T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7],
+                                     T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11], p.w);
+        es.sph[s] = w;
+        if (out_global != nullptr) out_global[s] = w;
+      }
+#pragma unroll 1
+      for (int ca = tlane; ca < rv.n_cl; ca += tsize) {  // link bounds of the self-collision broad phase
+        const float4 c = rv.cl_bound[ca];
+        const float *T = es.cumul + 12 * rv.cl_link[ca];
+        es.bc[ca] = make_float4(T[0] * c.x + T[1] * c.y + T[2] * c.z + T[3], T[4] * c.x + T[5] * c.y + T[6] * c.z + T[7],
+                                T[8] * c.x + T[9] * c.y + T[10] * c.z + T[11], c.w);
+      }
+    }
+    if (tw == TEAM - 1) {  // tool poses + tool-pose cost
+      float pose_c = 0.0f;
+      const bool do_pose = (a.goal_position != nullptr);
+#pragma unroll 1
+      for (int t = lane; t < L; t += 32) {
+        const float *T = es.cumul + 12 * rv.tool_map[t];
+        const V3 p = mk3(T[3], T[7], T[11]);
+        const Q4 qt = quat_from_transform(T);
+        if (a.link_pos) {
+          float *o = a.link_pos + ((size_t)e * L + t) * 3;
+          o[0] = p.x;
+          o[1] = p.y;
+          o[2] = p.z;
+        }
+        if (a.link_quat) *reinterpret_cast<float4 *>(a.link_quat + ((size_t)e * L + t) * 4) = make_float4(qt.w, qt.x, qt.y, qt.z);
+        float *pg = es.pose_g + 8 * t;
+        pg[0] = pg[1] = pg[2] = pg[4] = pg[5] = pg[6] = 0.0f;
+        if (do_pose) {
+          const int gi = a.idxs_goal ? __ldg(a.idxs_goal + b) : 0;
+          const bool term = !(h < a.H - 1 && a.H > 1);
+          const float *axes = term ? a.pose_axes_t : a.pose_axes_nt;
+          const float *tol = term ? a.pose_tol_t : a.pose_tol_nt;
+          const size_t go = ((size_t)gi * L + t) * cfg.num_goalset;
+          const PoseOut po = tool_pose_cost(p, qt, a.goal_position + go * 3, a.goal_quat + go * 4, cfg.num_goalset,
+                                            cfg.pose_weight[0], cfg.pose_weight[1], axes, t,
+                                            tol != nullptr ? __ldg(tol + 2 * t) : 0.0f,
+                                            tol != nullptr ? __ldg(tol + 2 * t + 1) : 0.0f, cfg.pose_rotation_method);
+          const V3 om = quat_grad_to_omega(qt, po.gq_w, po.gq_x, po.gq_y, po.gq_z);
+          pg[0] = po.g_pos.x;
+          pg[1] = po.g_pos.y;
+          pg[2] = po.g_pos.z;
+          pg[4] = om.x;
+          pg[5] = om.y;
+          pg[6] = om.z;
+          pose_c += po.pos_cost + po.rot_cost;
+          if (a.pose_cost) {
+            a.pose_cost[((size_t)e * L + t) * 2] = po.pos_cost;
+            a.pose_cost[((size_t)e * L + t) * 2 + 1] = po.rot_cost;
+          }
+          if (a.pose_goalset_idx) a.pose_goalset_idx[(size_t)e * L + t] = po.goal_idx;
+        }
+      }
+      pose_c = warp_sum(pose_c);
+      if (lane == 0) ts->pose_c = pose_c;
+    }
+    CB200_NAMED_BARRIER(bar_id, tsize);
+    // ---------------- phase B1: self collision (interleaved slices of the link-pair list), then scene collision
+    float self_c = 0.0f, fmax = 0.0f;
+    int bi = 0, bj = 0;
+    if (cfg.self_weight > 0.0f && rv.P > 0) {
+      unsigned long long key = 0ull;
+      int di, dj;
+      warp_self_collision_tiles<false>(rv, es, lane, di, dj, tw * 32, tsize, reinterpret_cast<unsigned char *>(es.ft) + 64 * tw, &key,
+                                       false);
+      if (lane == 0) ts->key[tw] = key;
+      CB200_NAMED_BARRIER(bar_id, tsize);
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int w = 0; w < TEAM; ++w) best = ts->key[w] > best ? ts->key[w] : best;
+      if (best != 0ull) {
+        bi = 0xffff - (int)((best >> 16) & 0xffffu);
+        bj = 0xffff - (int)(best & 0xffffu);
+        fmax = __uint_as_float((uint32_t)(best >> 32));
+        self_c = 0.5f * cfg.self_weight * fmax;
+      }
+    }
+    if (a.self_cost && tlane == 0) a.self_cost[e] = self_c;
+    const bool do_scene = SCENE != 0 && cfg.scene_weight > 0.0f;
+    const int env = (a.env_query_idx != nullptr) ? __ldg(a.env_query_idx + b) : 0;
+    int ce = 0, ncub = 0;
+    bool cull = false;
+    if ((SCENE & 1) && do_scene) {
+      ce = env < a.cuboids.num_envs ? env : 0;
+      ncub = a.cuboids.count[ce];
+      if (ncub > a.cuboids.max_n) ncub = a.cuboids.max_n;
+      cull = rv.n_lp > 0 && ncub <= 32;
+      if (cull) {
+#pragma unroll 1
+        for (int ca = tlane; ca < rv.n_cl; ca += tsize) {
+          const float4 cb = rv.cl_bound_scene[ca];
+          uint32_t mask = 0u;
+          if (cb.w >= 0.0f) {
+            const float *Tk = es.cumul + 12 * rv.cl_link[ca];
+            const V3 cw = mk3(Tk[0] * cb.x + Tk[1] * cb.y + Tk[2] * cb.z + Tk[3], Tk[4] * cb.x + Tk[5] * cb.y + Tk[6] * cb.z + Tk[7],
+                              Tk[8] * cb.x + Tk[9] * cb.y + Tk[10] * cb.z + Tk[11]);
+#pragma unroll 1
+            for (int i = 0; i < ncub; ++i) {
+              const int kk = ce * a.cuboids.max_n + i;
+              if (a.cuboids.enable[kk] != 1) continue;
+              const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
+              const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, cw), ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                                                 ldgf(a.cuboids.dims + 4 * kk + 2));
+              if (sg.sdf < cb.w + cfg.scene_activation) mask |= (1u << i);
+            }
+          }
+          es.cmask[ca] = mask;
+        }
+        CB200_NAMED_BARRIER(bar_id, tsize);
+      }
+    }
+    int n_list = 0;
+    float scene_c = 0.0f;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int sb = tw * 32; sb < S; sb += tsize) {  // this warp's passes; uniform trip count inside the warp
+      const int s = sb + lane;
+      V3 g = mk3(0, 0, 0);
+      float c = 0.0f;
+      if (s < S && do_scene) {
+        const float4 sp = es.sph[s];
+        const V3 cen = mk3(sp.x, sp.y, sp.z);
+        if (sp.w >= 0.0f) {
+          if (SCENE & 1) {
+            uint32_t m = cull ? es.cmask[rv.sph_cl[s]] : 0xffffffffu;
+            const float radj = sp.w + cfg.scene_activation;
+#pragma unroll 1
+            for (int i = 0; i < ncub && m != 0u; ++i) {
+              if (cull && !((m >> i) & 1u)) continue;
+              if (cull) m &= ~(1u << i);
+              const int kk = ce * a.cuboids.max_n + i;
+              if (a.cuboids.enable[kk] != 1) continue;
+              const ObsFrame f = load_obs_frame(a.cuboids.inv_pose + 8 * kk);
+              const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, cen), ldgf(a.cuboids.dims + 4 * kk), ldgf(a.cuboids.dims + 4 * kk + 1),
+                                                 ldgf(a.cuboids.dims + 4 * kk + 2));
+              const float pen = radj - sg.sdf;
+              if (pen > 0.0f) {
+                float ac, as;
+                collision_activation(pen, cfg.scene_activation, ac, as);
+                c += cfg.scene_weight * ac;
+                g = g + (cfg.scene_weight * as) * from_obstacle(f, sg.n);
+              }
+            }
+          }
+          if (SCENE & 2) {
+            const CuboidSet none{};
+            c += sphere_scene_discrete<2>(cen, sp.w, cfg.scene_activation, cfg.scene_weight, none, a.voxels, env, g);
+          }
+        }
+      }
+      const bool nz = (g.x != 0.0f) || (g.y != 0.0f) || (g.z != 0.0f);
+      const unsigned m = __ballot_sync(kFull, nz);
+      if (nz) my_list[n_list + __popc(m & lt)] = make_float4(g.x, g.y, g.z, __int_as_float(s));
+      n_list += __popc(m);
+      scene_c += c;
+      if (a.scene_cost && s < S) a.scene_cost[(size_t)e * S + s] = c;
+    }
+    scene_c = warp_sum(scene_c);
+    if (lane == 0) ts->scene_c[tw] = scene_c;
+    {
+      // ---------------- phase B2: J^T over the team's list segments
+      if (tw == 0 && fmax > 0.0f) {
+        if (lane == 0) {
+          const float4 pi = es.sph[bi], pj = es.sph[bj];
+          const float w = cfg.self_weight;
+          const float gx = w * (pj.x - pi.x), gy = w * (pj.y - pi.y), gz = w * (pj.z - pi.z);
+          my_list[n_list] = make_float4(gx, gy, gz, __int_as_float(bi));
+          my_list[n_list + 1] = make_float4(-gx, -gy, -gz, __int_as_float(bj));
+        }
+        n_list += 2;
+      }
+      __syncwarp();  // the warp's list entries are visible to all of its lanes
+      float acc[2];
+      warp_list_accumulate(rv, es, lane, my_list, n_list, tw == 0, acc);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        if (j < rv.nl) partial[tw * rv.nl + j] = acc[u];
+      }
+      CB200_NAMED_BARRIER(bar_id, tsize);
+      if (tw == 0) {
+        for (int j = lane; j < rv.nl; j += 32) {
+          float c = 0.0f;
+#pragma unroll
+          for (int w = 0; w < TEAM; ++w) c += partial[w * rv.nl + j];
+          es.contrib[j] = c;
+        }
+        __syncwarp();
+        float *gq = a.grad_q + (size_t)e * D;
+        for (int d = lane; d < D; d += 32) {
+          float g = es.gqv[d];
+          for (int i = rv.jl_off[d]; i < rv.jl_off[d + 1]; ++i) g += es.contrib[rv.jl_idx[i]];
+          gq[d] = g;
+        }
+        if (lane == 0) {
+          float tot = ts->cs_cost + ts->pose_c + self_c;
+#pragma unroll
+          for (int w = 0; w < TEAM; ++w) tot += ts->scene_c[w];
+          a.cost[e] = tot;
+        }
+      }
+    }
+    // ---------------- next row
+    if (tw == 0 && lane == 0) ts->next_row = a.work_counter != nullptr ? total_teams + atomicAdd(a.work_counter, 1) : e + total_teams;
+    CB200_NAMED_BARRIER(bar_id, tsize);
+    e = ts->next_row;
+    CB200_NAMED_BARRIER(bar_id, tsize);  // every warp has read next_row / the row state before the next row rewrites them
+  }
+  // the last team to leave re-arms the counter for the next launch
+  if (a.work_counter != nullptr && tw == 0 && lane == 0) {
+    __threadfence();
+    if (atomicAdd(a.work_counter + 1, 1) == total_teams - 1) {
+      a.work_counter[0] = 0;
+      a.work_counter[1] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // THE fused kernel, trajectory mode (swept scene collision + speed metric couple row h to h-1, h+1).
 // A CTA walks tiles of `nwarps` consecutive waypoints of one seed: every warp runs phase A for its
 // waypoint (warp 0 / the last warp also compute the halo waypoints' spheres), the CTA synchronises, then
@@ -2978,6 +3291,74 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       if (cand.nw > 0) {
         cand.key = bkey;
         bp = cand;
+      }
+    }
+    // Small batches: a team of warps per row (rollout_fused_team_kernel) when the rows would leave at least half of the
+    // resident warp slots idle.  CB200_TEAM = 0 / 2 / 4 forces the team size.
+    {
+      const char *ts = getenv("CB200_TEAM");
+      const int team_env = ts ? atoi(ts) : -1;
+      const long long slots = (long long)d.sm_count * maxw;
+      // Measured rule (profiles/r02_a_round2.md section 9).  Small robots (row <= 8 KB, here because of the ESDF): two warps per
+      // row while that leaves warp slots free.  Humanoids whose rows fill shared memory before 16 warps are resident (G1-43: 11
+      // rows per SM) always gain from teams -- 2 x 7 warps of 7 rows hide more latency than 11 warps of 11 rows; humanoids that
+      // do reach 16 rows per SM (G1-29) gain up to about two rows per warp slot.
+      const bool small_robot = (size_t)a.eval_floats * sizeof(float) <= 8192;
+      const bool smem_limited = bp.key == bkey && bp.nw * bp.per_sm < maxw;
+      int team = 0;
+      if (team_env >= 0) team = team_env;
+      else if (small_robot) team = (N * 2 <= slots) ? 2 : 0;
+      else if (smem_limited) team = (N <= slots) ? 4 : 2;
+      else if (N * 4 <= slots) team = 4;
+      else if (N <= 2 * slots) team = 2;
+      if ((team == 2 || team == 4) && h.nl <= 64) {
+        static KernelT const team_table[2][4] = {
+            {rollout_fused_team_kernel<0, 2>, rollout_fused_team_kernel<1, 2>, rollout_fused_team_kernel<2, 2>,
+             rollout_fused_team_kernel<3, 2>},
+            {rollout_fused_team_kernel<0, 4>, rollout_fused_team_kernel<1, 4>, rollout_fused_team_kernel<2, 4>,
+             rollout_fused_team_kernel<3, 4>}};
+        KernelT tk = team_table[team == 4][scene];
+        const int team_floats = (big_floats + team_extra_floats(team, h.nl, h.S) + 3) & ~3;
+        static thread_local long long tkeys[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};
+        static thread_local int tnw[2][4];
+        long long &tkey = tkeys[team == 4][scene];
+        if (tkey != bkey) {
+          cudaFuncAttributes fa;
+          cudaError_t e0 = cudaFuncGetAttributes(&fa, tk);
+          if (e0 != cudaSuccess) return ret(e0);
+          const size_t limit = (size_t)d.max_smem - fa.sharedSizeBytes;
+          cudaError_t e1 = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+          if (e1 != cudaSuccess) return ret(e1);
+          int nw = 0;
+          for (int w = maxw; w >= team; w -= team) {
+            if ((size_t)h.smem_bytes + (size_t)(w / team) * team_floats * sizeof(float) <= limit) {
+              nw = w;
+              break;
+            }
+          }
+          tnw[team == 4][scene] = nw;
+          tkey = bkey;
+        }
+        const int nw = tnw[team == 4][scene];
+        if (nw >= team) {
+          a.eval_floats = team_floats;
+          const char *qs = getenv("CB200_QUEUE");
+          a.work_counter = (qs && atoi(qs) == 0) ? nullptr : io->work_counter;
+          const int nteams = nw / team;
+          const size_t smem_b = (size_t)h.smem_bytes + (size_t)nteams * team_floats * sizeof(float);
+          long long g = d.sm_count;
+          const long long need_ctas = (N + nteams - 1) / nteams;
+          // spread the rows over all SMs first: fewer teams per CTA rather than fewer CTAs
+          int launch_teams = nteams;
+          if (need_ctas < g) {
+            launch_teams = (int)((N + g - 1) / g);
+            if (launch_teams < 1) launch_teams = 1;
+          }
+          long long ctas = (N + launch_teams - 1) / launch_teams;
+          if (ctas > g) ctas = g;
+          CB200_LAUNCH(tk, (int)(ctas < 1 ? 1 : ctas), launch_teams * team * 32, smem_b, (cudaStream_t)stream, a);
+          return finish();
+        }
       }
     }
     if (bp.key == bkey) {

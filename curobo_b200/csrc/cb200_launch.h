@@ -15,6 +15,14 @@
 #define CB200_LAUNCH(kernel, grid, block, smem_bytes, stream, ...) kernel<<<(grid), (block), (smem_bytes), (stream)>>>(__VA_ARGS__)
 #endif
 
+// A barrier among a SUBSET of a CTA's warps (PTX named barrier): the warps of a team that shares one row meet without the other
+// teams of the CTA.  `nthreads` must be a multiple of 32; ids 1..15 (0 is __syncthreads).
+#ifdef CB200_SIMT_EMULATION
+#define CB200_NAMED_BARRIER(id, nthreads) simt::named_barrier((id), (nthreads))
+#else
+#define CB200_NAMED_BARRIER(id, nthreads) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory")
+#endif
+
 // Every launching entry point runs on the device that OWNS its output buffer, whatever the caller's current device is:
 // occupancy queries, cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the launch itself are per device, and the host
 // layer passes raw pointers + the tensor's stream without entering a device context.  CB200_DEVICE_GUARD(ptr) looks the

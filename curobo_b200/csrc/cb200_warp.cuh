@@ -155,6 +155,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // (12 lanes per link, two links per step).  cumul[l] = cumul[parent[l]] * local[l].
 // Reference semantics: kinematics_forward_helper.cuh:316-512.
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_fk_compose(const RobotView &rv, const EvalSmem &es, int lane);
 __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es, int lane) {
   // local transforms go to a scratch buffer (the not-yet-written world-sphere area) when it is large enough,
   // so a compose step needs one warp barrier instead of two; otherwise they are composed in place.
@@ -168,6 +169,13 @@ __device__ __forceinline__ void warp_fk(const RobotView &rv, const EvalSmem &es,
     local_link_transform(rv.fixed + 12 * l, jt, th, (l == 0 ? es.cumul : loc) + 12 * l);
   }
   __syncwarp();
+  warp_fk_compose(rv, es, lane);
+}
+
+// second half of warp_fk: the level-scheduled compose (the local transforms are in place; see warp_fk)
+__device__ __forceinline__ void warp_fk_compose(const RobotView &rv, const EvalSmem &es, int lane) {
+  const bool scratch = rv.S * 4 >= rv.nl * 12;
+  const float *loc = scratch ? reinterpret_cast<const float *>(es.sph) : es.cumul;
   // compose: 12 lanes per link, two links (same depth level) per step; the schedule holds byte offsets
   const int sub = lane >> 4, k = lane & 15;
   const bool lane_ok = k < 12;
@@ -271,20 +279,27 @@ __device__ __forceinline__ float4 padded_sphere(const RobotView &rv, const EvalS
   return x;
 }
 
+// base0 / stride: the slice of the link-pair list this warp scans (a team of warps sharing one row takes interleaved
+// slices); idx_scratch: 64 bytes of per-warp scratch for the second-level cull (default: the row's idle force / torque area);
+// key_out: the warp's reduced arg-max key (f bits | ~i | ~j), 0 when nothing is positive.
 template <bool PADDED_COPY = true>
 __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, const EvalSmem &es, int lane, int &bi,
-                                                           int &bj) {
-  #pragma unroll 1
-  for (int a = lane; a < rv.n_cl; a += 32) {
-    const float4 c = rv.cl_bound[a];
-    const float *T = es.cumul + 12 * rv.cl_link[a];
-    es.bc[a] = make_float4(T[0] * c.x + T[1] * c.y + T[2] * c.z + T[3], T[4] * c.x + T[5] * c.y + T[6] * c.z + T[7],
-                           T[8] * c.x + T[9] * c.y + T[10] * c.z + T[11], c.w);
+                                                           int &bj, int base0 = 0, int stride = 32,
+                                                           unsigned char *idx_scratch = nullptr,
+                                                           unsigned long long *key_out = nullptr, bool fill_bounds = true) {
+  if (fill_bounds) {
+    #pragma unroll 1
+    for (int a = lane; a < rv.n_cl; a += 32) {
+      const float4 c = rv.cl_bound[a];
+      const float *T = es.cumul + 12 * rv.cl_link[a];
+      es.bc[a] = make_float4(T[0] * c.x + T[1] * c.y + T[2] * c.z + T[3], T[4] * c.x + T[5] * c.y + T[6] * c.z + T[7],
+                             T[8] * c.x + T[9] * c.y + T[10] * c.z + T[11], c.w);
+    }
+    __syncwarp();
   }
-  __syncwarp();
   unsigned long long key = 0ull;  // f bits | ~i | ~j : max = largest f, then smallest i, then smallest j
   #pragma unroll 1
-  for (int base = 0; base < rv.n_lp; base += 32) {
+  for (int base = base0; base < rv.n_lp; base += stride) {
     uint32_t pr = 0;
     bool hit = false;
     if (base + lane < rv.n_lp) {
@@ -321,7 +336,7 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
         }
         const unsigned ma = __ballot_sync(kFull, ca), mb = __ballot_sync(kFull, cb);
         if (ma == 0u || mb == 0u) continue;
-        unsigned char *ia = reinterpret_cast<unsigned char *>(es.ft), *ib = ia + 32;
+        unsigned char *ia = idx_scratch != nullptr ? idx_scratch : reinterpret_cast<unsigned char *>(es.ft), *ib = ia + 32;
         const unsigned lt = (1u << lane) - 1u;
         if (ca) ia[__popc(ma & lt)] = (unsigned char)lane;
         if (cb) ib[__popc(mb & lt)] = (unsigned char)lane;
@@ -367,6 +382,7 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
     const unsigned long long other = __shfl_xor_sync(kFull, key, o);
     key = other > key ? other : key;
   }
+  if (key_out != nullptr) *key_out = key;
   bi = bj = 0;
   if (key == 0ull) return 0.0f;
   bi = 0xffff - (int)((key >> 16) & 0xffffu);
@@ -586,6 +602,62 @@ __device__ __forceinline__ void warp_fk_backward_from_ft(const RobotView &rv, co
   __syncwarp();
   warp_fk_upsweep(rv, es, lane, gq_out);
 }
+// sparse J^T over a list of (gradient, sphere) entries (the transposed chain walk of warp_fk_backward_sparse with the list as
+// the source): lane j (and j + 32) accumulates the contribution to joint link j; `with_tools` adds the tool-frame gradients.
+__device__ __forceinline__ void warp_list_accumulate(const RobotView &rv, const EvalSmem &es, int lane, const float4 *list, int n,
+                                                     bool with_tools, float (&acc)[2]) {
+  const int nu = rv.nl > 32 ? 2 : 1;
+  V3 ax[2], og[2];
+  float sc[2];
+  int jt[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = lane + 32 * u;
+    jt[u] = -1;
+    if (u >= nu) continue;
+    sc[u] = 0.0f;
+    ax[u] = og[u] = mk3(0, 0, 0);
+    if (j < rv.nl) {
+      jt[u] = rv.joint_type[j];
+      if (jt[u] >= 0) {
+        const float *Tj = es.cumul + 12 * j;
+        const int a = (jt[u] >= JT_XR) ? jt[u] - JT_XR : jt[u];
+        ax[u] = mk3(Tj[a], Tj[4 + a], Tj[8 + a]);
+        og[u] = mk3(Tj[3], Tj[7], Tj[11]);
+        sc[u] = rv.joff[2 * j];
+      }
+    }
+  }
+  acc[0] = acc[1] = 0.0f;
+  auto add = [&](unsigned long long mask, V3 p, V3 g, V3 om) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = lane + 32 * u;
+      if (u < nu && jt[u] >= 0 && ((mask >> j) & 1ull)) {
+        acc[u] += (jt[u] >= JT_XR) ? sc[u] * (dot(ax[u], cross(p - og[u], g)) + dot(ax[u], om)) : sc[u] * dot(ax[u], g);
+      }
+    }
+  };
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const float4 g4 = list[i];
+    const int s = __float_as_int(g4.w);
+    const float4 p4 = es.sph[s];
+    add(rv.anc_mask[rv.sph_link[s]], mk3(p4.x, p4.y, p4.z), mk3(g4.x, g4.y, g4.z), mk3(0, 0, 0));
+  }
+  if (with_tools) {
+#pragma unroll 1
+    for (int t = 0; t < rv.L; ++t) {
+      const float *pg = es.pose_g + 8 * t;
+      const V3 g = mk3(pg[0], pg[1], pg[2]), om = mk3(pg[4], pg[5], pg[6]);
+      if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && om.x == 0.0f && om.y == 0.0f && om.z == 0.0f) continue;
+      const int k = rv.tool_map[t];
+      const float *Tk = es.cumul + 12 * k;
+      add(rv.anc_mask[k], mk3(Tk[3], Tk[7], Tk[11]), g, om);
+    }
+  }
+}
+
 // sparse J^T over the list (the transposed chain walk of warp_fk_backward_sparse with the list as the source)
 __device__ __forceinline__ void warp_fk_backward_list(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out, int n) {
   const int nu = rv.nl > 32 ? 2 : 1;

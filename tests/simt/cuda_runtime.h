@@ -84,6 +84,23 @@ struct Warp {                                                  // one per 32 con
 };
 inline thread_local Warp *t_warp = nullptr;
 inline thread_local int t_lane = 0;
+// named barriers (PTX bar.sync id, nthreads): one std::barrier per id, created by the first thread that arrives
+struct NamedBarriers {
+  std::mutex mu;
+  std::unique_ptr<std::barrier<>> bar[16];
+};
+inline thread_local NamedBarriers *t_named = nullptr;
+inline void named_barrier(int id, int nthreads) {
+#ifndef CB200_SIMT_DROP_BARRIERS
+  std::barrier<> *b;
+  {
+    std::lock_guard<std::mutex> g(t_named->mu);
+    if (!t_named->bar[id]) t_named->bar[id].reset(new std::barrier<>(nthreads));
+    b = t_named->bar[id].get();
+  }
+  b->arrive_and_wait();
+#endif
+}
 }  // namespace simt
 #define threadIdx (simt::t_threadIdx)
 #define blockIdx (simt::t_blockIdx)
@@ -186,6 +203,7 @@ template <class Kernel, class... Args>
 void launch(Kernel kern, int grid, int block, const Args &...args) {
   for (int b = 0; b < grid; ++b) {
     std::barrier<> bar(block);
+    NamedBarriers named;
     std::vector<std::unique_ptr<Warp>> warps;
     for (int w = 0; w * 32 < block; ++w) {
       warps.emplace_back(new Warp(std::min(32, block - w * 32)));
@@ -200,6 +218,7 @@ void launch(Kernel kern, int grid, int block, const Args &...args) {
         t_blockDim = uint3{(unsigned)block, 1, 1};
         t_gridDim = uint3{(unsigned)grid, 1, 1};
         t_barrier = &bar;
+        t_named = &named;
         t_warp = warps[t / 32].get();
         t_lane = t % 32;
         kern(args...);

@@ -239,6 +239,12 @@ def test_big_robot_kernel(run, monkeypatch, robot, n, buried):
     run("test_gpu_rollout", "test_big_robot_kernel_matches_standard_kernel_and_oracle", monkeypatch, robot, n, buried)
 
 
+@pytest.mark.parametrize("robot,n,team,scene", [("g1_29", 5, 2, "esdf"), ("g1_29", 3, 4, "both"), ("g1_29", 3, 2, "buried"),
+                                                 ("franka", 6, 4, "cuboid")])
+def test_team_kernel(run, monkeypatch, robot, n, team, scene):
+    run("test_gpu_rollout", "test_team_kernel_matches_big_kernel_and_oracle", monkeypatch, robot, n, team, scene)
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pyref", "MANIFEST.json")),
                     reason="oracle/_ref/pyref not built")
 def test_reference_call_sites_over_b200_backend(run):

@@ -636,6 +636,7 @@ def test_big_robot_kernel_matches_standard_kernel_and_oracle(monkeypatch, robot,
     else:
         vox = small_voxel_world()
     outs = {}
+    monkeypatch.setenv("CB200_TEAM", "0")          # (few rows would select the team variant, which has its own test below)
     for flag in ("0", "1"):
         monkeypatch.setenv("CB200_BIG", flag)
         out, want = check_against_oracle(rm, cfg, q, vox=vox, goal=(gp, gq), idx=idx)
@@ -648,6 +649,55 @@ def test_big_robot_kernel_matches_standard_kernel_and_oracle(monkeypatch, robot,
     assert torch.allclose(a[1], b[1], rtol=2e-4, atol=2e-6 * float(a[1].abs().max()))     # different summation order in J^T
     # the ticket counter is re-armed by every launch
     eng = RolloutEngine(rm, cfg, DEV, None, VoxelData.from_world(vox, DEV))
+    eng.update_goal(T(gp), T(gq), T(idx))
+    first = eng.evaluate_action(T(q)).grad_q.clone()
+    for _ in range(3):
+        again = eng.evaluate_action(T(q)).grad_q
+    torch.cuda.synchronize()
+    assert torch.equal(first, again) and int(eng._work_counter.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("robot,n,team,scene", [("g1_29", 24, 2, "esdf"), ("g1_29", 9, 4, "esdf"), ("g1_43", 8, 2, "esdf"),
+                                                 ("g1_29", 10, 2, "buried"), ("franka", 32, 4, "cuboid"),
+                                                 ("g1_29", 12, 4, "both")])
+def test_team_kernel_matches_big_kernel_and_oracle(monkeypatch, robot, n, team, scene):
+    """rollout_fused_team_kernel (TEAM warps share one row: strided spheres / link pairs / list segments, partial J^T sums,
+    named barriers) against rollout_fused_big_kernel on the same rows and against the oracle.  "buried": every sphere collides, a
+    list segment overflows and the team's first warp redoes the row through the single-warp code.  CB200_TEAM forces the team
+    size (default: by rows vs resident warps)."""
+    from curobo_b200.world import VoxelWorld
+    rm = load_robot(robot)
+    cfg = RolloutConfig(self_weight=5000.0, scene_weight=5000.0, scene_activation=0.02, cspace_type="position",
+                        cspace_weight=(5000.0, 0, 0, 0, 0), cspace_activation=(0.01, 0, 0, 0, 0), pose_weight=(2000.0, 100.0))
+    q = (humanoid_q(rm, n, seed=71) if robot != "franka" else random_q(rm, n, seed=71))[:, None, :]
+    gp, gq = goal_from_q(rm, (humanoid_q(rm, 2, seed=72, scale=0.5) if robot != "franka" else random_q(rm, 2, seed=72)))
+    idx = (np.arange(n) % 2).astype(np.int32)
+    vox = cub = None
+    if scene == "buried":
+        g = np.stack(np.meshgrid(*[np.arange(48)] * 3, indexing="ij"), -1).astype(np.float32)
+        vox = VoxelWorld.from_grid((np.linalg.norm(g - 23.5, axis=-1) * 0.06 - 1.2).astype(np.float32), 0.06)
+    if scene in ("esdf", "both"):
+        vox = small_voxel_world()
+    if scene in ("cuboid", "both"):
+        cub = make_benchmark_cuboid_world()
+    monkeypatch.setenv("CB200_BIG", "1")
+    outs = {}
+    for flag in ("0", str(team)):
+        monkeypatch.setenv("CB200_TEAM", flag)
+        out, want = check_against_oracle(rm, cfg, q, vox=vox, cub=cub, goal=(gp, gq), idx=idx)
+        outs[flag] = (out.cost.clone(), out.grad_q.clone(), out.scene_cost.clone(), out.self_cost.clone())
+    if scene == "buried":
+        assert int((want["scene_cost"] > 0).sum(-1).min()) > 96, "every row must overflow its list segments"
+    else:
+        assert float(want["scene_cost"].sum()) > 0 and (robot == "franka" or float(want["self_cost"].sum()) > 0)
+    a, b = outs["0"], outs[str(team)]
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])          # per-term costs: same arithmetic, bit for bit
+    assert torch.allclose(a[0], b[0], rtol=2e-6, atol=0.0)
+    assert torch.allclose(a[1], b[1], rtol=2e-4, atol=2e-6 * float(a[1].abs().max()))     # partial sums per warp of the team
+    monkeypatch.delenv("CB200_BIG")
+    monkeypatch.delenv("CB200_TEAM")                                    # default selection: few rows -> a team kernel
+    eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV) if cub is not None else None,
+                        VoxelData.from_world(vox, DEV) if vox is not None else None)
     eng.update_goal(T(gp), T(gq), T(idx))
     first = eng.evaluate_action(T(q)).grad_q.clone()
     for _ in range(3):
