@@ -700,8 +700,8 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_big_kernel(co
 // row's state and split its parallel phases: local link transforms, spheres, link bounds, the link-pair scan, the ESDF sphere
 // loop and the list-based J^T are strided over TEAM x 32 lanes; the serial parts (c-space, the level-scheduled FK compose) run
 // on the team's first warp, the tool-pose cost on its last; teams meet at named barriers (one id per team), every team has its
-// own gradient-list segment (full length: no overflow case; deterministic: segment order = warp order) and partial J^T
-// accumulators.  Measured (profiles/r02_a_round2.md section 9): G1-29, 1,024 rows 104 -> 58 us; the host picks the variant by rows
+// own gradient-list segment (a full segment is folded into the warp's partial sums and restarted: no overflow case;
+// deterministic) and partial J^T accumulators.  Measured (profiles/r02_a_round2.md section 9): G1-29, 1,024 rows 104 -> 58 us; the host picks the variant by rows
 // vs resident warp slots.
 // ------------------------------------------------------------------------------------------------
 template <int TEAM>
@@ -711,11 +711,20 @@ struct TeamScratch {  // per team, behind the row state
   float cs_cost, pose_c;
   int next_row, pad;
 };
-// list entries per WARP of a team: every sphere the warp visits may carry a gradient, + the self-collision pair.  A team kernel
-// keeps 16 / TEAM rows per SM instead of 16, so the full-length list fits and a row can never overflow it.
-__host__ __device__ inline int team_seg(int team, int S) { return ((S + team * 32 - 1) / (team * 32)) * 32 + 2; }
-__host__ __device__ inline int team_extra_floats(int team, int nl, int S) {
-  return team * nl + 28 + 4 * team + team * team_seg(team, S) * 4;
+// Every warp of a team has its own kGradListCap-entry list segment (the first warp uses the row's own list).  A warp whose segment
+// fills up -- a row deep in collision -- folds the segment into its J^T partial sums on the spot and starts it again
+// (team_flush_list: out of line, cold), so a segment never overflows and no row is ever redone.
+__host__ __device__ inline int team_extra_floats(int team, int nl) {
+  return team * nl + 28 + 4 * team + (team - 1) * kGradListCap * 4;
+}
+static __device__ __noinline__ void team_flush_list(const unsigned char *smem_blob, const unsigned char *gmem_blob, float *base,
+                                                    int lane, const float4 *list, int n, float *acc0, float *acc1) {
+  const RobotView rv = make_robot_view(smem_blob, gmem_blob);
+  const EvalSmem es = carve_big_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
+  float t[2];
+  warp_list_accumulate(rv, es, lane, list, n, false, t);
+  *acc0 += t[0];
+  *acc1 += t[1];
 }
 
 template <int SCENE, int TEAM>
@@ -733,7 +742,8 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_team_kernel(c
   float *extra = base + big_smem_floats(rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
   float *partial = extra;                                   // [TEAM][nl] J^T accumulators
   TeamScratch<TEAM> *ts = reinterpret_cast<TeamScratch<TEAM> *>(extra + ((TEAM * rv.nl + 1) & ~1));
-  float4 *my_list = reinterpret_cast<float4 *>(extra + ((TEAM * rv.nl + 24 + 4 * TEAM + 3) & ~3)) + tw * team_seg(TEAM, rv.S);
+  float4 *my_list =
+      tw == 0 ? es.glist : reinterpret_cast<float4 *>(extra + ((TEAM * rv.nl + 24 + 4 * TEAM + 3) & ~3)) + (tw - 1) * kGradListCap;
   const int bar_id = 1 + team;
   const cb200_rollout_cfg &cfg = a.cfg;
   const int N = a.B * a.H, S = rv.S, D = rv.D, L = rv.L;
@@ -899,7 +909,7 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_team_kernel(c
       }
     }
     int n_list = 0;
-    float scene_c = 0.0f;
+    float scene_c = 0.0f, flushed0 = 0.0f, flushed1 = 0.0f;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
     for (int sb = tw * 32; sb < S; sb += tsize) {  // this warp's passes; uniform trip count inside the warp
@@ -939,8 +949,16 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_team_kernel(c
       }
       const bool nz = (g.x != 0.0f) || (g.y != 0.0f) || (g.z != 0.0f);
       const unsigned m = __ballot_sync(kFull, nz);
-      if (nz) my_list[n_list + __popc(m & lt)] = make_float4(g.x, g.y, g.z, __int_as_float(s));
-      n_list += __popc(m);
+      if (m) {
+        if (n_list + __popc(m) > kGradListCap - 2) {  // (two slots stay free for the self-collision pair)
+          __syncwarp();
+          team_flush_list(smem, a.blob, base, lane, my_list, n_list, &flushed0, &flushed1);
+          __syncwarp();
+          n_list = 0;
+        }
+        if (nz) my_list[n_list + __popc(m & lt)] = make_float4(g.x, g.y, g.z, __int_as_float(s));
+        n_list += __popc(m);
+      }
       scene_c += c;
       if (a.scene_cost && s < S) a.scene_cost[(size_t)e * S + s] = c;
     }
@@ -961,6 +979,8 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_team_kernel(c
       __syncwarp();  // the warp's list entries are visible to all of its lanes
       float acc[2];
       warp_list_accumulate(rv, es, lane, my_list, n_list, tw == 0, acc);
+      acc[0] += flushed0;
+      acc[1] += flushed1;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int j = lane + 32 * u;
@@ -1025,7 +1045,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
   const int D = rv.D, S = rv.S;
   const int tiles_per_seed = (a.H + nwarps - 1) / nwarps;
   const long long n_tiles = (long long)a.B * tiles_per_seed;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  __shared__ int next_tile;  // tiles after a CTA's first come from the ticket counter (tiles differ in cost: see rollout_fused_kernel)
+  for (long long tile = blockIdx.x; tile < n_tiles;) {
     const int b = (int)(tile / tiles_per_seed);
     const int h0 = (int)(tile - (long long)b * tiles_per_seed) * nwarps;
     const int h = h0 + warp;
@@ -1066,8 +1087,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
       if (h < a.H - 1) next = (warp < nwarps - 1) ? reinterpret_cast<const float4 *>(all + (size_t)(warp + 1) * a.eval_floats + rv.nl * 12) : halo_next;
       r = row_phase_b1<true, SCENE>(a, rv, es, lane, e, b, prev, next);
     }
+    if (threadIdx.x == 0 && a.work_counter != nullptr) next_tile = (int)gridDim.x + atomicAdd(a.work_counter, 1);
     __syncthreads();
     if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+    // (next_tile is rewritten only after the next iteration's first __syncthreads, which every thread passes after this read)
+    tile = a.work_counter != nullptr ? (long long)next_tile : tile + gridDim.x;
+  }
+  if (a.work_counter != nullptr && threadIdx.x == 0) {  // the last CTA to leave re-arms the counter for the next launch
+    __threadfence();
+    if (atomicAdd(a.work_counter + 1, 1) == (int)gridDim.x - 1) {
+      a.work_counter[0] = 0;
+      a.work_counter[1] = 0;
+    }
   }
 }
 
@@ -3300,17 +3331,16 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       const int team_env = ts ? atoi(ts) : -1;
       const long long slots = (long long)d.sm_count * maxw;
       // Measured rule (profiles/r02_a_round2.md section 9).  Small robots (row <= 8 KB, here because of the ESDF): two warps per
-      // row while that leaves warp slots free.  Humanoids whose rows fill shared memory before 16 warps are resident (G1-43: 11
-      // rows per SM) always gain from teams -- 2 x 7 warps of 7 rows hide more latency than 11 warps of 11 rows; humanoids that
-      // do reach 16 rows per SM (G1-29) gain up to about two rows per warp slot.
+      // row while that leaves warp slots free.  Humanoids: four warps per row while that leaves slots free, then two -- always
+      // when the one-warp plan is shared-memory limited (G1-43: 11 rows per SM; 8 teams of 2 warps are 16 warps, 388 -> 259 us
+      // at 8,192 rows), otherwise (G1-29) up to about two rows per warp slot.
       const bool small_robot = (size_t)a.eval_floats * sizeof(float) <= 8192;
       const bool smem_limited = bp.key == bkey && bp.nw * bp.per_sm < maxw;
       int team = 0;
       if (team_env >= 0) team = team_env;
       else if (small_robot) team = (N * 2 <= slots) ? 2 : 0;
-      else if (smem_limited) team = (N <= slots) ? 4 : 2;
       else if (N * 4 <= slots) team = 4;
-      else if (N <= 2 * slots) team = 2;
+      else if (smem_limited || N <= 2 * slots) team = 2;
       if ((team == 2 || team == 4) && h.nl <= 64) {
         static KernelT const team_table[2][4] = {
             {rollout_fused_team_kernel<0, 2>, rollout_fused_team_kernel<1, 2>, rollout_fused_team_kernel<2, 2>,
@@ -3318,7 +3348,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
             {rollout_fused_team_kernel<0, 4>, rollout_fused_team_kernel<1, 4>, rollout_fused_team_kernel<2, 4>,
              rollout_fused_team_kernel<3, 4>}};
         KernelT tk = team_table[team == 4][scene];
-        const int team_floats = (big_floats + team_extra_floats(team, h.nl, h.S) + 3) & ~3;
+        const int team_floats = (big_floats + team_extra_floats(team, h.nl) + 3) & ~3;
         static thread_local long long tkeys[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};
         static thread_local int tnw[2][4];
         long long &tkey = tkeys[team == 4][scene];
@@ -3493,13 +3523,15 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   const int nw = pl.nw;
   {
     const char *qs = getenv("CB200_QUEUE");  // tuning knob: 0 = static striding even when a counter is given
-    a.work_counter = (!traj && !(qs && atoi(qs) == 0)) ? io->work_counter : nullptr;
+    a.work_counter = !(qs && atoi(qs) == 0) ? io->work_counter : nullptr;
+    if (traj && (long long)io->batch_size * ((io->horizon + nw - 1) / nw) > 0x3fffffffLL) a.work_counter = nullptr;  // int tickets
   }
   const size_t smem = (size_t)h.smem_bytes + halo_bytes + (size_t)nw * a.eval_floats * sizeof(float);
   long long grid_ll = (long long)d.sm_count * pl.per_sm;
   const long long need_ctas = traj ? (long long)io->batch_size * ((io->horizon + nw - 1) / nw) : (N + nw - 1) / nw;
   if (grid_ll > need_ctas) grid_ll = need_ctas;
   const int grid = (int)(grid_ll < 1 ? 1 : grid_ll);
+  if (need_ctas <= grid_ll) a.work_counter = nullptr;  // every row / tile has its own warp / CTA: nothing to hand out
   CB200_LAUNCH(kern, grid, nw * 32, smem, (cudaStream_t)stream, a);
   return finish();
 }

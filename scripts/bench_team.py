@@ -19,7 +19,8 @@ for name in names:
         wl = bench.shard_workload(full, 0, n)
         line = f"{name} rows {n:5d}:"
         ref = None
-        for team in ("0", "2", "4", ""):
+        for team in (sys.argv[3].split(",") if len(sys.argv) > 3 else ("0", "2", "4", "")):
+            team = "" if team == "auto" else team
             if team:
                 os.environ["CB200_TEAM"] = team
             else:
