@@ -239,6 +239,10 @@ def test_big_robot_kernel(run, monkeypatch, robot, n, buried):
     run("test_gpu_rollout", "test_big_robot_kernel_matches_standard_kernel_and_oracle", monkeypatch, robot, n, buried)
 
 
+def test_traj_dense_gradients_over_many_tiles(run, monkeypatch):
+    run("test_gpu_rollout", "test_traj_dense_gradients_over_many_tiles", monkeypatch, 40, 20)
+
+
 @pytest.mark.parametrize("robot,n,team,scene", [("g1_29", 5, 2, "esdf"), ("g1_29", 3, 4, "both"), ("g1_29", 3, 2, "buried"),
                                                  ("franka", 6, 4, "cuboid")])
 def test_team_kernel(run, monkeypatch, robot, n, team, scene):

@@ -304,6 +304,46 @@ def test_traj_rollout_vs_oracle(B, H, speed):
     assert torch.equal(c1, out.cost) and torch.equal(g1, out.grad_q)
 
 
+@pytest.mark.parametrize("B,H", [(40, 20), (700, 12)])
+def test_traj_dense_gradients_over_many_tiles(monkeypatch, B, H):
+    """Trajectory kernel on a robot BURIED in a solid ball (every sphere collides: the J^T takes the dense, out-of-line form) with
+    more tiles than resident CTAs, so CTAs iterate over tiles handed out by the ticket counter: oracle parity on a subset of
+    seeds, bit-equality with static striding (CB200_QUEUE=0), determinism, and the ticket counter re-armed."""
+    from curobo_b200.world import VoxelWorld
+    if DEV == "cpu" and B > 100:
+        pytest.skip("full-size variant: GPU only")
+    rm = load_robot("franka")
+    q = random_walk_q(rm, B, H, seed=80 + H)
+    dt = np.full(B, 0.05, np.float32)
+    g = np.stack(np.meshgrid(*[np.arange(48)] * 3, indexing="ij"), -1).astype(np.float32)
+    vox = VoxelWorld.from_grid((np.linalg.norm(g - 23.5, axis=-1) * 0.06 - 1.2).astype(np.float32), 0.06)
+    cfg = RolloutConfig.trajopt()
+    gp, gq = goal_from_q(rm, random_q(rm, 2, seed=81))
+    idx = (np.arange(B) % 2).astype(np.int32)
+    outs = {}
+    for name, env in (("queue", {}), ("static", {"CB200_QUEUE": "0"})):
+        monkeypatch.delenv("CB200_QUEUE", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = RolloutEngine(rm, cfg, DEV, None, VoxelData.from_world(vox, DEV))
+        eng.update_goal(T(gp), T(gq), T(idx), non_terminal_axes=torch.zeros((1, 6), dtype=torch.float32, device=DEV))
+        for _ in range(2):
+            out = eng.evaluate_action(T(q), dt=T(dt))
+        torch.cuda.synchronize()
+        outs[name] = (out.cost.clone(), out.grad_q.clone(), out.scene_cost.clone())
+        assert int(eng._work_counter.abs().sum()) == 0
+    for x, y in zip(outs["queue"], outs["static"]):
+        assert torch.equal(x, y)
+    n = min(B, 12)                                                            # oracle on the first seeds
+    ocfg = cfg.to_oracle_cfg(1)
+    ocfg["pose_non_terminal_axes"] = np.zeros((1, 6), np.float32)
+    want = O.rollout_cost_grad(rm, q[:n], ocfg, world_voxel=vox, goal_pos=gp, goal_quat=gq, idxs_goal=idx[:n], dt=dt[:n])
+    assert int((want["scene_cost"] > 0).sum(-1).min()) > 2 * rm.num_links, "every row must take the dense J^T"
+    cost, grad, _ = outs["queue"]
+    np.testing.assert_allclose(cost[:n].cpu().numpy(), want["cost_bh"], rtol=2e-4, atol=1e-5 * want["cost_bh"].max())
+    grad_close(grad[:n].cpu().numpy(), want["grad_q"], rtol=2e-3, scale=2e-5)
+
+
 def test_traj_full_size_mpc_properties():
     """config 4 shape: 1024 particles x 30 horizon, swept + speed metric on the 256^3 ESDF.
     fused == FK kernel + swept scene kernel (per-op) on the scene term; stationary trajectories == discrete."""
