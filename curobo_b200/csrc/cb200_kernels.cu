@@ -282,7 +282,7 @@ struct RowB1 {
   int bi, bj, nnz;
 };
 
-template <bool SWEEP, int SCENE>
+template <bool SWEEP, int SCENE, bool CULL2 = true>
 __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
                                               int b, const float4 *prev_sph, const float4 *next_sph) {
   const cb200_rollout_cfg &cfg = a.cfg;
@@ -290,7 +290,7 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
   RowB1 r{0.0f, 0.0f, 0.0f, 0, 0, 0};
   // ---- self collision (reads padded spheres in gsph)
   if (cfg.self_weight > 0.0f && rv.P > 0) {
-    r.fmax = (rv.n_lp > 0) ? warp_self_collision_tiles(rv, es, lane, r.bi, r.bj)
+    r.fmax = (rv.n_lp > 0) ? warp_self_collision_tiles<true, CULL2>(rv, es, lane, r.bi, r.bj)
                            : warp_self_collision_pairs(es.gsph, rv.pairs, rv.P, lane, r.bi, r.bj);
     r.self_c = (r.fmax > 0.0f) ? 0.5f * cfg.self_weight * r.fmax : 0.0f;
   }
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
     const EvalSmem es = carve_eval_smem(base, rv.nl, rv.D, rv.S, rv.L, rv.n_cl);
     float cs_cost = 0.0f, pose_c = 0.0f;
     row_phase_a<SPLINE>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
-    const RowB1 r = row_phase_b1<false, SCENE>(a, rv, es, lane, e, b, nullptr, nullptr);
+    const RowB1 r = row_phase_b1<false, SCENE, MINB != 3>(a, rv, es, lane, e, b, nullptr, nullptr);
     row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
 #else
     const PhaseAOut pa = phase_a_ool(&a, smem, base, lane, e, b, h);

@@ -282,7 +282,9 @@ __device__ __forceinline__ float4 padded_sphere(const RobotView &rv, const EvalS
 // base0 / stride: the slice of the link-pair list this warp scans (a team of warps sharing one row takes interleaved
 // slices); idx_scratch: 64 bytes of per-warp scratch for the second-level cull (default: the row's idle force / torque area);
 // key_out: the warp's reduced arg-max key (f bits | ~i | ~j), 0 when nothing is positive.
-template <bool PADDED_COPY = true>
+// CULL2 = false (arm build of the IK kernel: links of <= ~10 spheres): blocks are scanned whole -- the second-level cull's code is
+// 1.6 KB of the row's instruction footprint, which is what that kernel is short of (profiles/r02_a_round2.md section 11).
+template <bool PADDED_COPY = true, bool CULL2 = true>
 __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, const EvalSmem &es, int lane, int &bi,
                                                            int &bj, int base0 = 0, int stride = 32,
                                                            unsigned char *idx_scratch = nullptr,
@@ -316,7 +318,7 @@ __device__ __forceinline__ float warp_self_collision_tiles(const RobotView &rv, 
       const int a = q & 0xffffu, b = q >> 16;
       const int sa = rv.cl_start[a], na = rv.cl_start[a + 1] - sa;
       const int sb = rv.cl_start[b], nb = rv.cl_start[b + 1] - sb;
-      if (es.ft != nullptr && na <= 32 && nb <= 32 && na * nb > 64) {  // (a block of <= 2 passes is cheaper to scan
+      if (CULL2 && es.ft != nullptr && na <= 32 && nb <= 32 && na * nb > 64) {  // (a block of <= 2 passes is cheaper to scan
                                                                         // than to cull; the tile schedule has no scratch)
         // Second-level cull (exact): a pair (i, j) with f > 0 has |p_i - c_b| < r_i + R_b and |p_j - c_a| < r_j + R_a
         // (bounds enclose the padded sphere balls), so only spheres that reach the OTHER link's bound can matter.

@@ -73,6 +73,33 @@ def main():
             dis.append((cf, cl))
     if len(dis) != len(ncu):
         print(f"WARNING: {len(dis)} disassembled vs {len(ncu)} profiled instructions (sources differ from the profiled build?)")
+    if "--static" in sys.argv:
+        # instruction-cache footprint: SASS instructions executed by >= 10 % of the evals, per source line and per function
+        hot = [k for k in range(min(len(dis), len(ncu))) if ncu[k][1] >= 0.1 * evals]
+        print(f"kernel: {sec['name']}\nSASS instructions: {len(ncu)} ({len(ncu) * 16 / 1024:.1f} KB); executed at all: "
+              f"{sum(1 for x in ncu if x[1] > 0)}; hot (>= 10 % of evals): {len(hot)} = {len(hot) * 16 / 1024:.1f} KB")
+        src = {f: open(os.path.join(srcdir, f)).read().split("\n") for f in os.listdir(srcdir)}
+
+        def func_of(f, l):
+            if f not in src or not l:
+                return f"{f}:?"
+            for i in range(l - 1, -1, -1):
+                m = re.match(r"^(?:template.*>\s*)?(?:static\s+)?(?:__device__|CB_HD|__global__|inline|__host__)[^;{]*?([A-Za-z_0-9]+)\s*\(", src[f][i])
+                if m and not src[f][i].startswith(" "):
+                    return f"{f}:{m.group(1)}"
+            return f"{f}:?"
+        per_fn, per_line = collections.Counter(), collections.Counter()
+        for k in hot:
+            per_line[dis[k]] += 1
+            per_fn[func_of(*dis[k])] += 1
+        print("hot static instructions per function (16 B each):")
+        for fn, c in per_fn.most_common(top):
+            print(f"{c:6d} {c * 16 / 1024:6.2f} KB  {fn}")
+        print("per line:")
+        for (f, l), c in per_line.most_common(top):
+            code = src[f][l - 1].strip()[:100] if f in src and l else ""
+            print(f"{c:6d}  {f}:{l}  {code}")
+        return
     agg, lanes = collections.Counter(), collections.Counter()
     for k in range(min(len(dis), len(ncu))):
         agg[dis[k]] += ncu[k][1]
