@@ -2595,9 +2595,13 @@ static void bounding_ball(const float *link_spheres, const float *padding, int s
   out[3] = (float)(std::max(Rf, Rr) * (1.0 + 1e-4) + 1e-5);
 }
 
+// which kernel the last cb200_rollout_cost_grad call of this thread launched (CB200_VARIANT_*; test / bench introspection)
+static thread_local int g_last_variant = 0;
+
 extern "C" {
 
 int cb200_abi_version(void) { return CB200_ABI_VERSION; }
+int cb200_last_rollout_variant(void) { return g_last_variant; }
 int cb200_sm_arch(void) { return 100; }
 const char *cb200_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
 
@@ -3237,6 +3241,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       const long long need = (N + kLaneThreads - 1) / kLaneThreads;
       long long g = (long long)d.sm_count * lane_per_sm[scene];
       if (g > need) g = need;
+      g_last_variant = CB200_VARIANT_LANE;
       CB200_LAUNCH(lk, (int)g, kLaneThreads, ll.total_bytes, (cudaStream_t)stream, a);
       return launch_status();
     }
@@ -3269,6 +3274,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       const long long n_tiles = (N + tl.T - 1) / tl.T;
       long long g = (long long)d.sm_count * tile_per_sm[scene];
       if (g > n_tiles) g = n_tiles;
+      g_last_variant = CB200_VARIANT_TILE;
       CB200_LAUNCH(tk, (int)g, kWarpsPerCta * 32, tl.total_bytes, (cudaStream_t)stream, a);
       return launch_status();
     }
@@ -3386,6 +3392,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
           }
           long long ctas = (N + launch_teams - 1) / launch_teams;
           if (ctas > g) ctas = g;
+          g_last_variant = team == 4 ? CB200_VARIANT_TEAM4 : CB200_VARIANT_TEAM2;
           CB200_LAUNCH(tk, (int)(ctas < 1 ? 1 : ctas), launch_teams * team * 32, smem_b, (cudaStream_t)stream, a);
           return finish();
         }
@@ -3401,6 +3408,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
       long long g = (long long)d.sm_count * bp.per_sm;
       const long long need_ctas = (N + bp.nw - 1) / bp.nw;
       if (g > need_ctas) g = need_ctas;
+      g_last_variant = CB200_VARIANT_BIG;
       CB200_LAUNCH(bk, (int)(g < 1 ? 1 : g), bp.nw * 32, smem_b, (cudaStream_t)stream, a);
       return finish();
     }
@@ -3464,6 +3472,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     long long grid_ll = (long long)d.sm_count * dpl.per_sm;
     const long long need_ctas = (long long)io->batch_size * ((io->horizon + dpl.R - 1) / dpl.R);
     if (grid_ll > need_ctas) grid_ll = need_ctas;
+    g_last_variant = CB200_VARIANT_TRAJ_DYN;
     CB200_LAUNCH(dk, (int)(grid_ll < 1 ? 1 : grid_ll), dpl.nw * 32, dpl.smem, (cudaStream_t)stream, a, dpl.R);
     return finish();
   }
@@ -3532,6 +3541,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   if (grid_ll > need_ctas) grid_ll = need_ctas;
   const int grid = (int)(grid_ll < 1 ? 1 : grid_ll);
   if (need_ctas <= grid_ll) a.work_counter = nullptr;  // every row / tile has its own warp / CTA: nothing to hand out
+  g_last_variant = traj ? CB200_VARIANT_TRAJ : (variant == 5 ? CB200_VARIANT_ARM : CB200_VARIANT_STANDARD);
   CB200_LAUNCH(kern, grid, nw * 32, smem, (cudaStream_t)stream, a);
   return finish();
 }

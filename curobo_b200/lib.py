@@ -78,6 +78,7 @@ class RolloutIO(C.Structure):
 _I = C.c_int
 _SIGS = {
     "cb200_abi_version": ([], _I),
+    "cb200_last_rollout_variant": ([], _I),
     "cb200_sm_arch": ([], _I),
     "cb200_error_string": ([_I], C.c_char_p),
     "cb200_device_info": ([_I, C.POINTER(_I), C.POINTER(_I)], _I),

@@ -34,6 +34,19 @@ int cb200_abi_version(void);
 int cb200_sm_arch(void);
 /* Human-readable string for the last non-zero return code of this thread (cudaGetErrorString). */
 const char *cb200_error_string(int err);
+/* Which kernel the last cb200_rollout_cost_grad call of this thread launched (introspection for tests and the bench line; the
+   choice is made by the launcher from the robot, the scene content and the row count -- see DESIGN.md "Row scheduling"). */
+#define CB200_VARIANT_NONE 0
+#define CB200_VARIANT_STANDARD 1 /* rollout_fused_kernel: one warp per row */
+#define CB200_VARIANT_ARM 2      /* ... its 80-register build for arms against cuboids */
+#define CB200_VARIANT_BIG 4      /* rollout_fused_big_kernel: humanoids / ESDF scenes, gradient list */
+#define CB200_VARIANT_TEAM2 5    /* rollout_fused_team_kernel: two warps per row */
+#define CB200_VARIANT_TEAM4 6    /* ... four warps per row */
+#define CB200_VARIANT_TRAJ 7     /* rollout_traj_kernel: trajectory mode (swept collision, state costs) */
+#define CB200_VARIANT_TRAJ_DYN 8 /* rollout_traj_dyn_kernel: trajectory mode + inverse dynamics */
+#define CB200_VARIANT_TILE 9     /* experimental schedules (off by default) */
+#define CB200_VARIANT_LANE 10
+int cb200_last_rollout_variant(void);
 
 /* -------------------------------------------------------------------------------------------
  * (a2) FK + robot spheres + tool poses.

@@ -95,6 +95,15 @@ def main():
         print("hot static instructions per function (16 B each):")
         for fn, c in per_fn.most_common(top):
             print(f"{c:6d} {c * 16 / 1024:6.2f} KB  {fn}")
+        print("contiguous hot runs (>= 24 instructions): start, length, functions inside")
+        run = []
+        for k in hot + [10 ** 9]:
+            if run and k != run[-1] + 1:
+                if len(run) >= 24:
+                    fc = collections.Counter(func_of(*dis[i]).split(":")[1] for i in run)
+                    print(f"  @{run[0]:5d} len {len(run):4d}  " + ", ".join(f"{f} {c}" for f, c in fc.most_common(5)))
+                run = []
+            run.append(k)
         print("per line:")
         for (f, l), c in per_line.most_common(top):
             code = src[f][l - 1].strip()[:100] if f in src and l else ""

@@ -53,7 +53,7 @@ inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cuda
 template <class K>
 inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, K) { *a = cudaFuncAttributes(); return cudaSuccess; }
 template <class K>
-inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 2; return cudaSuccess; }
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 3; return cudaSuccess; }
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -39,6 +39,12 @@ def goal_from_q(rm, qg):
     return p[:, :, None, :].copy(), qt[:, :, None, :].copy()
 
 
+def last_variant():
+    """which kernel the last rollout launch used (include/curobo_b200.h: CB200_VARIANT_*)"""
+    from curobo_b200 import lib as cblib
+    return int(cblib.load().cb200_last_rollout_variant())
+
+
 def check_against_oracle(rm, cfg, q, cub=None, vox=None, goal=None, idx=None):
     eng = RolloutEngine(rm, cfg, DEV, CuboidData.from_world(cub, DEV) if cub is not None else None,
                         VoxelData.from_world(vox, DEV) if vox is not None else None, store_fk_outputs=True)
@@ -725,6 +731,7 @@ def test_team_kernel_matches_big_kernel_and_oracle(monkeypatch, robot, n, team, 
     for flag in ("0", str(team)):
         monkeypatch.setenv("CB200_TEAM", flag)
         out, want = check_against_oracle(rm, cfg, q, vox=vox, cub=cub, goal=(gp, gq), idx=idx)
+        assert last_variant() == {"0": 4, "2": 5, "4": 6}[flag]      # CB200_VARIANT_BIG / TEAM2 / TEAM4
         outs[flag] = (out.cost.clone(), out.grad_q.clone(), out.scene_cost.clone(), out.self_cost.clone())
     if scene == "buried":
         assert int((want["scene_cost"] > 0).sum(-1).min()) > 96, "every row must overflow its list segments"
