@@ -396,6 +396,7 @@ __device__ __forceinline__ RowB1 row_phase_b1(const FusedArgs &a, const RobotVie
 }
 
 // phase B2: add the self-collision gradient to the two spheres of the worst pair, J^T backward, row cost.
+template <bool SMALL = false>
 __device__ __forceinline__ void row_phase_b2(const FusedArgs &a, const RobotView &rv, const EvalSmem &es,
                                              const unsigned char *smem_blob, int lane, int e, const RowB1 &r,
                                              float cs_cost, float pose_c) {
@@ -415,7 +416,7 @@ __device__ __forceinline__ void row_phase_b2(const FusedArgs &a, const RobotView
   }
   __syncwarp();
   float *gq = a.grad_q + (size_t)e * rv.D;
-  if (!warp_fk_backward_sparse(rv, es, lane, gq, r.nnz)) warp_fk_backward_cold(smem_blob, a.blob, es.cumul, lane, gq);
+  if (!warp_fk_backward_sparse<SMALL>(rv, es, lane, gq, r.nnz)) warp_fk_backward_cold(smem_blob, a.blob, es.cumul, lane, gq);
   const float tot = warp_sum(cs_cost + pose_c + r.scene_c) + r.self_c;
   if (lane == 0) a.cost[e] = tot;
   __syncwarp();
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
     float cs_cost = 0.0f, pose_c = 0.0f;
     row_phase_a<SPLINE>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
     const RowB1 r = row_phase_b1<false, SCENE, MINB != 3>(a, rv, es, lane, e, b, nullptr, nullptr);
-    row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+    row_phase_b2<MINB == 3>(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
 #else
     const PhaseAOut pa = phase_a_ool(&a, smem, base, lane, e, b, h);
     const RowB1 r = phase_b1_ool<SCENE>(&a, smem, base, lane, e, b);

@@ -486,9 +486,72 @@ static __device__ __noinline__ void warp_fk_backward_cold(const unsigned char *s
 // chain walk (kinematics_backward_helper.cuh:15-99) with the chain laid across lanes.
 // Returns false (nothing written) when the gradient is dense; the caller then uses warp_fk_backward.
 // ----------------------------------------------------------------------------------------------
+// SMALL = true (arm build: <= 24 links, so one link per lane, and <= 128 spheres): the second link slot is compiled out and the
+// tool frames ride through the same broadcast loop as the spheres (entries S .. S + L - 1) -- one copy of the accumulate code
+// instead of two; the row's instruction footprint is what that kernel is short of (profiles/r02_a_round2.md section 11).
+template <bool SMALL = false>
 __device__ __forceinline__ bool warp_fk_backward_sparse(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out,
                                                         int nnz) {
   if (nnz > 2 * rv.nl) return false;  // nnz = spheres with a non-zero gradient (counted by the caller)
+  if (SMALL) {
+    float sc = 0.0f;
+    V3 ax = mk3(0, 0, 0), og = mk3(0, 0, 0);
+    int jt = -1;
+    if (lane < rv.nl) {
+      jt = rv.joint_type[lane];
+      if (jt >= 0) {
+        const float *Tj = es.cumul + 12 * lane;
+        const int a = (jt >= JT_XR) ? jt - JT_XR : jt;
+        ax = mk3(Tj[a], Tj[4 + a], Tj[8 + a]);
+        og = mk3(Tj[3], Tj[7], Tj[11]);
+        sc = rv.joff[2 * lane];
+      }
+    }
+    float acc = 0.0f;
+    const int n_entries = rv.S + rv.L;
+#pragma unroll 1
+    for (int base = 0; base < n_entries; base += 32) {
+      const int s = base + lane;
+      bool nz = false;
+      if (s < rv.S) {
+        const float4 g = es.gsph[s];
+        nz = (g.x != 0.0f) || (g.y != 0.0f) || (g.z != 0.0f);
+      } else if (s < n_entries) {
+        const float *pg = es.pose_g + 8 * (s - rv.S);
+        nz = pg[0] != 0.0f || pg[1] != 0.0f || pg[2] != 0.0f || pg[4] != 0.0f || pg[5] != 0.0f || pg[6] != 0.0f;
+      }
+      unsigned m = __ballot_sync(kFull, nz);
+      while (m) {
+        const int ss = base + __ffs(m) - 1;
+        m &= m - 1;
+        V3 p, g, om = mk3(0, 0, 0);
+        int k;
+        if (ss < rv.S) {
+          const float4 g4 = es.gsph[ss], p4 = es.sph[ss];
+          k = rv.sph_link[ss];
+          p = mk3(p4.x, p4.y, p4.z);
+          g = mk3(g4.x, g4.y, g4.z);
+        } else {
+          const float *pg = es.pose_g + 8 * (ss - rv.S);
+          k = rv.tool_map[ss - rv.S];
+          const float *Tk = es.cumul + 12 * k;
+          p = mk3(Tk[3], Tk[7], Tk[11]);
+          g = mk3(pg[0], pg[1], pg[2]);
+          om = mk3(pg[4], pg[5], pg[6]);
+        }
+        if (jt >= 0 && ((rv.anc_mask[k] >> lane) & 1ull))
+          acc += (jt >= JT_XR) ? sc * (dot(ax, cross(p - og, g)) + dot(ax, om)) : sc * dot(ax, g);
+      }
+    }
+    if (lane < rv.nl) es.contrib[lane] = acc;
+    __syncwarp();
+    for (int d = lane; d < rv.D; d += 32) {
+      float g = es.gqv[d];
+      for (int i = rv.jl_off[d]; i < rv.jl_off[d + 1]; ++i) g += es.contrib[rv.jl_idx[i]];
+      gq_out[d] = g;
+    }
+    return true;
+  }
   const int nu = rv.nl > 32 ? 2 : 1;
   // per-lane link constants (slot 0: link lane, slot 1: link lane + 32)
   V3 ax[2], og[2];
