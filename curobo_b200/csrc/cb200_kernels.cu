@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) rollout_fused_kernel(
 // ------------------------------------------------------------------------------------------------
 constexpr int kBigWarps = 16;
 
-template <int SCENE>
+template <int SCENE, bool SMALL = false>
 __device__ __forceinline__ RowB1 row_phase_b1_list(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
                                                    int b, int &n_list, bool &dense) {
   const cb200_rollout_cfg &cfg = a.cfg;
@@ -526,7 +526,7 @@ __device__ __forceinline__ RowB1 row_phase_b1_list(const FusedArgs &a, const Rob
   n_list = 0;
   dense = false;
   if (cfg.self_weight > 0.0f && rv.P > 0) {
-    r.fmax = warp_self_collision_tiles<false>(rv, es, lane, r.bi, r.bj);
+    r.fmax = warp_self_collision_tiles<false, !SMALL>(rv, es, lane, r.bi, r.bj);
     r.self_c = (r.fmax > 0.0f) ? 0.5f * cfg.self_weight * r.fmax : 0.0f;
   }
   if (a.self_cost && lane == 0) a.self_cost[e] = r.self_c;
@@ -626,6 +626,7 @@ __device__ __forceinline__ RowB1 row_phase_b1_list(const FusedArgs &a, const Rob
   return r;
 }
 
+template <bool SMALL = false>
 __device__ __forceinline__ void row_phase_b2_list(const FusedArgs &a, const RobotView &rv, const EvalSmem &es, int lane, int e,
                                                   const RowB1 &r, float cs_cost, float pose_c, int n_list, bool dense) {
   if (r.fmax > 0.0f) {  // the worst pair's gradient: two more list entries
@@ -641,7 +642,7 @@ __device__ __forceinline__ void row_phase_b2_list(const FusedArgs &a, const Robo
   }
   float *gq = a.grad_q + (size_t)e * rv.D;
   if (!dense) {
-    warp_fk_backward_list(rv, es, lane, gq, n_list);
+    warp_fk_backward_list<SMALL>(rv, es, lane, gq, n_list);
   } else {
     warp_drain_list_to_ft(rv, es, lane, n_list);
     warp_fk_backward_from_ft(rv, es, lane, gq);
@@ -651,7 +652,9 @@ __device__ __forceinline__ void row_phase_b2_list(const FusedArgs &a, const Robo
   __syncwarp();
 }
 
-template <int SCENE>
+// SMALL: arms (<= 24 links, <= 128 spheres) that come here because of an ESDF scene -- the trims of the IK kernel's arm build
+// (whole-block self-collision scan, one-slot J^T with the tool frames in the list loop): less code to fetch per row.
+template <int SCENE, bool SMALL = false>
 __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_big_kernel(const __grid_constant__ FusedArgs a) {
   CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
@@ -673,8 +676,8 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_big_kernel(co
     row_phase_a<false>(a, rv, es, lane, e, b, h, cs_cost, pose_c);
     int n_list;
     bool dense;
-    const RowB1 r = row_phase_b1_list<SCENE>(a, rv, es, lane, e, b, n_list, dense);
-    row_phase_b2_list(a, rv, es, lane, e, r, cs_cost, pose_c, n_list, dense);
+    const RowB1 r = row_phase_b1_list<SCENE, SMALL>(a, rv, es, lane, e, b, n_list, dense);
+    row_phase_b2_list<SMALL>(a, rv, es, lane, e, r, cs_cost, pose_c, n_list, dense);
     if (a.work_counter != nullptr) {
       int nxt = 0;
       if (lane == 0) nxt = total_warps + atomicAdd(a.work_counter, 1);
@@ -3289,17 +3292,20 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   const bool big_fit = !traj && a.spl.knots == nullptr && h.n_lp > 0 && h.P > 0;
   const bool big_want = big_env >= 0 ? big_env != 0 : ((size_t)a.eval_floats * sizeof(float) > 8192 || (scene & 2) != 0);
   if (big_fit && big_want) {
-    static KernelT const big_table[4] = {rollout_fused_big_kernel<0>, rollout_fused_big_kernel<1>, rollout_fused_big_kernel<2>,
-                                         rollout_fused_big_kernel<3>};
+    static KernelT const big_table[2][4] = {
+        {rollout_fused_big_kernel<0>, rollout_fused_big_kernel<1>, rollout_fused_big_kernel<2>, rollout_fused_big_kernel<3>},
+        {rollout_fused_big_kernel<0, true>, rollout_fused_big_kernel<1, true>, rollout_fused_big_kernel<2, true>,
+         rollout_fused_big_kernel<3, true>}};
+    const int small_arm = (h.nl <= 24 && h.S <= 128) ? 1 : 0;
     // (an 18-warp build -- 576 threads, 96 registers, small spills -- measured 0.237 ms on G1-29 against 0.219 ms for 16 warps)
     const int maxw = kBigWarps;
-    KernelT bk = big_table[scene];
+    KernelT bk = big_table[small_arm][scene];
     struct BigPlan {
       long long key = -1;
       int nw = 0, per_sm = 0;
     };
-    static thread_local BigPlan bplans[4];
-    BigPlan &bp = bplans[scene];
+    static thread_local BigPlan bplans[2][4];
+    BigPlan &bp = bplans[small_arm][scene];
     const int big_floats = big_smem_floats(h.nl, h.D, h.S, h.L, h.n_cl);
     const long long bkey = ((long long)h.smem_bytes << 32) ^ ((long long)big_floats << 8) ^ ((long long)(d.ordinal + 1) << 56);
     if (bkey != bp.key) {

@@ -724,7 +724,56 @@ __device__ __forceinline__ void warp_list_accumulate(const RobotView &rv, const 
 }
 
 // sparse J^T over the list (the transposed chain walk of warp_fk_backward_sparse with the list as the source)
+// SMALL: as in warp_fk_backward_sparse (<= 24 links: one link per lane; tool frames go through the same loop as the list).
+template <bool SMALL = false>
 __device__ __forceinline__ void warp_fk_backward_list(const RobotView &rv, const EvalSmem &es, int lane, float *gq_out, int n) {
+  if (SMALL) {
+    float sc = 0.0f;
+    V3 ax = mk3(0, 0, 0), og = mk3(0, 0, 0);
+    int jt = -1;
+    if (lane < rv.nl) {
+      jt = rv.joint_type[lane];
+      if (jt >= 0) {
+        const float *Tj = es.cumul + 12 * lane;
+        const int a = (jt >= JT_XR) ? jt - JT_XR : jt;
+        ax = mk3(Tj[a], Tj[4 + a], Tj[8 + a]);
+        og = mk3(Tj[3], Tj[7], Tj[11]);
+        sc = rv.joff[2 * lane];
+      }
+    }
+    float acc = 0.0f;
+#pragma unroll 1
+    for (int i = 0; i < n + rv.L; ++i) {
+      V3 p, g, om = mk3(0, 0, 0);
+      int k;
+      if (i < n) {
+        const float4 g4 = es.glist[i];
+        const int s = __float_as_int(g4.w);
+        const float4 p4 = es.sph[s];
+        k = rv.sph_link[s];
+        p = mk3(p4.x, p4.y, p4.z);
+        g = mk3(g4.x, g4.y, g4.z);
+      } else {
+        const float *pg = es.pose_g + 8 * (i - n);
+        k = rv.tool_map[i - n];
+        const float *Tk = es.cumul + 12 * k;
+        p = mk3(Tk[3], Tk[7], Tk[11]);
+        g = mk3(pg[0], pg[1], pg[2]);
+        om = mk3(pg[4], pg[5], pg[6]);
+        if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && om.x == 0.0f && om.y == 0.0f && om.z == 0.0f) continue;
+      }
+      if (jt >= 0 && ((rv.anc_mask[k] >> lane) & 1ull))
+        acc += (jt >= JT_XR) ? sc * (dot(ax, cross(p - og, g)) + dot(ax, om)) : sc * dot(ax, g);
+    }
+    if (lane < rv.nl) es.contrib[lane] = acc;
+    __syncwarp();
+    for (int d = lane; d < rv.D; d += 32) {
+      float g = es.gqv[d];
+      for (int i = rv.jl_off[d]; i < rv.jl_off[d + 1]; ++i) g += es.contrib[rv.jl_idx[i]];
+      gq_out[d] = g;
+    }
+    return;
+  }
   const int nu = rv.nl > 32 ? 2 : 1;
   V3 ax[2], og[2];
   float sc[2];
