@@ -1035,7 +1035,8 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_team_kernel(c
 // waypoint (warp 0 / the last warp also compute the halo waypoints' spheres), the CTA synchronises, then
 // every warp runs phase B reading its neighbours' sphere positions from shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int SCENE, bool SPLINE>
+// SMALL: arms (<= 24 links, <= 128 spheres): whole-block self-collision scan and the one-slot sparse J^T (see the IK arm build).
+template <int SCENE, bool SPLINE, bool SMALL = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_kernel(const __grid_constant__ FusedArgs a) {
   CB200_EXTERN_SHARED __align__(128) unsigned char smem[];
   __shared__ unsigned long long mbar;
@@ -1089,11 +1090,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CB200_MINB) rollout_traj_ke
       const float4 *prev = nullptr, *next = nullptr;
       if (h > 0) prev = (warp > 0) ? reinterpret_cast<const float4 *>(all + (size_t)(warp - 1) * a.eval_floats + rv.nl * 12) : halo_prev;
       if (h < a.H - 1) next = (warp < nwarps - 1) ? reinterpret_cast<const float4 *>(all + (size_t)(warp + 1) * a.eval_floats + rv.nl * 12) : halo_next;
-      r = row_phase_b1<true, SCENE>(a, rv, es, lane, e, b, prev, next);
+      r = row_phase_b1<true, SCENE, !SMALL>(a, rv, es, lane, e, b, prev, next);
     }
     if (threadIdx.x == 0 && a.work_counter != nullptr) next_tile = (int)gridDim.x + atomicAdd(a.work_counter, 1);
     __syncthreads();
-    if (active) row_phase_b2(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
+    if (active) row_phase_b2<SMALL>(a, rv, es, smem, lane, e, r, cs_cost, pose_c);
     // (next_tile is rewritten only after the next iteration's first __syncthreads, which every thread passes after this read)
     tile = a.work_counter != nullptr ? (long long)next_tile : tile + gridDim.x;
   }
@@ -3422,6 +3423,14 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   }
   int variant = (traj ? 1 : 0) + (a.spl.knots != nullptr ? 3 : 0);
   KernelT kern = table[variant][scene];
+  if (traj && h.nl <= 24 && h.S <= 128) {
+    static KernelT const traj_small[2][4] = {
+        {rollout_traj_kernel<0, false, true>, rollout_traj_kernel<1, false, true>, rollout_traj_kernel<2, false, true>,
+         rollout_traj_kernel<3, false, true>},
+        {rollout_traj_kernel<0, true, true>, rollout_traj_kernel<1, true, true>, rollout_traj_kernel<2, true, true>,
+         rollout_traj_kernel<3, true, true>}};
+    kern = traj_small[a.spl.knots != nullptr ? 1 : 0][scene];
+  }
   if (io->dynamics != nullptr) {
     // inverse dynamics inside the trajectory kernel: rows must come from caller-provided states (or the expanded spline
     // schedule, which arrives here with a.spl.knots == nullptr) and the STATE c-space cost must be on
