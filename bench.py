@@ -674,7 +674,16 @@ def main():
 
     if "knots" in args.workload:
         raise SystemExit("the B-spline knots workload is measured under other_workloads (--extra-workloads) only")
+    def last_kernel():
+        """name of the kernel the last rollout launch used (include/curobo_b200.h: CB200_VARIANT_*)"""
+        from curobo_b200 import lib as cblib
+        names = {1: "rollout_fused_kernel", 2: "rollout_fused_kernel (80-register arm build)", 4: "rollout_fused_big_kernel",
+                 5: "rollout_fused_team_kernel<2 warps per row>", 6: "rollout_fused_team_kernel<4 warps per row>",
+                 7: "rollout_traj_kernel", 8: "rollout_traj_dyn_kernel", 9: "rollout_tile_kernel", 10: "rollout_lane_kernel"}
+        return names.get(int(cblib.load().cb200_last_rollout_variant()), "?")
+
     wl, eng, q, ms_list, ms_warm = timed_run(args.workload, args.steps, args.warmup, preroll_s=0.5, warm_too=True)
+    headline_kernel = last_kernel()
     evals_per_step = wl["B"] * wl["H"]
     total_ms_max = max_over_ranks(float(sum(ms_list)))
     value = world * evals_per_step * args.steps / (total_ms_max * 1e-3)
@@ -786,7 +795,7 @@ def main():
                     "api": "curobo_b200.rollout.HostRolloutPipeline: one CUDA graph per step = H2D + rollout kernel + D2H"},
             "gpu_launches": args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "rollout_fused_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": headline_kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "bytes_per_eval": wl["bytes_per_eval"], "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "note": "path is FP32-issue/latency bound by construction (working set is L2-resident); see DESIGN.md"},
@@ -800,7 +809,7 @@ def main():
                     w2, _, _, ms2, _ = timed_run(name, max(5, args.steps // 5), 3)
                     k_ms = float(np.mean(ms2))
                     ach = w2["bytes_per_eval"] * w2["B"] * w2["H"] / (k_ms * 1e-3) / 1e9
-                    others[name] = {"value": w2["B"] * w2["H"] / (k_ms * 1e-3), "kernel_ms": k_ms,
+                    others[name] = {"value": w2["B"] * w2["H"] / (k_ms * 1e-3), "kernel_ms": k_ms, "kernel": last_kernel(),
                                     "bytes_per_eval": w2["bytes_per_eval"], "hbm_frac": ach / peak}
                     if w2["cfg"].use_sweep and w2.get("q") is not None and name in ("franka_mpc_1024x30_esdf_swept",
                                                                                      "franka_trajopt_32x32_esdf_swept"):
