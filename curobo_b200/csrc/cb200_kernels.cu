@@ -3220,6 +3220,10 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     const char *e = getenv("CB200_ARM_REGCAP");
     return e ? atoi(e) : 1;
   }();
+  static const int arm_esdf = []() {  // 0: arms against an ESDF always take the big-robot kernel (the round-2 default before 3l)
+    const char *e = getenv("CB200_ARM_ESDF");
+    return e ? atoi(e) : 1;
+  }();
   // small robots (arms) in discrete mode: thread-per-row "lane" schedule
   static const int lane_env = []() {
     const char *e = getenv("CB200_LANE");
@@ -3286,12 +3290,16 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
   }
   // big robots (humanoids) and ESDF scenes, discrete mode: the list-based kernel with up to 16 warps per SM (see
   // rollout_fused_big_kernel).  CB200_BIG = 0 / 1 forces it off / on.  Default: on when a row of the standard layout exceeds
-  // 8 KB, and for any robot against an ESDF (Franka + 256^3 ESDF: 0.089 ms vs 0.096 ms; with cuboids only the 80-register arm
-  // build of the standard kernel is faster, 0.076 ms vs 0.082 ms).
+  // 8 KB, and against an ESDF for robots that have no 80-register arm build (or too few rows to fill it: see arm_sized below).
   const char *big_str = getenv("CB200_BIG");  // read per call: tests switch it inside one process
   const int big_env = big_str ? atoi(big_str) : -1;
   const bool big_fit = !traj && a.spl.knots == nullptr && h.n_lp > 0 && h.P > 0;
-  const bool big_want = big_env >= 0 ? big_env != 0 : ((size_t)a.eval_floats * sizeof(float) > 8192 || (scene & 2) != 0);
+  // (arms against an ESDF: the 80-register arm build of the standard kernel is faster at full batches -- Franka + 256^3 ESDF,
+  //  16,384 rows: 0.0793 vs 0.0864 ms -- so they come here only when rows are scarce enough for two warps per row)
+  const bool arm_sized = arm_regcap != 0 && arm_esdf != 0 && h.nl <= 24 && h.S <= 128;
+  const bool big_want = big_env >= 0 ? big_env != 0
+                                     : ((size_t)a.eval_floats * sizeof(float) > 8192 ||
+                                        ((scene & 2) != 0 && (!arm_sized || N * 2 <= (long long)d.sm_count * kBigWarps)));
   if (big_fit && big_want) {
     static KernelT const big_table[2][4] = {
         {rollout_fused_big_kernel<0>, rollout_fused_big_kernel<1>, rollout_fused_big_kernel<2>, rollout_fused_big_kernel<3>},
@@ -3492,7 +3500,7 @@ int cb200_rollout_cost_grad(const cb200_rollout_cfg *cfg, const cb200_rollout_io
     CB200_LAUNCH(dk, (int)(grid_ll < 1 ? 1 : grid_ll), dpl.nw * 32, dpl.smem, (cudaStream_t)stream, a, dpl.R);
     return finish();
   }
-  if (variant == 0 && arm_regcap != 0 && scene <= 1 && h.nl <= 24 && h.S <= 128) {  // ESDF variants spill at 80: -3 %
+  if (variant == 0 && arm_regcap != 0 && (scene <= 1 || arm_esdf != 0) && h.nl <= 24 && h.S <= 128) {
     kern = arm_table[scene];
     variant = 5;
   }
