@@ -70,3 +70,48 @@ def launch_esdf_signed_distance(site_index: torch.Tensor, static_sdf, combined_s
     err = _lib.load().cb200_esdf_signed_distance(site_index.data_ptr(), ptrs[0], ptrs[1], distance.data_ptr(), int(nx), int(ny),
                                                  int(nz), float(voxel_size), float(adjacent_skip_steps), stream_ptr(dev))
     _lib.check(err, "esdf_signed_distance")
+
+
+def launch_tsdf_integrate_depth(block_data: torch.Tensor, nx: int, ny: int, nz: int, voxel_size: float, origin,
+                                intrinsics: torch.Tensor, cam_positions: torch.Tensor, cam_quaternions: torch.Tensor,
+                                depth_images: torch.Tensor, depth_min: float, depth_max: float, truncation_distance: float) -> None:
+    """Dense form of integrate_voxels_kernel (builder_camera_integrate.py:399-489): block_data [nx*ny*nz, 2] float16 holds
+    (sum sdf * w, sum w) per voxel and is updated in place from depth_images [C, H, W] (float32, metres), intrinsics [C, 3, 3],
+    cam_positions [C, 3], cam_quaternions [C, 4] (wxyz, camera -> world).  `origin` = grid centre (3 floats, host)."""
+    import ctypes as C
+    dev = block_data.device
+    check_tensors(dev, torch.float16, block_data=block_data)
+    check_tensors(dev, torch.float32, intrinsics=intrinsics, cam_positions=cam_positions, cam_quaternions=cam_quaternions,
+                  depth_images=depth_images)
+    n = int(nx) * int(ny) * int(nz)
+    if block_data.numel() != 2 * n:
+        raise ValueError(f"block_data must hold 2 * nx*ny*nz = {2 * n} elements")
+    if depth_images.dim() != 3:
+        raise ValueError("depth_images must be [num_cameras, height, width]")
+    c, h, w = (int(v) for v in depth_images.shape)
+    if intrinsics.numel() != 9 * c or cam_positions.numel() != 3 * c or cam_quaternions.numel() != 4 * c:
+        raise ValueError("intrinsics / cam_positions / cam_quaternions must be [C,3,3] / [C,3] / [C,4] for C = depth_images.shape[0]")
+    org = (C.c_float * 3)(*[float(v) for v in origin])
+    err = _lib.load().cb200_tsdf_integrate_depth(block_data.data_ptr(), int(nx), int(ny), int(nz), float(voxel_size), org, c,
+                                                 intrinsics.data_ptr(), cam_positions.data_ptr(), cam_quaternions.data_ptr(),
+                                                 depth_images.data_ptr(), h, w, float(depth_min), float(depth_max),
+                                                 float(truncation_distance), stream_ptr(dev))
+    _lib.check(err, "tsdf_integrate_depth")
+
+
+def launch_tsdf_combined_sdf(block_data: torch.Tensor, static_sdf, combined_sdf: torch.Tensor, min_weight: float) -> None:
+    """combined_sdf (float32) = min(sum_sdf_w / sum_w where sum_w > min_weight else 1e10, static_sdf): sample_combined_sdf
+    (wp_tsdf_sample.py:22-97) for the dense grid."""
+    dev = block_data.device
+    check_tensors(dev, torch.float16, block_data=block_data)
+    check_tensors(dev, torch.float32, combined_sdf=combined_sdf)
+    n = combined_sdf.numel()
+    if block_data.numel() != 2 * n:
+        raise ValueError("block_data must hold two float16 per voxel of combined_sdf")
+    if static_sdf is not None:
+        check_tensors(dev, torch.float32, static_sdf=static_sdf)
+        if static_sdf.numel() != n:
+            raise ValueError("static_sdf must match combined_sdf")
+    err = _lib.load().cb200_tsdf_combined_sdf(block_data.data_ptr(), None if static_sdf is None else static_sdf.data_ptr(),
+                                              combined_sdf.data_ptr(), n, float(min_weight), stream_ptr(dev))
+    _lib.check(err, "tsdf_combined_sdf")

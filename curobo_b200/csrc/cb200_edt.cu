@@ -165,6 +165,73 @@ __global__ void __launch_bounds__(256) esdf_signed_distance_kernel(const int *__
   }
 }
 
+// Depth -> TSDF for a DENSE grid at the ESDF's resolution: the voxel-centric projective update of the reference's camera
+// integrator (perception/mapper/kernel/builder/builder_camera_integrate.py:399-489, integrate_voxels_kernel) with the dense
+// index in place of (block pool index, local index); the block discovery / allocation phases 1-3 of the block-sparse store (hash
+// table) are out of scope.  block_data[i] = (sum of sdf * weight, sum of weight) as two fp16, accumulated in fp32 and rounded
+// once per call, as the reference does.  Voxel centre = (idx + 0.5 - n / 2) * voxel_size + origin (builder_coord.py:57-66).
+struct TsdfCameras {
+  const float *intrinsics;  // [C, 3, 3]
+  const float *position;    // [C, 3]
+  const float *quaternion;  // [C, 4] wxyz, camera -> world
+  const float *depth;       // [C, H, W] metres
+  int num, height, width;
+};
+__global__ void __launch_bounds__(256) tsdf_integrate_depth_kernel(__half *__restrict__ block_data, int nx, int ny, int nz,
+                                                                    long long total, float voxel_size, float ox, float oy, float oz,
+                                                                    TsdfCameras cams, float depth_min, float depth_max,
+                                                                    float truncation) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((long long)nz * ny));
+    const float wx = ((float)x + 0.5f - (float)nx * 0.5f) * voxel_size + ox, wy = ((float)y + 0.5f - (float)ny * 0.5f) * voxel_size + oy,
+                wz = ((float)z + 0.5f - (float)nz * 0.5f) * voxel_size + oz;
+    float total_sw = 0.0f, total_w = 0.0f;
+    for (int c = 0; c < cams.num; ++c) {
+      const float *cp = cams.position + 3 * c, *cq = cams.quaternion + 4 * c, *K = cams.intrinsics + 9 * c;
+      // wp.quat_rotate(quat_inverse(q), v): v (2 w^2 - 1) + 2 w (qv x v) + 2 qv (qv . v) with qv = -(x, y, z)
+      const float qx = -cq[1], qy = -cq[2], qz = -cq[3], qw = cq[0];
+      const float vx = wx - cp[0], vy = wy - cp[1], vz = wz - cp[2];
+      const float cc = 2.0f * qw * qw - 1.0f;
+      const float crx = qy * vz - qz * vy, cry = qz * vx - qx * vz, crz = qx * vy - qy * vx;
+      const float d = qx * vx + qy * vy + qz * vz;
+      const float xc = vx * cc + crx * qw * 2.0f + qx * d * 2.0f, yc = vy * cc + cry * qw * 2.0f + qy * d * 2.0f,
+                  zc = vz * cc + crz * qw * 2.0f + qz * d * 2.0f;
+      if (!(zc > depth_min)) continue;
+      const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+      // (IEEE divisions: the library is built with approximate division, and the pixel index must not depend on it)
+      const float u = __fdiv_rn(fx * xc, zc) + cx, v = __fdiv_rn(fy * yc, zc) + cy;
+      const int px = (int)u, py = (int)v;  // truncation towards zero, as wp.int32(float)
+      if (px < 0 || px >= cams.width || py < 0 || py >= cams.height) continue;
+      const float depth = cams.depth[((long long)c * cams.height + py) * cams.width + px];
+      if (!(depth >= depth_min && depth <= depth_max)) continue;
+      const float sdf = depth - zc;
+      if (!(sdf >= -truncation)) continue;
+      const float sdf_clamped = fminf(sdf, truncation);
+      const float coverage = __fdiv_rn(fx * voxel_size, zc) * __fdiv_rn(fy * voxel_size, zc);
+      const float weight = fmaxf(coverage, 1.0f);  // compute_tsdf_weight == 1 (wp_integrate_common.py:57-105)
+      total_sw += sdf_clamped * weight;
+      total_w += weight;
+    }
+    if (total_w > 0.0f) {
+      const float old_sw = __half2float(block_data[2 * i]), old_w = __half2float(block_data[2 * i + 1]);
+      block_data[2 * i] = __float2half_rn(old_sw + total_sw);
+      block_data[2 * i + 1] = __float2half_rn(old_w + total_w);
+    }
+  }
+}
+
+// combined SDF of the dynamic (depth) and static channels: wp_tsdf_sample.py:22-97 (sample_dynamic_sdf / sample_combined_sdf):
+// sum_sdf_w / sum_w where the weight exceeds min_weight, else 1e10 (unobserved); min with the static SDF when there is one.
+__global__ void __launch_bounds__(256) tsdf_combined_sdf_kernel(const __half *__restrict__ block_data, const float *__restrict__ static_sdf,
+                                                                 float *__restrict__ out, long long total, float min_weight) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float sw = __half2float(block_data[2 * i]), w = __half2float(block_data[2 * i + 1]);
+    float d = w > min_weight ? __fdiv_rn(sw, w) : 1e10f;
+    if (static_sdf != nullptr) d = fminf(d, static_sdf[i]);
+    out[i] = d;
+  }
+}
+
 template <class K>
 bool allow_smem(K kern, int smem) {
   if (smem <= 48 * 1024) return true;
@@ -246,6 +313,32 @@ int cb200_esdf_signed_distance(const int32_t *site_index, const float *static_sd
   const long long total = (long long)nx * ny * nz;
   CB200_LAUNCH(esdf_signed_distance_kernel, grid_for((total + 255) / 256), 256, 0, (cudaStream_t)stream, site_index, static_sdf,
                combined_sdf, reinterpret_cast<__half *>(distance_fp16), nx, ny, nz, total, voxel_size, adjacent_skip_steps);
+  return status(cudaGetLastError());
+}
+
+int cb200_tsdf_integrate_depth(uint16_t *block_data_fp16, int nx, int ny, int nz, float voxel_size, const float *origin,
+                               int num_cameras, const float *intrinsics, const float *cam_positions,
+                               const float *cam_quaternions, const float *depth_images, int image_height, int image_width,
+                               float depth_min, float depth_max, float truncation_distance, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(block_data_fp16);
+  if (block_data_fp16 == nullptr || origin == nullptr || intrinsics == nullptr || cam_positions == nullptr ||
+      cam_quaternions == nullptr || depth_images == nullptr || !dims_ok(nx, ny, nz) || !(voxel_size > 0.0f) || num_cameras < 1 ||
+      image_height < 1 || image_width < 1 || !(truncation_distance > 0.0f))
+    return status(cudaErrorInvalidValue);
+  const long long total = (long long)nx * ny * nz;
+  const TsdfCameras cams{intrinsics, cam_positions, cam_quaternions, depth_images, num_cameras, image_height, image_width};
+  CB200_LAUNCH(tsdf_integrate_depth_kernel, grid_for((total + 255) / 256), 256, 0, (cudaStream_t)stream,
+               reinterpret_cast<__half *>(block_data_fp16), nx, ny, nz, total, voxel_size, origin[0], origin[1], origin[2], cams,
+               depth_min, depth_max, truncation_distance);
+  return status(cudaGetLastError());
+}
+
+int cb200_tsdf_combined_sdf(const uint16_t *block_data_fp16, const float *static_sdf, float *combined_sdf, long long num_voxels,
+                            float min_weight, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(combined_sdf);
+  if (block_data_fp16 == nullptr || combined_sdf == nullptr || num_voxels < 1) return status(cudaErrorInvalidValue);
+  CB200_LAUNCH(tsdf_combined_sdf_kernel, grid_for((num_voxels + 255) / 256), 256, 0, (cudaStream_t)stream,
+               reinterpret_cast<const __half *>(block_data_fp16), static_sdf, combined_sdf, num_voxels, min_weight);
   return status(cudaGetLastError());
 }
 

@@ -96,3 +96,35 @@ class DenseESDFBuilder:
                                            combined_sdf.view(-1), self.dist_field.view(-1), nx, ny, nz, self.edt.voxel_size,
                                            self.adjacent_skip_steps)
         return self.dist_field
+
+
+class DenseTSDF:
+    """Depth images -> TSDF on a dense grid [nx, ny, nz] at the ESDF's resolution: the voxel-centric projective update of the
+    reference's CameraProjectIntegrator (kernel/builder/builder_camera_integrate.py:399-489) without the block-sparse store in
+    front of it.  `block_data` [nx, ny, nz, 2] float16 = (sum sdf * w, sum w); `combined_sdf(static_sdf)` is what
+    DenseESDFBuilder.compute takes (sample_combined_sdf, kernel/wp_tsdf_sample.py:22-97).  Buffers are allocated once."""
+
+    def __init__(self, grid_shape: Tuple[int, int, int], voxel_size: float, truncation_distance: float, device,
+                 origin=(0.0, 0.0, 0.0), depth_min: float = 0.1, depth_max: float = 10.0, minimum_tsdf_weight: float = 0.1):
+        self.grid_shape = tuple(int(v) for v in grid_shape)
+        self.voxel_size, self.truncation_distance = float(voxel_size), float(truncation_distance)
+        self.origin = tuple(float(v) for v in origin)
+        self.depth_min, self.depth_max, self.minimum_tsdf_weight = float(depth_min), float(depth_max), float(minimum_tsdf_weight)
+        self.device = torch.device(device)
+        self.block_data = torch.zeros(self.grid_shape + (2,), dtype=torch.float16, device=self.device)
+        self._combined = torch.empty(self.grid_shape, dtype=torch.float32, device=self.device)
+
+    def reset(self) -> None:
+        self.block_data.zero_()
+
+    def integrate(self, depth_images: torch.Tensor, intrinsics: torch.Tensor, cam_positions: torch.Tensor,
+                  cam_quaternions: torch.Tensor) -> None:
+        nx, ny, nz = self.grid_shape
+        pba_cu.launch_tsdf_integrate_depth(self.block_data.view(-1), nx, ny, nz, self.voxel_size, self.origin, intrinsics,
+                                           cam_positions, cam_quaternions, depth_images, self.depth_min, self.depth_max,
+                                           self.truncation_distance)
+
+    def combined_sdf(self, static_sdf: torch.Tensor = None) -> torch.Tensor:
+        pba_cu.launch_tsdf_combined_sdf(self.block_data.view(-1), None if static_sdf is None else static_sdf.view(-1),
+                                        self._combined.view(-1), self.minimum_tsdf_weight)
+        return self._combined

@@ -492,6 +492,25 @@ int cb200_esdf_seed_sites(const float *combined_sdf, int32_t *site_index, int nx
 int cb200_esdf_signed_distance(const int32_t *site_index, const float *static_sdf, const float *combined_sdf,
                                uint16_t *distance_fp16, int nx, int ny, int nz, float voxel_size, float adjacent_skip_steps,
                                cb200_stream_t stream);
+/* Depth images -> TSDF -> combined SDF, the stage in front of the seeding, for the same DENSE grid:
+ *   cb200_tsdf_integrate_depth  <- integrate_voxels_kernel  kernel/builder/builder_camera_integrate.py:399-489 (phase 4 of
+ *                                  CameraProjectIntegrator, kernel/wp_integrate_camera_project.py:27-41): one thread per voxel,
+ *                                  serial camera loop: voxel centre ((idx + 0.5 - n / 2) voxel + origin, builder_coord.py:57-66)
+ *                                  into the camera frame (quaternion wxyz = camera -> world), pinhole projection, pixel index by
+ *                                  truncation, depth within [depth_min, depth_max], sdf = depth - z_cam kept when >= -truncation
+ *                                  and clamped to +truncation, weight = max((fx voxel / z)(fy voxel / z), 1)
+ *                                  (compute_tsdf_weight == 1, kernel/wp_integrate_common.py:57-105);
+ *                                  block_data[voxel] = fp16 pair (sum sdf * w, sum w), accumulated in fp32, rounded once per call.
+ *                                  The block discovery / allocation phases of the block-sparse store are out of scope.
+ *   cb200_tsdf_combined_sdf     <- sample_combined_sdf  kernel/wp_tsdf_sample.py:22-97: sum_sdf_w / sum_w where the weight exceeds
+ *                                  min_weight, else 1e10; min with static_sdf (may be NULL).  Output feeds cb200_esdf_seed_sites. */
+int cb200_tsdf_integrate_depth(uint16_t *block_data_fp16, int nx, int ny, int nz, float voxel_size, const float *origin /* host [3] */,
+                               int num_cameras, const float *intrinsics /* [C,3,3] */, const float *cam_positions /* [C,3] */,
+                               const float *cam_quaternions /* [C,4] wxyz */, const float *depth_images /* [C,H,W] */,
+                               int image_height, int image_width, float depth_min, float depth_max, float truncation_distance,
+                               cb200_stream_t stream);
+int cb200_tsdf_combined_sdf(const uint16_t *block_data_fp16, const float *static_sdf, float *combined_sdf, long long num_voxels,
+                            float min_weight, cb200_stream_t stream);
 
 /* Host helper: pack robot constants (HOST pointers) into `out` (host buffer of
  * cb200_robot_blob_bytes(...) bytes) that the caller then copies to the device once.

@@ -206,3 +206,69 @@ def signed_distance_fp16(result, static_sdf, combined_sdf, voxel_size, skip_step
         src = np.where(src > 1e9, np.asarray(combined_sdf, np.float32), src)
     signed = np.where(~(src > 1e9) & (src < 0), -edt, edt)
     return np.where(r < 0, np.float32(1e4), signed).astype(np.float16)
+
+
+def tsdf_integrate_depth(block_data, voxel_size, origin, intrinsics, cam_positions, cam_quaternions, depth_images, depth_min,
+                         depth_max, truncation):
+    """Dense restatement of integrate_voxels_kernel (perception/mapper/kernel/builder/builder_camera_integrate.py:399-489) --
+    TEST INFRASTRUCTURE.  block_data [nx, ny, nz, 2] float16 = (sum sdf * w, sum w), returned updated (a copy).
+    Voxel centre (idx + 0.5 - n / 2) voxel + origin (builder_coord.py:57-66); camera frame by wp.quat_rotate(quat_inverse(q), .)
+    = v (2 w^2 - 1) + 2 w (qv x v) + 2 qv (qv . v); pixel index by truncation towards zero; sdf = depth - z_cam kept when
+    >= -truncation, clamped to +truncation; weight = max((fx voxel / z)(fy voxel / z), 1) (compute_tsdf_weight == 1,
+    wp_integrate_common.py:57-105); fp32 accumulation over the cameras, one fp16 rounding per call.  All arithmetic in float32 in
+    the kernel's order.  Parity at the Warp boundary unpinned (warp-lang is not installed); pinned on analytic scenes in tests."""
+    f = np.float32
+    bd = np.array(block_data, dtype=np.float16, copy=True)
+    nx, ny, nz = bd.shape[:3]
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    wx = (ix.astype(f) + f(0.5) - f(nx) * f(0.5)) * f(voxel_size) + f(origin[0])
+    wy = (iy.astype(f) + f(0.5) - f(ny) * f(0.5)) * f(voxel_size) + f(origin[1])
+    wz = (iz.astype(f) + f(0.5) - f(nz) * f(0.5)) * f(voxel_size) + f(origin[2])
+    tot_sw = np.zeros((nx, ny, nz), f)
+    tot_w = np.zeros((nx, ny, nz), f)
+    C, H, W = depth_images.shape
+    for c in range(C):
+        K = np.asarray(intrinsics[c], f)
+        cp = np.asarray(cam_positions[c], f)
+        q = np.asarray(cam_quaternions[c], f)                                 # wxyz
+        qx, qy, qz, qw = -q[1], -q[2], -q[3], q[0]
+        vx, vy, vz = wx - cp[0], wy - cp[1], wz - cp[2]
+        cc = f(2.0) * qw * qw - f(1.0)
+        crx, cry, crz = qy * vz - qz * vy, qz * vx - qx * vz, qx * vy - qy * vx
+        d = qx * vx + qy * vy + qz * vz
+        xc = vx * cc + crx * qw * f(2.0) + qx * d * f(2.0)
+        yc = vy * cc + cry * qw * f(2.0) + qy * d * f(2.0)
+        zc = vz * cc + crz * qw * f(2.0) + qz * d * f(2.0)
+        ok = zc > f(depth_min)
+        zs = np.where(ok, zc, f(1.0))
+        fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+        u = fx * xc / zs + cx
+        v = fy * yc / zs + cy
+        with np.errstate(invalid="ignore"):
+            px = np.trunc(np.clip(u, -1e9, 1e9)).astype(np.int64)
+            py = np.trunc(np.clip(v, -1e9, 1e9)).astype(np.int64)
+        ok &= (px >= 0) & (px < W) & (py >= 0) & (py < H)
+        depth = np.asarray(depth_images[c], f)[np.clip(py, 0, H - 1), np.clip(px, 0, W - 1)]
+        ok &= (depth >= f(depth_min)) & (depth <= f(depth_max))
+        sdf = depth - zc
+        ok &= sdf >= -f(truncation)
+        sdf_c = np.minimum(sdf, f(truncation))
+        cov = (fx * f(voxel_size) / zs) * (fy * f(voxel_size) / zs)
+        w = np.maximum(cov, f(1.0))
+        tot_sw += np.where(ok, sdf_c * w, f(0.0)).astype(f)
+        tot_w += np.where(ok, w, f(0.0)).astype(f)
+    upd = tot_w > 0
+    bd[..., 0] = np.where(upd, (bd[..., 0].astype(f) + tot_sw).astype(np.float16), bd[..., 0])
+    bd[..., 1] = np.where(upd, (bd[..., 1].astype(f) + tot_w).astype(np.float16), bd[..., 1])
+    return bd
+
+
+def tsdf_combined_sdf(block_data, static_sdf, min_weight):
+    """sample_combined_sdf (perception/mapper/kernel/wp_tsdf_sample.py:22-97) for the dense grid: float32 [nx, ny, nz]."""
+    f = np.float32
+    sw, w = block_data[..., 0].astype(f), block_data[..., 1].astype(f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.where(w > f(min_weight), sw / np.where(w > f(min_weight), w, f(1.0)), f(1e10)).astype(f)
+    if static_sdf is not None:
+        d = np.minimum(d, np.asarray(static_sdf, f))
+    return d

@@ -163,3 +163,45 @@ def test_signed_distance_oracle_properties():
     unknown = np.full_like(sdf, 1e10)
     assert (E.signed_distance_fp16(res, unknown, unknown, voxel, 1.0).astype(np.float32) >= 0).all()
     assert (E.signed_distance_fp16(np.full((3, 3, 3), E.EMPTY, np.int32), None, None, voxel) == np.float16(1e4)).all()
+
+
+def test_tsdf_depth_integration_oracle_on_a_plane():
+    """Oracle of the depth -> TSDF stage (restatement of integrate_voxels_kernel, builder_camera_integrate.py:399-489) on a scene
+    with a closed form: a camera at (0, 0, -1) looking along +z (identity rotation) sees a fronto-parallel plane at depth 1, i.e.
+    the world plane z = 0.  Inside the frustum sdf = depth - z_cam = -z_world, kept for z_world <= truncation (behind the surface
+    only down to -truncation is cut: sdf >= -truncation), clamped to +truncation in front; weights = max(pixel coverage, 1) per
+    integration; unobserved elsewhere.  Then sample_combined_sdf: weight threshold and the min with a static channel."""
+    from oracle import edt_oracle as E
+    shape, voxel, trunc = (16, 16, 24), 0.05, 0.2
+    H, W, f = 64, 64, 30.0
+    K = np.array([[[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]]], np.float32)
+    pos = np.array([[0.0, 0.0, -1.0]], np.float32)
+    quat = np.array([[1.0, 0.0, 0.0, 0.0]], np.float32)
+    depth = np.ones((1, H, W), np.float32)
+    bd = E.tsdf_integrate_depth(np.zeros(shape + (2,), np.float16), voxel, (0, 0, 0), K, pos, quat, depth, 0.1, 5.0, trunc)
+    wz = (np.arange(shape[2]) + 0.5 - shape[2] / 2) * voxel
+    w = bd[..., 1].astype(np.float32)
+    seen = w > 0
+    assert seen[:, :, wz <= trunc + 1e-6].all(), "the frustum covers the whole grid in front of and just behind the plane"
+    assert not seen[:, :, wz > trunc + 1e-6].any(), "more than the truncation distance behind the surface is not updated"
+    sdf = E.tsdf_combined_sdf(bd, None, 0.5)
+    front = np.broadcast_to(wz < -trunc, shape) & seen
+    band = np.broadcast_to(np.abs(wz) <= trunc, shape) & seen
+    assert np.allclose(sdf[front], trunc, atol=2e-3)
+    assert np.allclose(sdf[band], np.broadcast_to(-wz, shape)[band], atol=2e-3)
+    assert (sdf[~seen] > 1e9).all()
+    zc = wz + 1.0
+    cov = (f * voxel / zc) ** 2
+    assert np.allclose(w[8, 8, wz <= trunc], np.maximum(cov, 1.0)[wz <= trunc], rtol=2e-3)
+    bd2 = E.tsdf_integrate_depth(bd, voxel, (0, 0, 0), K, pos, quat, depth, 0.1, 5.0, trunc)          # a second frame accumulates
+    assert np.allclose(bd2[..., 1].astype(np.float32)[seen], 2 * w[seen], rtol=2e-3)
+    assert np.allclose(E.tsdf_combined_sdf(bd2, None, 0.5)[band], sdf[band], atol=3e-3)
+    assert (E.tsdf_combined_sdf(bd, None, 1e6) > 1e9).all()                                           # weight threshold
+    static = np.full(shape, 1e10, np.float32)
+    static[:, :, :3] = -0.3
+    comb = E.tsdf_combined_sdf(bd, static, 0.5)
+    assert (comb[:, :, :3] == -0.3).all() and np.array_equal(comb[:, :, 3:], sdf[:, :, 3:])
+    depth0 = depth.copy()
+    depth0[0, :, : W // 2] = 0.0                                                                      # invalid pixels: no update
+    bd3 = E.tsdf_integrate_depth(np.zeros(shape + (2,), np.float16), voxel, (0, 0, 0), K, pos, quat, depth0, 0.1, 5.0, trunc)
+    assert (bd3[: shape[0] // 2 - 1, :, :, 1] == 0).all() and (bd3[shape[0] // 2 + 1:, :, wz <= trunc, 1] > 0).all()

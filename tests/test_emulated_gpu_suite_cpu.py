@@ -284,6 +284,11 @@ def test_pending_edt(run):
         run("test_gpu_zz_edt", "test_dense_esdf_builder_vs_oracle", shape, skip)
 
 
+def test_depth_to_esdf_chain(run):
+    run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (24, 24, 24))
+    run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (40, 36, 44))
+
+
 @pytest.mark.skipif(os.environ.get("CB200_EMULATE_LONG") != "1", reason="~5 min of emulated launches: set CB200_EMULATE_LONG=1 (passes)")
 def test_complete_ik_solve(run):
     """24 goals x 16 seeds x 100 L-BFGS iterations, 3 kernel launches per iteration (step + search points, fused rollout on the

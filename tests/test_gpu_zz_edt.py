@@ -143,3 +143,97 @@ def test_dense_esdf_builder_vs_oracle(shape, skip):
     pba_cu2.launch_esdf_signed_distance(b.site_index.view(-1), None, None, out.view(-1), *shape, voxel, 1.0)
     assert np.array_equal(np.abs(gf) >= 0, np.ones(shape, bool)) and (out.cpu().numpy().astype(np.float32) >= 0).all()
     assert b2.dist_field.shape == tuple(shape)
+
+
+def _look_at_quat(eye, target):
+    """camera -> world quaternion (wxyz) of a pinhole camera at `eye` whose +z axis points at `target` (x right, y down)."""
+    zc = np.asarray(target, np.float64) - np.asarray(eye, np.float64)
+    zc /= np.linalg.norm(zc)
+    up = np.array([0.0, 0.0, 1.0]) if abs(zc[2]) < 0.9 else np.array([1.0, 0.0, 0.0])
+    xc = np.cross(zc, up)
+    xc /= np.linalg.norm(xc)
+    yc = np.cross(zc, xc)
+    R = np.stack([xc, yc, zc], 1)                                             # columns = camera axes in the world
+    w = np.sqrt(max(0.0, 1.0 + R[0, 0] + R[1, 1] + R[2, 2])) / 2.0
+    if w > 1e-6:
+        q = np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
+    else:
+        q = np.array([0.0, 1.0, 0.0, 0.0])
+    return (q / np.linalg.norm(q)).astype(np.float32), R
+
+
+def depth_scene(shape, voxel, n_cam=2, hw=(48, 64), seed=0):
+    """Cameras around a ball of radius 0.3 * extent at the grid centre: rendered depth (ray / sphere, plus a far wall), with some
+    invalid (zero) pixels."""
+    rng = np.random.default_rng(seed)
+    ext = voxel * min(shape)
+    radius = 0.3 * ext
+    H, W = hw
+    K = np.zeros((n_cam, 3, 3), np.float32)
+    pos = np.zeros((n_cam, 3), np.float32)
+    quat = np.zeros((n_cam, 4), np.float32)
+    depth = np.zeros((n_cam, H, W), np.float32)
+    for c in range(n_cam):
+        ang = 2 * np.pi * c / n_cam + 0.3
+        eye = np.array([np.cos(ang), np.sin(ang), 0.35]) * 1.6 * ext
+        q, R = _look_at_quat(eye, (0.0, 0.0, 0.0))
+        f = 0.9 * W
+        K[c] = [[f, 0, W / 2 - 0.5], [0, f, H / 2 - 0.5], [0, 0, 1]]
+        pos[c], quat[c] = eye, q
+        v, u = np.meshgrid(np.arange(H) + 0.5, np.arange(W) + 0.5, indexing="ij")
+        d = np.stack([(u - K[c, 0, 2]) / f, (v - K[c, 1, 2]) / f, np.ones_like(u)], -1)       # camera-frame ray, z = 1
+        dw = d @ R.T
+        a = (dw * dw).sum(-1)
+        b = 2 * (dw @ eye)
+        cc = eye @ eye - radius * radius
+        disc = b * b - 4 * a * cc
+        t = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), 3.0 * ext)     # z-depth of the hit (d.z = 1)
+        depth[c] = t.astype(np.float32)
+        depth[c][rng.random((H, W)) < 0.03] = 0.0
+    return K, pos, quat, depth, radius
+
+
+@pytest.mark.parametrize("shape", [(40, 36, 44), (24, 24, 24)])
+def test_depth_to_esdf_chain_vs_oracle(shape):
+    """Depth images -> DenseTSDF.integrate (dense form of the reference's integrate_voxels_kernel) -> combined SDF -> seeds ->
+    exact transform -> signed fp16 ESDF, against the oracle's restatement stage by stage.  The projection's pixel index is a
+    float truncation, so a voxel whose projection lands within rounding of a pixel edge may read the neighbouring pixel: at most
+    0.5 % of the voxels may differ from the float32 numpy restatement, the rest must match to one fp16 ulp; two integrations
+    accumulate; the ESDF of the chain has the ball's surface where the depth says it is."""
+    from curobo_b200.esdf import DenseTSDF
+    voxel = 0.02
+    trunc = 4 * voxel
+    K, pos, quat, depth, radius = depth_scene(shape, voxel, seed=sum(shape))
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    tsdf = DenseTSDF(shape, voxel, trunc, DEV, depth_min=0.05, depth_max=5.0, minimum_tsdf_weight=0.5)
+    want = np.zeros(tuple(shape) + (2,), np.float16)
+    for it in range(2):
+        tsdf.integrate(T(depth), T(K), T(pos), T(quat))
+        want = E.tsdf_integrate_depth(want, voxel, (0, 0, 0), K, pos, quat, depth, 0.05, 5.0, trunc)
+    torch.cuda.synchronize()
+    got = tsdf.block_data.cpu().numpy()
+    gw, ww = got.astype(np.float32), want.astype(np.float32)
+    close = np.isclose(gw, ww, rtol=2e-3, atol=2e-3).all(-1)
+    assert close.mean() > 0.99, f"{(~close).sum()} of {close.size} voxels differ"
+    assert (ww[..., 1] > 0).mean() > 0.02, "the cameras must see part of the grid"
+    comb = tsdf.combined_sdf().cpu().numpy()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(comb, E.tsdf_combined_sdf(got, None, 0.5), rtol=1e-6)   # same inputs, IEEE division
+    static = np.full(shape, 1e10, np.float32)
+    static[:, :, :2] = -voxel                                                 # a floor slab as the static channel
+    comb_s = tsdf.combined_sdf(T(static)).cpu().numpy()
+    np.testing.assert_allclose(comb_s, E.tsdf_combined_sdf(got, static, 0.5), rtol=1e-6)
+    b = DenseESDFBuilder(shape, voxel, trunc, DEV)
+    field = b.compute(T(comb), None).cpu().numpy().astype(np.float32)
+    torch.cuda.synchronize()
+    seeds = E.seed_sites_from_sdf(comb, voxel, trunc)
+    assert (seeds >= 0).sum() > 0
+    wantf = E.signed_distance_fp16(b.site_index.cpu().numpy(), None, comb, voxel, 1.0).astype(np.float32)
+    assert np.array_equal(np.sign(field), np.sign(wantf)), f"{int((np.sign(field) != np.sign(wantf)).sum())} signs differ"
+    assert np.abs(field - wantf).max() <= 2e-3 * max(1.0, np.abs(wantf).max())
+    # geometry: observed voxels just outside the ball's visible surface have a small positive distance close to |c| - radius
+    ix, iy, iz = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+    ctr = np.stack([(ix + 0.5 - shape[0] / 2) * voxel, (iy + 0.5 - shape[1] / 2) * voxel, (iz + 0.5 - shape[2] / 2) * voxel], -1)
+    r = np.linalg.norm(ctr, axis=-1)
+    shell = (comb < 1e9) & (np.abs(comb) < 0.5 * voxel)
+    assert shell.sum() > 20 and np.abs(r[shell] - radius).mean() < 1.5 * voxel
