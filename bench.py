@@ -302,9 +302,44 @@ def edt_bench(device, peak, n=256, iters=10):
             ts.append(e0.elapsed_time(e1))
     ms = float(np.median(ts))
     nbytes = 3 * 8 * n ** 3
-    return {"grid": [n, n, n], "sites": int(occ.sum()), "transform_ms": ms, "voxels_per_s": n ** 3 / (ms * 1e-3),
-            "bytes_per_voxel": 24, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "launches": 3,
-            "esdf_builder": esdf_builder_bench(device, n)}
+    out = {"grid": [n, n, n], "sites": int(occ.sum()), "transform_ms": ms, "voxels_per_s": n ** 3 / (ms * 1e-3),
+           "bytes_per_voxel": 24, "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "launches": 3,
+           "esdf_builder": esdf_builder_bench(device, n)}
+    try:
+        out["depth_to_esdf"] = depth_to_esdf_bench(device, n)
+    except Exception as ex:                                               # noqa: BLE001
+        out["depth_to_esdf"] = {"error": repr(ex)[:200]}
+    return out
+
+
+def depth_to_esdf_bench(device, n=256, iters=10, hw=(480, 640)):
+    """Depth frame -> collision-ready ESDF (whole chain): DenseTSDF.integrate (two rendered depth images of a
+    sphere) -> combined SDF -> DenseESDFBuilder.compute (seed + exact transform + signed fp16 distance); 7 launches per frame."""
+    import torch
+    from curobo_b200.esdf import DenseESDFBuilder, DenseTSDF
+    from curobo_b200.world import depth_scene
+    voxel = 2.56 / n
+    trunc = 4 * voxel
+    K, pos, quat, depth, _ = depth_scene((n, n, n), voxel, n_cam=2, hw=hw, seed=1)
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(device)  # noqa: E731
+    d, k, p, q = T(depth), T(K), T(pos), T(quat)
+    tsdf = DenseTSDF((n, n, n), voxel, trunc, device, depth_min=0.05, depth_max=10.0, minimum_tsdf_weight=0.5)
+    b = DenseESDFBuilder((n, n, n), voxel, trunc, device)
+    ts, ti = [], []
+    for i in range(iters + 2):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        tsdf.integrate(d, k, p, q)
+        e1.record()
+        b.compute(tsdf.combined_sdf(), None)
+        e2.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ti.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e2))
+    return {"frame_ms": float(np.median(ts)), "integrate_ms": float(np.median(ti)), "cameras": 2, "image": list(hw),
+            "observed_frac": float((tsdf.block_data[..., 1] > 0).float().mean()),
+            "stages": "depth integration + combined SDF + seed + 3-pass transform + signed fp16 distance"}
 
 
 def esdf_builder_bench(device, n=256, iters=10):

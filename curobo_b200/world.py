@@ -166,3 +166,52 @@ def make_empty_esdf(dims=(0.5, 0.5, 0.5), voxel_size=0.02, center=(0.0, 0.0, 0.0
     n = [int(round(d / voxel_size)) for d in dims]
     return VoxelWorld.from_grid(np.full(n, fill_value, np.float16), voxel_size,
                                 pose=[center[0], center[1], center[2], 1, 0, 0, 0], max_dist=max_dist)
+
+
+def _look_at_quat(eye, target):
+    """camera -> world quaternion (wxyz) of a pinhole camera at `eye` whose +z axis points at `target` (x right, y down)."""
+    zc = np.asarray(target, np.float64) - np.asarray(eye, np.float64)
+    zc /= np.linalg.norm(zc)
+    up = np.array([0.0, 0.0, 1.0]) if abs(zc[2]) < 0.9 else np.array([1.0, 0.0, 0.0])
+    xc = np.cross(zc, up)
+    xc /= np.linalg.norm(xc)
+    yc = np.cross(zc, xc)
+    R = np.stack([xc, yc, zc], 1)                                             # columns = camera axes in the world
+    w = np.sqrt(max(0.0, 1.0 + R[0, 0] + R[1, 1] + R[2, 2])) / 2.0
+    if w > 1e-6:
+        q = np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
+    else:
+        q = np.array([0.0, 1.0, 0.0, 0.0])
+    return (q / np.linalg.norm(q)).astype(np.float32), R
+
+
+def depth_scene(shape, voxel, n_cam=2, hw=(48, 64), seed=0):
+    """Synthetic input of the depth -> TSDF stage (tests, bench): n_cam pinhole cameras around a ball of radius 0.3 * extent at the
+    grid centre; rendered z-depth (ray / sphere, a far wall behind), 3 % invalid (zero) pixels.  Returns intrinsics [C,3,3],
+    positions [C,3], quaternions [C,4] (wxyz, camera -> world), depth [C,H,W] (float32) and the ball radius."""
+    rng = np.random.default_rng(seed)
+    ext = voxel * min(shape)
+    radius = 0.3 * ext
+    H, W = hw
+    K = np.zeros((n_cam, 3, 3), np.float32)
+    pos = np.zeros((n_cam, 3), np.float32)
+    quat = np.zeros((n_cam, 4), np.float32)
+    depth = np.zeros((n_cam, H, W), np.float32)
+    for c in range(n_cam):
+        ang = 2 * np.pi * c / n_cam + 0.3
+        eye = np.array([np.cos(ang), np.sin(ang), 0.35]) * 1.6 * ext
+        q, R = _look_at_quat(eye, (0.0, 0.0, 0.0))
+        f = 0.9 * W
+        K[c] = [[f, 0, W / 2 - 0.5], [0, f, H / 2 - 0.5], [0, 0, 1]]
+        pos[c], quat[c] = eye, q
+        v, u = np.meshgrid(np.arange(H) + 0.5, np.arange(W) + 0.5, indexing="ij")
+        d = np.stack([(u - K[c, 0, 2]) / f, (v - K[c, 1, 2]) / f, np.ones_like(u)], -1)       # camera-frame ray, z = 1
+        dw = d @ R.T
+        a = (dw * dw).sum(-1)
+        b = 2 * (dw @ eye)
+        cc = eye @ eye - radius * radius
+        disc = b * b - 4 * a * cc
+        t = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), 3.0 * ext)     # z-depth of the hit (d.z = 1)
+        depth[c] = t.astype(np.float32)
+        depth[c][rng.random((H, W)) < 0.03] = 0.0
+    return K, pos, quat, depth, radius

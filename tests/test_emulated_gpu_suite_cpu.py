@@ -313,6 +313,7 @@ def test_bench_side_entries_execute(run, monkeypatch):
     assert set(r["franka_64"]) == {"forward", "backward"} and r["franka_64"]["forward"]["bytes_per_row"] == 4 * (4 * 7 + 13 * 20)
     e = bench.edt_bench("cpu", 6500.0, n=24, iters=1)
     assert e["grid"] == [24, 24, 24] and e["launches"] == 3 and e["sites"] > 0
+    assert "error" not in e["depth_to_esdf"] and e["depth_to_esdf"]["observed_frac"] > 0.02, e["depth_to_esdf"]
 
 
 @pytest.mark.parametrize("robot,B,H", [("franka", 3, 7), ("g1_29", 2, 4)])

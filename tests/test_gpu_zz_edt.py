@@ -12,6 +12,7 @@ import ref_kernels
 from edt_cases import MEDIUM, SMALL, occupancy
 from curobo_b200.backends import pba as pba_cu
 from curobo_b200.esdf import DenseESDFBuilder, ParallelBandingEDT, seed_sites_from_occupancy
+from curobo_b200.world import depth_scene
 from oracle import edt_oracle as E
 
 pytestmark = pytest.mark.gpu
@@ -143,54 +144,6 @@ def test_dense_esdf_builder_vs_oracle(shape, skip):
     pba_cu2.launch_esdf_signed_distance(b.site_index.view(-1), None, None, out.view(-1), *shape, voxel, 1.0)
     assert np.array_equal(np.abs(gf) >= 0, np.ones(shape, bool)) and (out.cpu().numpy().astype(np.float32) >= 0).all()
     assert b2.dist_field.shape == tuple(shape)
-
-
-def _look_at_quat(eye, target):
-    """camera -> world quaternion (wxyz) of a pinhole camera at `eye` whose +z axis points at `target` (x right, y down)."""
-    zc = np.asarray(target, np.float64) - np.asarray(eye, np.float64)
-    zc /= np.linalg.norm(zc)
-    up = np.array([0.0, 0.0, 1.0]) if abs(zc[2]) < 0.9 else np.array([1.0, 0.0, 0.0])
-    xc = np.cross(zc, up)
-    xc /= np.linalg.norm(xc)
-    yc = np.cross(zc, xc)
-    R = np.stack([xc, yc, zc], 1)                                             # columns = camera axes in the world
-    w = np.sqrt(max(0.0, 1.0 + R[0, 0] + R[1, 1] + R[2, 2])) / 2.0
-    if w > 1e-6:
-        q = np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
-    else:
-        q = np.array([0.0, 1.0, 0.0, 0.0])
-    return (q / np.linalg.norm(q)).astype(np.float32), R
-
-
-def depth_scene(shape, voxel, n_cam=2, hw=(48, 64), seed=0):
-    """Cameras around a ball of radius 0.3 * extent at the grid centre: rendered depth (ray / sphere, plus a far wall), with some
-    invalid (zero) pixels."""
-    rng = np.random.default_rng(seed)
-    ext = voxel * min(shape)
-    radius = 0.3 * ext
-    H, W = hw
-    K = np.zeros((n_cam, 3, 3), np.float32)
-    pos = np.zeros((n_cam, 3), np.float32)
-    quat = np.zeros((n_cam, 4), np.float32)
-    depth = np.zeros((n_cam, H, W), np.float32)
-    for c in range(n_cam):
-        ang = 2 * np.pi * c / n_cam + 0.3
-        eye = np.array([np.cos(ang), np.sin(ang), 0.35]) * 1.6 * ext
-        q, R = _look_at_quat(eye, (0.0, 0.0, 0.0))
-        f = 0.9 * W
-        K[c] = [[f, 0, W / 2 - 0.5], [0, f, H / 2 - 0.5], [0, 0, 1]]
-        pos[c], quat[c] = eye, q
-        v, u = np.meshgrid(np.arange(H) + 0.5, np.arange(W) + 0.5, indexing="ij")
-        d = np.stack([(u - K[c, 0, 2]) / f, (v - K[c, 1, 2]) / f, np.ones_like(u)], -1)       # camera-frame ray, z = 1
-        dw = d @ R.T
-        a = (dw * dw).sum(-1)
-        b = 2 * (dw @ eye)
-        cc = eye @ eye - radius * radius
-        disc = b * b - 4 * a * cc
-        t = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), 3.0 * ext)     # z-depth of the hit (d.z = 1)
-        depth[c] = t.astype(np.float32)
-        depth[c][rng.random((H, W)) < 0.03] = 0.0
-    return K, pos, quat, depth, radius
 
 
 @pytest.mark.parametrize("shape", [(40, 36, 44), (24, 24, 24)])
