@@ -705,8 +705,8 @@ __global__ void __launch_bounds__(kBigWarps * 32, 1) rollout_fused_big_kernel(co
 // loop and the list-based J^T are strided over TEAM x 32 lanes; the serial parts (c-space, the level-scheduled FK compose) run
 // on the team's first warp, the tool-pose cost on its last; teams meet at named barriers (one id per team), every team has its
 // own gradient-list segment (a full segment is folded into the warp's partial sums and restarted: no overflow case;
-// deterministic) and partial J^T accumulators.  Measured (profiles/r02_a_round2.md section 9): G1-29, 1,024 rows 104 -> 58 us; the host picks the variant by rows
-// vs resident warp slots.
+// deterministic) and partial J^T accumulators.  Measured (profiles/r02_a_round2.md section 9): G1-29, 1,024 rows 104 -> 58 us,
+// G1-43, 8,192 rows 388 -> 259 us; the host picks the variant from rows vs resident warp slots (see the launcher).
 // ------------------------------------------------------------------------------------------------
 template <int TEAM>
 struct TeamScratch {  // per team, behind the row state
