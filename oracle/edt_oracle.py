@@ -168,7 +168,10 @@ def unsigned_distance_fp16(result, voxel_size, empty_value=1e4):
 def seed_sites_from_sdf(sdf, voxel_size, truncation):
     """Seed rule of the ESDF builder for a dense SDF at the ESDF's resolution (builder_esdf.py:255-261, 286-300): a voxel is a
     site when it is observed (sdf <= 1e9) and |sdf| <= 0.9 voxel (surface) or sdf < -(truncation - 1.1 voxel) (truncation
-    boundary); sites hold their own packed coordinates, everything else -1."""
+    boundary); sites hold their own packed coordinates, everything else -1.  = the SCATTER seeding kernel at equal resolution
+    (builder_esdf.py:192-266; the gather variant dilates the band and is not restated).  Pinned, together with
+    signed_distance_fp16 below, on the reference's kernel sources executed under the Warp stand-in
+    (tests/golden/make_esdf_golden.py -> esdf_reference_golden.npz)."""
     sdf = np.asarray(sdf, np.float32)
     vs, tr = np.float32(voxel_size), np.float32(truncation)
     seed = ~(sdf > np.float32(1e9)) & ((np.abs(sdf) <= vs * np.float32(0.9)) | (sdf < -(tr - vs * np.float32(1.1))))
@@ -216,7 +219,8 @@ def tsdf_integrate_depth(block_data, voxel_size, origin, intrinsics, cam_positio
     = v (2 w^2 - 1) + 2 w (qv x v) + 2 qv (qv . v); pixel index by truncation towards zero; sdf = depth - z_cam kept when
     >= -truncation, clamped to +truncation; weight = max((fx voxel / z)(fy voxel / z), 1) (compute_tsdf_weight == 1,
     wp_integrate_common.py:57-105); fp32 accumulation over the cameras, one fp16 rounding per call.  All arithmetic in float32 in
-    the kernel's order.  Parity at the Warp boundary unpinned (warp-lang is not installed); pinned on analytic scenes in tests."""
+    the kernel's order.  Pinned on the reference's own kernel source executed under the Warp stand-in
+    (tests/golden/make_tsdf_golden.py -> tsdf_reference_golden.npz) and on a closed-form scene (tests/test_edt_cpu.py)."""
     f = np.float32
     bd = np.array(block_data, dtype=np.float16, copy=True)
     nx, ny, nz = bd.shape[:3]

@@ -205,3 +205,47 @@ def test_tsdf_depth_integration_oracle_on_a_plane():
     depth0[0, :, : W // 2] = 0.0                                                                      # invalid pixels: no update
     bd3 = E.tsdf_integrate_depth(np.zeros(shape + (2,), np.float16), voxel, (0, 0, 0), K, pos, quat, depth0, 0.1, 5.0, trunc)
     assert (bd3[: shape[0] // 2 - 1, :, :, 1] == 0).all() and (bd3[shape[0] // 2 + 1:, :, wz <= trunc, 1] > 0).all()
+
+
+def test_tsdf_oracle_vs_the_references_own_kernel_source():
+    """tests/golden/tsdf_reference_golden.npz holds the output of the REFERENCE's `integrate_voxels_kernel` source
+    (builder_camera_integrate.py:399-489 + the coordinate functions of builder_coord.py) executed under the pure-Python Warp stand-in
+    with every block of a small grid visible (tests/golden/make_tsdf_golden.py).  The oracle's dense restatement must reproduce it:
+    same voxels updated, (sum sdf * w, sum w) equal to fp16 rounding -- the stand-in evaluates scalar float32 expressions in the
+    kernel's order, numpy evaluates the same expressions vectorised, so at most a voxel on a pixel edge may differ."""
+    import os
+    from oracle import edt_oracle as E
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tsdf_reference_golden.npz"))
+    for case in ("a", "b"):
+        shape = tuple(int(v) for v in g[f"{case}/shape"])
+        want_frames = g[f"{case}/block_data"]
+        bd = np.zeros(shape + (2,), np.float16)
+        for want in want_frames:
+            bd = E.tsdf_integrate_depth(bd, float(g[f"{case}/voxel"]), g[f"{case}/origin"], g[f"{case}/K"], g[f"{case}/pos"],
+                                        g[f"{case}/quat"], g[f"{case}/depth"], float(g[f"{case}/depth_min"]),
+                                        float(g[f"{case}/depth_max"]), float(g[f"{case}/trunc"]))
+            seen_w, seen_g = want[..., 1] > 0, bd[..., 1] > 0
+            differ = (seen_w != seen_g) | ~np.isclose(bd.astype(np.float32), want.astype(np.float32), rtol=2e-3, atol=2e-3).all(-1)
+            assert differ.sum() <= max(1, int(0.003 * differ.size)), f"case {case}: {int(differ.sum())} of {differ.size} voxels differ"
+            assert seen_w.sum() > 100
+
+
+def test_esdf_seeding_and_sign_oracle_vs_the_references_own_kernel_sources():
+    """tests/golden/esdf_reference_golden.npz: the reference's scatter seeding kernel and compute_esdf_from_min_tsdf_kernel
+    (builder_esdf.py:192-266, :412-499, with sample_combined_sdf / sample_static_sdf) executed under the Warp stand-in on a small
+    all-blocks-allocated TSDF (tests/golden/make_esdf_golden.py).  The oracle's dense restatement (what the CUDA kernels are held to)
+    must give the same seed sites and the same signed fp16 distances."""
+    import os
+    from oracle import edt_oracle as E
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "esdf_reference_golden.npz"))
+    voxel, trunc, minw, skip = float(g["voxel"]), float(g["trunc"]), float(g["min_weight"]), float(g["skip"])
+    static = g["static"].astype(np.float32)
+    combined = E.tsdf_combined_sdf(g["block_data"], static, minw)
+    seeds = E.seed_sites_from_sdf(combined, voxel, trunc)
+    assert np.array_equal(seeds, g["seeds"]), f"{int((seeds != g['seeds']).sum())} seed voxels differ"
+    assert (seeds >= 0).sum() > 100
+    static_in = np.where(np.isfinite(static), static, np.float32(1e10)).astype(np.float32)
+    want = g["dist_field"].astype(np.float32)
+    got = E.signed_distance_fp16(g["propagated"], static_in, combined, voxel, skip).astype(np.float32)
+    assert np.array_equal(np.sign(got), np.sign(want)), f"{int((np.sign(got) != np.sign(want)).sum())} signs differ"
+    assert np.abs(got - want).max() <= 1e-3 and (want < 0).sum() > 10 and (want > 0).sum() > 100

@@ -287,6 +287,7 @@ def test_pending_edt(run):
 def test_depth_to_esdf_chain(run):
     run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (24, 24, 24))
     run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (40, 36, 44))
+    run("test_gpu_zz_edt", "test_esdf_producer_kernels_vs_reference_source_goldens")
 
 
 @pytest.mark.skipif(os.environ.get("CB200_EMULATE_LONG") != "1", reason="~5 min of emulated launches: set CB200_EMULATE_LONG=1 (passes)")

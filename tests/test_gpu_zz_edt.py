@@ -190,3 +190,43 @@ def test_depth_to_esdf_chain_vs_oracle(shape):
     r = np.linalg.norm(ctr, axis=-1)
     shell = (comb < 1e9) & (np.abs(comb) < 0.5 * voxel)
     assert shell.sum() > 20 and np.abs(r[shell] - radius).mean() < 1.5 * voxel
+
+
+def test_esdf_producer_kernels_vs_reference_source_goldens():
+    """The CUDA kernels of the ESDF producer held directly against outputs of the REFERENCE's own kernel sources (executed under the
+    Warp stand-in; tests/golden/make_tsdf_golden.py, make_esdf_golden.py): depth integration (integrate_voxels_kernel), combined SDF +
+    scatter seeding (seed_esdf_sites_from_block_sparse_kernel) and the signed distance step (compute_esdf_from_min_tsdf_kernel)."""
+    import os
+    from curobo_b200.esdf import DenseTSDF
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    t = np.load(os.path.join(gold, "tsdf_reference_golden.npz"))
+    for case in ("a", "b"):
+        shape = tuple(int(v) for v in t[f"{case}/shape"])
+        tsdf = DenseTSDF(shape, float(t[f"{case}/voxel"]), float(t[f"{case}/trunc"]), DEV, origin=t[f"{case}/origin"],
+                         depth_min=float(t[f"{case}/depth_min"]), depth_max=float(t[f"{case}/depth_max"]))
+        for want in t[f"{case}/block_data"]:
+            tsdf.integrate(T(t[f"{case}/depth"]), T(t[f"{case}/K"]), T(t[f"{case}/pos"]), T(t[f"{case}/quat"]))
+            torch.cuda.synchronize()
+            got = tsdf.block_data.cpu().numpy()
+            differ = ((want[..., 1] > 0) != (got[..., 1] > 0)) | \
+                ~np.isclose(got.astype(np.float32), want.astype(np.float32), rtol=2e-3, atol=2e-3).all(-1)
+            assert differ.sum() <= max(2, int(0.01 * differ.size)), f"case {case}: {int(differ.sum())} of {differ.size} voxels differ"
+    g = np.load(os.path.join(gold, "esdf_reference_golden.npz"))
+    shape = tuple(int(v) for v in g["shape"])
+    voxel, trunc, minw, skip = float(g["voxel"]), float(g["trunc"]), float(g["min_weight"]), float(g["skip"])
+    static = g["static"].astype(np.float32)
+    static_in = np.where(np.isfinite(static), static, np.float32(1e10)).astype(np.float32)
+    n = int(np.prod(shape))
+    comb = torch.empty(shape, dtype=torch.float32, device=DEV)
+    pba_cu.launch_tsdf_combined_sdf(T(g["block_data"]).view(-1), T(static_in).view(-1), comb.view(-1), minw)
+    sites = torch.empty(n, dtype=torch.int32, device=DEV)
+    pba_cu.launch_esdf_seed_sites(comb.view(-1), sites, *shape, voxel, trunc)
+    torch.cuda.synchronize()
+    assert np.array_equal(sites.cpu().numpy().reshape(shape), g["seeds"])
+    out = torch.empty(n, dtype=torch.float16, device=DEV)
+    pba_cu.launch_esdf_signed_distance(T(g["propagated"].astype(np.int32)).view(-1), T(static_in).view(-1), comb.view(-1), out, *shape,
+                                       voxel, skip)
+    torch.cuda.synchronize()
+    got, want = out.cpu().numpy().reshape(shape).astype(np.float32), g["dist_field"].astype(np.float32)
+    assert np.array_equal(np.sign(got), np.sign(want)) and np.abs(got - want).max() <= 2e-3
