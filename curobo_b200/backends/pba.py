@@ -115,3 +115,20 @@ def launch_tsdf_combined_sdf(block_data: torch.Tensor, static_sdf, combined_sdf:
     err = _lib.load().cb200_tsdf_combined_sdf(block_data.data_ptr(), None if static_sdf is None else static_sdf.data_ptr(),
                                               combined_sdf.data_ptr(), n, float(min_weight), stream_ptr(dev))
     _lib.check(err, "tsdf_combined_sdf")
+
+
+def launch_esdf_seed_sites_gather(combined_sdf: torch.Tensor, site_index: torch.Tensor, nx: int, ny: int, nz: int, voxel_size: float,
+                                  truncation_distance: float, origin) -> None:
+    """The reference's default seeding (seed_esdf_sites_gather_kernel, builder_esdf.py:308-404) for a dense SDF on the ESDF's own
+    grid: the seed rule probed at the voxel centre and half a voxel away along each axis.  Every voxel is written (-1 = no site)."""
+    import ctypes as C
+    dev = site_index.device
+    check_tensors(dev, torch.float32, combined_sdf=combined_sdf)
+    check_tensors(dev, torch.int32, site_index=site_index)
+    n = int(nx) * int(ny) * int(nz)
+    if combined_sdf.numel() != n or site_index.numel() != n:
+        raise ValueError(f"combined_sdf / site_index must hold nx*ny*nz = {n} elements")
+    org = (C.c_float * 3)(*[float(v) for v in origin])
+    err = _lib.load().cb200_esdf_seed_sites_gather(combined_sdf.data_ptr(), site_index.data_ptr(), int(nx), int(ny), int(nz),
+                                                   float(voxel_size), float(truncation_distance), org, stream_ptr(dev))
+    _lib.check(err, "esdf_seed_sites_gather")

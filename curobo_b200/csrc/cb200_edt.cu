@@ -135,6 +135,44 @@ __global__ void __launch_bounds__(256) esdf_seed_sites_kernel(const float *__res
   }
 }
 
+// The reference's DEFAULT seeding (mapper_cfg.py:103 seeding_method = "gather"; seed_esdf_sites_gather_kernel, builder_esdf.py:
+// 308-404 with _check_seed_at_world_pos :267-306): an ESDF voxel is a site when the seed rule holds in the TSDF voxel that
+// contains its centre OR one of the six points half an ESDF voxel away along the axes.  For the dense case (ESDF grid == TSDF grid)
+// the probes land on the voxel itself and on neighbours -- which ones is decided by float32 rounding of
+// int((world - origin) / voxel + n / 2), so the arithmetic is spelled with IEEE intrinsics in the reference's order (no FMA
+// contraction, no approximate division): the dilated band is then the reference's band, voxel for voxel.
+__device__ __forceinline__ bool seed_rule_at_world(const float *__restrict__ sdf, int nx, int ny, int nz, float wx, float wy, float wz,
+                                                   float ox, float oy, float oz, float voxel_size, float surface, float trunc_edge) {
+  const int gx = (int)__fadd_rn(__fdiv_rn(__fsub_rn(wx, ox), voxel_size), __fmul_rn((float)nx, 0.5f));
+  const int gy = (int)__fadd_rn(__fdiv_rn(__fsub_rn(wy, oy), voxel_size), __fmul_rn((float)ny, 0.5f));
+  const int gz = (int)__fadd_rn(__fdiv_rn(__fsub_rn(wz, oz), voxel_size), __fmul_rn((float)nz, 0.5f));
+  if (gx < 0 || gx >= nx || gy < 0 || gy >= ny || gz < 0 || gz >= nz) return false;
+  const float d = sdf[((long long)gx * ny + gy) * nz + gz];
+  if (d > 1e9f) return false;
+  return fabsf(d) <= surface || d < trunc_edge;
+}
+__global__ void __launch_bounds__(256) esdf_seed_sites_gather_kernel(const float *__restrict__ sdf, int *__restrict__ sites, int nx,
+                                                                      int ny, int nz, long long total, float voxel_size,
+                                                                      float truncation, float ox, float oy, float oz) {
+  const float surface = __fmul_rn(voxel_size, 0.9f), trunc_edge = -__fsub_rn(truncation, __fmul_rn(voxel_size, 1.1f));
+  const float half = __fmul_rn(voxel_size, 0.5f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((long long)nz * ny));
+    // centre = origin + (idx + 0.5 - n * 0.5) * voxel, in that order (builder_esdf.py:333-335)
+    const float cx = __fadd_rn(ox, __fmul_rn(__fsub_rn(__fadd_rn((float)x, 0.5f), __fmul_rn((float)nx, 0.5f)), voxel_size));
+    const float cy = __fadd_rn(oy, __fmul_rn(__fsub_rn(__fadd_rn((float)y, 0.5f), __fmul_rn((float)ny, 0.5f)), voxel_size));
+    const float cz = __fadd_rn(oz, __fmul_rn(__fsub_rn(__fadd_rn((float)z, 0.5f), __fmul_rn((float)nz, 0.5f)), voxel_size));
+    const bool hit = seed_rule_at_world(sdf, nx, ny, nz, cx, cy, cz, ox, oy, oz, voxel_size, surface, trunc_edge) ||
+                     seed_rule_at_world(sdf, nx, ny, nz, __fadd_rn(cx, half), cy, cz, ox, oy, oz, voxel_size, surface, trunc_edge) ||
+                     seed_rule_at_world(sdf, nx, ny, nz, __fsub_rn(cx, half), cy, cz, ox, oy, oz, voxel_size, surface, trunc_edge) ||
+                     seed_rule_at_world(sdf, nx, ny, nz, cx, __fadd_rn(cy, half), cz, ox, oy, oz, voxel_size, surface, trunc_edge) ||
+                     seed_rule_at_world(sdf, nx, ny, nz, cx, __fsub_rn(cy, half), cz, ox, oy, oz, voxel_size, surface, trunc_edge) ||
+                     seed_rule_at_world(sdf, nx, ny, nz, cx, cy, __fadd_rn(cz, half), ox, oy, oz, voxel_size, surface, trunc_edge) ||
+                     seed_rule_at_world(sdf, nx, ny, nz, cx, cy, __fsub_rn(cz, half), ox, oy, oz, voxel_size, surface, trunc_edge);
+    sites[i] = hit ? pack(x, y, z) : -1;
+  }
+}
+
 __device__ __forceinline__ float round_half_away(float v) { return v < 0.0f ? -floorf(0.5f - v) : floorf(v + 0.5f); }
 
 __global__ void __launch_bounds__(256) esdf_signed_distance_kernel(const int *__restrict__ sites, const float *__restrict__ static_sdf,
@@ -301,6 +339,17 @@ int cb200_esdf_seed_sites(const float *combined_sdf, int32_t *site_index, int nx
   const long long total = (long long)nx * ny * nz;
   CB200_LAUNCH(esdf_seed_sites_kernel, grid_for((total + 255) / 256), 256, 0, (cudaStream_t)stream, combined_sdf, site_index, ny, nz,
                total, voxel_size, truncation_distance);
+  return status(cudaGetLastError());
+}
+
+int cb200_esdf_seed_sites_gather(const float *combined_sdf, int32_t *site_index, int nx, int ny, int nz, float voxel_size,
+                                 float truncation_distance, const float *origin, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(site_index);
+  if (combined_sdf == nullptr || site_index == nullptr || origin == nullptr || !dims_ok(nx, ny, nz) || !(voxel_size > 0.0f))
+    return status(cudaErrorInvalidValue);
+  const long long total = (long long)nx * ny * nz;
+  CB200_LAUNCH(esdf_seed_sites_gather_kernel, grid_for((total + 255) / 256), 256, 0, (cudaStream_t)stream, combined_sdf, site_index, nx,
+               ny, nz, total, voxel_size, truncation_distance, origin[0], origin[1], origin[2]);
   return status(cudaGetLastError());
 }
 

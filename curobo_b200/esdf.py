@@ -80,7 +80,14 @@ class DenseESDFBuilder:
     (z fastest, fp16)."""
 
     def __init__(self, grid_shape: Tuple[int, int, int], voxel_size: float, truncation_distance: float, device,
-                 adjacent_skip_steps: float = 1.0):
+                 adjacent_skip_steps: float = 1.0, seeding_method: str = "scatter", origin=(0.0, 0.0, 0.0)):
+        """seeding_method: "scatter" (a voxel is a site when the seed rule holds for its own SDF: the reference's scatter kernel at
+        equal resolution) or "gather" (the reference's default, mapper_cfg.py:103: the rule probed at the centre and half a voxel
+        away along each axis -- a band up to one voxel thicker; needs the grid `origin` because the probes' voxels are decided by
+        float rounding of world coordinates)."""
+        if seeding_method not in ("scatter", "gather"):
+            raise ValueError("seeding_method must be 'scatter' or 'gather'")
+        self.seeding_method, self.origin = seeding_method, tuple(float(v) for v in origin)
         self.edt = ParallelBandingEDT(grid_shape, voxel_size, torch.device(device))
         self.truncation_distance = float(truncation_distance)
         self.adjacent_skip_steps = float(adjacent_skip_steps)
@@ -89,8 +96,12 @@ class DenseESDFBuilder:
 
     def compute(self, combined_sdf: torch.Tensor, static_sdf: torch.Tensor = None) -> torch.Tensor:
         nx, ny, nz = self.edt.grid_shape
-        pba_cu.launch_esdf_seed_sites(combined_sdf.view(-1), self.site_index.view(-1), nx, ny, nz, self.edt.voxel_size,
-                                      self.truncation_distance)
+        if self.seeding_method == "gather":
+            pba_cu.launch_esdf_seed_sites_gather(combined_sdf.view(-1), self.site_index.view(-1), nx, ny, nz, self.edt.voxel_size,
+                                                 self.truncation_distance, self.origin)
+        else:
+            pba_cu.launch_esdf_seed_sites(combined_sdf.view(-1), self.site_index.view(-1), nx, ny, nz, self.edt.voxel_size,
+                                          self.truncation_distance)
         self.edt.propagate(self.site_index)
         pba_cu.launch_esdf_signed_distance(self.site_index.view(-1), None if static_sdf is None else static_sdf.view(-1),
                                            combined_sdf.view(-1), self.dist_field.view(-1), nx, ny, nz, self.edt.voxel_size,

@@ -105,6 +105,7 @@ _SIGS = {
     "cb200_edt_unsigned_distance": ([c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),
     "cb200_esdf_seed_sites": ([c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),
     "cb200_esdf_signed_distance": ([c_p, c_p, c_p, c_p, _I, _I, _I, C.c_float, C.c_float, c_p], _I),
+    "cb200_esdf_seed_sites_gather": ([c_p, c_p, _I, _I, _I, C.c_float, C.c_float, C.POINTER(C.c_float), c_p], _I),
     "cb200_tsdf_integrate_depth": ([c_p, _I, _I, _I, C.c_float, C.POINTER(C.c_float), _I, c_p, c_p, c_p, c_p, _I, _I, C.c_float,
                                     C.c_float, C.c_float, c_p], _I),
     "cb200_tsdf_combined_sdf": ([c_p, c_p, c_p, C.c_longlong, C.c_float, c_p], _I),

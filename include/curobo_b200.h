@@ -489,6 +489,13 @@ int cb200_edt_unsigned_distance(const int32_t *site_index, uint16_t *distance_fp
  *                                  unobserved; fp16(1e4) where the grid has no site.  Either SDF pointer may be NULL. */
 int cb200_esdf_seed_sites(const float *combined_sdf, int32_t *site_index, int nx, int ny, int nz, float voxel_size,
                           float truncation_distance, cb200_stream_t stream);
+/*   cb200_esdf_seed_sites_gather <- seed_esdf_sites_gather_kernel  builder_esdf.py:308-404 (the reference's default,
+ *                                  mapper_cfg.py:103): the same rule probed at the voxel centre and half a voxel away along each
+ *                                  axis (7 probes, _check_seed_at_world_pos :267-306), world -> voxel by int((w - origin) / voxel +
+ *                                  n / 2) in IEEE float32 in the reference's order, so the dilated band is the reference's band.
+ *                                  `origin` = grid centre (3 floats, host).  ESDF grid == TSDF grid (the dense case). */
+int cb200_esdf_seed_sites_gather(const float *combined_sdf, int32_t *site_index, int nx, int ny, int nz, float voxel_size,
+                                 float truncation_distance, const float *origin, cb200_stream_t stream);
 int cb200_esdf_signed_distance(const int32_t *site_index, const float *static_sdf, const float *combined_sdf,
                                uint16_t *distance_fp16, int nx, int ny, int nz, float voxel_size, float adjacent_skip_steps,
                                cb200_stream_t stream);

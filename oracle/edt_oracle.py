@@ -178,6 +178,36 @@ def seed_sites_from_sdf(sdf, voxel_size, truncation):
     return seed_grid(seed)
 
 
+def seed_sites_gather_from_sdf(sdf, voxel_size, truncation, origin):
+    """The reference's DEFAULT seeding (mapper_cfg.py:103; seed_esdf_sites_gather_kernel builder_esdf.py:308-404 with
+    _check_seed_at_world_pos :267-306) for a dense SDF on the ESDF's own grid: 7 probes per voxel (centre, +- half a voxel along
+    each axis), world -> voxel by int((w - origin) / voxel + n / 2) in float32 in the kernel's order.  Pinned on the reference's
+    kernel source under the Warp stand-in (tests/golden/make_esdf_golden.py)."""
+    f = np.float32
+    sdf = np.asarray(sdf, f)
+    nx, ny, nz = sdf.shape
+    vs, tr = f(voxel_size), f(truncation)
+    o = np.asarray(origin, f)
+    surface, edge = vs * f(0.9), -(tr - vs * f(1.1))
+    half = vs * f(0.5)
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cx = o[0] + (ix.astype(f) + f(0.5) - f(nx) * f(0.5)) * vs
+    cy = o[1] + (iy.astype(f) + f(0.5) - f(ny) * f(0.5)) * vs
+    cz = o[2] + (iz.astype(f) + f(0.5) - f(nz) * f(0.5)) * vs
+
+    def rule(wx, wy, wz):
+        gx = np.trunc((wx - o[0]) / vs + f(nx) * f(0.5)).astype(np.int64)
+        gy = np.trunc((wy - o[1]) / vs + f(ny) * f(0.5)).astype(np.int64)
+        gz = np.trunc((wz - o[2]) / vs + f(nz) * f(0.5)).astype(np.int64)
+        ok = (gx >= 0) & (gx < nx) & (gy >= 0) & (gy < ny) & (gz >= 0) & (gz < nz)
+        d = sdf[np.clip(gx, 0, nx - 1), np.clip(gy, 0, ny - 1), np.clip(gz, 0, nz - 1)]
+        return ok & ~(d > f(1e9)) & ((np.abs(d) <= surface) | (d < edge))
+    hit = rule(cx, cy, cz)
+    for dx, dy, dz in ((half, 0, 0), (-half, 0, 0), (0, half, 0), (0, -half, 0), (0, 0, half), (0, 0, -half)):
+        hit |= rule((cx + f(dx)).astype(f), (cy + f(dy)).astype(f), (cz + f(dz)).astype(f))
+    return seed_grid(hit)
+
+
 def _round_half_away(v):
     return np.where(v < 0, -np.floor(np.float32(0.5) - v), np.floor(v + np.float32(0.5)))
 

@@ -79,15 +79,20 @@ def main():
     vs = wp.from_numpy(np.asarray([voxel], np.float32), dtype=wp.float32)
     wp.launch(ek["seed_esdf_sites_from_block_sparse_kernel"], dim=(nb, bs ** 3), inputs=[tsdf, site, org, vs, float(min_weight)])
     seeds = np.asarray(site.numpy(), np.int32).reshape(shape).copy()
+    site_g = wp.from_numpy(np.full(n, -1, np.int32), dtype=wp.int32)            # the default method: gather (pre-cleared to -1)
+    wp.launch(ek["seed_esdf_sites_gather_kernel"], dim=n, inputs=[tsdf, site_g, org, vs, float(min_weight)])
+    seeds_gather = np.asarray(site_g.numpy(), np.int32).reshape(shape).copy()
     prop = E.pba3d(seeds, "zyx")                                                 # exact nearest sites (oracle)
     site2 = wp.from_numpy(prop.reshape(-1).astype(np.int32), dtype=wp.int32)
     dist = wp.from_numpy(np.zeros(n, np.float16), dtype=wp.float16)
     wp.launch(ek["compute_esdf_from_min_tsdf_kernel"], dim=n, inputs=[site2, vs, dist, tsdf, float(min_weight), org, float(skip)])
     out = dict(shape=np.asarray(shape), voxel=np.float32(voxel), origin=np.asarray(origin, np.float32), trunc=np.float32(trunc),
-               min_weight=np.float32(min_weight), skip=np.float32(skip), block_data=bd, static=static, seeds=seeds, propagated=prop,
+               min_weight=np.float32(min_weight), skip=np.float32(skip), block_data=bd, static=static, seeds=seeds,
+               seeds_gather=seeds_gather, propagated=prop,
                dist_field=np.asarray(dist.numpy(), np.float16).reshape(shape))
     np.savez_compressed(os.path.join(HERE, "esdf_reference_golden.npz"), **out)
     d = out["dist_field"].astype(np.float32)
+    print("gather seeds", int((seeds_gather >= 0).sum()))
     print("seeds", int((seeds >= 0).sum()), "of", n, "| negative distances", int((d < 0).sum()), "| unsigned-empty", int((d > 1e3).sum()))
 
 

@@ -66,6 +66,9 @@ inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
 inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
 
 struct float4 {
   float x, y, z, w;

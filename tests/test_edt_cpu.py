@@ -244,6 +244,9 @@ def test_esdf_seeding_and_sign_oracle_vs_the_references_own_kernel_sources():
     seeds = E.seed_sites_from_sdf(combined, voxel, trunc)
     assert np.array_equal(seeds, g["seeds"]), f"{int((seeds != g['seeds']).sum())} seed voxels differ"
     assert (seeds >= 0).sum() > 100
+    gather = E.seed_sites_gather_from_sdf(combined, voxel, trunc, g["origin"])          # the reference's default method
+    assert np.array_equal(gather, g["seeds_gather"]), f"{int((gather != g['seeds_gather']).sum())} gather seed voxels differ"
+    assert (gather >= 0).sum() > (seeds >= 0).sum() and ((seeds >= 0) <= (gather >= 0)).all(), "gather dilates the scatter band"
     static_in = np.where(np.isfinite(static), static, np.float32(1e10)).astype(np.float32)
     want = g["dist_field"].astype(np.float32)
     got = E.signed_distance_fp16(g["propagated"], static_in, combined, voxel, skip).astype(np.float32)

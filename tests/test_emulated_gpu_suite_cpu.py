@@ -284,6 +284,34 @@ def test_pending_edt(run):
         run("test_gpu_zz_edt", "test_dense_esdf_builder_vs_oracle", shape, skip)
 
 
+def test_gather_seeding_kernel_vs_reference_source_golden(run, monkeypatch):
+    """cb200_esdf_seed_sites_gather (the reference's DEFAULT seeding, seed_esdf_sites_gather_kernel) against the output of the
+    reference's kernel source under the Warp stand-in, and DenseESDFBuilder(seeding_method="gather") end to end against the oracle.
+    Emulated only: the kernel was written after the round's GPU budget was spent (its arithmetic is spelled with IEEE intrinsics,
+    so the B200 must give the same voxels); the builder's default stays "scatter", which is GPU-validated."""
+    from oracle import edt_oracle as E
+    from curobo_b200.backends import pba as pba_cu
+    from curobo_b200.esdf import DenseESDFBuilder
+    g = np.load(os.path.join(ROOT, "tests", "golden", "esdf_reference_golden.npz"))
+    shape = tuple(int(v) for v in g["shape"])
+    voxel, trunc, minw = float(g["voxel"]), float(g["trunc"]), float(g["min_weight"])
+    static = g["static"].astype(np.float32)
+    static_in = np.where(np.isfinite(static), static, np.float32(1e10)).astype(np.float32)
+    comb = E.tsdf_combined_sdf(g["block_data"], static_in, minw)
+    sites = torch.empty(int(np.prod(shape)), dtype=torch.int32)
+    pba_cu.launch_esdf_seed_sites_gather(torch.as_tensor(comb).view(-1), sites, *shape, voxel, trunc, g["origin"])
+    assert np.array_equal(sites.numpy().reshape(shape), g["seeds_gather"])
+    b = DenseESDFBuilder(shape, voxel, trunc, "cpu", seeding_method="gather", origin=g["origin"])
+    field = b.compute(torch.as_tensor(comb), torch.as_tensor(static_in)).numpy().astype(np.float32)
+    res = b.site_index.numpy()
+    seeds = E.seed_sites_gather_from_sdf(comb, voxel, trunc, g["origin"])
+    assert np.array_equal(E.squared_distance(res), E.squared_distance(E.pba3d(seeds, "zyx")))
+    want = E.signed_distance_fp16(res, static_in, comb, voxel, 1.0).astype(np.float32)
+    assert np.array_equal(np.sign(field), np.sign(want)) and np.abs(field - want).max() <= 2e-3
+    with pytest.raises(ValueError):
+        DenseESDFBuilder(shape, voxel, trunc, "cpu", seeding_method="nearest")
+
+
 def test_depth_to_esdf_chain(run):
     run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (24, 24, 24))
     run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (40, 36, 44))
