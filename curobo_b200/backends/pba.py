@@ -132,3 +132,23 @@ def launch_esdf_seed_sites_gather(combined_sdf: torch.Tensor, site_index: torch.
     err = _lib.load().cb200_esdf_seed_sites_gather(combined_sdf.data_ptr(), site_index.data_ptr(), int(nx), int(ny), int(nz),
                                                    float(voxel_size), float(truncation_distance), org, stream_ptr(dev))
     _lib.check(err, "esdf_seed_sites_gather")
+
+
+def launch_tsdf_stamp_cuboids(static_sdf: torch.Tensor, nx: int, ny: int, nz: int, voxel_size: float, origin,
+                              truncation_distance: float, cuboids, env_idx: int = 0) -> None:
+    """Dense form of stamp_sdf_kernel (builder_stamp.py:263-315) for cuboids: static_sdf (float32 [nx*ny*nz], > 1e9 = nothing
+    stamped) is updated in place from `cuboids` (curobo_b200.scene.CuboidData) of environment `env_idx`."""
+    import ctypes as C
+    from ..scene import c_cuboid_set
+    dev = static_sdf.device
+    check_tensors(dev, torch.float32, static_sdf=static_sdf)
+    n = int(nx) * int(ny) * int(nz)
+    if static_sdf.numel() != n:
+        raise ValueError(f"static_sdf must hold nx*ny*nz = {n} elements")
+    cs = c_cuboid_set(cuboids, dev)
+    if cs is None:
+        raise ValueError("cuboids must be given")
+    org = (C.c_float * 3)(*[float(v) for v in origin])
+    err = _lib.load().cb200_tsdf_stamp_cuboids(static_sdf.data_ptr(), int(nx), int(ny), int(nz), float(voxel_size), org,
+                                               float(truncation_distance), C.byref(cs), int(env_idx), stream_ptr(dev))
+    _lib.check(err, "tsdf_stamp_cuboids")

@@ -19,6 +19,7 @@
 #include "../../include/curobo_b200.h"
 #include "cb200_launch.h"
 #include "cb200_edt.cuh"
+#include "cb200_math.cuh"
 
 namespace {
 using namespace cb200::edt;
@@ -270,6 +271,37 @@ __global__ void __launch_bounds__(256) tsdf_combined_sdf_kernel(const __half *__
   }
 }
 
+// World cuboids -> the STATIC channel of the dense TSDF: the per-voxel step of the reference's obstacle stamping
+// (stamp_sdf_kernel, perception/mapper/kernel/builder/builder_stamp.py:263-315, with the cuboid overloads is_obs_enabled /
+// load_obstacle_transform / compute_local_sdf of geom/data/data_cuboid.py:461-545) without the block enumeration / allocation in
+// front of it: min over the enabled cuboids of the box SDF at the voxel centre; where |min| <= truncation the voxel takes
+// clamp(min(existing, min), +-truncation), rounded through fp16 as the reference's static_block_data stores it.  static_sdf is
+// float32 (> 1e9 = nothing stamped), the format DenseESDFBuilder takes.
+__global__ void __launch_bounds__(256) tsdf_stamp_cuboids_kernel(float *__restrict__ static_sdf, int nx, int ny, int nz, long long total,
+                                                                  float voxel_size, float ox, float oy, float oz, float truncation,
+                                                                  cb200::CuboidSet cs, int env) {
+  using namespace cb200;
+  int ncub = cs.count[env];
+  if (ncub > cs.max_n) ncub = cs.max_n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((long long)nz * ny));
+    const V3 c = mk3(((float)x + 0.5f - (float)nx * 0.5f) * voxel_size + ox, ((float)y + 0.5f - (float)ny * 0.5f) * voxel_size + oy,
+                     ((float)z + 0.5f - (float)nz * 0.5f) * voxel_size + oz);
+    float min_sdf = 1e10f;
+    for (int k = 0; k < ncub; ++k) {
+      const int kk = env * cs.max_n + k;
+      if (cs.enable[kk] != 1) continue;
+      const ObsFrame f = load_obs_frame(cs.inv_pose + 8 * kk);
+      const SdfGrad sg = cuboid_sdf_grad(to_obstacle(f, c), cs.dims[4 * kk], cs.dims[4 * kk + 1], cs.dims[4 * kk + 2]);
+      min_sdf = fminf(min_sdf, sg.sdf);
+    }
+    if (fabsf(min_sdf) <= truncation) {
+      const float final_sdf = fminf(static_sdf[i], min_sdf);
+      static_sdf[i] = __half2float(__float2half_rn(fminf(fmaxf(final_sdf, -truncation), truncation)));
+    }
+  }
+}
+
 template <class K>
 bool allow_smem(K kern, int smem) {
   if (smem <= 48 * 1024) return true;
@@ -379,6 +411,20 @@ int cb200_tsdf_integrate_depth(uint16_t *block_data_fp16, int nx, int ny, int nz
   CB200_LAUNCH(tsdf_integrate_depth_kernel, grid_for((total + 255) / 256), 256, 0, (cudaStream_t)stream,
                reinterpret_cast<__half *>(block_data_fp16), nx, ny, nz, total, voxel_size, origin[0], origin[1], origin[2], cams,
                depth_min, depth_max, truncation_distance);
+  return status(cudaGetLastError());
+}
+
+int cb200_tsdf_stamp_cuboids(float *static_sdf, int nx, int ny, int nz, float voxel_size, const float *origin,
+                             float truncation_distance, const cb200_cuboid_set *cuboids, int env_idx, cb200_stream_t stream) {
+  CB200_DEVICE_GUARD(static_sdf);
+  if (static_sdf == nullptr || origin == nullptr || cuboids == nullptr || cuboids->inv_pose == nullptr || cuboids->dims == nullptr ||
+      cuboids->enable == nullptr || cuboids->count == nullptr || cuboids->max_n < 1 || env_idx < 0 || env_idx >= cuboids->num_envs ||
+      !dims_ok(nx, ny, nz) || !(voxel_size > 0.0f) || !(truncation_distance > 0.0f))
+    return status(cudaErrorInvalidValue);
+  const long long total = (long long)nx * ny * nz;
+  const cb200::CuboidSet cs{cuboids->dims, cuboids->inv_pose, cuboids->enable, cuboids->count, cuboids->max_n, cuboids->num_envs};
+  CB200_LAUNCH(tsdf_stamp_cuboids_kernel, grid_for((total + 255) / 256), 256, 0, (cudaStream_t)stream, static_sdf, nx, ny, nz, total,
+               voxel_size, origin[0], origin[1], origin[2], truncation_distance, cs, env_idx);
   return status(cudaGetLastError());
 }
 

@@ -124,9 +124,22 @@ class DenseTSDF:
         self.device = torch.device(device)
         self.block_data = torch.zeros(self.grid_shape + (2,), dtype=torch.float16, device=self.device)
         self._combined = torch.empty(self.grid_shape, dtype=torch.float32, device=self.device)
+        self.static_sdf = None                       # allocated by the first stamp_cuboids
 
     def reset(self) -> None:
         self.block_data.zero_()
+        if self.static_sdf is not None:
+            self.static_sdf.fill_(1e10)
+
+    def stamp_cuboids(self, cuboids, env_idx: int = 0) -> torch.Tensor:
+        """World cuboids (curobo_b200.scene.CuboidData) into the static channel (stamp_sdf_kernel, builder_stamp.py:263-315):
+        returns the float32 [nx, ny, nz] static SDF (> 1e9 = nothing stamped), kept and min-combined across calls."""
+        if self.static_sdf is None:
+            self.static_sdf = torch.full(self.grid_shape, 1e10, dtype=torch.float32, device=self.device)
+        nx, ny, nz = self.grid_shape
+        pba_cu.launch_tsdf_stamp_cuboids(self.static_sdf.view(-1), nx, ny, nz, self.voxel_size, self.origin, self.truncation_distance,
+                                         cuboids, env_idx)
+        return self.static_sdf
 
     def integrate(self, depth_images: torch.Tensor, intrinsics: torch.Tensor, cam_positions: torch.Tensor,
                   cam_quaternions: torch.Tensor) -> None:

@@ -518,6 +518,13 @@ int cb200_tsdf_integrate_depth(uint16_t *block_data_fp16, int nx, int ny, int nz
                                cb200_stream_t stream);
 int cb200_tsdf_combined_sdf(const uint16_t *block_data_fp16, const float *static_sdf, float *combined_sdf, long long num_voxels,
                             float min_weight, cb200_stream_t stream);
+/*   cb200_tsdf_stamp_cuboids   <- stamp_sdf_kernel  kernel/builder/builder_stamp.py:263-315 with the cuboid overloads of
+ *                                  geom/data/data_cuboid.py:461-545 (the per-voxel step of BlockSparseTSDFIntegrator's obstacle
+ *                                  stamping; block enumeration / allocation out of scope): static_sdf (f32, > 1e9 = nothing
+ *                                  stamped, updated in place) takes clamp(min(existing, min over enabled cuboids of the box SDF
+ *                                  at the voxel centre), +-truncation), rounded through fp16, where |min| <= truncation. */
+int cb200_tsdf_stamp_cuboids(float *static_sdf, int nx, int ny, int nz, float voxel_size, const float *origin /* host [3] */,
+                             float truncation_distance, const cb200_cuboid_set *cuboids, int env_idx, cb200_stream_t stream);
 
 /* Host helper: pack robot constants (HOST pointers) into `out` (host buffer of
  * cb200_robot_blob_bytes(...) bytes) that the caller then copies to the device once.

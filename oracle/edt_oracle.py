@@ -306,3 +306,42 @@ def tsdf_combined_sdf(block_data, static_sdf, min_weight):
     if static_sdf is not None:
         d = np.minimum(d, np.asarray(static_sdf, f))
     return d
+
+
+def tsdf_stamp_cuboids(static_sdf, voxel_size, origin, truncation, dims, inv_pose, enable, count, max_n, env=0):
+    """Dense restatement of stamp_sdf_kernel (perception/mapper/kernel/builder/builder_stamp.py:263-315) with the cuboid overloads
+    of geom/data/data_cuboid.py:461-545 -- TEST INFRASTRUCTURE.  static_sdf float32 [nx, ny, nz] (> 1e9 = nothing stamped), returned
+    updated (a copy): where |min over enabled cuboids of the box SDF at the voxel centre| <= truncation the voxel takes
+    clamp(min(existing, min), +-truncation) rounded through fp16.  dims [n_env * max_n, 4], inv_pose [n_env * max_n, 8]
+    (x y z qw qx qy qz), enable, count: the CuboidWorld arrays.  Pinned on the reference's kernel source under the Warp stand-in
+    (tests/golden/make_esdf_golden.py)."""
+    f = np.float32
+    out = np.array(static_sdf, dtype=f, copy=True)
+    nx, ny, nz = out.shape
+    vs, tr = f(voxel_size), f(truncation)
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    c = np.stack([(ix.astype(f) + f(0.5) - f(nx) * f(0.5)) * vs + f(origin[0]), (iy.astype(f) + f(0.5) - f(ny) * f(0.5)) * vs + f(origin[1]),
+                  (iz.astype(f) + f(0.5) - f(nz) * f(0.5)) * vs + f(origin[2])], -1).astype(f)
+    dims = np.asarray(dims, f).reshape(-1, 4)
+    inv = np.asarray(inv_pose, f).reshape(-1, 8)
+    en = np.asarray(enable).reshape(-1)
+    mn = np.full((nx, ny, nz), f(1e10), f)
+    for k in range(int(np.asarray(count).reshape(-1)[env])):
+        kk = env * int(max_n) + k
+        if en[kk] != 1:
+            continue
+        p, q = inv[kk, :3], inv[kk, 3:7]                                       # wp.transform_point(t, x) = quat_rotate(q, x) + p
+        qv, qw = np.array([q[1], q[2], q[3]], f), q[0]
+        cc = f(2.0) * qw * qw - f(1.0)
+        cr = np.cross(np.broadcast_to(qv, c.shape), c).astype(f)
+        d = (c @ qv).astype(f)[..., None]
+        lp = (c * cc + cr * qw * f(2.0) + qv * d * f(2.0)).astype(f) + p
+        h = dims[kk, :3] * f(0.5)
+        qd = np.abs(lp) - h
+        od = np.sqrt((np.maximum(qd, f(0.0)) ** 2).sum(-1)).astype(f)
+        sdf = (od + np.minimum(qd.max(-1), f(0.0))).astype(f)
+        mn = np.minimum(mn, sdf)
+    upd = np.abs(mn) <= tr
+    fin = np.clip(np.minimum(out, mn), -tr, tr).astype(np.float16).astype(f)
+    out[upd] = fin[upd]
+    return out

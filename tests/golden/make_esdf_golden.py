@@ -24,7 +24,11 @@ import warp as wp  # noqa: E402  (the stand-in)
 
 from oracle import edt_oracle as E  # noqa: E402
 
+from curobo_b200.world import CuboidWorld  # noqa: E402
+
 coord = R.ref("curobo._src.perception.mapper.kernel.builder.builder_coord")
+stamp = R.ref("curobo._src.perception.mapper.kernel.builder.builder_stamp")
+data_cuboid = R.ref("curobo._src.geom.data.data_cuboid")
 esdf = R.ref("curobo._src.perception.mapper.kernel.builder.builder_esdf")
 types_ = R.ref("curobo._src.perception.mapper.kernel.warp_types")
 
@@ -36,6 +40,57 @@ def to_blocks(dense, bs, grid_blocks):
         blk = dense[g[0] * bs:(g[0] + 1) * bs, g[1] * bs:(g[1] + 1) * bs, g[2] * bs:(g[2] + 1) * bs]
         out.append(np.moveaxis(blk, (0, 1, 2), (2, 1, 0)).reshape((bs ** 3,) + dense.shape[3:]))
     return np.stack(out)
+
+
+def run_stamp(ck, shape, bs, voxel, origin, trunc):
+    """stamp_sdf_kernel (builder_stamp.py:263-315) over every block of the grid, two environments of cuboids (one disabled slot),
+    two stamping calls into the same static channel (min-combine)."""
+    nx, ny, nz = shape
+    grid_blocks = [(gx, gy, gz) for gx in range(nx // bs) for gy in range(ny // bs) for gz in range(nz // bs)]
+    keys = []
+    for g in grid_blocks:
+        k = ck["block_grid_to_key_coords"](wp.int32(g[0]), wp.int32(g[1]), wp.int32(g[2]))
+        keys.append((int(k[0]), int(k[1]), int(k[2])))
+
+    def unpack_block_key(key):
+        k = keys[int(key)]
+        return wp.vec3i(k[0], k[1], k[2])
+    sk = stamp.make_stamp_kernels(bs, grid_shape=(nz, ny, nx), origin_xyz=origin, voxel_size=voxel, truncation_distance=trunc,
+                                  pack_key_only=None, unpack_block_key=unpack_block_key,
+                                  block_local_to_world=ck["block_local_to_world"], hash_lookup=None,
+                                  hash_table_insert_with_pool_idx=None, free_list_pop=None)
+    o = np.asarray(origin)
+    from curobo_b200.world import _inv_pose_from_pose
+    cw = CuboidWorld.create([{"dims": [0.3, 0.2, 0.25], "pose": list(o + [0.05, 0.0, 0.1]) + [0.9, 0.1, 0.3, -0.2]},
+                             {"dims": [0.8, 0.6, 0.1], "pose": list(o + [0.0, 0.0, -0.3]) + [1, 0, 0, 0]},
+                             {"dims": [0.2, 0.2, 0.2], "pose": list(o + [-0.2, 0.1, 0.2]) + [1, 0, 0, 0]}], max_n=3, num_envs=2)
+    cw.dims[1], cw.enable[1], cw.count[1] = 0.0, 0, 1                          # environment 1: a single rotated slab
+    cw.inv_pose[1] = 0.0
+    cw.inv_pose[1, :, 3] = 1.0
+    cw.dims[1, 0, :3] = [0.12, 0.5, 0.5]
+    cw.inv_pose[1, 0] = _inv_pose_from_pose(list(o + [0.2, 0.0, 0.0]) + [0.7071068, 0, 0, 0.7071068])
+    cw.enable[1, 0] = 1
+    cw.enable[0, 2] = 0                                                          # a disabled slot
+    st = data_cuboid.CuboidDataWarp()
+    st.dims = wp.from_numpy(cw.dims.reshape(-1, 4), dtype=wp.float32, ndim=2)
+    st.inv_pose = wp.from_numpy(cw.inv_pose.reshape(-1, 8), dtype=wp.float32, ndim=2)
+    st.enable = wp.from_numpy(cw.enable.reshape(-1), dtype=wp.uint8)
+    st.n_per_env = wp.from_numpy(cw.count.reshape(-1), dtype=wp.int32)
+    st.max_n, st.num_envs = wp.int32(cw.max_n), wp.int32(cw.num_envs)
+    nb = len(keys)
+    static = wp.from_numpy(np.full((nb, bs ** 3), np.inf, np.float16), dtype=wp.float16, ndim=2)
+    sums = wp.from_numpy(np.zeros(nb, np.int32), dtype=wp.int32)
+    outs = []
+    for env in (0, 1):                                                           # env 1 is stamped on top of env 0
+        wp.launch(sk["stamp_sdf_kernel"], dim=(nb, bs ** 3),
+                  inputs=[wp.from_numpy(np.arange(nb, dtype=np.int64), dtype=wp.int64),
+                          wp.from_numpy(np.arange(nb, dtype=np.int32), dtype=wp.int32), nb, st, env, static, sums])
+        blocks = np.asarray(static.numpy(), np.float16).reshape(nb, bs, bs, bs)   # [lz, ly, lx]
+        dense = np.zeros(shape, np.float16)
+        for b, g in enumerate(grid_blocks):
+            dense[g[0] * bs:(g[0] + 1) * bs, g[1] * bs:(g[1] + 1) * bs, g[2] * bs:(g[2] + 1) * bs] = blocks[b].transpose(2, 1, 0)
+        outs.append(dense.copy())
+    return np.stack(outs), cw
 
 
 def main():
@@ -50,6 +105,7 @@ def main():
     static[:, :, 2] = np.float16(0.02)                                           # ... and its surface layer
     static[2:5, 1:4, 9:12] = np.float16(-0.2)                                    # an interior (beyond the truncation edge) box
     ck = coord.make_coord_kernels(bs, grid_shape=(nz, ny, nx), origin_xyz=origin, voxel_size=voxel)
+    stamped, cw = run_stamp(ck, shape, bs, voxel, origin, trunc)
     table = {}
 
     def hash_lookup(hash_table, kx, ky, kz, capacity):
@@ -88,11 +144,12 @@ def main():
     wp.launch(ek["compute_esdf_from_min_tsdf_kernel"], dim=n, inputs=[site2, vs, dist, tsdf, float(min_weight), org, float(skip)])
     out = dict(shape=np.asarray(shape), voxel=np.float32(voxel), origin=np.asarray(origin, np.float32), trunc=np.float32(trunc),
                min_weight=np.float32(min_weight), skip=np.float32(skip), block_data=bd, static=static, seeds=seeds,
-               seeds_gather=seeds_gather, propagated=prop,
+               seeds_gather=seeds_gather, propagated=prop, stamped=stamped, cub_dims=cw.dims, cub_inv_pose=cw.inv_pose,
+               cub_enable=cw.enable, cub_count=cw.count, cub_max_n=np.int32(cw.max_n),
                dist_field=np.asarray(dist.numpy(), np.float16).reshape(shape))
     np.savez_compressed(os.path.join(HERE, "esdf_reference_golden.npz"), **out)
     d = out["dist_field"].astype(np.float32)
-    print("gather seeds", int((seeds_gather >= 0).sum()))
+    print("gather seeds", int((seeds_gather >= 0).sum()), "| stamped voxels", [int(np.isfinite(x).sum()) for x in stamped])
     print("seeds", int((seeds >= 0).sum()), "of", n, "| negative distances", int((d < 0).sum()), "| unsigned-empty", int((d > 1e3).sum()))
 
 

@@ -312,6 +312,40 @@ def test_gather_seeding_kernel_vs_reference_source_golden(run, monkeypatch):
         DenseESDFBuilder(shape, voxel, trunc, "cpu", seeding_method="nearest")
 
 
+def test_stamp_cuboids_kernel_vs_reference_source_golden(run, monkeypatch):
+    """cb200_tsdf_stamp_cuboids (dense form of the reference's stamp_sdf_kernel) against the output of the reference's kernel source
+    under the Warp stand-in, through DenseTSDF.stamp_cuboids; then world cuboids + depth images -> ESDF end to end against the
+    oracle.  Emulated only (written after the round's GPU budget was spent); nothing on the GPU path depends on it."""
+    from oracle import edt_oracle as E
+    from curobo_b200.esdf import DenseESDFBuilder, DenseTSDF
+    from curobo_b200.scene import CuboidData
+    from curobo_b200.world import CuboidWorld
+    g = np.load(os.path.join(ROOT, "tests", "golden", "esdf_reference_golden.npz"))
+    t = np.load(os.path.join(ROOT, "tests", "golden", "tsdf_reference_golden.npz"))
+    shape = tuple(int(v) for v in g["shape"])
+    voxel, trunc, minw = float(g["voxel"]), float(g["trunc"]), float(g["min_weight"])
+    cw = CuboidWorld(g["cub_dims"], g["cub_inv_pose"], g["cub_enable"], g["cub_count"])
+    cd = CuboidData.from_world(cw, "cpu")
+    tsdf = DenseTSDF(shape, voxel, trunc, "cpu", origin=g["origin"], depth_min=float(t["a/depth_min"]),
+                     depth_max=float(t["a/depth_max"]), minimum_tsdf_weight=minw)
+    for env in (0, 1):
+        st = tsdf.stamp_cuboids(cd, env).numpy()
+        want = g["stamped"][env].astype(np.float32)
+        m = np.isfinite(want)
+        assert np.array_equal(st < 1e9, m) and np.abs(st[m] - want[m]).max() <= 2e-4
+    for _ in range(2):
+        tsdf.integrate(torch.as_tensor(t["a/depth"]), torch.as_tensor(t["a/K"]), torch.as_tensor(t["a/pos"]), torch.as_tensor(t["a/quat"]))
+    assert np.array_equal(tsdf.block_data.numpy(), t["a/block_data"][-1])
+    comb = tsdf.combined_sdf(tsdf.static_sdf).numpy()
+    assert np.array_equal(comb, E.tsdf_combined_sdf(t["a/block_data"][-1], st, minw))
+    b = DenseESDFBuilder(shape, voxel, trunc, "cpu", seeding_method="gather", origin=g["origin"])
+    field = b.compute(torch.as_tensor(comb), tsdf.static_sdf).numpy().astype(np.float32)
+    want = E.signed_distance_fp16(b.site_index.numpy(), st, comb, voxel, 1.0).astype(np.float32)
+    assert np.array_equal(np.sign(field), np.sign(want)) and np.abs(field - want).max() <= 2e-3 and (want < 0).sum() > 0
+    tsdf.reset()
+    assert float(tsdf.block_data.abs().sum()) == 0.0 and bool((tsdf.static_sdf > 1e9).all())
+
+
 def test_depth_to_esdf_chain(run):
     run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (24, 24, 24))
     run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (40, 36, 44))
