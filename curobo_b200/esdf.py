@@ -94,6 +94,20 @@ class DenseESDFBuilder:
         self.site_index = torch.empty(self.edt.grid_shape, dtype=torch.int32, device=self.edt.device)
         self.dist_field = torch.empty(self.edt.grid_shape, dtype=torch.float16, device=self.edt.device)
 
+    def to_voxel_data(self, origin=None, max_esdf_distance: float = 100.0):
+        """The ESDF as the obstacle type the collision operators and the fused rollout read: a one-layer curobo_b200.scene.VoxelData
+        whose `features` ALIAS `dist_field` (a later `compute` updates the world in place; call RolloutEngine.refresh_world() --
+        or VoxelData.build_mip() -- afterwards so that the lower-bound level follows).  `origin` = grid centre (default: the
+        builder's), identity rotation."""
+        from .scene import VoxelData
+        nx, ny, nz = self.edt.grid_shape
+        o = self.origin if origin is None else tuple(float(v) for v in origin)
+        dev = self.edt.device
+        params = torch.tensor([[[nx, ny, nz, self.edt.voxel_size]]], dtype=torch.float32, device=dev)
+        inv_pose = torch.tensor([[[-o[0], -o[1], -o[2], 1.0, 0.0, 0.0, 0.0]]], dtype=torch.float32, device=dev)
+        return VoxelData(params, inv_pose, torch.ones((1, 1), dtype=torch.uint8, device=dev),
+                         torch.ones(1, dtype=torch.int32, device=dev), self.dist_field.view(1, 1, -1), 1, 1, float(max_esdf_distance))
+
     def compute(self, combined_sdf: torch.Tensor, static_sdf: torch.Tensor = None) -> torch.Tensor:
         nx, ny, nz = self.edt.grid_shape
         if self.seeding_method == "gather":

@@ -346,6 +346,50 @@ def test_stamp_cuboids_kernel_vs_reference_source_golden(run, monkeypatch):
     assert float(tsdf.block_data.abs().sum()) == 0.0 and bool((tsdf.static_sdf > 1e9).all())
 
 
+def test_built_esdf_feeds_the_collision_operator(run, monkeypatch):
+    """World cuboid -> static TSDF channel -> ESDF (DenseESDFBuilder) -> VoxelData (to_voxel_data) -> SphereObstacleCollision: the
+    cost of spheres against the BUILT grid agrees with their cost against the analytic cuboid to within a voxel, i.e. the producer's
+    output is consumable by the hot path as it stands.  Emulated only (see test_stamp_cuboids_kernel_vs_reference_source_golden)."""
+    import importlib
+    from curobo_b200.esdf import DenseESDFBuilder, DenseTSDF
+    from curobo_b200.scene import CollisionBuffer, CuboidData, SceneData, SphereObstacleCollision
+    from curobo_b200.world import CuboidWorld
+    shape, voxel = (40, 40, 40), 0.02
+    trunc = 4 * voxel
+    cw = CuboidWorld.create([{"dims": [0.3, 0.24, 0.2], "pose": [0.02, -0.01, 0.03, 1, 0, 0, 0]}])
+    cd = CuboidData.from_world(cw, "cpu")
+    tsdf = DenseTSDF(shape, voxel, trunc, "cpu")
+    static = tsdf.stamp_cuboids(cd, 0)
+    b = DenseESDFBuilder(shape, voxel, trunc, "cpu", seeding_method="gather")
+    b.compute(static, static)
+    vd = b.to_voxel_data(max_esdf_distance=10.0)
+    assert vd.features.data_ptr() == b.dist_field.data_ptr()
+    rng = np.random.default_rng(0)
+    n = 400
+    sph = np.zeros((1, 1, n, 4), np.float32)
+    sph[0, 0, :, :3] = rng.uniform(-0.3, 0.3, size=(n, 3))
+    sph[0, 0, :, 3] = 0.03
+    w, eta = torch.tensor([1.0]), torch.tensor([0.05])
+    costs = []
+    for scene in (SceneData(cd, None), SceneData(None, vd)):
+        buf = CollisionBuffer.from_shape((1, 1, n, 4), "cpu")
+        costs.append(SphereObstacleCollision.apply(torch.as_tensor(sph), buf, scene, w, eta, None, torch.zeros(1, dtype=torch.int32),
+                                                   False).numpy().reshape(-1).copy())
+    exact, built = costs
+    assert (exact > 0).sum() > 50 and (exact == 0).sum() > 50
+    # (deep inside the box the static channel is unobserved -- |sdf| > truncation is not stamped -- and the ESDF measures from the
+    #  truncation-boundary seeds, as in the reference; compare where the analytic distance is within the stamped band or outside)
+    q = np.abs(sph[0, 0, :, :3] - np.array([0.02, -0.01, 0.03], np.float32)) - np.array([0.15, 0.12, 0.1], np.float32)
+    sdf = np.linalg.norm(np.maximum(q, 0), axis=1) + np.minimum(q.max(1), 0)
+    m = sdf > -(trunc - 2 * voxel)
+    assert m.sum() > 300 and (exact[m] > 0).sum() > 30
+    # the activation is 1-Lipschitz in the distance; the built field measures to the centres of a (dilated) band of seed voxels,
+    # so it is within ~2 voxels of the analytic distance -- the reference's own approximation, not an error of the plumbing
+    assert np.abs(exact[m] - built[m]).max() <= 2.5 * voxel, float(np.abs(exact[m] - built[m]).max())
+    assert np.abs(exact[m] - built[m]).mean() <= 0.3 * voxel
+    assert (built[~m] > 0).all(), "deep inside the box the built grid still reports a collision"
+
+
 def test_depth_to_esdf_chain(run):
     run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (24, 24, 24))
     run("test_gpu_zz_edt", "test_depth_to_esdf_chain_vs_oracle", (40, 36, 44))
